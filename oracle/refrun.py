@@ -1,0 +1,145 @@
+#!/usr/bin/env python3
+"""
+TEST INFRASTRUCTURE ONLY -- runs the UNMODIFIED reference hot path as the parity oracle.
+
+Only usable where `/root/reference` exists (the build container).  It imports the reference's
+`superpang.lib.Assembler` (with the Cython helpers compiled by `oracle/build_ref.py` and the
+`graph_tool` / `mappy` / `speedict` import shims under `oracle/shims/`) and drives:
+
+  * `Assembler.__init__`                       (reference `lib/Assembler.py:80-256`)   -- DBG build
+  * the NBP-collection head of `Assembler.run` (reference `lib/Assembler.py:269-363`)  -- restated
+    below 1:1 as a driver that calls the reference's OWN classmethods `is_NBP_init`,
+    `reconstruct_sequence` (`:995-1059`) and `get_ori2cov_onevertex` (`:1212-1248`) through the
+    reference's own `multimap` (`:59-74`); the goodOris rule is `:944-946`.
+
+It is used (a) to validate the independent restatement in `oracle/dbg_oracle.py` and (b) to
+generate the golden vectors committed under `tests/golden/` (`oracle/make_golden.py`).
+Nothing in the product path, the `-m gpu` tests, `smoke()` or `bench.py` imports this file.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REFERENCE = os.environ.get("SPB_REFERENCE", "/root/reference")
+
+
+def available():
+    return os.path.isdir(os.path.join(REFERENCE, "src", "superpang", "lib"))
+
+
+def import_reference():
+    """Import the reference Assembler class; returns (Assembler, lib modules dict)."""
+    if not available():
+        raise RuntimeError("reference tree not present")
+    sys.path.insert(0, os.path.join(HERE, "shims"))
+    sys.path.insert(0, os.path.join(REFERENCE, "src"))
+    import build_ref  # noqa  (oracle/ is on sys.path when run as a script or via tests)
+    build_ref.build(REFERENCE)
+    import superpang.lib as lib
+    p = os.path.join(HERE, "_ref", "superpang_lib")
+    if p not in lib.__path__:
+        lib.__path__.append(p)
+    from superpang.lib.Assembler import Assembler
+    return Assembler
+
+
+def run_reference(fasta, ksize=301, threads=1, debug=True, with_origins=True, quiet=True):
+    """Run the reference DBG build + NBP collection on `fasta`; return the canonical result dict."""
+    Assembler = import_reference()
+    import graph_tool as gt
+    import io
+    import contextlib
+
+    sink = io.StringIO() if quiet else sys.stdout
+    with contextlib.redirect_stdout(sink):
+        A = Assembler(fasta, ksize, threads, None, debug, 1)
+        # ---- head of Assembler.run, reference lib/Assembler.py:269-363 (driver restatement) ----
+        A.DBG.vp.comp = gt.topology.label_components(A.DBG, directed=False)[0]            # :271
+        comps, sizes = np.unique(A.DBG.vp.comp.get_array(), return_counts=True)              # :272
+        comps = [c for c, s in sorted(zip(comps, sizes), key=lambda x: x[1], reverse=True)]  # :273
+        nbps_out = []
+        for ic, c in enumerate(comps):
+            vs = np.where(A.DBG.vp.comp.get_array() == np.int16(c))[0]                       # :285
+            vset = set(vs.tolist())
+            seqPathsThisComp = {n: sp for n, sp in A.seqPaths.items() if int(sp[0][0]) in vset}  # :296
+            NBPs = []
+            badEdges = set()
+            flags = A.multimap(A.is_NBP_init, threads, vs, A.DBG, A.seqLimits, A.vertex2coords,
+                               A.ref2name, A.seqDict, A.ksize)                               # :302
+            inits = {int(v) for v, f in zip(vs, flags) if f}
+            isCycle = False
+            if not inits:                                                                    # :307
+                if min(len(set(A.DBG.get_out_neighbors(v))) for v in vs) == 2:               # :309
+                    for v in vs:
+                        neighbors = A.DBG.get_out_neighbors(v)
+                        if len(set(neighbors)) == 2:                                         # :312
+                            inits.add(int(v))
+                            inits.add(int(neighbors[0]))
+                            isCycle = True
+                            badEdges.add(A.DBG.edge(v, neighbors[0]))
+                            badEdges.add(A.DBG.edge(neighbors[0], v))
+                            break
+            if badEdges:                                                                     # :322
+                for e in A.DBG.edges():
+                    A.DBG.ep.efilt[e] = e not in badEdges
+                A.DBG.set_edge_filter(A.DBG.ep.efilt)
+            for ini in inits:                                                                # :327
+                for n in set(sorted(A.DBG.get_out_neighbors(ini))):
+                    NBP = [ini, int(n)]
+                    last = ini
+                    while True:
+                        if NBP[-1] in inits:
+                            break
+                        s = [x for x in A.DBG.get_out_neighbors(NBP[-1]) if x != last and x != NBP[-1]][0]
+                        last = NBP[-1]
+                        NBP.append(int(s))
+                    NBPs.append(tuple(NBP))
+            if isCycle:                                                                      # :341
+                assert len(NBPs) == 2
+                NBPs = [NBP + (NBP[0],) for NBP in NBPs]
+            for NBP in NBPs:
+                assert len(NBP) > 1                                                          # :347
+            NBPs = [NBP for NBP in NBPs if NBP[0] != NBP[1] and NBP[-1] != NBP[-2]]          # :354
+            seqs = A.multimap(A.reconstruct_sequence, threads, NBPs, A.vertex2coords, A.ref2name,
+                              A.seqDict, A.ksize)                                            # :357
+            if with_origins:
+                from collections import defaultdict
+                o2c = A.multimap(A.get_ori2cov_onevertex, threads, NBPs, seqPathsThisComp,
+                                 defaultdict(list), A.seqLimitsPerSeq, debug, chunksize=10)  # :922
+            else:
+                o2c = [None] * len(NBPs)
+            if badEdges:
+                A.DBG.clear_filters()
+            for NBP, seq, ori2cov in zip(NBPs, seqs, o2c):
+                if ori2cov is None:
+                    oris = ()
+                else:                                                                        # :944-946
+                    good = {o for o, cov in ori2cov.items() if cov >= 1}
+                    good.add(list(sorted(ori2cov, key=lambda o: ori2cov[o], reverse=True))[0])
+                    oris = tuple(sorted({o.split('_Nsplit_')[0] for o in good}))
+                nbps_out.append((tuple(int(x) for x in NBP), seq, oris, ic, isCycle))
+
+    edges = A.DBG._edges.astype(np.uint32)
+    res = dict(
+        k=ksize,
+        names=list(A.seqDict),
+        n_inst=int(sum(len(s) - ksize + 1 for s in A.seqDict.values() if len(s) > ksize)),
+        vertex2coords=np.asarray(A.vertex2coords, dtype=np.uint32),
+        edges=edges,
+        seqPaths={n: np.asarray(sp, dtype=np.uint32) for n, sp in A.seqPaths.items()},
+        seqLimits=sorted(int(v) for v in A.seqLimits),
+        ncomp=len(comps),
+        nbps=nbps_out,
+    )
+    return res
+
+
+if __name__ == "__main__":
+    sys.path.insert(0, HERE)
+    import digests
+    r = run_reference(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 301,
+                      threads=int(sys.argv[3]) if len(sys.argv) > 3 else 1)
+    import json
+    print(json.dumps(digests.summarize(r), indent=1))
