@@ -1,0 +1,256 @@
+#!/usr/bin/env python3
+"""
+bench.py -- canonical k-mers/s through DBG build + NBP compaction at k=301 (BASELINE.json metric).
+
+A "step" = one pass of the hot path over one synthetic genome set:
+    spb_load (2-bit pack, both strands) -> spb_build_dbg -> spb_compact
+`value`  : k-mer instances / s with the ASCII input already resident in HBM (CUDA events on the
+           library's stream, max over ranks).
+`e2e`    : same metric through the host-facing API: pinned HOST ASCII in, H2D inside the timed region,
+           and the NBP sequences + origin lists + offsets copied back to pinned host memory.
+`--impl reference` : the oracle port of the reference's CPU path (oracle/dbg_oracle.py) on a bounded
+           sample of the same workload, on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1], configs[2]
+    "c2": dict(n_genomes=10, length=2_000_000, ani=0.97, seed=1, desc="synthetic 10 genomes x 2 Mbp ANI 0.97"),
+    "c3": dict(n_genomes=100, length=5_000_000, ani=0.96, seed=2, desc="synthetic 100 genomes x 5 Mbp ANI 0.96"),
+    "tiny": dict(n_genomes=4, length=200_000, ani=0.97, seed=5, desc="synthetic 4 genomes x 200 kbp ANI 0.97"),
+}
+K = 301
+
+
+def algorithmic_bytes(n_inst, n_v, nbp_bases, k=K):
+    """N_inst*(16W+24) + N_v*(8W+32) + B_nbp, W = ceil(2k/64)."""
+    W = (2 * k + 63) // 64
+    return n_inst * (16 * W + 24) + n_v * (8 * W + 32) + nbp_bases
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(self.rows))
+
+
+def make_workload(name, mode):
+    from superpang_b200 import synth
+    from superpang_b200.assembler import concat_sequences
+    w = WORKLOADS[name]
+    names, seqs = synth.genome_set(w["n_genomes"], w["length"], w["ani"], seed=w["seed"], mode=mode)
+    buf, off = concat_sequences(seqs)
+    return w, names, buf, off, synth.n_instances(seqs, K)
+
+
+def cpu_reference_sample(workload, mode, target_inst=600_000):
+    """Oracle port of the reference CPU path on a bounded sample of the same generator output."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dbg_oracle
+    from superpang_b200 import synth
+    w = WORKLOADS[workload]
+    n_g = min(w["n_genomes"], 3)
+    length = max(2 * K, target_inst // n_g)
+    names, seqs = synth.genome_set(n_g, length, w["ani"], seed=w["seed"], mode=mode)
+    sd = {n: s.tobytes().decode() for n, s in zip(names, seqs)}
+    t0 = time.perf_counter()
+    res = dbg_oracle.run_oracle(sd, K)
+    dt = time.perf_counter() - t0
+    return dict(value=res["n_inst"] / dt, unit="k-mers/s", cores=1, kind="port",
+                sample=f"{n_g} genomes x {length} bp of the same generator ({mode}), {res['n_inst']} k-mer instances, "
+                       f"{dt:.1f} s; oracle/dbg_oracle.py (Python port of reference lib/Assembler.py; host has {os.cpu_count()} cores)")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    cb = None
+    for i in range(args.warmup + args.steps):
+        cb = cpu_reference_sample(args.workload, args.mode, target_inst=args.ref_inst)
+        if i >= args.warmup:
+            vals.append(cb["value"])
+    v = float(np.mean(vals))
+    w = WORKLOADS[args.workload]
+    cb["value"] = v
+    n_inst_sample = int(cb["sample"].split(" k-mer instances")[0].split(", ")[-1])
+    print(json.dumps(dict(
+        impl="reference", metric="canonical k-mers/s through DBG build+NBP compaction at k=301", value=v, unit="k-mers/s",
+        n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * n_inst_sample / v, higher_is_better=True,
+        scaling="weak", vs_baseline=None, dtype="u64", data="synthetic",
+        config=dict(workload=f"{w['desc']}, k={K}, mode={args.mode}", k=K, mode=args.mode),
+        cpu_baseline=cb, e2e=dict(value=v, unit="k-mers/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default="snp", choices=["snp", "block"])
+    ap.add_argument("--ref-inst", type=int, default=600_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from superpang_b200 import _capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    w, names, buf, off, n_inst = make_workload(args.workload, args.mode)
+    host = torch.from_numpy(buf).pin_memory()
+    dbuf = host.to(dev, non_blocking=True)
+    stream = torch.cuda.current_stream()
+    eng = _capi.Engine(device=local, stream=stream.cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def step_resident():
+        eng.load(dbuf, off, K)
+        eng.build_dbg()
+        return eng.compact()
+
+    out_bufs = {}
+
+    def step_e2e():
+        eng.load(host, off, K)              # H2D of the ASCII input inside the library call
+        eng.build_dbg()
+        c = eng.compact()
+        n, nb, no = c["n_nbp"], c["nbp_bases"], c["n_origin_pairs"]
+        key = (n, nb, no)
+        if out_bufs.get("key") != key:
+            out_bufs.update(key=key, soff=torch.empty(n + 1, dtype=torch.int64).pin_memory(), seq=torch.empty(max(nb, 1), dtype=torch.uint8).pin_memory(),
+                            ooff=torch.empty(n + 1, dtype=torch.int64).pin_memory(), oidx=torch.empty(max(no, 1), dtype=torch.int32).pin_memory())
+        eng._ck(eng.lib.spb_get_nbp_seqs(eng.h, out_bufs["soff"].data_ptr(), out_bufs["seq"].data_ptr()))
+        eng._ck(eng.lib.spb_get_nbp_origins(eng.h, out_bufs["ooff"].data_ptr(), out_bufs["oidx"].data_ptr()))
+        return c, 8 * (n + 1) * 2 + nb + 4 * no
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        times, stages, last = [], [], None
+        launches0 = eng.lib.spb_launch_count()
+        for _ in range(steps):
+            flush.fill_(1)                   # flush L2 between timed iterations
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            last = fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+            stages.append(eng.stage_stats())
+        if world > 1:
+            dist.barrier()
+        timed.launches = eng.lib.spb_launch_count() - launches0
+        return times, stages, last
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    times, stages, counts = timed(step_resident, args.steps, args.warmup)
+    launches = timed.launches
+    e2e_times, _, e2e_last = timed(step_e2e, args.steps, max(1, args.warmup - 1))
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    ms = float(np.sum(times))
+    ms_e2e = float(np.sum(e2e_times))
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    total_inst = n_inst * world                      # weak scaling: every rank processes its own genome set
+    value = total_inst * args.steps / (ms / 1e3)
+    e2e_value = total_inst * args.steps / (ms_e2e / 1e3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        # dominant kernel = k_extract_insert; its algorithmic bytes: SURVEY §8(d) key produce + consume (16W B / instance)
+        # + unique key stored (8W B / vertex)
+        W = (2 * K + 63) // 64
+        st_keys = sorted(stages[0])
+        st_mean = {k_: float(np.mean([s[k_] for s in stages])) for k_ in st_keys}
+        dom = max(st_mean, key=st_mean.get)
+        dom_bytes = counts["n_inst"] * 16 * W + counts["n_vertices"] * 8 * W
+        ach = dom_bytes / (st_mean["extract_insert_ms"] / 1e3) / 1e9
+        pipe_bytes = algorithmic_bytes(counts["n_inst"], counts["n_vertices"], counts["nbp_bases"])
+        pipe_ach = pipe_bytes / (ms / args.steps / 1e3) / 1e9
+        line = dict(
+            metric="canonical k-mers/s through DBG build+NBP compaction at k=301", value=value, unit="k-mers/s",
+            n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True,
+            scaling="weak", vs_baseline=None, dtype="u64", data="synthetic",
+            config=dict(workload=f"{w['desc']}, k={K}, mode={args.mode}", k=K, mode=args.mode, n_inst_per_gpu=n_inst,
+                        n_vertices=counts["n_vertices"], n_nbp=counts["n_nbp"], nbp_bases=counts["nbp_bases"],
+                        l2="flushed between timed iterations (256 MiB write)"),
+            e2e=dict(value=e2e_value, unit="k-mers/s", ms_per_step=ms_e2e / args.steps, h2d_bytes_per_step=int(buf.nbytes + off.nbytes),
+                     d2h_bytes_per_step=int(e2e_last[1])),
+            gpu_launches=int(launches),
+            roofline=dict(bound="hbm", kernel="k_extract_insert", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None,
+                          peak_source=peak_src, kernel_ms=st_mean["extract_insert_ms"], dominant_stage=dom,
+                          pipeline=dict(achieved=pipe_ach, frac=pipe_ach / peak, bytes=pipe_bytes)),
+            stages_ms=st_mean,
+            clocks=sampler.summary(),
+        )
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference_sample(args.workload, args.mode, target_inst=args.ref_inst)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,126 @@
+/*
+ * superpang_b200 -- C-ABI of the B200-native DBG-build + NBP-compaction path.
+ *
+ * The reference (fpusan/SuperPang v1.3.1) has NO plugin / FFI interface for this path: the only
+ * seam is the Python class constructed at `src/superpang/scripts/SuperPang.py:199`
+ * (`Assembler(fasta, ksize, threads, diskdb, debug, gap_size).run(...)`).  Each entry point below
+ * therefore cites the *reference code it replaces* (paths relative to `src/superpang/`), and
+ * INTEGRATION.md shows the `ctypes` binding a maintainer adds to `lib/Assembler.py`.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch / C++ types; every function returns 0 (SPB_OK) or a
+ *     negative error code and leaves a message retrievable with spb_last_error();
+ *   - all work is enqueued on the CUDA stream handed to spb_create() (e.g. torch's current stream);
+ *   - result getters copy into CALLER-OWNED buffers that may be device memory (torch tensors) or
+ *     host memory (numpy arrays) -- cudaMemcpyDefault resolves the direction through UVA;
+ *   - there is no CPU fallback: without a CUDA device spb_create() fails with SPB_ECUDA.
+ *
+ * Vertex ids are the reference's ids (order of first appearance, `lib/Assembler.py:186-195`),
+ * sequences are indexed by their position in the reference's `seqDict` (`lib/Assembler.py:94-96`).
+ */
+#ifndef SUPERPANG_B200_H
+#define SUPERPANG_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPB_OK            0
+#define SPB_EINVAL       -1   /* even k, k < 3, empty input, non-ACGT base, T >= 2^32-64 ...      */
+#define SPB_ENOMEM       -2
+#define SPB_EDEGENERATE  -3   /* inputs on which the reference's own asserts fire     */
+#define SPB_ECUDA        -4
+#define SPB_ESTATE       -5   /* call order violated (e.g. spb_compact before spb_build_dbg)      */
+
+#define SPB_NONE 0xFFFFFFFFu  /* "no vertex" marker in per-sequence tables                        */
+
+typedef struct spb_ctx spb_ctx;
+
+typedef struct spb_counts {
+  uint64_t n_seq;            /* sequences handed to spb_load (incl. those with len <= k)           */
+  uint64_t n_bases;          /* total bases T                                                      */
+  uint64_t n_inst;           /* k-mer instances: sum over len > k of (len - k + 1)                 */
+  uint64_t n_vertices;       /* distinct canonical k-mers                                          */
+  uint64_t n_edges;          /* unique undirected edges incl. self-loops (np.unique rows)          */
+  uint64_t n_junction;       /* directed junction entries kept after the implicit-edge filter      */
+  uint64_t n_inits;          /* NBP-init vertices                                                  */
+  uint64_t n_pieces;         /* maximal runs of consecutive-id extender vertices                   */
+  uint64_t n_comp;           /* connected components of the DBG                                    */
+  uint64_t n_cycle_comp;     /* components that are pure cycles (broken at one edge)               */
+  uint64_t n_nbp;            /* raw NBPs, both orientations (after the terminal-duplicate filter)  */
+  uint64_t nbp_vertices;     /* sum of NBP lengths in vertices                                     */
+  uint64_t nbp_bases;        /* sum of NBP sequence lengths (k - 1 + L each)                       */
+  uint64_t n_origin_pairs;   /* sum over NBPs of #origin sequences                                 */
+  uint64_t n_seq_intervals;  /* total rows of all seqPaths interval lists                          */
+  uint64_t table_slots;      /* capacity of the k-mer hash table                                   */
+} spb_counts;
+
+/* Create / destroy a context bound to one CUDA device and one stream (NULL = legacy default
+ * stream).  Replaces the reference's fork-pool "runtime" (`lib/Assembler.py:37-74`, `:135-148`). */
+int  spb_create(spb_ctx** out, int device, void* cuda_stream);
+void spb_destroy(spb_ctx* ctx);
+const char* spb_last_error(const spb_ctx* ctx);
+
+/* Hand over the N-split input sequences (what `read_fasta(..., Ns='split')` returned,
+ * `lib/utils.py:5-30`, `lib/Assembler.py:94`): upper-case ASCII A/C/G/T only, concatenated, with
+ * seq_off[n_seq + 1] base offsets.  Sequences with len <= k must be passed too so that `ref`
+ * numbering matches (`lib/Assembler.py:150-153`).  `ascii` may be host (pinned or pageable) or
+ * device memory.  2-bit packs both strands into HBM (replaces `Compressor.compress`,
+ * `lib/Compressor.pyx:32-58`, and `reverse_complement`, `lib/cutils.pyx:16-28`). */
+int spb_load(spb_ctx* ctx, const uint8_t* ascii, const uint64_t* seq_off, uint32_t n_seq, uint32_t k);
+
+/* DBG build: canonical k-mer extraction, exact dedup with reference-identical vertex numbering,
+ * per-instance vertex ids, (k-1)-overlap edges.  Replaces `Assembler.__init__`,
+ * `lib/Assembler.py:150-252` (seq2hashes `:978-992`, the dict loop `:186-217`, np.unique `:247-249`). */
+int spb_build_dbg(spb_ctx* ctx, spb_counts* out);
+
+/* NBP compaction: init detection, chain contraction + list ranking, cycle breaking, NBP vertex
+ * lists, NBP sequences, NBP->origin sets, connected components.  Replaces the head of
+ * `Assembler.run`, `lib/Assembler.py:269-363` (is_NBP_init `:995-1035`, reconstruct_sequence
+ * `:1038-1059`) and the origin lookup `get_ori2cov_onevertex` + goodOris (`:1212-1262`, `:944-946`). */
+int spb_compact(spb_ctx* ctx, spb_counts* out);
+
+/* ---- getters (sizes come from spb_counts; buffers are caller-owned, host or device) ---------- */
+
+/* uint32[n_vertices][2] = (ref, idx) of each vertex's first appearance (`lib/Assembler.py:194`). */
+int spb_get_vertex2coords(spb_ctx* ctx, uint32_t* out);
+/* uint32[n_edges][2], rows (min,max) in lexicographic order (`lib/Assembler.py:247-249`). */
+int spb_get_edges(spb_ctx* ctx, uint32_t* out);
+/* uint32[n_bases]: vertex id of the k-mer instance starting at every base position, SPB_NONE where
+ * no k-mer starts (the per-sequence `sp` arrays of `lib/Assembler.py:183-197`, concatenated). */
+int spb_get_instance_vertices(spb_ctx* ctx, uint32_t* out);
+/* uint32[n_seq][2]: first / last vertex of each sequence (`seqLimitsPerSeq`, `lib/Assembler.py:206-211`);
+ * SPB_NONE for sequences with len <= k. */
+int spb_get_seqlimits(spb_ctx* ctx, uint32_t* out);
+/* seqPaths (`compress_vertices`, `lib/vtools.pyx:18-49`, incl. its leading-zero quirk):
+ * off uint64[n_seq + 1] row offsets, intervals uint32[n_seq_intervals][2]. */
+int spb_get_seq_intervals(spb_ctx* ctx, uint64_t* off, uint32_t* intervals);
+/* int32[n_vertices]: connected-component label, numbered by lowest vertex id
+ * (`label_components`, `lib/Assembler.py:271`). */
+int spb_get_components(spb_ctx* ctx, int32_t* out);
+/* NBP vertex lists: off uint64[n_nbp + 1], verts uint32[nbp_vertices], comp int32[n_nbp],
+ * is_cycle uint8[n_nbp] (`lib/Assembler.py:327-354`).  Any pointer may be NULL to skip it. */
+int spb_get_nbps(spb_ctx* ctx, uint64_t* off, uint32_t* verts, int32_t* comp, uint8_t* is_cycle);
+/* NBP sequences: off uint64[n_nbp + 1], ascii uint8[nbp_bases] (`lib/Assembler.py:357`). */
+int spb_get_nbp_seqs(spb_ctx* ctx, uint64_t* off, uint8_t* ascii);
+/* NBP origins: off uint64[n_nbp + 1], seq_idx uint32[n_origin_pairs] (sorted per NBP; indices into
+ * the loaded sequence list; the caller cuts names at `_Nsplit_`, `lib/Assembler.py:946`). */
+int spb_get_nbp_origins(spb_ctx* ctx, uint64_t* off, uint32_t* seq_idx);
+/* Current counters (n_seq_intervals is filled by the first spb_get_seq_intervals call, which may
+ * be made with NULL buffers just to size them). */
+int spb_get_counts(spb_ctx* ctx, spb_counts* out);
+/* Per-stage device times of the last spb_build_dbg + spb_compact (ms, CUDA events) as a JSON
+ * string written into buf (truncated to cap). */
+int spb_get_stage_stats(spb_ctx* ctx, char* buf, uint64_t cap);
+
+/* Number of this library's own kernel launches since it was loaded (CUB launches not counted). */
+uint64_t spb_launch_count(void);
+/* Library / build identification ("cuda sm_100a" for the product; the CPU kernel-logic emulator
+ * used by the not-gpu test tier answers "emu"). */
+const char* spb_build_kind(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

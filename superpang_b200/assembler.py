@@ -1,0 +1,201 @@
+"""
+Host-side mirror of the reference's `Assembler` for the accelerated path.
+
+`Assembler(fasta, ksize, threads, diskdb=None, debug=False, gap_size=1)` has the reference's
+constructor signature (`src/superpang/lib/Assembler.py:80`) and fills the attributes its host tail
+reads -- `ksize`, `seqDict`, `ref2name`, `vertex2coords`, `seqPaths`, `seqLimits`,
+`seqLimitsPerSeq`, `includedSeqs` (`lib/Assembler.py:85-96`, `:194`, `:206-220`, `:246`) -- from the
+CUDA library instead of the Python dict loop.  `collect_nbps()` replaces the NBP-collection head of
+`Assembler.run` (`lib/Assembler.py:269-363`): per connected component, in the reference's processing
+order, the raw NBP vertex tuples, `NBP2seq` sorted by (len, seq) descending (`:362`), the cycle flag
+(`:305`) and the per-NBP origin names after the goodOris rule (`:944-946`).
+
+Everything numeric happens on the GPU behind the C-ABI (`include/superpang_b200.h`); this module only
+converts device results into the Python containers the reference's downstream code expects.
+"""
+import re
+from collections import namedtuple
+
+import numpy as np
+
+from ._capi import Engine, SPB_NONE
+
+_AMBIG = {ord(a): ord("N") for a in "RYKMSWBDHV"}
+_ALLOWED = frozenset("ACTGN")
+_RE_REMOVE = re.compile(r"[\s.-]+")
+
+Component = namedtuple("Component", ["label", "n_vertices", "NBPs", "NBP2seq", "isCycle", "origins"])
+
+
+def read_fasta(fasta, gap_size=1):
+    """Same behaviour as the reference's `read_fasta(fasta, ambigs='as_Ns', Ns='split', gap_size)`
+    (`lib/utils.py:5-30`, `:52-59`): strip whitespace/`.`/`-`, upper-case, U->T, IUPAC ambiguity -> N,
+    illegal characters raise ValueError, split at every run of `gap_size` Ns, strip Ns from the pieces,
+    name them `{name}_Nsplit_{i}` only if the record had a gap; duplicated names raise."""
+    gap = "N" * gap_size
+    seqDict = {}
+    with open(fasta) as fh:
+        txt = fh.read().strip().lstrip(">")
+    for rec in txt.split("\n>"):
+        name, seq = rec.split("\n", 1)
+        name = name.split(" ")[0]
+        seq = _RE_REMOVE.sub("", seq).upper().replace("U", "T").translate(_AMBIG)
+        bad = set(seq) - _ALLOWED
+        if bad:
+            raise ValueError(f'Illegal chars in seq "{name}": {bad}')
+        if name in seqDict:
+            raise Exception(f'Sequence "{name}" is duplicated in your input file')
+        if gap not in seq:
+            seqDict[name] = seq
+        else:
+            i = 0
+            for piece in seq.split(gap):
+                piece = piece.strip("N")
+                if piece:
+                    seqDict[f"{name}_Nsplit_{i}"] = piece
+                    i += 1
+    return seqDict
+
+
+def concat_sequences(seqs):
+    """list of str / bytes / uint8 arrays -> (uint8[T], uint64[n+1])."""
+    lens = np.fromiter((len(s) for s in seqs), dtype=np.uint64, count=len(seqs))
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    buf = np.empty(int(off[-1]), dtype=np.uint8)
+    for s, a in zip(seqs, off[:-1]):
+        a = int(a)
+        if isinstance(s, np.ndarray):
+            buf[a:a + len(s)] = s
+        else:
+            b = s.encode() if isinstance(s, str) else s
+            buf[a:a + len(b)] = np.frombuffer(b, dtype=np.uint8)
+    return buf, off
+
+
+class Assembler:
+    def __init__(self, fasta, ksize, threads=1, diskdb=None, debug=False, gap_size=1, *, engine=None, device=0):
+        """Build the de Bruijn graph on the GPU.
+
+        `threads` and `diskdb` (`--lowmem`) are accepted for drop-in compatibility and ignored: the
+        fork pool and the RocksDB k-mer store (`lib/Assembler.py:109-117`, `:148`) are replaced by HBM.
+        `gap_size != 1` (raw k-mer strings with Ns as keys, `lib/Assembler.py:173-180`) is not covered
+        by the 2-bit GPU path and is refused."""
+        if gap_size != 1:
+            raise NotImplementedError("the B200 path only covers --gap-size 1 (2-bit k-mers)")
+        self.ksize = int(ksize)
+        self.debug = debug
+        if isinstance(fasta, dict):
+            self.seqDict = {n: (s if isinstance(s, str) else bytes(s).decode()) for n, s in fasta.items()}
+        else:
+            self.seqDict = read_fasta(fasta, gap_size=gap_size)
+        if any("N" in s for s in self.seqDict.values()):
+            raise ValueError("sequences still contain N after splitting")
+        self.ref2name = list(self.seqDict)
+        self.includedSeqs = sum(1 for s in self.seqDict.values() if len(s) > self.ksize)
+        self._eng = engine if engine is not None else Engine(device=device)
+        buf, off = concat_sequences(list(self.seqDict.values()))
+        self._seq_off = off
+        self._eng.load(buf, off, self.ksize)
+        self.counts = self._eng.build_dbg()
+        self._compacted = False
+        self._cache = {}
+
+    # ---- DBG-build state consumed by the reference's host tail ------------------------------
+    @property
+    def vertex2coords(self):
+        if "v2c" not in self._cache:
+            self._cache["v2c"] = self._eng.vertex2coords()
+        return self._cache["v2c"]
+
+    @property
+    def edges(self):
+        if "edges" not in self._cache:
+            self._cache["edges"] = self._eng.edges()
+        return self._cache["edges"]
+
+    def _limits(self):
+        if "lim" not in self._cache:
+            self._cache["lim"] = self._eng.seqlimits()
+        return self._cache["lim"]
+
+    @property
+    def seqLimits(self):
+        lim = self._limits()
+        return set(int(x) for x in lim.ravel() if x != SPB_NONE)
+
+    @property
+    def seqLimitsPerSeq(self):
+        lim = self._limits()
+        return {n: {int(a), int(b)} for n, (a, b) in zip(self.ref2name, lim) if a != SPB_NONE}
+
+    @property
+    def seqPaths(self):
+        if "sp" not in self._cache:
+            off, iv = self._eng.seq_intervals()
+            self._cache["sp"] = {n: iv[int(off[i]):int(off[i + 1])] for i, n in enumerate(self.ref2name)
+                                 if off[i + 1] > off[i]}
+        return self._cache["sp"]
+
+    def instance_vertices(self, name):
+        """The per-sequence `sp` array of `lib/Assembler.py:183-197` (vertex id of every k-mer)."""
+        if "inst" not in self._cache:
+            self._cache["inst"] = self._eng.instance_vertices()
+        i = self.ref2name.index(name)
+        a, b = int(self._seq_off[i]), int(self._seq_off[i + 1])
+        return self._cache["inst"][a:b - self.ksize + 1] if b - a > self.ksize else np.zeros(0, np.uint32)
+
+    # ---- NBP collection ---------------------------------------------------------------------
+    def compact(self):
+        if not self._compacted:
+            self.counts = self._eng.compact()
+            self._compacted = True
+        return self.counts
+
+    def raw_nbps(self):
+        """[(vertex tuple, sequence str, origin-name tuple, component label, isCycle)] for every raw NBP."""
+        self.compact()
+        voff, verts, comp, cyc = self._eng.nbps()
+        soff, seqs = self._eng.nbp_seqs()
+        ooff, oidx = self._eng.nbp_origins()
+        short = [n.split("_Nsplit_")[0] for n in self.ref2name]           # lib/Assembler.py:946
+        sbytes = seqs.tobytes()
+        out = []
+        for i in range(len(comp)):
+            v = tuple(verts[int(voff[i]):int(voff[i + 1])].tolist())
+            s = sbytes[int(soff[i]):int(soff[i + 1])].decode()
+            o = tuple(sorted({short[j] for j in oidx[int(ooff[i]):int(ooff[i + 1])]}))
+            out.append((v, s, o, int(comp[i]), bool(cyc[i])))
+        return out
+
+    def collect_nbps(self):
+        """Per component, in the reference's order (size descending, ties by label; `lib/Assembler.py:271-273`)."""
+        raw = self.raw_nbps()
+        labels = self._eng.components()
+        sizes = np.bincount(labels, minlength=int(self.counts["n_comp"]))
+        order = [c for c, s in sorted(zip(range(len(sizes)), sizes), key=lambda x: x[1], reverse=True)]
+        by = {c: [] for c in order}
+        for r in raw:
+            by[r[3]].append(r)
+        comps = []
+        for c in order:
+            rows = sorted(by[c], key=lambda r: (len(r[1]), r[1]), reverse=True)        # lib/Assembler.py:362
+            NBP2seq = {r[0]: r[1] for r in rows}
+            comps.append(Component(label=c, n_vertices=int(sizes[c]), NBPs=list(NBP2seq), NBP2seq=NBP2seq,
+                                   isCycle=any(r[4] for r in rows), origins={r[0]: set(r[2]) for r in rows}))
+        return comps
+
+    # ---- canonical result for parity tests ----------------------------------------------------
+    def to_result(self):
+        raw = self.raw_nbps()
+        return dict(
+            k=self.ksize,
+            names=list(self.seqDict),
+            n_inst=int(self.counts["n_inst"]),
+            vertex2coords=self.vertex2coords,
+            edges=self.edges,
+            seqPaths=self.seqPaths,
+            seqLimits=sorted(self.seqLimits),
+            ncomp=int(self.counts["n_comp"]),
+            nbps=raw,
+        )

@@ -1,0 +1,682 @@
+// superpang_b200 -- host orchestration + C-ABI (include/superpang_b200.h).
+//
+// Built by nvcc for sm_100a into libsuperpang_b200.so (the product), or by g++ -DSPB_EMU into
+// tests/emu/libspb_emu.so (kernel-logic emulator for the CPU-only test tier; never shipped).
+#include "spb_kernels.cuh"
+#include "../../include/superpang_b200.h"
+
+#include <cstdio>
+#include <cstdarg>
+#include <vector>
+#include <string>
+#include <algorithm>
+
+#ifndef SPB_EMU
+#include <cub/cub.cuh>
+#endif
+
+// =========================================================================================== runtime
+struct spb_ctx {
+  int device = 0;
+  spb_stream_t stream = 0;
+  char err[512] = {0};
+  int state = 0;                       // 0 created, 1 loaded, 2 dbg built, 3 compacted
+  u32 k = 0, n_seq = 0;
+  u64 T = 0, n_inst = 0, npos_pad = 0, nw = 0;
+  std::vector<u64> seq_off_h;
+  spb_counts cnt;
+  std::vector<void*> owned;            // every live device allocation (freed in destroy)
+  // ---- persistent device state
+  u64 *F = 0, *R = 0, *seq_off = 0;
+  u32 *vbits = 0, *obits = 0, *fbits = 0, *sp = 0, *v2pos = 0, *seqlim = 0, *errflag = 0;
+  u8* vflags = 0;
+  u32 nV = 0, nJ = 0;
+  u64* Jk = 0; u8* Js = 0;
+  u32* edges = 0;
+  // compaction
+  u32 nI = 0, nP = 0, nD = 0, nN = 0, nO = 0, nM = 0, nIv = 0;
+  u32 *init_list = 0, *ibase = 0, *plo = 0, *phi = 0, *dart_nbp = 0, *vnbp = 0, *parent = 0, *label_of_root = 0;
+  NbpTab nt; int32_t* nbp_comp = 0;
+  u64 *voff = 0, *soff = 0, *ooff = 0;
+  u32 *verts = 0, *origins = 0; u8* seqs = 0;
+  u32* iv = 0; u64* iv_off = 0;
+  std::string stats;
+};
+
+static int fail(spb_ctx* c, int code, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(c->err, sizeof c->err, fmt, ap); va_end(ap);
+  return code;
+}
+
+#ifdef SPB_EMU
+#define CK(x) do { (void)(x); } while (0)
+static void* dev_alloc_raw(spb_ctx*, u64 bytes) { return malloc(bytes ? bytes : 1); }
+static void dev_free_raw(spb_ctx*, void* p) { free(p); }
+static void dev_memset(spb_ctx*, void* p, int v, u64 bytes) { memset(p, v, bytes); }
+static void dev_copy(spb_ctx*, void* dst, const void* src, u64 bytes) { memcpy(dst, src, bytes); }
+static void dev_sync(spb_ctx*) {}
+struct StageTimer { void start(spb_ctx*) {} float stop(spb_ctx*) { return 0.f; } };
+#else
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(c, SPB_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); } while (0)
+static void* dev_alloc_raw(spb_ctx* c, u64 bytes) {
+  void* p = nullptr;
+  if (cudaMallocAsync(&p, bytes ? bytes : 1, c->stream) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+static void dev_free_raw(spb_ctx* c, void* p) { cudaFreeAsync(p, c->stream); }
+static void dev_memset(spb_ctx* c, void* p, int v, u64 bytes) { cudaMemsetAsync(p, v, bytes, c->stream); }
+static void dev_copy(spb_ctx* c, void* dst, const void* src, u64 bytes) { cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, c->stream); }
+static void dev_sync(spb_ctx* c) { cudaStreamSynchronize(c->stream); }
+struct StageTimer {
+  cudaEvent_t a = 0, b = 0;
+  void start(spb_ctx* c) { if (!a) { cudaEventCreate(&a); cudaEventCreate(&b); } cudaEventRecord(a, c->stream); }
+  float stop(spb_ctx* c) { cudaEventRecord(b, c->stream); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+  ~StageTimer() { if (a) { cudaEventDestroy(a); cudaEventDestroy(b); } }
+};
+#endif
+
+template <class T> static T* dalloc(spb_ctx* c, u64 n) {
+  void* p = dev_alloc_raw(c, n * sizeof(T) + 64);
+  if (p) c->owned.push_back(p);
+  return (T*)p;
+}
+template <class T> static void dfree(spb_ctx* c, T*& p) {
+  if (!p) return;
+  auto it = std::find(c->owned.begin(), c->owned.end(), (void*)p);
+  if (it != c->owned.end()) { *it = c->owned.back(); c->owned.pop_back(); }
+  dev_free_raw(c, (void*)p);
+  p = nullptr;
+}
+#define ALLOC(ptr, T, n) do { (ptr) = dalloc<T>(c, (n)); if (!(ptr)) return fail(c, SPB_ENOMEM, "device allocation of %llu bytes failed (%s)", (unsigned long long)((n) * sizeof(T)), #ptr); } while (0)
+template <class T> static T dread(spb_ctx* c, const T* p) { T v; dev_copy(c, &v, p, sizeof(T)); dev_sync(c); return v; }
+
+static inline u64 nblk(u64 n, u32 t) { return (n + t - 1) / t; }
+#define TPB 256
+
+// =========================================================================================== primitives
+// Device-wide scan / sort / select.  CUDA: CUB (CCCL shipped with CUDA 12.9).  Emulator: <algorithm>.
+#ifdef SPB_EMU
+static int prim_scan_u32(spb_ctx*, const u32* in, u32* out, u64 n, u64* total) {
+  u64 s = 0; for (u64 i = 0; i < n; ++i) { u32 v = in[i]; out[i] = (u32)s; s += v; } *total = s; return 0;
+}
+static int prim_scan_u64(spb_ctx*, const u64* in, u64* out, u64 n, u64* total) {
+  u64 s = 0; for (u64 i = 0; i < n; ++i) { u64 v = in[i]; out[i] = s; s += v; } *total = s; return 0;
+}
+static int prim_sort_u64_u8(spb_ctx*, u64*& k, u8*& v, u64*& k2, u8*& v2, u64 n) {
+  std::vector<u64> idx(n); for (u64 i = 0; i < n; ++i) idx[i] = i;
+  std::stable_sort(idx.begin(), idx.end(), [&](u64 a, u64 b) { return k[a] < k[b]; });
+  for (u64 i = 0; i < n; ++i) { k2[i] = k[idx[i]]; v2[i] = v[idx[i]]; }
+  std::swap(k, k2); std::swap(v, v2); return 0;
+}
+static int prim_sort_u64_u64(spb_ctx*, u64*& k, u64*& v, u64*& k2, u64*& v2, u64 n) {
+  std::vector<u64> idx(n); for (u64 i = 0; i < n; ++i) idx[i] = i;
+  std::stable_sort(idx.begin(), idx.end(), [&](u64 a, u64 b) { return k[a] < k[b]; });
+  for (u64 i = 0; i < n; ++i) { k2[i] = k[idx[i]]; v2[i] = v[idx[i]]; }
+  std::swap(k, k2); std::swap(v, v2); return 0;
+}
+static int prim_sort_u64(spb_ctx*, u64*& k, u64* k2, u64 n) { std::sort(k, k + n); (void)k2; return 0; }
+static int prim_select_flag(spb_ctx*, const u8* flags, u8 mask, u64 n, u32* out, u32* count) {
+  u32 m = 0; for (u64 i = 0; i < n; ++i) if (flags[i] & mask) out[m++] = (u32)i; *count = m; return 0;
+}
+static int prim_count_flag(spb_ctx*, const u8* flags, u8 mask, u64 n, u32* count) {
+  u32 m = 0; for (u64 i = 0; i < n; ++i) if (flags[i] & mask) ++m; *count = m; return 0;
+}
+static int prim_segmax_u64(spb_ctx*, const u64* in, u64* out, u64 n) {   // running max within equal high-32 segments
+  for (u64 i = 0; i < n; ++i) out[i] = (i && (in[i] >> 32) == (out[i - 1] >> 32) && out[i - 1] > in[i]) ? out[i - 1] : in[i];
+  return 0;
+}
+#else
+struct FlagPred { const u8* f; u8 m; __device__ bool operator()(u32 i) const { return (f[i] & m) != 0; } };
+struct SegMaxOp { __device__ u64 operator()(u64 a, u64 b) const { return ((a >> 32) == (b >> 32) && a > b) ? a : b; } };
+#define CUB2(call_with_tmp) do { void* tmp = nullptr; size_t tb = 0; CK(call_with_tmp); tmp = dev_alloc_raw(c, tb); \
+    if (!tmp) return fail(c, SPB_ENOMEM, "cub temp storage (%zu bytes)", tb); cudaError_t e2_ = (call_with_tmp); dev_free_raw(c, tmp); CK(e2_); } while (0)
+static int prim_scan_u32(spb_ctx* c, const u32* in, u32* out, u64 n, u64* total) {
+  if (n == 0) { *total = 0; return 0; }
+  CUB2(cub::DeviceScan::ExclusiveSum(tmp, tb, in, out, (size_t)n, c->stream));
+  u32 a = 0, b = 0; dev_copy(c, &a, in + n - 1, 4); dev_copy(c, &b, out + n - 1, 4); dev_sync(c);
+  *total = (u64)a + b; return 0;
+}
+static int prim_scan_u64(spb_ctx* c, const u64* in, u64* out, u64 n, u64* total) {
+  if (n == 0) { *total = 0; return 0; }
+  CUB2(cub::DeviceScan::ExclusiveSum(tmp, tb, in, out, (size_t)n, c->stream));
+  u64 a = 0, b = 0; dev_copy(c, &a, in + n - 1, 8); dev_copy(c, &b, out + n - 1, 8); dev_sync(c);
+  *total = a + b; return 0;
+}
+static int prim_sort_u64_u8(spb_ctx* c, u64*& k, u8*& v, u64*& k2, u8*& v2, u64 n) {
+  if (n == 0) return 0;
+  cub::DoubleBuffer<u64> dk(k, k2); cub::DoubleBuffer<u8> dv(v, v2);
+  CUB2(cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, (size_t)n, 0, 64, c->stream));
+  if (dk.Current() != k) { std::swap(k, k2); }
+  if (dv.Current() != v) { std::swap(v, v2); }
+  return 0;
+}
+static int prim_sort_u64_u64(spb_ctx* c, u64*& k, u64*& v, u64*& k2, u64*& v2, u64 n) {
+  if (n == 0) return 0;
+  cub::DoubleBuffer<u64> dk(k, k2); cub::DoubleBuffer<u64> dv(v, v2);
+  CUB2(cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, (size_t)n, 0, 64, c->stream));
+  if (dk.Current() != k) { std::swap(k, k2); }
+  if (dv.Current() != v) { std::swap(v, v2); }
+  return 0;
+}
+static int prim_sort_u64(spb_ctx* c, u64*& k, u64* k2, u64 n) {
+  if (n == 0) return 0;
+  cub::DoubleBuffer<u64> dk(k, k2);
+  CUB2(cub::DeviceRadixSort::SortKeys(tmp, tb, dk, (size_t)n, 0, 64, c->stream));
+  if (dk.Current() != k) {            // keep the result in the caller's primary buffer
+    CK(cudaMemcpyAsync(k, k2, n * 8, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  return 0;
+}
+static int prim_select_flag(spb_ctx* c, const u8* flags, u8 mask, u64 n, u32* out, u32* count) {
+  *count = 0;
+  if (n == 0) return 0;
+  u32* dcount = (u32*)dev_alloc_raw(c, 8);
+  if (!dcount) return fail(c, SPB_ENOMEM, "select count");
+  cub::CountingInputIterator<u32> it(0);
+  FlagPred pred{flags, mask};
+  CUB2(cub::DeviceSelect::If(tmp, tb, it, out, dcount, (int)n, pred, c->stream));
+  *count = dread(c, dcount);
+  dev_free_raw(c, dcount);
+  return 0;
+}
+__global__ void k_count_flag(const u8* __restrict__ f, u8 m, u64 n, u32* cnt) {
+  u64 i = SPB_GTID();
+  bool b = i < n && (f[i] & m);
+  u32 bal = __ballot_sync(0xffffffffu, b);
+  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(cnt, (u32)__popc(bal));
+}
+static int prim_count_flag(spb_ctx* c, const u8* flags, u8 mask, u64 n, u32* count) {
+  u32* d = (u32*)dev_alloc_raw(c, 8);
+  if (!d) return fail(c, SPB_ENOMEM, "count");
+  dev_memset(c, d, 0, 4);
+  SPB_LAUNCH(k_count_flag, nblk(n, TPB), TPB, c->stream, flags, mask, n, d);
+  *count = dread(c, d);
+  dev_free_raw(c, d);
+  return 0;
+}
+static int prim_segmax_u64(spb_ctx* c, const u64* in, u64* out, u64 n) {
+  if (n == 0) return 0;
+  CUB2(cub::DeviceScan::InclusiveScan(tmp, tb, in, out, SegMaxOp(), (size_t)n, c->stream));
+  return 0;
+}
+#endif
+#define PRIM(x) do { int r_ = (x); if (r_) return r_; } while (0)
+
+// sorted u64 keys (+ optional u8 payload) -> unique, in place; checks payload agreement
+static int unique_sorted(spb_ctx* c, u64*& keys, u8*& pay, u64 n, u32* n_out) {
+  *n_out = 0;
+  if (n == 0) return 0;
+  u32 *head, *pos; u64* ok; u8* op = nullptr;
+  ALLOC(head, u32, n); ALLOC(pos, u32, n); ALLOC(ok, u64, n);
+  if (pay) ALLOC(op, u8, n);
+  SPB_LAUNCH(k_unique_heads, nblk(n, TPB), TPB, c->stream, keys, pay, n, head, c->errflag);
+  u64 total = 0;
+  PRIM(prim_scan_u32(c, head, pos, n, &total));
+  SPB_LAUNCH(k_unique_scatter, nblk(n, TPB), TPB, c->stream, keys, pay, n, head, pos, ok, op);
+  dfree(c, head); dfree(c, pos); dfree(c, keys); keys = ok;
+  if (pay) { dfree(c, pay); pay = op; }
+  *n_out = (u32)total;
+  return 0;
+}
+
+static int check_err(spb_ctx* c, const char* where) {
+  u32 e = dread(c, c->errflag);
+  if (e & ERR_BADCHAR) return fail(c, SPB_EINVAL, "%s: input contains characters other than A/C/G/T", where);
+  if (e & ERR_DEGENERATE)
+    return fail(c, SPB_EDEGENERATE, "%s: degenerate input (k-mer overlaps are not orientation-unique; the reference asserts on it, lib/Assembler.py:1088/:1104)", where);
+  if (e & ERR_OVERFLOW) return fail(c, SPB_ENOMEM, "%s: internal list overflow", where);
+#ifndef SPB_EMU
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return fail(c, SPB_ECUDA, "%s: %s", where, cudaGetErrorString(ce));
+#endif
+  return 0;
+}
+
+// =========================================================================================== C-ABI
+extern "C" {
+
+const char* spb_build_kind(void) {
+#ifdef SPB_EMU
+  return "emu";
+#else
+  return "cuda sm_100a";
+#endif
+}
+
+int spb_create(spb_ctx** out, int device, void* cuda_stream) {
+  if (!out) return SPB_EINVAL;
+  *out = nullptr;
+#ifndef SPB_EMU
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) { cudaGetLastError(); return SPB_ECUDA; }
+  if (cudaSetDevice(device) != cudaSuccess) return SPB_ECUDA;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+#endif
+  spb_ctx* c = new spb_ctx();
+  c->device = device;
+  c->stream = (spb_stream_t)cuda_stream;
+  memset(&c->cnt, 0, sizeof c->cnt);
+  memset(&c->nt, 0, sizeof c->nt);
+  c->errflag = dalloc<u32>(c, 4);
+  if (!c->errflag) { delete c; return SPB_ENOMEM; }
+  dev_memset(c, c->errflag, 0, 16);
+  *out = c;
+  return SPB_OK;
+}
+
+static void free_all(spb_ctx* c, bool keep_err) {
+  for (void* p : c->owned) if (!(keep_err && p == (void*)c->errflag)) dev_free_raw(c, p);
+  c->owned.clear();
+  if (keep_err) c->owned.push_back(c->errflag);
+}
+
+void spb_destroy(spb_ctx* c) {
+  if (!c) return;
+#ifndef SPB_EMU
+  cudaSetDevice(c->device);
+#endif
+  free_all(c, false);
+  dev_sync(c);
+  delete c;
+}
+
+const char* spb_last_error(const spb_ctx* c) { return c ? c->err : "null context"; }
+
+int spb_load(spb_ctx* c, const uint8_t* ascii, const uint64_t* seq_off, uint32_t n_seq, uint32_t k) {
+  if (!c) return SPB_EINVAL;
+#ifndef SPB_EMU
+  CK(cudaSetDevice(c->device));
+#endif
+  if (!ascii || !seq_off || n_seq == 0) return fail(c, SPB_EINVAL, "empty input");
+  if (k < 3 || (k & 1) == 0) return fail(c, SPB_EINVAL, "k must be odd and >= 3 (got %u); the reference assumes odd k (SURVEY Q8)", k);
+  if (k > 4000) return fail(c, SPB_EINVAL, "k = %u exceeds the reference's limit (Compressor.pyx:35)", k);
+  u64 T = seq_off[n_seq];
+  if (seq_off[0] != 0) return fail(c, SPB_EINVAL, "seq_off[0] must be 0");
+  for (u32 s = 0; s < n_seq; ++s) if (seq_off[s + 1] < seq_off[s]) return fail(c, SPB_EINVAL, "seq_off not monotone");
+  if (T == 0) return fail(c, SPB_EINVAL, "empty input");
+  if (T >= (1ull << 32) - 4096) return fail(c, SPB_EINVAL, "input of %llu bases exceeds the 32-bit position range of one device", (unsigned long long)T);
+  // drop previous state
+  u32* ef = c->errflag;
+  free_all(c, true);
+  { spb_ctx fresh; fresh.device = c->device; fresh.stream = c->stream; fresh.errflag = ef; fresh.owned = c->owned; memset(&fresh.cnt, 0, sizeof fresh.cnt); memset(&fresh.nt, 0, sizeof fresh.nt); *c = fresh; }
+  dev_memset(c, c->errflag, 0, 16);
+  c->k = k; c->n_seq = n_seq; c->T = T;
+  c->seq_off_h.assign(seq_off, seq_off + n_seq + 1);
+  u64 ninst = 0;
+  for (u32 s = 0; s < n_seq; ++s) { u64 len = seq_off[s + 1] - seq_off[s]; if (len > k) ninst += len - k + 1; }
+  c->n_inst = ninst;
+  const u32 W = (2 * k + 63) / 64;
+  c->nw = (T + 31) / 32;
+  c->npos_pad = nblk(T, TPB) * TPB + TPB;
+  u8* d_ascii;
+  ALLOC(d_ascii, u8, T);
+  dev_copy(c, d_ascii, ascii, T);
+  ALLOC(c->seq_off, u64, n_seq + 1);
+  dev_copy(c, c->seq_off, seq_off, (n_seq + 1) * 8ull);
+  u64 nwp = c->nw + W + 8;
+  ALLOC(c->F, u64, nwp); ALLOC(c->R, u64, nwp);
+  dev_memset(c, c->F, 0, nwp * 8); dev_memset(c, c->R, 0, nwp * 8);
+  SPB_LAUNCH(k_pack, nblk(c->nw, TPB), TPB, c->stream, d_ascii, T, c->F, c->R, c->nw, c->errflag);
+  u64 nw32 = c->npos_pad / 32;
+  ALLOC(c->vbits, u32, nw32 + 8);
+  dev_memset(c, c->vbits, 0, (nw32 + 8) * 4);
+  SPB_LAUNCH(k_valid_bits, nblk(nw32, TPB), TPB, c->stream, c->seq_off, n_seq, T, k, c->vbits, nw32);
+  dfree(c, d_ascii);
+  int r = check_err(c, "spb_load");
+  if (r) return r;
+  c->cnt.n_seq = n_seq; c->cnt.n_bases = T; c->cnt.n_inst = ninst;
+  c->state = 1;
+  return SPB_OK;
+}
+
+int spb_build_dbg(spb_ctx* c, spb_counts* out) {
+  if (!c) return SPB_EINVAL;
+  if (c->state < 1) return fail(c, SPB_ESTATE, "spb_build_dbg before spb_load");
+  if (c->state > 1) return fail(c, SPB_ESTATE, "spb_build_dbg called twice; call spb_load again");
+#ifndef SPB_EMU
+  CK(cudaSetDevice(c->device));
+#endif
+  const u64 T = c->T; const u32 k = c->k;
+  StageTimer tm; char buf[256]; c->stats = "{";
+  // ---- K1: canonical extraction + dedup insert
+  tm.start(c);
+  u64 cap = 1024; while (cap < 2 * c->n_inst) cap <<= 1;
+  c->cnt.table_slots = cap;
+  u64* slots; ALLOC(slots, u64, cap);
+  dev_memset(c, slots, 0xFF, cap * 8);
+  u64 nw32 = c->npos_pad / 32;
+  ALLOC(c->sp, u32, c->npos_pad + 8);
+  ALLOC(c->obits, u32, nw32 + 8); ALLOC(c->fbits, u32, nw32 + 8);
+  dev_memset(c, c->obits, 0, (nw32 + 8) * 4); dev_memset(c, c->fbits, 0, (nw32 + 8) * 4);
+  u64 grid = nblk(T, TPB);
+  SPB_LAUNCH(k_extract_insert, grid, TPB, c->stream, c->F, c->R, c->vbits, T, k, slots, cap - 1, c->sp, c->obits);
+  snprintf(buf, sizeof buf, "\"extract_insert_ms\": %.4f", tm.stop(c)); c->stats += buf;
+  // ---- K2/K3: first appearances -> vertex ids
+  tm.start(c);
+  SPB_LAUNCH(k_first_flags, grid, TPB, c->stream, slots, c->sp, c->vbits, T, c->fbits);
+  dfree(c, slots);
+  u64 nb = c->npos_pad / 256;
+  u32 *blkcnt, *blkoff; ALLOC(blkcnt, u32, nb); ALLOC(blkoff, u32, nb);
+  SPB_LAUNCH(k_block_counts, nblk(nb, TPB), TPB, c->stream, c->fbits, blkcnt, nb);
+  u64 nV = 0;
+  PRIM(prim_scan_u32(c, blkcnt, blkoff, nb, &nV));
+  c->nV = (u32)nV;
+  ALLOC(c->v2pos, u32, nV + 1); ALLOC(c->vflags, u8, nV + 16);
+  dev_memset(c, c->vflags, 0, nV + 16);
+  SPB_LAUNCH(k_assign_ids, grid, TPB, c->stream, c->sp, c->vbits, T, c->fbits, blkoff, c->v2pos, c->vflags);
+  dfree(c, blkcnt); dfree(c, blkoff);
+  snprintf(buf, sizeof buf, ", \"vertex_ids_ms\": %.4f", tm.stop(c)); c->stats += buf;
+  // ---- K4: junction edges
+  tm.start(c);
+  u64* jcount; ALLOC(jcount, u64, 2);
+  u64 jcap = std::max<u64>(4096, c->n_inst / 8);
+  u64* Jk = nullptr; u8* Js = nullptr; u64 nj = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    ALLOC(Jk, u64, jcap); ALLOC(Js, u8, jcap);
+    dev_memset(c, jcount, 0, 16);
+    SPB_LAUNCH(k_junction_emit, grid, TPB, c->stream, c->sp, T, c->vflags, c->v2pos, c->obits, Jk, Js, jcount, jcap);
+    nj = dread(c, jcount);
+    if (nj <= jcap) break;
+    dfree(c, Jk); dfree(c, Js); jcap = nj;
+  }
+  dfree(c, jcount);
+  {
+    u64* k2; u8* v2; ALLOC(k2, u64, nj); ALLOC(v2, u8, nj);
+    PRIM(prim_sort_u64_u8(c, Jk, Js, k2, v2, nj));
+    dfree(c, k2); dfree(c, v2);
+  }
+  PRIM(unique_sorted(c, Jk, Js, nj, &c->nJ));
+  c->Jk = Jk; c->Js = Js;
+  if (!c->Jk) { ALLOC(c->Jk, u64, 1); ALLOC(c->Js, u8, 1); }
+  SPB_LAUNCH(k_mark_hasj, nblk(c->nJ, TPB), TPB, c->stream, c->Jk, c->nJ, c->vflags);
+  ALLOC(c->seqlim, u32, 2ull * c->n_seq);
+  SPB_LAUNCH(k_mark_seqlim, nblk(c->n_seq, TPB), TPB, c->stream, c->seq_off, c->n_seq, k, c->sp, c->vflags, c->seqlim);
+  // ---- explicit edge list
+  GView g{c->vflags, c->Jk, c->Js, c->nJ, c->nV};
+  u32 *ecnt, *eoff; ALLOC(ecnt, u32, nV + 1); ALLOC(eoff, u32, nV + 1);
+  SPB_LAUNCH(k_edge_counts, nblk(nV, TPB), TPB, c->stream, g, ecnt);
+  u64 nE = 0;
+  PRIM(prim_scan_u32(c, ecnt, eoff, nV, &nE));
+  ALLOC(c->edges, u32, 2 * nE + 2);
+  SPB_LAUNCH(k_edge_write, nblk(nV, TPB), TPB, c->stream, g, eoff, c->edges);
+  dfree(c, ecnt); dfree(c, eoff);
+  snprintf(buf, sizeof buf, ", \"edges_ms\": %.4f", tm.stop(c)); c->stats += buf;
+  int r = check_err(c, "spb_build_dbg");
+  if (r) return r;
+  c->cnt.n_vertices = nV; c->cnt.n_edges = nE; c->cnt.n_junction = c->nJ;
+  c->state = 2;
+  if (out) *out = c->cnt;
+  return SPB_OK;
+}
+
+int spb_compact(spb_ctx* c, spb_counts* out) {
+  if (!c) return SPB_EINVAL;
+  if (c->state != 2) return fail(c, SPB_ESTATE, "spb_compact needs a freshly built DBG (state %d)", c->state);
+#ifndef SPB_EMU
+  CK(cudaSetDevice(c->device));
+#endif
+  const u64 T = c->T; const u32 k = c->k; const u32 nV = c->nV;
+  StageTimer tm; char buf[256];
+  GView g{c->vflags, c->Jk, c->Js, c->nJ, nV};
+  u32 *pl_nbr = 0, *pr_nbr = 0, *nxt = 0, *ptr[2] = {0, 0}, *acc[2] = {0, 0}, *root[2] = {0, 0}, *mnv[2] = {0, 0};
+  u8 *pl_side = 0, *pr_side = 0;
+  u32* ucount; ALLOC(ucount, u32, 4);
+  int cur = 0;
+  u32 ncyc = 0;
+  tm.start(c);
+  for (int pass = 0; pass < 2; ++pass) {
+    // ---- K5: init detection, K6: pieces
+    SPB_LAUNCH(k_classify, nblk(nV, TPB), TPB, c->stream, g, c->vflags, c->errflag);
+    SPB_LAUNCH(k_piece_flags, nblk(nV, TPB), TPB, c->stream, c->vflags, nV);
+    PRIM(prim_count_flag(c, c->vflags, VF_INIT, nV, &c->nI));
+    ALLOC(c->init_list, u32, c->nI + 1);
+    PRIM(prim_select_flag(c, c->vflags, VF_INIT, nV, c->init_list, &c->nI));
+    PRIM(prim_count_flag(c, c->vflags, VF_PSTART, nV, &c->nP));
+    ALLOC(c->plo, u32, c->nP + 1); ALLOC(c->phi, u32, c->nP + 1);
+    u32 np2 = 0;
+    PRIM(prim_select_flag(c, c->vflags, VF_PSTART, nV, c->plo, &c->nP));
+    PRIM(prim_select_flag(c, c->vflags, VF_PEND, nV, c->phi, &np2));
+    if (np2 != c->nP) return fail(c, SPB_ECUDA, "internal: piece starts (%u) != piece ends (%u)", c->nP, np2);
+    const u32 nP = c->nP, nD = 2 * nP;
+    c->nD = nD;
+    ALLOC(pl_nbr, u32, nP + 1); ALLOC(pr_nbr, u32, nP + 1); ALLOC(pl_side, u8, nP + 1); ALLOC(pr_side, u8, nP + 1);
+    SPB_LAUNCH(k_piece_ends, nblk(nP, TPB), TPB, c->stream, g, c->plo, c->phi, nP, pl_nbr, pl_side, pr_nbr, pr_side, c->errflag);
+    // ---- K7/K8: darts + list ranking
+    ALLOC(nxt, u32, nD + 1);
+    SPB_LAUNCH(k_dart_next, nblk(nD, TPB), TPB, c->stream, c->vflags, c->plo, nP, pl_nbr, pl_side, pr_nbr, pr_side, nxt);
+    for (int i = 0; i < 2; ++i) { ALLOC(ptr[i], u32, nD + 1); ALLOC(acc[i], u32, nD + 1); ALLOC(root[i], u32, nD + 1); ALLOC(mnv[i], u32, nD + 1); }
+    cur = 0;
+    SPB_LAUNCH(k_rank_init, nblk(nD, TPB), TPB, c->stream, nxt, c->plo, c->phi, nD, ptr[0], acc[0], root[0], mnv[0]);
+    u32 rounds = 1; while ((1ull << rounds) < (u64)nD + 1) ++rounds;
+    ++rounds;
+    for (u32 r = 0; r < rounds && nD; ++r) {
+      SPB_LAUNCH(k_rank_jump, nblk(nD, TPB), TPB, c->stream, nD, ptr[cur], acc[cur], root[cur], mnv[cur], ptr[cur ^ 1], acc[cur ^ 1],
+                 root[cur ^ 1], mnv[cur ^ 1]);
+      cur ^= 1;
+    }
+    dev_memset(c, ucount, 0, 16);
+    SPB_LAUNCH(k_count_unresolved, nblk(nD, TPB), TPB, c->stream, ptr[cur], nD, ucount);
+    u32 unresolved = dread(c, ucount);
+    if (unresolved == 0) break;
+    if (pass == 1) return fail(c, SPB_ECUDA, "internal: %u darts unresolved after cycle cutting", unresolved);
+    // ---- K9: pure-cycle components: cut one edge per ring, then redo classification
+    SPB_LAUNCH(k_cycle_cut, nblk(nD, TPB), TPB, c->stream, g, c->vflags, c->Js, ptr[cur], mnv[cur], c->plo, nD, ucount + 1);
+    ncyc = dread(c, ucount + 1);
+    dfree(c, c->init_list); dfree(c, c->plo); dfree(c, c->phi); dfree(c, pl_nbr); dfree(c, pr_nbr); dfree(c, pl_side); dfree(c, pr_side);
+    dfree(c, nxt);
+    for (int i = 0; i < 2; ++i) { dfree(c, ptr[i]); dfree(c, acc[i]); dfree(c, root[i]); dfree(c, mnv[i]); }
+  }
+  dfree(c, ucount);
+  c->cnt.n_cycle_comp = ncyc;
+  const u32 nP = c->nP, nD = c->nD, nI = c->nI;
+  snprintf(buf, sizeof buf, ", \"classify_rank_ms\": %.4f", tm.stop(c)); c->stats += buf;
+  // ---- K10: NBP table
+  tm.start(c);
+  u32* ideg; ALLOC(ideg, u32, nI + 1); ALLOC(c->ibase, u32, nI + 1);
+  SPB_LAUNCH(k_init_degrees, nblk(nI, TPB), TPB, c->stream, g, c->init_list, nI, ideg);
+  u64 nN64 = 0;
+  PRIM(prim_scan_u32(c, ideg, c->ibase, nI, &nN64));
+  dfree(c, ideg);
+  const u32 nN = (u32)nN64; c->nN = nN;
+  NbpTab& t = c->nt;
+  ALLOC(t.a, u32, nN + 1); ALLOC(t.b, u32, nN + 1); ALLOC(t.L, u32, nN + 1); ALLOC(t.head, u32, nN + 1); ALLOC(t.last, u32, nN + 1);
+  ALLOC(t.aside, u8, nN + 1); ALLOC(t.bside, u8, nN + 1); ALLOC(t.cyc, u8, nN + 1);
+  u32* head_nbp; ALLOC(head_nbp, u32, nD + 1); dev_memset(c, head_nbp, 0xFF, (nD + 1) * 4ull);
+  ALLOC(c->dart_nbp, u32, nD + 1);
+  SPB_LAUNCH(k_nbp_heads, nblk(nI, TPB), TPB, c->stream, g, c->vflags, c->init_list, c->ibase, nI, c->plo, nP, t, head_nbp);
+  SPB_LAUNCH(k_dart_finish, nblk(nD, TPB), TPB, c->stream, nxt, root[cur], acc[cur], c->plo, c->phi, pl_nbr, pl_side, pr_nbr, pr_side,
+             head_nbp, nD, c->dart_nbp, t);
+  u64 *vlen, *slen; ALLOC(vlen, u64, nN + 1); ALLOC(slen, u64, nN + 1);
+  ALLOC(c->voff, u64, nN + 1); ALLOC(c->soff, u64, nN + 1);
+  SPB_LAUNCH(k_nbp_lengths, nblk(nN, TPB), TPB, c->stream, t, nN, k, vlen, slen);
+  u64 totv = 0, tots = 0;
+  PRIM(prim_scan_u64(c, vlen, c->voff, nN, &totv));
+  PRIM(prim_scan_u64(c, slen, c->soff, nN, &tots));
+  dev_copy(c, c->voff + nN, &totv, 8); dev_copy(c, c->soff + nN, &tots, 8); dev_sync(c);
+  dfree(c, vlen); dfree(c, slen);
+  // ---- K11/K12: NBP vertex lists + sequences
+  ALLOC(c->verts, u32, totv + 1); ALLOC(c->seqs, u8, tots + 1);
+  ALLOC(c->vnbp, u32, (u64)nV + 1); dev_memset(c, c->vnbp, 0xFF, ((u64)nV + 1) * 4);
+  SPB_LAUNCH(k_emit_ends, nN, 128, c->stream, t, nN, k, T, c->F, c->R, c->v2pos, c->voff, c->soff, c->verts, c->seqs);
+  u32 *nch, *choff; ALLOC(nch, u32, nD + 1); ALLOC(choff, u32, nD + 1);
+  SPB_LAUNCH(k_dart_chunks, nblk(nD, TPB), TPB, c->stream, c->plo, c->phi, nD, nch);
+  u64 nchunks = 0;
+  PRIM(prim_scan_u32(c, nch, choff, nD, &nchunks));
+  SPB_LAUNCH(k_emit_darts, nchunks, 256, c->stream, choff, nD, c->plo, c->phi, c->dart_nbp, acc[cur], k, T, c->F, c->R, c->v2pos, c->voff,
+             c->soff, c->verts, c->seqs, c->vnbp);
+  dfree(c, nch); dfree(c, choff); dfree(c, head_nbp); dfree(c, nxt);
+  dfree(c, pl_nbr); dfree(c, pr_nbr); dfree(c, pl_side); dfree(c, pr_side);
+  for (int i = 0; i < 2; ++i) { dfree(c, ptr[i]); dfree(c, acc[i]); dfree(c, root[i]); dfree(c, mnv[i]); }
+  snprintf(buf, sizeof buf, ", \"emit_ms\": %.4f", tm.stop(c)); c->stats += buf;
+  // ---- K13: origins
+  tm.start(c);
+  {
+    u64* counts; ALLOC(counts, u64, 4);
+    u8* has01; ALLOC(has01, u8, 2ull * c->n_seq + 8);
+    u64 ocap = std::max<u64>(4096, c->n_inst / 16), mcap = std::max<u64>(4096, c->n_inst / 64);
+    u64 *op = 0, *mp = 0; u64 no = 0, nm = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      ALLOC(op, u64, ocap + 1); ALLOC(mp, u64, mcap + 1);
+      dev_memset(c, counts, 0, 32); dev_memset(c, has01, 0, 2ull * c->n_seq + 8);
+      SPB_LAUNCH(k_origin_pairs, nblk(T, TPB), TPB, c->stream, c->sp, T, c->vnbp, c->vflags, c->seq_off, c->n_seq, op, counts, ocap, mp,
+                 counts + 1, mcap, has01);
+      SPB_LAUNCH(k_origin_quirk, nblk(c->n_seq, TPB), TPB, c->stream, has01, c->n_seq, c->vnbp, c->vflags, op, counts, ocap, mp, counts + 1,
+                 mcap);
+      no = dread(c, counts); nm = dread(c, counts + 1);
+      if (no <= ocap && nm <= mcap) break;
+      dfree(c, op); dfree(c, mp); ocap = std::max(ocap, no); mcap = std::max(mcap, nm);
+    }
+    dfree(c, counts); dfree(c, has01);
+    u64* tmp; u8* nopay = nullptr;
+    ALLOC(tmp, u64, std::max(no, nm) + 1);
+    PRIM(prim_sort_u64(c, op, tmp, no));
+    PRIM(prim_sort_u64(c, mp, tmp, nm));
+    dfree(c, tmp);
+    PRIM(unique_sorted(c, op, nopay, no, &c->nO));
+    PRIM(unique_sorted(c, mp, nopay, nm, &c->nM));
+    if (!op) ALLOC(op, u64, 1);
+    if (!mp) ALLOC(mp, u64, 1);
+    u64* ocnt; ALLOC(ocnt, u64, nN + 1); ALLOC(c->ooff, u64, nN + 1);
+    SPB_LAUNCH(k_nbp_origins, nblk(nN, TPB), TPB, c->stream, t, nN, c->dart_nbp, op, c->nO, mp, c->nM, (const u64*)nullptr, ocnt, (u32*)nullptr);
+    u64 toto = 0;
+    PRIM(prim_scan_u64(c, ocnt, c->ooff, nN, &toto));
+    dev_copy(c, c->ooff + nN, &toto, 8); dev_sync(c);
+    ALLOC(c->origins, u32, toto + 1);
+    SPB_LAUNCH(k_nbp_origins, nblk(nN, TPB), TPB, c->stream, t, nN, c->dart_nbp, op, c->nO, mp, c->nM, c->ooff, ocnt, c->origins);
+    dfree(c, ocnt); dfree(c, op); dfree(c, mp);
+    c->cnt.n_origin_pairs = toto;
+  }
+  snprintf(buf, sizeof buf, ", \"origins_ms\": %.4f", tm.stop(c)); c->stats += buf;
+  // ---- K14: connected components
+  tm.start(c);
+  {
+    ALLOC(c->parent, u32, nI + 1); ALLOC(c->label_of_root, u32, nI + 1);
+    u32* cmin; ALLOC(cmin, u32, nI + 1); dev_memset(c, cmin, 0xFF, (nI + 1) * 4ull);
+    u64 *rk, *rk2; ALLOC(rk, u64, nI + 1); ALLOC(rk2, u64, nI + 1);
+    u32* nroots; ALLOC(nroots, u32, 4); dev_memset(c, nroots, 0, 16);
+    SPB_LAUNCH(k_uf_init, nblk(nI, TPB), TPB, c->stream, c->parent, nI);
+    SPB_LAUNCH(k_uf_union, nblk(nN, TPB), TPB, c->stream, t, nN, c->init_list, nI, c->parent);
+    SPB_LAUNCH(k_comp_min_init, nblk(nI, TPB), TPB, c->stream, c->init_list, nI, c->parent, cmin);
+    SPB_LAUNCH(k_comp_min_piece, nblk(nP, TPB), TPB, c->stream, c->plo, nP, c->dart_nbp, t, c->init_list, nI, c->parent, cmin);
+    SPB_LAUNCH(k_comp_roots, nblk(nI, TPB), TPB, c->stream, c->parent, cmin, nI, rk, nroots);
+    u32 nr = dread(c, nroots);
+    PRIM(prim_sort_u64(c, rk, rk2, nr));
+    SPB_LAUNCH(k_comp_labels, nblk(nr, TPB), TPB, c->stream, rk, nr, c->label_of_root);
+    ALLOC(c->nbp_comp, int32_t, nN + 1);
+    SPB_LAUNCH(k_nbp_comp, nblk(nN, TPB), TPB, c->stream, t, nN, c->init_list, nI, c->parent, c->label_of_root, c->nbp_comp);
+    dfree(c, cmin); dfree(c, rk); dfree(c, rk2); dfree(c, nroots);
+    c->cnt.n_comp = nr;
+  }
+  snprintf(buf, sizeof buf, ", \"components_ms\": %.4f}", tm.stop(c)); c->stats += buf;
+  int r = check_err(c, "spb_compact");
+  if (r) return r;
+  c->cnt.n_inits = nI; c->cnt.n_pieces = nP; c->cnt.n_nbp = nN; c->cnt.nbp_vertices = totv; c->cnt.nbp_bases = tots;
+  c->state = 3;
+  if (out) *out = c->cnt;
+  return SPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------- getters
+#define NEED(st) do { if (!c) return SPB_EINVAL; if (c->state < (st)) return fail(c, SPB_ESTATE, "%s: results not available yet (state %d)", __func__, c->state); } while (0)
+
+int spb_get_vertex2coords(spb_ctx* c, uint32_t* out) {
+  NEED(2);
+  u32* tmp; ALLOC(tmp, u32, 2ull * c->nV + 2);
+  SPB_LAUNCH(k_coords, nblk(c->nV, TPB), TPB, c->stream, c->v2pos, c->nV, c->seq_off, c->n_seq, tmp);
+  dev_copy(c, out, tmp, 8ull * c->nV); dev_sync(c);
+  dfree(c, tmp);
+  return check_err(c, __func__);
+}
+int spb_get_edges(spb_ctx* c, uint32_t* out) { NEED(2); dev_copy(c, out, c->edges, 8ull * c->cnt.n_edges); dev_sync(c); return SPB_OK; }
+int spb_get_instance_vertices(spb_ctx* c, uint32_t* out) { NEED(2); dev_copy(c, out, c->sp, 4ull * c->T); dev_sync(c); return SPB_OK; }
+int spb_get_seqlimits(spb_ctx* c, uint32_t* out) { NEED(2); dev_copy(c, out, c->seqlim, 8ull * c->n_seq); dev_sync(c); return SPB_OK; }
+
+static int build_intervals(spb_ctx* c) {
+  if (c->iv) return 0;
+  const u64 T = c->T;
+  u8* flags; ALLOC(flags, u8, T + 8);
+  SPB_LAUNCH(k_run_flags, nblk(T, TPB), TPB, c->stream, c->sp, T, flags);
+  u32 nR = 0, nR2 = 0;
+  PRIM(prim_count_flag(c, flags, 1, T, &nR));
+  u32 *rs, *re; ALLOC(rs, u32, nR + 1); ALLOC(re, u32, nR + 1);
+  PRIM(prim_select_flag(c, flags, 1, T, rs, &nR));
+  PRIM(prim_select_flag(c, flags, 2, T, re, &nR2));
+  dfree(c, flags);
+  if (nR != nR2) return fail(c, SPB_ECUDA, "internal: run starts (%u) != run ends (%u)", nR, nR2);
+  u64 *key, *val, *k2, *v2; ALLOC(key, u64, nR + 1); ALLOC(val, u64, nR + 1); ALLOC(k2, u64, nR + 1); ALLOC(v2, u64, nR + 1);
+  SPB_LAUNCH(k_run_intervals, nblk(nR, TPB), TPB, c->stream, c->sp, rs, re, nR, c->seq_off, c->n_seq, key, val);
+  dfree(c, rs); dfree(c, re);
+  PRIM(prim_sort_u64_u64(c, key, val, k2, v2, nR));
+  u64* runmax = k2;        // reuse the sort's spare key buffer
+  PRIM(prim_segmax_u64(c, val, runmax, nR));
+  u32 *head, *pos; ALLOC(head, u32, nR + 1); ALLOC(pos, u32, nR + 1);
+  SPB_LAUNCH(k_interval_heads, nblk(nR, TPB), TPB, c->stream, key, runmax, nR, head);
+  u64 nIv = 0;
+  PRIM(prim_scan_u32(c, head, pos, nR, &nIv));
+  u32* iv_seq; ALLOC(iv_seq, u32, nIv + 1); ALLOC(c->iv, u32, 2 * nIv + 2);
+  SPB_LAUNCH(k_interval_write, nblk(nR, TPB), TPB, c->stream, key, runmax, nR, head, pos, c->iv, iv_seq);
+  ALLOC(c->iv_off, u64, c->n_seq + 2);
+  SPB_LAUNCH(k_interval_offsets, nblk(c->n_seq + 1, TPB), TPB, c->stream, iv_seq, (u32)nIv, c->n_seq, c->iv_off);
+  dfree(c, key); dfree(c, val); dfree(c, k2); dfree(c, v2); dfree(c, head); dfree(c, pos); dfree(c, iv_seq);
+  c->nIv = (u32)nIv; c->cnt.n_seq_intervals = nIv;
+  dev_sync(c);
+  return check_err(c, "seq_intervals");
+}
+int spb_get_seq_intervals(spb_ctx* c, uint64_t* off, uint32_t* intervals) {
+  NEED(2);
+  int r = build_intervals(c);
+  if (r) return r;
+  if (off) dev_copy(c, off, c->iv_off, 8ull * (c->n_seq + 1));
+  if (intervals) dev_copy(c, intervals, c->iv, 8ull * c->nIv);
+  dev_sync(c);
+  return SPB_OK;
+}
+int spb_get_components(spb_ctx* c, int32_t* out) {
+  NEED(3);
+  int32_t* tmp; ALLOC(tmp, int32_t, (u64)c->nV + 1);
+  SPB_LAUNCH(k_vertex_comp, nblk(c->nV, TPB), TPB, c->stream, c->vflags, c->nV, c->vnbp, c->init_list, c->nI, c->parent, c->label_of_root,
+             c->nbp_comp, tmp);
+  dev_copy(c, out, tmp, 4ull * c->nV); dev_sync(c);
+  dfree(c, tmp);
+  return check_err(c, __func__);
+}
+int spb_get_nbps(spb_ctx* c, uint64_t* off, uint32_t* verts, int32_t* comp, uint8_t* is_cycle) {
+  NEED(3);
+  if (off) dev_copy(c, off, c->voff, 8ull * (c->nN + 1));
+  if (verts) dev_copy(c, verts, c->verts, 4ull * c->cnt.nbp_vertices);
+  if (comp) dev_copy(c, comp, c->nbp_comp, 4ull * c->nN);
+  if (is_cycle) dev_copy(c, is_cycle, c->nt.cyc, (u64)c->nN);
+  dev_sync(c);
+  return SPB_OK;
+}
+int spb_get_nbp_seqs(spb_ctx* c, uint64_t* off, uint8_t* ascii) {
+  NEED(3);
+  if (off) dev_copy(c, off, c->soff, 8ull * (c->nN + 1));
+  if (ascii) dev_copy(c, ascii, c->seqs, c->cnt.nbp_bases);
+  dev_sync(c);
+  return SPB_OK;
+}
+int spb_get_nbp_origins(spb_ctx* c, uint64_t* off, uint32_t* seq_idx) {
+  NEED(3);
+  if (off) dev_copy(c, off, c->ooff, 8ull * (c->nN + 1));
+  if (seq_idx) dev_copy(c, seq_idx, c->origins, 4ull * c->cnt.n_origin_pairs);
+  dev_sync(c);
+  return SPB_OK;
+}
+uint64_t spb_launch_count(void) { return g_spb_launches; }
+int spb_get_counts(spb_ctx* c, spb_counts* out) {
+  if (!c || !out) return SPB_EINVAL;
+  *out = c->cnt;
+  return SPB_OK;
+}
+int spb_get_stage_stats(spb_ctx* c, char* buf, uint64_t cap) {
+  if (!c || !buf || !cap) return SPB_EINVAL;
+  snprintf(buf, cap, "%s", c->stats.c_str());
+  return SPB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,800 @@
+// superpang_b200 -- device kernels (sm_100a) for DBG build + NBP compaction.
+//
+// Data layout in HBM:
+//   F, R      2-bit packed forward strand and reverse-complement strand of the CONCATENATED input,
+//             32 bases per u64, first base in the top bits, so that integer compare of limbs ==
+//             lexicographic compare of bases (A<C<G<T).  rc(F[a..a+k)) == R[T-a-k..T-a).
+//   position  p = global base offset; a k-mer instance is identified by its start position.
+//   slots     open-addressing table, u64 = tag(24) | first-known position(39) | orientation(1).
+//   sp        u32 per position: vertex id of the instance (SPB_INVALID where no k-mer starts).
+//   vflags    u8 per vertex (VF_* bits); implicit edge (v, v+1) is the VF_R bit of v.
+//   J         sorted unique directed "junction" entries (src<<32|dst) + side byte; these are the
+//             only edges that are not (v, v+1) between consecutive first appearances.
+#pragma once
+#include "spb_platform.h"
+
+#define SPB_INVALID 0xFFFFFFFFu
+#define SPB_TERM 0xFFFFFFFFu
+#define SPB_EMPTY 0xFFFFFFFFFFFFFFFFull
+#define SPB_POSMASK ((1ull << 39) - 1)
+
+enum { VF_R = 1, VF_HASJ = 2, VF_SEQLIM = 4, VF_INIT = 8, VF_CYC = 16, VF_PSTART = 32, VF_PEND = 64, VF_IN2 = 128 };
+enum { JS_SRC_R = 1, JS_DST_R = 2, JS_CUT = 4 };
+enum { SIDE_L = 0, SIDE_R = 1 };
+enum { ERR_BADCHAR = 1, ERR_DEGENERATE = 2, ERR_OVERFLOW = 4 };
+
+// ------------------------------------------------------------------------------------ bit helpers
+__device__ __forceinline__ u32 get_bit(const u32* bits, u64 i) { return (bits[i >> 5] >> (i & 31)) & 1u; }
+
+// One bit per thread of a full grid: warp ballot on the GPU (no atomics); the emulator ORs into a
+// pre-zeroed array.  `i` must be the global thread id and every thread of the warp must call it.
+__device__ __forceinline__ void store_bit(u32* bits, u64 i, bool flag) {
+#ifdef SPB_EMU
+  if (flag) bits[i >> 5] |= 1u << (i & 31);
+#else
+  u32 m = __ballot_sync(0xffffffffu, flag);
+  if ((threadIdx.x & 31) == 0) bits[i >> 5] = m;
+#endif
+}
+
+// append `n` items to a list guarded by a u64 counter; returns the first slot
+__device__ __forceinline__ u64 list_reserve(u64* counter, u32 n) {
+#ifdef SPB_EMU
+  return atomicAdd(counter, (u64)n);
+#else
+  // warp-aggregated: one atomic per warp
+  u32 active = __activemask();
+  u32 lane = threadIdx.x & 31;
+  u32 incl = n;
+  // inclusive prefix over active lanes (n is 0..3: do it with ballots per bit)
+  u32 b0 = __ballot_sync(active, n & 1), b1 = __ballot_sync(active, n & 2);
+  u32 below = (1u << lane) - 1;
+  u32 before = __popc(b0 & below) + 2 * __popc(b1 & below);
+  u32 total = __popc(b0) + 2 * __popc(b1);
+  int leader = __ffs(active) - 1;
+  u64 base = 0;
+  if ((int)lane == leader) base = atomicAdd(counter, (u64)total);
+  base = __shfl_sync(active, base, leader);
+  (void)incl;
+  return base + before;
+#endif
+}
+
+// ------------------------------------------------------------------------------------ windows
+// limb j of the 2k-bit window starting at base a of packed strand S (first base in the top bits)
+struct Win {
+  const u64* w;   // word pointer
+  u32 sh;         // bit shift 0..62
+};
+__device__ __forceinline__ Win win_at(const u64* S, u64 a) { Win r; r.w = S + (a >> 5); r.sh = (u32)(a & 31) * 2; return r; }
+__device__ __forceinline__ u64 funnel(u64 hi, u64 lo, u32 sh) { return sh ? (hi << sh) | (lo >> (64 - sh)) : hi; }
+__device__ __forceinline__ u64 tail_mask(u32 k) { u32 nb = 2 * k - 64 * ((2 * k + 63) / 64 - 1); return nb == 64 ? ~0ull : (~0ull << (64 - nb)); }
+
+// lexicographic compare of two k-base windows: -1 / 0 / +1
+__device__ __forceinline__ int win_cmp(const u64* A, u64 a, const u64* B, u64 b, u32 k) {
+  const u32 W = (2 * k + 63) / 64;
+  Win x = win_at(A, a), y = win_at(B, b);
+  u64 x0 = __ldg(x.w), y0 = __ldg(y.w);
+  for (u32 j = 0; j < W; ++j) {
+    u64 x1 = __ldg(x.w + j + 1), y1 = __ldg(y.w + j + 1);
+    u64 lx = funnel(x0, x1, x.sh), ly = funnel(y0, y1, y.sh);
+    if (j == W - 1) { u64 m = tail_mask(k); lx &= m; ly &= m; }
+    if (lx != ly) return lx > ly ? 1 : -1;
+    x0 = x1; y0 = y1;
+  }
+  return 0;
+}
+
+__device__ __forceinline__ u64 win_hash(const u64* A, u64 a, u32 k) {
+  const u32 W = (2 * k + 63) / 64;
+  Win x = win_at(A, a);
+  u64 h = 0x9E3779B97F4A7C15ull ^ (u64)k;
+  u64 x0 = __ldg(x.w);
+  for (u32 j = 0; j < W; ++j) {
+    u64 x1 = __ldg(x.w + j + 1);
+    u64 l = funnel(x0, x1, x.sh);
+    if (j == W - 1) l &= tail_mask(k);
+    h ^= l; h *= 0xff51afd7ed558ccdull; h ^= h >> 32;
+    x0 = x1;
+  }
+  h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 29;
+  return h;
+}
+
+__device__ __forceinline__ u32 base_at(const u64* S, u64 a) { return (u32)(S[a >> 5] >> (62 - 2 * (a & 31))) & 3u; }
+
+// ------------------------------------------------------------------------------------ K0: pack
+// One thread per packed word of F and of R (32 bases).  A=0 C=1 G=2 T=3.
+__device__ __forceinline__ u32 ascii_code(u32 c, u32* bad) {
+  if (c != 'A' && c != 'C' && c != 'G' && c != 'T') *bad = 1;
+  u32 t = (c >> 1) & 3u;        // A0 C1 T2 G3
+  return t ^ (t >> 1);          // A0 C1 G2 T3
+}
+__global__ void k_pack(const u8* __restrict__ ascii, u64 T, u64* __restrict__ F, u64* __restrict__ R, u64 nw, u32* err) {
+  u64 w = SPB_GTID();
+  if (w >= nw) return;
+  u64 f = 0, r = 0; u32 bad = 0;
+  for (u32 j = 0; j < 32; ++j) {
+    u64 p = w * 32 + j;
+    u32 cf = 0, cr = 0;
+    if (p < T) {
+      cf = ascii_code(__ldg(ascii + p), &bad);
+      cr = 3u - ascii_code(__ldg(ascii + (T - 1 - p)), &bad);
+    }
+    f = (f << 2) | cf; r = (r << 2) | cr;
+  }
+  F[w] = f; R[w] = r;
+  if (bad) atomicOr(err, (u32)ERR_BADCHAR);
+}
+
+// valid-start bitmap: bit p set iff a k-mer of some sequence starts at p.  One thread per 32 positions.
+__device__ __forceinline__ u32 upper_bound_u64(const u64* a, u32 n, u64 x) {  // first i with a[i] > x
+  u32 lo = 0, hi = n;
+  while (lo < hi) { u32 mid = (lo + hi) >> 1; if (__ldg(a + mid) <= x) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+__global__ void k_valid_bits(const u64* __restrict__ seq_off, u32 n_seq, u64 T, u32 k, u32* __restrict__ vbits, u64 nwords32) {
+  u64 w = SPB_GTID();
+  if (w >= nwords32) return;
+  u64 p0 = w * 32;
+  u32 m = 0;
+  if (p0 < T) {
+    u32 s = upper_bound_u64(seq_off, n_seq + 1, p0) - 1;     // sequence containing p0
+    for (; s < n_seq; ++s) {
+      u64 b = __ldg(seq_off + s), e = __ldg(seq_off + s + 1);
+      if (b >= p0 + 32) break;
+      if (e - b > k) {                                        // len > k (reference lib/Assembler.py:151)
+        u64 lo = b > p0 ? b : p0, hi = e - k + 1;             // valid starts [b, e-k]
+        if (hi > p0 + 32) hi = p0 + 32;
+        for (u64 p = lo; p < hi; ++p) m |= 1u << (p - p0);
+      }
+    }
+  }
+  vbits[w] = m;
+}
+
+// ------------------------------------------------------------------------------------ K1: extract + dedup insert
+// One thread per base position.  Canonical = lexicographic max of (k-mer, reverse complement)
+// (reference lib/Assembler.py:989-991).  The table keeps, per distinct canonical k-mer, the
+// SMALLEST position seen (atomicMin) -> first appearance in (sequence, position) order
+// (reference lib/Assembler.py:186-195).  Equality is always verified on the full 2k bits.
+__global__ void SPB_LAUNCH_BOUNDS(256)
+k_extract_insert(const u64* __restrict__ F, const u64* __restrict__ R, const u32* __restrict__ vbits, u64 T, u32 k,
+                 u64* slots, u64 capmask, u32* __restrict__ slotidx, u32* obits) {
+  u64 p = SPB_GTID();
+  bool valid = p < T && get_bit(vbits, p);
+  bool o = false;
+  if (valid) {
+    u64 ra = T - p - k;
+    o = win_cmp(F, p, R, ra, k) >= 0;
+    const u64* S = o ? F : R;
+    u64 a = o ? p : ra;
+    u64 h = win_hash(S, a, k);
+    u64 idx = h & capmask, tag = h >> 40;
+    u64 entry = (tag << 40) | (p << 1) | (o ? 1ull : 0ull);
+    for (;;) {
+      u64 cur = __ldcg(slots + idx);
+      if (cur == SPB_EMPTY) {
+        cur = atomicCAS(slots + idx, SPB_EMPTY, entry);
+        if (cur == SPB_EMPTY) break;
+      }
+      if ((cur >> 40) == tag) {
+        u64 q = (cur >> 1) & SPB_POSMASK;
+        bool oq = cur & 1;
+        const u64* S2 = oq ? F : R;
+        u64 b = oq ? q : T - q - k;
+        if (q == p || win_cmp(S, a, S2, b, k) == 0) {
+          if (entry < cur) atomicMin(slots + idx, entry);
+          break;
+        }
+      }
+      idx = (idx + 1) & capmask;
+    }
+    slotidx[p] = (u32)idx;
+  }
+  store_bit(obits, p, o);
+}
+
+// K2: representative (first) position of every instance; first-appearance bitmap.
+__global__ void k_first_flags(const u64* __restrict__ slots, u32* __restrict__ rep, const u32* __restrict__ vbits, u64 T, u32* fbits) {
+  u64 p = SPB_GTID();
+  bool valid = p < T && get_bit(vbits, p);
+  bool first = false;
+  if (valid) {
+    u64 cur = __ldcg(slots + rep[p]);
+    u32 r = (u32)((cur >> 1) & SPB_POSMASK);
+    rep[p] = r;
+    first = (r == (u32)p);
+  }
+  store_bit(fbits, p, first);
+}
+
+// per 256-position block: number of first appearances
+__global__ void k_block_counts(const u32* __restrict__ fbits, u32* __restrict__ cnt, u64 nblk) {
+  u64 b = SPB_GTID();
+  if (b >= nblk) return;
+  u32 c = 0;
+  for (u32 j = 0; j < 8; ++j) c += __popc(fbits[b * 8 + j]);
+  cnt[b] = c;
+}
+
+__device__ __forceinline__ u32 rank_first(const u32* fbits, const u32* blkoff, u32 x) {
+  u32 b = x >> 8, w = (x >> 5) & 7;
+  u32 r = __ldg(blkoff + b);
+  for (u32 j = 0; j < w; ++j) r += __popc(__ldg(fbits + b * 8 + j));
+  r += __popc(__ldg(fbits + (x >> 5)) & ((1u << (x & 31)) - 1));
+  return r;
+}
+
+// K3: vertex ids (= rank of the representative among first appearances), vertex -> first position,
+// implicit-edge bit.  `sp` holds rep[] on entry and vertex ids on exit.
+__global__ void k_assign_ids(u32* __restrict__ sp, const u32* __restrict__ vbits, u64 T, const u32* __restrict__ fbits,
+                             const u32* __restrict__ blkoff, u32* __restrict__ v2pos, u8* __restrict__ vflags) {
+  u64 p = SPB_GTID();
+  if (p >= T) return;
+  if (!get_bit(vbits, p)) { sp[p] = SPB_INVALID; return; }
+  u32 r = sp[p];
+  u32 vid = rank_first(fbits, blkoff, r);
+  sp[p] = vid;
+  if (r == (u32)p) {
+    v2pos[vid] = (u32)p;
+    vflags[vid] = get_bit(fbits, p + 1) ? VF_R : 0;   // (p, p+1) both first appearances => edge (vid, vid+1)
+  }
+}
+
+// K4: junction candidates.  The instance pair (p, p+1) yields edge {sp[p], sp[p+1]} (reference
+// lib/Assembler.py:199-201).  It is dropped when it coincides with an implicit edge (v, v+1).
+__global__ void k_junction_emit(const u32* __restrict__ sp, u64 T, const u8* __restrict__ vflags, const u32* __restrict__ v2pos,
+                                const u32* __restrict__ obits, u64* __restrict__ Jk, u8* __restrict__ Js, u64* counter, u64 cap) {
+  u64 p = SPB_GTID();
+  u32 n = 0, u = 0, w = 0;
+  if (p + 1 < T) {
+    u = sp[p]; w = sp[p + 1];
+    if (u != SPB_INVALID && w != SPB_INVALID) {
+      bool implicit = (w == u + 1 && (vflags[u] & VF_R)) || (u == w + 1 && (vflags[w] & VF_R));
+      if (!implicit) n = (u == w) ? 1 : 2;
+    }
+  }
+#ifndef SPB_EMU
+  if (__ballot_sync(0xffffffffu, n != 0) == 0) return;
+#endif
+  u64 slot = list_reserve(counter, n);
+  if (n == 0 || slot + n > cap) return;
+  u32 su = get_bit(obits, p) ^ get_bit(obits, v2pos[u]);       // instance strand vs. vertex' stored k-mer
+  u32 sw = get_bit(obits, p + 1) ^ get_bit(obits, v2pos[w]);
+  u32 side_u = su ? SIDE_L : SIDE_R;                           // where w attaches on u
+  u32 side_w = sw ? SIDE_R : SIDE_L;                           // where u attaches on w
+  Jk[slot] = ((u64)u << 32) | w; Js[slot] = (u8)(side_u | (side_w << 1));
+  if (n == 2) { Jk[slot + 1] = ((u64)w << 32) | u; Js[slot + 1] = (u8)(side_w | (side_u << 1)); }
+}
+
+// heads of runs of equal keys in a sorted u64 array; optionally check that the payload agrees
+__global__ void k_unique_heads(const u64* __restrict__ keys, const u8* __restrict__ pay, u64 n, u32* __restrict__ head, u32* err) {
+  u64 i = SPB_GTID();
+  if (i >= n) return;
+  bool h = (i == 0) || keys[i] != keys[i - 1];
+  head[i] = h ? 1u : 0u;
+  if (!h && pay && pay[i] != pay[i - 1]) atomicOr(err, (u32)ERR_DEGENERATE);
+}
+__global__ void k_unique_scatter(const u64* __restrict__ keys, const u8* __restrict__ pay, u64 n, const u32* __restrict__ head,
+                                 const u32* __restrict__ pos, u64* __restrict__ okeys, u8* __restrict__ opay) {
+  u64 i = SPB_GTID();
+  if (i >= n || !head[i]) return;
+  okeys[pos[i]] = keys[i];
+  if (pay) opay[pos[i]] = pay[i];
+}
+
+// ------------------------------------------------------------------------------------ graph view
+struct GView {
+  const u8* vflags; const u64* Jk; const u8* Js; u32 nJ; u32 nV;
+};
+__device__ __forceinline__ u32 lower_bound_key(const u64* a, u32 n, u64 x) {  // first i with a[i] >= x
+  u32 lo = 0, hi = n;
+  while (lo < hi) { u32 mid = (lo + hi) >> 1; if (__ldg(a + mid) < x) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+__device__ __forceinline__ u32 upper_bound_u32(const u32* a, u32 n, u32 x) {  // first i with a[i] > x
+  u32 lo = 0, hi = n;
+  while (lo < hi) { u32 mid = (lo + hi) >> 1; if (__ldg(a + mid) <= x) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+// f(nbr, side_of_nbr_on_v, side_of_v_on_nbr) for every distinct non-self neighbour of v, in the
+// fixed order: v-1 (implicit), v+1 (implicit), junction neighbours ascending.
+template <class Fn> __device__ __forceinline__ void for_each_nbr(const GView& g, u32 v, Fn f) {
+  u8 fl = g.vflags[v];
+  if (v > 0 && (g.vflags[v - 1] & VF_R)) f(v - 1, (u32)SIDE_L, (u32)SIDE_R);
+  if (fl & VF_R) f(v + 1, (u32)SIDE_R, (u32)SIDE_L);
+  if (fl & VF_HASJ) {
+    u32 i = lower_bound_key(g.Jk, g.nJ, (u64)v << 32);
+    for (; i < g.nJ && (u32)(g.Jk[i] >> 32) == v; ++i) {
+      u32 d = (u32)g.Jk[i]; u32 s = g.Js[i];
+      if (d != v && !(s & JS_CUT)) f(d, s & 1u, (s >> 1) & 1u);
+    }
+  }
+}
+
+__global__ void k_mark_hasj(const u64* __restrict__ Jk, u32 nJ, u8* vflags) {
+  u64 i = SPB_GTID();
+  if (i >= nJ) return;
+  u32 s = (u32)(Jk[i] >> 32);
+  if (i > 0 && (u32)(Jk[i - 1] >> 32) == s) return;
+  atomicOr((u32*)vflags + (s >> 2), (u32)VF_HASJ << ((s & 3) * 8));
+}
+__global__ void k_mark_seqlim(const u64* __restrict__ seq_off, u32 n_seq, u32 k, const u32* __restrict__ sp, u8* vflags, u32* seqlim) {
+  u64 s = SPB_GTID();
+  if (s >= n_seq) return;
+  u64 b = seq_off[s], e = seq_off[s + 1];
+  u32 v0 = SPB_INVALID, v1 = SPB_INVALID;
+  if (e - b > k) {
+    v0 = sp[b]; v1 = sp[e - k];
+    atomicOr((u32*)vflags + (v0 >> 2), (u32)VF_SEQLIM << ((v0 & 3) * 8));
+    atomicOr((u32*)vflags + (v1 >> 2), (u32)VF_SEQLIM << ((v1 & 3) * 8));
+  }
+  seqlim[2 * s] = v0; seqlim[2 * s + 1] = v1;
+}
+
+// K5: init detection (reference lib/Assembler.py:995-1035): init iff #distinct non-self
+// neighbours != 2, or the vertex is a sequence limit and both neighbours attach to the same side.
+__global__ void k_classify(GView g, u8* vflags, u32* err) {
+  u64 v = SPB_GTID();
+  if (v >= g.nV) return;
+  u32 cnt = 0, s0 = 0, s1 = 0;
+  for_each_nbr(g, (u32)v, [&](u32, u32 side, u32) { if (cnt == 0) s0 = side; else if (cnt == 1) s1 = side; ++cnt; });
+  u8 f = g.vflags[v];
+  bool init = cnt != 2;
+  if (!init && s0 == s1) {
+    init = true;
+    if (!(f & VF_SEQLIM)) atomicOr(err, (u32)ERR_DEGENERATE);  // the reference would assert (lib/Assembler.py:1104)
+  }
+  f &= (u8)~(VF_INIT | VF_PSTART | VF_PEND | VF_IN2);
+  if (init) f |= VF_INIT;
+  vflags[v] = f;
+}
+
+__global__ void k_init_degrees(GView g, const u32* __restrict__ init_list, u32 nI, u32* __restrict__ ideg) {
+  u64 i = SPB_GTID();
+  if (i >= nI) return;
+  u32 c = 0;
+  for_each_nbr(g, init_list[i], [&](u32, u32, u32) { ++c; });
+  ideg[i] = c;
+}
+
+// K6: pieces = maximal runs of consecutive-id extender vertices linked by implicit edges.
+__global__ void k_piece_flags(u8* vflags, u32 nV) {
+  u64 v = SPB_GTID();
+  if (v >= nV) return;
+  u8 f = vflags[v];
+  if (f & VF_INIT) return;
+  bool start = !(v > 0 && (vflags[v - 1] & VF_R) && !(vflags[v - 1] & VF_INIT));
+  bool end = !((f & VF_R) && !(vflags[v + 1] & VF_INIT));
+  vflags[v] = f | (start ? VF_PSTART : 0) | (end ? VF_PEND : 0);
+}
+
+// outside neighbours of the two ends of every piece: the neighbour on the LEFT of lo, on the RIGHT of hi
+__global__ void k_piece_ends(GView g, const u32* __restrict__ plo, const u32* __restrict__ phi, u32 nP,
+                             u32* __restrict__ pl_nbr, u8* __restrict__ pl_side, u32* __restrict__ pr_nbr, u8* __restrict__ pr_side, u32* err) {
+  u64 P = SPB_GTID();
+  if (P >= nP) return;
+  u32 ln = SPB_INVALID, rn = SPB_INVALID, ls = 0, rs = 0;
+  for_each_nbr(g, plo[P], [&](u32 n, u32 side, u32 oside) { if (side == SIDE_L) { ln = n; ls = oside; } });
+  for_each_nbr(g, phi[P], [&](u32 n, u32 side, u32 oside) { if (side == SIDE_R) { rn = n; rs = oside; } });
+  if (ln == SPB_INVALID || rn == SPB_INVALID) atomicOr(err, (u32)ERR_DEGENERATE);
+  pl_nbr[P] = ln; pl_side[P] = (u8)ls; pr_nbr[P] = rn; pr_side[P] = (u8)rs;
+}
+
+__device__ __forceinline__ u32 piece_of(const u32* plo, u32 nP, u32 v) { return upper_bound_u32(plo, nP, v) - 1; }
+
+// K7: darts.  d = 2P + dir; dir 0 = "up" (enter at lo from its left, leave hi to its right, vertices in
+// forward orientation), dir 1 = "down".  nxt[d] = following dart or SPB_TERM when the walk reaches an init.
+__global__ void k_dart_next(const u8* __restrict__ vflags, const u32* __restrict__ plo, u32 nP,
+                            const u32* __restrict__ pl_nbr, const u8* __restrict__ pl_side, const u32* __restrict__ pr_nbr,
+                            const u8* __restrict__ pr_side, u32* __restrict__ nxt) {
+  u64 d = SPB_GTID();
+  if (d >= 2ull * nP) return;
+  u32 P = (u32)(d >> 1); bool up = !(d & 1);
+  u32 y = up ? pr_nbr[P] : pl_nbr[P];
+  u32 sy = up ? pr_side[P] : pl_side[P];          // side of y on which we arrive
+  if (y == SPB_INVALID || (vflags[y] & VF_INIT)) { nxt[d] = SPB_TERM; return; }
+  u32 Q = piece_of(plo, nP, y);
+  nxt[d] = 2 * Q + (sy == SIDE_L ? 0u : 1u);       // arriving on y's left => traverse y forward
+}
+
+// list ranking over the predecessor links (synchronous pointer jumping, ping-pong buffers).
+//   ptr[d]  = an ancestor dart, or SPB_TERM once the head of the list is known
+//   acc[d]  = #vertices from that ancestor's first vertex to d's first vertex; absolute rank when resolved
+//   root[d] = head dart (valid when resolved);  mnv[d] = min vertex id seen (used to break pure cycles)
+__global__ void k_rank_init(const u32* __restrict__ nxt, const u32* __restrict__ plo, const u32* __restrict__ phi, u32 nD,
+                            u32* __restrict__ ptr, u32* __restrict__ acc, u32* __restrict__ root, u32* __restrict__ mnv) {
+  u64 d = SPB_GTID();
+  if (d >= nD) return;
+  u32 b = nxt[d ^ 1];
+  if (b == SPB_TERM) { ptr[d] = SPB_TERM; acc[d] = 1; root[d] = (u32)d; }
+  else { u32 pb = b ^ 1; ptr[d] = pb; acc[d] = phi[pb >> 1] - plo[pb >> 1] + 1; root[d] = SPB_TERM; }
+  mnv[d] = plo[d >> 1];
+}
+__global__ void k_rank_jump(u32 nD, const u32* __restrict__ ptr, const u32* __restrict__ acc, const u32* __restrict__ root,
+                            const u32* __restrict__ mnv, u32* __restrict__ optr, u32* __restrict__ oacc, u32* __restrict__ oroot,
+                            u32* __restrict__ omnv) {
+  u64 d = SPB_GTID();
+  if (d >= nD) return;
+  u32 b = ptr[d];
+  if (b == SPB_TERM) { optr[d] = SPB_TERM; oacc[d] = acc[d]; oroot[d] = root[d]; omnv[d] = mnv[d]; return; }
+  optr[d] = ptr[b]; oacc[d] = acc[d] + acc[b]; oroot[d] = root[b];
+  u32 m = mnv[d], mb = mnv[b];
+  omnv[d] = m < mb ? m : mb;
+}
+__global__ void k_count_unresolved(const u32* __restrict__ ptr, u32 nD, u32* cnt) {
+  u64 d = SPB_GTID();
+  if (d >= nD) return;
+  if (ptr[d] != SPB_TERM) atomicAdd(cnt, 1u);
+}
+
+// Pure-cycle components (reference lib/Assembler.py:304-325): a = lowest vertex id of the ring,
+// n0 = its lower-id neighbour; both become inits and the edge (a, n0) is cut.
+__global__ void k_cycle_cut(GView g, u8* vflags, u8* Js, const u32* __restrict__ ptr, const u32* __restrict__ mnv,
+                            const u32* __restrict__ plo, u32 nD, u32* ncyc) {
+  u64 d = SPB_GTID();
+  if (d >= nD || (d & 1)) return;              // one representative: the up-dart of the piece that starts at the minimum
+  if (ptr[d] == SPB_TERM) return;
+  u32 a = plo[d >> 1];
+  if (mnv[d] != a) return;
+  u32 n0 = SPB_INVALID;
+  for_each_nbr(g, a, [&](u32 n, u32, u32) { if (n < n0) n0 = n; });
+  atomicAdd(ncyc, 1u);
+  // mark both ends as cycle inits
+  atomicOr((u32*)vflags + (a >> 2), (u32)(VF_CYC) << ((a & 3) * 8));
+  atomicOr((u32*)vflags + (n0 >> 2), (u32)(VF_CYC) << ((n0 & 3) * 8));
+  if (n0 == a + 1 && (g.vflags[a] & VF_R)) {
+    // implicit edge: clear the R bit (atomic AND via CAS-free trick: only this thread touches bit R of a)
+    u32* wp = (u32*)vflags + (a >> 2);
+    u32 bit = (u32)VF_R << ((a & 3) * 8);
+    u32 old = *wp;
+    while (true) { u32 prev = atomicCAS(wp, old, old & ~bit); if (prev == old) break; old = prev; }
+  } else {
+    u32 i = lower_bound_key(g.Jk, g.nJ, ((u64)a << 32) | n0); Js[i] |= JS_CUT;
+    u32 j = lower_bound_key(g.Jk, g.nJ, ((u64)n0 << 32) | a); Js[j] |= JS_CUT;
+  }
+}
+
+// K10: NBP table.  One raw NBP per (init a, distinct neighbour u) (reference lib/Assembler.py:327-339).
+struct NbpTab {
+  u32* a; u8* aside; u32* b; u8* bside; u32* L; u32* head; u32* last; u8* cyc;
+};
+__global__ void k_nbp_heads(GView g, u8* vflags, const u32* __restrict__ init_list, const u32* __restrict__ ibase, u32 nI,
+                            const u32* __restrict__ plo, u32 nP, NbpTab t, u32* __restrict__ head_nbp) {
+  u64 i = SPB_GTID();
+  if (i >= nI) return;
+  u32 a = init_list[i];
+  u32 id = ibase[i];
+  u8 cyc = (g.vflags[a] & VF_CYC) ? 1 : 0;
+  bool two = false;
+  for_each_nbr(g, a, [&](u32 u, u32 side, u32 oside) {
+    t.a[id] = a; t.aside[id] = (u8)side; t.cyc[id] = cyc;
+    if (g.vflags[u] & VF_INIT) {
+      t.L[id] = 2; t.b[id] = u; t.bside[id] = (u8)oside; t.head[id] = SPB_TERM; t.last[id] = SPB_TERM; two = true;
+    } else {
+      u32 Q = piece_of(plo, nP, u);
+      u32 d = 2 * Q + (oside == SIDE_L ? 0u : 1u);
+      head_nbp[d] = id; t.head[id] = d;
+    }
+    ++id;
+  });
+  if (two || cyc) atomicOr((u32*)vflags + (a >> 2), (u32)VF_IN2 << ((a & 3) * 8));
+}
+__global__ void k_dart_finish(const u32* __restrict__ nxt, const u32* __restrict__ root, const u32* __restrict__ acc,
+                              const u32* __restrict__ plo, const u32* __restrict__ phi, const u32* __restrict__ pl_nbr,
+                              const u8* __restrict__ pl_side, const u32* __restrict__ pr_nbr, const u8* __restrict__ pr_side,
+                              const u32* __restrict__ head_nbp, u32 nD, u32* __restrict__ dart_nbp, NbpTab t) {
+  u64 d = SPB_GTID();
+  if (d >= nD) return;
+  if (root[d] == SPB_TERM) { dart_nbp[d] = SPB_INVALID; return; }   // unresolved (cannot happen after cycle cutting)
+  u32 id = head_nbp[root[d]];
+  dart_nbp[d] = id;
+  if (nxt[d] == SPB_TERM) {
+    u32 P = (u32)(d >> 1); bool up = !(d & 1);
+    t.L[id] = acc[d] + (phi[P] - plo[P] + 1) + 1;
+    t.b[id] = up ? pr_nbr[P] : pl_nbr[P];
+    t.bside[id] = up ? pr_side[P] : pl_side[P];
+    t.last[id] = (u32)d;
+  }
+}
+// per-NBP lengths (vertices / bases) as u64 for the offset scans; cycle NBPs repeat their first vertex
+__global__ void k_nbp_lengths(NbpTab t, u32 nN, u32 k, u64* __restrict__ vlen, u64* __restrict__ slen) {
+  u64 i = SPB_GTID();
+  if (i >= nN) return;
+  u64 L = (u64)t.L[i] + t.cyc[i];
+  vlen[i] = L; slen[i] = L + k - 1;
+}
+
+__device__ __forceinline__ u8 code2ascii(u32 c) { return (u8)("ACGT"[c]); }
+
+// K11: NBP head / tail: first vertex with its k oriented bases, last vertex with its last base.
+__global__ void k_emit_ends(NbpTab t, u32 nN, u32 k, u64 T, const u64* __restrict__ F, const u64* __restrict__ R,
+                            const u32* __restrict__ v2pos, const u64* __restrict__ voff, const u64* __restrict__ soff,
+                            u32* __restrict__ verts, u8* __restrict__ seq) {
+  u32 id = blockIdx.x;
+  if (id >= nN) return;
+  u32 a = t.a[id], b = t.b[id];
+  u64 vo = voff[id], so = soff[id];
+  u32 L = t.L[id];
+  bool afwd = t.aside[id] == SIDE_R;          // second vertex on a's right => a read forward
+  bool bfwd = t.bside[id] == SIDE_L;          // predecessor on b's left  => b read forward
+  u64 pa = v2pos[a], pb = v2pos[b];
+  const u64* S = afwd ? F : R;
+  u64 s0 = afwd ? pa : T - pa - k;
+  for (u32 j = threadIdx.x; j < k; j += blockDim.x) seq[so + j] = code2ascii(base_at(S, s0 + j));
+  if (threadIdx.x == 0) {
+    verts[vo] = a; verts[vo + L - 1] = b;
+    seq[so + k - 1 + (L - 1)] = code2ascii(bfwd ? base_at(F, pb + k - 1) : base_at(R, T - 1 - pb));
+    if (t.cyc[id]) {                            // closing vertex of a broken cycle (reference lib/Assembler.py:341-343)
+      verts[vo + L] = a;
+      seq[so + k - 1 + L] = code2ascii(afwd ? base_at(F, pa + k - 1) : base_at(R, T - 1 - pa));
+    }
+  }
+}
+
+// K12: the bulk of every NBP: the vertices of its darts.  Work is cut into chunks of SPB_CHUNK ranks.
+#define SPB_CHUNK 1024
+__global__ void k_dart_chunks(const u32* __restrict__ plo, const u32* __restrict__ phi, u32 nD, u32* __restrict__ nch) {
+  u64 d = SPB_GTID();
+  if (d >= nD) return;
+  u32 len = phi[d >> 1] - plo[d >> 1] + 1;
+  nch[d] = (len + SPB_CHUNK - 1) / SPB_CHUNK;
+}
+__global__ void SPB_LAUNCH_BOUNDS(256)
+k_emit_darts(const u32* __restrict__ choff, u32 nD, const u32* __restrict__ plo, const u32* __restrict__ phi,
+             const u32* __restrict__ dart_nbp, const u32* __restrict__ acc, u32 k, u64 T, const u64* __restrict__ F,
+             const u64* __restrict__ R, const u32* __restrict__ v2pos, const u64* __restrict__ voff,
+             const u64* __restrict__ soff, u32* __restrict__ verts, u8* __restrict__ seq, u32* __restrict__ vnbp) {
+  u32 c = blockIdx.x;
+  u32 d = upper_bound_u32(choff, nD, c) - 1;
+  u32 P = d >> 1; bool up = !(d & 1);
+  u32 lo = plo[P], hi = phi[P], len = hi - lo + 1;
+  u32 id = dart_nbp[d];
+  u32 un = dart_nbp[d ^ 1]; if (id < un) un = id;
+  u64 vo = voff[id] + acc[d], so = soff[id] + (k - 1) + acc[d];
+  u64 src = up ? (u64)v2pos[lo] + k - 1 : T - 1 - (u64)v2pos[hi];
+  const u64* S = up ? F : R;
+  u32 t0 = (c - choff[d]) * SPB_CHUNK;
+  for (u32 t = t0 + threadIdx.x; t < t0 + SPB_CHUNK && t < len; t += blockDim.x) {
+    u32 v = up ? lo + t : hi - t;
+    verts[vo + t] = v;
+    seq[so + t] = code2ascii(base_at(S, src + t));
+    if (up) vnbp[v] = un;
+  }
+}
+
+// K13: origins.  (undirected NBP, sequence) pairs where the NBP changes along a sequence; (init vertex,
+// sequence) membership pairs for the inits of 2-vertex NBPs (reference lib/Assembler.py:1212-1262).
+__global__ void k_origin_pairs(const u32* __restrict__ sp, u64 T, const u32* __restrict__ vnbp, const u8* __restrict__ vflags,
+                               const u64* __restrict__ seq_off, u32 n_seq, u64* __restrict__ opairs, u64* ocount, u64 ocap,
+                               u64* __restrict__ mpairs, u64* mcount, u64 mcap, u8* __restrict__ has01) {
+  u64 p = SPB_GTID();
+  if (p >= T) return;
+  u32 v = sp[p];
+  if (v == SPB_INVALID) return;
+  u32 c = vnbp[v];
+  bool in2 = (vflags[v] & VF_IN2) != 0;
+  u32 prev = SPB_INVALID;
+  bool pfirst = true;
+  if (p > 0) { u32 pv = sp[p - 1]; if (pv != SPB_INVALID) { prev = vnbp[pv]; pfirst = false; } }
+  bool emit_o = (c != SPB_INVALID) && (pfirst || c != prev);
+  if (!emit_o && !in2 && v > 1) return;
+  u32 s = upper_bound_u64(seq_off, n_seq + 1, p) - 1;
+  if (v <= 1) has01[2 * s + v] = 1;
+  if (emit_o) { u64 i = atomicAdd(ocount, 1ull); if (i < ocap) opairs[i] = ((u64)c << 32) | s; }
+  if (in2) { u64 i = atomicAdd(mcount, 1ull); if (i < mcap) mpairs[i] = ((u64)v << 32) | s; }
+}
+// compress_vertices leading-zero quirk (reference lib/vtools.pyx:29-45): a sequence whose smallest
+// vertex id is 1 is recorded as containing vertex 0 as well.
+__global__ void k_origin_quirk(const u8* __restrict__ has01, u32 n_seq, const u32* __restrict__ vnbp, const u8* __restrict__ vflags,
+                               u64* __restrict__ opairs, u64* ocount, u64 ocap, u64* __restrict__ mpairs, u64* mcount, u64 mcap) {
+  u64 s = SPB_GTID();
+  if (s >= n_seq) return;
+  if (!(has01[2 * s + 1] && !has01[2 * s])) return;
+  u32 c = vnbp[0];
+  if (c != SPB_INVALID) { u64 i = atomicAdd(ocount, 1ull); if (i < ocap) opairs[i] = ((u64)c << 32) | s; }
+  if (vflags[0] & VF_IN2) { u64 i = atomicAdd(mcount, 1ull); if (i < mcap) mpairs[i] = (u64)s; }
+}
+
+__device__ __forceinline__ void key_range(const u64* keys, u32 n, u32 hi32, u32* lo, u32* hi) {
+  *lo = lower_bound_key(keys, n, (u64)hi32 << 32);
+  *hi = lower_bound_key(keys, n, ((u64)hi32 << 32) | 0xFFFFFFFFull);
+  if (*hi < n && keys[*hi] == (((u64)hi32 << 32) | 0xFFFFFFFFull)) ++*hi;
+}
+// merge-count / merge-write of two sorted u32-suffix lists: union (mode 0) or intersection (mode 1)
+__device__ __forceinline__ u32 merge_lists(const u64* A, u32 a0, u32 a1, const u64* B, u32 b0, u32 b1, int mode, u32* out) {
+  u32 n = 0;
+  while (a0 < a1 || b0 < b1) {
+    u32 x = a0 < a1 ? (u32)A[a0] : 0xFFFFFFFFu, y = b0 < b1 ? (u32)B[b0] : 0xFFFFFFFFu;
+    if (a0 < a1 && b0 < b1 && x == y) { if (out) out[n] = x; ++n; ++a0; ++b0; }
+    else if (b0 >= b1 || (a0 < a1 && x < y)) { if (mode == 0) { if (out) out[n] = x; ++n; } ++a0; }
+    else { if (mode == 0) { if (out) out[n] = y; ++n; } ++b0; }
+  }
+  return n;
+}
+// per-NBP origin lists.  L >= 3: sequences touching an interior vertex; cycle NBPs also count their
+// last init (it is interior once the first vertex is appended); L == 2: sequences containing both.
+__global__ void k_nbp_origins(NbpTab t, u32 nN, const u32* __restrict__ dart_nbp, const u64* __restrict__ opairs, u32 nO,
+                              const u64* __restrict__ mpairs, u32 nM, const u64* __restrict__ ooff, u64* __restrict__ ocnt,
+                              u32* __restrict__ out) {
+  u64 id = SPB_GTID();
+  if (id >= nN) return;
+  u32* dst = out ? out + ooff[id] : nullptr;
+  u32 n;
+  if (t.head[id] == SPB_TERM) {
+    u32 a0, a1, b0, b1;
+    key_range(mpairs, nM, t.a[id], &a0, &a1); key_range(mpairs, nM, t.b[id], &b0, &b1);
+    n = merge_lists(mpairs, a0, a1, mpairs, b0, b1, 1, dst);
+  } else {
+    u32 un = dart_nbp[t.head[id]], rv = dart_nbp[t.last[id] ^ 1];
+    if (rv < un) un = rv;
+    u32 a0, a1, b0 = 0, b1 = 0;
+    key_range(opairs, nO, un, &a0, &a1);
+    if (t.cyc[id]) key_range(mpairs, nM, t.b[id], &b0, &b1);
+    n = merge_lists(opairs, a0, a1, mpairs, b0, b1, 0, dst);
+  }
+  if (!out) ocnt[id] = n;
+}
+
+// K14: connected components = union-find over inits, one union per NBP (a, b).
+__device__ __forceinline__ u32 uf_find(u32* parent, u32 x) {
+  while (true) { u32 p = parent[x]; if (p == x) return x; u32 gp = parent[p]; if (gp != p) parent[x] = gp; x = p; }
+}
+__device__ __forceinline__ u32 lower_bound_u32(const u32* a, u32 n, u32 x) {
+  u32 lo = 0, hi = n;
+  while (lo < hi) { u32 mid = (lo + hi) >> 1; if (__ldg(a + mid) < x) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+__global__ void k_uf_init(u32* parent, u32 n) { u64 i = SPB_GTID(); if (i < n) parent[i] = (u32)i; }
+__global__ void k_uf_union(NbpTab t, u32 nN, const u32* __restrict__ init_list, u32 nI, u32* parent) {
+  u64 id = SPB_GTID();
+  if (id >= nN) return;
+  u32 x = lower_bound_u32(init_list, nI, t.a[id]), y = lower_bound_u32(init_list, nI, t.b[id]);
+  while (true) {
+    x = uf_find(parent, x); y = uf_find(parent, y);
+    if (x == y) break;
+    if (x > y) { u32 z = x; x = y; y = z; }
+    if (atomicCAS(parent + y, y, x) == y) break;     // hook the larger root under the smaller
+  }
+}
+// component minimum vertex (may be an extender): inits contribute themselves, pieces their lowest vertex
+__global__ void k_comp_min_init(const u32* __restrict__ init_list, u32 nI, u32* parent, u32* cmin) {
+  u64 i = SPB_GTID();
+  if (i >= nI) return;
+  u32 r = uf_find(parent, (u32)i);
+  atomicMin(cmin + r, init_list[i]);
+}
+__global__ void k_comp_min_piece(const u32* __restrict__ plo, u32 nP, const u32* __restrict__ dart_nbp, NbpTab t,
+                                 const u32* __restrict__ init_list, u32 nI, u32* parent, u32* cmin) {
+  u64 P = SPB_GTID();
+  if (P >= nP) return;
+  u32 a = t.a[dart_nbp[2 * P]];
+  u32 r = uf_find(parent, lower_bound_u32(init_list, nI, a));
+  atomicMin(cmin + r, plo[P]);
+}
+__global__ void k_comp_roots(u32* parent, const u32* __restrict__ cmin, u32 nI, u64* __restrict__ rootkeys, u32* nroots) {
+  u64 i = SPB_GTID();
+  if (i >= nI) return;
+  if (parent[i] == (u32)i) { u32 j = atomicAdd(nroots, 1u); rootkeys[j] = ((u64)cmin[i] << 32) | (u32)i; }
+}
+__global__ void k_comp_labels(const u64* __restrict__ rootkeys, u32 nroots, u32* __restrict__ label_of_root) {
+  u64 j = SPB_GTID();
+  if (j >= nroots) return;
+  label_of_root[(u32)rootkeys[j]] = (u32)j;
+}
+__global__ void k_nbp_comp(NbpTab t, u32 nN, const u32* __restrict__ init_list, u32 nI, u32* parent,
+                           const u32* __restrict__ label_of_root, int32_t* __restrict__ nbp_comp) {
+  u64 id = SPB_GTID();
+  if (id >= nN) return;
+  nbp_comp[id] = (int32_t)label_of_root[uf_find(parent, lower_bound_u32(init_list, nI, t.a[id]))];
+}
+__global__ void k_vertex_comp(const u8* __restrict__ vflags, u32 nV, const u32* __restrict__ vnbp, const u32* __restrict__ init_list,
+                              u32 nI, u32* parent, const u32* __restrict__ label_of_root, const int32_t* __restrict__ nbp_comp,
+                              int32_t* __restrict__ out) {
+  u64 v = SPB_GTID();
+  if (v >= nV) return;
+  if (vflags[v] & VF_INIT) out[v] = (int32_t)label_of_root[uf_find(parent, lower_bound_u32(init_list, nI, (u32)v))];
+  else out[v] = nbp_comp[vnbp[v]];
+}
+
+// ------------------------------------------------------------------------------------ getters
+__global__ void k_coords(const u32* __restrict__ v2pos, u32 nV, const u64* __restrict__ seq_off, u32 n_seq, u32* __restrict__ out) {
+  u64 v = SPB_GTID();
+  if (v >= nV) return;
+  u64 p = v2pos[v];
+  u32 s = upper_bound_u64(seq_off, n_seq + 1, p) - 1;
+  out[2 * v] = s; out[2 * v + 1] = (u32)(p - seq_off[s]);
+}
+
+// explicit edge list (reference lib/Assembler.py:247-249): per vertex v the rows (v, x), x >= v:
+// self-loop first, then the implicit (v, v+1), then junction neighbours above v.
+__global__ void k_edge_counts(GView g, u32* __restrict__ cnt) {
+  u64 v = SPB_GTID();
+  if (v >= g.nV) return;
+  u8 fl = g.vflags[v];
+  u32 c = (fl & VF_R) ? 1 : 0;
+  if (fl & VF_HASJ) {
+    u32 i = lower_bound_key(g.Jk, g.nJ, ((u64)v << 32) | v);
+    for (; i < g.nJ && (u32)(g.Jk[i] >> 32) == v; ++i) ++c;
+  }
+  cnt[v] = c;
+}
+__global__ void k_edge_write(GView g, const u32* __restrict__ off, u32* __restrict__ edges) {
+  u64 v = SPB_GTID();
+  if (v >= g.nV) return;
+  u8 fl = g.vflags[v];
+  u64 o = off[v];
+  bool r = (fl & VF_R) != 0;
+  if (fl & VF_HASJ) {
+    u32 i = lower_bound_key(g.Jk, g.nJ, ((u64)v << 32) | v);
+    for (; i < g.nJ && (u32)(g.Jk[i] >> 32) == v; ++i) {
+      u32 d = (u32)g.Jk[i];
+      if (r && d > v + 1) { edges[2 * o] = (u32)v; edges[2 * o + 1] = (u32)v + 1; ++o; r = false; }
+      edges[2 * o] = (u32)v; edges[2 * o + 1] = d; ++o;
+    }
+  }
+  if (r) { edges[2 * o] = (u32)v; edges[2 * o + 1] = (u32)v + 1; }
+}
+
+// seqPaths (reference lib/vtools.pyx:18-49).  Along a sequence the vertex ids form monotone runs with
+// step +1 or -1; a run boundary lies before p when p opens its sequence, the step is not +-1, or
+// the direction changes.  Run starts and run ends are compacted separately (order preserving), so
+// the i-th start pairs with the i-th end.
+__device__ __forceinline__ int run_step(const u32* sp, u64 p) {   // step from p-1 to p: +1, -1, or 0 (= boundary)
+  if (p == 0) return 0;
+  u32 a = sp[p - 1], b = sp[p];
+  if (a == SPB_INVALID || b == SPB_INVALID) return 0;
+  return (b == a + 1) ? 1 : (a == b + 1) ? -1 : 0;
+}
+__device__ __forceinline__ bool run_boundary(const u32* sp, u64 p) {  // true if a run starts at p (sp[p] valid)
+  int s = run_step(sp, p);
+  if (s == 0) return true;
+  int s1 = run_step(sp, p - 1);
+  return s1 != 0 && s1 != s;
+}
+__global__ void k_run_flags(const u32* __restrict__ sp, u64 T, u8* __restrict__ flags) {
+  u64 p = SPB_GTID();
+  if (p >= T) return;
+  u8 f = 0;
+  if (sp[p] != SPB_INVALID) {
+    if (run_boundary(sp, p)) f |= 1;
+    if (p + 1 >= T || sp[p + 1] == SPB_INVALID || run_boundary(sp, p + 1)) f |= 2;
+  }
+  flags[p] = f;
+}
+__global__ void k_run_intervals(const u32* __restrict__ sp, const u32* __restrict__ rs, const u32* __restrict__ re, u32 nR,
+                                const u64* __restrict__ seq_off, u32 n_seq, u64* __restrict__ key, u64* __restrict__ val) {
+  u64 i = SPB_GTID();
+  if (i >= nR) return;
+  u32 a = sp[rs[i]], b = sp[re[i]];
+  u32 lo = a < b ? a : b, hi = a < b ? b : a;
+  u64 s = upper_bound_u64(seq_off, n_seq + 1, rs[i]) - 1;
+  key[i] = (s << 32) | lo; val[i] = (s << 32) | hi;
+}
+// after sorting by (seq, lo) and a segmented running max of hi: interval heads
+__global__ void k_interval_heads(const u64* __restrict__ key, const u64* __restrict__ runmax, u32 nR, u32* __restrict__ head) {
+  u64 i = SPB_GTID();
+  if (i >= nR) return;
+  bool h = (i == 0) || (key[i] >> 32) != (key[i - 1] >> 32) || (u32)key[i] > (u32)runmax[i - 1] + 1;
+  head[i] = h ? 1u : 0u;
+}
+__global__ void k_interval_write(const u64* __restrict__ key, const u64* __restrict__ runmax, u32 nR, const u32* __restrict__ head,
+                                 const u32* __restrict__ pos, u32* __restrict__ iv, u32* __restrict__ iv_seq) {
+  u64 i = SPB_GTID();
+  if (i >= nR) return;
+  if (head[i]) {
+    u32 lo = (u32)key[i];
+    bool first_of_seq = (i == 0) || (key[i] >> 32) != (key[i - 1] >> 32);
+    if (first_of_seq && lo <= 1) lo = 0;          // compress_vertices `last = cs = 0` quirk (lib/vtools.pyx:29-38)
+    iv[2 * (u64)pos[i]] = lo; iv_seq[pos[i]] = (u32)(key[i] >> 32);
+  }
+  bool last = (i + 1 == nR) || head[i + 1];
+  if (last) iv[2 * (u64)(head[i] ? pos[i] : pos[i] - 1) + 1] = (u32)runmax[i];   // pos = exclusive scan of head
+}
+__global__ void k_interval_offsets(const u32* __restrict__ iv_seq, u32 nIv, u32 n_seq, u64* __restrict__ off) {
+  // off[s] = first interval row of sequence s (rows are grouped by sequence, ascending)
+  u64 s = SPB_GTID();
+  if (s > n_seq) return;
+  off[s] = lower_bound_u32(iv_seq, nIv, (u32)s);
+}

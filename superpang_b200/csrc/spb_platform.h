@@ -1,0 +1,58 @@
+// superpang_b200 -- platform layer.
+//
+// The library is CUDA for sm_100a.  The same kernel sources can ALSO be compiled by g++ with
+// -DSPB_EMU, where every "kernel" is executed thread-by-thread on the host.  That build
+// (tests/emu/libspb_emu.so) exists only so that the CPU-only CI tier (`pytest -m "not gpu"`) can
+// check the kernels' *logic* against the oracle; it is never built into, or loaded by, the product
+// package, which fails loudly when libsuperpang_b200.so (the nvcc build) is missing.
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <cstring>
+#include <cstdlib>
+
+typedef unsigned long long u64;
+static unsigned long long g_spb_launches = 0;   // number of this library's own kernel launches (host side)
+typedef uint32_t u32;
+typedef uint8_t u8;
+
+#ifdef SPB_EMU
+// ---------------------------------------------------------------- host emulation of the kernels
+#include <algorithm>
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define SPB_LAUNCH_BOUNDS(n)
+struct spb_emu_dim3 { unsigned x = 1, y = 1, z = 1; };
+static spb_emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+typedef void* spb_stream_t;
+template <class F> static inline void spb_emu_launch(size_t nb, unsigned nt, F f) {
+  gridDim.x = (unsigned)nb; blockDim.x = nt;
+  for (size_t b = 0; b < nb; ++b) { blockIdx.x = (unsigned)b; for (unsigned t = 0; t < nt; ++t) { threadIdx.x = t; f(); } }
+}
+#define SPB_LAUNCH(K, NB, NT, STREAM, ...) \
+  do { if ((NB) > 0) { ++g_spb_launches; spb_emu_launch((size_t)(NB), (unsigned)(NT), [&]() { K(__VA_ARGS__); }); } } while (0)
+static inline u64 atomicCAS(u64* a, u64 cmp, u64 val) { u64 o = *a; if (o == cmp) *a = val; return o; }
+static inline u32 atomicCAS(u32* a, u32 cmp, u32 val) { u32 o = *a; if (o == cmp) *a = val; return o; }
+static inline u64 atomicMin(u64* a, u64 v) { u64 o = *a; if (v < o) *a = v; return o; }
+static inline u32 atomicMin(u32* a, u32 v) { u32 o = *a; if (v < o) *a = v; return o; }
+static inline u64 atomicAdd(u64* a, u64 v) { u64 o = *a; *a = o + v; return o; }
+static inline u32 atomicAdd(u32* a, u32 v) { u32 o = *a; *a = o + v; return o; }
+static inline u32 atomicOr(u32* a, u32 v) { u32 o = *a; *a = o | v; return o; }
+static inline int __popcll(u64 x) { return __builtin_popcountll(x); }
+static inline int __popc(u32 x) { return __builtin_popcount(x); }
+template <class T> static inline T __ldg(const T* p) { return *p; }
+template <class T> static inline T __ldcg(const T* p) { return *p; }
+#else
+// ---------------------------------------------------------------- CUDA (sm_100a)
+#include <cuda_runtime.h>
+#define SPB_LAUNCH_BOUNDS(n) __launch_bounds__(n)
+typedef cudaStream_t spb_stream_t;
+#define SPB_LAUNCH(K, NB, NT, STREAM, ...) \
+  do { if ((NB) > 0) { ++g_spb_launches; K<<<(unsigned)(NB), (unsigned)(NT), 0, (STREAM)>>>(__VA_ARGS__); } } while (0)
+#endif
+
+// global linear thread id (64-bit)
+#define SPB_GTID() ((u64)blockIdx.x * blockDim.x + threadIdx.x)

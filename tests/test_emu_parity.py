@@ -1,0 +1,90 @@
+"""CPU tier: the CUDA kernels' LOGIC, executed by the host emulator build (tests/emu, -DSPB_EMU),
+against the reference goldens and the oracle.  The emulator is test infrastructure; the product
+never loads it.  The `-m gpu` tier runs the same checks through the real sm_100a library."""
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+import dbg_oracle
+import digests
+import helpers
+from superpang_b200 import _capi
+from superpang_b200.assembler import Assembler
+
+
+def run_emu(emu_lib, seqdict, k):
+    return Assembler(dict(seqdict), k, engine=_capi.Engine(lib=emu_lib))
+
+
+@pytest.mark.parametrize("case", helpers.load_crafted(), ids=lambda c: f"{c['name']}-k{c['k']}")
+def test_emu_matches_reference_golden(emu_lib, case):
+    A = run_emu(emu_lib, dict(map(tuple, case["records"])), case["k"])
+    got = A.to_result()
+    digests.assert_same(helpers.golden_to_result(case), got)
+    helpers.assert_summary(digests.summarize(got), case["summary"])
+
+
+@pytest.mark.parametrize("case", helpers.load_json("synthetic.json")["cases"],
+                         ids=lambda c: f"{c['mode']}-seed{c['seed']}-k{c['k']}")
+def test_emu_matches_reference_synthetic(emu_lib, case):
+    sd = helpers.synth_seqdict(case["n_genomes"], case["length"], case["ani"], case["seed"], case["mode"])
+    helpers.assert_summary(digests.summarize(run_emu(emu_lib, sd, case["k"]).to_result()), case["summary"])
+
+
+def test_emu_matches_reference_real_slice(emu_lib):
+    want = helpers.load_json("real_slice.json")
+    got = digests.summarize(run_emu(emu_lib, helpers.real_slice_records(), want["k"]).to_result())
+    helpers.assert_summary(got, want["summary"])
+
+
+_COMP = str.maketrans("ACGT", "TGCA")
+
+
+@st.composite
+def genome_sets(draw):
+    """Small random pangenomes built from shared blocks, inversions, duplications and point edits:
+    planted branches, tips, loops, shared ends and repeats."""
+    rng = np.random.default_rng(draw(st.integers(0, 2**32 - 1)))
+    nblocks = draw(st.integers(2, 6))
+    blocks = ["".join("ACGT"[c] for c in rng.integers(0, 4, int(rng.integers(20, 120)))) for _ in range(nblocks)]
+    nseq = draw(st.integers(1, 5))
+    seqs = {}
+    for i in range(nseq):
+        parts = []
+        for _ in range(int(rng.integers(1, 6))):
+            b = blocks[int(rng.integers(0, nblocks))]
+            if rng.random() < 0.3:
+                b = b.translate(_COMP)[::-1]
+            if rng.random() < 0.3:
+                j = int(rng.integers(0, len(b)))
+                b = b[:j] + "ACGT"[int(rng.integers(0, 4))] + b[j + 1:]
+            parts.append(b)
+        s = "".join(parts)
+        if rng.random() < 0.15:
+            s = s + s[:int(rng.integers(1, 40))]
+        seqs[f"s{i}"] = s
+    return seqs
+
+
+@settings(max_examples=120, deadline=None, suppress_health_check=list(HealthCheck))
+@given(genome_sets(), st.sampled_from([9, 15, 21, 31]))
+def test_emu_matches_oracle_random(emu_lib, seqs, k):
+    try:
+        want = dbg_oracle.run_oracle(seqs, k)
+    except (AssertionError, IndexError):
+        # degenerate input: the reference itself asserts; the product must refuse, not differ
+        with pytest.raises(_capi.SpbError):
+            run_emu(emu_lib, seqs, k).to_result()
+        return
+    if not want["vertex2coords"].shape[0]:
+        return
+    digests.assert_same(want, run_emu(emu_lib, seqs, k).to_result())
+
+
+def test_rejects_bad_input(emu_lib):
+    with pytest.raises(_capi.SpbError):
+        run_emu(emu_lib, {"a": "ACGT" * 20}, 30)           # even k
+    with pytest.raises(_capi.SpbError):
+        run_emu(emu_lib, {"a": "ACGTRYACGT" * 10}, 9)       # non-ACGT reaches the device
+    with pytest.raises(NotImplementedError):
+        Assembler({"a": "ACGT" * 20}, 9, gap_size=2, engine=_capi.Engine(lib=emu_lib))

@@ -1,0 +1,130 @@
+"""GPU tier (`-m gpu`): the product path -- libsuperpang_b200.so (sm_100a) through the C-ABI -- against the
+reference goldens, the oracle on seeded inputs, the KAT digests of the bundled genomes, and
+size-independent properties at benchmark scale.  Bit-exact: integer / byte work only."""
+import os
+
+import numpy as np
+import pytest
+
+import dbg_oracle
+import digests
+import helpers
+from superpang_b200 import _capi, synth
+from superpang_b200.assembler import Assembler, read_fasta
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gpu(seqdict, k):
+    A = Assembler(seqdict, k, device=0)
+    assert A._eng.kind == "cuda sm_100a"
+    return A
+
+
+@pytest.mark.parametrize("case", helpers.load_crafted(), ids=lambda c: f"{c['name']}-k{c['k']}")
+def test_gpu_matches_reference_golden(case):
+    got = run_gpu(dict(map(tuple, case["records"])), case["k"]).to_result()
+    digests.assert_same(helpers.golden_to_result(case), got)
+    helpers.assert_summary(digests.summarize(got), case["summary"])
+
+
+@pytest.mark.parametrize("case", helpers.load_json("synthetic.json")["cases"],
+                         ids=lambda c: f"{c['mode']}-seed{c['seed']}-k{c['k']}")
+def test_gpu_matches_reference_synthetic(case):
+    sd = helpers.synth_seqdict(case["n_genomes"], case["length"], case["ani"], case["seed"], case["mode"])
+    helpers.assert_summary(digests.summarize(run_gpu(sd, case["k"]).to_result()), case["summary"])
+
+
+def test_gpu_matches_reference_real_slice():
+    want = helpers.load_json("real_slice.json")
+    helpers.assert_summary(digests.summarize(run_gpu(helpers.real_slice_records(), want["k"]).to_result()), want["summary"])
+
+
+@pytest.mark.parametrize("mode,k", [("block", 301), ("snp", 301), ("block", 101), ("block", 501)])
+def test_gpu_matches_oracle_medium(mode, k):
+    """~0.4 M instances: field-by-field against the oracle."""
+    sd = helpers.synth_seqdict(6, 70000, 0.96, 31, mode)
+    digests.assert_same(dbg_oracle.run_oracle(sd, k), run_gpu(sd, k).to_result())
+
+
+@pytest.mark.parametrize("which", ["A", "B"])
+def test_gpu_kat_bundled_genomes(which):
+    """KAT digests of the reference's bundled genomes; data staged by build()."""
+    fa = os.path.join(helpers.DATA, f"{which}.fa")
+    if not os.path.exists(fa):
+        pytest.skip("tests/_data not staged (reference test data absent at build time)")
+    A = Assembler(fa, 301, device=0)
+    helpers.assert_summary(digests.summarize(A.to_result()), helpers.load_json(f"kat_{which}.json"))
+
+
+def _codes(s):
+    lut = np.zeros(256, np.uint8)
+    lut[list(b"ACGT")] = [0, 1, 2, 3]
+    return lut[np.frombuffer(s.encode() if isinstance(s, str) else s, dtype=np.uint8)]
+
+
+@pytest.mark.parametrize("mode", ["snp", "block"])
+def test_gpu_properties_at_scale(mode):
+    """BASELINE config 2 (10 genomes x 2 Mbp, k=301): properties that do not need the oracle."""
+    k = 301
+    names, seqs = synth.genome_set(10, 2_000_000, 0.97, seed=1, mode=mode)
+    eng = _capi.Engine(device=0)
+    from superpang_b200.assembler import concat_sequences
+    buf, off = concat_sequences(seqs)
+    eng.load(buf, off, k)
+    c = eng.build_dbg()
+    c = eng.compact()
+    assert c["n_inst"] == synth.n_instances(seqs, k)
+    sp = eng.instance_vertices()
+    v2c = eng.vertex2coords()
+    valid = sp != _capi.SPB_NONE
+    assert int(valid.sum()) == c["n_inst"]
+    # vertex ids = order of first appearance: first occurrence positions are strictly increasing
+    lin = off[v2c[:, 0].astype(np.int64)].astype(np.int64) + v2c[:, 1].astype(np.int64)
+    assert np.all(np.diff(lin) > 0)
+    assert np.array_equal(sp[lin], np.arange(c["n_vertices"], dtype=np.uint32))
+    assert int(sp[valid].max()) == c["n_vertices"] - 1
+    # edges: exactly the unique unordered consecutive-instance pairs
+    pair = valid[:-1] & valid[1:]
+    a, b = sp[:-1][pair].astype(np.uint64), sp[1:][pair].astype(np.uint64)
+    key = np.unique((np.minimum(a, b) << np.uint64(32)) | np.maximum(a, b))
+    e = eng.edges().astype(np.uint64)
+    assert np.array_equal((e[:, 0] << np.uint64(32)) | e[:, 1], key)
+    # NBPs: every vertex is an init (end of its NBPs) or interior to exactly one NBP pair
+    voff, verts, comp, cyc = eng.nbps()
+    soff, sq = eng.nbp_seqs()
+    assert np.all((soff[1:] - soff[:-1]) == (voff[1:] - voff[:-1]) + np.uint64(k - 1))
+    L = (voff[1:] - voff[:-1]).astype(np.int64)
+    interior = np.ones(verts.size, bool)
+    interior[voff[:-1].astype(np.int64)] = False
+    interior[voff[1:].astype(np.int64) - 1] = False
+    cnt = np.bincount(verts[interior], minlength=c["n_vertices"])
+    assert set(np.unique(cnt)) <= {0, 2}
+    ends = np.zeros(c["n_vertices"], bool)
+    ends[verts[~interior]] = True
+    assert np.all(ends | (cnt == 2))
+    # reverse-complement closure of the NBP sequence multiset (by hash)
+    import hashlib
+    comp_tab = bytes.maketrans(b"ACGT", b"TGCA")
+    sb = sq.tobytes()
+    hs, hr = [], []
+    for i in range(len(L)):
+        s = sb[int(soff[i]):int(soff[i + 1])]
+        hs.append(hashlib.sha1(s).digest())
+        hr.append(hashlib.sha1(s.translate(comp_tab)[::-1]).digest())
+    assert sorted(hs) == sorted(hr)
+    # a sample of NBPs re-k-merises to exactly its vertices (canonical k-mer of the vertex' first appearance)
+    rng = np.random.default_rng(0)
+    allseq = np.concatenate(seqs)
+    for i in rng.choice(len(L), size=min(40, len(L)), replace=False):
+        s = np.frombuffer(sb[int(soff[i]):int(soff[i + 1])], dtype=np.uint8)
+        vs = verts[int(voff[i]):int(voff[i + 1])]
+        for r in rng.choice(len(vs), size=min(25, len(vs)), replace=False):
+            km = s[r:r + k].tobytes()
+            p = int(lin[vs[r]])
+            ref = allseq[p:p + k].tobytes()
+            assert km == ref or km == ref.translate(comp_tab)[::-1]
+    # origins are non-empty, sorted, in range
+    ooff, oidx = eng.nbp_origins()
+    assert np.all(ooff[1:] > ooff[:-1])
+    assert int(oidx.max()) < len(seqs)
