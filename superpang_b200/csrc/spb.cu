@@ -10,6 +10,7 @@
 #include <vector>
 #include <string>
 #include <algorithm>
+#include <map>
 
 #ifndef SPB_EMU
 #include <cub/cub.cuh>
@@ -25,10 +26,12 @@ struct spb_ctx {
   u64 T = 0, n_inst = 0, npos_pad = 0, nw = 0;
   std::vector<u64> seq_off_h;
   spb_counts cnt;
-  std::vector<void*> owned;            // every live device allocation (freed in destroy)
+  std::map<void*, u64> live;           // live device blocks -> size
+  std::multimap<u64, void*> cache;     // freed blocks kept for reuse (steady state: no cudaMalloc at all)
+  u64* pinned = 0;                     // pinned host scratch for scalar read-backs
   // ---- persistent device state
-  u64 *F = 0, *R = 0, *seq_off = 0;
-  u32 *vbits = 0, *obits = 0, *fbits = 0, *sp = 0, *v2pos = 0, *seqlim = 0, *errflag = 0;
+  u64* seq_off = 0;
+  u32 *F = 0, *R = 0, *vbits = 0, *obits = 0, *fbits = 0, *sp = 0, *v2pos = 0, *seqlim = 0, *errflag = 0;
   u8* vflags = 0;
   u32 nV = 0, nJ = 0;
   u64* Jk = 0; u8* Js = 0;
@@ -50,20 +53,20 @@ static int fail(spb_ctx* c, int code, const char* fmt, ...) {
 
 #ifdef SPB_EMU
 #define CK(x) do { (void)(x); } while (0)
-static void* dev_alloc_raw(spb_ctx*, u64 bytes) { return malloc(bytes ? bytes : 1); }
-static void dev_free_raw(spb_ctx*, void* p) { free(p); }
+static void* backend_alloc(u64 bytes) { return malloc(bytes); }
+static void backend_free(void* p) { free(p); }
 static void dev_memset(spb_ctx*, void* p, int v, u64 bytes) { memset(p, v, bytes); }
 static void dev_copy(spb_ctx*, void* dst, const void* src, u64 bytes) { memcpy(dst, src, bytes); }
 static void dev_sync(spb_ctx*) {}
 struct StageTimer { void start(spb_ctx*) {} float stop(spb_ctx*) { return 0.f; } };
 #else
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(c, SPB_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); } while (0)
-static void* dev_alloc_raw(spb_ctx* c, u64 bytes) {
+static void* backend_alloc(u64 bytes) {
   void* p = nullptr;
-  if (cudaMallocAsync(&p, bytes ? bytes : 1, c->stream) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   return p;
 }
-static void dev_free_raw(spb_ctx* c, void* p) { cudaFreeAsync(p, c->stream); }
+static void backend_free(void* p) { cudaFree(p); }
 static void dev_memset(spb_ctx* c, void* p, int v, u64 bytes) { cudaMemsetAsync(p, v, bytes, c->stream); }
 static void dev_copy(spb_ctx* c, void* dst, const void* src, u64 bytes) { cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, c->stream); }
 static void dev_sync(spb_ctx* c) { cudaStreamSynchronize(c->stream); }
@@ -75,20 +78,47 @@ struct StageTimer {
 };
 #endif
 
-template <class T> static T* dalloc(spb_ctx* c, u64 n) {
-  void* p = dev_alloc_raw(c, n * sizeof(T) + 64);
-  if (p) c->owned.push_back(p);
-  return (T*)p;
+// Caching block allocator.  Every buffer of the pipeline is used on the context's single stream, so a
+// freed block can be handed out again immediately (stream order == program order).  After the first
+// pass over a workload the allocation sequence repeats exactly and no cudaMalloc / cudaFree happens.
+static void cache_release(spb_ctx* c) {
+  for (auto& kv : c->cache) backend_free(kv.second);
+  c->cache.clear();
 }
+static void* dev_alloc_raw(spb_ctx* c, u64 bytes) {
+  bytes = (std::max<u64>(bytes, 1) + 511) & ~511ull;
+  auto it = c->cache.lower_bound(bytes);
+  if (it != c->cache.end() && it->first <= bytes + bytes / 4 + (1u << 20)) {
+    void* p = it->second; u64 sz = it->first;
+    c->cache.erase(it);
+    c->live[p] = sz;
+    return p;
+  }
+  void* p = backend_alloc(bytes);
+  if (!p) { dev_sync(c); cache_release(c); p = backend_alloc(bytes); }
+  if (p) c->live[p] = bytes;
+  return p;
+}
+static void dev_free_raw(spb_ctx* c, void* p) {
+  auto it = c->live.find(p);
+  if (it == c->live.end()) return;
+  c->cache.insert({it->second, p});
+  c->live.erase(it);
+}
+
+template <class T> static T* dalloc(spb_ctx* c, u64 n) { return (T*)dev_alloc_raw(c, n * sizeof(T) + 64); }
 template <class T> static void dfree(spb_ctx* c, T*& p) {
   if (!p) return;
-  auto it = std::find(c->owned.begin(), c->owned.end(), (void*)p);
-  if (it != c->owned.end()) { *it = c->owned.back(); c->owned.pop_back(); }
   dev_free_raw(c, (void*)p);
   p = nullptr;
 }
 #define ALLOC(ptr, T, n) do { (ptr) = dalloc<T>(c, (n)); if (!(ptr)) return fail(c, SPB_ENOMEM, "device allocation of %llu bytes failed (%s)", (unsigned long long)((n) * sizeof(T)), #ptr); } while (0)
-template <class T> static T dread(spb_ctx* c, const T* p) { T v; dev_copy(c, &v, p, sizeof(T)); dev_sync(c); return v; }
+// scalar read-back through pinned host memory (one stream sync)
+template <class T> static T dread(spb_ctx* c, const T* p) {
+  dev_copy(c, c->pinned, p, sizeof(T)); dev_sync(c);
+  T v; memcpy(&v, c->pinned, sizeof(T)); return v;
+}
+static void dread_n(spb_ctx* c, void* dst, const void* src, u64 bytes) { dev_copy(c, c->pinned, src, bytes); dev_sync(c); memcpy(dst, c->pinned, bytes); }
 
 static inline u64 nblk(u64 n, u32 t) { return (n + t - 1) / t; }
 #define TPB 256
@@ -232,6 +262,10 @@ static int check_err(spb_ctx* c, const char* where) {
   return 0;
 }
 
+template <int W> static void launch_extract(spb_ctx* c, u64 grid, u64* slots, u64 cap, u32* wbits, u32* dbits) {
+  SPB_LAUNCH(k_extract_insert<W>, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, slots, cap - 1, c->sp, c->obits, wbits, dbits);
+}
+
 // =========================================================================================== C-ABI
 extern "C" {
 
@@ -250,17 +284,20 @@ int spb_create(spb_ctx** out, int device, void* cuda_stream) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) { cudaGetLastError(); return SPB_ECUDA; }
   if (cudaSetDevice(device) != cudaSuccess) return SPB_ECUDA;
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-    uint64_t thr = UINT64_MAX;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-  }
+  // random 8-byte table probes: do not let L2 over-fetch neighbouring sectors from HBM
+  cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+  cudaGetLastError();
 #endif
   spb_ctx* c = new spb_ctx();
   c->device = device;
   c->stream = (spb_stream_t)cuda_stream;
   memset(&c->cnt, 0, sizeof c->cnt);
   memset(&c->nt, 0, sizeof c->nt);
+#ifdef SPB_EMU
+  c->pinned = (u64*)malloc(4096);
+#else
+  if (cudaHostAlloc((void**)&c->pinned, 4096, cudaHostAllocDefault) != cudaSuccess) { delete c; return SPB_ENOMEM; }
+#endif
   c->errflag = dalloc<u32>(c, 4);
   if (!c->errflag) { delete c; return SPB_ENOMEM; }
   dev_memset(c, c->errflag, 0, 16);
@@ -268,10 +305,16 @@ int spb_create(spb_ctx** out, int device, void* cuda_stream) {
   return SPB_OK;
 }
 
-static void free_all(spb_ctx* c, bool keep_err) {
-  for (void* p : c->owned) if (!(keep_err && p == (void*)c->errflag)) dev_free_raw(c, p);
-  c->owned.clear();
-  if (keep_err) c->owned.push_back(c->errflag);
+// return every live block except the error flag to the cache and reset the per-input state
+static void reset_state(spb_ctx* c) {
+  std::vector<void*> blocks;
+  for (auto& kv : c->live) if (kv.first != (void*)c->errflag) blocks.push_back(kv.first);
+  for (void* p : blocks) dev_free_raw(c, p);
+  spb_ctx fresh;
+  fresh.device = c->device; fresh.stream = c->stream; fresh.errflag = c->errflag; fresh.pinned = c->pinned;
+  fresh.live.swap(c->live); fresh.cache.swap(c->cache);
+  memset(&fresh.cnt, 0, sizeof fresh.cnt); memset(&fresh.nt, 0, sizeof fresh.nt);
+  *c = fresh;
 }
 
 void spb_destroy(spb_ctx* c) {
@@ -279,8 +322,15 @@ void spb_destroy(spb_ctx* c) {
 #ifndef SPB_EMU
   cudaSetDevice(c->device);
 #endif
-  free_all(c, false);
   dev_sync(c);
+  for (auto& kv : c->live) backend_free(kv.first);
+  c->live.clear();
+  cache_release(c);
+#ifdef SPB_EMU
+  free(c->pinned);
+#else
+  cudaFreeHost(c->pinned);
+#endif
   delete c;
 }
 
@@ -299,18 +349,15 @@ int spb_load(spb_ctx* c, const uint8_t* ascii, const uint64_t* seq_off, uint32_t
   for (u32 s = 0; s < n_seq; ++s) if (seq_off[s + 1] < seq_off[s]) return fail(c, SPB_EINVAL, "seq_off not monotone");
   if (T == 0) return fail(c, SPB_EINVAL, "empty input");
   if (T >= (1ull << 32) - 4096) return fail(c, SPB_EINVAL, "input of %llu bases exceeds the 32-bit position range of one device", (unsigned long long)T);
-  // drop previous state
-  u32* ef = c->errflag;
-  free_all(c, true);
-  { spb_ctx fresh; fresh.device = c->device; fresh.stream = c->stream; fresh.errflag = ef; fresh.owned = c->owned; memset(&fresh.cnt, 0, sizeof fresh.cnt); memset(&fresh.nt, 0, sizeof fresh.nt); *c = fresh; }
+  reset_state(c);
   dev_memset(c, c->errflag, 0, 16);
   c->k = k; c->n_seq = n_seq; c->T = T;
   c->seq_off_h.assign(seq_off, seq_off + n_seq + 1);
   u64 ninst = 0;
   for (u32 s = 0; s < n_seq; ++s) { u64 len = seq_off[s + 1] - seq_off[s]; if (len > k) ninst += len - k + 1; }
   c->n_inst = ninst;
-  const u32 W = (2 * k + 63) / 64;
-  c->nw = (T + 31) / 32;
+  const u32 W = (2 * k + 31) / 32;
+  c->nw = (T + 15) / 16;
   c->npos_pad = nblk(T, TPB) * TPB + TPB;
   u8* d_ascii;
   ALLOC(d_ascii, u8, T);
@@ -318,13 +365,12 @@ int spb_load(spb_ctx* c, const uint8_t* ascii, const uint64_t* seq_off, uint32_t
   ALLOC(c->seq_off, u64, n_seq + 1);
   dev_copy(c, c->seq_off, seq_off, (n_seq + 1) * 8ull);
   u64 nwp = c->nw + W + 8;
-  ALLOC(c->F, u64, nwp); ALLOC(c->R, u64, nwp);
-  dev_memset(c, c->F, 0, nwp * 8); dev_memset(c, c->R, 0, nwp * 8);
+  ALLOC(c->F, u32, nwp); ALLOC(c->R, u32, nwp);
+  dev_memset(c, c->F + c->nw, 0, (nwp - c->nw) * 4); dev_memset(c, c->R + c->nw, 0, (nwp - c->nw) * 4);
   SPB_LAUNCH(k_pack, nblk(c->nw, TPB), TPB, c->stream, d_ascii, T, c->F, c->R, c->nw, c->errflag);
   u64 nw32 = c->npos_pad / 32;
   ALLOC(c->vbits, u32, nw32 + 8);
-  dev_memset(c, c->vbits, 0, (nw32 + 8) * 4);
-  SPB_LAUNCH(k_valid_bits, nblk(nw32, TPB), TPB, c->stream, c->seq_off, n_seq, T, k, c->vbits, nw32);
+  SPB_LAUNCH(k_valid_bits, nblk(nw32 + 8, TPB), TPB, c->stream, c->seq_off, n_seq, T, k, c->vbits, nw32 + 8);
   dfree(c, d_ascii);
   int r = check_err(c, "spb_load");
   if (r) return r;
@@ -351,24 +397,34 @@ int spb_build_dbg(spb_ctx* c, spb_counts* out) {
   u64 nw32 = c->npos_pad / 32;
   ALLOC(c->sp, u32, c->npos_pad + 8);
   ALLOC(c->obits, u32, nw32 + 8); ALLOC(c->fbits, u32, nw32 + 8);
-  dev_memset(c, c->obits, 0, (nw32 + 8) * 4); dev_memset(c, c->fbits, 0, (nw32 + 8) * 4);
-  u64 grid = nblk(T, TPB);
-  SPB_LAUNCH(k_extract_insert, grid, TPB, c->stream, c->F, c->R, c->vbits, T, k, slots, cap - 1, c->sp, c->obits);
+  u32 *wbits, *dbits; ALLOC(wbits, u32, nw32 + 8); ALLOC(dbits, u32, nw32 + 8);
+  dev_memset(c, dbits, 0, (nw32 + 8) * 4);
+#ifdef SPB_EMU
+  dev_memset(c, c->obits, 0, (nw32 + 8) * 4); dev_memset(c, wbits, 0, (nw32 + 8) * 4);
+#else
+  dev_memset(c, c->obits + nw32, 0, 32); dev_memset(c, wbits + nw32, 0, 32);   // the grid writes every other word
+#endif
+  u64 grid = c->npos_pad / TPB;
+  switch ((2 * k + 31) / 32) {
+    case 7: launch_extract<7>(c, grid, slots, cap, wbits, dbits); break;       // k = 101
+    case 19: launch_extract<19>(c, grid, slots, cap, wbits, dbits); break;     // k = 301
+    case 32: launch_extract<32>(c, grid, slots, cap, wbits, dbits); break;     // k = 501
+    default: launch_extract<0>(c, grid, slots, cap, wbits, dbits); break;
+  }
   snprintf(buf, sizeof buf, "\"extract_insert_ms\": %.4f", tm.stop(c)); c->stats += buf;
-  // ---- K2/K3: first appearances -> vertex ids
+  // ---- K3: first appearances -> vertex ids
   tm.start(c);
-  SPB_LAUNCH(k_first_flags, grid, TPB, c->stream, slots, c->sp, c->vbits, T, c->fbits);
-  dfree(c, slots);
   u64 nb = c->npos_pad / 256;
   u32 *blkcnt, *blkoff; ALLOC(blkcnt, u32, nb); ALLOC(blkoff, u32, nb);
-  SPB_LAUNCH(k_block_counts, nblk(nb, TPB), TPB, c->stream, c->fbits, blkcnt, nb);
+  SPB_LAUNCH(k_first_bits, nblk(nb, TPB), TPB, c->stream, wbits, dbits, c->fbits, blkcnt, nb);
+  dev_memset(c, c->fbits + nw32, 0, 32);
   u64 nV = 0;
   PRIM(prim_scan_u32(c, blkcnt, blkoff, nb, &nV));
   c->nV = (u32)nV;
-  ALLOC(c->v2pos, u32, nV + 1); ALLOC(c->vflags, u8, nV + 16);
-  dev_memset(c, c->vflags, 0, nV + 16);
-  SPB_LAUNCH(k_assign_ids, grid, TPB, c->stream, c->sp, c->vbits, T, c->fbits, blkoff, c->v2pos, c->vflags);
-  dfree(c, blkcnt); dfree(c, blkoff);
+  ALLOC(c->v2pos, u32, nV + 1); ALLOC(c->vflags, u8, nV + 64);
+  dev_memset(c, c->vflags + (nV & ~7ull), 0, 64);
+  SPB_LAUNCH(k_assign_ids, nblk(T, TPB), TPB, c->stream, c->sp, c->vbits, T, c->fbits, blkoff, slots, c->v2pos, c->vflags);
+  dfree(c, blkcnt); dfree(c, blkoff); dfree(c, slots); dfree(c, wbits); dfree(c, dbits);
   snprintf(buf, sizeof buf, ", \"vertex_ids_ms\": %.4f", tm.stop(c)); c->stats += buf;
   // ---- K4: junction edges
   tm.start(c);
@@ -378,7 +434,7 @@ int spb_build_dbg(spb_ctx* c, spb_counts* out) {
   for (int attempt = 0; attempt < 2; ++attempt) {
     ALLOC(Jk, u64, jcap); ALLOC(Js, u8, jcap);
     dev_memset(c, jcount, 0, 16);
-    SPB_LAUNCH(k_junction_emit, grid, TPB, c->stream, c->sp, T, c->vflags, c->v2pos, c->obits, Jk, Js, jcount, jcap);
+    SPB_LAUNCH(k_junction_emit, nblk(T, TPB), TPB, c->stream, c->sp, T, c->vflags, c->v2pos, c->obits, Jk, Js, jcount, jcap);
     nj = dread(c, jcount);
     if (nj <= jcap) break;
     dfree(c, Jk); dfree(c, Js); jcap = nj;
@@ -391,18 +447,18 @@ int spb_build_dbg(spb_ctx* c, spb_counts* out) {
   }
   PRIM(unique_sorted(c, Jk, Js, nj, &c->nJ));
   c->Jk = Jk; c->Js = Js;
-  if (!c->Jk) { ALLOC(c->Jk, u64, 1); ALLOC(c->Js, u8, 1); }
   SPB_LAUNCH(k_mark_hasj, nblk(c->nJ, TPB), TPB, c->stream, c->Jk, c->nJ, c->vflags);
   ALLOC(c->seqlim, u32, 2ull * c->n_seq);
   SPB_LAUNCH(k_mark_seqlim, nblk(c->n_seq, TPB), TPB, c->stream, c->seq_off, c->n_seq, k, c->sp, c->vflags, c->seqlim);
   // ---- explicit edge list
   GView g{c->vflags, c->Jk, c->Js, c->nJ, c->nV};
-  u32 *ecnt, *eoff; ALLOC(ecnt, u32, nV + 1); ALLOC(eoff, u32, nV + 1);
-  SPB_LAUNCH(k_edge_counts, nblk(nV, TPB), TPB, c->stream, g, ecnt);
+  u64 nT = (nV + 7) / 8;
+  u32 *ecnt, *eoff; ALLOC(ecnt, u32, nT + 1); ALLOC(eoff, u32, nT + 1);
+  SPB_LAUNCH(k_edge_counts8, nblk(nT, TPB), TPB, c->stream, g, ecnt);
   u64 nE = 0;
-  PRIM(prim_scan_u32(c, ecnt, eoff, nV, &nE));
+  PRIM(prim_scan_u32(c, ecnt, eoff, nT, &nE));
   ALLOC(c->edges, u32, 2 * nE + 2);
-  SPB_LAUNCH(k_edge_write, nblk(nV, TPB), TPB, c->stream, g, eoff, c->edges);
+  SPB_LAUNCH(k_edge_write8, nblk(nT, TPB), TPB, c->stream, g, eoff, c->edges);
   dfree(c, ecnt); dfree(c, eoff);
   snprintf(buf, sizeof buf, ", \"edges_ms\": %.4f", tm.stop(c)); c->stats += buf;
   int r = check_err(c, "spb_build_dbg");
@@ -429,18 +485,21 @@ int spb_compact(spb_ctx* c, spb_counts* out) {
   u32 ncyc = 0;
   tm.start(c);
   for (int pass = 0; pass < 2; ++pass) {
-    // ---- K5: init detection, K6: pieces
-    SPB_LAUNCH(k_classify, nblk(nV, TPB), TPB, c->stream, g, c->vflags, c->errflag);
-    SPB_LAUNCH(k_piece_flags, nblk(nV, TPB), TPB, c->stream, c->vflags, nV);
-    PRIM(prim_count_flag(c, c->vflags, VF_INIT, nV, &c->nI));
-    ALLOC(c->init_list, u32, c->nI + 1);
-    PRIM(prim_select_flag(c, c->vflags, VF_INIT, nV, c->init_list, &c->nI));
-    PRIM(prim_count_flag(c, c->vflags, VF_PSTART, nV, &c->nP));
-    ALLOC(c->plo, u32, c->nP + 1); ALLOC(c->phi, u32, c->nP + 1);
-    u32 np2 = 0;
-    PRIM(prim_select_flag(c, c->vflags, VF_PSTART, nV, c->plo, &c->nP));
-    PRIM(prim_select_flag(c, c->vflags, VF_PEND, nV, c->phi, &np2));
-    if (np2 != c->nP) return fail(c, SPB_ECUDA, "internal: piece starts (%u) != piece ends (%u)", c->nP, np2);
+    // ---- K5: init detection, K6: pieces (8 vertices per thread), then one scan + compaction for the three lists
+    const u32 nT = (nV + 7) / 8;
+    u32 *cnt3, *off3; ALLOC(cnt3, u32, 3ull * nT + 1); ALLOC(off3, u32, 3ull * nT + 1);
+    SPB_LAUNCH(k_classify8, nblk(nT, TPB), TPB, c->stream, g, c->vflags, c->errflag);
+    SPB_LAUNCH(k_piece_flags8, nblk(nT, TPB), TPB, c->stream, c->vflags, nV, cnt3, nT);
+    u64 tot3 = 0;
+    PRIM(prim_scan_u32(c, cnt3, off3, 3ull * nT, &tot3));
+    u32 marks[2];
+    dev_copy(c, c->pinned, off3 + nT, 4); dev_copy(c, (u32*)c->pinned + 1, off3 + 2ull * nT, 4); dev_sync(c);
+    memcpy(marks, c->pinned, 8);
+    c->nI = marks[0]; c->nP = marks[1] - marks[0];
+    if ((u64)c->nI + 2ull * c->nP != tot3) return fail(c, SPB_ECUDA, "internal: piece starts (%u) != piece ends (%llu)", c->nP, (unsigned long long)(tot3 - marks[1]));
+    ALLOC(c->init_list, u32, c->nI + 1); ALLOC(c->plo, u32, c->nP + 1); ALLOC(c->phi, u32, c->nP + 1);
+    SPB_LAUNCH(k_compact3, nblk(nT, TPB), TPB, c->stream, c->vflags, nV, off3, nT, c->nI, c->nP, c->init_list, c->plo, c->phi);
+    dfree(c, cnt3); dfree(c, off3);
     const u32 nP = c->nP, nD = 2 * nP;
     c->nD = nD;
     ALLOC(pl_nbr, u32, nP + 1); ALLOC(pr_nbr, u32, nP + 1); ALLOC(pl_side, u8, nP + 1); ALLOC(pr_side, u8, nP + 1);

@@ -61,61 +61,84 @@ __device__ __forceinline__ u64 list_reserve(u64* counter, u32 n) {
 }
 
 // ------------------------------------------------------------------------------------ windows
-// limb j of the 2k-bit window starting at base a of packed strand S (first base in the top bits)
-struct Win {
-  const u64* w;   // word pointer
-  u32 sh;         // bit shift 0..62
-};
-__device__ __forceinline__ Win win_at(const u64* S, u64 a) { Win r; r.w = S + (a >> 5); r.sh = (u32)(a & 31) * 2; return r; }
-__device__ __forceinline__ u64 funnel(u64 hi, u64 lo, u32 sh) { return sh ? (hi << sh) | (lo >> (64 - sh)) : hi; }
-__device__ __forceinline__ u64 tail_mask(u32 k) { u32 nb = 2 * k - 64 * ((2 * k + 63) / 64 - 1); return nb == 64 ? ~0ull : (~0ull << (64 - nb)); }
+// Packed strands are arrays of u32 words, 16 bases per word, first base in the top bits, so that
+// unsigned compare of 32-bit limbs == lexicographic compare of bases (A<C<G<T).
+// limb j of the window starting at base a:  funnelshift(w[a/16 + j], w[a/16 + j + 1], 2*(a%16)).
+__device__ __forceinline__ u32 limb_at(const u32* __restrict__ w, u32 sh, u32 j) { return __funnelshift_l(__ldg(w + j + 1), __ldg(w + j), sh); }
+__device__ __forceinline__ u32 nlimbs(u32 k) { return (2 * k + 31) / 32; }
+__device__ __forceinline__ u32 tail_mask(u32 k) { u32 nb = 2 * k - 32 * (nlimbs(k) - 1); return nb == 32 ? ~0u : (~0u << (32 - nb)); }
 
 // lexicographic compare of two k-base windows: -1 / 0 / +1
-__device__ __forceinline__ int win_cmp(const u64* A, u64 a, const u64* B, u64 b, u32 k) {
-  const u32 W = (2 * k + 63) / 64;
-  Win x = win_at(A, a), y = win_at(B, b);
-  u64 x0 = __ldg(x.w), y0 = __ldg(y.w);
+__device__ __forceinline__ int win_cmp(const u32* A, u64 a, const u32* B, u64 b, u32 k) {
+  const u32 W = nlimbs(k);
+  const u32* x = A + (a >> 4); const u32* y = B + (b >> 4);
+  const u32 sx = (u32)(a & 15) * 2, sy = (u32)(b & 15) * 2;
+  u32 x0 = __ldg(x), y0 = __ldg(y);
   for (u32 j = 0; j < W; ++j) {
-    u64 x1 = __ldg(x.w + j + 1), y1 = __ldg(y.w + j + 1);
-    u64 lx = funnel(x0, x1, x.sh), ly = funnel(y0, y1, y.sh);
-    if (j == W - 1) { u64 m = tail_mask(k); lx &= m; ly &= m; }
+    u32 x1 = __ldg(x + j + 1), y1 = __ldg(y + j + 1);
+    u32 lx = __funnelshift_l(x1, x0, sx), ly = __funnelshift_l(y1, y0, sy);
+    if (j == W - 1) { u32 m = tail_mask(k); lx &= m; ly &= m; }
     if (lx != ly) return lx > ly ? 1 : -1;
     x0 = x1; y0 = y1;
   }
   return 0;
 }
 
-__device__ __forceinline__ u64 win_hash(const u64* A, u64 a, u32 k) {
-  const u32 W = (2 * k + 63) / 64;
-  Win x = win_at(A, a);
-  u64 h = 0x9E3779B97F4A7C15ull ^ (u64)k;
-  u64 x0 = __ldg(x.w);
-  for (u32 j = 0; j < W; ++j) {
-    u64 x1 = __ldg(x.w + j + 1);
-    u64 l = funnel(x0, x1, x.sh);
-    if (j == W - 1) l &= tail_mask(k);
-    h ^= l; h *= 0xff51afd7ed558ccdull; h ^= h >> 32;
-    x0 = x1;
-  }
-  h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 29;
+// 64-bit hash of a k-base window: two 32-bit multiplicative chains over the limbs + fmix64.
+// Only the distribution matters: equality is always verified on the full 2k bits.
+__device__ __forceinline__ u64 hash_finish(u32 a, u32 b) {
+  u64 h = ((u64)a << 32) | b;
+  h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
   return h;
 }
+template <int W> __device__ __forceinline__ u64 win_hash_t(const u32* A, u64 a, u32 k) {
+  const u32* x = A + (a >> 4); const u32 sh = (u32)(a & 15) * 2;
+  u32 ha = 0x9E3779B9u ^ k, hb = 0x85EBCA6Bu;
+  u32 x0 = __ldg(x);
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    u32 x1 = __ldg(x + j + 1);
+    u32 l = __funnelshift_l(x1, x0, sh);
+    if (j == W - 1) l &= tail_mask(k);
+    ha = ha * 0x9E3779B1u + l; hb = (hb ^ l) * 0x85EBCA77u;
+    x0 = x1;
+  }
+  return hash_finish(ha, hb);
+}
+__device__ __forceinline__ u64 win_hash_rt(const u32* A, u64 a, u32 k) {
+  const u32 W = nlimbs(k);
+  const u32* x = A + (a >> 4); const u32 sh = (u32)(a & 15) * 2;
+  u32 ha = 0x9E3779B9u ^ k, hb = 0x85EBCA6Bu;
+  u32 x0 = __ldg(x);
+  for (u32 j = 0; j < W; ++j) {
+    u32 x1 = __ldg(x + j + 1);
+    u32 l = __funnelshift_l(x1, x0, sh);
+    if (j == W - 1) l &= tail_mask(k);
+    ha = ha * 0x9E3779B1u + l; hb = (hb ^ l) * 0x85EBCA77u;
+    x0 = x1;
+  }
+  return hash_finish(ha, hb);
+}
+template <int W> __device__ __forceinline__ u64 win_hash(const u32* A, u64 a, u32 k) {
+  if (W > 0) return win_hash_t<(W > 0 ? W : 1)>(A, a, k);
+  return win_hash_rt(A, a, k);
+}
 
-__device__ __forceinline__ u32 base_at(const u64* S, u64 a) { return (u32)(S[a >> 5] >> (62 - 2 * (a & 31))) & 3u; }
+__device__ __forceinline__ u32 base_at(const u32* S, u64 a) { return (S[a >> 4] >> (30 - 2 * (a & 15))) & 3u; }
 
 // ------------------------------------------------------------------------------------ K0: pack
-// One thread per packed word of F and of R (32 bases).  A=0 C=1 G=2 T=3.
+// One thread per packed word of F and of R (16 bases).  A=0 C=1 G=2 T=3.
 __device__ __forceinline__ u32 ascii_code(u32 c, u32* bad) {
   if (c != 'A' && c != 'C' && c != 'G' && c != 'T') *bad = 1;
   u32 t = (c >> 1) & 3u;        // A0 C1 T2 G3
   return t ^ (t >> 1);          // A0 C1 G2 T3
 }
-__global__ void k_pack(const u8* __restrict__ ascii, u64 T, u64* __restrict__ F, u64* __restrict__ R, u64 nw, u32* err) {
+__global__ void k_pack(const u8* __restrict__ ascii, u64 T, u32* __restrict__ F, u32* __restrict__ R, u64 nw, u32* err) {
   u64 w = SPB_GTID();
   if (w >= nw) return;
-  u64 f = 0, r = 0; u32 bad = 0;
-  for (u32 j = 0; j < 32; ++j) {
-    u64 p = w * 32 + j;
+  u32 f = 0, r = 0, bad = 0;
+  for (u32 j = 0; j < 16; ++j) {
+    u64 p = w * 16 + j;
     u32 cf = 0, cr = 0;
     if (p < T) {
       cf = ascii_code(__ldg(ascii + p), &bad);
@@ -146,7 +169,7 @@ __global__ void k_valid_bits(const u64* __restrict__ seq_off, u32 n_seq, u64 T, 
       if (e - b > k) {                                        // len > k (reference lib/Assembler.py:151)
         u64 lo = b > p0 ? b : p0, hi = e - k + 1;             // valid starts [b, e-k]
         if (hi > p0 + 32) hi = p0 + 32;
-        for (u64 p = lo; p < hi; ++p) m |= 1u << (p - p0);
+        if (hi > lo) { u32 n = (u32)(hi - lo); m |= (n == 32 ? ~0u : ((1u << n) - 1)) << (lo - p0); }
       }
     }
   }
@@ -158,33 +181,46 @@ __global__ void k_valid_bits(const u64* __restrict__ seq_off, u32 n_seq, u64 T, 
 // (reference lib/Assembler.py:989-991).  The table keeps, per distinct canonical k-mer, the
 // SMALLEST position seen (atomicMin) -> first appearance in (sequence, position) order
 // (reference lib/Assembler.py:186-195).  Equality is always verified on the full 2k bits.
-__global__ void SPB_LAUNCH_BOUNDS(256)
-k_extract_insert(const u64* __restrict__ F, const u64* __restrict__ R, const u32* __restrict__ vbits, u64 T, u32 k,
-                 u64* slots, u64 capmask, u32* __restrict__ slotidx, u32* obits) {
+//   wbits[p]  the thread installed its entry (CAS into an empty slot, or an atomicMin that lowered it)
+//   dbits[q]  position q was installed earlier and then displaced by a smaller position
+// first appearance  <=>  wbits & ~dbits   (every displacement is observed exactly once through the
+// value atomicMin returns), so no second pass over the table is needed to find the firsts.
+template <int W> __global__ void SPB_LAUNCH_BOUNDS(256)
+k_extract_insert(const u32* __restrict__ F, const u32* __restrict__ R, const u32* __restrict__ vbits, u64 T, u32 k,
+                 u64* slots, u64 capmask, u32* __restrict__ slotidx, u32* obits, u32* wbits, u32* dbits) {
   u64 p = SPB_GTID();
   bool valid = p < T && get_bit(vbits, p);
-  bool o = false;
+  bool o = false, won = false;
   if (valid) {
     u64 ra = T - p - k;
-    o = win_cmp(F, p, R, ra, k) >= 0;
-    const u64* S = o ? F : R;
+    // orientation: almost always decided by the first limb
+    {
+      const u32* x = F + (p >> 4); const u32* y = R + (ra >> 4);
+      u32 lx = __funnelshift_l(__ldg(x + 1), __ldg(x), (u32)(p & 15) * 2), ly = __funnelshift_l(__ldg(y + 1), __ldg(y), (u32)(ra & 15) * 2);
+      o = (lx != ly) ? (lx > ly) : (win_cmp(F, p, R, ra, k) >= 0);
+    }
+    const u32* S = o ? F : R;
     u64 a = o ? p : ra;
-    u64 h = win_hash(S, a, k);
+    u64 h = win_hash<W>(S, a, k);
     u64 idx = h & capmask, tag = h >> 40;
     u64 entry = (tag << 40) | (p << 1) | (o ? 1ull : 0ull);
     for (;;) {
-      u64 cur = __ldcg(slots + idx);
-      if (cur == SPB_EMPTY) {
-        cur = atomicCAS(slots + idx, SPB_EMPTY, entry);
-        if (cur == SPB_EMPTY) break;
-      }
+      u64 cur = atomicCAS(slots + idx, SPB_EMPTY, entry);
+      if (cur == SPB_EMPTY) { won = true; break; }
       if ((cur >> 40) == tag) {
         u64 q = (cur >> 1) & SPB_POSMASK;
         bool oq = cur & 1;
-        const u64* S2 = oq ? F : R;
+        const u32* S2 = oq ? F : R;
         u64 b = oq ? q : T - q - k;
         if (q == p || win_cmp(S, a, S2, b, k) == 0) {
-          if (entry < cur) atomicMin(slots + idx, entry);
+          if (entry < cur) {
+            u64 old = atomicMin(slots + idx, entry);
+            if (old > entry) {                       // we lowered the slot: old's position is no longer the first
+              won = true;
+              u64 dq = (old >> 1) & SPB_POSMASK;
+              atomicOr(dbits + (dq >> 5), 1u << (dq & 31));
+            }
+          }
           break;
         }
       }
@@ -193,28 +229,15 @@ k_extract_insert(const u64* __restrict__ F, const u64* __restrict__ R, const u32
     slotidx[p] = (u32)idx;
   }
   store_bit(obits, p, o);
+  store_bit(wbits, p, won);
 }
 
-// K2: representative (first) position of every instance; first-appearance bitmap.
-__global__ void k_first_flags(const u64* __restrict__ slots, u32* __restrict__ rep, const u32* __restrict__ vbits, u64 T, u32* fbits) {
-  u64 p = SPB_GTID();
-  bool valid = p < T && get_bit(vbits, p);
-  bool first = false;
-  if (valid) {
-    u64 cur = __ldcg(slots + rep[p]);
-    u32 r = (u32)((cur >> 1) & SPB_POSMASK);
-    rep[p] = r;
-    first = (r == (u32)p);
-  }
-  store_bit(fbits, p, first);
-}
-
-// per 256-position block: number of first appearances
-__global__ void k_block_counts(const u32* __restrict__ fbits, u32* __restrict__ cnt, u64 nblk) {
+// first-appearance bitmap fbits = wbits & ~dbits, and per 256-position block counts
+__global__ void k_first_bits(const u32* __restrict__ wbits, const u32* __restrict__ dbits, u32* __restrict__ fbits, u32* __restrict__ cnt, u64 nblk) {
   u64 b = SPB_GTID();
   if (b >= nblk) return;
   u32 c = 0;
-  for (u32 j = 0; j < 8; ++j) c += __popc(fbits[b * 8 + j]);
+  for (u32 j = 0; j < 8; ++j) { u32 f = wbits[b * 8 + j] & ~dbits[b * 8 + j]; fbits[b * 8 + j] = f; c += __popc(f); }
   cnt[b] = c;
 }
 
@@ -227,16 +250,18 @@ __device__ __forceinline__ u32 rank_first(const u32* fbits, const u32* blkoff, u
 }
 
 // K3: vertex ids (= rank of the representative among first appearances), vertex -> first position,
-// implicit-edge bit.  `sp` holds rep[] on entry and vertex ids on exit.
+// implicit-edge bit.  `sp` holds the slot index of every instance on entry and vertex ids on exit;
+// only instances that are not first appearances read their representative back from the table.
 __global__ void k_assign_ids(u32* __restrict__ sp, const u32* __restrict__ vbits, u64 T, const u32* __restrict__ fbits,
-                             const u32* __restrict__ blkoff, u32* __restrict__ v2pos, u8* __restrict__ vflags) {
+                             const u32* __restrict__ blkoff, const u64* __restrict__ slots, u32* __restrict__ v2pos, u8* __restrict__ vflags) {
   u64 p = SPB_GTID();
   if (p >= T) return;
   if (!get_bit(vbits, p)) { sp[p] = SPB_INVALID; return; }
-  u32 r = sp[p];
+  bool first = get_bit(fbits, p);
+  u32 r = first ? (u32)p : (u32)((__ldcg(slots + sp[p]) >> 1) & SPB_POSMASK);
   u32 vid = rank_first(fbits, blkoff, r);
   sp[p] = vid;
-  if (r == (u32)p) {
+  if (first) {
     v2pos[vid] = (u32)p;
     vflags[vid] = get_bit(fbits, p + 1) ? VF_R : 0;   // (p, p+1) both first appearances => edge (vid, vid+1)
   }
@@ -335,20 +360,77 @@ __global__ void k_mark_seqlim(const u64* __restrict__ seq_off, u32 n_seq, u32 k,
 
 // K5: init detection (reference lib/Assembler.py:995-1035): init iff #distinct non-self
 // neighbours != 2, or the vertex is a sequence limit and both neighbours attach to the same side.
-__global__ void k_classify(GView g, u8* vflags, u32* err) {
-  u64 v = SPB_GTID();
-  if (v >= g.nV) return;
+// Eight vertices (one u64 of flag bytes) per thread.  A vertex without junction entries has only the
+// implicit neighbours v-1 (left) and v+1 (right): init <=> not both present; the general rule runs
+// only for the few vertices that carry junction entries.
+__device__ __forceinline__ bool classify_slow(const GView& g, u32 v, u8 f, u32* err) {
   u32 cnt = 0, s0 = 0, s1 = 0;
-  for_each_nbr(g, (u32)v, [&](u32, u32 side, u32) { if (cnt == 0) s0 = side; else if (cnt == 1) s1 = side; ++cnt; });
-  u8 f = g.vflags[v];
+  for_each_nbr(g, v, [&](u32, u32 side, u32) { if (cnt == 0) s0 = side; else if (cnt == 1) s1 = side; ++cnt; });
   bool init = cnt != 2;
   if (!init && s0 == s1) {
     init = true;
     if (!(f & VF_SEQLIM)) atomicOr(err, (u32)ERR_DEGENERATE);  // the reference would assert (lib/Assembler.py:1104)
   }
-  f &= (u8)~(VF_INIT | VF_PSTART | VF_PEND | VF_IN2);
-  if (init) f |= VF_INIT;
-  vflags[v] = f;
+  return init;
+}
+__global__ void k_classify8(GView g, u8* vflags, u32* err) {
+  u64 t = SPB_GTID();
+  u64 v0 = t * 8;
+  if (v0 >= g.nV) return;
+  u64 w = *(const u64*)(g.vflags + v0);
+  u32 prev = v0 ? g.vflags[v0 - 1] : 0;
+  u64 out = w & ~(0x0101010101010101ull * (u64)(VF_INIT | VF_PSTART | VF_PEND | VF_IN2));
+  for (u32 i = 0; i < 8 && v0 + i < g.nV; ++i) {
+    u32 f = (u32)(w >> (8 * i)) & 0xFF;
+    bool init;
+    if (!(f & VF_HASJ)) init = !((prev & VF_R) && (f & VF_R));
+    else init = classify_slow(g, (u32)(v0 + i), (u8)f, err);
+    if (init) out |= (u64)VF_INIT << (8 * i);
+    prev = f;
+  }
+  *(u64*)(vflags + v0) = out;
+}
+
+// K6: pieces = maximal runs of consecutive-id extender vertices linked by implicit edges; also the
+// per-thread counts of inits / piece starts / piece ends for the compaction below.
+__global__ void k_piece_flags8(u8* vflags, u32 nV, u32* __restrict__ cnt3, u32 nT) {
+  u64 t = SPB_GTID();
+  u64 v0 = t * 8;
+  if (v0 >= nV) return;
+  u64 w = *(const u64*)(vflags + v0);
+  u32 pf = v0 ? vflags[v0 - 1] : 0;
+  u32 nxt8 = vflags[v0 + 8];                       // padded: bytes >= nV are zero
+  u64 out = w;
+  u32 cI = 0, cS = 0, cE = 0;
+  for (u32 i = 0; i < 8 && v0 + i < nV; ++i) {
+    u32 f = (u32)(w >> (8 * i)) & 0xFF;
+    u32 nf = i < 7 ? (u32)(w >> (8 * (i + 1))) & 0xFF : nxt8;
+    if (v0 + i + 1 >= nV) nf = 0;
+    if (f & VF_INIT) ++cI;
+    else {
+      bool start = !((pf & VF_R) && !(pf & VF_INIT));
+      bool end = !((f & VF_R) && !(nf & VF_INIT));
+      if (start) { out |= (u64)VF_PSTART << (8 * i); ++cS; }
+      if (end) { out |= (u64)VF_PEND << (8 * i); ++cE; }
+    }
+    pf = f;
+  }
+  *(u64*)(vflags + v0) = out;
+  cnt3[t] = cI; cnt3[nT + t] = cS; cnt3[2 * (u64)nT + t] = cE;
+}
+__global__ void k_compact3(const u8* __restrict__ vflags, u32 nV, const u32* __restrict__ off3, u32 nT, u32 totI, u32 totS,
+                           u32* __restrict__ init_list, u32* __restrict__ plo, u32* __restrict__ phi) {
+  u64 t = SPB_GTID();
+  u64 v0 = t * 8;
+  if (v0 >= nV) return;
+  u64 w = *(const u64*)(vflags + v0);
+  u32 oI = off3[t], oS = off3[nT + t] - totI, oE = off3[2 * (u64)nT + t] - totI - totS;
+  for (u32 i = 0; i < 8 && v0 + i < nV; ++i) {
+    u32 f = (u32)(w >> (8 * i)) & 0xFF;
+    if (f & VF_INIT) init_list[oI++] = (u32)(v0 + i);
+    if (f & VF_PSTART) plo[oS++] = (u32)(v0 + i);
+    if (f & VF_PEND) phi[oE++] = (u32)(v0 + i);
+  }
 }
 
 __global__ void k_init_degrees(GView g, const u32* __restrict__ init_list, u32 nI, u32* __restrict__ ideg) {
@@ -357,17 +439,6 @@ __global__ void k_init_degrees(GView g, const u32* __restrict__ init_list, u32 n
   u32 c = 0;
   for_each_nbr(g, init_list[i], [&](u32, u32, u32) { ++c; });
   ideg[i] = c;
-}
-
-// K6: pieces = maximal runs of consecutive-id extender vertices linked by implicit edges.
-__global__ void k_piece_flags(u8* vflags, u32 nV) {
-  u64 v = SPB_GTID();
-  if (v >= nV) return;
-  u8 f = vflags[v];
-  if (f & VF_INIT) return;
-  bool start = !(v > 0 && (vflags[v - 1] & VF_R) && !(vflags[v - 1] & VF_INIT));
-  bool end = !((f & VF_R) && !(vflags[v + 1] & VF_INIT));
-  vflags[v] = f | (start ? VF_PSTART : 0) | (end ? VF_PEND : 0);
 }
 
 // outside neighbours of the two ends of every piece: the neighbour on the LEFT of lo, on the RIGHT of hi
@@ -509,7 +580,7 @@ __global__ void k_nbp_lengths(NbpTab t, u32 nN, u32 k, u64* __restrict__ vlen, u
 __device__ __forceinline__ u8 code2ascii(u32 c) { return (u8)("ACGT"[c]); }
 
 // K11: NBP head / tail: first vertex with its k oriented bases, last vertex with its last base.
-__global__ void k_emit_ends(NbpTab t, u32 nN, u32 k, u64 T, const u64* __restrict__ F, const u64* __restrict__ R,
+__global__ void k_emit_ends(NbpTab t, u32 nN, u32 k, u64 T, const u32* __restrict__ F, const u32* __restrict__ R,
                             const u32* __restrict__ v2pos, const u64* __restrict__ voff, const u64* __restrict__ soff,
                             u32* __restrict__ verts, u8* __restrict__ seq) {
   u32 id = blockIdx.x;
@@ -520,7 +591,7 @@ __global__ void k_emit_ends(NbpTab t, u32 nN, u32 k, u64 T, const u64* __restric
   bool afwd = t.aside[id] == SIDE_R;          // second vertex on a's right => a read forward
   bool bfwd = t.bside[id] == SIDE_L;          // predecessor on b's left  => b read forward
   u64 pa = v2pos[a], pb = v2pos[b];
-  const u64* S = afwd ? F : R;
+  const u32* S = afwd ? F : R;
   u64 s0 = afwd ? pa : T - pa - k;
   for (u32 j = threadIdx.x; j < k; j += blockDim.x) seq[so + j] = code2ascii(base_at(S, s0 + j));
   if (threadIdx.x == 0) {
@@ -543,8 +614,8 @@ __global__ void k_dart_chunks(const u32* __restrict__ plo, const u32* __restrict
 }
 __global__ void SPB_LAUNCH_BOUNDS(256)
 k_emit_darts(const u32* __restrict__ choff, u32 nD, const u32* __restrict__ plo, const u32* __restrict__ phi,
-             const u32* __restrict__ dart_nbp, const u32* __restrict__ acc, u32 k, u64 T, const u64* __restrict__ F,
-             const u64* __restrict__ R, const u32* __restrict__ v2pos, const u64* __restrict__ voff,
+             const u32* __restrict__ dart_nbp, const u32* __restrict__ acc, u32 k, u64 T, const u32* __restrict__ F,
+             const u32* __restrict__ R, const u32* __restrict__ v2pos, const u64* __restrict__ voff,
              const u64* __restrict__ soff, u32* __restrict__ verts, u8* __restrict__ seq, u32* __restrict__ vnbp) {
   u32 c = blockIdx.x;
   u32 d = upper_bound_u32(choff, nD, c) - 1;
@@ -554,13 +625,24 @@ k_emit_darts(const u32* __restrict__ choff, u32 nD, const u32* __restrict__ plo,
   u32 un = dart_nbp[d ^ 1]; if (id < un) un = id;
   u64 vo = voff[id] + acc[d], so = soff[id] + (k - 1) + acc[d];
   u64 src = up ? (u64)v2pos[lo] + k - 1 : T - 1 - (u64)v2pos[hi];
-  const u64* S = up ? F : R;
+  const u32* S = up ? F : R;
   u32 t0 = (c - choff[d]) * SPB_CHUNK;
-  for (u32 t = t0 + threadIdx.x; t < t0 + SPB_CHUNK && t < len; t += blockDim.x) {
+  u32 n = len - t0 < SPB_CHUNK ? len - t0 : SPB_CHUNK;
+  for (u32 t = t0 + threadIdx.x; t < t0 + n; t += blockDim.x) {
     u32 v = up ? lo + t : hi - t;
     verts[vo + t] = v;
-    seq[so + t] = code2ascii(base_at(S, src + t));
     if (up) vnbp[v] = un;
+  }
+  // sequence bytes: one aligned 4-byte word of the output per thread (4 bases = 8 bits of the strand)
+  u64 D0 = so + t0, D1 = D0 + n;
+  for (u64 wq = (D0 & ~3ull) + 4ull * threadIdx.x; wq < D1; wq += 4ull * blockDim.x) {
+    u64 b0 = wq < D0 ? D0 : wq, b1 = wq + 4 < D1 ? wq + 4 : D1;
+    u64 i = src + (b0 - so);                         // strand base index of the first byte we write
+    u32 bits = __funnelshift_l(__ldg(S + (i >> 4) + 1), __ldg(S + (i >> 4)), (u32)(i & 15) * 2) >> 24;   // 4 bases
+    u32 word = 0;
+    for (u32 j = 0; j < 4; ++j) word |= ((0x54474341u >> (8 * ((bits >> (6 - 2 * j)) & 3u))) & 0xFFu) << (8 * j);
+    if (b0 == wq && b1 == wq + 4) *(u32*)(seq + wq) = word;
+    else for (u64 q = b0; q < b1; ++q) seq[q] = (u8)(word >> (8 * (q - b0)));
   }
 }
 
@@ -708,33 +790,44 @@ __global__ void k_coords(const u32* __restrict__ v2pos, u32 nV, const u64* __res
 }
 
 // explicit edge list (reference lib/Assembler.py:247-249): per vertex v the rows (v, x), x >= v:
-// self-loop first, then the implicit (v, v+1), then junction neighbours above v.
-__global__ void k_edge_counts(GView g, u32* __restrict__ cnt) {
-  u64 v = SPB_GTID();
-  if (v >= g.nV) return;
-  u8 fl = g.vflags[v];
-  u32 c = (fl & VF_R) ? 1 : 0;
-  if (fl & VF_HASJ) {
-    u32 i = lower_bound_key(g.Jk, g.nJ, ((u64)v << 32) | v);
-    for (; i < g.nJ && (u32)(g.Jk[i] >> 32) == v; ++i) ++c;
-  }
-  cnt[v] = c;
-}
-__global__ void k_edge_write(GView g, const u32* __restrict__ off, u32* __restrict__ edges) {
-  u64 v = SPB_GTID();
-  if (v >= g.nV) return;
-  u8 fl = g.vflags[v];
-  u64 o = off[v];
-  bool r = (fl & VF_R) != 0;
-  if (fl & VF_HASJ) {
-    u32 i = lower_bound_key(g.Jk, g.nJ, ((u64)v << 32) | v);
-    for (; i < g.nJ && (u32)(g.Jk[i] >> 32) == v; ++i) {
-      u32 d = (u32)g.Jk[i];
-      if (r && d > v + 1) { edges[2 * o] = (u32)v; edges[2 * o + 1] = (u32)v + 1; ++o; r = false; }
-      edges[2 * o] = (u32)v; edges[2 * o + 1] = d; ++o;
+// self-loop first, then the implicit (v, v+1), then junction neighbours above v.  8 vertices per thread.
+__global__ void k_edge_counts8(GView g, u32* __restrict__ cnt) {
+  u64 t = SPB_GTID();
+  u64 v0 = t * 8;
+  if (v0 >= g.nV) return;
+  u64 w = *(const u64*)(g.vflags + v0);
+  u32 c = 0;
+  for (u32 i = 0; i < 8 && v0 + i < g.nV; ++i) {
+    u32 fl = (u32)(w >> (8 * i)) & 0xFF;
+    if (fl & VF_R) ++c;
+    if (fl & VF_HASJ) {
+      u32 v = (u32)(v0 + i);
+      u32 j = lower_bound_key(g.Jk, g.nJ, ((u64)v << 32) | v);
+      for (; j < g.nJ && (u32)(g.Jk[j] >> 32) == v; ++j) ++c;
     }
   }
-  if (r) { edges[2 * o] = (u32)v; edges[2 * o + 1] = (u32)v + 1; }
+  cnt[t] = c;
+}
+__global__ void k_edge_write8(GView g, const u32* __restrict__ off, u32* __restrict__ edges) {
+  u64 t = SPB_GTID();
+  u64 v0 = t * 8;
+  if (v0 >= g.nV) return;
+  u64 w = *(const u64*)(g.vflags + v0);
+  u64 o = off[t];
+  for (u32 i = 0; i < 8 && v0 + i < g.nV; ++i) {
+    u32 fl = (u32)(w >> (8 * i)) & 0xFF;
+    u32 v = (u32)(v0 + i);
+    bool r = (fl & VF_R) != 0;
+    if (fl & VF_HASJ) {
+      u32 j = lower_bound_key(g.Jk, g.nJ, ((u64)v << 32) | v);
+      for (; j < g.nJ && (u32)(g.Jk[j] >> 32) == v; ++j) {
+        u32 d = (u32)g.Jk[j];
+        if (r && d > v + 1) { edges[2 * o] = v; edges[2 * o + 1] = v + 1; ++o; r = false; }
+        edges[2 * o] = v; edges[2 * o + 1] = d; ++o;
+      }
+    }
+    if (r) { edges[2 * o] = v; edges[2 * o + 1] = v + 1; ++o; }
+  }
 }
 
 // seqPaths (reference lib/vtools.pyx:18-49).  Along a sequence the vertex ids form monotone runs with

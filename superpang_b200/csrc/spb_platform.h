@@ -42,6 +42,7 @@ static inline u64 atomicAdd(u64* a, u64 v) { u64 o = *a; *a = o + v; return o; }
 static inline u32 atomicAdd(u32* a, u32 v) { u32 o = *a; *a = o + v; return o; }
 static inline u32 atomicOr(u32* a, u32 v) { u32 o = *a; *a = o | v; return o; }
 static inline int __popcll(u64 x) { return __builtin_popcountll(x); }
+static inline u32 __funnelshift_l(u32 lo, u32 hi, u32 sh) { sh &= 31; return sh ? (hi << sh) | (lo >> (32 - sh)) : hi; }
 static inline int __popc(u32 x) { return __builtin_popcount(x); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 template <class T> static inline T __ldcg(const T* p) { return *p; }
