@@ -123,7 +123,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="snp", choices=["snp", "block"])
     ap.add_argument("--ref-inst", type=int, default=600_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
