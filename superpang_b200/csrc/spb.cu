@@ -43,6 +43,9 @@ struct spb_ctx {
   u64 *voff = 0, *soff = 0, *ooff = 0;
   u32 *verts = 0, *origins = 0; u8* seqs = 0;
   u32* iv = 0; u64* iv_off = 0;
+  // staged dedup state (records sent by this rank)
+  u64 *dd_keys = 0, *dd_bstart = 0; u32* dd_pos = 0; u64 dd_n = 0, dd_lo = 0, dd_hi = 0; u32 dd_bb = 0; bool dd_fbits_ready = false;
+  std::vector<u64> dd_bstart_h;
   std::string stats;
 };
 
@@ -145,6 +148,13 @@ static int prim_sort_u64_u64(spb_ctx*, u64*& k, u64*& v, u64*& k2, u64*& v2, u64
   std::swap(k, k2); std::swap(v, v2); return 0;
 }
 static int prim_sort_u64(spb_ctx*, u64*& k, u64* k2, u64 n) { std::sort(k, k + n); (void)k2; return 0; }
+static int prim_partition_u64_u32(spb_ctx*, u64*& k, u32*& v, u64*& k2, u32*& v2, u64 n, int b0, int b1) {   // stable, by key bits [b0, b1)
+  std::vector<u64> idx(n); for (u64 i = 0; i < n; ++i) idx[i] = i;
+  u64 mask = (b1 - b0 >= 64) ? ~0ull : ((1ull << (b1 - b0)) - 1);
+  std::stable_sort(idx.begin(), idx.end(), [&](u64 a, u64 b) { return ((k[a] >> b0) & mask) < ((k[b] >> b0) & mask); });
+  for (u64 i = 0; i < n; ++i) { k2[i] = k[idx[i]]; v2[i] = v[idx[i]]; }
+  std::swap(k, k2); std::swap(v, v2); return 0;
+}
 static int prim_select_flag(spb_ctx*, const u8* flags, u8 mask, u64 n, u32* out, u32* count) {
   u32 m = 0; for (u64 i = 0; i < n; ++i) if (flags[i] & mask) out[m++] = (u32)i; *count = m; return 0;
 }
@@ -184,6 +194,14 @@ static int prim_sort_u64_u64(spb_ctx* c, u64*& k, u64*& v, u64*& k2, u64*& v2, u
   if (n == 0) return 0;
   cub::DoubleBuffer<u64> dk(k, k2); cub::DoubleBuffer<u64> dv(v, v2);
   CUB2(cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, (size_t)n, 0, 64, c->stream));
+  if (dk.Current() != k) { std::swap(k, k2); }
+  if (dv.Current() != v) { std::swap(v, v2); }
+  return 0;
+}
+static int prim_partition_u64_u32(spb_ctx* c, u64*& k, u32*& v, u64*& k2, u32*& v2, u64 n, int b0, int b1) {
+  if (n == 0) return 0;
+  cub::DoubleBuffer<u64> dk(k, k2); cub::DoubleBuffer<u32> dv(v, v2);
+  CUB2(cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, (size_t)n, b0, b1, c->stream));
   if (dk.Current() != k) { std::swap(k, k2); }
   if (dv.Current() != v) { std::swap(v, v2); }
   return 0;
@@ -379,55 +397,115 @@ int spb_load(spb_ctx* c, const uint8_t* ascii, const uint64_t* seq_off, uint32_t
   return SPB_OK;
 }
 
-int spb_build_dbg(spb_ctx* c, spb_counts* out) {
-  if (!c) return SPB_EINVAL;
-  if (c->state < 1) return fail(c, SPB_ESTATE, "spb_build_dbg before spb_load");
-  if (c->state > 1) return fail(c, SPB_ESTATE, "spb_build_dbg called twice; call spb_load again");
-#ifndef SPB_EMU
-  CK(cudaSetDevice(c->device));
-#endif
-  const u64 T = c->T; const u32 k = c->k;
-  StageTimer tm; char buf[256]; c->stats = "{";
-  // ---- K1: canonical extraction + dedup insert
-  tm.start(c);
-  u64 cap = 1024; while (cap < 2 * c->n_inst) cap <<= 1;
-  c->cnt.table_slots = cap;
-  u64* slots; ALLOC(slots, u64, cap);
-  dev_memset(c, slots, 0xFF, cap * 8);
+static u32 default_bucket_bits(u64 n_inst, u32 n_owners) {
+  u32 bb = 0;
+  while (bb < 14 && (n_inst >> bb) > 1200000ull) ++bb;      // ~1 M records per bucket: 16 MB scratch table, L2 resident
+  u32 need = 0; while ((1u << need) < n_owners) ++need;
+  return bb > need ? bb : need;
+}
+
+static int alloc_position_state(spb_ctx* c) {
+  if (c->sp) return 0;
   u64 nw32 = c->npos_pad / 32;
   ALLOC(c->sp, u32, c->npos_pad + 8);
   ALLOC(c->obits, u32, nw32 + 8); ALLOC(c->fbits, u32, nw32 + 8);
-  u32 *wbits, *dbits; ALLOC(wbits, u32, nw32 + 8); ALLOC(dbits, u32, nw32 + 8);
-  dev_memset(c, dbits, 0, (nw32 + 8) * 4);
-#ifdef SPB_EMU
-  dev_memset(c, c->obits, 0, (nw32 + 8) * 4); dev_memset(c, wbits, 0, (nw32 + 8) * 4);
-#else
-  dev_memset(c, c->obits + nw32, 0, 32); dev_memset(c, wbits + nw32, 0, 32);   // the grid writes every other word
-#endif
-  u64 grid = c->npos_pad / TPB;
-  switch ((2 * k + 31) / 32) {
-    case 7: launch_extract<7>(c, grid, slots, cap, wbits, dbits); break;       // k = 101
-    case 19: launch_extract<19>(c, grid, slots, cap, wbits, dbits); break;     // k = 301
-    case 32: launch_extract<32>(c, grid, slots, cap, wbits, dbits); break;     // k = 501
-    default: launch_extract<0>(c, grid, slots, cap, wbits, dbits); break;
+  dev_memset(c, c->obits, 0, (nw32 + 8) * 4); dev_memset(c, c->fbits, 0, (nw32 + 8) * 4);
+  return 0;
+}
+
+// S1: records of the positions [pos_lo, pos_hi) (pos_lo a multiple of 256), partitioned by the top `bb` hash bits
+static int dd_records(spb_ctx* c, u64 pos_lo, u64 pos_hi, u32 bb) {
+  int r0 = alloc_position_state(c); if (r0) return r0;
+  u64 n = nblk(pos_hi - pos_lo, TPB) * TPB;
+  u64 *keys, *keys2; u32 *pos, *pos2;
+  ALLOC(keys, u64, n); ALLOC(pos, u32, n);
+  u64 grid = n / TPB;
+  switch ((2 * c->k + 31) / 32) {
+    case 7:  SPB_LAUNCH(k_make_records<7>, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, keys, pos, c->obits); break;
+    case 19: SPB_LAUNCH(k_make_records<19>, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, keys, pos, c->obits); break;
+    case 32: SPB_LAUNCH(k_make_records<32>, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, keys, pos, c->obits); break;
+    default: SPB_LAUNCH(k_make_records<0>, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, keys, pos, c->obits); break;
   }
-  snprintf(buf, sizeof buf, "\"extract_insert_ms\": %.4f", tm.stop(c)); c->stats += buf;
-  // ---- K3: first appearances -> vertex ids
-  tm.start(c);
+  if (bb > 0) {
+    ALLOC(keys2, u64, n); ALLOC(pos2, u32, n);
+    PRIM(prim_partition_u64_u32(c, keys, pos, keys2, pos2, n, 64 - bb, 64));
+    dfree(c, keys2); dfree(c, pos2);
+  }
+  const u32 B = 1u << bb;
+  u64* coff; ALLOC(coff, u64, 2);
+  u64 co[2] = {0, n};
+  memcpy(c->pinned, co, 16); dev_copy(c, coff, c->pinned, 16);
+  ALLOC(c->dd_bstart, u64, B + 2);
+  SPB_LAUNCH(k_bucket_bounds, nblk(B + 1, TPB), TPB, c->stream, keys, coff, 1u, bb, 0u, B, c->dd_bstart);
+  c->dd_bstart_h.resize(B + 1);
+  dev_copy(c, c->dd_bstart_h.data(), c->dd_bstart, (B + 1) * 8ull); dev_sync(c);
+  dfree(c, coff);
+  c->dd_keys = keys; c->dd_pos = pos; c->dd_n = n; c->dd_lo = pos_lo; c->dd_hi = pos_hi; c->dd_bb = bb;
+  return 0;
+}
+
+// S2: deduplicate the records of buckets [b_lo, b_hi) received in `nchunks` bucket-sorted chunks; rep[i] = first position
+static int dd_owner(spb_ctx* c, const u64* keys, const u32* pos, const u64* chunk_counts, u32 nchunks, u32 bb, u32 b_lo, u32 b_hi, u32* rep) {
+  const u32 B = b_hi - b_lo;
+  std::vector<u64> coff_h(nchunks + 1, 0);
+  for (u32 r = 0; r < nchunks; ++r) coff_h[r + 1] = coff_h[r] + chunk_counts[r];
+  if (coff_h[nchunks] == 0) return 0;
+  u64 *coff, *sub;
+  ALLOC(coff, u64, nchunks + 1); ALLOC(sub, u64, (u64)nchunks * (B + 1));
+  dev_copy(c, coff, coff_h.data(), (nchunks + 1) * 8ull); dev_sync(c);
+  SPB_LAUNCH(k_bucket_bounds, nblk((u64)nchunks * (B + 1), TPB), TPB, c->stream, keys, coff, nchunks, bb, b_lo, B, sub);
+  std::vector<u64> sub_h((u64)nchunks * (B + 1));
+  dev_copy(c, sub_h.data(), sub, sub_h.size() * 8); dev_sync(c);
+  std::vector<u64> nb(B, 0); u64 nmax = 0;
+  for (u32 b = 0; b < B; ++b) { for (u32 r = 0; r < nchunks; ++r) nb[b] += sub_h[(u64)r * (B + 1) + b + 1] - sub_h[(u64)r * (B + 1) + b]; nmax = std::max(nmax, nb[b]); }
+  u64 cap = 1024; while (cap < 2 * nmax) cap <<= 1;
+  c->cnt.table_slots = cap;
+  u64* scratch[2]; ALLOC(scratch[0], u64, cap); ALLOC(scratch[1], u64, cap);
+  dev_memset(c, scratch[0], 0xFF, cap * 8);
+  BktView v{keys, pos, rep, coff, sub, nchunks, B, 0};
+  u32 step = 0;
+  for (u32 b = 0; b < B; ++b) {
+    if (nb[b] == 0) continue;
+    v.b = b;
+    u64* cur = scratch[step & 1]; u64* other = scratch[(step & 1) ^ 1];
+    SPB_LAUNCH(k_bkt_insert, nblk(nb[b], TPB), TPB, c->stream, v, nb[b], c->F, c->R, c->T, c->k, cur, cap - 1);
+    u64 g = std::max<u64>(nblk(nb[b], TPB), std::min<u64>(nblk(cap, TPB), 148 * 8));
+    SPB_LAUNCH(k_bkt_final, g, TPB, c->stream, v, nb[b], cur, other, cap);
+    ++step;
+  }
+  dfree(c, scratch[0]); dfree(c, scratch[1]); dfree(c, coff); dfree(c, sub);
+  return 0;
+}
+
+// S3: scatter the representatives of the records this rank produced back to position order
+static int dd_scatter(spb_ctx* c, const u32* rep) {
+  const u32 B = 1u << c->dd_bb;
+  u64 maxlen = 0;
+  for (u32 b = 0; b < B; ++b) maxlen = std::max(maxlen, c->dd_bstart_h[b + 1] - c->dd_bstart_h[b]);
+  SPB_LAUNCH(k_unpartition, nblk(maxlen * B, TPB), TPB, c->stream, c->dd_pos, rep, c->dd_bstart, B, c->sp, c->fbits);
+  dfree(c, c->dd_keys); dfree(c, c->dd_pos); dfree(c, c->dd_bstart);
+  return 0;
+}
+
+// vertex ids for the positions [lo, hi) + the vertex table (needs the complete fbits bitmap)
+static int dd_ids(spb_ctx* c, u64 lo, u64 hi, const u64* slots) {
+  const u64 T = c->T;
   u64 nb = c->npos_pad / 256;
   u32 *blkcnt, *blkoff; ALLOC(blkcnt, u32, nb); ALLOC(blkoff, u32, nb);
-  SPB_LAUNCH(k_first_bits, nblk(nb, TPB), TPB, c->stream, wbits, dbits, c->fbits, blkcnt, nb);
-  dev_memset(c, c->fbits + nw32, 0, 32);
+  SPB_LAUNCH(k_block_counts, nblk(nb, TPB), TPB, c->stream, c->fbits, blkcnt, nb);
   u64 nV = 0;
   PRIM(prim_scan_u32(c, blkcnt, blkoff, nb, &nV));
   c->nV = (u32)nV;
   ALLOC(c->v2pos, u32, nV + 1); ALLOC(c->vflags, u8, nV + 64);
   dev_memset(c, c->vflags + (nV & ~7ull), 0, 64);
-  SPB_LAUNCH(k_assign_ids, nblk(T, TPB), TPB, c->stream, c->sp, c->vbits, T, c->fbits, blkoff, slots, c->v2pos, c->vflags);
-  dfree(c, blkcnt); dfree(c, blkoff); dfree(c, slots); dfree(c, wbits); dfree(c, dbits);
-  snprintf(buf, sizeof buf, ", \"vertex_ids_ms\": %.4f", tm.stop(c)); c->stats += buf;
-  // ---- K4: junction edges
-  tm.start(c);
+  SPB_LAUNCH(k_assign_ids, nblk(T, TPB), TPB, c->stream, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, slots, c->v2pos, c->vflags);
+  dfree(c, blkcnt); dfree(c, blkoff);
+  return 0;
+}
+
+// junction edges, sequence limits, explicit edge list (needs the complete sp / obits arrays)
+static int dd_graph(spb_ctx* c) {
+  const u64 T = c->T; const u32 k = c->k; const u64 nV = c->nV;
   u64* jcount; ALLOC(jcount, u64, 2);
   u64 jcap = std::max<u64>(4096, c->n_inst / 8);
   u64* Jk = nullptr; u8* Js = nullptr; u64 nj = 0;
@@ -450,7 +528,6 @@ int spb_build_dbg(spb_ctx* c, spb_counts* out) {
   SPB_LAUNCH(k_mark_hasj, nblk(c->nJ, TPB), TPB, c->stream, c->Jk, c->nJ, c->vflags);
   ALLOC(c->seqlim, u32, 2ull * c->n_seq);
   SPB_LAUNCH(k_mark_seqlim, nblk(c->n_seq, TPB), TPB, c->stream, c->seq_off, c->n_seq, k, c->sp, c->vflags, c->seqlim);
-  // ---- explicit edge list
   GView g{c->vflags, c->Jk, c->Js, c->nJ, c->nV};
   u64 nT = (nV + 7) / 8;
   u32 *ecnt, *eoff; ALLOC(ecnt, u32, nT + 1); ALLOC(eoff, u32, nT + 1);
@@ -460,10 +537,76 @@ int spb_build_dbg(spb_ctx* c, spb_counts* out) {
   ALLOC(c->edges, u32, 2 * nE + 2);
   SPB_LAUNCH(k_edge_write8, nblk(nT, TPB), TPB, c->stream, g, eoff, c->edges);
   dfree(c, ecnt); dfree(c, eoff);
+  c->cnt.n_vertices = nV; c->cnt.n_edges = nE; c->cnt.n_junction = c->nJ;
+  return 0;
+}
+
+// the older single-table dedup (two random HBM accesses per instance); kept selectable for A/B measurements
+static int dedup_global_table(spb_ctx* c) {
+  const u64 T = c->T;
+  int r0 = alloc_position_state(c); if (r0) return r0;
+  u64 cap = 1024; while (cap < 2 * c->n_inst) cap <<= 1;
+  c->cnt.table_slots = cap;
+  u64* slots; ALLOC(slots, u64, cap);
+  dev_memset(c, slots, 0xFF, cap * 8);
+  u64 nw32 = c->npos_pad / 32;
+  u32 *wbits, *dbits; ALLOC(wbits, u32, nw32 + 8); ALLOC(dbits, u32, nw32 + 8);
+  dev_memset(c, dbits, 0, (nw32 + 8) * 4); dev_memset(c, wbits, 0, (nw32 + 8) * 4);
+  u64 grid = c->npos_pad / TPB;
+  switch ((2 * c->k + 31) / 32) {
+    case 7: launch_extract<7>(c, grid, slots, cap, wbits, dbits); break;       // k = 101
+    case 19: launch_extract<19>(c, grid, slots, cap, wbits, dbits); break;     // k = 301
+    case 32: launch_extract<32>(c, grid, slots, cap, wbits, dbits); break;     // k = 501
+    default: launch_extract<0>(c, grid, slots, cap, wbits, dbits); break;
+  }
+  u64 nb = c->npos_pad / 256;
+  u32* blkcnt; ALLOC(blkcnt, u32, nb);
+  SPB_LAUNCH(k_first_bits, nblk(nb, TPB), TPB, c->stream, wbits, dbits, c->fbits, blkcnt, nb);
+  dev_memset(c, c->fbits + nw32, 0, 32);
+  dfree(c, blkcnt); dfree(c, wbits); dfree(c, dbits);
+  int r = dd_ids(c, 0, T, slots);
+  dfree(c, slots);
+  return r;
+}
+
+int spb_build_dbg(spb_ctx* c, spb_counts* out) {
+  if (!c) return SPB_EINVAL;
+  if (c->state < 1) return fail(c, SPB_ESTATE, "spb_build_dbg before spb_load");
+  if (c->state > 1) return fail(c, SPB_ESTATE, "spb_build_dbg called twice; call spb_load again");
+#ifndef SPB_EMU
+  CK(cudaSetDevice(c->device));
+#endif
+  StageTimer tm; char buf[256]; c->stats = "{";
+  const char* mode = getenv("SPB_DEDUP");
+  if (mode && !strcmp(mode, "global")) {
+    tm.start(c);
+    PRIM(dedup_global_table(c));
+    snprintf(buf, sizeof buf, "\"dedup_global_ms\": %.4f", tm.stop(c)); c->stats += buf;
+  } else {
+    // ---- S1: records + partition
+    tm.start(c);
+    u32 bb = default_bucket_bits(c->n_inst, 1);
+    if (const char* e = getenv("SPB_BUCKET_BITS")) bb = (u32)atoi(e);
+    PRIM(dd_records(c, 0, c->T, bb));
+    snprintf(buf, sizeof buf, "\"records_partition_ms\": %.4f", tm.stop(c)); c->stats += buf;
+    // ---- S2: L2-staged dedup per bucket
+    tm.start(c);
+    u32* rep; ALLOC(rep, u32, c->dd_n + 1);
+    u64 cc = c->dd_n;
+    PRIM(dd_owner(c, c->dd_keys, c->dd_pos, &cc, 1, bb, 0, 1u << bb, rep));
+    snprintf(buf, sizeof buf, ", \"bucket_dedup_ms\": %.4f", tm.stop(c)); c->stats += buf;
+    // ---- S3 + ids
+    tm.start(c);
+    PRIM(dd_scatter(c, rep));
+    dfree(c, rep);
+    PRIM(dd_ids(c, 0, c->T, nullptr));
+    snprintf(buf, sizeof buf, ", \"scatter_ids_ms\": %.4f", tm.stop(c)); c->stats += buf;
+  }
+  tm.start(c);
+  PRIM(dd_graph(c));
   snprintf(buf, sizeof buf, ", \"edges_ms\": %.4f", tm.stop(c)); c->stats += buf;
   int r = check_err(c, "spb_build_dbg");
   if (r) return r;
-  c->cnt.n_vertices = nV; c->cnt.n_edges = nE; c->cnt.n_junction = c->nJ;
   c->state = 2;
   if (out) *out = c->cnt;
   return SPB_OK;

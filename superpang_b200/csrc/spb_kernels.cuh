@@ -232,6 +232,122 @@ k_extract_insert(const u32* __restrict__ F, const u32* __restrict__ R, const u32
   store_bit(wbits, p, won);
 }
 
+// ------------------------------------------------------------------------------------ staged dedup
+// The global table above needs two random HBM row activations per instance.  The staged path keeps
+// the table in L2 instead: (S1) every instance becomes a 12-byte record (64-bit hash with the
+// orientation in bit 0, position), the records are radix-partitioned by the top hash bits into
+// buckets of ~1 M records; (S2) each bucket is deduplicated in a small scratch table that lives in L2;
+// (S3) the representatives are scattered back to position order bucket-interleaved ("i-major"), so
+// that writes to one sector happen close together in time and merge in L2.  With several GPUs the
+// buckets are the unit of ownership: S1 and S3 run on the GPU that owns the positions, S2 on the GPU
+// that owns the bucket, with an all-to-all of records before and of representatives after S2.
+template <int W> __global__ void SPB_LAUNCH_BOUNDS(256)
+k_make_records(const u32* __restrict__ F, const u32* __restrict__ R, const u32* __restrict__ vbits, u64 T, u32 k,
+               u64 pos_lo, u64 pos_hi, u64* __restrict__ keys, u32* __restrict__ pos, u32* obits) {
+  u64 i = SPB_GTID();
+  u64 p = pos_lo + i;
+  bool valid = p < pos_hi && get_bit(vbits, p);
+  bool o = false;
+  u64 key = ~0ull;
+  if (valid) {
+    u64 ra = T - p - k;
+    const u32* x = F + (p >> 4); const u32* y = R + (ra >> 4);
+    u32 lx = __funnelshift_l(__ldg(x + 1), __ldg(x), (u32)(p & 15) * 2), ly = __funnelshift_l(__ldg(y + 1), __ldg(y), (u32)(ra & 15) * 2);
+    o = (lx != ly) ? (lx > ly) : (win_cmp(F, p, R, ra, k) >= 0);
+    u64 h = win_hash<W>(o ? F : R, o ? p : ra, k);
+    key = (h & ~1ull) | (o ? 1ull : 0ull);
+    if (key == ~0ull) key ^= 2ull;
+  }
+  keys[i] = key; pos[i] = (u32)p;
+  store_bit(obits, p, o);
+}
+
+// sub[r * (B + 1) + b] = first record of chunk r whose bucket (top `bb` bits of the key) is >= b_lo + b
+__global__ void k_bucket_bounds(const u64* __restrict__ keys, const u64* __restrict__ chunk_off, u32 nchunks, u32 bb, u32 b_lo, u32 B,
+                                u64* __restrict__ sub) {
+  u64 g = SPB_GTID();
+  if (g >= (u64)nchunks * (B + 1)) return;
+  u32 r = (u32)(g / (B + 1)), b = (u32)(g % (B + 1));
+  u64 lo = chunk_off[r], hi = chunk_off[r + 1];
+  u64 bucket = (u64)b_lo + b;
+  if (bb == 0) { sub[g] = b ? hi - chunk_off[r] : 0; return; }
+  u64 a = lo, e = hi;
+  while (a < e) { u64 mid = (a + e) >> 1; if ((__ldg(keys + mid) >> (64 - bb)) < bucket) a = mid + 1; else e = mid; }
+  sub[g] = a - lo;
+}
+
+struct BktView {
+  const u64* keys; const u32* pos; u32* sidx;      // records (all chunks concatenated) and per-record slot / representative
+  const u64* chunk_off; const u64* sub;            // chunk offsets [nchunks+1], sub-range table [nchunks][B+1]
+  u32 nchunks, B, b;                               // b = bucket index relative to b_lo
+};
+__device__ __forceinline__ u64 bkt_record(const BktView& v, u64 t) {   // t-th record of bucket v.b -> index into the record arrays
+  for (u32 r = 0; r < v.nchunks; ++r) {
+    u64 s0 = v.sub[(u64)r * (v.B + 1) + v.b], s1 = v.sub[(u64)r * (v.B + 1) + v.b + 1];
+    if (t < s1 - s0) return v.chunk_off[r] + s0 + t;
+    t -= s1 - s0;
+  }
+  return ~0ull;
+}
+__global__ void SPB_LAUNCH_BOUNDS(256)
+k_bkt_insert(BktView v, u64 n_b, const u32* __restrict__ F, const u32* __restrict__ R, u64 T, u32 k, u64* scratch, u64 capmask) {
+  u64 t = SPB_GTID();
+  if (t >= n_b) return;
+  u64 rec = bkt_record(v, t);
+  u64 key = v.keys[rec];
+  if (key == ~0ull) { v.sidx[rec] = SPB_INVALID; return; }
+  u64 p = v.pos[rec];
+  bool o = key & 1;
+  u64 tag = (key >> 1) & 0x7FFFFFull, idx = (key >> 24) & capmask;
+  u64 entry = (tag << 40) | (p << 1) | (o ? 1ull : 0ull);
+  const u32* S = o ? F : R;
+  u64 a = o ? p : T - p - k;
+  for (;;) {
+    u64 cur = atomicCAS(scratch + idx, SPB_EMPTY, entry);
+    if (cur == SPB_EMPTY) break;
+    if ((cur >> 40) == tag) {
+      u64 q = (cur >> 1) & SPB_POSMASK;
+      bool oq = cur & 1;
+      if (q == p || win_cmp(S, a, oq ? F : R, oq ? q : T - q - k, k) == 0) {
+        if (entry < cur) atomicMin(scratch + idx, entry);
+        break;
+      }
+    }
+    idx = (idx + 1) & capmask;
+  }
+  v.sidx[rec] = (u32)idx;
+}
+// representative of every record of the bucket; the same launch clears the other scratch table
+__global__ void k_bkt_final(BktView v, u64 n_b, const u64* __restrict__ scratch, u64* clear, u64 clear_n) {
+  u64 t = SPB_GTID();
+  if (t < n_b) {
+    u64 rec = bkt_record(v, t);
+    u32 si = v.sidx[rec];
+    if (si != SPB_INVALID) v.sidx[rec] = (u32)((scratch[si] >> 1) & SPB_POSMASK);
+  }
+  u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 j = t; j < clear_n; j += stride) clear[j] = SPB_EMPTY;
+}
+// S3: bucket-interleaved scatter back to position order
+__global__ void k_unpartition(const u32* __restrict__ pos, const u32* __restrict__ rep, const u64* __restrict__ bstart, u32 B, u32* __restrict__ sp, u32* fbits) {
+  u64 g = SPB_GTID();
+  u32 b = (u32)(g % B);
+  u64 rec = bstart[b] + g / B;
+  if (rec >= bstart[b + 1]) return;
+  u32 r = rep[rec];
+  if (r == SPB_INVALID) return;
+  u32 p = pos[rec];
+  if (r == p) atomicOr(fbits + (p >> 5), 1u << (p & 31));
+  else sp[p] = r;
+}
+__global__ void k_block_counts(const u32* __restrict__ fbits, u32* __restrict__ cnt, u64 nblk) {
+  u64 b = SPB_GTID();
+  if (b >= nblk) return;
+  u32 c = 0;
+  for (u32 j = 0; j < 8; ++j) c += __popc(fbits[b * 8 + j]);
+  cnt[b] = c;
+}
+
 // first-appearance bitmap fbits = wbits & ~dbits, and per 256-position block counts
 __global__ void k_first_bits(const u32* __restrict__ wbits, const u32* __restrict__ dbits, u32* __restrict__ fbits, u32* __restrict__ cnt, u64 nblk) {
   u64 b = SPB_GTID();
@@ -252,15 +368,17 @@ __device__ __forceinline__ u32 rank_first(const u32* fbits, const u32* blkoff, u
 // K3: vertex ids (= rank of the representative among first appearances), vertex -> first position,
 // implicit-edge bit.  `sp` holds the slot index of every instance on entry and vertex ids on exit;
 // only instances that are not first appearances read their representative back from the table.
-__global__ void k_assign_ids(u32* __restrict__ sp, const u32* __restrict__ vbits, u64 T, const u32* __restrict__ fbits,
+__global__ void k_assign_ids(u32* __restrict__ sp, const u32* __restrict__ vbits, u64 T, u64 lo, u64 hi, const u32* __restrict__ fbits,
                              const u32* __restrict__ blkoff, const u64* __restrict__ slots, u32* __restrict__ v2pos, u8* __restrict__ vflags) {
   u64 p = SPB_GTID();
   if (p >= T) return;
-  if (!get_bit(vbits, p)) { sp[p] = SPB_INVALID; return; }
+  bool mine = p >= lo && p < hi;                 // multi-GPU: sp is filled for the local slice only, the vertex table everywhere
+  if (!get_bit(vbits, p)) { if (mine) sp[p] = SPB_INVALID; return; }
   bool first = get_bit(fbits, p);
-  u32 r = first ? (u32)p : (u32)((__ldcg(slots + sp[p]) >> 1) & SPB_POSMASK);
+  if (!first && !mine) return;
+  u32 r = first ? (u32)p : (slots ? (u32)((__ldcg(slots + sp[p]) >> 1) & SPB_POSMASK) : sp[p]);   // staged path: sp already holds the representative
   u32 vid = rank_first(fbits, blkoff, r);
-  sp[p] = vid;
+  if (mine) sp[p] = vid;
   if (first) {
     v2pos[vid] = (u32)p;
     vflags[vid] = get_bit(fbits, p + 1) ? VF_R : 0;   // (p, p+1) both first appearances => edge (vid, vid+1)
