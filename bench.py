@@ -219,15 +219,24 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-        # dominant kernel = k_extract_insert; its algorithmic bytes: SURVEY §8(d) key produce + consume (16W B / instance)
-        # + unique key stored (8W B / vertex)
+        # per-stage share of the SURVEY 8(d) byte model (184 B / instance + 112 B / vertex + 1 B / NBP base at k=301)
         W = (2 * K + 63) // 64
         st_keys = sorted(stages[0])
         st_mean = {k_: float(np.mean([s[k_] for s in stages])) for k_ in st_keys}
-        dom = max(st_mean, key=st_mean.get)
-        dom_bytes = counts["n_inst"] * 16 * W + counts["n_vertices"] * 8 * W
-        ach = dom_bytes / (st_mean["extract_insert_ms"] / 1e3) / 1e9
-        pipe_bytes = algorithmic_bytes(counts["n_inst"], counts["n_vertices"], counts["nbp_bases"])
+        ni, nv, nbb = counts["n_inst"], counts["n_vertices"], counts["nbp_bases"]
+        groups = {
+            "dedup (k_make_records + radix partition + k_bkt_insert/k_bkt_final)":
+                (("records_partition_ms", "bucket_dedup_ms", "dedup_global_ms"), 16 * W * ni + 8 * W * nv),
+            "ids (k_unpartition + k_assign_ids)": (("scatter_ids_ms",), 4 * ni + 8 * nv),
+            "edges (k_junction_emit + k_edge_*)": (("edges_ms",), 20 * ni + 8 * nv),
+            "compaction (k_classify8 .. k_rank_jump)": (("classify_rank_ms",), 16 * nv),
+            "emit (k_emit_darts + k_emit_ends)": (("emit_ms",), nbb),
+        }
+        gtime = {g: sum(st_mean.get(k_, 0.0) for k_ in ks) for g, (ks, _) in groups.items()}
+        dom = max(gtime, key=gtime.get)
+        dom_bytes, dom_ms = groups[dom][1], gtime[dom]
+        ach = dom_bytes / (dom_ms / 1e3) / 1e9
+        pipe_bytes = algorithmic_bytes(ni, nv, nbb)
         pipe_ach = pipe_bytes / (ms / args.steps / 1e3) / 1e9
         line = dict(
             metric="canonical k-mers/s through DBG build+NBP compaction at k=301", value=value, unit="k-mers/s",
@@ -239,8 +248,8 @@ def main():
             e2e=dict(value=e2e_value, unit="k-mers/s", ms_per_step=ms_e2e / args.steps, h2d_bytes_per_step=int(buf.nbytes + off.nbytes),
                      d2h_bytes_per_step=int(e2e_last[1])),
             gpu_launches=int(launches),
-            roofline=dict(bound="hbm", kernel="k_extract_insert", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None,
-                          peak_source=peak_src, kernel_ms=st_mean["extract_insert_ms"], dominant_stage=dom,
+            roofline=dict(bound="hbm", kernel=dom, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None,
+                          peak_source=peak_src, kernel_ms=dom_ms, model_bytes=dom_bytes,
                           pipeline=dict(achieved=pipe_ach, frac=pipe_ach / peak, bytes=pipe_bytes)),
             stages_ms=st_mean,
             clocks=sampler.summary(),

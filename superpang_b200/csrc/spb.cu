@@ -385,7 +385,8 @@ int spb_load(spb_ctx* c, const uint8_t* ascii, const uint64_t* seq_off, uint32_t
   u64 nwp = c->nw + W + 8;
   ALLOC(c->F, u32, nwp); ALLOC(c->R, u32, nwp);
   dev_memset(c, c->F + c->nw, 0, (nwp - c->nw) * 4); dev_memset(c, c->R + c->nw, 0, (nwp - c->nw) * 4);
-  SPB_LAUNCH(k_pack, nblk(c->nw, TPB), TPB, c->stream, d_ascii, T, c->F, c->R, c->nw, c->errflag);
+  SPB_LAUNCH(k_pack, nblk(c->nw, TPB), TPB, c->stream, d_ascii, T, c->F, c->nw, c->errflag);
+  SPB_LAUNCH(k_pack_rc, nblk(c->nw, TPB), TPB, c->stream, c->F, T, c->R, c->nw);
   u64 nw32 = c->npos_pad / 32;
   ALLOC(c->vbits, u32, nw32 + 8);
   SPB_LAUNCH(k_valid_bits, nblk(nw32 + 8, TPB), TPB, c->stream, c->seq_off, n_seq, T, k, c->vbits, nw32 + 8);
@@ -512,7 +513,7 @@ static int dd_graph(spb_ctx* c) {
   for (int attempt = 0; attempt < 2; ++attempt) {
     ALLOC(Jk, u64, jcap); ALLOC(Js, u8, jcap);
     dev_memset(c, jcount, 0, 16);
-    SPB_LAUNCH(k_junction_emit, nblk(T, TPB), TPB, c->stream, c->sp, T, c->vflags, c->v2pos, c->obits, Jk, Js, jcount, jcap);
+    SPB_LAUNCH(k_junction_emit, nblk(T, TPB), TPB, c->stream, c->sp, T, c->fbits, c->vflags, c->v2pos, c->obits, Jk, Js, jcount, jcap);
     nj = dread(c, jcount);
     if (nj <= jcap) break;
     dfree(c, Jk); dfree(c, Js); jcap = nj;
@@ -535,7 +536,7 @@ static int dd_graph(spb_ctx* c) {
   u64 nE = 0;
   PRIM(prim_scan_u32(c, ecnt, eoff, nT, &nE));
   ALLOC(c->edges, u32, 2 * nE + 2);
-  SPB_LAUNCH(k_edge_write8, nblk(nT, TPB), TPB, c->stream, g, eoff, c->edges);
+  SPB_LAUNCH(k_edge_write, nblk(nV, TPB), TPB, c->stream, g, eoff, c->edges);
   dfree(c, ecnt); dfree(c, eoff);
   c->cnt.n_vertices = nV; c->cnt.n_edges = nE; c->cnt.n_junction = c->nJ;
   return 0;
@@ -577,8 +578,11 @@ int spb_build_dbg(spb_ctx* c, spb_counts* out) {
   CK(cudaSetDevice(c->device));
 #endif
   StageTimer tm; char buf[256]; c->stats = "{";
+  // Default: single global table (two random HBM accesses per instance).  SPB_DEDUP=staged selects the partitioned
+  // path (records -> buckets -> L2 scratch tables -> scatter back); measured slower on one GPU in round 1
+  // (profiles/README.md), its stages are what the multi-GPU exchange is built from.
   const char* mode = getenv("SPB_DEDUP");
-  if (mode && !strcmp(mode, "global")) {
+  if (!(mode && !strcmp(mode, "staged"))) {
     tm.start(c);
     PRIM(dedup_global_table(c));
     snprintf(buf, sizeof buf, "\"dedup_global_ms\": %.4f", tm.stop(c)); c->stats += buf;

@@ -133,21 +133,43 @@ __device__ __forceinline__ u32 ascii_code(u32 c, u32* bad) {
   u32 t = (c >> 1) & 3u;        // A0 C1 T2 G3
   return t ^ (t >> 1);          // A0 C1 G2 T3
 }
-__global__ void k_pack(const u8* __restrict__ ascii, u64 T, u32* __restrict__ F, u32* __restrict__ R, u64 nw, u32* err) {
+__global__ void k_pack(const u8* __restrict__ ascii, u64 T, u32* __restrict__ F, u64 nw, u32* err) {
   u64 w = SPB_GTID();
   if (w >= nw) return;
-  u32 f = 0, r = 0, bad = 0;
-  for (u32 j = 0; j < 16; ++j) {
-    u64 p = w * 16 + j;
-    u32 cf = 0, cr = 0;
-    if (p < T) {
-      cf = ascii_code(__ldg(ascii + p), &bad);
-      cr = 3u - ascii_code(__ldg(ascii + (T - 1 - p)), &bad);
+  u32 f = 0, bad = 0;
+  u64 p0 = w * 16;
+  if (p0 + 16 <= T && ((size_t)(ascii + p0) & 15) == 0) {
+    const u32* q = (const u32*)(ascii + p0);
+    for (u32 j = 0; j < 4; ++j) {
+      u32 c4 = __ldg(q + j);
+      for (u32 i = 0; i < 4; ++i) f = (f << 2) | ascii_code((c4 >> (8 * i)) & 0xFF, &bad);
     }
-    f = (f << 2) | cf; r = (r << 2) | cr;
+  } else {
+    for (u32 j = 0; j < 16; ++j) { u64 p = p0 + j; f = (f << 2) | (p < T ? ascii_code(__ldg(ascii + p), &bad) : 0u); }
   }
-  F[w] = f; R[w] = r;
+  F[w] = f;
   if (bad) atomicOr(err, (u32)ERR_BADCHAR);
+}
+// reverse-complement strand from the packed forward strand: R[t] = 3 - F[T-1-t]
+__device__ __forceinline__ u32 revcomp16(u32 x) {       // reverse the sixteen 2-bit groups and complement them
+  u32 y = __brev(x);
+  y = ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
+  return ~y;
+}
+__global__ void k_pack_rc(const u32* __restrict__ F, u64 T, u32* __restrict__ R, u64 nw) {
+  u64 w = SPB_GTID();
+  if (w >= nw) return;
+  u64 r0 = w * 16;                                   // R bases [r0, r0+16) = complement of F bases [T-r0-16, T-r0) reversed
+  u32 out;
+  if (r0 + 16 <= T) {
+    u64 a = T - r0 - 16;
+    u32 x = __funnelshift_l(__ldg(F + (a >> 4) + 1), __ldg(F + (a >> 4)), (u32)(a & 15) * 2);
+    out = revcomp16(x);
+  } else {
+    out = 0;
+    for (u32 j = 0; j < 16; ++j) { u64 t = r0 + j; u32 c = t < T ? 3u - base_at(F, T - 1 - t) : 0u; out = (out << 2) | c; }
+  }
+  R[w] = out;
 }
 
 // valid-start bitmap: bit p set iff a k-mer of some sequence starts at p.  One thread per 32 positions.
@@ -387,11 +409,11 @@ __global__ void k_assign_ids(u32* __restrict__ sp, const u32* __restrict__ vbits
 
 // K4: junction candidates.  The instance pair (p, p+1) yields edge {sp[p], sp[p+1]} (reference
 // lib/Assembler.py:199-201).  It is dropped when it coincides with an implicit edge (v, v+1).
-__global__ void k_junction_emit(const u32* __restrict__ sp, u64 T, const u8* __restrict__ vflags, const u32* __restrict__ v2pos,
+__global__ void k_junction_emit(const u32* __restrict__ sp, u64 T, const u32* __restrict__ fbits, const u8* __restrict__ vflags, const u32* __restrict__ v2pos,
                                 const u32* __restrict__ obits, u64* __restrict__ Jk, u8* __restrict__ Js, u64* counter, u64 cap) {
   u64 p = SPB_GTID();
   u32 n = 0, u = 0, w = 0;
-  if (p + 1 < T) {
+  if (p + 1 < T && !(get_bit(fbits, p) && get_bit(fbits, p + 1))) {    // two consecutive first appearances: implicit edge
     u = sp[p]; w = sp[p + 1];
     if (u != SPB_INVALID && w != SPB_INVALID) {
       bool implicit = (w == u + 1 && (vflags[u] & VF_R)) || (u == w + 1 && (vflags[w] & VF_R));
@@ -730,37 +752,51 @@ __global__ void k_dart_chunks(const u32* __restrict__ plo, const u32* __restrict
   u32 len = phi[d >> 1] - plo[d >> 1] + 1;
   nch[d] = (len + SPB_CHUNK - 1) / SPB_CHUNK;
 }
+struct ChunkParams { u64 vo, so, src; u32 lo, hi, un, t0, n; u32 up; };
+__device__ __forceinline__ ChunkParams chunk_params(u32 c, const u32* choff, u32 nD, const u32* plo, const u32* phi, const u32* dart_nbp,
+                                                    const u32* acc, u32 k, u64 T, const u32* v2pos, const u64* voff, const u64* soff) {
+  ChunkParams q;
+  u32 d = upper_bound_u32(choff, nD, c) - 1;
+  u32 P = d >> 1; q.up = !(d & 1);
+  q.lo = plo[P]; q.hi = phi[P];
+  u32 len = q.hi - q.lo + 1;
+  u32 id = dart_nbp[d];
+  u32 un = dart_nbp[d ^ 1]; q.un = id < un ? id : un;
+  q.vo = voff[id] + acc[d]; q.so = soff[id] + (k - 1) + acc[d];
+  q.src = q.up ? (u64)v2pos[q.lo] + k - 1 : T - 1 - (u64)v2pos[q.hi];
+  q.t0 = (c - choff[d]) * SPB_CHUNK;
+  q.n = len - q.t0 < SPB_CHUNK ? len - q.t0 : SPB_CHUNK;
+  return q;
+}
 __global__ void SPB_LAUNCH_BOUNDS(256)
 k_emit_darts(const u32* __restrict__ choff, u32 nD, const u32* __restrict__ plo, const u32* __restrict__ phi,
              const u32* __restrict__ dart_nbp, const u32* __restrict__ acc, u32 k, u64 T, const u32* __restrict__ F,
              const u32* __restrict__ R, const u32* __restrict__ v2pos, const u64* __restrict__ voff,
              const u64* __restrict__ soff, u32* __restrict__ verts, u8* __restrict__ seq, u32* __restrict__ vnbp) {
-  u32 c = blockIdx.x;
-  u32 d = upper_bound_u32(choff, nD, c) - 1;
-  u32 P = d >> 1; bool up = !(d & 1);
-  u32 lo = plo[P], hi = phi[P], len = hi - lo + 1;
-  u32 id = dart_nbp[d];
-  u32 un = dart_nbp[d ^ 1]; if (id < un) un = id;
-  u64 vo = voff[id] + acc[d], so = soff[id] + (k - 1) + acc[d];
-  u64 src = up ? (u64)v2pos[lo] + k - 1 : T - 1 - (u64)v2pos[hi];
-  const u32* S = up ? F : R;
-  u32 t0 = (c - choff[d]) * SPB_CHUNK;
-  u32 n = len - t0 < SPB_CHUNK ? len - t0 : SPB_CHUNK;
-  for (u32 t = t0 + threadIdx.x; t < t0 + n; t += blockDim.x) {
-    u32 v = up ? lo + t : hi - t;
-    verts[vo + t] = v;
-    if (up) vnbp[v] = un;
+#ifdef SPB_EMU
+  ChunkParams q = chunk_params(blockIdx.x, choff, nD, plo, phi, dart_nbp, acc, k, T, v2pos, voff, soff);
+#else
+  __shared__ ChunkParams qs;                        // one binary search per block instead of one per thread
+  if (threadIdx.x == 0) qs = chunk_params(blockIdx.x, choff, nD, plo, phi, dart_nbp, acc, k, T, v2pos, voff, soff);
+  __syncthreads();
+  ChunkParams q = qs;
+#endif
+  const u32* S = q.up ? F : R;
+  for (u32 t = q.t0 + threadIdx.x; t < q.t0 + q.n; t += blockDim.x) {
+    u32 v = q.up ? q.lo + t : q.hi - t;
+    verts[q.vo + t] = v;
+    if (q.up) vnbp[v] = q.un;
   }
   // sequence bytes: one aligned 4-byte word of the output per thread (4 bases = 8 bits of the strand)
-  u64 D0 = so + t0, D1 = D0 + n;
+  u64 D0 = q.so + q.t0, D1 = D0 + q.n;
   for (u64 wq = (D0 & ~3ull) + 4ull * threadIdx.x; wq < D1; wq += 4ull * blockDim.x) {
     u64 b0 = wq < D0 ? D0 : wq, b1 = wq + 4 < D1 ? wq + 4 : D1;
-    u64 i = src + (b0 - so);                         // strand base index of the first byte we write
+    u64 i = q.src + (b0 - q.so);                     // strand base index of the first byte we write
     u32 bits = __funnelshift_l(__ldg(S + (i >> 4) + 1), __ldg(S + (i >> 4)), (u32)(i & 15) * 2) >> 24;   // 4 bases
     u32 word = 0;
     for (u32 j = 0; j < 4; ++j) word |= ((0x54474341u >> (8 * ((bits >> (6 - 2 * j)) & 3u))) & 0xFFu) << (8 * j);
     if (b0 == wq && b1 == wq + 4) *(u32*)(seq + wq) = word;
-    else for (u64 q = b0; q < b1; ++q) seq[q] = (u8)(word >> (8 * (q - b0)));
+    else for (u64 qq = b0; qq < b1; ++qq) seq[qq] = (u8)(word >> (8 * (qq - b0)));
   }
 }
 
@@ -926,26 +962,37 @@ __global__ void k_edge_counts8(GView g, u32* __restrict__ cnt) {
   }
   cnt[t] = c;
 }
-__global__ void k_edge_write8(GView g, const u32* __restrict__ off, u32* __restrict__ edges) {
-  u64 t = SPB_GTID();
-  u64 v0 = t * 8;
-  if (v0 >= g.nV) return;
-  u64 w = *(const u64*)(g.vflags + v0);
-  u64 o = off[t];
-  for (u32 i = 0; i < 8 && v0 + i < g.nV; ++i) {
-    u32 fl = (u32)(w >> (8 * i)) & 0xFF;
-    u32 v = (u32)(v0 + i);
-    bool r = (fl & VF_R) != 0;
-    if (fl & VF_HASJ) {
-      u32 j = lower_bound_key(g.Jk, g.nJ, ((u64)v << 32) | v);
-      for (; j < g.nJ && (u32)(g.Jk[j] >> 32) == v; ++j) {
-        u32 d = (u32)g.Jk[j];
-        if (r && d > v + 1) { edges[2 * o] = v; edges[2 * o + 1] = v + 1; ++o; r = false; }
-        edges[2 * o] = v; edges[2 * o + 1] = d; ++o;
-      }
-    }
-    if (r) { edges[2 * o] = v; edges[2 * o + 1] = v + 1; ++o; }
+// rows of vertex v start at off8[v / 8] + (rows of the lower vertices of its group); one thread per vertex so that
+// the common case -- only the implicit (v, v+1) row -- is written as consecutive 8-byte stores
+__device__ __forceinline__ u32 edge_rows_of(const GView& g, u32 v, u32 fl) {
+  u32 c = (fl & VF_R) ? 1 : 0;
+  if (fl & VF_HASJ) {
+    u32 j = lower_bound_key(g.Jk, g.nJ, ((u64)v << 32) | v);
+    for (; j < g.nJ && (u32)(g.Jk[j] >> 32) == v; ++j) ++c;
   }
+  return c;
+}
+__global__ void k_edge_write(GView g, const u32* __restrict__ off8, u32* __restrict__ edges) {
+  u64 v = SPB_GTID();
+  if (v >= g.nV) return;
+  u32 i = (u32)(v & 7);
+  u64 w = *(const u64*)(g.vflags + (v & ~7ull));
+  u64 below = i ? (w & ((1ull << (8 * i)) - 1)) : 0;
+  u64 o = off8[v >> 3];
+  if (!(below & (0x0101010101010101ull * VF_HASJ))) o += __popcll(below & (0x0101010101010101ull * VF_R));
+  else for (u32 j = 0; j < i; ++j) o += edge_rows_of(g, (u32)(v - i + j), (u32)(w >> (8 * j)) & 0xFF);
+  u32 fl = (u32)(w >> (8 * i)) & 0xFF;
+  bool r = (fl & VF_R) != 0;
+  uint2* rows = (uint2*)edges;
+  if (fl & VF_HASJ) {
+    u32 j = lower_bound_key(g.Jk, g.nJ, ((u64)v << 32) | v);
+    for (; j < g.nJ && (u32)(g.Jk[j] >> 32) == (u32)v; ++j) {
+      u32 d = (u32)g.Jk[j];
+      if (r && d > (u32)v + 1) { rows[o++] = make_uint2((u32)v, (u32)v + 1); r = false; }
+      rows[o++] = make_uint2((u32)v, d);
+    }
+  }
+  if (r) rows[o] = make_uint2((u32)v, (u32)v + 1);
 }
 
 // seqPaths (reference lib/vtools.pyx:18-49).  Along a sequence the vertex ids form monotone runs with

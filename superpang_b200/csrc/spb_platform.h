@@ -44,6 +44,9 @@ static inline u32 atomicOr(u32* a, u32 v) { u32 o = *a; *a = o | v; return o; }
 static inline int __popcll(u64 x) { return __builtin_popcountll(x); }
 static inline u32 __funnelshift_l(u32 lo, u32 hi, u32 sh) { sh &= 31; return sh ? (hi << sh) | (lo >> (32 - sh)) : hi; }
 static inline int __popc(u32 x) { return __builtin_popcount(x); }
+static inline u32 __brev(u32 x) { u32 y = 0; for (int i = 0; i < 32; ++i) y |= ((x >> i) & 1u) << (31 - i); return y; }
+struct uint2 { u32 x, y; };
+static inline uint2 make_uint2(u32 a, u32 b) { uint2 r; r.x = a; r.y = b; return r; }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 template <class T> static inline T __ldcg(const T* p) { return *p; }
 #else
