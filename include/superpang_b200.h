@@ -81,6 +81,30 @@ int spb_build_dbg(spb_ctx* ctx, spb_counts* out);
  * `:1038-1059`) and the origin lookup `get_ori2cov_onevertex` + goodOris (`:1212-1262`, `:944-946`). */
 int spb_compact(spb_ctx* ctx, spb_counts* out);
 
+/* ---- multi-GPU building blocks (one process per GPU; every rank loads the whole input) ---------
+ * K-mers are hash-partitioned over the ranks; the host side (torch.distributed / NCCL) performs the
+ * collectives between the stages on the device pointers these functions hand out:
+ *   spb_mg_records   records (64-bit hash | orientation, position) of the positions [pos_lo, pos_hi), sorted by
+ *                    owner; owner_counts[n_owners] = split sizes for the all-to-all
+ *   spb_mg_dedup     owner side: exact dedup of the received records; rep_out[i] = first position of record i
+ *   spb_mg_scatter   position side: representatives (returned by the reverse all-to-all, same order as sent)
+ *                    -> first-appearance bits + per-position representative for the local slice
+ *   spb_mg_buffers   device pointers of the first-appearance bitmap, orientation bitmap and per-position array
+ *                    (all-gathered in place by the host, slice = spb_mg_slice positions per rank)
+ *   spb_mg_ids       vertex ids for the local slice + the vertex table (after the bitmap all-gather)
+ *   spb_mg_graph     junction edges / explicit edge list (after the all-gather of the vertex ids);
+ *                    leaves the context in the same state as spb_build_dbg, spb_compact follows unchanged.
+ * Replaces the reference's single-process dict loop, `lib/Assembler.py:186-217`, for n_ranks > 1. */
+int spb_mg_slice(spb_ctx* ctx, uint32_t n_ranks, uint64_t* slice_len);
+int spb_mg_records(spb_ctx* ctx, uint64_t pos_lo, uint64_t pos_hi, uint32_t n_owners, uint64_t* owner_counts,
+                   void** keys_dev, void** pos_dev);
+int spb_mg_dedup(spb_ctx* ctx, const uint64_t* keys, const uint32_t* pos, const uint64_t* chunk_counts,
+                 uint32_t n_chunks, uint32_t n_owners, uint32_t owner, uint32_t* rep_out);
+int spb_mg_scatter(spb_ctx* ctx, const uint32_t* rep);
+int spb_mg_buffers(spb_ctx* ctx, void** fbits_dev, void** obits_dev, void** sp_dev);
+int spb_mg_ids(spb_ctx* ctx, uint64_t pos_lo, uint64_t pos_hi);
+int spb_mg_graph(spb_ctx* ctx, spb_counts* out);
+
 /* ---- getters (sizes come from spb_counts; buffers are caller-owned, host or device) ---------- */
 
 /* uint32[n_vertices][2] = (ref, idx) of each vertex's first appearance (`lib/Assembler.py:194`). */

@@ -23,6 +23,7 @@ EXPORTS = (
     "spb_get_vertex2coords", "spb_get_edges", "spb_get_instance_vertices", "spb_get_seqlimits",
     "spb_get_seq_intervals", "spb_get_components", "spb_get_nbps", "spb_get_nbp_seqs",
     "spb_get_nbp_origins", "spb_get_counts", "spb_get_stage_stats", "spb_build_kind", "spb_launch_count",
+    "spb_mg_slice", "spb_mg_records", "spb_mg_dedup", "spb_mg_scatter", "spb_mg_buffers", "spb_mg_ids", "spb_mg_graph",
 )
 
 
@@ -81,6 +82,13 @@ def _declare(lib):
     lib.spb_get_stage_stats.argtypes = [vp, C.c_char_p, C.c_uint64]
     lib.spb_build_kind.restype = C.c_char_p
     lib.spb_launch_count.restype = C.c_uint64
+    lib.spb_mg_slice.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint64)]
+    lib.spb_mg_records.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    lib.spb_mg_dedup.argtypes = [vp, u64p, u32p, C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32, C.c_uint32, u32p]
+    lib.spb_mg_scatter.argtypes = [vp, u32p]
+    lib.spb_mg_buffers.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    lib.spb_mg_ids.argtypes = [vp, C.c_uint64, C.c_uint64]
+    lib.spb_mg_graph.argtypes = [vp, C.POINTER(SpbCounts)]
     return lib
 
 
@@ -95,11 +103,44 @@ def _ptr(a):
     return a.data_ptr()          # torch tensor (host pinned or device)
 
 
+def _wrap(ptr, n, dtype, cuda, device):
+    """Zero-copy torch view of `n` elements of library-owned memory (device memory for the CUDA build)."""
+    import torch
+    dev = torch.device("cuda", device) if cuda else torch.device("cpu")
+    if n == 0 or not ptr:
+        return torch.empty(0, dtype=dtype, device=dev)
+    typestr, npdt, size = {torch.int64: ("<i8", np.int64, 8), torch.int32: ("<i4", np.int32, 4)}[dtype]
+    if cuda:
+        class _Ptr:
+            pass
+        o = _Ptr()
+        o.__cuda_array_interface__ = dict(shape=(int(n),), typestr=typestr, data=(int(ptr), False), version=3, strides=None)
+        return torch.as_tensor(o, device=dev)
+    buf = (C.c_byte * (int(n) * size)).from_address(int(ptr))
+    return torch.from_numpy(np.frombuffer(buf, dtype=npdt))
+
+
+def _all_gather_inplace(full, rank, world, group):
+    """all-gather where every rank already holds its own chunk of `full` at the right offset."""
+    import torch.distributed as dist
+    n = full.numel() // world
+    mine = full[rank * n:(rank + 1) * n]
+    try:
+        dist.all_gather_into_tensor(full, mine, group=group)
+    except Exception:
+        parts = [full[i * n:(i + 1) * n] for i in range(world)]
+        tmp = [p.clone() for p in parts]
+        dist.all_gather(tmp, mine.clone(), group=group)
+        for p, t in zip(parts, tmp):
+            p.copy_(t)
+
+
 class Engine:
     """One context = one GPU + one stream.  Mirrors the call order of the C-ABI."""
 
     def __init__(self, device=0, stream=None, lib=None):
         self.lib = lib if lib is not None else load_library()
+        self.device = int(device)
         self.kind = self.lib.spb_build_kind().decode()
         h = C.c_void_p()
         rc = self.lib.spb_create(C.byref(h), int(device), C.c_void_p(stream or 0))
@@ -139,6 +180,64 @@ class Engine:
 
     def compact(self):
         self._ck(self.lib.spb_compact(self.h, C.byref(self.counts)))
+        return self.counts.as_dict()
+
+    def build_dbg_distributed(self, group=None):
+        """DBG build over all ranks of `group` (one process per GPU; every rank has loaded the whole input).
+
+        K-mers are hash-partitioned over the ranks: positions are cut into equal slices, each rank turns its
+        slice into (hash, position) records, an all-to-all routes every record to the rank owning its hash
+        range, the owner deduplicates exactly and an all-to-all returns the first position of every record.
+        First-appearance / orientation bitmaps and the per-position vertex ids are all-gathered, after which
+        every rank holds the complete DBG and `compact()` proceeds unchanged (replicated).  NCCL on GPUs;
+        the CPU test tier drives the same code with the host emulator over gloo."""
+        import torch
+        import torch.distributed as dist
+        G, r = dist.get_world_size(group), dist.get_rank(group)
+        cuda = self.kind.startswith("cuda")
+        dev = torch.device("cuda", self.device) if cuda else torch.device("cpu")
+        T = int(self._keep[1][-1])
+        S = C.c_uint64()
+        self._ck(self.lib.spb_mg_slice(self.h, G, C.byref(S)))
+        S = int(S.value)
+        lo, hi = r * S, min((r + 1) * S, T)
+        cnt = (C.c_uint64 * G)()
+        kp, pp = C.c_void_p(), C.c_void_p()
+        self._ck(self.lib.spb_mg_records(self.h, lo, max(lo, hi), G, cnt, C.byref(kp), C.byref(pp)))
+        send = [int(x) for x in cnt]
+        keys = _wrap(kp.value, sum(send), torch.int64, cuda, self.device)
+        pos = _wrap(pp.value, sum(send), torch.int32, cuda, self.device)
+        sc = torch.tensor(send, dtype=torch.int64, device=dev)
+        rc_t = torch.empty_like(sc)
+        dist.all_to_all_single(rc_t, sc, group=group)
+        recv = [int(x) for x in rc_t.tolist()]
+        rkeys = torch.empty(sum(recv), dtype=torch.int64, device=dev)
+        rpos = torch.empty(sum(recv), dtype=torch.int32, device=dev)
+        dist.all_to_all_single(rkeys, keys, recv, send, group=group)
+        dist.all_to_all_single(rpos, pos, recv, send, group=group)
+        rep = torch.empty(sum(recv), dtype=torch.int32, device=dev)
+        chunk = (C.c_uint64 * G)(*recv)
+        if cuda:
+            torch.cuda.current_stream().synchronize()
+        self._ck(self.lib.spb_mg_dedup(self.h, rkeys.data_ptr(), rpos.data_ptr(), chunk, G, G, r, rep.data_ptr()))
+        back = torch.empty(sum(send), dtype=torch.int32, device=dev)
+        dist.all_to_all_single(back, rep, send, recv, group=group)
+        if cuda:
+            torch.cuda.current_stream().synchronize()
+        self._ck(self.lib.spb_mg_scatter(self.h, back.data_ptr()))
+        fb, ob, sp = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(self.lib.spb_mg_buffers(self.h, C.byref(fb), C.byref(ob), C.byref(sp)))
+        for ptr in (fb, ob):
+            full = _wrap(ptr.value, G * S // 32, torch.int32, cuda, self.device)
+            _all_gather_inplace(full, r, G, group)
+        if cuda:
+            torch.cuda.current_stream().synchronize()
+        self._ck(self.lib.spb_mg_ids(self.h, lo, max(lo, hi)))
+        full = _wrap(sp.value, G * S, torch.int32, cuda, self.device)
+        _all_gather_inplace(full, r, G, group)
+        if cuda:
+            torch.cuda.current_stream().synchronize()
+        self._ck(self.lib.spb_mg_graph(self.h, C.byref(self.counts)))
         return self.counts.as_dict()
 
     def refresh_counts(self):

@@ -74,7 +74,8 @@ def concat_sequences(seqs):
 
 
 class Assembler:
-    def __init__(self, fasta, ksize, threads=1, diskdb=None, debug=False, gap_size=1, *, engine=None, device=0):
+    def __init__(self, fasta, ksize, threads=1, diskdb=None, debug=False, gap_size=1, *, engine=None, device=0, dist_group=None,
+                 distributed=False):
         """Build the de Bruijn graph on the GPU.
 
         `threads` and `diskdb` (`--lowmem`) are accepted for drop-in compatibility and ignored: the
@@ -97,7 +98,8 @@ class Assembler:
         buf, off = concat_sequences(list(self.seqDict.values()))
         self._seq_off = off
         self._eng.load(buf, off, self.ksize)
-        self.counts = self._eng.build_dbg()
+        # multi-GPU: one process per GPU (torch.distributed initialised by the caller), k-mers hash-partitioned over the ranks
+        self.counts = self._eng.build_dbg_distributed(dist_group) if (distributed or dist_group is not None) else self._eng.build_dbg()
         self._compacted = False
         self._cache = {}
 

@@ -405,8 +405,9 @@ static u32 default_bucket_bits(u64 n_inst, u32 n_owners) {
   return bb > need ? bb : need;
 }
 
-static int alloc_position_state(spb_ctx* c) {
+static int alloc_position_state(spb_ctx* c, u64 min_positions = 0) {
   if (c->sp) return 0;
+  if (min_positions + TPB > c->npos_pad) c->npos_pad = nblk(min_positions, TPB) * TPB + TPB;
   u64 nw32 = c->npos_pad / 32;
   ALLOC(c->sp, u32, c->npos_pad + 8);
   ALLOC(c->obits, u32, nw32 + 8); ALLOC(c->fbits, u32, nw32 + 8);
@@ -415,8 +416,9 @@ static int alloc_position_state(spb_ctx* c) {
 }
 
 // S1: records of the positions [pos_lo, pos_hi) (pos_lo a multiple of 256), partitioned by the top `bb` hash bits
-static int dd_records(spb_ctx* c, u64 pos_lo, u64 pos_hi, u32 bb) {
-  int r0 = alloc_position_state(c); if (r0) return r0;
+static int dd_records(spb_ctx* c, u64 pos_lo, u64 pos_hi, u32 bb, u64 min_positions = 0) {
+  int r0 = alloc_position_state(c, min_positions); if (r0) return r0;
+  if (pos_hi < pos_lo) pos_hi = pos_lo;
   u64 n = nblk(pos_hi - pos_lo, TPB) * TPB;
   u64 *keys, *keys2; u32 *pos, *pos2;
   ALLOC(keys, u64, n); ALLOC(pos, u32, n);
@@ -461,7 +463,9 @@ static int dd_owner(spb_ctx* c, const u64* keys, const u32* pos, const u64* chun
   for (u32 b = 0; b < B; ++b) { for (u32 r = 0; r < nchunks; ++r) nb[b] += sub_h[(u64)r * (B + 1) + b + 1] - sub_h[(u64)r * (B + 1) + b]; nmax = std::max(nmax, nb[b]); }
   u64 cap = 1024; while (cap < 2 * nmax) cap <<= 1;
   c->cnt.table_slots = cap;
-  u64* scratch[2]; ALLOC(scratch[0], u64, cap); ALLOC(scratch[1], u64, cap);
+  u64* scratch[2] = {nullptr, nullptr};
+  ALLOC(scratch[0], u64, cap);
+  if (B > 1) ALLOC(scratch[1], u64, cap); else scratch[1] = scratch[0];
   dev_memset(c, scratch[0], 0xFF, cap * 8);
   BktView v{keys, pos, rep, coff, sub, nchunks, B, 0};
   u32 step = 0;
@@ -471,10 +475,11 @@ static int dd_owner(spb_ctx* c, const u64* keys, const u32* pos, const u64* chun
     u64* cur = scratch[step & 1]; u64* other = scratch[(step & 1) ^ 1];
     SPB_LAUNCH(k_bkt_insert, nblk(nb[b], TPB), TPB, c->stream, v, nb[b], c->F, c->R, c->T, c->k, cur, cap - 1);
     u64 g = std::max<u64>(nblk(nb[b], TPB), std::min<u64>(nblk(cap, TPB), 148 * 8));
-    SPB_LAUNCH(k_bkt_final, g, TPB, c->stream, v, nb[b], cur, other, cap);
+    SPB_LAUNCH(k_bkt_final, g, TPB, c->stream, v, nb[b], cur, other, B > 1 ? cap : 0);
     ++step;
   }
-  dfree(c, scratch[0]); dfree(c, scratch[1]); dfree(c, coff); dfree(c, sub);
+  if (B > 1) dfree(c, scratch[1]);
+  dfree(c, scratch[0]); dfree(c, coff); dfree(c, sub);
   return 0;
 }
 
@@ -610,6 +615,89 @@ int spb_build_dbg(spb_ctx* c, spb_counts* out) {
   PRIM(dd_graph(c));
   snprintf(buf, sizeof buf, ", \"edges_ms\": %.4f", tm.stop(c)); c->stats += buf;
   int r = check_err(c, "spb_build_dbg");
+  if (r) return r;
+  c->state = 2;
+  if (out) *out = c->cnt;
+  return SPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------- multi-GPU stages
+// One process per GPU, every rank holds the whole packed input (spb_load).  Positions are split into equal
+// slices (one per rank); k-mers are hash-partitioned over the ranks (owner = top log2(n_owners) hash bits):
+//   spb_mg_records -> [all-to-all of (hash, position) records] -> spb_mg_dedup (exact dedup in the owner's table)
+//   -> [all-to-all of representatives back] -> spb_mg_scatter -> [all-gather of the first-appearance and
+//   orientation bitmaps] -> spb_mg_ids -> [all-gather of the per-position vertex ids] -> spb_mg_graph.
+// The exchanges are NCCL collectives issued by the host side (torch.distributed) on the device pointers below.
+static bool pow2(u32 x) { return x && !(x & (x - 1)); }
+
+int spb_mg_slice(spb_ctx* c, uint32_t n_ranks, uint64_t* slice_len) {
+  if (!c || !slice_len || !n_ranks) return SPB_EINVAL;
+  *slice_len = nblk(nblk(c->T, n_ranks), 1024) * 1024;
+  return SPB_OK;
+}
+
+int spb_mg_records(spb_ctx* c, uint64_t pos_lo, uint64_t pos_hi, uint32_t n_owners, uint64_t* owner_counts, void** keys_dev, void** pos_dev) {
+  if (!c) return SPB_EINVAL;
+  if (c->state != 1) return fail(c, SPB_ESTATE, "spb_mg_records needs a freshly loaded input");
+  if (!pow2(n_owners)) return fail(c, SPB_EINVAL, "n_owners must be a power of two");
+  if (pos_lo % 256) return fail(c, SPB_EINVAL, "pos_lo must be a multiple of 256");
+#ifndef SPB_EMU
+  CK(cudaSetDevice(c->device));
+#endif
+  u32 bb = 0; while ((1u << bb) < n_owners) ++bb;
+  uint64_t slice = 0; spb_mg_slice(c, n_owners, &slice);
+  if (pos_hi > c->T) pos_hi = c->T;
+  PRIM(dd_records(c, pos_lo, pos_hi, bb, slice * n_owners));
+  for (u32 o = 0; o < n_owners; ++o) owner_counts[o] = c->dd_bstart_h[o + 1] - c->dd_bstart_h[o];
+  *keys_dev = c->dd_keys; *pos_dev = c->dd_pos;
+  return check_err(c, "spb_mg_records");
+}
+
+int spb_mg_dedup(spb_ctx* c, const uint64_t* keys, const uint32_t* pos, const uint64_t* chunk_counts, uint32_t n_chunks,
+                 uint32_t n_owners, uint32_t owner, uint32_t* rep_out) {
+  if (!c) return SPB_EINVAL;
+  if (c->state != 1) return fail(c, SPB_ESTATE, "spb_mg_dedup needs a loaded input");
+  if (!pow2(n_owners) || owner >= n_owners) return fail(c, SPB_EINVAL, "bad owner / n_owners");
+#ifndef SPB_EMU
+  CK(cudaSetDevice(c->device));
+#endif
+  u32 bb = 0; while ((1u << bb) < n_owners) ++bb;
+  PRIM(dd_owner(c, (const u64*)keys, pos, (const u64*)chunk_counts, n_chunks, bb, owner, owner + 1, rep_out));
+  return check_err(c, "spb_mg_dedup");
+}
+
+int spb_mg_scatter(spb_ctx* c, const uint32_t* rep) {
+  if (!c) return SPB_EINVAL;
+  if (c->state != 1 || !c->dd_pos) return fail(c, SPB_ESTATE, "spb_mg_scatter without spb_mg_records");
+  PRIM(dd_scatter(c, rep));
+  return check_err(c, "spb_mg_scatter");
+}
+
+int spb_mg_buffers(spb_ctx* c, void** fbits_dev, void** obits_dev, void** sp_dev) {
+  if (!c || !c->sp) return SPB_EINVAL;
+  if (fbits_dev) *fbits_dev = c->fbits;
+  if (obits_dev) *obits_dev = c->obits;
+  if (sp_dev) *sp_dev = c->sp;
+  return SPB_OK;
+}
+
+int spb_mg_ids(spb_ctx* c, uint64_t pos_lo, uint64_t pos_hi) {
+  if (!c) return SPB_EINVAL;
+  if (c->state != 1 || !c->sp) return fail(c, SPB_ESTATE, "spb_mg_ids out of order");
+  if (pos_hi > c->T) pos_hi = c->T;
+  PRIM(dd_ids(c, pos_lo, pos_hi, nullptr));
+  return check_err(c, "spb_mg_ids");
+}
+
+int spb_mg_graph(spb_ctx* c, spb_counts* out) {
+  if (!c) return SPB_EINVAL;
+  if (c->state != 1 || !c->v2pos) return fail(c, SPB_ESTATE, "spb_mg_graph out of order");
+  c->stats = "{\"multi_gpu\": 1";
+  StageTimer tm; char buf[128];
+  tm.start(c);
+  PRIM(dd_graph(c));
+  snprintf(buf, sizeof buf, ", \"edges_ms\": %.4f", tm.stop(c)); c->stats += buf;
+  int r = check_err(c, "spb_mg_graph");
   if (r) return r;
   c->state = 2;
   if (out) *out = c->cnt;

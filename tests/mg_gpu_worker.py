@@ -1,0 +1,43 @@
+"""GPU worker (run under torchrun, one rank per GPU): multi-GPU DBG build over NCCL with the sm_100a library,
+checked against the reference goldens on every rank."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import digests
+    import helpers
+    from superpang_b200 import _capi
+    from superpang_b200.assembler import Assembler
+    cases = []
+    for c in helpers.load_json("synthetic.json")["cases"]:
+        cases.append((helpers.synth_seqdict(c["n_genomes"], c["length"], c["ani"], c["seed"], c["mode"]), c["k"], c["summary"]))
+    rs = helpers.load_json("real_slice.json")
+    cases.append((helpers.real_slice_records(), rs["k"], rs["summary"]))
+    for c in helpers.load_crafted()[:22]:
+        cases.append((dict(map(tuple, c["records"])), c["k"], c["summary"]))
+    for fa, name in (("A.fa", "kat_A.json"), ("B.fa", "kat_B.json")):
+        path = os.path.join(helpers.DATA, fa)
+        if os.path.exists(path):
+            cases.append((path, 301, helpers.load_json(name)))
+    for sd, k, want in cases:
+        A = Assembler(sd, k, engine=_capi.Engine(device=local, stream=torch.cuda.current_stream().cuda_stream), distributed=True)
+        assert A._eng.kind == "cuda sm_100a"
+        helpers.assert_summary(digests.summarize(A.to_result()), want)
+    dist.barrier()
+    if dist.get_rank() == 0:
+        print(f"multi-GPU parity OK on {dist.get_world_size()} ranks, {len(cases)} cases")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -128,3 +128,19 @@ def test_gpu_properties_at_scale(mode):
     ooff, oidx = eng.nbp_origins()
     assert np.all(ooff[1:] > ooff[:-1])
     assert int(oidx.max()) < len(seqs)
+
+
+def test_gpu_multi_rank_parity():
+    """>= 2 GPUs: hash-partitioned DBG build over NCCL, every rank must reproduce the reference goldens."""
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = 2 if n < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", "29611", os.path.join(helpers.ROOT, "tests", "mg_gpu_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "multi-GPU parity OK" in r.stdout
