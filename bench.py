@@ -190,7 +190,11 @@ def main():
             e1.record(stream)
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1))
-            stages.append(eng.stage_stats())
+            st = dict(eng.stage_stats())
+            st.update(getattr(eng, "mg_times", {}))
+            st.pop("multi_gpu", None)
+            st.pop("mg_graph_ms", None)
+            stages.append(st)
         if world > 1:
             dist.barrier()
         timed.launches = eng.lib.spb_launch_count() - launches0

@@ -196,6 +196,18 @@ class Engine:
         G, r = dist.get_world_size(group), dist.get_rank(group)
         cuda = self.kind.startswith("cuda")
         dev = torch.device("cuda", self.device) if cuda else torch.device("cpu")
+        marks = []
+
+        def mark(name):                      # stage boundaries (CUDA events on the current stream)
+            if cuda:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(torch.cuda.current_stream())
+                marks.append((name, e))
+
+        def sync():
+            if cuda:
+                torch.cuda.current_stream().synchronize()
+
         T = int(self._keep[1][-1])
         S = C.c_uint64()
         self._ck(self.lib.spb_mg_slice(self.h, G, C.byref(S)))
@@ -203,7 +215,9 @@ class Engine:
         lo, hi = r * S, min((r + 1) * S, T)
         cnt = (C.c_uint64 * G)()
         kp, pp = C.c_void_p(), C.c_void_p()
+        mark("start")
         self._ck(self.lib.spb_mg_records(self.h, lo, max(lo, hi), G, cnt, C.byref(kp), C.byref(pp)))
+        mark("records_partition")
         send = [int(x) for x in cnt]
         keys = _wrap(kp.value, sum(send), torch.int64, cuda, self.device)
         pos = _wrap(pp.value, sum(send), torch.int32, cuda, self.device)
@@ -217,27 +231,33 @@ class Engine:
         dist.all_to_all_single(rpos, pos, recv, send, group=group)
         rep = torch.empty(sum(recv), dtype=torch.int32, device=dev)
         chunk = (C.c_uint64 * G)(*recv)
-        if cuda:
-            torch.cuda.current_stream().synchronize()
+        mark("exchange_records")
+        sync()
         self._ck(self.lib.spb_mg_dedup(self.h, rkeys.data_ptr(), rpos.data_ptr(), chunk, G, G, r, rep.data_ptr()))
+        mark("owner_dedup")
         back = torch.empty(sum(send), dtype=torch.int32, device=dev)
         dist.all_to_all_single(back, rep, send, recv, group=group)
-        if cuda:
-            torch.cuda.current_stream().synchronize()
+        mark("exchange_reps")
+        sync()
         self._ck(self.lib.spb_mg_scatter(self.h, back.data_ptr()))
         fb, ob, sp = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._ck(self.lib.spb_mg_buffers(self.h, C.byref(fb), C.byref(ob), C.byref(sp)))
+        mark("scatter")
         for ptr in (fb, ob):
             full = _wrap(ptr.value, G * S // 32, torch.int32, cuda, self.device)
             _all_gather_inplace(full, r, G, group)
-        if cuda:
-            torch.cuda.current_stream().synchronize()
+        sync()
         self._ck(self.lib.spb_mg_ids(self.h, lo, max(lo, hi)))
+        mark("bitmaps_ids")
         full = _wrap(sp.value, G * S, torch.int32, cuda, self.device)
         _all_gather_inplace(full, r, G, group)
-        if cuda:
-            torch.cuda.current_stream().synchronize()
+        mark("allgather_ids")
+        sync()
         self._ck(self.lib.spb_mg_graph(self.h, C.byref(self.counts)))
+        mark("graph")
+        if cuda:
+            sync()
+            self.mg_times = {f"mg_{n}_ms": marks[i - 1][1].elapsed_time(e) for i, (n, e) in enumerate(marks) if i}
         return self.counts.as_dict()
 
     def refresh_counts(self):

@@ -467,19 +467,21 @@ static int dd_owner(spb_ctx* c, const u64* keys, const u32* pos, const u64* chun
   ALLOC(scratch[0], u64, cap);
   if (B > 1) ALLOC(scratch[1], u64, cap); else scratch[1] = scratch[0];
   dev_memset(c, scratch[0], 0xFF, cap * 8);
+  u32* dbits; ALLOC(dbits, u32, c->npos_pad / 32 + 8);
+  dev_memset(c, dbits, 0, (c->npos_pad / 32 + 8) * 4);
   BktView v{keys, pos, rep, coff, sub, nchunks, B, 0};
   u32 step = 0;
   for (u32 b = 0; b < B; ++b) {
     if (nb[b] == 0) continue;
     v.b = b;
     u64* cur = scratch[step & 1]; u64* other = scratch[(step & 1) ^ 1];
-    SPB_LAUNCH(k_bkt_insert, nblk(nb[b], TPB), TPB, c->stream, v, nb[b], c->F, c->R, c->T, c->k, cur, cap - 1);
+    SPB_LAUNCH(k_bkt_insert, nblk(nb[b], TPB), TPB, c->stream, v, nb[b], c->F, c->R, c->T, c->k, cur, cap - 1, dbits);
     u64 g = std::max<u64>(nblk(nb[b], TPB), std::min<u64>(nblk(cap, TPB), 148 * 8));
-    SPB_LAUNCH(k_bkt_final, g, TPB, c->stream, v, nb[b], cur, other, B > 1 ? cap : 0);
+    SPB_LAUNCH(k_bkt_final, g, TPB, c->stream, v, nb[b], c->F, c->R, c->T, c->k, cur, cap - 1, dbits, other, B > 1 ? cap : 0);
     ++step;
   }
   if (B > 1) dfree(c, scratch[1]);
-  dfree(c, scratch[0]); dfree(c, coff); dfree(c, sub);
+  dfree(c, scratch[0]); dfree(c, coff); dfree(c, sub); dfree(c, dbits);
   return 0;
 }
 
@@ -494,7 +496,7 @@ static int dd_scatter(spb_ctx* c, const u32* rep) {
 }
 
 // vertex ids for the positions [lo, hi) + the vertex table (needs the complete fbits bitmap)
-static int dd_ids(spb_ctx* c, u64 lo, u64 hi, const u64* slots) {
+static int dd_ids(spb_ctx* c, u64 lo, u64 hi, const u64* slots, u64 cap = 1) {
   const u64 T = c->T;
   u64 nb = c->npos_pad / 256;
   u32 *blkcnt, *blkoff; ALLOC(blkcnt, u32, nb); ALLOC(blkoff, u32, nb);
@@ -504,7 +506,12 @@ static int dd_ids(spb_ctx* c, u64 lo, u64 hi, const u64* slots) {
   c->nV = (u32)nV;
   ALLOC(c->v2pos, u32, nV + 1); ALLOC(c->vflags, u8, nV + 64);
   dev_memset(c, c->vflags + (nV & ~7ull), 0, 64);
-  SPB_LAUNCH(k_assign_ids, nblk(T, TPB), TPB, c->stream, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, slots, c->v2pos, c->vflags);
+  switch ((2 * c->k + 31) / 32) {
+    case 7:  SPB_LAUNCH(k_assign_ids<7>, nblk(T, TPB), TPB, c->stream, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags); break;
+    case 19: SPB_LAUNCH(k_assign_ids<19>, nblk(T, TPB), TPB, c->stream, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags); break;
+    case 32: SPB_LAUNCH(k_assign_ids<32>, nblk(T, TPB), TPB, c->stream, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags); break;
+    default: SPB_LAUNCH(k_assign_ids<0>, nblk(T, TPB), TPB, c->stream, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags); break;
+  }
   dfree(c, blkcnt); dfree(c, blkoff);
   return 0;
 }
@@ -570,7 +577,7 @@ static int dedup_global_table(spb_ctx* c) {
   SPB_LAUNCH(k_first_bits, nblk(nb, TPB), TPB, c->stream, wbits, dbits, c->fbits, blkcnt, nb);
   dev_memset(c, c->fbits + nw32, 0, 32);
   dfree(c, blkcnt); dfree(c, wbits); dfree(c, dbits);
-  int r = dd_ids(c, 0, T, slots);
+  int r = dd_ids(c, 0, T, slots, cap);
   dfree(c, slots);
   return r;
 }

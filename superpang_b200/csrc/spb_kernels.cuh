@@ -213,6 +213,7 @@ k_extract_insert(const u32* __restrict__ F, const u32* __restrict__ R, const u32
   u64 p = SPB_GTID();
   bool valid = p < T && get_bit(vbits, p);
   bool o = false, won = false;
+  u32 seen = SPB_INVALID;
   if (valid) {
     u64 ra = T - p - k;
     // orientation: almost always decided by the first limb
@@ -241,14 +242,17 @@ k_extract_insert(const u32* __restrict__ F, const u32* __restrict__ R, const u32
               won = true;
               u64 dq = (old >> 1) & SPB_POSMASK;
               atomicOr(dbits + (dq >> 5), 1u << (dq & 31));
-            }
+            } else q = (old >> 1) & SPB_POSMASK;
           }
+          seen = (u32)q;
           break;
         }
       }
       idx = (idx + 1) & capmask;
     }
-    slotidx[p] = (u32)idx;
+    // an instance that did not install its own position remembers the (then) first position it matched; that is
+    // its representative unless that position was displaced later (checked against the final bitmap in k_assign_ids)
+    slotidx[p] = won ? SPB_INVALID : seen;
   }
   store_bit(obits, p, o);
   store_bit(wbits, p, won);
@@ -312,7 +316,7 @@ __device__ __forceinline__ u64 bkt_record(const BktView& v, u64 t) {   // t-th r
   return ~0ull;
 }
 __global__ void SPB_LAUNCH_BOUNDS(256)
-k_bkt_insert(BktView v, u64 n_b, const u32* __restrict__ F, const u32* __restrict__ R, u64 T, u32 k, u64* scratch, u64 capmask) {
+k_bkt_insert(BktView v, u64 n_b, const u32* __restrict__ F, const u32* __restrict__ R, u64 T, u32 k, u64* scratch, u64 capmask, u32* dbits) {
   u64 t = SPB_GTID();
   if (t >= n_b) return;
   u64 rec = bkt_record(v, t);
@@ -324,6 +328,7 @@ k_bkt_insert(BktView v, u64 n_b, const u32* __restrict__ F, const u32* __restric
   u64 entry = (tag << 40) | (p << 1) | (o ? 1ull : 0ull);
   const u32* S = o ? F : R;
   u64 a = o ? p : T - p - k;
+  u32 seen = (u32)p;                                // winners are their own candidate representative
   for (;;) {
     u64 cur = atomicCAS(scratch + idx, SPB_EMPTY, entry);
     if (cur == SPB_EMPTY) break;
@@ -331,21 +336,45 @@ k_bkt_insert(BktView v, u64 n_b, const u32* __restrict__ F, const u32* __restric
       u64 q = (cur >> 1) & SPB_POSMASK;
       bool oq = cur & 1;
       if (q == p || win_cmp(S, a, oq ? F : R, oq ? q : T - q - k, k) == 0) {
-        if (entry < cur) atomicMin(scratch + idx, entry);
+        if (entry < cur) {
+          u64 old = atomicMin(scratch + idx, entry);
+          u64 oq2 = (old >> 1) & SPB_POSMASK;
+          if (old > entry) atomicOr(dbits + (oq2 >> 5), 1u << (oq2 & 31));    // oq2 is no longer the first position
+          else q = oq2;
+        }
+        if (q > p) q = p;
+        seen = (u32)q;
         break;
       }
     }
     idx = (idx + 1) & capmask;
   }
-  v.sidx[rec] = (u32)idx;
+  v.sidx[rec] = seen;                                // exact unless `seen` is displaced later (k_bkt_final re-probes then)
 }
 // representative of every record of the bucket; the same launch clears the other scratch table
-__global__ void k_bkt_final(BktView v, u64 n_b, const u64* __restrict__ scratch, u64* clear, u64 clear_n) {
+__global__ void k_bkt_final(BktView v, u64 n_b, const u32* __restrict__ F, const u32* __restrict__ R, u64 T, u32 k,
+                            const u64* __restrict__ scratch, u64 capmask, const u32* __restrict__ dbits, u64* clear, u64 clear_n) {
   u64 t = SPB_GTID();
   if (t < n_b) {
     u64 rec = bkt_record(v, t);
-    u32 si = v.sidx[rec];
-    if (si != SPB_INVALID) v.sidx[rec] = (u32)((scratch[si] >> 1) & SPB_POSMASK);
+    u32 r = v.sidx[rec];
+    if (r != SPB_INVALID && get_bit(dbits, r)) {     // candidate was displaced after we saw it: exact re-probe by key
+      u64 key = v.keys[rec], p = v.pos[rec];
+      bool o = key & 1;
+      u64 tag = (key >> 1) & 0x7FFFFFull, idx = (key >> 24) & capmask;
+      const u32* S = o ? F : R;
+      u64 a = o ? p : T - p - k;
+      for (;;) {
+        u64 cur = scratch[idx];
+        if (cur == SPB_EMPTY) break;
+        if ((cur >> 40) == tag) {
+          u64 q = (cur >> 1) & SPB_POSMASK;
+          bool oq = cur & 1;
+          if (q == p || win_cmp(S, a, oq ? F : R, oq ? q : T - q - k, k) == 0) { v.sidx[rec] = (u32)q; break; }
+        }
+        idx = (idx + 1) & capmask;
+      }
+    }
   }
   u64 stride = (u64)gridDim.x * blockDim.x;
   for (u64 j = t; j < clear_n; j += stride) clear[j] = SPB_EMPTY;
@@ -387,18 +416,46 @@ __device__ __forceinline__ u32 rank_first(const u32* fbits, const u32* blkoff, u
   return r;
 }
 
+// exact lookup of the first position of the k-mer at p in the finished table (rarely needed, see k_assign_ids)
+template <int W> __device__ __forceinline__ u32 lookup_rep(const u32* __restrict__ F, const u32* __restrict__ R, u64 T, u32 k,
+                                                           const u64* __restrict__ slots, u64 capmask, u64 p) {
+  u64 ra = T - p - k;
+  bool o = win_cmp(F, p, R, ra, k) >= 0;
+  const u32* S = o ? F : R;
+  u64 a = o ? p : ra;
+  u64 h = win_hash<W>(S, a, k);
+  u64 idx = h & capmask, tag = h >> 40;
+  for (;;) {
+    u64 cur = __ldcg(slots + idx);
+    if (cur == SPB_EMPTY) return (u32)p;             // cannot happen: every instance was inserted
+    if ((cur >> 40) == tag) {
+      u64 q = (cur >> 1) & SPB_POSMASK;
+      bool oq = cur & 1;
+      if (q == p || win_cmp(S, a, oq ? F : R, oq ? q : T - q - k, k) == 0) return (u32)q;
+    }
+    idx = (idx + 1) & capmask;
+  }
+}
+
 // K3: vertex ids (= rank of the representative among first appearances), vertex -> first position,
-// implicit-edge bit.  `sp` holds the slot index of every instance on entry and vertex ids on exit;
-// only instances that are not first appearances read their representative back from the table.
-__global__ void k_assign_ids(u32* __restrict__ sp, const u32* __restrict__ vbits, u64 T, u64 lo, u64 hi, const u32* __restrict__ fbits,
-                             const u32* __restrict__ blkoff, const u64* __restrict__ slots, u32* __restrict__ v2pos, u8* __restrict__ vflags) {
+// implicit-edge bit.  On entry sp[p] holds, for an instance that is not a first appearance, the position it
+// matched during the insert (global-table path; exact unless that position was displaced later -> table lookup)
+// or its exact representative (staged / multi-GPU path, slots == nullptr).  On exit sp[p] = vertex id.
+template <int W> __global__ void
+k_assign_ids(u32* __restrict__ sp, const u32* __restrict__ vbits, u64 T, u64 lo, u64 hi, const u32* __restrict__ fbits,
+             const u32* __restrict__ blkoff, const u64* __restrict__ slots, u64 capmask, const u32* __restrict__ F,
+             const u32* __restrict__ R, u32 k, u32* __restrict__ v2pos, u8* __restrict__ vflags) {
   u64 p = SPB_GTID();
   if (p >= T) return;
   bool mine = p >= lo && p < hi;                 // multi-GPU: sp is filled for the local slice only, the vertex table everywhere
   if (!get_bit(vbits, p)) { if (mine) sp[p] = SPB_INVALID; return; }
   bool first = get_bit(fbits, p);
   if (!first && !mine) return;
-  u32 r = first ? (u32)p : (slots ? (u32)((__ldcg(slots + sp[p]) >> 1) & SPB_POSMASK) : sp[p]);   // staged path: sp already holds the representative
+  u32 r = (u32)p;
+  if (!first) {
+    r = sp[p];
+    if (slots && (r == SPB_INVALID || !get_bit(fbits, r))) r = lookup_rep<W>(F, R, T, k, slots, capmask, p);
+  }
   u32 vid = rank_first(fbits, blkoff, r);
   if (mine) sp[p] = vid;
   if (first) {

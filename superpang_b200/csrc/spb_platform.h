@@ -28,9 +28,22 @@ typedef uint8_t u8;
 struct spb_emu_dim3 { unsigned x = 1, y = 1, z = 1; };
 static spb_emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 typedef void* spb_stream_t;
+// Threads run one after the other.  SPB_EMU_ORDER=reverse runs them in descending order and =shuffle in a
+// pseudo-random block order, so that the tests also exercise the paths that only trigger when a larger position
+// reaches the table before a smaller one (on the GPU that depends on scheduling).
 template <class F> static inline void spb_emu_launch(size_t nb, unsigned nt, F f) {
   gridDim.x = (unsigned)nb; blockDim.x = nt;
-  for (size_t b = 0; b < nb; ++b) { blockIdx.x = (unsigned)b; for (unsigned t = 0; t < nt; ++t) { threadIdx.x = t; f(); } }
+  const char* ord = getenv("SPB_EMU_ORDER");
+  int mode = !ord ? 0 : (ord[0] == 'r' ? 1 : (ord[0] == 's' ? 2 : 0));
+  for (size_t i = 0; i < nb; ++i) {
+    size_t b = mode == 0 ? i : mode == 1 ? nb - 1 - i : (size_t)(((unsigned long long)i * 2654435761ull + 12345) % nb);
+    if (mode == 2) { b = i; }   // shuffle handled below per thread to stay a permutation
+    blockIdx.x = (unsigned)b;
+    for (unsigned j = 0; j < nt; ++j) {
+      unsigned t = mode == 0 ? j : mode == 1 ? nt - 1 - j : (unsigned)((j * 167u + 13u) % nt);
+      threadIdx.x = t; f();
+    }
+  }
 }
 #define SPB_LAUNCH(K, NB, NT, STREAM, ...) \
   do { if ((NB) > 0) { ++g_spb_launches; spb_emu_launch((size_t)(NB), (unsigned)(NT), [&]() { K(__VA_ARGS__); }); } } while (0)

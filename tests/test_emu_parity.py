@@ -88,3 +88,25 @@ def test_rejects_bad_input(emu_lib):
         run_emu(emu_lib, {"a": "ACGTRYACGT" * 10}, 9)       # non-ACGT reaches the device
     with pytest.raises(NotImplementedError):
         Assembler({"a": "ACGT" * 20}, 9, gap_size=2, engine=_capi.Engine(lib=emu_lib))
+
+
+VARIANTS = [
+    {"SPB_EMU_ORDER": "reverse"},                                   # larger positions reach the table first (displacements)
+    {"SPB_EMU_ORDER": "shuffle"},
+    {"SPB_DEDUP": "staged", "SPB_BUCKET_BITS": "3"},                # partitioned dedup, 8 buckets
+    {"SPB_DEDUP": "staged", "SPB_BUCKET_BITS": "5", "SPB_EMU_ORDER": "reverse"},
+]
+
+
+@pytest.mark.parametrize("env", VARIANTS, ids=lambda e: ",".join(f"{k[4:].lower()}={v}" for k, v in e.items()))
+def test_emu_variants_match_reference_golden(emu_lib, monkeypatch, env):
+    """The dedup paths that depend on GPU scheduling (displaced first positions, exact re-probe) and the
+    partitioned dedup, forced in the emulator through thread order / path selection."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for case in helpers.load_crafted():
+        got = run_emu(emu_lib, dict(map(tuple, case["records"])), case["k"]).to_result()
+        digests.assert_same(helpers.golden_to_result(case), got)
+    for case in helpers.load_json("synthetic.json")["cases"][:3]:
+        sd = helpers.synth_seqdict(case["n_genomes"], case["length"], case["ani"], case["seed"], case["mode"])
+        helpers.assert_summary(digests.summarize(run_emu(emu_lib, sd, case["k"]).to_result()), case["summary"])
