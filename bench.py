@@ -161,9 +161,19 @@ def main():
     out_bufs = {}
 
     def step_e2e():
-        eng.load(host, off, K)              # H2D of the ASCII input inside the library call
+        if world == 1:
+            eng.load(host, off, K)          # H2D of the ASCII input inside the library call
+        else:
+            # one H2D on rank 0, then the genome travels over NVLink (NCCL broadcast); results are read back by rank 0,
+            # the rank that hosts the reference's single-process tail
+            if rank == 0:
+                dbuf.copy_(host, non_blocking=True)
+            dist.broadcast(dbuf, src=0)
+            eng.load(dbuf, off, K)
         build()
         c = eng.compact()
+        if rank != 0:
+            return c, 0
         n, nb, no = c["n_nbp"], c["nbp_bases"], c["n_origin_pairs"]
         key = (n, nb, no)
         if out_bufs.get("key") != key:

@@ -124,6 +124,8 @@ template <class T> static T dread(spb_ctx* c, const T* p) {
 static void dread_n(spb_ctx* c, void* dst, const void* src, u64 bytes) { dev_copy(c, c->pinned, src, bytes); dev_sync(c); memcpy(dst, c->pinned, bytes); }
 
 static inline u64 nblk(u64 n, u32 t) { return (n + t - 1) / t; }
+// grid of a grid-stride kernel: enough resident blocks for every SM, never millions of tiny ones
+static inline u64 gs_grid(u64 n) { u64 b = (n + 255) / 256; return b < 148 * 32 ? b : 148 * 32; }
 #define TPB 256
 
 // =========================================================================================== primitives
@@ -499,20 +501,20 @@ static int dd_scatter(spb_ctx* c, const u32* rep) {
 static int dd_ids(spb_ctx* c, u64 lo, u64 hi, const u64* slots, u64 cap = 1) {
   const u64 T = c->T;
   u64 nb = c->npos_pad / 256;
-  u32 *blkcnt, *blkoff; ALLOC(blkcnt, u32, nb); ALLOC(blkoff, u32, nb);
-  SPB_LAUNCH(k_block_counts, nblk(nb, TPB), TPB, c->stream, c->fbits, blkcnt, nb);
+  u32 *blkcnt, *blkoff; u8* wpre; ALLOC(blkcnt, u32, nb); ALLOC(blkoff, u32, nb); ALLOC(wpre, u8, nb * 8 + 8);
+  SPB_LAUNCH(k_block_counts, nblk(nb, TPB), TPB, c->stream, c->fbits, blkcnt, wpre, nb);
   u64 nV = 0;
   PRIM(prim_scan_u32(c, blkcnt, blkoff, nb, &nV));
   c->nV = (u32)nV;
   ALLOC(c->v2pos, u32, nV + 1); ALLOC(c->vflags, u8, nV + 64);
   dev_memset(c, c->vflags + (nV & ~7ull), 0, 64);
   switch ((2 * c->k + 31) / 32) {
-    case 7:  SPB_LAUNCH(k_assign_ids<7>, nblk(T, TPB), TPB, c->stream, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags); break;
-    case 19: SPB_LAUNCH(k_assign_ids<19>, nblk(T, TPB), TPB, c->stream, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags); break;
-    case 32: SPB_LAUNCH(k_assign_ids<32>, nblk(T, TPB), TPB, c->stream, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags); break;
-    default: SPB_LAUNCH(k_assign_ids<0>, nblk(T, TPB), TPB, c->stream, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags); break;
+    case 7:  SPB_LAUNCH(k_assign_ids<7>, gs_grid(T), TPB, c->stream, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags); break;
+    case 19: SPB_LAUNCH(k_assign_ids<19>, gs_grid(T), TPB, c->stream, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags); break;
+    case 32: SPB_LAUNCH(k_assign_ids<32>, gs_grid(T), TPB, c->stream, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags); break;
+    default: SPB_LAUNCH(k_assign_ids<0>, gs_grid(T), TPB, c->stream, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags); break;
   }
-  dfree(c, blkcnt); dfree(c, blkoff);
+  dfree(c, blkcnt); dfree(c, blkoff); dfree(c, wpre);
   return 0;
 }
 
@@ -525,7 +527,7 @@ static int dd_graph(spb_ctx* c) {
   for (int attempt = 0; attempt < 2; ++attempt) {
     ALLOC(Jk, u64, jcap); ALLOC(Js, u8, jcap);
     dev_memset(c, jcount, 0, 16);
-    SPB_LAUNCH(k_junction_emit, nblk(T, TPB), TPB, c->stream, c->sp, T, c->fbits, c->vflags, c->v2pos, c->obits, Jk, Js, jcount, jcap);
+    SPB_LAUNCH(k_junction_emit, std::min<u64>(nblk(T, TPB), 148 * 16), TPB, c->stream, c->sp, T, c->fbits, c->vflags, c->v2pos, c->obits, Jk, Js, jcount, jcap);
     nj = dread(c, jcount);
     if (nj <= jcap) break;
     dfree(c, Jk); dfree(c, Js); jcap = nj;
@@ -573,10 +575,9 @@ static int dedup_global_table(spb_ctx* c) {
     default: launch_extract<0>(c, grid, slots, cap, wbits, dbits); break;
   }
   u64 nb = c->npos_pad / 256;
-  u32* blkcnt; ALLOC(blkcnt, u32, nb);
-  SPB_LAUNCH(k_first_bits, nblk(nb, TPB), TPB, c->stream, wbits, dbits, c->fbits, blkcnt, nb);
+  SPB_LAUNCH(k_first_bits, nblk(nb, TPB), TPB, c->stream, wbits, dbits, c->fbits, nb);
   dev_memset(c, c->fbits + nw32, 0, 32);
-  dfree(c, blkcnt); dfree(c, wbits); dfree(c, dbits);
+  dfree(c, wbits); dfree(c, dbits);
   int r = dd_ids(c, 0, T, slots, cap);
   dfree(c, slots);
   return r;
@@ -823,7 +824,7 @@ int spb_compact(spb_ctx* c, spb_counts* out) {
     for (int attempt = 0; attempt < 2; ++attempt) {
       ALLOC(op, u64, ocap + 1); ALLOC(mp, u64, mcap + 1);
       dev_memset(c, counts, 0, 32); dev_memset(c, has01, 0, 2ull * c->n_seq + 8);
-      SPB_LAUNCH(k_origin_pairs, nblk(T, TPB), TPB, c->stream, c->sp, T, c->vnbp, c->vflags, c->seq_off, c->n_seq, op, counts, ocap, mp,
+      SPB_LAUNCH(k_origin_pairs, gs_grid(T), TPB, c->stream, c->sp, T, c->vnbp, c->vflags, c->seq_off, c->n_seq, op, counts, ocap, mp,
                  counts + 1, mcap, has01);
       SPB_LAUNCH(k_origin_quirk, nblk(c->n_seq, TPB), TPB, c->stream, has01, c->n_seq, c->vnbp, c->vflags, op, counts, ocap, mp, counts + 1,
                  mcap);

@@ -391,29 +391,25 @@ __global__ void k_unpartition(const u32* __restrict__ pos, const u32* __restrict
   if (r == p) atomicOr(fbits + (p >> 5), 1u << (p & 31));
   else sp[p] = r;
 }
-__global__ void k_block_counts(const u32* __restrict__ fbits, u32* __restrict__ cnt, u64 nblk) {
+__global__ void k_block_counts(const u32* __restrict__ fbits, u32* __restrict__ cnt, u8* __restrict__ wpre, u64 nblk) {
   u64 b = SPB_GTID();
   if (b >= nblk) return;
   u32 c = 0;
-  for (u32 j = 0; j < 8; ++j) c += __popc(fbits[b * 8 + j]);
+  for (u32 j = 0; j < 8; ++j) { wpre[b * 8 + j] = (u8)c; c += __popc(fbits[b * 8 + j]); }
   cnt[b] = c;
 }
 
 // first-appearance bitmap fbits = wbits & ~dbits, and per 256-position block counts
-__global__ void k_first_bits(const u32* __restrict__ wbits, const u32* __restrict__ dbits, u32* __restrict__ fbits, u32* __restrict__ cnt, u64 nblk) {
+__global__ void k_first_bits(const u32* __restrict__ wbits, const u32* __restrict__ dbits, u32* __restrict__ fbits, u64 nblk) {
   u64 b = SPB_GTID();
   if (b >= nblk) return;
-  u32 c = 0;
-  for (u32 j = 0; j < 8; ++j) { u32 f = wbits[b * 8 + j] & ~dbits[b * 8 + j]; fbits[b * 8 + j] = f; c += __popc(f); }
-  cnt[b] = c;
+  for (u32 j = 0; j < 8; ++j) fbits[b * 8 + j] = wbits[b * 8 + j] & ~dbits[b * 8 + j];
 }
 
-__device__ __forceinline__ u32 rank_first(const u32* fbits, const u32* blkoff, u32 x) {
-  u32 b = x >> 8, w = (x >> 5) & 7;
-  u32 r = __ldg(blkoff + b);
-  for (u32 j = 0; j < w; ++j) r += __popc(__ldg(fbits + b * 8 + j));
-  r += __popc(__ldg(fbits + (x >> 5)) & ((1u << (x & 31)) - 1));
-  return r;
+// rank of position x among first appearances: block offset (256 positions) + prefix of the words of the block
+// + bits below x in its own word
+__device__ __forceinline__ u32 rank_first(const u32* fbits, const u32* blkoff, const u8* wpre, u32 x) {
+  return __ldg(blkoff + (x >> 8)) + __ldg(wpre + (x >> 5)) + __popc(__ldg(fbits + (x >> 5)) & ((1u << (x & 31)) - 1));
 }
 
 // exact lookup of the first position of the k-mer at p in the finished table (rarely needed, see k_assign_ids)
@@ -443,24 +439,25 @@ template <int W> __device__ __forceinline__ u32 lookup_rep(const u32* __restrict
 // or its exact representative (staged / multi-GPU path, slots == nullptr).  On exit sp[p] = vertex id.
 template <int W> __global__ void
 k_assign_ids(u32* __restrict__ sp, const u32* __restrict__ vbits, u64 T, u64 lo, u64 hi, const u32* __restrict__ fbits,
-             const u32* __restrict__ blkoff, const u64* __restrict__ slots, u64 capmask, const u32* __restrict__ F,
+             const u32* __restrict__ blkoff, const u8* __restrict__ wpre, const u64* __restrict__ slots, u64 capmask, const u32* __restrict__ F,
              const u32* __restrict__ R, u32 k, u32* __restrict__ v2pos, u8* __restrict__ vflags) {
-  u64 p = SPB_GTID();
-  if (p >= T) return;
-  bool mine = p >= lo && p < hi;                 // multi-GPU: sp is filled for the local slice only, the vertex table everywhere
-  if (!get_bit(vbits, p)) { if (mine) sp[p] = SPB_INVALID; return; }
-  bool first = get_bit(fbits, p);
-  if (!first && !mine) return;
-  u32 r = (u32)p;
-  if (!first) {
-    r = sp[p];
-    if (slots && (r == SPB_INVALID || !get_bit(fbits, r))) r = lookup_rep<W>(F, R, T, k, slots, capmask, p);
-  }
-  u32 vid = rank_first(fbits, blkoff, r);
-  if (mine) sp[p] = vid;
-  if (first) {
-    v2pos[vid] = (u32)p;
-    vflags[vid] = get_bit(fbits, p + 1) ? VF_R : 0;   // (p, p+1) both first appearances => edge (vid, vid+1)
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 p = SPB_GTID(); p < T; p += stride) {    // grid-stride: a capped grid avoids scheduling millions of tiny blocks
+    bool mine = p >= lo && p < hi;               // multi-GPU: sp is filled for the local slice only, the vertex table everywhere
+    if (!get_bit(vbits, p)) { if (mine) sp[p] = SPB_INVALID; continue; }
+    bool first = get_bit(fbits, p);
+    if (!first && !mine) continue;
+    u32 r = (u32)p;
+    if (!first) {
+      r = sp[p];
+      if (slots && (r == SPB_INVALID || !get_bit(fbits, r))) r = lookup_rep<W>(F, R, T, k, slots, capmask, p);
+    }
+    u32 vid = rank_first(fbits, blkoff, wpre, r);
+    if (mine) sp[p] = vid;
+    if (first) {
+      v2pos[vid] = (u32)p;
+      vflags[vid] = get_bit(fbits, p + 1) ? VF_R : 0;   // (p, p+1) both first appearances => edge (vid, vid+1)
+    }
   }
 }
 
@@ -468,26 +465,35 @@ k_assign_ids(u32* __restrict__ sp, const u32* __restrict__ vbits, u64 T, u64 lo,
 // lib/Assembler.py:199-201).  It is dropped when it coincides with an implicit edge (v, v+1).
 __global__ void k_junction_emit(const u32* __restrict__ sp, u64 T, const u32* __restrict__ fbits, const u8* __restrict__ vflags, const u32* __restrict__ v2pos,
                                 const u32* __restrict__ obits, u64* __restrict__ Jk, u8* __restrict__ Js, u64* counter, u64 cap) {
-  u64 p = SPB_GTID();
-  u32 n = 0, u = 0, w = 0;
-  if (p + 1 < T && !(get_bit(fbits, p) && get_bit(fbits, p + 1))) {    // two consecutive first appearances: implicit edge
-    u = sp[p]; w = sp[p + 1];
-    if (u != SPB_INVALID && w != SPB_INVALID) {
-      bool implicit = (w == u + 1 && (vflags[u] & VF_R)) || (u == w + 1 && (vflags[w] & VF_R));
-      if (!implicit) n = (u == w) ? 1 : 2;
+  // one warp per 32 positions (= one word of the first-appearance bitmap), grid-stride: a word whose 32 pairs
+  // (p, p+1) are all pairs of consecutive first appearances holds only implicit edges and is skipped at once
+  const u64 nwords = (T + 31) / 32;
+  const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+  const u32 lane = threadIdx.x & 31;
+  for (u64 wd = SPB_GTID() >> 5; wd < nwords; wd += nwarps) {
+    u32 f = __ldg(fbits + wd), fn = __ldg(fbits + wd + 1);
+    if ((f & ((f >> 1) | (fn << 31))) == 0xFFFFFFFFu) continue;
+    u64 p = wd * 32 + lane;
+    u32 n = 0, u = 0, w = 0;
+    if (p + 1 < T && !(get_bit(fbits, p) && get_bit(fbits, p + 1))) {
+      u = sp[p]; w = sp[p + 1];
+      if (u != SPB_INVALID && w != SPB_INVALID) {
+        bool implicit = (w == u + 1 && (vflags[u] & VF_R)) || (u == w + 1 && (vflags[w] & VF_R));
+        if (!implicit) n = (u == w) ? 1 : 2;
+      }
     }
-  }
 #ifndef SPB_EMU
-  if (__ballot_sync(0xffffffffu, n != 0) == 0) return;
+    if (__ballot_sync(0xffffffffu, n != 0) == 0) continue;
 #endif
-  u64 slot = list_reserve(counter, n);
-  if (n == 0 || slot + n > cap) return;
-  u32 su = get_bit(obits, p) ^ get_bit(obits, v2pos[u]);       // instance strand vs. vertex' stored k-mer
-  u32 sw = get_bit(obits, p + 1) ^ get_bit(obits, v2pos[w]);
-  u32 side_u = su ? SIDE_L : SIDE_R;                           // where w attaches on u
-  u32 side_w = sw ? SIDE_R : SIDE_L;                           // where u attaches on w
-  Jk[slot] = ((u64)u << 32) | w; Js[slot] = (u8)(side_u | (side_w << 1));
-  if (n == 2) { Jk[slot + 1] = ((u64)w << 32) | u; Js[slot + 1] = (u8)(side_w | (side_u << 1)); }
+    u64 slot = list_reserve(counter, n);
+    if (n == 0 || slot + n > cap) continue;
+    u32 su = get_bit(obits, p) ^ get_bit(obits, v2pos[u]);       // instance strand vs. vertex' stored k-mer
+    u32 sw = get_bit(obits, p + 1) ^ get_bit(obits, v2pos[w]);
+    u32 side_u = su ? SIDE_L : SIDE_R;                           // where w attaches on u
+    u32 side_w = sw ? SIDE_R : SIDE_L;                           // where u attaches on w
+    Jk[slot] = ((u64)u << 32) | w; Js[slot] = (u8)(side_u | (side_w << 1));
+    if (n == 2) { Jk[slot + 1] = ((u64)w << 32) | u; Js[slot + 1] = (u8)(side_w | (side_u << 1)); }
+  }
 }
 
 // heads of runs of equal keys in a sorted u64 array; optionally check that the payload agrees
@@ -570,20 +576,29 @@ __device__ __forceinline__ bool classify_slow(const GView& g, u32 v, u8 f, u32* 
   }
   return init;
 }
+#define SPB_M8 0x0101010101010101ull
 __global__ void k_classify8(GView g, u8* vflags, u32* err) {
   u64 t = SPB_GTID();
   u64 v0 = t * 8;
   if (v0 >= g.nV) return;
   u64 w = *(const u64*)(g.vflags + v0);
-  u32 prev = v0 ? g.vflags[v0 - 1] : 0;
-  u64 out = w & ~(0x0101010101010101ull * (u64)(VF_INIT | VF_PSTART | VF_PEND | VF_IN2));
-  for (u32 i = 0; i < 8 && v0 + i < g.nV; ++i) {
-    u32 f = (u32)(w >> (8 * i)) & 0xFF;
-    bool init;
-    if (!(f & VF_HASJ)) init = !((prev & VF_R) && (f & VF_R));
-    else init = classify_slow(g, (u32)(v0 + i), (u8)f, err);
-    if (init) out |= (u64)VF_INIT << (8 * i);
-    prev = f;
+  u64 prev = v0 ? g.vflags[v0 - 1] : 0;
+  u64 nvalid = g.nV - v0 < 8 ? g.nV - v0 : 8;
+  u64 vm = nvalid == 8 ? ~0ull : ((1ull << (8 * nvalid)) - 1);
+  // all eight bytes at once (VF_R = bit 0, VF_HASJ = bit 1, VF_INIT = bit 3)
+  u64 r = w & SPB_M8, rprev = (r << 8) | (prev & VF_R);
+  u64 hasj = (w >> 1) & SPB_M8;
+  u64 init = ~(r & rprev) & SPB_M8 & ~hasj;          // no junction entries: init <=> not both implicit neighbours
+  u64 out = (w & ~(SPB_M8 * (u64)(VF_INIT | VF_PSTART | VF_PEND | VF_IN2))) | ((init & vm) << 3);
+  u64 slow = hasj & vm;
+  while (slow) {                                      // the few vertices with junction entries: general rule
+#ifdef SPB_EMU
+    u32 i = (u32)(__builtin_ctzll(slow) >> 3);
+#else
+    u32 i = (u32)((__ffsll((long long)slow) - 1) >> 3);
+#endif
+    slow &= slow - 1;
+    if (classify_slow(g, (u32)(v0 + i), (u8)(w >> (8 * i)), err)) out |= (u64)VF_INIT << (8 * i);
   }
   *(u64*)(vflags + v0) = out;
 }
@@ -595,25 +610,18 @@ __global__ void k_piece_flags8(u8* vflags, u32 nV, u32* __restrict__ cnt3, u32 n
   u64 v0 = t * 8;
   if (v0 >= nV) return;
   u64 w = *(const u64*)(vflags + v0);
-  u32 pf = v0 ? vflags[v0 - 1] : 0;
-  u32 nxt8 = vflags[v0 + 8];                       // padded: bytes >= nV are zero
-  u64 out = w;
-  u32 cI = 0, cS = 0, cE = 0;
-  for (u32 i = 0; i < 8 && v0 + i < nV; ++i) {
-    u32 f = (u32)(w >> (8 * i)) & 0xFF;
-    u32 nf = i < 7 ? (u32)(w >> (8 * (i + 1))) & 0xFF : nxt8;
-    if (v0 + i + 1 >= nV) nf = 0;
-    if (f & VF_INIT) ++cI;
-    else {
-      bool start = !((pf & VF_R) && !(pf & VF_INIT));
-      bool end = !((f & VF_R) && !(nf & VF_INIT));
-      if (start) { out |= (u64)VF_PSTART << (8 * i); ++cS; }
-      if (end) { out |= (u64)VF_PEND << (8 * i); ++cE; }
-    }
-    pf = f;
-  }
-  *(u64*)(vflags + v0) = out;
-  cnt3[t] = cI; cnt3[nT + t] = cS; cnt3[2 * (u64)nT + t] = cE;
+  u64 pf = v0 ? vflags[v0 - 1] : 0;
+  u64 nf = v0 + 8 < nV ? vflags[v0 + 8] : 0;
+  u64 nvalid = nV - v0 < 8 ? nV - v0 : 8;
+  u64 vm = nvalid == 8 ? ~0ull : ((1ull << (8 * nvalid)) - 1);
+  u64 init = (w >> 3) & SPB_M8 & vm, r = w & SPB_M8 & vm;
+  u64 ext = ~init & SPB_M8 & vm;
+  u64 p_r = (r << 8) | (pf & 1), p_init = (init << 8) | ((pf >> 3) & 1);
+  u64 n_init = (init >> 8) | (((nf >> 3) & 1) << 56);
+  u64 start = ext & ~(p_r & ~p_init);                 // no extender predecessor through an implicit edge
+  u64 end = ext & ~(r & ~n_init);                     // no extender successor through an implicit edge
+  *(u64*)(vflags + v0) = w | (start << 5) | (end << 6);
+  cnt3[t] = (u32)__popcll(init); cnt3[nT + t] = (u32)__popcll(start); cnt3[2 * (u64)nT + t] = (u32)__popcll(end);
 }
 __global__ void k_compact3(const u8* __restrict__ vflags, u32 nV, const u32* __restrict__ off3, u32 nT, u32 totI, u32 totS,
                            u32* __restrict__ init_list, u32* __restrict__ plo, u32* __restrict__ phi) {
@@ -802,7 +810,7 @@ __global__ void k_emit_ends(NbpTab t, u32 nN, u32 k, u64 T, const u32* __restric
 }
 
 // K12: the bulk of every NBP: the vertices of its darts.  Work is cut into chunks of SPB_CHUNK ranks.
-#define SPB_CHUNK 1024
+#define SPB_CHUNK 4096
 __global__ void k_dart_chunks(const u32* __restrict__ plo, const u32* __restrict__ phi, u32 nD, u32* __restrict__ nch) {
   u64 d = SPB_GTID();
   if (d >= nD) return;
@@ -862,21 +870,22 @@ k_emit_darts(const u32* __restrict__ choff, u32 nD, const u32* __restrict__ plo,
 __global__ void k_origin_pairs(const u32* __restrict__ sp, u64 T, const u32* __restrict__ vnbp, const u8* __restrict__ vflags,
                                const u64* __restrict__ seq_off, u32 n_seq, u64* __restrict__ opairs, u64* ocount, u64 ocap,
                                u64* __restrict__ mpairs, u64* mcount, u64 mcap, u8* __restrict__ has01) {
-  u64 p = SPB_GTID();
-  if (p >= T) return;
-  u32 v = sp[p];
-  if (v == SPB_INVALID) return;
-  u32 c = vnbp[v];
-  bool in2 = (vflags[v] & VF_IN2) != 0;
-  u32 prev = SPB_INVALID;
-  bool pfirst = true;
-  if (p > 0) { u32 pv = sp[p - 1]; if (pv != SPB_INVALID) { prev = vnbp[pv]; pfirst = false; } }
-  bool emit_o = (c != SPB_INVALID) && (pfirst || c != prev);
-  if (!emit_o && !in2 && v > 1) return;
-  u32 s = upper_bound_u64(seq_off, n_seq + 1, p) - 1;
-  if (v <= 1) has01[2 * s + v] = 1;
-  if (emit_o) { u64 i = atomicAdd(ocount, 1ull); if (i < ocap) opairs[i] = ((u64)c << 32) | s; }
-  if (in2) { u64 i = atomicAdd(mcount, 1ull); if (i < mcap) mpairs[i] = ((u64)v << 32) | s; }
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 p = SPB_GTID(); p < T; p += stride) {
+    u32 v = sp[p];
+    if (v == SPB_INVALID) continue;
+    u32 c = vnbp[v];
+    bool in2 = (vflags[v] & VF_IN2) != 0;
+    u32 prev = SPB_INVALID;
+    bool pfirst = true;
+    if (p > 0) { u32 pv = sp[p - 1]; if (pv != SPB_INVALID) { prev = vnbp[pv]; pfirst = false; } }
+    bool emit_o = (c != SPB_INVALID) && (pfirst || c != prev);
+    if (!emit_o && !in2 && v > 1) continue;
+    u32 s = upper_bound_u64(seq_off, n_seq + 1, p) - 1;
+    if (v <= 1) has01[2 * s + v] = 1;
+    if (emit_o) { u64 i = atomicAdd(ocount, 1ull); if (i < ocap) opairs[i] = ((u64)c << 32) | s; }
+    if (in2) { u64 i = atomicAdd(mcount, 1ull); if (i < mcap) mpairs[i] = ((u64)v << 32) | s; }
+  }
 }
 // compress_vertices leading-zero quirk (reference lib/vtools.pyx:29-45): a sequence whose smallest
 // vertex id is 1 is recorded as containing vertex 0 as well.
