@@ -110,7 +110,7 @@ def run_reference_arm(args):
     cb["value"] = v
     n_inst_sample = int(cb["sample"].split(" k-mer instances")[0].split(", ")[-1])
     print(json.dumps(dict(
-        impl="reference", metric="canonical k-mers/s through DBG build+NBP compaction at k=301", value=v, unit="k-mers/s",
+        impl="reference", metric=f"canonical k-mers/s through DBG build+NBP compaction at k={K}", value=v, unit="k-mers/s",
         n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * n_inst_sample / v, higher_is_better=True,
         scaling="strong", vs_baseline=None, dtype="u64", data="synthetic",
         config=dict(workload=f"{w['desc']}, k={K}, mode={args.mode}", k=K, mode=args.mode),
@@ -127,7 +127,10 @@ def main():
     ap.add_argument("--mode", default="snp", choices=["snp", "block"])
     ap.add_argument("--ref-inst", type=int, default=600_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--k", type=int, default=301, help="k-mer size (BASELINE config 5 sweeps 101 / 301 / 501)")
     args = ap.parse_args()
+    global K
+    K = args.k
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -242,9 +245,13 @@ def main():
         st_mean = {k_: float(np.mean([s[k_] for s in stages])) for k_ in st_keys}
         ni, nv, nbb = counts["n_inst"], counts["n_vertices"], counts["nbp_bases"]
         groups = {
-            "dedup (k_make_records + radix partition + k_bkt_insert/k_bkt_final)":
-                (("records_partition_ms", "bucket_dedup_ms", "dedup_global_ms"), 16 * W * ni + 8 * W * nv),
-            "ids (k_unpartition + k_assign_ids)": (("scatter_ids_ms",), 4 * ni + 8 * nv),
+            "k_extract_insert (canonical k-mer extraction + exact dedup insert)": (("k_extract_insert_ms",), 16 * W * ni + 8 * W * nv),
+            "staged dedup (k_make_records + radix partition + k_bkt_insert/k_bkt_final)":
+                (("records_partition_ms", "bucket_dedup_ms"), 16 * W * ni + 8 * W * nv),
+            "multi-GPU dedup (records, all-to-all, owner dedup, scatter)":
+                (("mg_records_partition_ms", "mg_exchange_records_ms", "mg_owner_dedup_ms", "mg_exchange_reps_ms", "mg_scatter_ms"),
+                 16 * W * ni + 8 * W * nv),
+            "ids (k_assign_ids)": (("scatter_ids_ms", "mg_bitmaps_ids_ms", "mg_allgather_ids_ms"), 4 * ni + 8 * nv),
             "edges (k_junction_emit + k_edge_*)": (("edges_ms",), 20 * ni + 8 * nv),
             "compaction (k_classify8 .. k_rank_jump)": (("classify_rank_ms",), 16 * nv),
             "emit (k_emit_darts + k_emit_ends)": (("emit_ms",), nbb),
@@ -253,10 +260,17 @@ def main():
         dom = max(gtime, key=gtime.get)
         dom_bytes, dom_ms = groups[dom][1], gtime[dom]
         ach = dom_bytes / (dom_ms / 1e3) / 1e9
+        # measured DRAM traffic of the dominant kernel (ncu --set full, per launch), if a capture of this workload is committed
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tr.get(f"{args.workload}:{args.mode}:{world}:{K}", {}).get(dom.split(" ")[0])
+        except Exception:
+            pass
         pipe_bytes = algorithmic_bytes(ni, nv, nbb)
         pipe_ach = pipe_bytes / (ms / args.steps / 1e3) / 1e9
         line = dict(
-            metric="canonical k-mers/s through DBG build+NBP compaction at k=301", value=value, unit="k-mers/s",
+            metric=f"canonical k-mers/s through DBG build+NBP compaction at k={K}", value=value, unit="k-mers/s",
             n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True,
             scaling="strong", vs_baseline=None, dtype="u64", data="synthetic",
             config=dict(workload=f"{w['desc']}, k={K}, mode={args.mode}", k=K, mode=args.mode, n_inst=n_inst,
@@ -266,7 +280,7 @@ def main():
             e2e=dict(value=e2e_value, unit="k-mers/s", ms_per_step=ms_e2e / args.steps, h2d_bytes_per_step=int(buf.nbytes + off.nbytes),
                      d2h_bytes_per_step=int(e2e_last[1])),
             gpu_launches=int(launches),
-            roofline=dict(bound="hbm", kernel=dom, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None,
+            roofline=dict(bound="hbm", kernel=dom, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=traffic,
                           peak_source=peak_src, kernel_ms=dom_ms, model_bytes=dom_bytes,
                           pipeline=dict(achieved=pipe_ach, frac=pipe_ach / peak, bytes=pipe_bytes)),
             stages_ms=st_mean,
