@@ -149,7 +149,7 @@ static int prim_sort_u64_u64(spb_ctx*, u64*& k, u64*& v, u64*& k2, u64*& v2, u64
   for (u64 i = 0; i < n; ++i) { k2[i] = k[idx[i]]; v2[i] = v[idx[i]]; }
   std::swap(k, k2); std::swap(v, v2); return 0;
 }
-static int prim_sort_u64(spb_ctx*, u64*& k, u64* k2, u64 n) { std::sort(k, k + n); (void)k2; return 0; }
+static int prim_sort_u64(spb_ctx*, u64*& k, u64* k2, u64 n, int end_bit = 64) { std::sort(k, k + n); (void)k2; (void)end_bit; return 0; }
 static int prim_partition_u64_u32(spb_ctx*, u64*& k, u32*& v, u64*& k2, u32*& v2, u64 n, int b0, int b1) {   // stable, by key bits [b0, b1)
   std::vector<u64> idx(n); for (u64 i = 0; i < n; ++i) idx[i] = i;
   u64 mask = (b1 - b0 >= 64) ? ~0ull : ((1ull << (b1 - b0)) - 1);
@@ -208,10 +208,10 @@ static int prim_partition_u64_u32(spb_ctx* c, u64*& k, u32*& v, u64*& k2, u32*& 
   if (dv.Current() != v) { std::swap(v, v2); }
   return 0;
 }
-static int prim_sort_u64(spb_ctx* c, u64*& k, u64* k2, u64 n) {
+static int prim_sort_u64(spb_ctx* c, u64*& k, u64* k2, u64 n, int end_bit = 64) {   // keys are known to fit in end_bit bits
   if (n == 0) return 0;
   cub::DoubleBuffer<u64> dk(k, k2);
-  CUB2(cub::DeviceRadixSort::SortKeys(tmp, tb, dk, (size_t)n, 0, 64, c->stream));
+  CUB2(cub::DeviceRadixSort::SortKeys(tmp, tb, dk, (size_t)n, 0, end_bit, c->stream));
   if (dk.Current() != k) {            // keep the result in the caller's primary buffer
     CK(cudaMemcpyAsync(k, k2, n * 8, cudaMemcpyDeviceToDevice, c->stream));
   }
@@ -805,13 +805,18 @@ int spb_compact(spb_ctx* c, spb_counts* out) {
   // ---- K11/K12: NBP vertex lists + sequences
   ALLOC(c->verts, u32, totv + 1); ALLOC(c->seqs, u8, tots + 1);
   ALLOC(c->vnbp, u32, (u64)nV + 1); dev_memset(c, c->vnbp, 0xFF, ((u64)nV + 1) * 4);
-  SPB_LAUNCH(k_emit_ends, nN, 128, c->stream, t, nN, k, T, c->F, c->R, c->v2pos, c->voff, c->soff, c->verts, c->seqs);
-  u32 *nch, *choff; ALLOC(nch, u32, nD + 1); ALLOC(choff, u32, nD + 1);
-  SPB_LAUNCH(k_dart_chunks, nblk(nD, TPB), TPB, c->stream, c->plo, c->phi, nD, nch);
-  u64 nchunks = 0;
+  SPB_LAUNCH(k_emit_ends, nblk((u64)nN * 32, TPB), TPB, c->stream, t, nN, k, T, c->F, c->R, c->v2pos, c->voff, c->soff, c->verts, c->seqs);
+  u32 *nch, *choff, *nel, *eoff; ALLOC(nch, u32, nD + 1); ALLOC(choff, u32, nD + 1); ALLOC(nel, u32, nD + 1); ALLOC(eoff, u32, nD + 1);
+  SPB_LAUNCH(k_dart_chunks, nblk(nD, TPB), TPB, c->stream, c->plo, c->phi, nD, nch, nel);
+  u64 nchunks = 0, nshort = 0;
   PRIM(prim_scan_u32(c, nch, choff, nD, &nchunks));
+  PRIM(prim_scan_u32(c, nel, eoff, nD, &nshort));
+  if (nshort >= (1ull << 32) || nchunks >= (1ull << 31)) return fail(c, SPB_EINVAL, "input too large for 32-bit dart offsets");
   SPB_LAUNCH(k_emit_darts, nchunks, 256, c->stream, choff, nD, c->plo, c->phi, c->dart_nbp, acc[cur], k, T, c->F, c->R, c->v2pos, c->voff,
              c->soff, c->verts, c->seqs, c->vnbp);
+  SPB_LAUNCH(k_emit_short, nblk(nshort, 256), 256, c->stream, eoff, nD, nshort, c->plo, c->phi, c->dart_nbp, acc[cur], k, T, c->F, c->R,
+             c->v2pos, c->voff, c->soff, c->verts, c->seqs, c->vnbp);
+  dfree(c, nel); dfree(c, eoff);
   dfree(c, nch); dfree(c, choff); dfree(c, head_nbp); dfree(c, nxt);
   dfree(c, pl_nbr); dfree(c, pr_nbr); dfree(c, pl_side); dfree(c, pr_side);
   for (int i = 0; i < 2; ++i) { dfree(c, ptr[i]); dfree(c, acc[i]); dfree(c, root[i]); dfree(c, mnv[i]); }
@@ -821,15 +826,18 @@ int spb_compact(spb_ctx* c, spb_counts* out) {
   {
     u64* counts; ALLOC(counts, u64, 4);
     u8* has01; ALLOC(has01, u8, 2ull * c->n_seq + 8);
+    u32 sb = 1; while ((1ull << sb) <= c->n_seq) ++sb;          // keys = (NBP or vertex id) << sb | sequence index
+    u32 ob = sb + 1; while (ob < 64 && (1ull << (ob - sb)) <= (u64)nN) ++ob;
+    u32 mb = sb + 1; while (mb < 64 && (1ull << (mb - sb)) <= (u64)nV) ++mb;
     u64 ocap = std::max<u64>(4096, c->n_inst / 16), mcap = std::max<u64>(4096, c->n_inst / 64);
     u64 *op = 0, *mp = 0; u64 no = 0, nm = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
       ALLOC(op, u64, ocap + 1); ALLOC(mp, u64, mcap + 1);
       dev_memset(c, counts, 0, 32); dev_memset(c, has01, 0, 2ull * c->n_seq + 8);
       SPB_LAUNCH(k_origin_pairs, gs_grid(T), TPB, c->stream, c->sp, T, c->vnbp, c->vflags, c->seq_off, c->n_seq, op, counts, ocap, mp,
-                 counts + 1, mcap, has01);
+                 counts + 1, mcap, has01, sb);
       SPB_LAUNCH(k_origin_quirk, nblk(c->n_seq, TPB), TPB, c->stream, has01, c->n_seq, c->vnbp, c->vflags, op, counts, ocap, mp, counts + 1,
-                 mcap);
+                 mcap, sb);
       no = dread(c, counts); nm = dread(c, counts + 1);
       if (no <= ocap && nm <= mcap) break;
       dfree(c, op); dfree(c, mp); ocap = std::max(ocap, no); mcap = std::max(mcap, nm);
@@ -837,20 +845,20 @@ int spb_compact(spb_ctx* c, spb_counts* out) {
     dfree(c, counts); dfree(c, has01);
     u64* tmp; u8* nopay = nullptr;
     ALLOC(tmp, u64, std::max(no, nm) + 1);
-    PRIM(prim_sort_u64(c, op, tmp, no));
-    PRIM(prim_sort_u64(c, mp, tmp, nm));
+    PRIM(prim_sort_u64(c, op, tmp, no, ob));
+    PRIM(prim_sort_u64(c, mp, tmp, nm, mb));
     dfree(c, tmp);
     PRIM(unique_sorted(c, op, nopay, no, &c->nO));
     PRIM(unique_sorted(c, mp, nopay, nm, &c->nM));
     if (!op) ALLOC(op, u64, 1);
     if (!mp) ALLOC(mp, u64, 1);
     u64* ocnt; ALLOC(ocnt, u64, nN + 1); ALLOC(c->ooff, u64, nN + 1);
-    SPB_LAUNCH(k_nbp_origins, nblk(nN, TPB), TPB, c->stream, t, nN, c->dart_nbp, op, c->nO, mp, c->nM, (const u64*)nullptr, ocnt, (u32*)nullptr);
+    SPB_LAUNCH(k_nbp_origins, nblk(nN, TPB), TPB, c->stream, t, nN, c->dart_nbp, op, c->nO, mp, c->nM, sb, (const u64*)nullptr, ocnt, (u32*)nullptr);
     u64 toto = 0;
     PRIM(prim_scan_u64(c, ocnt, c->ooff, nN, &toto));
     dev_copy(c, c->ooff + nN, &toto, 8); dev_sync(c);
     ALLOC(c->origins, u32, toto + 1);
-    SPB_LAUNCH(k_nbp_origins, nblk(nN, TPB), TPB, c->stream, t, nN, c->dart_nbp, op, c->nO, mp, c->nM, c->ooff, ocnt, c->origins);
+    SPB_LAUNCH(k_nbp_origins, nblk(nN, TPB), TPB, c->stream, t, nN, c->dart_nbp, op, c->nO, mp, c->nM, sb, c->ooff, ocnt, c->origins);
     dfree(c, ocnt); dfree(c, op); dfree(c, mp);
     c->cnt.n_origin_pairs = toto;
   }

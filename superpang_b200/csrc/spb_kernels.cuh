@@ -60,6 +60,24 @@ __device__ __forceinline__ u64 list_reserve(u64* counter, u32 n) {
 #endif
 }
 
+// append one item per flagged thread to a list guarded by a u64 counter (one atomic per warp); callable under
+// divergence.  Returns the slot of the calling thread (meaningful only when flag is set).
+__device__ __forceinline__ u64 warp_append(u64* counter, bool flag) {
+#ifdef SPB_EMU
+  return flag ? atomicAdd(counter, 1ull) : ~0ull;
+#else
+  u32 act = __activemask();
+  u32 bal = __ballot_sync(act, flag);
+  if (!flag) return ~0ull;
+  u32 lane = threadIdx.x & 31;
+  int leader = __ffs(bal) - 1;
+  u64 base = 0;
+  if ((int)lane == leader) base = atomicAdd(counter, (u64)__popc(bal));
+  base = __shfl_sync(bal, base, leader);
+  return base + __popc(bal & ((1u << lane) - 1));
+#endif
+}
+
 // ------------------------------------------------------------------------------------ windows
 // Packed strands are arrays of u32 words, 16 bases per word, first base in the top bits, so that
 // unsigned compare of 32-bit limbs == lexicographic compare of bases (A<C<G<T).
@@ -788,7 +806,8 @@ __device__ __forceinline__ u8 code2ascii(u32 c) { return (u8)("ACGT"[c]); }
 __global__ void k_emit_ends(NbpTab t, u32 nN, u32 k, u64 T, const u32* __restrict__ F, const u32* __restrict__ R,
                             const u32* __restrict__ v2pos, const u64* __restrict__ voff, const u64* __restrict__ soff,
                             u32* __restrict__ verts, u8* __restrict__ seq) {
-  u32 id = blockIdx.x;
+  u64 id = SPB_GTID() >> 5;                    // one warp per NBP
+  u32 lane = threadIdx.x & 31;
   if (id >= nN) return;
   u32 a = t.a[id], b = t.b[id];
   u64 vo = voff[id], so = soff[id];
@@ -798,8 +817,8 @@ __global__ void k_emit_ends(NbpTab t, u32 nN, u32 k, u64 T, const u32* __restric
   u64 pa = v2pos[a], pb = v2pos[b];
   const u32* S = afwd ? F : R;
   u64 s0 = afwd ? pa : T - pa - k;
-  for (u32 j = threadIdx.x; j < k; j += blockDim.x) seq[so + j] = code2ascii(base_at(S, s0 + j));
-  if (threadIdx.x == 0) {
+  for (u32 j = lane; j < k; j += 32) seq[so + j] = code2ascii(base_at(S, s0 + j));
+  if (lane == 0) {
     verts[vo] = a; verts[vo + L - 1] = b;
     seq[so + k - 1 + (L - 1)] = code2ascii(bfwd ? base_at(F, pb + k - 1) : base_at(R, T - 1 - pb));
     if (t.cyc[id]) {                            // closing vertex of a broken cycle (reference lib/Assembler.py:341-343)
@@ -811,11 +830,50 @@ __global__ void k_emit_ends(NbpTab t, u32 nN, u32 k, u64 T, const u32* __restric
 
 // K12: the bulk of every NBP: the vertices of its darts.  Work is cut into chunks of SPB_CHUNK ranks.
 #define SPB_CHUNK 4096
-__global__ void k_dart_chunks(const u32* __restrict__ plo, const u32* __restrict__ phi, u32 nD, u32* __restrict__ nch) {
+#define SPB_SHORT_DART 512
+// long darts are cut into chunks (k_emit_darts), short ones are emitted element-parallel (k_emit_short)
+__global__ void k_dart_chunks(const u32* __restrict__ plo, const u32* __restrict__ phi, u32 nD, u32* __restrict__ nch, u32* __restrict__ nel) {
   u64 d = SPB_GTID();
   if (d >= nD) return;
   u32 len = phi[d >> 1] - plo[d >> 1] + 1;
-  nch[d] = (len + SPB_CHUNK - 1) / SPB_CHUNK;
+  bool is_short = len < SPB_SHORT_DART;
+  nch[d] = is_short ? 0 : (len + SPB_CHUNK - 1) / SPB_CHUNK;
+  nel[d] = is_short ? len : 0;
+}
+// element e of the concatenated short darts: eoff = exclusive scan of their lengths (long darts count 0)
+__global__ void SPB_LAUNCH_BOUNDS(256)
+k_emit_short(const u32* __restrict__ eoff, u32 nD, u64 nE, const u32* __restrict__ plo, const u32* __restrict__ phi,
+             const u32* __restrict__ dart_nbp, const u32* __restrict__ acc, u32 k, u64 T, const u32* __restrict__ F,
+             const u32* __restrict__ R, const u32* __restrict__ v2pos, const u64* __restrict__ voff,
+             const u64* __restrict__ soff, u32* __restrict__ verts, u8* __restrict__ seq, u32* __restrict__ vnbp) {
+  u64 e0 = (u64)blockIdx.x * blockDim.x, e = e0 + threadIdx.x;
+  // darts touched by this block: [dlo, dhi)
+#ifdef SPB_EMU
+  u32 dlo = upper_bound_u32(eoff, nD, (u32)e0) - 1;
+  u64 elast = e0 + blockDim.x - 1 < nE ? e0 + blockDim.x - 1 : nE - 1;
+  u32 dhi = upper_bound_u32(eoff, nD, (u32)elast);
+#else
+  __shared__ u32 sd[2];
+  if (threadIdx.x == 0) {
+    sd[0] = upper_bound_u32(eoff, nD, (u32)e0) - 1;
+    u64 elast = e0 + blockDim.x - 1 < nE ? e0 + blockDim.x - 1 : nE - 1;
+    sd[1] = upper_bound_u32(eoff, nD, (u32)elast);
+  }
+  __syncthreads();
+  u32 dlo = sd[0], dhi = sd[1];
+#endif
+  if (e >= nE) return;
+  u32 d = dlo + upper_bound_u32(eoff + dlo, dhi - dlo, (u32)e) - 1;
+  u32 t = (u32)e - eoff[d];
+  u32 P = d >> 1; bool up = !(d & 1);
+  u32 lo = plo[P], hi = phi[P];
+  u32 id = dart_nbp[d];
+  u32 v = up ? lo + t : hi - t;
+  u64 r = (u64)acc[d] + t;
+  verts[voff[id] + r] = v;
+  u64 src = up ? (u64)v2pos[lo] + k - 1 + t : T - 1 - (u64)v2pos[hi] + t;
+  seq[soff[id] + (k - 1) + r] = code2ascii(base_at(up ? F : R, src));
+  if (up) { u32 un = dart_nbp[d ^ 1]; vnbp[v] = id < un ? id : un; }
 }
 struct ChunkParams { u64 vo, so, src; u32 lo, hi, un, t0, n; u32 up; };
 __device__ __forceinline__ ChunkParams chunk_params(u32 c, const u32* choff, u32 nD, const u32* plo, const u32* phi, const u32* dart_nbp,
@@ -869,7 +927,7 @@ k_emit_darts(const u32* __restrict__ choff, u32 nD, const u32* __restrict__ plo,
 // sequence) membership pairs for the inits of 2-vertex NBPs (reference lib/Assembler.py:1212-1262).
 __global__ void k_origin_pairs(const u32* __restrict__ sp, u64 T, const u32* __restrict__ vnbp, const u8* __restrict__ vflags,
                                const u64* __restrict__ seq_off, u32 n_seq, u64* __restrict__ opairs, u64* ocount, u64 ocap,
-                               u64* __restrict__ mpairs, u64* mcount, u64 mcap, u8* __restrict__ has01) {
+                               u64* __restrict__ mpairs, u64* mcount, u64 mcap, u8* __restrict__ has01, u32 sb) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
   for (u64 p = SPB_GTID(); p < T; p += stride) {
     u32 v = sp[p];
@@ -883,32 +941,32 @@ __global__ void k_origin_pairs(const u32* __restrict__ sp, u64 T, const u32* __r
     if (!emit_o && !in2 && v > 1) continue;
     u32 s = upper_bound_u64(seq_off, n_seq + 1, p) - 1;
     if (v <= 1) has01[2 * s + v] = 1;
-    if (emit_o) { u64 i = atomicAdd(ocount, 1ull); if (i < ocap) opairs[i] = ((u64)c << 32) | s; }
-    if (in2) { u64 i = atomicAdd(mcount, 1ull); if (i < mcap) mpairs[i] = ((u64)v << 32) | s; }
+    u64 i = warp_append(ocount, emit_o); if (emit_o && i < ocap) opairs[i] = ((u64)c << sb) | s;
+    u64 j = warp_append(mcount, in2);    if (in2 && j < mcap) mpairs[j] = ((u64)v << sb) | s;
   }
 }
 // compress_vertices leading-zero quirk (reference lib/vtools.pyx:29-45): a sequence whose smallest
 // vertex id is 1 is recorded as containing vertex 0 as well.
 __global__ void k_origin_quirk(const u8* __restrict__ has01, u32 n_seq, const u32* __restrict__ vnbp, const u8* __restrict__ vflags,
-                               u64* __restrict__ opairs, u64* ocount, u64 ocap, u64* __restrict__ mpairs, u64* mcount, u64 mcap) {
+                               u64* __restrict__ opairs, u64* ocount, u64 ocap, u64* __restrict__ mpairs, u64* mcount, u64 mcap, u32 sb) {
   u64 s = SPB_GTID();
   if (s >= n_seq) return;
   if (!(has01[2 * s + 1] && !has01[2 * s])) return;
   u32 c = vnbp[0];
-  if (c != SPB_INVALID) { u64 i = atomicAdd(ocount, 1ull); if (i < ocap) opairs[i] = ((u64)c << 32) | s; }
+  if (c != SPB_INVALID) { u64 i = atomicAdd(ocount, 1ull); if (i < ocap) opairs[i] = ((u64)c << sb) | s; }
   if (vflags[0] & VF_IN2) { u64 i = atomicAdd(mcount, 1ull); if (i < mcap) mpairs[i] = (u64)s; }
 }
 
-__device__ __forceinline__ void key_range(const u64* keys, u32 n, u32 hi32, u32* lo, u32* hi) {
-  *lo = lower_bound_key(keys, n, (u64)hi32 << 32);
-  *hi = lower_bound_key(keys, n, ((u64)hi32 << 32) | 0xFFFFFFFFull);
-  if (*hi < n && keys[*hi] == (((u64)hi32 << 32) | 0xFFFFFFFFull)) ++*hi;
+__device__ __forceinline__ void key_range(const u64* keys, u32 n, u32 id, u32 sb, u32* lo, u32* hi) {   // entries with key >> sb == id
+  *lo = lower_bound_key(keys, n, (u64)id << sb);
+  *hi = lower_bound_key(keys, n, ((u64)id + 1) << sb);
 }
-// merge-count / merge-write of two sorted u32-suffix lists: union (mode 0) or intersection (mode 1)
-__device__ __forceinline__ u32 merge_lists(const u64* A, u32 a0, u32 a1, const u64* B, u32 b0, u32 b1, int mode, u32* out) {
+// merge-count / merge-write of two sorted lists of (id << sb | seq) keys: union (mode 0) or intersection (mode 1) of the seq parts
+__device__ __forceinline__ u32 merge_lists(const u64* A, u32 a0, u32 a1, const u64* B, u32 b0, u32 b1, int mode, u32 sb, u32* out) {
+  const u64 m = (1ull << sb) - 1;
   u32 n = 0;
   while (a0 < a1 || b0 < b1) {
-    u32 x = a0 < a1 ? (u32)A[a0] : 0xFFFFFFFFu, y = b0 < b1 ? (u32)B[b0] : 0xFFFFFFFFu;
+    u32 x = a0 < a1 ? (u32)(A[a0] & m) : 0xFFFFFFFFu, y = b0 < b1 ? (u32)(B[b0] & m) : 0xFFFFFFFFu;
     if (a0 < a1 && b0 < b1 && x == y) { if (out) out[n] = x; ++n; ++a0; ++b0; }
     else if (b0 >= b1 || (a0 < a1 && x < y)) { if (mode == 0) { if (out) out[n] = x; ++n; } ++a0; }
     else { if (mode == 0) { if (out) out[n] = y; ++n; } ++b0; }
@@ -918,7 +976,7 @@ __device__ __forceinline__ u32 merge_lists(const u64* A, u32 a0, u32 a1, const u
 // per-NBP origin lists.  L >= 3: sequences touching an interior vertex; cycle NBPs also count their
 // last init (it is interior once the first vertex is appended); L == 2: sequences containing both.
 __global__ void k_nbp_origins(NbpTab t, u32 nN, const u32* __restrict__ dart_nbp, const u64* __restrict__ opairs, u32 nO,
-                              const u64* __restrict__ mpairs, u32 nM, const u64* __restrict__ ooff, u64* __restrict__ ocnt,
+                              const u64* __restrict__ mpairs, u32 nM, u32 sb, const u64* __restrict__ ooff, u64* __restrict__ ocnt,
                               u32* __restrict__ out) {
   u64 id = SPB_GTID();
   if (id >= nN) return;
@@ -926,15 +984,15 @@ __global__ void k_nbp_origins(NbpTab t, u32 nN, const u32* __restrict__ dart_nbp
   u32 n;
   if (t.head[id] == SPB_TERM) {
     u32 a0, a1, b0, b1;
-    key_range(mpairs, nM, t.a[id], &a0, &a1); key_range(mpairs, nM, t.b[id], &b0, &b1);
-    n = merge_lists(mpairs, a0, a1, mpairs, b0, b1, 1, dst);
+    key_range(mpairs, nM, t.a[id], sb, &a0, &a1); key_range(mpairs, nM, t.b[id], sb, &b0, &b1);
+    n = merge_lists(mpairs, a0, a1, mpairs, b0, b1, 1, sb, dst);
   } else {
     u32 un = dart_nbp[t.head[id]], rv = dart_nbp[t.last[id] ^ 1];
     if (rv < un) un = rv;
     u32 a0, a1, b0 = 0, b1 = 0;
-    key_range(opairs, nO, un, &a0, &a1);
-    if (t.cyc[id]) key_range(mpairs, nM, t.b[id], &b0, &b1);
-    n = merge_lists(opairs, a0, a1, mpairs, b0, b1, 0, dst);
+    key_range(opairs, nO, un, sb, &a0, &a1);
+    if (t.cyc[id]) key_range(mpairs, nM, t.b[id], sb, &b0, &b1);
+    n = merge_lists(opairs, a0, a1, mpairs, b0, b1, 0, sb, dst);
   }
   if (!out) ocnt[id] = n;
 }
