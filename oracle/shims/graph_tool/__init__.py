@@ -2,17 +2,23 @@
 TEST INFRASTRUCTURE ONLY -- minimal stand-in for the `graph_tool` package.
 
 The reference (fpusan/SuperPang, `src/superpang/lib/Assembler.py:14-15`) imports graph-tool,
-which is not installed in this image.  This stub provides exactly the subset that the
-hot path (`Assembler.__init__`, `Assembler.py:251-255`, and the NBP-collection head of
-`Assembler.run`, `Assembler.py:271-334`) touches, so that the *unmodified* reference code can
-be executed as the parity oracle (see `oracle/refrun.py`).
+which is not installed in this image.  This stub provides the subset that `Assembler.__init__`
+(`Assembler.py:251-255`) and `Assembler.run` (`Assembler.py:271-334`, `:376-384`, `:418-424`, `:468-472`, `:500`,
+`:537-568`, `:635`, `:682-700`, `:767-779`, `:969-975`) touch, so that the *unmodified* reference code can
+be executed as the parity oracle (`oracle/refrun.py`) and for the drop-in integration test
+(`oracle/dropin.py`).  Checklist: SURVEY.md appendix A.
 
-Semantics implemented (SURVEY.md appendix A):
-  * `Graph(directed=False).add_edge_list(uint32[E,2])`: vertex count = max id + 1.
-  * `get_out_neighbors(v)`: for an undirected graph, the neighbours through edges in which `v`
-    is the source (edge-insertion order) followed by those in which `v` is the target; an
-    undirected self-loop is listed twice (graph-tool behaviour); honours the edge filter.
-  * `label_components(g, directed=False)`: components numbered in order of their lowest vertex id.
+Semantics implemented:
+  * `Graph(directed=False).add_edge_list(uint32[E,2])`: vertex count = max id + 1; `get_out_neighbors(v)` lists the
+    neighbours through edges in which `v` is the source (edge-insertion order) followed by those in which `v`
+    is the target; an undirected self-loop is listed twice; honours the edge filter.
+  * `Graph()` (directed): `add_vertex`, `add_edge` (parallel edges allowed), `get_out/in/all_neighbors`,
+    `vertices()` / `edges()` / `num_vertices()` / `num_edges()`, all honouring the vertex filter, which is a LIVE
+    view of the property map handed to `set_vertex_filter` (as in graph-tool).
+  * property maps index by vertex / edge descriptor or int, expose `get_array()`, and ITERATE over the visible
+    vertices only (`zip(g.vertices(), label_components(g)[0])`, `Assembler.py:540`).
+  * `label_components(g, directed=False)`: components of the visible sub-graph, numbered in order of their
+    lowest vertex id.
 
 Nothing under `superpang_b200/` imports this module.
 """
@@ -21,8 +27,9 @@ from . import topology  # noqa: F401
 
 
 class _PropertyMap:
-    def __init__(self, arr):
+    def __init__(self, arr, graph=None):
         self.a = arr
+        self._g = graph            # set for vertex maps: iteration follows the graph's vertex filter
 
     def get_array(self):
         return self.a
@@ -34,7 +41,12 @@ class _PropertyMap:
         self.a[int(k)] = v
 
     def __iter__(self):
+        if self._g is not None and self._g._vfilt is not None:
+            return iter(self.a[self._g._visible_mask()])
         return iter(self.a)
+
+    def __len__(self):
+        return len(self.a)
 
 
 class _PropDict:
@@ -71,9 +83,12 @@ class Graph:
     def __init__(self, directed=True):
         self._directed = directed
         self._nv = 0
-        self._edges = np.zeros((0, 2), dtype=np.int64)
+        self._edges = np.zeros((0, 2), dtype=np.int64)      # static edge list (add_edge_list)
         self._adj_ptr = None
         self._efilt = None
+        self._vfilt = None                                  # live _PropertyMap (or None)
+        self._vfilt_inv = False
+        self._dyn_out, self._dyn_in, self._dyn_edges = [], [], []   # dynamic graphs (add_vertex / add_edge)
         self.vp = _PropDict()
         self.ep = _PropDict()
 
@@ -99,44 +114,33 @@ class Graph:
         counts = np.bincount(owner, minlength=self._nv)
         self._adj_ptr = np.concatenate([[0], np.cumsum(counts)])
 
-    # -- queries ------------------------------------------------------------------------
-    def num_vertices(self):
-        return self._nv
+    def add_vertex(self):
+        self._dyn_out.append([])
+        self._dyn_in.append([])
+        self._nv += 1
+        return self._nv - 1
 
-    def num_edges(self):
-        if self._efilt is not None:
-            return int(np.count_nonzero(self._efilt))
-        return self._edges.shape[0]
-
-    def get_out_neighbors(self, v):
-        v = int(v)
-        lo, hi = self._adj_ptr[v], self._adj_ptr[v + 1]
-        nbr = self._adj_nbr[lo:hi]
-        if self._efilt is not None:
-            nbr = nbr[self._efilt[self._adj_eid[lo:hi]]]
-        return nbr
-
-    get_all_neighbors = get_out_neighbors
-
-    def edge(self, a, b):
+    def add_edge(self, a, b):
         a, b = int(a), int(b)
-        lo, hi = self._adj_ptr[a], self._adj_ptr[a + 1]
-        for nb, e in zip(self._adj_nbr[lo:hi], self._adj_eid[lo:hi]):
-            if nb == b:
-                return _Edge(int(self._edges[e, 0]), int(self._edges[e, 1]), int(e))
-        return None
+        self._dyn_out[a].append(b)
+        self._dyn_in[b].append(a)
+        self._dyn_edges.append((a, b))
+        return _Edge(a, b, len(self._dyn_edges) - 1)
 
-    def edges(self):
-        for e in range(self._edges.shape[0]):
-            if self._efilt is None or self._efilt[e]:
-                yield _Edge(int(self._edges[e, 0]), int(self._edges[e, 1]), e)
+    # -- filters -------------------------------------------------------------------------
+    def _visible_mask(self):
+        m = np.asarray(self._vfilt.a, dtype=bool)
+        return ~m if self._vfilt_inv else m
 
-    # -- properties / filters -------------------------------------------------------------
-    def new_vertex_property(self, typ):
-        return _PropertyMap(np.zeros(self._nv, dtype=_TYPES[typ]))
+    def _vis(self, v):
+        if self._vfilt is None:
+            return True
+        x = bool(self._vfilt.a[v])
+        return (not x) if self._vfilt_inv else x
 
-    def new_edge_property(self, typ):
-        return _PropertyMap(np.zeros(self._edges.shape[0], dtype=_TYPES[typ]))
+    def set_vertex_filter(self, prop, inverted=False):
+        self._vfilt = prop
+        self._vfilt_inv = inverted
 
     def set_edge_filter(self, prop, inverted=False):
         if prop is None:
@@ -147,3 +151,83 @@ class Graph:
 
     def clear_filters(self):
         self._efilt = None
+        self._vfilt = None
+        self._vfilt_inv = False
+
+    # -- queries ------------------------------------------------------------------------
+    def num_vertices(self):
+        if self._vfilt is not None:
+            return int(np.count_nonzero(self._visible_mask()))
+        return self._nv
+
+    def num_edges(self):
+        if self._adj_ptr is not None:
+            if self._efilt is not None:
+                return int(np.count_nonzero(self._efilt))
+            return self._edges.shape[0]
+        return sum(1 for a, b in self._dyn_edges if self._vis(a) and self._vis(b))
+
+    def vertices(self):
+        for v in range(self._nv):
+            if self._vis(v):
+                yield v
+
+    def get_out_neighbors(self, v):
+        v = int(v)
+        if self._adj_ptr is not None:
+            lo, hi = self._adj_ptr[v], self._adj_ptr[v + 1]
+            nbr = self._adj_nbr[lo:hi]
+            if self._efilt is not None:
+                nbr = nbr[self._efilt[self._adj_eid[lo:hi]]]
+            return nbr
+        return np.asarray([x for x in self._dyn_out[v] if self._vis(x)], dtype=np.int64)
+
+    def get_in_neighbors(self, v):
+        v = int(v)
+        if self._adj_ptr is not None:
+            return self.get_out_neighbors(v)
+        return np.asarray([x for x in self._dyn_in[v] if self._vis(x)], dtype=np.int64)
+
+    def get_all_neighbors(self, v):
+        v = int(v)
+        if self._adj_ptr is not None:
+            return self.get_out_neighbors(v)
+        return np.asarray([x for x in self._dyn_out[v] + self._dyn_in[v] if self._vis(x)], dtype=np.int64)
+
+    def edge(self, a, b):
+        a, b = int(a), int(b)
+        lo, hi = self._adj_ptr[a], self._adj_ptr[a + 1]
+        for nb, e in zip(self._adj_nbr[lo:hi], self._adj_eid[lo:hi]):
+            if nb == b:
+                return _Edge(int(self._edges[e, 0]), int(self._edges[e, 1]), int(e))
+        return None
+
+    def edges(self):
+        if self._adj_ptr is not None:
+            for e in range(self._edges.shape[0]):
+                if self._efilt is None or self._efilt[e]:
+                    yield _Edge(int(self._edges[e, 0]), int(self._edges[e, 1]), e)
+        else:
+            for i, (a, b) in enumerate(self._dyn_edges):
+                if self._vis(a) and self._vis(b):
+                    yield _Edge(a, b, i)
+
+    def _visible_edge_array(self):
+        if self._adj_ptr is not None:
+            e = self._edges
+            return e[self._efilt] if self._efilt is not None else e
+        if not self._dyn_edges:
+            return np.zeros((0, 2), dtype=np.int64)
+        e = np.asarray(self._dyn_edges, dtype=np.int64)
+        if self._vfilt is not None:
+            m = self._visible_mask()
+            e = e[m[e[:, 0]] & m[e[:, 1]]]
+        return e
+
+    # -- properties -----------------------------------------------------------------------
+    def new_vertex_property(self, typ):
+        return _PropertyMap(np.zeros(self._nv, dtype=_TYPES[typ]), graph=self)
+
+    def new_edge_property(self, typ):
+        n = self._edges.shape[0] if self._adj_ptr is not None else len(self._dyn_edges)
+        return _PropertyMap(np.zeros(n, dtype=_TYPES[typ]))

@@ -3,21 +3,25 @@ import numpy as np
 
 
 def label_components(g, directed=False):
+    """Components of the VISIBLE sub-graph (vertex / edge filters honoured), numbered in order of their lowest
+    vertex id.  Hidden vertices get label -1 in the underlying array; iterating the returned map yields the
+    labels of the visible vertices only."""
     from scipy.sparse import coo_matrix
     from scipy.sparse.csgraph import connected_components
     from . import _PropertyMap
 
-    n = g.num_vertices()
-    e = g._edges
-    if g._efilt is not None:
-        e = e[g._efilt]
+    n = g._nv
+    e = g._visible_edge_array()
     m = coo_matrix((np.ones(e.shape[0], dtype=np.int8), (e[:, 0], e[:, 1])), shape=(n, n))
     _, lab = connected_components(m, directed=False)
-    # renumber in order of lowest vertex id (graph-tool labels components in discovery order)
-    _, first = np.unique(lab, return_index=True)
-    order = np.argsort(first)
-    remap = np.empty_like(order)
-    remap[order] = np.arange(order.size)
-    lab = remap[lab].astype(np.int32)
-    hist = np.bincount(lab)
-    return _PropertyMap(lab), hist
+    vis = g._visible_mask() if g._vfilt is not None else np.ones(n, dtype=bool)
+    out = np.full(n, -1, dtype=np.int32)
+    if vis.any():
+        lv = lab[vis]
+        _, first, inv = np.unique(lv, return_index=True, return_inverse=True)
+        order = np.argsort(first)                       # labels in order of first (lowest-id) visible vertex
+        rank = np.empty_like(order)
+        rank[order] = np.arange(order.size)
+        out[vis] = rank[inv].astype(np.int32)
+    hist = np.bincount(out[out >= 0]) if (out >= 0).any() else np.zeros(0, dtype=np.int64)
+    return _PropertyMap(out, graph=g), hist

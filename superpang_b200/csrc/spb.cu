@@ -806,17 +806,15 @@ int spb_compact(spb_ctx* c, spb_counts* out) {
   ALLOC(c->verts, u32, totv + 1); ALLOC(c->seqs, u8, tots + 1);
   ALLOC(c->vnbp, u32, (u64)nV + 1); dev_memset(c, c->vnbp, 0xFF, ((u64)nV + 1) * 4);
   SPB_LAUNCH(k_emit_ends, nblk((u64)nN * 32, TPB), TPB, c->stream, t, nN, k, T, c->F, c->R, c->v2pos, c->voff, c->soff, c->verts, c->seqs);
-  u32 *nch, *choff, *nel, *eoff; ALLOC(nch, u32, nD + 1); ALLOC(choff, u32, nD + 1); ALLOC(nel, u32, nD + 1); ALLOC(eoff, u32, nD + 1);
-  SPB_LAUNCH(k_dart_chunks, nblk(nD, TPB), TPB, c->stream, c->plo, c->phi, nD, nch, nel);
-  u64 nchunks = 0, nshort = 0;
+  u32 *nch, *choff; ALLOC(nch, u32, nD + 1); ALLOC(choff, u32, nD + 1);
+  SPB_LAUNCH(k_dart_chunks, nblk(nD, TPB), TPB, c->stream, c->plo, c->phi, nD, nch);
+  u64 nchunks = 0;
   PRIM(prim_scan_u32(c, nch, choff, nD, &nchunks));
-  PRIM(prim_scan_u32(c, nel, eoff, nD, &nshort));
-  if (nshort >= (1ull << 32) || nchunks >= (1ull << 31)) return fail(c, SPB_EINVAL, "input too large for 32-bit dart offsets");
+  if (nchunks >= (1ull << 31)) return fail(c, SPB_EINVAL, "input too large for 32-bit dart offsets");
   SPB_LAUNCH(k_emit_darts, nchunks, 256, c->stream, choff, nD, c->plo, c->phi, c->dart_nbp, acc[cur], k, T, c->F, c->R, c->v2pos, c->voff,
              c->soff, c->verts, c->seqs, c->vnbp);
-  SPB_LAUNCH(k_emit_short, nblk(nshort, 256), 256, c->stream, eoff, nD, nshort, c->plo, c->phi, c->dart_nbp, acc[cur], k, T, c->F, c->R,
-             c->v2pos, c->voff, c->soff, c->verts, c->seqs, c->vnbp);
-  dfree(c, nel); dfree(c, eoff);
+  SPB_LAUNCH(k_emit_short, std::min<u64>(nblk((u64)nD * 32, 256), 148 * 32), 256, c->stream, nD, c->plo, c->phi, c->dart_nbp, acc[cur], k, T,
+             c->F, c->R, c->v2pos, c->voff, c->soff, c->verts, c->seqs, c->vnbp);
   dfree(c, nch); dfree(c, choff); dfree(c, head_nbp); dfree(c, nxt);
   dfree(c, pl_nbr); dfree(c, pr_nbr); dfree(c, pl_side); dfree(c, pr_side);
   for (int i = 0; i < 2; ++i) { dfree(c, ptr[i]); dfree(c, acc[i]); dfree(c, root[i]); dfree(c, mnv[i]); }
@@ -829,7 +827,7 @@ int spb_compact(spb_ctx* c, spb_counts* out) {
     u32 sb = 1; while ((1ull << sb) <= c->n_seq) ++sb;          // keys = (NBP or vertex id) << sb | sequence index
     u32 ob = sb + 1; while (ob < 64 && (1ull << (ob - sb)) <= (u64)nN) ++ob;
     u32 mb = sb + 1; while (mb < 64 && (1ull << (mb - sb)) <= (u64)nV) ++mb;
-    u64 ocap = std::max<u64>(4096, c->n_inst / 16), mcap = std::max<u64>(4096, c->n_inst / 64);
+    u64 ocap = std::max<u64>(4096, c->n_inst / 4), mcap = std::max<u64>(4096, c->n_inst / 32);
     u64 *op = 0, *mp = 0; u64 no = 0, nm = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
       ALLOC(op, u64, ocap + 1); ALLOC(mp, u64, mcap + 1);

@@ -832,48 +832,39 @@ __global__ void k_emit_ends(NbpTab t, u32 nN, u32 k, u64 T, const u32* __restric
 #define SPB_CHUNK 4096
 #define SPB_SHORT_DART 512
 // long darts are cut into chunks (k_emit_darts), short ones are emitted element-parallel (k_emit_short)
-__global__ void k_dart_chunks(const u32* __restrict__ plo, const u32* __restrict__ phi, u32 nD, u32* __restrict__ nch, u32* __restrict__ nel) {
+__global__ void k_dart_chunks(const u32* __restrict__ plo, const u32* __restrict__ phi, u32 nD, u32* __restrict__ nch) {
   u64 d = SPB_GTID();
   if (d >= nD) return;
   u32 len = phi[d >> 1] - plo[d >> 1] + 1;
   bool is_short = len < SPB_SHORT_DART;
   nch[d] = is_short ? 0 : (len + SPB_CHUNK - 1) / SPB_CHUNK;
-  nel[d] = is_short ? len : 0;
 }
-// element e of the concatenated short darts: eoff = exclusive scan of their lengths (long darts count 0)
+// short darts: one warp per dart (grid-stride over all darts, long ones are skipped); the per-dart parameters are
+// loaded once per warp and the lanes write consecutive ranks
 __global__ void SPB_LAUNCH_BOUNDS(256)
-k_emit_short(const u32* __restrict__ eoff, u32 nD, u64 nE, const u32* __restrict__ plo, const u32* __restrict__ phi,
+k_emit_short(u32 nD, const u32* __restrict__ plo, const u32* __restrict__ phi,
              const u32* __restrict__ dart_nbp, const u32* __restrict__ acc, u32 k, u64 T, const u32* __restrict__ F,
              const u32* __restrict__ R, const u32* __restrict__ v2pos, const u64* __restrict__ voff,
              const u64* __restrict__ soff, u32* __restrict__ verts, u8* __restrict__ seq, u32* __restrict__ vnbp) {
-  u64 e0 = (u64)blockIdx.x * blockDim.x, e = e0 + threadIdx.x;
-  // darts touched by this block: [dlo, dhi)
-#ifdef SPB_EMU
-  u32 dlo = upper_bound_u32(eoff, nD, (u32)e0) - 1;
-  u64 elast = e0 + blockDim.x - 1 < nE ? e0 + blockDim.x - 1 : nE - 1;
-  u32 dhi = upper_bound_u32(eoff, nD, (u32)elast);
-#else
-  __shared__ u32 sd[2];
-  if (threadIdx.x == 0) {
-    sd[0] = upper_bound_u32(eoff, nD, (u32)e0) - 1;
-    u64 elast = e0 + blockDim.x - 1 < nE ? e0 + blockDim.x - 1 : nE - 1;
-    sd[1] = upper_bound_u32(eoff, nD, (u32)elast);
+  const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+  const u32 lane = threadIdx.x & 31;
+  for (u64 d = SPB_GTID() >> 5; d < nD; d += nwarps) {
+    u32 P = (u32)(d >> 1); bool up = !(d & 1);
+    u32 lo = plo[P], hi = phi[P], len = hi - lo + 1;
+    if (len >= SPB_SHORT_DART) continue;
+    u32 id = dart_nbp[d], un = dart_nbp[d ^ 1];
+    if (id < un) un = id;
+    u64 r0 = acc[d];
+    u64 vo = voff[id] + r0, so = soff[id] + (k - 1) + r0;
+    u64 src = up ? (u64)v2pos[lo] + k - 1 : T - 1 - (u64)v2pos[hi];
+    const u32* S = up ? F : R;
+    for (u32 t = lane; t < len; t += 32) {
+      u32 v = up ? lo + t : hi - t;
+      verts[vo + t] = v;
+      seq[so + t] = code2ascii(base_at(S, src + t));
+      if (up) vnbp[v] = un;
+    }
   }
-  __syncthreads();
-  u32 dlo = sd[0], dhi = sd[1];
-#endif
-  if (e >= nE) return;
-  u32 d = dlo + upper_bound_u32(eoff + dlo, dhi - dlo, (u32)e) - 1;
-  u32 t = (u32)e - eoff[d];
-  u32 P = d >> 1; bool up = !(d & 1);
-  u32 lo = plo[P], hi = phi[P];
-  u32 id = dart_nbp[d];
-  u32 v = up ? lo + t : hi - t;
-  u64 r = (u64)acc[d] + t;
-  verts[voff[id] + r] = v;
-  u64 src = up ? (u64)v2pos[lo] + k - 1 + t : T - 1 - (u64)v2pos[hi] + t;
-  seq[soff[id] + (k - 1) + r] = code2ascii(base_at(up ? F : R, src));
-  if (up) { u32 un = dart_nbp[d ^ 1]; vnbp[v] = id < un ? id : un; }
 }
 struct ChunkParams { u64 vo, so, src; u32 lo, hi, un, t0, n; u32 up; };
 __device__ __forceinline__ ChunkParams chunk_params(u32 c, const u32* choff, u32 nD, const u32* plo, const u32* phi, const u32* dart_nbp,
@@ -1023,7 +1014,7 @@ __global__ void k_comp_min_init(const u32* __restrict__ init_list, u32 nI, u32* 
   u64 i = SPB_GTID();
   if (i >= nI) return;
   u32 r = uf_find(parent, (u32)i);
-  atomicMin(cmin + r, init_list[i]);
+  if (init_list[i] < cmin[r]) atomicMin(cmin + r, init_list[i]);   // one giant component: do not hammer a single address
 }
 __global__ void k_comp_min_piece(const u32* __restrict__ plo, u32 nP, const u32* __restrict__ dart_nbp, NbpTab t,
                                  const u32* __restrict__ init_list, u32 nI, u32* parent, u32* cmin) {
@@ -1031,7 +1022,7 @@ __global__ void k_comp_min_piece(const u32* __restrict__ plo, u32 nP, const u32*
   if (P >= nP) return;
   u32 a = t.a[dart_nbp[2 * P]];
   u32 r = uf_find(parent, lower_bound_u32(init_list, nI, a));
-  atomicMin(cmin + r, plo[P]);
+  if (plo[P] < cmin[r]) atomicMin(cmin + r, plo[P]);
 }
 __global__ void k_comp_roots(u32* parent, const u32* __restrict__ cmin, u32 nI, u64* __restrict__ rootkeys, u32* nroots) {
   u64 i = SPB_GTID();

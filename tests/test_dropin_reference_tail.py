@@ -1,0 +1,36 @@
+"""CPU tier, build container only: the drop-in claim end to end.  The reference's complete `Assembler.run()`
+(host tail `lib/Assembler.py:365-963`, bubbles off) is executed on top of the B200 path's DBG + NBPs (kernels run by
+the host emulator here) through the in-memory patch of `oracle/dropin.py`, and must produce exactly the final
+contigs of the unmodified reference.  Skipped wherever /root/reference is absent."""
+import os
+
+import pytest
+
+import cases
+import refrun
+from superpang_b200 import _capi
+
+pytestmark = pytest.mark.skipif(not refrun.available(), reason="reference tree not present")
+
+
+@pytest.mark.parametrize("case", cases.crafted_cases(k=31), ids=lambda c: c[0])
+def test_reference_tail_on_b200_head(emu_lib, case, tmp_path):
+    import dropin
+    name, k, recs = case
+    fa = os.path.join(tmp_path, "in.fa")
+    cases.write_fasta(fa, recs)
+    ref = dropin.run_reference_full(fa, k)
+    got = dropin.run_dropin_full(fa, k, _capi.Engine(lib=emu_lib))
+    assert dropin.canonical(ref) == dropin.canonical(got)
+    assert dropin.contigs_digest(ref) == dropin.contigs_digest(got)
+
+
+def test_reference_tail_on_b200_head_synthetic(emu_lib, tmp_path):
+    import dropin
+    from superpang_b200 import synth
+    names, seqs = synth.genome_set(5, 30000, 0.96, seed=77, mode="block")
+    fa = os.path.join(tmp_path, "syn.fa")
+    synth.write_fasta(fa, names, seqs)
+    ref = dropin.run_reference_full(fa, 301)
+    got = dropin.run_dropin_full(fa, 301, _capi.Engine(lib=emu_lib))
+    assert dropin.canonical(ref) == dropin.canonical(got)
