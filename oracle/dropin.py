@@ -34,8 +34,9 @@ import refrun  # noqa: E402
 RUN_ARGS = dict(minlen=0, mincov=0, bubble_identity_threshold=1, genome_assignment_threshold=1)
 
 
-def _patched_class(Assembler):
-    """Subclass of the reference Assembler whose run() takes the NBP collection from the B200 path."""
+def _patched_run(Assembler):
+    """The reference's run() with the NBP-collection block replaced (returned as a plain function; it is bound to an
+    instance of the ORIGINAL class so that the reference's multiprocessing pool can still pickle its classmethods)."""
     import inspect
     import textwrap
     import superpang.lib.Assembler as mod
@@ -49,7 +50,7 @@ def _patched_class(Assembler):
     new_src = "\n".join(lines[:start] + patch + lines[end + 1:])
     ns = dict(vars(mod))
     exec(compile(new_src, "<reference run() with the INTEGRATION.md patch>", "exec"), ns)
-    return type("AssemblerB200", (Assembler,), {"run": ns["run"]})
+    return ns["run"]
 
 
 def contigs_digest(contigs):
@@ -78,7 +79,9 @@ def run_dropin_full(fasta, k, engine, threads=1):
     from graph_tool.all import Graph
     from superpang_b200.assembler import Assembler as B200Assembler
     B = B200Assembler(fasta, k, threads, None, True, 1, engine=engine)
-    A = object.__new__(_patched_class(Assembler))
+    import types
+    A = object.__new__(Assembler)
+    A.run = types.MethodType(_patched_run(Assembler), A)
     A.ksize, A.seqDict, A.ref2name, A.includedSeqs = B.ksize, B.seqDict, B.ref2name, B.includedSeqs
     A.vertex2coords = B.vertex2coords
     A.seqPaths = dict(B.seqPaths)

@@ -282,8 +282,9 @@ static int check_err(spb_ctx* c, const char* where) {
   return 0;
 }
 
-template <int W> static void launch_extract(spb_ctx* c, u64 grid, u64* slots, u64 cap, u32* wbits, u32* dbits) {
-  SPB_LAUNCH(k_extract_insert<W>, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, slots, cap - 1, c->sp, c->obits, wbits, dbits);
+template <int W> static void launch_extract(spb_ctx* c, u64 grid, u64* slots, u64 cap, u32* seenpos, u32* wbits, u32* dbits, u64* arec, u64 nA) {
+  SPB_LAUNCH(k_anchor_insert<W>, nblk(nA, TPB), TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, slots, cap - 1, seenpos, dbits, arec, nA);
+  SPB_LAUNCH(k_extract_insert<W>, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, slots, cap - 1, seenpos, c->obits, wbits, dbits, arec);
 }
 
 // =========================================================================================== C-ABI
@@ -498,7 +499,8 @@ static int dd_scatter(spb_ctx* c, const u32* rep) {
 }
 
 // vertex ids for the positions [lo, hi) + the vertex table (needs the complete fbits bitmap)
-static int dd_ids(spb_ctx* c, u64 lo, u64 hi, const u64* slots, u64 cap = 1) {
+static int dd_ids(spb_ctx* c, u64 lo, u64 hi, const u64* slots, u64 cap = 1, const u32* sp_in = nullptr) {
+  if (!sp_in) sp_in = c->sp;
   const u64 T = c->T;
   u64 nb = c->npos_pad / 256;
   u32 *blkcnt, *blkoff; u8* wpre; ALLOC(blkcnt, u32, nb); ALLOC(blkoff, u32, nb); ALLOC(wpre, u8, nb * 8 + 8);
@@ -509,10 +511,10 @@ static int dd_ids(spb_ctx* c, u64 lo, u64 hi, const u64* slots, u64 cap = 1) {
   ALLOC(c->v2pos, u32, nV + 1); ALLOC(c->vflags, u8, nV + 64);
   dev_memset(c, c->vflags + (nV & ~7ull), 0, 64);
   switch ((2 * c->k + 31) / 32) {
-    case 7:  SPB_LAUNCH(k_assign_ids<7>, gs_grid(T), TPB, c->stream, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags); break;
-    case 19: SPB_LAUNCH(k_assign_ids<19>, gs_grid(T), TPB, c->stream, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags); break;
-    case 32: SPB_LAUNCH(k_assign_ids<32>, gs_grid(T), TPB, c->stream, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags); break;
-    default: SPB_LAUNCH(k_assign_ids<0>, gs_grid(T), TPB, c->stream, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags); break;
+    case 7:  SPB_LAUNCH(k_assign_ids<7>, gs_grid(T), TPB, c->stream, sp_in, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags); break;
+    case 19: SPB_LAUNCH(k_assign_ids<19>, gs_grid(T), TPB, c->stream, sp_in, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags); break;
+    case 32: SPB_LAUNCH(k_assign_ids<32>, gs_grid(T), TPB, c->stream, sp_in, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags); break;
+    default: SPB_LAUNCH(k_assign_ids<0>, gs_grid(T), TPB, c->stream, sp_in, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags); break;
   }
   dfree(c, blkcnt); dfree(c, blkoff); dfree(c, wpre);
   return 0;
@@ -568,20 +570,23 @@ static int dedup_global_table(spb_ctx* c) {
   u32 *wbits, *dbits; ALLOC(wbits, u32, nw32 + 8); ALLOC(dbits, u32, nw32 + 8);
   dev_memset(c, dbits, 0, (nw32 + 8) * 4); dev_memset(c, wbits, 0, (nw32 + 8) * 4);
   u64 grid = c->npos_pad / TPB;
+  u64 nA = c->npos_pad / 32;
+  u32* seenpos; u64* arec; ALLOC(seenpos, u32, c->npos_pad + 8); ALLOC(arec, u64, nA + 8);
   StageTimer tk; tk.start(c);
   switch ((2 * c->k + 31) / 32) {
-    case 7: launch_extract<7>(c, grid, slots, cap, wbits, dbits); break;       // k = 101
-    case 19: launch_extract<19>(c, grid, slots, cap, wbits, dbits); break;     // k = 301
-    case 32: launch_extract<32>(c, grid, slots, cap, wbits, dbits); break;     // k = 501
-    default: launch_extract<0>(c, grid, slots, cap, wbits, dbits); break;
+    case 7: launch_extract<7>(c, grid, slots, cap, seenpos, wbits, dbits, arec, nA); break;       // k = 101
+    case 19: launch_extract<19>(c, grid, slots, cap, seenpos, wbits, dbits, arec, nA); break;     // k = 301
+    case 32: launch_extract<32>(c, grid, slots, cap, seenpos, wbits, dbits, arec, nA); break;     // k = 501
+    default: launch_extract<0>(c, grid, slots, cap, seenpos, wbits, dbits, arec, nA); break;
   }
   { char b2[96]; snprintf(b2, sizeof b2, "\"k_extract_insert_ms\": %.4f, ", tk.stop(c)); c->stats += b2; }
+  dfree(c, arec);
   u64 nb = c->npos_pad / 256;
   SPB_LAUNCH(k_first_bits, nblk(nb, TPB), TPB, c->stream, wbits, dbits, c->fbits, nb);
   dev_memset(c, c->fbits + nw32, 0, 32);
   dfree(c, wbits); dfree(c, dbits);
-  int r = dd_ids(c, 0, T, slots, cap);
-  dfree(c, slots);
+  int r = dd_ids(c, 0, T, slots, cap, seenpos);
+  dfree(c, slots); dfree(c, seenpos);
   return r;
 }
 
@@ -827,7 +832,7 @@ int spb_compact(spb_ctx* c, spb_counts* out) {
     u32 sb = 1; while ((1ull << sb) <= c->n_seq) ++sb;          // keys = (NBP or vertex id) << sb | sequence index
     u32 ob = sb + 1; while (ob < 64 && (1ull << (ob - sb)) <= (u64)nN) ++ob;
     u32 mb = sb + 1; while (mb < 64 && (1ull << (mb - sb)) <= (u64)nV) ++mb;
-    u64 ocap = std::max<u64>(4096, c->n_inst / 4), mcap = std::max<u64>(4096, c->n_inst / 32);
+    u64 ocap = std::max<u64>(4096, c->n_inst / 4), mcap = std::max<u64>(4096, c->n_inst / 4);
     u64 *op = 0, *mp = 0; u64 no = 0, nm = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
       ALLOC(op, u64, ocap + 1); ALLOC(mp, u64, mcap + 1);

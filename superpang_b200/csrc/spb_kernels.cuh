@@ -225,52 +225,107 @@ __global__ void k_valid_bits(const u64* __restrict__ seq_off, u32 n_seq, u64 T, 
 //   dbits[q]  position q was installed earlier and then displaced by a smaller position
 // first appearance  <=>  wbits & ~dbits   (every displacement is observed exactly once through the
 // value atomicMin returns), so no second pass over the table is needed to find the firsts.
+__device__ __forceinline__ bool orient_fwd(const u32* __restrict__ F, const u32* __restrict__ R, u64 T, u32 k, u64 p) {
+  u64 ra = T - p - k;                               // almost always decided by the first limb
+  const u32* x = F + (p >> 4); const u32* y = R + (ra >> 4);
+  u32 lx = __funnelshift_l(__ldg(x + 1), __ldg(x), (u32)(p & 15) * 2), ly = __funnelshift_l(__ldg(y + 1), __ldg(y), (u32)(ra & 15) * 2);
+  return (lx != ly) ? (lx > ly) : (win_cmp(F, p, R, ra, k) >= 0);
+}
+// hash + probe + exact verification + atomicMin; returns won, and for a non-winner the matched (smaller) position
+// and that position's orientation bit
+template <int W> __device__ __forceinline__ bool insert_full(const u32* __restrict__ F, const u32* __restrict__ R, u64 T, u32 k, u64* slots,
+                                                             u64 capmask, u32* dbits, u64 p, bool o, u32* seen, u32* seen_o) {
+  const u32* S = o ? F : R;
+  u64 a = o ? p : T - p - k;
+  u64 h = win_hash<W>(S, a, k);
+  u64 idx = h & capmask, tag = h >> 40;
+  u64 entry = (tag << 40) | (p << 1) | (o ? 1ull : 0ull);
+  for (;;) {
+    u64 cur = atomicCAS(slots + idx, SPB_EMPTY, entry);
+    if (cur == SPB_EMPTY) return true;
+    if ((cur >> 40) == tag) {
+      u64 q = (cur >> 1) & SPB_POSMASK;
+      bool oq = cur & 1;
+      if (q == p || win_cmp(S, a, oq ? F : R, oq ? q : T - q - k, k) == 0) {
+        if (entry < cur) {
+          u64 old = atomicMin(slots + idx, entry);
+          if (old > entry) {                         // we lowered the slot: old's position is no longer the first
+            u64 dq = (old >> 1) & SPB_POSMASK;
+            atomicOr(dbits + (dq >> 5), 1u << (dq & 31));
+            return true;
+          }
+          cur = old;
+        }
+        *seen = (u32)((cur >> 1) & SPB_POSMASK); *seen_o = (u32)(cur & 1);
+        return false;
+      }
+    }
+    idx = (idx + 1) & capmask;
+  }
+}
+__device__ __forceinline__ bool all_valid(const u32* __restrict__ vbits, u64 a, u32 n) {   // n <= 32 consecutive valid starts from a
+  u64 two = (u64)__ldg(vbits + (a >> 5)) | ((u64)__ldg(vbits + (a >> 5) + 1) << 32);
+  u64 m = ((n >= 64 ? ~0ull : ((1ull << n) - 1))) << (a & 31);
+  return (two & m) == m;
+}
+enum { AR_OQ = 1, AR_OP = 2, AR_MATCHED = 4, AR_WON = 8, AR_VALID = 16 };
+
+// Pass 1 ("anchors"): every 32nd position goes through the table.  arec[i] = matched position | flags << 32.
+template <int W> __global__ void SPB_LAUNCH_BOUNDS(256)
+k_anchor_insert(const u32* __restrict__ F, const u32* __restrict__ R, const u32* __restrict__ vbits, u64 T, u32 k,
+                u64* slots, u64 capmask, u32* __restrict__ seenpos, u32* dbits, u64* __restrict__ arec, u64 nA) {
+  u64 i = SPB_GTID();
+  if (i >= nA) return;
+  u64 p = i * 32;
+  u64 rec = 0;
+  if (p < T && get_bit(vbits, p)) {
+    bool o = orient_fwd(F, R, T, k, p);
+    u32 seen = SPB_INVALID, so = 0;
+    bool won = insert_full<W>(F, R, T, k, slots, capmask, dbits, p, o, &seen, &so);
+    seenpos[p] = won ? SPB_INVALID : seen;
+    rec = (u64)(won ? 0u : seen) | ((u64)(AR_VALID | (o ? AR_OP : 0) | (won ? AR_WON : AR_MATCHED) | (so ? AR_OQ : 0)) << 32);
+  }
+  arec[i] = rec;
+}
+
+// Pass 2: all other positions.  If the anchor p0 of the 32-block matched an earlier position q0 (same or opposite
+// strand), position p0 + j is tested against q0 +- j by comparing only the j new bases: equal => its k-mer equals the
+// k-mer at m = q0 +- j (exact, by induction on the shared k-1 bases), no hash, no table access.  In genome sets that
+// share long stretches this removes almost every random HBM access; everything else takes the full path.
+//   wbits[p]  the thread installed its entry (CAS into an empty slot, or an atomicMin that lowered it)
+//   dbits[q]  position q was installed earlier and then displaced by a smaller position
+// first appearance  <=>  wbits & ~dbits; a non-first instance leaves in seenpos[p] a smaller position with the same
+// k-mer (k_assign_ids follows these links to the first appearance).
 template <int W> __global__ void SPB_LAUNCH_BOUNDS(256)
 k_extract_insert(const u32* __restrict__ F, const u32* __restrict__ R, const u32* __restrict__ vbits, u64 T, u32 k,
-                 u64* slots, u64 capmask, u32* __restrict__ slotidx, u32* obits, u32* wbits, u32* dbits) {
+                 u64* slots, u64 capmask, u32* __restrict__ seenpos, u32* obits, u32* wbits, u32* dbits, const u64* __restrict__ arec) {
   u64 p = SPB_GTID();
   bool valid = p < T && get_bit(vbits, p);
   bool o = false, won = false;
-  u32 seen = SPB_INVALID;
   if (valid) {
-    u64 ra = T - p - k;
-    // orientation: almost always decided by the first limb
-    {
-      const u32* x = F + (p >> 4); const u32* y = R + (ra >> 4);
-      u32 lx = __funnelshift_l(__ldg(x + 1), __ldg(x), (u32)(p & 15) * 2), ly = __funnelshift_l(__ldg(y + 1), __ldg(y), (u32)(ra & 15) * 2);
-      o = (lx != ly) ? (lx > ly) : (win_cmp(F, p, R, ra, k) >= 0);
-    }
-    const u32* S = o ? F : R;
-    u64 a = o ? p : ra;
-    u64 h = win_hash<W>(S, a, k);
-    u64 idx = h & capmask, tag = h >> 40;
-    u64 entry = (tag << 40) | (p << 1) | (o ? 1ull : 0ull);
-    for (;;) {
-      u64 cur = atomicCAS(slots + idx, SPB_EMPTY, entry);
-      if (cur == SPB_EMPTY) { won = true; break; }
-      if ((cur >> 40) == tag) {
-        u64 q = (cur >> 1) & SPB_POSMASK;
-        bool oq = cur & 1;
-        const u32* S2 = oq ? F : R;
-        u64 b = oq ? q : T - q - k;
-        if (q == p || win_cmp(S, a, S2, b, k) == 0) {
-          if (entry < cur) {
-            u64 old = atomicMin(slots + idx, entry);
-            if (old > entry) {                       // we lowered the slot: old's position is no longer the first
-              won = true;
-              u64 dq = (old >> 1) & SPB_POSMASK;
-              atomicOr(dbits + (dq >> 5), 1u << (dq & 31));
-            } else q = (old >> 1) & SPB_POSMASK;
+    const u32 j = (u32)(p & 31);
+    const u64 rec = __ldg(arec + (p >> 5));
+    const u32 fl = (u32)(rec >> 32);
+    o = j ? orient_fwd(F, R, T, k, p) : (fl & AR_OP) != 0;
+    if (j == 0) won = (fl & AR_WON) != 0;            // the anchor itself was handled by pass 1
+    else {
+      bool ext = false;
+      u32 seen = SPB_INVALID, so = 0;
+      if ((fl & AR_VALID) && (fl & AR_MATCHED)) {
+        const u64 p0 = p - j, q0 = (u32)rec;
+        const u32 vm = j == 31 ? 0xFFFFFFFFu : ((1u << (j + 1)) - 1);
+        if ((__ldg(vbits + (p >> 5)) & vm) == vm) {                      // p0 .. p are k-mer starts of one sequence
+          bool opposite = ((fl & AR_OQ) != 0) != ((fl & AR_OP) != 0);
+          if (!opposite) {
+            if (all_valid(vbits, q0, j + 1) && win_cmp(F, p0 + k, F, q0 + k, j) == 0) { ext = true; seen = (u32)(q0 + j); }
+          } else if (q0 >= j) {
+            if (all_valid(vbits, q0 - j, j + 1) && win_cmp(F, p0 + k, R, T - q0, j) == 0) { ext = true; seen = (u32)(q0 - j); }
           }
-          seen = (u32)q;
-          break;
         }
       }
-      idx = (idx + 1) & capmask;
+      if (!ext) won = insert_full<W>(F, R, T, k, slots, capmask, dbits, p, o, &seen, &so);
+      seenpos[p] = won ? SPB_INVALID : seen;
     }
-    // an instance that did not install its own position remembers the (then) first position it matched; that is
-    // its representative unless that position was displaced later (checked against the final bitmap in k_assign_ids)
-    slotidx[p] = won ? SPB_INVALID : seen;
   }
   store_bit(obits, p, o);
   store_bit(wbits, p, won);
@@ -456,7 +511,7 @@ template <int W> __device__ __forceinline__ u32 lookup_rep(const u32* __restrict
 // matched during the insert (global-table path; exact unless that position was displaced later -> table lookup)
 // or its exact representative (staged / multi-GPU path, slots == nullptr).  On exit sp[p] = vertex id.
 template <int W> __global__ void
-k_assign_ids(u32* __restrict__ sp, const u32* __restrict__ vbits, u64 T, u64 lo, u64 hi, const u32* __restrict__ fbits,
+k_assign_ids(const u32* sp_in, u32* sp, const u32* __restrict__ vbits, u64 T, u64 lo, u64 hi, const u32* __restrict__ fbits,
              const u32* __restrict__ blkoff, const u8* __restrict__ wpre, const u64* __restrict__ slots, u64 capmask, const u32* __restrict__ F,
              const u32* __restrict__ R, u32 k, u32* __restrict__ v2pos, u8* __restrict__ vflags) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
@@ -467,8 +522,15 @@ k_assign_ids(u32* __restrict__ sp, const u32* __restrict__ vbits, u64 T, u64 lo,
     if (!first && !mine) continue;
     u32 r = (u32)p;
     if (!first) {
-      r = sp[p];
-      if (slots && (r == SPB_INVALID || !get_bit(fbits, r))) r = lookup_rep<W>(F, R, T, k, slots, capmask, p);
+      // sp_in[p] = a smaller position with the same k-mer (global-table path: follow the links down to a first
+      // appearance; a displaced winner on the way ends in an exact table lookup) or the exact representative (staged /
+      // multi-GPU path, slots == nullptr: the loop exits at once)
+      r = sp_in[p];
+      for (u32 hop = 0; slots; ++hop) {
+        if (r == SPB_INVALID || hop > 256) { r = lookup_rep<W>(F, R, T, k, slots, capmask, p); break; }
+        if (get_bit(fbits, r)) break;
+        r = sp_in[r];
+      }
     }
     u32 vid = rank_first(fbits, blkoff, wpre, r);
     if (mine) sp[p] = vid;
