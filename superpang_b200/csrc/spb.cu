@@ -282,9 +282,22 @@ static int check_err(spb_ctx* c, const char* where) {
   return 0;
 }
 
-template <int W> static void launch_extract(spb_ctx* c, u64 grid, u64* slots, u64 cap, u32* seenpos, u32* wbits, u32* dbits, u64* arec, u64 nA) {
-  SPB_LAUNCH(k_anchor_insert<W>, nblk(nA, TPB), TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, slots, cap - 1, seenpos, dbits, arec, nA);
-  SPB_LAUNCH(k_extract_insert<W>, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, slots, cap - 1, seenpos, c->obits, wbits, dbits, arec);
+// one range of positions through the dedup table; anchored = pass 1 (every 32nd position) + pass 2 (extension test)
+template <int W> static void launch_extract(spb_ctx* c, u64 lo, u64 hi, u64* slots, u64 cap, u32* seenpos, u32* wbits, u32* dbits, u64* arec,
+                                            u64* ext_count) {
+  if (hi <= lo) return;
+  if (arec) SPB_LAUNCH(k_anchor_insert<W>, nblk(nblk(hi - lo, 32), TPB), TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, slots, cap - 1, seenpos,
+                       dbits, arec, lo, hi);
+  SPB_LAUNCH(k_extract_insert<W>, nblk(hi - lo, TPB), TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, slots, cap - 1, seenpos, c->obits, wbits,
+             dbits, (const u64*)arec, lo, hi, ext_count);
+}
+static void launch_extract_k(spb_ctx* c, u64 lo, u64 hi, u64* slots, u64 cap, u32* seenpos, u32* wbits, u32* dbits, u64* arec, u64* ext_count) {
+  switch ((2 * c->k + 31) / 32) {
+    case 7: launch_extract<7>(c, lo, hi, slots, cap, seenpos, wbits, dbits, arec, ext_count); break;       // k = 101
+    case 19: launch_extract<19>(c, lo, hi, slots, cap, seenpos, wbits, dbits, arec, ext_count); break;     // k = 301
+    case 32: launch_extract<32>(c, lo, hi, slots, cap, seenpos, wbits, dbits, arec, ext_count); break;     // k = 501
+    default: launch_extract<0>(c, lo, hi, slots, cap, seenpos, wbits, dbits, arec, ext_count); break;
+  }
 }
 
 // =========================================================================================== C-ABI
@@ -569,18 +582,31 @@ static int dedup_global_table(spb_ctx* c) {
   u64 nw32 = c->npos_pad / 32;
   u32 *wbits, *dbits; ALLOC(wbits, u32, nw32 + 8); ALLOC(dbits, u32, nw32 + 8);
   dev_memset(c, dbits, 0, (nw32 + 8) * 4); dev_memset(c, wbits, 0, (nw32 + 8) * 4);
-  u64 grid = c->npos_pad / TPB;
-  u64 nA = c->npos_pad / 32;
-  u32* seenpos; u64* arec; ALLOC(seenpos, u32, c->npos_pad + 8); ALLOC(arec, u64, nA + 8);
+  // Positions go through the table in chunks, in order.  Chunk 0 is plain.  From chunk 1 on, the "anchor + extend"
+  // scheme is tried: if the second chunk extends well (genome sets that share long stretches: the realistic case), all
+  // remaining chunks use it, each seeing the complete table of the chunks before it; otherwise (nearly all k-mers
+  // unique) the rest is one plain launch.  The result is the same either way.
+  u64 CH = 1ull << 22;
+  if (const char* e = getenv("SPB_CHUNK_BITS")) { int b = atoi(e); if (b >= 8 && b <= 32) CH = 1ull << b; }   // tests: tiny chunks
+  const u64 P = c->npos_pad;
+  u64 nA = P / 32;
+  u32* seenpos; u64 *arec, *extc; ALLOC(seenpos, u32, P + 8); ALLOC(arec, u64, nA + 8); ALLOC(extc, u64, 2);
+  dev_memset(c, extc, 0, 16);
   StageTimer tk; tk.start(c);
-  switch ((2 * c->k + 31) / 32) {
-    case 7: launch_extract<7>(c, grid, slots, cap, seenpos, wbits, dbits, arec, nA); break;       // k = 101
-    case 19: launch_extract<19>(c, grid, slots, cap, seenpos, wbits, dbits, arec, nA); break;     // k = 301
-    case 32: launch_extract<32>(c, grid, slots, cap, seenpos, wbits, dbits, arec, nA); break;     // k = 501
-    default: launch_extract<0>(c, grid, slots, cap, seenpos, wbits, dbits, arec, nA); break;
+  int anchored = 0;
+  if (const char* e = getenv("SPB_ANCHOR")) anchored = atoi(e) ? 2 : -1;      // 1 = force on, 0 = force off (A/B measurements, tests)
+  u64 done = std::min(P, CH);
+  launch_extract_k(c, 0, done, slots, cap, seenpos, wbits, dbits, nullptr, nullptr);
+  if (done < P && anchored >= 0) {
+    u64 hi = std::min(P, done + CH);
+    launch_extract_k(c, done, hi, slots, cap, seenpos, wbits, dbits, arec, extc);
+    if (anchored == 0) anchored = (double)dread(c, extc) >= 0.25 * (double)(hi - done) ? 1 : -1;
+    done = hi;
   }
-  { char b2[96]; snprintf(b2, sizeof b2, "\"k_extract_insert_ms\": %.4f, ", tk.stop(c)); c->stats += b2; }
-  dfree(c, arec);
+  if (anchored > 0) for (; done < P; done += CH) launch_extract_k(c, done, std::min(P, done + CH), slots, cap, seenpos, wbits, dbits, arec, nullptr);
+  else launch_extract_k(c, done, P, slots, cap, seenpos, wbits, dbits, nullptr, nullptr);
+  { char b2[128]; snprintf(b2, sizeof b2, "\"k_extract_insert_ms\": %.4f, \"anchored\": %d, ", tk.stop(c), anchored > 0 ? 1 : 0); c->stats += b2; }
+  dfree(c, arec); dfree(c, extc);
   u64 nb = c->npos_pad / 256;
   SPB_LAUNCH(k_first_bits, nblk(nb, TPB), TPB, c->stream, wbits, dbits, c->fbits, nb);
   dev_memset(c, c->fbits + nw32, 0, 32);

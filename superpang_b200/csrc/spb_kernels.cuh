@@ -273,10 +273,9 @@ enum { AR_OQ = 1, AR_OP = 2, AR_MATCHED = 4, AR_WON = 8, AR_VALID = 16 };
 // Pass 1 ("anchors"): every 32nd position goes through the table.  arec[i] = matched position | flags << 32.
 template <int W> __global__ void SPB_LAUNCH_BOUNDS(256)
 k_anchor_insert(const u32* __restrict__ F, const u32* __restrict__ R, const u32* __restrict__ vbits, u64 T, u32 k,
-                u64* slots, u64 capmask, u32* __restrict__ seenpos, u32* dbits, u64* __restrict__ arec, u64 nA) {
-  u64 i = SPB_GTID();
-  if (i >= nA) return;
-  u64 p = i * 32;
+                u64* slots, u64 capmask, u32* __restrict__ seenpos, u32* dbits, u64* __restrict__ arec, u64 pos_lo, u64 pos_hi) {
+  u64 p = pos_lo + SPB_GTID() * 32;                  // pos_lo is a multiple of 32
+  if (p >= pos_hi) return;
   u64 rec = 0;
   if (p < T && get_bit(vbits, p)) {
     bool o = orient_fwd(F, R, T, k, p);
@@ -285,7 +284,7 @@ k_anchor_insert(const u32* __restrict__ F, const u32* __restrict__ R, const u32*
     seenpos[p] = won ? SPB_INVALID : seen;
     rec = (u64)(won ? 0u : seen) | ((u64)(AR_VALID | (o ? AR_OP : 0) | (won ? AR_WON : AR_MATCHED) | (so ? AR_OQ : 0)) << 32);
   }
-  arec[i] = rec;
+  arec[p >> 5] = rec;
 }
 
 // Pass 2: all other positions.  If the anchor p0 of the 32-block matched an earlier position q0 (same or opposite
@@ -298,37 +297,51 @@ k_anchor_insert(const u32* __restrict__ F, const u32* __restrict__ R, const u32*
 // k-mer (k_assign_ids follows these links to the first appearance).
 template <int W> __global__ void SPB_LAUNCH_BOUNDS(256)
 k_extract_insert(const u32* __restrict__ F, const u32* __restrict__ R, const u32* __restrict__ vbits, u64 T, u32 k,
-                 u64* slots, u64 capmask, u32* __restrict__ seenpos, u32* obits, u32* wbits, u32* dbits, const u64* __restrict__ arec) {
-  u64 p = SPB_GTID();
-  bool valid = p < T && get_bit(vbits, p);
-  bool o = false, won = false;
+                 u64* slots, u64 capmask, u32* __restrict__ seenpos, u32* obits, u32* wbits, u32* dbits,
+                 const u64* __restrict__ arec, u64 pos_lo, u64 pos_hi, u64* ext_count) {
+  u64 p = pos_lo + SPB_GTID();                       // pos_lo and the grid are multiples of 256
+  bool valid = p < pos_hi && p < T && get_bit(vbits, p);
+  bool o = false, won = false, ext = false;
   if (valid) {
     const u32 j = (u32)(p & 31);
-    const u64 rec = __ldg(arec + (p >> 5));
-    const u32 fl = (u32)(rec >> 32);
-    o = j ? orient_fwd(F, R, T, k, p) : (fl & AR_OP) != 0;
-    if (j == 0) won = (fl & AR_WON) != 0;            // the anchor itself was handled by pass 1
-    else {
-      bool ext = false;
-      u32 seen = SPB_INVALID, so = 0;
-      if ((fl & AR_VALID) && (fl & AR_MATCHED)) {
-        const u64 p0 = p - j, q0 = (u32)rec;
-        const u32 vm = j == 31 ? 0xFFFFFFFFu : ((1u << (j + 1)) - 1);
-        if ((__ldg(vbits + (p >> 5)) & vm) == vm) {                      // p0 .. p are k-mer starts of one sequence
-          bool opposite = ((fl & AR_OQ) != 0) != ((fl & AR_OP) != 0);
-          if (!opposite) {
-            if (all_valid(vbits, q0, j + 1) && win_cmp(F, p0 + k, F, q0 + k, j) == 0) { ext = true; seen = (u32)(q0 + j); }
-          } else if (q0 >= j) {
-            if (all_valid(vbits, q0 - j, j + 1) && win_cmp(F, p0 + k, R, T - q0, j) == 0) { ext = true; seen = (u32)(q0 - j); }
+    u32 seen = SPB_INVALID, so = 0;
+    if (!arec) {                                     // plain mode: every position takes the full path
+      o = orient_fwd(F, R, T, k, p);
+      won = insert_full<W>(F, R, T, k, slots, capmask, dbits, p, o, &seen, &so);
+      seenpos[p] = won ? SPB_INVALID : seen;
+    } else {
+      const u64 rec = __ldg(arec + (p >> 5));
+      const u32 fl = (u32)(rec >> 32);
+      o = j ? orient_fwd(F, R, T, k, p) : (fl & AR_OP) != 0;
+      if (j == 0) won = (fl & AR_WON) != 0;          // the anchor itself was handled by k_anchor_insert
+      else {
+        if ((fl & AR_VALID) && (fl & AR_MATCHED)) {
+          const u64 p0 = p - j, q0 = (u32)rec;
+          const u32 vm = j == 31 ? 0xFFFFFFFFu : ((1u << (j + 1)) - 1);
+          if ((__ldg(vbits + (p >> 5)) & vm) == vm) {                    // p0 .. p are k-mer starts of one sequence
+            bool opposite = ((fl & AR_OQ) != 0) != ((fl & AR_OP) != 0);
+            if (!opposite) {
+              if (all_valid(vbits, q0, j + 1) && win_cmp(F, p0 + k, F, q0 + k, j) == 0) { ext = true; seen = (u32)(q0 + j); }
+            } else if (q0 >= j) {
+              if (all_valid(vbits, q0 - j, j + 1) && win_cmp(F, p0 + k, R, T - q0, j) == 0) { ext = true; seen = (u32)(q0 - j); }
+            }
           }
         }
+        if (!ext) won = insert_full<W>(F, R, T, k, slots, capmask, dbits, p, o, &seen, &so);
+        seenpos[p] = won ? SPB_INVALID : seen;
       }
-      if (!ext) won = insert_full<W>(F, R, T, k, slots, capmask, dbits, p, o, &seen, &so);
-      seenpos[p] = won ? SPB_INVALID : seen;
     }
   }
   store_bit(obits, p, o);
   store_bit(wbits, p, won);
+  if (ext_count) {
+#ifdef SPB_EMU
+    if (ext) atomicAdd(ext_count, 1ull);
+#else
+    u32 b = __ballot_sync(0xffffffffu, ext);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(ext_count, (u64)__popc(b));
+#endif
+  }
 }
 
 // ------------------------------------------------------------------------------------ staged dedup

@@ -95,6 +95,10 @@ VARIANTS = [
     {"SPB_EMU_ORDER": "shuffle"},
     {"SPB_DEDUP": "staged", "SPB_BUCKET_BITS": "3"},                # partitioned dedup, 8 buckets
     {"SPB_DEDUP": "staged", "SPB_BUCKET_BITS": "5", "SPB_EMU_ORDER": "reverse"},
+    {"SPB_ANCHOR": "1", "SPB_CHUNK_BITS": "8"},                      # anchor + extend forced, 256-position chunks
+    {"SPB_ANCHOR": "1", "SPB_CHUNK_BITS": "9", "SPB_EMU_ORDER": "reverse"},
+    {"SPB_CHUNK_BITS": "10"},                                        # adaptive decision after the second chunk
+    {"SPB_ANCHOR": "0", "SPB_CHUNK_BITS": "8", "SPB_EMU_ORDER": "shuffle"},
 ]
 
 
