@@ -130,6 +130,25 @@ def test_gpu_properties_at_scale(mode):
     assert int(oidx.max()) < len(seqs)
 
 
+@pytest.mark.parametrize("env", [
+    {"SPB_ANCHOR": "1", "SPB_CHUNK_BITS": "12"},       # anchor + extend forced with 4096-position chunks
+    {"SPB_ANCHOR": "0", "SPB_CHUNK_BITS": "12"},
+    {"SPB_DEDUP": "staged", "SPB_BUCKET_BITS": "4"},   # partitioned dedup, 16 buckets
+], ids=lambda e: ",".join(f"{k[4:].lower()}={v}" for k, v in e.items()))
+def test_gpu_dedup_variants(monkeypatch, env):
+    """Every dedup strategy must give the reference's result (they differ only in how the table is reached)."""
+    for k_, v in env.items():
+        monkeypatch.setenv(k_, v)
+    for case in helpers.load_json("synthetic.json")["cases"]:
+        sd = helpers.synth_seqdict(case["n_genomes"], case["length"], case["ani"], case["seed"], case["mode"])
+        helpers.assert_summary(digests.summarize(run_gpu(sd, case["k"]).to_result()), case["summary"])
+    want = helpers.load_json("real_slice.json")
+    helpers.assert_summary(digests.summarize(run_gpu(helpers.real_slice_records(), want["k"]).to_result()), want["summary"])
+    fa = os.path.join(helpers.DATA, "A.fa")
+    if os.path.exists(fa):
+        helpers.assert_summary(digests.summarize(Assembler(fa, 301, device=0).to_result()), helpers.load_json("kat_A.json"))
+
+
 def test_gpu_multi_rank_parity():
     """>= 2 GPUs: hash-partitioned DBG build over NCCL, every rank must reproduce the reference goldens."""
     import subprocess
