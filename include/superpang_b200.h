@@ -131,6 +131,11 @@ int spb_get_nbp_seqs(spb_ctx* ctx, uint64_t* off, uint8_t* ascii);
 /* NBP origins: off uint64[n_nbp + 1], seq_idx uint32[n_origin_pairs] (sorted per NBP; indices into
  * the loaded sequence list; the caller cuts names at `_Nsplit_`, `lib/Assembler.py:946`). */
 int spb_get_nbp_origins(spb_ctx* ctx, uint64_t* off, uint32_t* seq_idx);
+/* NBP graph: successors of every raw NBP = the NBPs whose first k bases equal its last k bases
+ * (`lib/Assembler.py:365-384`), as CSR (off uint64[n_nbp + 1], succ uint32[*n_edges]), and rev uint32[n_nbp] = the id
+ * of the reverse-orientation partner of every NBP (the pairs of `lib/Assembler.py:405-455`).  Call once with NULL
+ * buffers to learn *n_edges. */
+int spb_get_nbp_graph(spb_ctx* ctx, uint64_t* n_edges, uint64_t* off, uint32_t* succ, uint32_t* rev);
 /* Current counters (n_seq_intervals is filled by the first spb_get_seq_intervals call, which may
  * be made with NULL buffers just to size them). */
 int spb_get_counts(spb_ctx* ctx, spb_counts* out);

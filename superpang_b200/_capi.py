@@ -23,7 +23,7 @@ EXPORTS = (
     "spb_get_vertex2coords", "spb_get_edges", "spb_get_instance_vertices", "spb_get_seqlimits",
     "spb_get_seq_intervals", "spb_get_components", "spb_get_nbps", "spb_get_nbp_seqs",
     "spb_get_nbp_origins", "spb_get_counts", "spb_get_stage_stats", "spb_build_kind", "spb_launch_count",
-    "spb_mg_slice", "spb_mg_records", "spb_mg_dedup", "spb_mg_scatter", "spb_mg_buffers", "spb_mg_ids", "spb_mg_graph",
+    "spb_get_nbp_graph", "spb_mg_slice", "spb_mg_records", "spb_mg_dedup", "spb_mg_scatter", "spb_mg_buffers", "spb_mg_ids", "spb_mg_graph",
 )
 
 
@@ -82,6 +82,7 @@ def _declare(lib):
     lib.spb_get_stage_stats.argtypes = [vp, C.c_char_p, C.c_uint64]
     lib.spb_build_kind.restype = C.c_char_p
     lib.spb_launch_count.restype = C.c_uint64
+    lib.spb_get_nbp_graph.argtypes = [vp, C.POINTER(C.c_uint64), u64p, u32p, u32p]
     lib.spb_mg_slice.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint64)]
     lib.spb_mg_records.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     lib.spb_mg_dedup.argtypes = [vp, u64p, u32p, C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32, C.c_uint32, u32p]
@@ -320,6 +321,17 @@ class Engine:
         seq = np.empty(self.counts.nbp_bases, dtype=np.uint8)
         self._ck(self.lib.spb_get_nbp_seqs(self.h, off.ctypes.data, seq.ctypes.data))
         return off, seq
+
+    def nbp_graph(self):
+        """(off, succ, rev): successors CSR of the NBP graph and the reverse-orientation partner of every raw NBP."""
+        ne = C.c_uint64()
+        self._ck(self.lib.spb_get_nbp_graph(self.h, C.byref(ne), None, None, None))
+        n = self.counts.n_nbp
+        off = np.empty(n + 1, dtype=np.uint64)
+        succ = np.empty(ne.value, dtype=np.uint32)
+        rev = np.empty(n, dtype=np.uint32)
+        self._ck(self.lib.spb_get_nbp_graph(self.h, C.byref(ne), off.ctypes.data, succ.ctypes.data, rev.ctypes.data))
+        return off, succ, rev
 
     def nbp_origins(self):
         off = np.empty(self.counts.n_nbp + 1, dtype=np.uint64)

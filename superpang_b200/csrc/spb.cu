@@ -43,6 +43,7 @@ struct spb_ctx {
   u64 *voff = 0, *soff = 0, *ooff = 0;
   u32 *verts = 0, *origins = 0; u8* seqs = 0;
   u32* iv = 0; u64* iv_off = 0;
+  u64* g_off = 0; u32 *g_succ = 0, *g_rev = 0; u64 g_edges = 0;      // NBP graph (lazy)
   // staged dedup state (records sent by this rank)
   u64 *dd_keys = 0, *dd_bstart = 0; u32* dd_pos = 0; u64 dd_n = 0, dd_lo = 0, dd_hi = 0; u32 dd_bb = 0; bool dd_fbits_ready = false;
   std::vector<u64> dd_bstart_h;
@@ -1012,6 +1013,37 @@ uint64_t spb_launch_count(void) { return g_spb_launches; }
 int spb_get_counts(spb_ctx* c, spb_counts* out) {
   if (!c || !out) return SPB_EINVAL;
   *out = c->cnt;
+  return SPB_OK;
+}
+static int build_nbp_graph(spb_ctx* c) {
+  if (c->g_off) return 0;
+  const u32 nN = c->nN;
+  u64 *key, *key2; u32 *id, *id2;
+  ALLOC(key, u64, nN + 1); ALLOC(key2, u64, nN + 1); ALLOC(id, u32, nN + 1); ALLOC(id2, u32, nN + 1);
+  SPB_LAUNCH(k_nbpg_keys, nblk(nN, TPB), TPB, c->stream, c->nt, nN, key, id);
+  PRIM(prim_partition_u64_u32(c, key, id, key2, id2, nN, 0, 34));
+  dfree(c, key2); dfree(c, id2);
+  u64* cnt; ALLOC(cnt, u64, nN + 1); ALLOC(c->g_off, u64, nN + 2); ALLOC(c->g_rev, u32, nN + 1);
+  SPB_LAUNCH(k_nbpg_join, nblk(nN, TPB), TPB, c->stream, c->nt, nN, key, id, c->dart_nbp, (const u64*)nullptr, cnt, (u32*)nullptr, c->g_rev);
+  u64 tot = 0;
+  PRIM(prim_scan_u64(c, cnt, c->g_off, nN, &tot));
+  dev_copy(c, c->g_off + nN, &tot, 8); dev_sync(c);
+  ALLOC(c->g_succ, u32, tot + 1);
+  SPB_LAUNCH(k_nbpg_join, nblk(nN, TPB), TPB, c->stream, c->nt, nN, key, id, c->dart_nbp, c->g_off, cnt, c->g_succ, (u32*)nullptr);
+  dfree(c, key); dfree(c, id); dfree(c, cnt);
+  c->g_edges = tot;
+  dev_sync(c);
+  return check_err(c, "nbp_graph");
+}
+int spb_get_nbp_graph(spb_ctx* c, uint64_t* n_edges, uint64_t* off, uint32_t* succ, uint32_t* rev) {
+  NEED(3);
+  int r = build_nbp_graph(c);
+  if (r) return r;
+  if (n_edges) *n_edges = c->g_edges;
+  if (off) dev_copy(c, off, c->g_off, 8ull * (c->nN + 1));
+  if (succ) dev_copy(c, succ, c->g_succ, 4ull * c->g_edges);
+  if (rev) dev_copy(c, rev, c->g_rev, 4ull * c->nN);
+  dev_sync(c);
   return SPB_OK;
 }
 int spb_get_stage_stats(spb_ctx* c, char* buf, uint64_t cap) {

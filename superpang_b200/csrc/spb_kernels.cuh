@@ -1124,6 +1124,40 @@ __global__ void k_vertex_comp(const u8* __restrict__ vflags, u32 nV, const u32* 
   else out[v] = nbp_comp[vnbp[v]];
 }
 
+// ------------------------------------------------------------------------------------ NBP graph
+// The reference links NBP1 -> NBP2 when the last k bases of NBP1 equal the first k bases of NBP2
+// (lib/Assembler.py:365-384).  A k-mer string is a (vertex, orientation) pair (odd k: no palindromes), so the join
+// key is (first vertex, read forward?) for the start of an NBP and (last vertex, read forward?) for its end.
+__device__ __forceinline__ u64 nbp_start_key(const NbpTab& t, u32 i) { return ((u64)t.a[i] << 1) | (t.aside[i] == SIDE_R ? 1u : 0u); }
+__device__ __forceinline__ u64 nbp_end_key(const NbpTab& t, u32 i) {
+  if (t.cyc[i]) return nbp_start_key(t, i);                      // a broken cycle ends with its first vertex again
+  return ((u64)t.b[i] << 1) | (t.bside[i] == SIDE_L ? 1u : 0u);
+}
+__global__ void k_nbpg_keys(NbpTab t, u32 nN, u64* __restrict__ key, u32* __restrict__ id) {
+  u64 i = SPB_GTID();
+  if (i >= nN) return;
+  key[i] = nbp_start_key(t, (u32)i); id[i] = (u32)i;
+}
+// successors of every NBP (count pass when succ == nullptr) and the id of its reverse-orientation partner
+__global__ void k_nbpg_join(NbpTab t, u32 nN, const u64* __restrict__ skey, const u32* __restrict__ sid, const u32* __restrict__ dart_nbp,
+                            const u64* __restrict__ off, u64* __restrict__ cnt, u32* __restrict__ succ, u32* __restrict__ rev) {
+  u64 i = SPB_GTID();
+  if (i >= nN) return;
+  u64 ek = nbp_end_key(t, (u32)i);
+  u32 lo = lower_bound_key(skey, nN, ek), hi = lower_bound_key(skey, nN, ek + 1);
+  if (!succ) { cnt[i] = hi - lo; }
+  else { u64 o = off[i]; for (u32 j = lo; j < hi; ++j) succ[o + (j - lo)] = sid[j]; }
+  if (rev && !succ) {
+    u32 r = SPB_INVALID;
+    if (t.head[i] != SPB_TERM) r = dart_nbp[t.last[i] ^ 1];       // the reversed last dart heads the partner
+    else {                                                          // 2-vertex NBP (a, b): its partner is (b, a)
+      u32 l2 = lower_bound_key(skey, nN, (u64)t.b[i] << 1), h2 = lower_bound_key(skey, nN, ((u64)t.b[i] + 1) << 1);
+      for (u32 j = l2; j < h2; ++j) { u32 c = sid[j]; if (t.head[c] == SPB_TERM && t.b[c] == t.a[i]) { r = c; break; } }
+    }
+    rev[i] = r;
+  }
+}
+
 // ------------------------------------------------------------------------------------ getters
 __global__ void k_coords(const u32* __restrict__ v2pos, u32 nV, const u64* __restrict__ seq_off, u32 n_seq, u32* __restrict__ out) {
   u64 v = SPB_GTID();
