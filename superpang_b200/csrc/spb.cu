@@ -864,7 +864,7 @@ int spb_compact(spb_ctx* c, spb_counts* out) {
     for (int attempt = 0; attempt < 2; ++attempt) {
       ALLOC(op, u64, ocap + 1); ALLOC(mp, u64, mcap + 1);
       dev_memset(c, counts, 0, 32); dev_memset(c, has01, 0, 2ull * c->n_seq + 8);
-      SPB_LAUNCH(k_origin_pairs, gs_grid(T), TPB, c->stream, c->sp, T, c->vnbp, c->vflags, c->seq_off, c->n_seq, op, counts, ocap, mp,
+      SPB_LAUNCH(k_origin_pairs, gs_grid(T), TPB, c->stream, c->sp, T, c->fbits, c->vnbp, c->vflags, c->seq_off, c->n_seq, op, counts, ocap, mp,
                  counts + 1, mcap, has01, sb);
       SPB_LAUNCH(k_origin_quirk, nblk(c->n_seq, TPB), TPB, c->stream, has01, c->n_seq, c->vnbp, c->vflags, op, counts, ocap, mp, counts + 1,
                  mcap, sb);

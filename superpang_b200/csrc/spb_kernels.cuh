@@ -527,11 +527,24 @@ template <int W> __global__ void
 k_assign_ids(const u32* sp_in, u32* sp, const u32* __restrict__ vbits, u64 T, u64 lo, u64 hi, const u32* __restrict__ fbits,
              const u32* __restrict__ blkoff, const u8* __restrict__ wpre, const u64* __restrict__ slots, u64 capmask, const u32* __restrict__ F,
              const u32* __restrict__ R, u32 k, u32* __restrict__ v2pos, u8* __restrict__ vflags) {
-  const u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 p = SPB_GTID(); p < T; p += stride) {    // grid-stride: a capped grid avoids scheduling millions of tiny blocks
+  // one warp per 32 positions (one word of the bitmaps), grid-stride
+  const u64 nwords = (T + 31) / 32;
+  const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+  const u32 lane = threadIdx.x & 31;
+  for (u64 wd = SPB_GTID() >> 5; wd < nwords; wd += nwarps) {
+    const u64 p = wd * 32 + lane;
+    const u32 f = __ldg(fbits + wd);
+    if (f == 0xFFFFFFFFu) {                          // 32 first appearances in a row: ids are consecutive
+      u32 vid = __ldg(blkoff + (wd >> 3)) + __ldg(wpre + wd) + lane;
+      if (p >= lo && p < hi) sp[p] = vid;
+      v2pos[vid] = (u32)p;
+      vflags[vid] = (lane < 31 || (__ldg(fbits + wd + 1) & 1u)) ? VF_R : 0;
+      continue;
+    }
+    if (p >= T) continue;
     bool mine = p >= lo && p < hi;               // multi-GPU: sp is filled for the local slice only, the vertex table everywhere
     if (!get_bit(vbits, p)) { if (mine) sp[p] = SPB_INVALID; continue; }
-    bool first = get_bit(fbits, p);
+    bool first = (f >> lane) & 1u;
     if (!first && !mine) continue;
     u32 r = (u32)p;
     if (!first) {
@@ -991,13 +1004,24 @@ k_emit_darts(const u32* __restrict__ choff, u32 nD, const u32* __restrict__ plo,
 
 // K13: origins.  (undirected NBP, sequence) pairs where the NBP changes along a sequence; (init vertex,
 // sequence) membership pairs for the inits of 2-vertex NBPs (reference lib/Assembler.py:1212-1262).
-__global__ void k_origin_pairs(const u32* __restrict__ sp, u64 T, const u32* __restrict__ vnbp, const u8* __restrict__ vflags,
+__global__ void k_origin_pairs(const u32* __restrict__ sp, u64 T, const u32* __restrict__ fbits, const u32* __restrict__ vnbp, const u8* __restrict__ vflags,
                                const u64* __restrict__ seq_off, u32 n_seq, u64* __restrict__ opairs, u64* ocount, u64 ocap,
                                u64* __restrict__ mpairs, u64* mcount, u64 mcap, u8* __restrict__ has01, u32 sb) {
-  const u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 p = SPB_GTID(); p < T; p += stride) {
+  // one warp per 32 positions, grid-stride.  Where p-1 and p are consecutive first appearances (vertices v-1, v joined by
+  // an implicit edge) the NBP changes at p only if v starts a piece, so one flag byte decides and the two vnbp gathers
+  // are skipped.
+  const u64 nwords = (T + 31) / 32;
+  const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+  const u32 lane = threadIdx.x & 31;
+  for (u64 wd = SPB_GTID() >> 5; wd < nwords; wd += nwarps) {
+    const u64 p = wd * 32 + lane;
+    if (p >= T) continue;
+    const u32 f = __ldg(fbits + wd);
+    const u32 fprev = wd ? (__ldg(fbits + wd - 1) >> 31) : 0u;
+    const bool pair_first = ((f & ((f << 1) | fprev)) >> lane) & 1u;       // p-1 and p both first appearances
     u32 v = sp[p];
     if (v == SPB_INVALID) continue;
+    if (pair_first && v > 1 && !(vflags[v] & (VF_INIT | VF_PSTART))) continue;
     u32 c = vnbp[v];
     bool in2 = (vflags[v] & VF_IN2) != 0;
     u32 prev = SPB_INVALID;
