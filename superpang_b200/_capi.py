@@ -121,6 +121,24 @@ def _wrap(ptr, n, dtype, cuda, device):
     return torch.from_numpy(np.frombuffer(buf, dtype=npdt))
 
 
+def _exchange(out, inp, out_splits, in_splits, rank, group):
+    """Variable-size all-to-all.  The chunk a rank keeps for itself is a plain device copy; the other chunks go to
+    NCCL as grouped send/recv on views of the caller's buffers (no staging copies).  Backends without the list form
+    (gloo, CPU tests) use all_to_all_single on the whole buffers."""
+    import torch
+    import torch.distributed as dist
+    if out.is_cuda:
+        outs = list(torch.split(out, out_splits))
+        ins = list(torch.split(inp, in_splits))
+        if in_splits[rank]:
+            outs[rank].copy_(ins[rank])
+        empty_o, empty_i = out[:0], inp[:0]
+        outs[rank], ins[rank] = empty_o, empty_i
+        dist.all_to_all(outs, ins, group=group)
+    else:
+        dist.all_to_all_single(out, inp, out_splits, in_splits, group=group)
+
+
 def _all_gather_inplace(full, rank, world, group):
     """all-gather where every rank already holds its own chunk of `full` at the right offset."""
     import torch.distributed as dist
@@ -228,8 +246,8 @@ class Engine:
         recv = [int(x) for x in rc_t.tolist()]
         rkeys = torch.empty(sum(recv), dtype=torch.int64, device=dev)
         rpos = torch.empty(sum(recv), dtype=torch.int32, device=dev)
-        dist.all_to_all_single(rkeys, keys, recv, send, group=group)
-        dist.all_to_all_single(rpos, pos, recv, send, group=group)
+        _exchange(rkeys, keys, recv, send, r, group)
+        _exchange(rpos, pos, recv, send, r, group)
         rep = torch.empty(sum(recv), dtype=torch.int32, device=dev)
         chunk = (C.c_uint64 * G)(*recv)
         mark("exchange_records")
@@ -237,7 +255,7 @@ class Engine:
         self._ck(self.lib.spb_mg_dedup(self.h, rkeys.data_ptr(), rpos.data_ptr(), chunk, G, G, r, rep.data_ptr()))
         mark("owner_dedup")
         back = torch.empty(sum(send), dtype=torch.int32, device=dev)
-        dist.all_to_all_single(back, rep, send, recv, group=group)
+        _exchange(back, rep, send, recv, r, group)
         mark("exchange_reps")
         sync()
         self._ck(self.lib.spb_mg_scatter(self.h, back.data_ptr()))

@@ -122,7 +122,6 @@ template <class T> static T dread(spb_ctx* c, const T* p) {
   dev_copy(c, c->pinned, p, sizeof(T)); dev_sync(c);
   T v; memcpy(&v, c->pinned, sizeof(T)); return v;
 }
-static void dread_n(spb_ctx* c, void* dst, const void* src, u64 bytes) { dev_copy(c, c->pinned, src, bytes); dev_sync(c); memcpy(dst, c->pinned, bytes); }
 
 static inline u64 nblk(u64 n, u32 t) { return (n + t - 1) / t; }
 // grid of a grid-stride kernel: enough resident blocks for every SM, never millions of tiny ones

@@ -45,7 +45,6 @@ __device__ __forceinline__ u64 list_reserve(u64* counter, u32 n) {
   // warp-aggregated: one atomic per warp
   u32 active = __activemask();
   u32 lane = threadIdx.x & 31;
-  u32 incl = n;
   // inclusive prefix over active lanes (n is 0..3: do it with ballots per bit)
   u32 b0 = __ballot_sync(active, n & 1), b1 = __ballot_sync(active, n & 2);
   u32 below = (1u << lane) - 1;
@@ -55,7 +54,6 @@ __device__ __forceinline__ u64 list_reserve(u64* counter, u32 n) {
   u64 base = 0;
   if ((int)lane == leader) base = atomicAdd(counter, (u64)total);
   base = __shfl_sync(active, base, leader);
-  (void)incl;
   return base + before;
 #endif
 }
