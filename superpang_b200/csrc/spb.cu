@@ -512,7 +512,7 @@ static int dd_scatter(spb_ctx* c, const u32* rep) {
 }
 
 // vertex ids for the positions [lo, hi) + the vertex table (needs the complete fbits bitmap)
-static int dd_ids(spb_ctx* c, u64 lo, u64 hi, const u64* slots, u64 cap = 1, const u32* sp_in = nullptr) {
+static int dd_ids(spb_ctx* c, u64 lo, u64 hi, const u64* slots, u64 cap = 1, const u32* sp_in = nullptr, int follow = 0) {
   if (!sp_in) sp_in = c->sp;
   const u64 T = c->T;
   u64 nb = c->npos_pad / 256;
@@ -524,10 +524,10 @@ static int dd_ids(spb_ctx* c, u64 lo, u64 hi, const u64* slots, u64 cap = 1, con
   ALLOC(c->v2pos, u32, nV + 1); ALLOC(c->vflags, u8, nV + 64);
   dev_memset(c, c->vflags + (nV & ~7ull), 0, 64);
   switch ((2 * c->k + 31) / 32) {
-    case 7:  SPB_LAUNCH(k_assign_ids<7>, gs_grid(T), TPB, c->stream, sp_in, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags); break;
-    case 19: SPB_LAUNCH(k_assign_ids<19>, gs_grid(T), TPB, c->stream, sp_in, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags); break;
-    case 32: SPB_LAUNCH(k_assign_ids<32>, gs_grid(T), TPB, c->stream, sp_in, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags); break;
-    default: SPB_LAUNCH(k_assign_ids<0>, gs_grid(T), TPB, c->stream, sp_in, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags); break;
+    case 7:  SPB_LAUNCH(k_assign_ids<7>, gs_grid(T), TPB, c->stream, sp_in, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags, follow, c->errflag); break;
+    case 19: SPB_LAUNCH(k_assign_ids<19>, gs_grid(T), TPB, c->stream, sp_in, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags, follow, c->errflag); break;
+    case 32: SPB_LAUNCH(k_assign_ids<32>, gs_grid(T), TPB, c->stream, sp_in, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags, follow, c->errflag); break;
+    default: SPB_LAUNCH(k_assign_ids<0>, gs_grid(T), TPB, c->stream, sp_in, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags, follow, c->errflag); break;
   }
   dfree(c, blkcnt); dfree(c, blkoff); dfree(c, wpre);
   return 0;
@@ -571,8 +571,51 @@ static int dd_graph(spb_ctx* c) {
   return 0;
 }
 
+// Partitioned dedup, "links" form (single GPU, mostly-unique inputs): records -> 2^bb buckets -> one L2-resident scratch
+// table per bucket; only duplicates / displaced positions write anything (a link to a smaller equal position).
+static int dedup_staged_links(spb_ctx* c) {
+  const u64 T = c->T, P = c->npos_pad;
+  u32 bb = 0; while (bb < 8 && (c->n_inst >> bb) > 2200000ull) ++bb;       // <= 256 buckets: one radix pass
+  if (const char* e = getenv("SPB_BUCKET_BITS")) bb = (u32)atoi(e);
+  StageTimer tk; char b2[128];
+  tk.start(c);
+  PRIM(dd_records(c, 0, T, bb));
+  snprintf(b2, sizeof b2, "\"records_partition_ms\": %.4f, ", tk.stop(c)); c->stats += b2;
+  tk.start(c);
+  const u32 B = 1u << bb;
+  u64 nmax = 0;
+  for (u32 b = 0; b < B; ++b) nmax = std::max(nmax, c->dd_bstart_h[b + 1] - c->dd_bstart_h[b]);
+  u64 cap = 1024; while (cap < 2 * nmax) cap <<= 1;
+  c->cnt.table_slots = cap;
+  u64* scratch[2]; ALLOC(scratch[0], u64, cap); ALLOC(scratch[1], u64, cap);
+  dev_memset(c, scratch[0], 0xFF, cap * 8);
+  if (B == 1) dev_memset(c, scratch[1], 0xFF, 8);
+  u32 *seenpos, *dupbits; ALLOC(seenpos, u32, P + 8); ALLOC(dupbits, u32, P / 32 + 8);
+  dev_memset(c, dupbits, 0, (P / 32 + 8) * 4);
+  u32 step = 0;
+  for (u32 b = 0; b < B; ++b) {
+    u64 lo = c->dd_bstart_h[b], n = c->dd_bstart_h[b + 1] - lo;
+    if (n == 0) continue;
+    u64* cur = scratch[step & 1]; u64* other = scratch[(step & 1) ^ 1];
+    u64 g = std::max<u64>(nblk(n, TPB), B > 1 ? std::min<u64>(nblk(cap, TPB), 148 * 8) : 0);
+    SPB_LAUNCH(k_bkt_insert_links, g, TPB, c->stream, c->dd_keys, c->dd_pos, lo, n, c->F, c->R, T, c->k, cur, cap - 1, seenpos, dupbits, other,
+               B > 1 ? cap : 0);
+    ++step;
+  }
+  dfree(c, scratch[0]); dfree(c, scratch[1]);
+  dfree(c, c->dd_keys); dfree(c, c->dd_pos); dfree(c, c->dd_bstart);
+  snprintf(b2, sizeof b2, "\"bucket_dedup_ms\": %.4f, ", tk.stop(c)); c->stats += b2;
+  u64 nb = P / 256, nw32 = P / 32;
+  SPB_LAUNCH(k_first_bits, nblk(nb, TPB), TPB, c->stream, c->vbits, dupbits, c->fbits, nb);     // first = valid and not linked
+  dev_memset(c, c->fbits + nw32, 0, 32);
+  dfree(c, dupbits);
+  int r = dd_ids(c, 0, T, nullptr, 1, seenpos, 1);
+  dfree(c, seenpos);
+  return r;
+}
+
 // the older single-table dedup (two random HBM accesses per instance); kept selectable for A/B measurements
-static int dedup_global_table(spb_ctx* c) {
+static int dedup_global_table(spb_ctx* c, bool allow_switch) {
   const u64 T = c->T;
   int r0 = alloc_position_state(c); if (r0) return r0;
   u64 cap = 1024; while (cap < 2 * c->n_inst) cap <<= 1;
@@ -602,6 +645,11 @@ static int dedup_global_table(spb_ctx* c) {
     launch_extract_k(c, done, hi, slots, cap, seenpos, wbits, dbits, arec, extc);
     if (anchored == 0) anchored = (double)dread(c, extc) >= 0.25 * (double)(hi - done) ? 1 : -1;
     done = hi;
+    if (anchored < 0 && allow_switch && c->n_inst >= (64ull << 20)) {
+      // mostly unique k-mers and a table far beyond L2: the partitioned "links" dedup is faster; start over with it
+      dfree(c, arec); dfree(c, extc); dfree(c, seenpos); dfree(c, slots); dfree(c, wbits); dfree(c, dbits);
+      return 1;
+    }
   }
   if (anchored > 0) for (; done < P; done += CH) launch_extract_k(c, done, std::min(P, done + CH), slots, cap, seenpos, wbits, dbits, arec, nullptr);
   else launch_extract_k(c, done, P, slots, cap, seenpos, wbits, dbits, nullptr, nullptr);
@@ -627,10 +675,19 @@ int spb_build_dbg(spb_ctx* c, spb_counts* out) {
   // Default: single global table (two random HBM accesses per instance).  SPB_DEDUP=staged selects the partitioned
   // path (records -> buckets -> L2 scratch tables -> scatter back); measured slower on one GPU in round 1
   // (profiles/README.md), its stages are what the multi-GPU exchange is built from.
-  const char* mode = getenv("SPB_DEDUP");
-  if (!(mode && !strcmp(mode, "staged"))) {
+  const char* mode = getenv("SPB_DEDUP");          // global | links | staged  (default: adaptive global -> links)
+  if (mode && !strcmp(mode, "links")) {
     tm.start(c);
-    PRIM(dedup_global_table(c));                     // also reports k_extract_insert_ms (the kernel alone)
+    PRIM(dedup_staged_links(c));
+    snprintf(buf, sizeof buf, "\"dedup_links_ms\": %.4f", tm.stop(c)); c->stats += buf;
+  } else if (!(mode && !strcmp(mode, "staged"))) {
+    tm.start(c);
+    int rc = dedup_global_table(c, !mode);            // also reports k_extract_insert_ms (the kernel alone)
+    if (rc == 1) {
+      c->stats = "{\"switched_to_links\": 1, ";
+      rc = dedup_staged_links(c);
+    }
+    if (rc) return rc;
     snprintf(buf, sizeof buf, "\"dedup_global_ms\": %.4f", tm.stop(c)); c->stats += buf;
   } else {
     // ---- S1: records + partition

@@ -463,6 +463,53 @@ __global__ void k_bkt_final(BktView v, u64 n_b, const u32* __restrict__ F, const
   u64 stride = (u64)gridDim.x * blockDim.x;
   for (u64 j = t; j < clear_n; j += stride) clear[j] = SPB_EMPTY;
 }
+// "links" variant of the per-bucket dedup: nothing is written per record.  Only the exceptions leave a trace, as a
+// link "position -> smaller position with the same k-mer": (a) an instance that found its k-mer already installed,
+// (b) an installed position that a smaller one displaced (written by the displacer).  Every position without a
+// link is a first appearance, and every chain of links ends at one (k_assign_ids follows them).  With mostly unique
+// k-mers almost no scattered write happens; the table of the bucket lives in L2.  The same launch clears the other
+// scratch table for the next bucket.
+__global__ void SPB_LAUNCH_BOUNDS(256)
+k_bkt_insert_links(const u64* __restrict__ keys, const u32* __restrict__ pos, u64 lo, u64 n, const u32* __restrict__ F,
+                   const u32* __restrict__ R, u64 T, u32 k, u64* scratch, u64 capmask, u32* seenpos, u32* dupbits,
+                   u64* clear, u64 clear_n) {
+  u64 t = SPB_GTID();
+  if (t < n) {
+    u64 key = keys[lo + t];
+    if (key != ~0ull) {
+      u64 p = pos[lo + t];
+      bool o = key & 1;
+      u64 tag = (key >> 1) & 0x7FFFFFull, idx = (key >> 24) & capmask;
+      u64 entry = (tag << 40) | (p << 1) | (o ? 1ull : 0ull);
+      const u32* S = o ? F : R;
+      u64 a = o ? p : T - p - k;
+      for (;;) {
+        u64 cur = atomicCAS(scratch + idx, SPB_EMPTY, entry);
+        if (cur == SPB_EMPTY) break;
+        if ((cur >> 40) == tag) {
+          u64 q = (cur >> 1) & SPB_POSMASK;
+          bool oq = cur & 1;
+          if (q == p || win_cmp(S, a, oq ? F : R, oq ? q : T - q - k, k) == 0) {
+            u64 from = p, to = q;                                   // default: we link to the installed position
+            if (entry < cur) {
+              u64 old = atomicMin(scratch + idx, entry);
+              u64 oq2 = (old >> 1) & SPB_POSMASK;
+              if (old > entry) { from = oq2; to = p; }               // we displaced oq2: it links to us
+              else to = oq2;
+            }
+            seenpos[from] = (u32)to;
+            atomicOr(dupbits + (from >> 5), 1u << (from & 31));
+            break;
+          }
+        }
+        idx = (idx + 1) & capmask;
+      }
+    }
+  }
+  u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 j = t; j < clear_n; j += stride) clear[j] = SPB_EMPTY;
+}
+
 // S3: bucket-interleaved scatter back to position order
 __global__ void k_unpartition(const u32* __restrict__ pos, const u32* __restrict__ rep, const u64* __restrict__ bstart, u32 B, u32* __restrict__ sp, u32* fbits) {
   u64 g = SPB_GTID();
@@ -524,7 +571,7 @@ template <int W> __device__ __forceinline__ u32 lookup_rep(const u32* __restrict
 template <int W> __global__ void
 k_assign_ids(const u32* sp_in, u32* sp, const u32* __restrict__ vbits, u64 T, u64 lo, u64 hi, const u32* __restrict__ fbits,
              const u32* __restrict__ blkoff, const u8* __restrict__ wpre, const u64* __restrict__ slots, u64 capmask, const u32* __restrict__ F,
-             const u32* __restrict__ R, u32 k, u32* __restrict__ v2pos, u8* __restrict__ vflags) {
+             const u32* __restrict__ R, u32 k, u32* __restrict__ v2pos, u8* __restrict__ vflags, int follow, u32* err) {
   // one warp per 32 positions (one word of the bitmaps), grid-stride
   const u64 nwords = (T + 31) / 32;
   const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
@@ -547,13 +594,21 @@ k_assign_ids(const u32* sp_in, u32* sp, const u32* __restrict__ vbits, u64 T, u6
     u32 r = (u32)p;
     if (!first) {
       // sp_in[p] = a smaller position with the same k-mer (global-table path: follow the links down to a first
-      // appearance; a displaced winner on the way ends in an exact table lookup) or the exact representative (staged /
-      // multi-GPU path, slots == nullptr: the loop exits at once)
+      // appearance; a displaced winner on the way ends in an exact table lookup), a pure link (links path: follow) or
+      // the exact representative (multi-GPU path)
       r = sp_in[p];
-      for (u32 hop = 0; slots; ++hop) {
-        if (r == SPB_INVALID || hop > 256) { r = lookup_rep<W>(F, R, T, k, slots, capmask, p); break; }
-        if (get_bit(fbits, r)) break;
-        r = sp_in[r];
+      if (slots) {
+        for (u32 hop = 0;; ++hop) {
+          if (r == SPB_INVALID || hop > 256) { r = lookup_rep<W>(F, R, T, k, slots, capmask, p); break; }
+          if (get_bit(fbits, r)) break;
+          r = sp_in[r];
+        }
+      } else if (follow) {                           // links without a table: chains strictly descend and end at a first appearance
+        while (!get_bit(fbits, r)) {
+          u32 nx = sp_in[r];
+          if (nx >= r) { atomicOr(err, (u32)ERR_OVERFLOW); break; }
+          r = nx;
+        }
       }
     }
     u32 vid = rank_first(fbits, blkoff, wpre, r);

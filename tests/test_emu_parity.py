@@ -99,6 +99,9 @@ VARIANTS = [
     {"SPB_ANCHOR": "1", "SPB_CHUNK_BITS": "9", "SPB_EMU_ORDER": "reverse"},
     {"SPB_CHUNK_BITS": "10"},                                        # adaptive decision after the second chunk
     {"SPB_ANCHOR": "0", "SPB_CHUNK_BITS": "8", "SPB_EMU_ORDER": "shuffle"},
+    {"SPB_DEDUP": "links", "SPB_BUCKET_BITS": "3"},                  # partitioned dedup, exceptions as links
+    {"SPB_DEDUP": "links", "SPB_BUCKET_BITS": "0", "SPB_EMU_ORDER": "reverse"},   # displacement chains
+    {"SPB_DEDUP": "links", "SPB_BUCKET_BITS": "5", "SPB_EMU_ORDER": "shuffle"},
 ]
 
 

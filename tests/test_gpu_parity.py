@@ -134,6 +134,7 @@ def test_gpu_properties_at_scale(mode):
     {"SPB_ANCHOR": "1", "SPB_CHUNK_BITS": "12"},       # anchor + extend forced with 4096-position chunks
     {"SPB_ANCHOR": "0", "SPB_CHUNK_BITS": "12"},
     {"SPB_DEDUP": "staged", "SPB_BUCKET_BITS": "4"},   # partitioned dedup, 16 buckets
+    {"SPB_DEDUP": "links", "SPB_BUCKET_BITS": "4"},    # partitioned dedup, exceptions as links
 ], ids=lambda e: ",".join(f"{k[4:].lower()}={v}" for k, v in e.items()))
 def test_gpu_dedup_variants(monkeypatch, env):
     """Every dedup strategy must give the reference's result (they differ only in how the table is reached)."""
