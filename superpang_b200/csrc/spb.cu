@@ -579,12 +579,46 @@ static int dedup_staged_links(spb_ctx* c) {
   if (const char* e = getenv("SPB_BUCKET_BITS")) bb = (u32)atoi(e);
   StageTimer tk; char b2[128];
   tk.start(c);
-  PRIM(dd_records(c, 0, T, bb));
+  const u32 B = 1u << bb;
+  std::vector<u64> blo(B), bn(B);
+  bool fused = !getenv("SPB_PARTITION_CUB") && bb <= 8;      // the fused kernel keeps a 256-entry histogram in shared memory
+  if (fused) {
+    // ---- fused hash + single-pass partition into fixed-capacity bucket regions
+    int r0 = alloc_position_state(c); if (r0) return r0;
+    u64 bcap = (c->n_inst / B) + (c->n_inst / B) / 16 + 8192;
+    bcap = (bcap + 255) & ~255ull;
+    u64* keys; u32 *pos, *cursor; ALLOC(keys, u64, B * bcap); ALLOC(pos, u32, B * bcap); ALLOC(cursor, u32, 256 + 8);
+    dev_memset(c, cursor, 0, (256 + 8) * 4);
+    u64 tiles = nblk(P, 256 * SPB_PT);
+    switch ((2 * c->k + 31) / 32) {
+      case 7:  SPB_LAUNCH_PHASED(k_partition_records<7>, 4, tiles, TPB, c->stream, c->F, c->R, c->vbits, T, c->k, bb, keys, pos, bcap, cursor, c->obits, c->errflag); break;
+      case 19: SPB_LAUNCH_PHASED(k_partition_records<19>, 4, tiles, TPB, c->stream, c->F, c->R, c->vbits, T, c->k, bb, keys, pos, bcap, cursor, c->obits, c->errflag); break;
+      case 32: SPB_LAUNCH_PHASED(k_partition_records<32>, 4, tiles, TPB, c->stream, c->F, c->R, c->vbits, T, c->k, bb, keys, pos, bcap, cursor, c->obits, c->errflag); break;
+      default: SPB_LAUNCH_PHASED(k_partition_records<0>, 4, tiles, TPB, c->stream, c->F, c->R, c->vbits, T, c->k, bb, keys, pos, bcap, cursor, c->obits, c->errflag); break;
+    }
+    std::vector<u32> cnt_h(B);
+    dev_copy(c, c->pinned, cursor, B * 4ull); dev_sync(c);
+    memcpy(cnt_h.data(), c->pinned, B * 4ull);
+    u32 e = dread(c, c->errflag);
+    dfree(c, cursor);
+    if (e & ERR_OVERFLOW) {                          // skewed hashes (masses of identical k-mers): exact two-pass partition instead
+      dev_memset(c, c->errflag, 0, 4);
+      dfree(c, keys); dfree(c, pos);
+      fused = false;
+    } else {
+      for (u32 b = 0; b < B; ++b) { blo[b] = (u64)b * bcap; bn[b] = cnt_h[b]; }
+      c->dd_keys = keys; c->dd_pos = pos;
+    }
+  }
+  if (!fused) {
+    PRIM(dd_records(c, 0, T, bb));
+    for (u32 b = 0; b < B; ++b) { blo[b] = c->dd_bstart_h[b]; bn[b] = c->dd_bstart_h[b + 1] - blo[b]; }
+    dfree(c, c->dd_bstart);
+  }
   snprintf(b2, sizeof b2, "\"records_partition_ms\": %.4f, ", tk.stop(c)); c->stats += b2;
   tk.start(c);
-  const u32 B = 1u << bb;
   u64 nmax = 0;
-  for (u32 b = 0; b < B; ++b) nmax = std::max(nmax, c->dd_bstart_h[b + 1] - c->dd_bstart_h[b]);
+  for (u32 b = 0; b < B; ++b) nmax = std::max(nmax, bn[b]);
   u64 cap = 1024; while (cap < 2 * nmax) cap <<= 1;
   c->cnt.table_slots = cap;
   u64* scratch[2]; ALLOC(scratch[0], u64, cap); ALLOC(scratch[1], u64, cap);
@@ -594,7 +628,7 @@ static int dedup_staged_links(spb_ctx* c) {
   dev_memset(c, dupbits, 0, (P / 32 + 8) * 4);
   u32 step = 0;
   for (u32 b = 0; b < B; ++b) {
-    u64 lo = c->dd_bstart_h[b], n = c->dd_bstart_h[b + 1] - lo;
+    u64 lo = blo[b], n = bn[b];
     if (n == 0) continue;
     u64* cur = scratch[step & 1]; u64* other = scratch[(step & 1) ^ 1];
     u64 g = std::max<u64>(nblk(n, TPB), B > 1 ? std::min<u64>(nblk(cap, TPB), 148 * 8) : 0);
@@ -603,7 +637,7 @@ static int dedup_staged_links(spb_ctx* c) {
     ++step;
   }
   dfree(c, scratch[0]); dfree(c, scratch[1]);
-  dfree(c, c->dd_keys); dfree(c, c->dd_pos); dfree(c, c->dd_bstart);
+  dfree(c, c->dd_keys); dfree(c, c->dd_pos);
   snprintf(b2, sizeof b2, "\"bucket_dedup_ms\": %.4f, ", tk.stop(c)); c->stats += b2;
   u64 nb = P / 256, nw32 = P / 32;
   SPB_LAUNCH(k_first_bits, nblk(nb, TPB), TPB, c->stream, c->vbits, dupbits, c->fbits, nb);     // first = valid and not linked

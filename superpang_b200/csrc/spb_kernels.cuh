@@ -372,6 +372,58 @@ k_make_records(const u32* __restrict__ F, const u32* __restrict__ R, const u32* 
   store_bit(obits, p, o);
 }
 
+// Single-pass radix partition fused with the record generation (replaces k_make_records + a library radix pass on the
+// single-GPU links path).  A block handles a tile of 2048 positions: hashes go to shared memory with a per-bucket
+// histogram; one atomicAdd per (block, bucket) on the global bucket cursors reserves the output run; the records
+// are then written into their runs.  Buckets are fixed-capacity regions (hashes are uniform; an overflow is flagged
+// and the caller falls back to the exact two-pass partition).
+#define SPB_PT 8
+template <int W> __global__ void SPB_LAUNCH_BOUNDS(256)
+k_partition_records(const u32* __restrict__ F, const u32* __restrict__ R, const u32* __restrict__ vbits, u64 T, u32 k, u32 bb,
+                    u64* __restrict__ keys, u32* __restrict__ pos, u64 bucket_cap, u32* cursor, u32* obits, u32* err) {
+  SPB_SHARED u64 skey[256 * SPB_PT];
+  SPB_SHARED u32 hist[256], base[256];
+  const u32 B = 1u << bb;
+  const u64 tile = (u64)blockIdx.x * (256 * SPB_PT);
+  SPB_PHASE_BEGIN(0)
+    hist[threadIdx.x] = 0;
+  SPB_PHASE_END
+  SPB_PHASE_BEGIN(1)
+    for (u32 j = 0; j < SPB_PT; ++j) {
+      u64 p = tile + j * 256 + threadIdx.x;
+      bool valid = p < T && get_bit(vbits, p);
+      bool o = false;
+      u64 key = ~0ull;
+      if (valid) {
+        o = orient_fwd(F, R, T, k, p);
+        u64 h = win_hash<W>(o ? F : R, o ? p : T - p - k, k);
+        key = (h & ~1ull) | (o ? 1ull : 0ull);
+        if (key == ~0ull) key ^= 2ull;
+        atomicAdd(&hist[bb ? (u32)(key >> (64 - bb)) : 0u], 1u);
+      }
+      skey[j * 256 + threadIdx.x] = key;
+      store_bit(obits, p, o);
+    }
+  SPB_PHASE_END
+  SPB_PHASE_BEGIN(2)
+    if (threadIdx.x < B) {
+      u32 cnt = hist[threadIdx.x];
+      base[threadIdx.x] = cnt ? atomicAdd(cursor + threadIdx.x, cnt) : 0u;
+      hist[threadIdx.x] = 0;
+    }
+  SPB_PHASE_END
+  SPB_PHASE_BEGIN(3)
+    for (u32 j = 0; j < SPB_PT; ++j) {
+      u64 key = skey[j * 256 + threadIdx.x];
+      if (key == ~0ull) continue;
+      u32 b = bb ? (u32)(key >> (64 - bb)) : 0u;
+      u64 idx = (u64)base[b] + atomicAdd(&hist[b], 1u);
+      if (idx < bucket_cap) { keys[(u64)b * bucket_cap + idx] = key; pos[(u64)b * bucket_cap + idx] = (u32)(tile + j * 256 + threadIdx.x); }
+      else atomicOr(err, (u32)ERR_OVERFLOW);
+    }
+  SPB_PHASE_END
+}
+
 // sub[r * (B + 1) + b] = first record of chunk r whose bucket (top `bb` bits of the key) is >= b_lo + b
 __global__ void k_bucket_bounds(const u64* __restrict__ keys, const u64* __restrict__ chunk_off, u32 nchunks, u32 bb, u32 b_lo, u32 B,
                                 u64* __restrict__ sub) {
@@ -661,7 +713,9 @@ __global__ void k_unique_heads(const u64* __restrict__ keys, const u8* __restric
   if (i >= n) return;
   bool h = (i == 0) || keys[i] != keys[i - 1];
   head[i] = h ? 1u : 0u;
-  if (!h && pay && pay[i] != pay[i - 1]) atomicOr(err, (u32)ERR_DEGENERATE);
+  // the same edge reached with different attachment sides is orientation-ambiguous (the reference asserts when it walks
+  // there); self-loops are exempt: their sides are never used (lib/Assembler.py:1013, :334)
+  if (!h && pay && pay[i] != pay[i - 1] && (u32)(keys[i] >> 32) != (u32)keys[i]) atomicOr(err, (u32)ERR_DEGENERATE);
 }
 __global__ void k_unique_scatter(const u64* __restrict__ keys, const u8* __restrict__ pay, u64 n, const u32* __restrict__ head,
                                  const u32* __restrict__ pos, u64* __restrict__ okeys, u8* __restrict__ opay) {

@@ -47,6 +47,27 @@ template <class F> static inline void spb_emu_launch(size_t nb, unsigned nt, F f
 }
 #define SPB_LAUNCH(K, NB, NT, STREAM, ...) \
   do { if ((NB) > 0) { ++g_spb_launches; spb_emu_launch((size_t)(NB), (unsigned)(NT), [&]() { K(__VA_ARGS__); }); } } while (0)
+// Block-cooperative kernels are written as phases separated by block barriers; anything that crosses a barrier lives
+// in SPB_SHARED memory.  The emulator runs every phase for all threads of a block before the next phase starts.
+static int spb_emu_phase = 0;
+#define SPB_SHARED static
+#define SPB_PHASE_BEGIN(n) if (spb_emu_phase == (n)) {
+#define SPB_PHASE_END }
+template <class F> static inline void spb_emu_launch_phased(int nph, size_t nb, unsigned nt, F f) {
+  gridDim.x = (unsigned)nb; blockDim.x = nt;
+  const char* ord = getenv("SPB_EMU_ORDER");
+  int mode = !ord ? 0 : (ord[0] == 'r' ? 1 : (ord[0] == 's' ? 2 : 0));
+  for (size_t i = 0; i < nb; ++i) {
+    blockIdx.x = (unsigned)(mode == 1 ? nb - 1 - i : i);
+    for (int ph = 0; ph < nph; ++ph) {
+      spb_emu_phase = ph;
+      for (unsigned j = 0; j < nt; ++j) { threadIdx.x = mode == 0 ? j : mode == 1 ? nt - 1 - j : (unsigned)((j * 167u + 13u) % nt); f(); }
+    }
+  }
+  spb_emu_phase = 0;
+}
+#define SPB_LAUNCH_PHASED(K, NPH, NB, NT, STREAM, ...) \
+  do { if ((NB) > 0) { ++g_spb_launches; spb_emu_launch_phased((NPH), (size_t)(NB), (unsigned)(NT), [&]() { K(__VA_ARGS__); }); } } while (0)
 static inline u64 atomicCAS(u64* a, u64 cmp, u64 val) { u64 o = *a; if (o == cmp) *a = val; return o; }
 static inline u32 atomicCAS(u32* a, u32 cmp, u32 val) { u32 o = *a; if (o == cmp) *a = val; return o; }
 static inline u64 atomicMin(u64* a, u64 v) { u64 o = *a; if (v < o) *a = v; return o; }
@@ -69,6 +90,10 @@ template <class T> static inline T __ldcg(const T* p) { return *p; }
 typedef cudaStream_t spb_stream_t;
 #define SPB_LAUNCH(K, NB, NT, STREAM, ...) \
   do { if ((NB) > 0) { ++g_spb_launches; K<<<(unsigned)(NB), (unsigned)(NT), 0, (STREAM)>>>(__VA_ARGS__); } } while (0)
+#define SPB_SHARED __shared__
+#define SPB_PHASE_BEGIN(n) { if ((n) > 0) __syncthreads();
+#define SPB_PHASE_END }
+#define SPB_LAUNCH_PHASED(K, NPH, NB, NT, STREAM, ...) SPB_LAUNCH(K, NB, NT, STREAM, __VA_ARGS__)
 #endif
 
 // global linear thread id (64-bit)

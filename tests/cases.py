@@ -46,6 +46,9 @@ def crafted_cases(k=31, seed=3):
         ("tips", [("a", s), ("b", s[:200] + _rnd(rng, 60)), ("c", _rnd(rng, 60) + s[400:])]),
         ("many_short", [(f"r{i}", s[i * 7:i * 7 + k + 1 + (i % 5)]) for i in range(40)]),
         ("nsplit_names", [("a_Nsplit_0", s[:200]), ("a_Nsplit_1", s[200:400]), ("b", s[50:300])]),
+        # dinucleotide repeat of k + 1 bases: consecutive k-mers are reverse complements of each other (one vertex, a
+        # self-loop reached with different attachment sides) -- found by the hypothesis test
+        ("dinucleotide_selfloop", [("a", _rnd(rng, 90) + "CG" * ((k + 1) // 2) + _rnd(rng, 90)), ("b", s[:120])]),
     ]
     return [(n, k, recs) for n, recs in cases]
 

@@ -19,7 +19,12 @@ def test_reference_tail_on_b200_head(emu_lib, case, tmp_path):
     name, k, recs = case
     fa = os.path.join(tmp_path, "in.fa")
     cases.write_fasta(fa, recs)
-    ref = dropin.run_reference_full(fa, k)
+    try:
+        ref = dropin.run_reference_full(fa, k)
+    except AssertionError:                          # the reference asserts on this input: the drop-in must refuse
+        with pytest.raises(_capi.DegenerateInputError):
+            dropin.run_dropin_full(fa, k, _capi.Engine(lib=emu_lib))
+        return
     got = dropin.run_dropin_full(fa, k, _capi.Engine(lib=emu_lib))
     assert dropin.canonical(ref) == dropin.canonical(got)
     assert dropin.contigs_digest(ref) == dropin.contigs_digest(got)

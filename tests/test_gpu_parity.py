@@ -23,6 +23,10 @@ def run_gpu(seqdict, k):
 
 @pytest.mark.parametrize("case", helpers.load_crafted(), ids=lambda c: f"{c['name']}-k{c['k']}")
 def test_gpu_matches_reference_golden(case):
+    if case.get("degenerate"):                      # the reference asserts here: the product must refuse
+        with pytest.raises(_capi.DegenerateInputError):
+            run_gpu(dict(map(tuple, case["records"])), case["k"]).to_result()
+        return
     got = run_gpu(dict(map(tuple, case["records"])), case["k"]).to_result()
     digests.assert_same(helpers.golden_to_result(case), got)
     helpers.assert_summary(digests.summarize(got), case["summary"])

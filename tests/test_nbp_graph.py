@@ -26,7 +26,7 @@ def check(A, k):
             assert set(verts[int(rev[i])]) == set(verts[i]) and int(rev[int(rev[i])]) == i
 
 
-@pytest.mark.parametrize("case", [c for c in helpers.load_crafted() if c["k"] == 31], ids=lambda c: c["name"])
+@pytest.mark.parametrize("case", [c for c in helpers.load_crafted() if c["k"] == 31 and not c.get("degenerate")], ids=lambda c: c["name"])
 def test_nbp_graph_emu(emu_lib, case):
     check(Assembler(dict(map(tuple, case["records"])), case["k"], engine=_capi.Engine(lib=emu_lib)), case["k"])
 

@@ -12,6 +12,10 @@ import helpers
 
 @pytest.mark.parametrize("case", helpers.load_crafted(), ids=lambda c: f"{c['name']}-k{c['k']}")
 def test_oracle_reproduces_reference_crafted(case):
+    if case.get("degenerate"):
+        with pytest.raises(AssertionError):
+            dbg_oracle.run_oracle(dict(map(tuple, case["records"])), case["k"])
+        return
     got = dbg_oracle.run_oracle(dict(map(tuple, case["records"])), case["k"])
     digests.assert_same(helpers.golden_to_result(case), got)
     helpers.assert_summary(digests.summarize(got), case["summary"])

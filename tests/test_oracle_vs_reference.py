@@ -17,4 +17,10 @@ def test_live_reference_matches_oracle(case, tmp_path):
     name, k, recs = case
     fa = os.path.join(tmp_path, "in.fa")
     cases.write_fasta(fa, recs)
-    digests.assert_same(refrun.run_reference(fa, k), dbg_oracle.run_oracle(fa, k))
+    try:
+        ref = refrun.run_reference(fa, k)
+    except AssertionError:                          # orientation-ambiguous input: the oracle must assert as well
+        with pytest.raises(AssertionError):
+            dbg_oracle.run_oracle(fa, k)
+        return
+    digests.assert_same(ref, dbg_oracle.run_oracle(fa, k))
