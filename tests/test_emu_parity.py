@@ -106,6 +106,7 @@ VARIANTS = [
     {"SPB_DEDUP": "links", "SPB_BUCKET_BITS": "3"},                  # partitioned dedup, exceptions as links
     {"SPB_DEDUP": "links", "SPB_BUCKET_BITS": "0", "SPB_EMU_ORDER": "reverse"},   # displacement chains
     {"SPB_DEDUP": "links", "SPB_BUCKET_BITS": "5", "SPB_EMU_ORDER": "shuffle"},
+    {"SPB_DEDUP": "links", "SPB_BUCKET_BITS": "4", "SPB_PARTITION_FUSED": "1", "SPB_EMU_ORDER": "shuffle"},   # block-phased partition kernel
 ]
 
 
