@@ -680,9 +680,11 @@ static int dedup_global_table(spb_ctx* c, bool allow_switch) {
   if (done < P && anchored >= 0) {
     u64 hi = std::min(P, done + CH);
     launch_extract_k(c, done, hi, slots, cap, seenpos, wbits, dbits, arec, extc);
-    if (anchored == 0) anchored = (double)dread(c, extc) >= 0.25 * (double)(hi - done) ? 1 : -1;
+    const u64 n_ext = dread(c, extc), n_dup = dread(c, extc + 1), chunk_n = hi - done;
+    if (anchored == 0) anchored = (double)n_ext >= 0.25 * (double)chunk_n ? 1 : -1;
     done = hi;
-    if (anchored < 0 && allow_switch && c->n_inst >= (64ull << 20)) {
+    // partitioned dedup only pays when almost nothing is duplicated (every duplicate costs it a scattered write)
+    if (anchored < 0 && allow_switch && c->n_inst >= (64ull << 20) && (double)n_dup < 0.02 * (double)chunk_n) {
       // mostly unique k-mers and a table far beyond L2: the partitioned "links" dedup is faster; start over with it
       dfree(c, arec); dfree(c, extc); dfree(c, seenpos); dfree(c, slots); dfree(c, wbits); dfree(c, dbits);
       return 1;

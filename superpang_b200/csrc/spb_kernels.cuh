@@ -332,12 +332,14 @@ k_extract_insert(const u32* __restrict__ F, const u32* __restrict__ R, const u32
   }
   store_bit(obits, p, o);
   store_bit(wbits, p, won);
-  if (ext_count) {
+  if (ext_count) {                                   // [0] extended positions, [1] duplicates (valid, not installed)
+    bool dup = valid && !won;
 #ifdef SPB_EMU
     if (ext) atomicAdd(ext_count, 1ull);
+    if (dup) atomicAdd(ext_count + 1, 1ull);
 #else
-    u32 b = __ballot_sync(0xffffffffu, ext);
-    if ((threadIdx.x & 31) == 0 && b) atomicAdd(ext_count, (u64)__popc(b));
+    u32 b = __ballot_sync(0xffffffffu, ext), b2 = __ballot_sync(0xffffffffu, dup);
+    if ((threadIdx.x & 31) == 0) { if (b) atomicAdd(ext_count, (u64)__popc(b)); if (b2) atomicAdd(ext_count + 1, (u64)__popc(b2)); }
 #endif
   }
 }
