@@ -101,6 +101,13 @@ int spb_mg_records(spb_ctx* ctx, uint64_t pos_lo, uint64_t pos_hi, uint32_t n_ow
 int spb_mg_dedup(spb_ctx* ctx, const uint64_t* keys, const uint32_t* pos, const uint64_t* chunk_counts,
                  uint32_t n_chunks, uint32_t n_owners, uint32_t owner, uint32_t* rep_out);
 int spb_mg_scatter(spb_ctx* ctx, const uint32_t* rep);
+/* "links" protocol (default): instead of one representative per record the owner returns only the exceptions --
+ * (position << 32 | first position) for every instance that is not a first appearance -- sorted by position, with
+ * send_counts[n_owners] per destination rank (position slices); the received records may be reordered in place.
+ * spb_mg_apply_links consumes the links a rank receives for its slice (replaces spb_mg_dedup + spb_mg_scatter). */
+int spb_mg_dedup_links(spb_ctx* ctx, uint64_t* keys_io, uint32_t* pos_io, uint64_t n_total, uint32_t n_owners,
+                       uint64_t* send_counts, void** links_dev);
+int spb_mg_apply_links(spb_ctx* ctx, const uint64_t* links, uint64_t n, uint64_t pos_lo, uint64_t pos_hi);
 int spb_mg_buffers(spb_ctx* ctx, void** fbits_dev, void** obits_dev, void** sp_dev);
 int spb_mg_ids(spb_ctx* ctx, uint64_t pos_lo, uint64_t pos_hi);
 int spb_mg_graph(spb_ctx* ctx, spb_counts* out);

@@ -23,7 +23,7 @@ EXPORTS = (
     "spb_get_vertex2coords", "spb_get_edges", "spb_get_instance_vertices", "spb_get_seqlimits",
     "spb_get_seq_intervals", "spb_get_components", "spb_get_nbps", "spb_get_nbp_seqs",
     "spb_get_nbp_origins", "spb_get_counts", "spb_get_stage_stats", "spb_build_kind", "spb_launch_count",
-    "spb_get_nbp_graph", "spb_mg_slice", "spb_mg_records", "spb_mg_dedup", "spb_mg_scatter", "spb_mg_buffers", "spb_mg_ids", "spb_mg_graph",
+    "spb_get_nbp_graph", "spb_mg_slice", "spb_mg_records", "spb_mg_dedup", "spb_mg_scatter", "spb_mg_dedup_links", "spb_mg_apply_links", "spb_mg_buffers", "spb_mg_ids", "spb_mg_graph",
 )
 
 
@@ -87,6 +87,8 @@ def _declare(lib):
     lib.spb_mg_records.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     lib.spb_mg_dedup.argtypes = [vp, u64p, u32p, C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32, C.c_uint32, u32p]
     lib.spb_mg_scatter.argtypes = [vp, u32p]
+    lib.spb_mg_dedup_links.argtypes = [vp, u64p, u32p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)]
+    lib.spb_mg_apply_links.argtypes = [vp, u64p, C.c_uint64, C.c_uint64, C.c_uint64]
     lib.spb_mg_buffers.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     lib.spb_mg_ids.argtypes = [vp, C.c_uint64, C.c_uint64]
     lib.spb_mg_graph.argtypes = [vp, C.POINTER(SpbCounts)]
@@ -248,17 +250,36 @@ class Engine:
         rpos = torch.empty(sum(recv), dtype=torch.int32, device=dev)
         _exchange(rkeys, keys, recv, send, r, group)
         _exchange(rpos, pos, recv, send, r, group)
-        rep = torch.empty(sum(recv), dtype=torch.int32, device=dev)
-        chunk = (C.c_uint64 * G)(*recv)
         mark("exchange_records")
         sync()
-        self._ck(self.lib.spb_mg_dedup(self.h, rkeys.data_ptr(), rpos.data_ptr(), chunk, G, G, r, rep.data_ptr()))
-        mark("owner_dedup")
-        back = torch.empty(sum(send), dtype=torch.int32, device=dev)
-        _exchange(back, rep, send, recv, r, group)
-        mark("exchange_reps")
-        sync()
-        self._ck(self.lib.spb_mg_scatter(self.h, back.data_ptr()))
+        if os.environ.get("SPB_MG_PROTOCOL", "links") == "reps":
+            # one representative per record travels back (kept for A/B measurements)
+            rep = torch.empty(sum(recv), dtype=torch.int32, device=dev)
+            chunk = (C.c_uint64 * G)(*recv)
+            self._ck(self.lib.spb_mg_dedup(self.h, rkeys.data_ptr(), rpos.data_ptr(), chunk, G, G, r, rep.data_ptr()))
+            mark("owner_dedup")
+            back = torch.empty(sum(send), dtype=torch.int32, device=dev)
+            _exchange(back, rep, send, recv, r, group)
+            mark("exchange_reps")
+            sync()
+            self._ck(self.lib.spb_mg_scatter(self.h, back.data_ptr()))
+        else:
+            # "links": only the instances that are not first appearances travel back, as (position -> first position)
+            lcnt = (C.c_uint64 * G)()
+            lp = C.c_void_p()
+            self._ck(self.lib.spb_mg_dedup_links(self.h, rkeys.data_ptr(), rpos.data_ptr(), sum(recv), G, lcnt, C.byref(lp)))
+            mark("owner_dedup")
+            lsend = [int(x) for x in lcnt]
+            links = _wrap(lp.value, sum(lsend), torch.int64, cuda, self.device)
+            lsc = torch.tensor(lsend, dtype=torch.int64, device=dev)
+            lrc = torch.empty_like(lsc)
+            dist.all_to_all_single(lrc, lsc, group=group)
+            lrecv = [int(x) for x in lrc.tolist()]
+            lback = torch.empty(sum(lrecv), dtype=torch.int64, device=dev)
+            _exchange(lback, links, lrecv, lsend, r, group)
+            mark("exchange_reps")
+            sync()
+            self._ck(self.lib.spb_mg_apply_links(self.h, lback.data_ptr() if lback.numel() else None, lback.numel(), lo, max(lo, hi)))
         fb, ob, sp = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._ck(self.lib.spb_mg_buffers(self.h, C.byref(fb), C.byref(ob), C.byref(sp)))
         mark("scatter")

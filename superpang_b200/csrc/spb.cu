@@ -47,6 +47,7 @@ struct spb_ctx {
   // staged dedup state (records sent by this rank)
   u64 *dd_keys = 0, *dd_bstart = 0; u32* dd_pos = 0; u64 dd_n = 0, dd_lo = 0, dd_hi = 0; u32 dd_bb = 0; bool dd_fbits_ready = false;
   std::vector<u64> dd_bstart_h;
+  u64* mg_links = 0; u32 *mg_seen = 0, *mg_dup = 0;                 // multi-GPU links protocol
   std::string stats;
 };
 
@@ -803,6 +804,101 @@ int spb_mg_dedup(spb_ctx* c, const uint64_t* keys, const uint32_t* pos, const ui
   return check_err(c, "spb_mg_dedup");
 }
 
+// Owner side, "links" protocol: dedup of the received records in L2-resident sub-bucket tables; returns only the
+// exceptions as (position -> first position) links, sorted by position, with per-destination-rank counts.
+int spb_mg_dedup_links(spb_ctx* c, uint64_t* keys_io, uint32_t* pos_io, uint64_t n_total, uint32_t n_owners, uint64_t* send_counts,
+                       void** links_dev) {
+  if (!c) return SPB_EINVAL;
+  if (c->state != 1) return fail(c, SPB_ESTATE, "spb_mg_dedup_links needs a loaded input");
+  if (!pow2(n_owners)) return fail(c, SPB_EINVAL, "n_owners must be a power of two");
+#ifndef SPB_EMU
+  CK(cudaSetDevice(c->device));
+#endif
+  u32 bbo = 0; while ((1u << bbo) < n_owners) ++bbo;
+  u32 sb = 0; while (sb < 8 && (n_total >> sb) > 2200000ull) ++sb;          // sub-buckets of ~2 M records
+  if (const char* e = getenv("SPB_BUCKET_BITS")) sb = (u32)atoi(e);
+  u64* keys = (u64*)keys_io; u32* pos = pos_io;
+  u64 *k2 = nullptr, *k2a = nullptr; u32 *p2 = nullptr, *p2a = nullptr;
+  if (sb > 0 && n_total) {
+    ALLOC(k2, u64, n_total); ALLOC(p2, u32, n_total);
+    k2a = k2; p2a = p2;                                // the partition may swap the roles of the two buffer pairs
+    PRIM(prim_partition_u64_u32(c, keys, pos, k2, p2, n_total, 64 - bbo - sb, 64 - bbo));
+  }
+  // (after the partition `keys` / `pos` point at the sorted copy, which may be the scratch pair)
+  const u32 B = 1u << sb;
+  u64 *coff, *sub; ALLOC(coff, u64, 2); ALLOC(sub, u64, B + 2);
+  u64 co[2] = {0, n_total};
+  memcpy(c->pinned, co, 16); dev_copy(c, coff, c->pinned, 16);
+  // bucket = bits [64-bbo-sb, 64-bbo): shift the owner bits out by comparing on (key << bbo)
+  std::vector<u64> bstart(B + 1, 0);
+  if (n_total) {
+    SPB_LAUNCH(k_bucket_bounds_shift, nblk(B + 1, TPB), TPB, c->stream, keys, n_total, bbo, sb, B, sub);
+    dev_copy(c, bstart.data(), sub, (B + 1) * 8ull); dev_sync(c);
+  }
+  u64 nmax = 0;
+  for (u32 b = 0; b < B; ++b) nmax = std::max(nmax, bstart[b + 1] - bstart[b]);
+  u64 cap = 1024; while (cap < 2 * nmax) cap <<= 1;
+  c->cnt.table_slots = cap;
+  u64* scratch[2]; ALLOC(scratch[0], u64, cap); ALLOC(scratch[1], u64, cap);
+  dev_memset(c, scratch[0], 0xFF, cap * 8);
+  u64* nlinks; ALLOC(nlinks, u64, 2); dev_memset(c, nlinks, 0, 16);
+  u64 lcap = std::max<u64>(4096, n_total / 8);
+  u64* links = nullptr; u64 nl = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    ALLOC(links, u64, lcap + 1);
+    dev_memset(c, nlinks, 0, 16);
+    if (attempt) dev_memset(c, scratch[0], 0xFF, cap * 8);
+    u32 step = 0;
+    for (u32 b = 0; b < B; ++b) {
+      u64 lo = bstart[b], n = bstart[b + 1] - lo;
+      if (n == 0) continue;
+      u64* cur = scratch[step & 1]; u64* other = scratch[(step & 1) ^ 1];
+      u64 g = std::max<u64>(nblk(n, TPB), std::min<u64>(nblk(cap, TPB), 148 * 8));
+      SPB_LAUNCH(k_bkt_insert_list, g, TPB, c->stream, keys, pos, lo, n, c->F, c->R, c->T, c->k, cur, cap - 1, links, nlinks, lcap, other, cap);
+      ++step;
+    }
+    nl = dread(c, nlinks);
+    if (nl <= lcap) break;
+    dfree(c, links); lcap = nl;
+  }
+  dfree(c, scratch[0]); dfree(c, scratch[1]); dfree(c, nlinks); dfree(c, coff); dfree(c, sub);
+  dfree(c, k2a); dfree(c, p2a);
+  if (getenv("SPB_DEBUG")) fprintf(stderr, "[spb] dedup_links: n_total=%llu B=%u cap=%llu links=%llu\n", (unsigned long long)n_total, B, (unsigned long long)cap, (unsigned long long)nl);
+  // sort by position, resolve chains, split by destination rank
+  u64* tmp; ALLOC(tmp, u64, nl + 1);
+  PRIM(prim_sort_u64(c, links, tmp, nl));
+  SPB_LAUNCH(k_links_resolve, nblk(nl, TPB), TPB, c->stream, links, nl, tmp);
+  uint64_t slice = 0; spb_mg_slice(c, n_owners, &slice);
+  u64* bounds; ALLOC(bounds, u64, n_owners + 2);
+  SPB_LAUNCH(k_links_bounds, nblk(n_owners + 1, TPB), TPB, c->stream, tmp, nl, slice, n_owners, bounds);
+  std::vector<u64> bh(n_owners + 1);
+  dev_copy(c, bh.data(), bounds, (n_owners + 1) * 8ull); dev_sync(c);
+  for (u32 r = 0; r < n_owners; ++r) send_counts[r] = bh[r + 1] - bh[r];
+  dfree(c, bounds); dfree(c, links);
+  dfree(c, c->mg_links);
+  c->mg_links = tmp;
+  *links_dev = tmp;
+  return check_err(c, "spb_mg_dedup_links");
+}
+
+// Position side, "links" protocol: the links received for the local slice -> first-appearance bits of the slice.
+int spb_mg_apply_links(spb_ctx* c, const uint64_t* links, uint64_t n, uint64_t pos_lo, uint64_t pos_hi) {
+  if (!c) return SPB_EINVAL;
+  if (c->state != 1 || !c->dd_pos) return fail(c, SPB_ESTATE, "spb_mg_apply_links without spb_mg_records");
+  const u64 P = c->npos_pad, nw32 = P / 32;
+  ALLOC(c->mg_seen, u32, P + 8); ALLOC(c->mg_dup, u32, nw32 + 8);
+  dev_memset(c, c->mg_dup, 0, (nw32 + 8) * 4);
+  SPB_LAUNCH(k_links_apply, nblk(n, TPB), TPB, c->stream, (const u64*)links, n, c->mg_seen, c->mg_dup);
+  if (getenv("SPB_DEBUG")) { std::vector<u64> h(std::min<u64>(n, 4)); dev_copy(c, h.data(), links, h.size() * 8); dev_sync(c); fprintf(stderr, "[spb] apply_links: n=%llu first=%llx %llx\n", (unsigned long long)n, n ? (unsigned long long)h[0] : 0ull, n > 1 ? (unsigned long long)h[1] : 0ull); }
+  // first appearance = valid and not linked; only the words of the local slice are meaningful (all-gathered next)
+  // (vbits covers the positions of the input only; the padded tail of the grown position arrays stays zero)
+  SPB_LAUNCH(k_first_bits, nblk(nblk(c->T, 256), TPB), TPB, c->stream, c->vbits, c->mg_dup, c->fbits, nblk(c->T, 256));
+  dfree(c, c->mg_dup); dfree(c, c->mg_links);
+  dfree(c, c->dd_keys); dfree(c, c->dd_pos); dfree(c, c->dd_bstart);
+  (void)pos_lo; (void)pos_hi;
+  return check_err(c, "spb_mg_apply_links");
+}
+
 int spb_mg_scatter(spb_ctx* c, const uint32_t* rep) {
   if (!c) return SPB_EINVAL;
   if (c->state != 1 || !c->dd_pos) return fail(c, SPB_ESTATE, "spb_mg_scatter without spb_mg_records");
@@ -822,7 +918,8 @@ int spb_mg_ids(spb_ctx* c, uint64_t pos_lo, uint64_t pos_hi) {
   if (!c) return SPB_EINVAL;
   if (c->state != 1 || !c->sp) return fail(c, SPB_ESTATE, "spb_mg_ids out of order");
   if (pos_hi > c->T) pos_hi = c->T;
-  PRIM(dd_ids(c, pos_lo, pos_hi, nullptr));
+  PRIM(dd_ids(c, pos_lo, pos_hi, nullptr, 1, c->mg_seen));       // links protocol: the representatives live in mg_seen
+  dfree(c, c->mg_seen);
   return check_err(c, "spb_mg_ids");
 }
 

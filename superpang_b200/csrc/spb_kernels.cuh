@@ -440,6 +440,15 @@ __global__ void k_bucket_bounds(const u64* __restrict__ keys, const u64* __restr
   sub[g] = a - lo;
 }
 
+// sub[b] = first record whose sub-bucket (the `sb` hash bits below the `bbo` owner bits) is >= b; records sorted by those bits
+__global__ void k_bucket_bounds_shift(const u64* __restrict__ keys, u64 n, u32 bbo, u32 sb, u32 B, u64* __restrict__ sub) {
+  u64 b = SPB_GTID();
+  if (b > B) return;
+  if (sb == 0) { sub[b] = b ? n : 0; return; }
+  u64 lo = 0, hi = n;
+  while (lo < hi) { u64 mid = (lo + hi) >> 1; if (((__ldg(keys + mid) << bbo) >> (64 - sb)) < b) lo = mid + 1; else hi = mid; }
+  sub[b] = lo;
+}
 struct BktView {
   const u64* keys; const u32* pos; u32* sidx;      // records (all chunks concatenated) and per-record slot / representative
   const u64* chunk_off; const u64* sub;            // chunk offsets [nchunks+1], sub-range table [nchunks][B+1]
@@ -562,6 +571,82 @@ k_bkt_insert_links(const u64* __restrict__ keys, const u32* __restrict__ pos, u6
   }
   u64 stride = (u64)gridDim.x * blockDim.x;
   for (u64 j = t; j < clear_n; j += stride) clear[j] = SPB_EMPTY;
+}
+
+// Owner side of the multi-GPU "links" protocol: like k_bkt_insert_links, but the links are appended to a list
+// (from << 32 | to) instead of being written in place (the positions belong to other ranks).
+__global__ void SPB_LAUNCH_BOUNDS(256)
+k_bkt_insert_list(const u64* __restrict__ keys, const u32* __restrict__ pos, u64 lo, u64 n, const u32* __restrict__ F,
+                  const u32* __restrict__ R, u64 T, u32 k, u64* scratch, u64 capmask, u64* __restrict__ links, u64* nlinks, u64 lcap,
+                  u64* clear, u64 clear_n) {
+  u64 t = SPB_GTID();
+  bool emit = false;
+  u64 link = 0;
+  if (t < n) {
+    u64 key = keys[lo + t];
+    if (key != ~0ull) {
+      u64 p = pos[lo + t];
+      bool o = key & 1;
+      u64 tag = (key >> 1) & 0x7FFFFFull, idx = (key >> 24) & capmask;
+      u64 entry = (tag << 40) | (p << 1) | (o ? 1ull : 0ull);
+      const u32* S = o ? F : R;
+      u64 a = o ? p : T - p - k;
+      for (;;) {
+        u64 cur = atomicCAS(scratch + idx, SPB_EMPTY, entry);
+        if (cur == SPB_EMPTY) break;
+        if ((cur >> 40) == tag) {
+          u64 q = (cur >> 1) & SPB_POSMASK;
+          bool oq = cur & 1;
+          if (q == p || win_cmp(S, a, oq ? F : R, oq ? q : T - q - k, k) == 0) {
+            u64 from = p, to = q;
+            if (entry < cur) {
+              u64 old = atomicMin(scratch + idx, entry);
+              u64 oq2 = (old >> 1) & SPB_POSMASK;
+              if (old > entry) { from = oq2; to = p; } else to = oq2;
+            }
+            emit = true; link = (from << 32) | to;
+            break;
+          }
+        }
+        idx = (idx + 1) & capmask;
+      }
+    }
+  }
+  u64 slot = warp_append(nlinks, emit);
+  if (emit && slot < lcap) links[slot] = link;
+  u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 j = t; j < clear_n; j += stride) clear[j] = SPB_EMPTY;
+}
+// links sorted by `from`: make every `to` a first appearance (a `to` that is itself the `from` of another link is
+// followed; all positions of a chain carry the same k-mer and therefore live at this owner)
+__global__ void k_links_resolve(const u64* __restrict__ links, u64 n, u64* __restrict__ out) {
+  u64 i = SPB_GTID();
+  if (i >= n) return;
+  u64 l = links[i];
+  u32 to = (u32)l;
+  for (;;) {
+    u64 lo = 0, hi = n;                               // lower_bound on the `from` part
+    while (lo < hi) { u64 mid = (lo + hi) >> 1; if ((links[mid] >> 32) < to) lo = mid + 1; else hi = mid; }
+    if (lo < n && (links[lo] >> 32) == to) to = (u32)links[lo]; else break;
+  }
+  out[i] = (l & 0xFFFFFFFF00000000ull) | to;
+}
+__global__ void k_links_bounds(const u64* __restrict__ links, u64 n, u64 slice, u32 n_ranks, u64* __restrict__ bounds) {
+  u64 r = SPB_GTID();
+  if (r > n_ranks) return;
+  u64 key = (r * slice) << 32;
+  if (r == n_ranks) { bounds[r] = n; return; }
+  u64 lo = 0, hi = n;
+  while (lo < hi) { u64 mid = (lo + hi) >> 1; if (links[mid] < key) lo = mid + 1; else hi = mid; }
+  bounds[r] = lo;
+}
+// position side: apply the links received for the local slice
+__global__ void k_links_apply(const u64* __restrict__ links, u64 n, u32* __restrict__ seenpos, u32* dupbits) {
+  u64 i = SPB_GTID();
+  if (i >= n) return;
+  u32 from = (u32)(links[i] >> 32);
+  seenpos[from] = (u32)links[i];
+  atomicOr(dupbits + (from >> 5), 1u << (from & 31));
 }
 
 // S3: bucket-interleaved scatter back to position order

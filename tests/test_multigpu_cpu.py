@@ -22,8 +22,13 @@ def _free_port():
     return str(p)
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_distributed_build_matches_reference(emu_lib, tmp_path, world):
+@pytest.mark.parametrize("world,env", [
+    (2, {}), (4, {}),
+    (2, {"SPB_EMU_ORDER": "reverse"}),                               # displacement chains resolved at the owner
+    (2, {"SPB_BUCKET_BITS": "3", "SPB_EMU_ORDER": "shuffle"}),       # owner sub-buckets
+    (2, {"SPB_MG_PROTOCOL": "reps"}),                                # one representative per record travels back
+], ids=lambda x: str(x) if isinstance(x, int) else (",".join(f"{k[4:].lower()}={v}" for k, v in x.items()) or "default"))
+def test_distributed_build_matches_reference(emu_lib, tmp_path, world, env):
     crafted = [c for c in helpers.load_crafted() if c["k"] == 31 and not c.get("degenerate")]
     syn = helpers.load_json("synthetic.json")["cases"][:2]
     cases = [dict(records=c["records"], k=c["k"]) for c in crafted]
@@ -36,8 +41,8 @@ def test_distributed_build_matches_reference(emu_lib, tmp_path, world):
     json.dump(cases, open(case_path, "w"))
     out = os.path.join(tmp_path, "out.json")
     port = _free_port()
-    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "mg_worker.py"), str(r), str(world), port, case_path, out])
-             for r in range(world)]
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "mg_worker.py"), str(r), str(world), port, case_path, out],
+                              env=dict(os.environ, **env)) for r in range(world)]
     for p in procs:
         assert p.wait(timeout=600) == 0
     for r in range(world):
