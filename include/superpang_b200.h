@@ -96,6 +96,9 @@ int spb_compact(spb_ctx* ctx, spb_counts* out);
  *                    leaves the context in the same state as spb_build_dbg, spb_compact follows unchanged.
  * Replaces the reference's single-process dict loop, `lib/Assembler.py:186-217`, for n_ranks > 1. */
 int spb_mg_slice(spb_ctx* ctx, uint32_t n_ranks, uint64_t* slice_len);
+/* Duplicate profile of the first two 4 M-position chunks (fractions of chunk 1 that extend an anchor match / that are
+ * duplicates); the host side picks the return protocol from it: links if almost nothing repeats, representatives otherwise. */
+int spb_mg_probe(spb_ctx* ctx, double* ext_ratio, double* dup_ratio);
 int spb_mg_records(spb_ctx* ctx, uint64_t pos_lo, uint64_t pos_hi, uint32_t n_owners, uint64_t* owner_counts,
                    void** keys_dev, void** pos_dev);
 int spb_mg_dedup(spb_ctx* ctx, const uint64_t* keys, const uint32_t* pos, const uint64_t* chunk_counts,

@@ -23,7 +23,7 @@ EXPORTS = (
     "spb_get_vertex2coords", "spb_get_edges", "spb_get_instance_vertices", "spb_get_seqlimits",
     "spb_get_seq_intervals", "spb_get_components", "spb_get_nbps", "spb_get_nbp_seqs",
     "spb_get_nbp_origins", "spb_get_counts", "spb_get_stage_stats", "spb_build_kind", "spb_launch_count",
-    "spb_get_nbp_graph", "spb_mg_slice", "spb_mg_records", "spb_mg_dedup", "spb_mg_scatter", "spb_mg_dedup_links", "spb_mg_apply_links", "spb_mg_buffers", "spb_mg_ids", "spb_mg_graph",
+    "spb_get_nbp_graph", "spb_mg_slice", "spb_mg_probe", "spb_mg_records", "spb_mg_dedup", "spb_mg_scatter", "spb_mg_dedup_links", "spb_mg_apply_links", "spb_mg_buffers", "spb_mg_ids", "spb_mg_graph",
 )
 
 
@@ -84,6 +84,7 @@ def _declare(lib):
     lib.spb_launch_count.restype = C.c_uint64
     lib.spb_get_nbp_graph.argtypes = [vp, C.POINTER(C.c_uint64), u64p, u32p, u32p]
     lib.spb_mg_slice.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint64)]
+    lib.spb_mg_probe.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.spb_mg_records.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     lib.spb_mg_dedup.argtypes = [vp, u64p, u32p, C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32, C.c_uint32, u32p]
     lib.spb_mg_scatter.argtypes = [vp, u32p]
@@ -237,6 +238,18 @@ class Engine:
         cnt = (C.c_uint64 * G)()
         kp, pp = C.c_void_p(), C.c_void_p()
         mark("start")
+        # return protocol: rank 0 samples the duplicate rate of the input (two chunks) and broadcasts the choice
+        protocol = os.environ.get("SPB_MG_PROTOCOL")
+        if protocol not in ("links", "reps"):
+            flag = torch.zeros(1, dtype=torch.int64, device=dev)
+            if r == 0:
+                er, dr = C.c_double(), C.c_double()
+                self._ck(self.lib.spb_mg_probe(self.h, C.byref(er), C.byref(dr)))
+                flag[0] = 1 if dr.value < 0.02 else 0
+            dist.broadcast(flag, src=0, group=group)
+            protocol = "links" if int(flag.item()) else "reps"
+        self.mg_protocol = protocol
+        mark("probe")
         self._ck(self.lib.spb_mg_records(self.h, lo, max(lo, hi), G, cnt, C.byref(kp), C.byref(pp)))
         mark("records_partition")
         send = [int(x) for x in cnt]
@@ -252,7 +265,7 @@ class Engine:
         _exchange(rpos, pos, recv, send, r, group)
         mark("exchange_records")
         sync()
-        if os.environ.get("SPB_MG_PROTOCOL", "links") == "reps":
+        if protocol == "reps":
             # one representative per record travels back (kept for A/B measurements)
             rep = torch.empty(sum(recv), dtype=torch.int32, device=dev)
             chunk = (C.c_uint64 * G)(*recv)

@@ -804,6 +804,37 @@ int spb_mg_dedup(spb_ctx* c, const uint64_t* keys, const uint32_t* pos, const ui
   return check_err(c, "spb_mg_dedup");
 }
 
+// Duplicate profile of the input from its first two 4 M-position chunks (chunk 0 into a scratch table, chunk 1 probed with
+// the anchor + extend scheme): extended fraction and duplicate fraction of chunk 1.  The multi-GPU host side uses it (on
+// rank 0, broadcast) to choose the return protocol: links when almost nothing is duplicated, representatives otherwise.
+int spb_mg_probe(spb_ctx* c, double* ext_ratio, double* dup_ratio) {
+  if (!c || !ext_ratio || !dup_ratio) return SPB_EINVAL;
+  if (c->state != 1) return fail(c, SPB_ESTATE, "spb_mg_probe needs a freshly loaded input");
+#ifndef SPB_EMU
+  CK(cudaSetDevice(c->device));
+#endif
+  u64 CH = 1ull << 22;
+  if (const char* e = getenv("SPB_CHUNK_BITS")) { int b = atoi(e); if (b >= 8 && b <= 32) CH = 1ull << b; }
+  const u64 P0 = nblk(c->T, TPB) * TPB + TPB;
+  *ext_ratio = 0; *dup_ratio = 0;
+  if (P0 <= CH) return SPB_OK;                       // a single chunk: nothing to compare against
+  const u64 hi = std::min(P0, 2 * CH);
+  u64 cap = 1024; while (cap < 2 * hi) cap <<= 1;
+  u64 *slots, *arec, *extc; u32 *seenpos, *wbits, *dbits, *obits_save = c->obits, *otmp;
+  ALLOC(slots, u64, cap); ALLOC(arec, u64, hi / 32 + 8); ALLOC(extc, u64, 2);
+  ALLOC(seenpos, u32, hi + 8); ALLOC(wbits, u32, hi / 32 + 8); ALLOC(dbits, u32, hi / 32 + 8); ALLOC(otmp, u32, hi / 32 + 8);
+  dev_memset(c, slots, 0xFF, cap * 8); dev_memset(c, extc, 0, 16);
+  dev_memset(c, wbits, 0, (hi / 32 + 8) * 4); dev_memset(c, dbits, 0, (hi / 32 + 8) * 4); dev_memset(c, otmp, 0, (hi / 32 + 8) * 4);
+  c->obits = otmp;                                   // the probe must not touch the real orientation bitmap
+  launch_extract_k(c, 0, CH, slots, cap, seenpos, wbits, dbits, nullptr, nullptr);
+  launch_extract_k(c, CH, hi, slots, cap, seenpos, wbits, dbits, arec, extc);
+  c->obits = obits_save;
+  u64 n_ext = dread(c, extc), n_dup = dread(c, extc + 1);
+  *ext_ratio = (double)n_ext / (double)(hi - CH); *dup_ratio = (double)n_dup / (double)(hi - CH);
+  dfree(c, slots); dfree(c, arec); dfree(c, extc); dfree(c, seenpos); dfree(c, wbits); dfree(c, dbits); dfree(c, otmp);
+  return check_err(c, "spb_mg_probe");
+}
+
 // Owner side, "links" protocol: dedup of the received records in L2-resident sub-bucket tables; returns only the
 // exceptions as (position -> first position) links, sorted by position, with per-destination-rank counts.
 int spb_mg_dedup_links(spb_ctx* c, uint64_t* keys_io, uint32_t* pos_io, uint64_t n_total, uint32_t n_owners, uint64_t* send_counts,
