@@ -29,6 +29,9 @@ struct spb_ctx {
   std::map<void*, u64> live;           // live device blocks -> size
   std::multimap<u64, void*> cache;     // freed blocks kept for reuse (steady state: no cudaMalloc at all)
   u64* pinned = 0;                     // pinned host scratch for scalar read-backs
+#ifndef SPB_EMU
+  cudaStream_t stream2 = 0; cudaEvent_t ev_fork = 0, ev_join = 0;    // second stream for the bucket loop (two L2 tables in flight)
+#endif
   // ---- persistent device state
   u64* seq_off = 0;
   u32 *F = 0, *R = 0, *vbits = 0, *obits = 0, *fbits = 0, *sp = 0, *v2pos = 0, *seqlim = 0, *errflag = 0;
@@ -123,6 +126,28 @@ template <class T> static T dread(spb_ctx* c, const T* p) {
   dev_copy(c, c->pinned, p, sizeof(T)); dev_sync(c);
   T v; memcpy(&v, c->pinned, sizeof(T)); return v;
 }
+
+// The bucket loops keep two L2-resident tables in flight: even buckets on the context's stream, odd ones on a second
+// stream (each bucket: clear its table, then insert).  fork/join order the second stream against the first.
+struct TwoStreams {
+  spb_stream_t st[2];
+#ifdef SPB_EMU
+  explicit TwoStreams(spb_ctx* c) { st[0] = st[1] = c->stream; }
+  void clear(spb_ctx*, int, void* p, u64 bytes) { memset(p, 0xFF, bytes); }
+  void join(spb_ctx*) {}
+#else
+  explicit TwoStreams(spb_ctx* c) {
+    if (!c->stream2) {
+      cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
+      cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+    }
+    st[0] = c->stream; st[1] = c->stream2;
+    cudaEventRecord(c->ev_fork, c->stream); cudaStreamWaitEvent(c->stream2, c->ev_fork, 0);
+  }
+  void clear(spb_ctx*, int i, void* p, u64 bytes) { cudaMemsetAsync(p, 0xFF, bytes, st[i]); }
+  void join(spb_ctx* c) { cudaEventRecord(c->ev_join, c->stream2); cudaStreamWaitEvent(c->stream, c->ev_join, 0); }
+#endif
+};
 
 static inline u64 nblk(u64 n, u32 t) { return (n + t - 1) / t; }
 // grid of a grid-stride kernel: enough resident blocks for every SM, never millions of tiny ones
@@ -347,6 +372,9 @@ static void reset_state(spb_ctx* c) {
   for (void* p : blocks) dev_free_raw(c, p);
   spb_ctx fresh;
   fresh.device = c->device; fresh.stream = c->stream; fresh.errflag = c->errflag; fresh.pinned = c->pinned;
+#ifndef SPB_EMU
+  fresh.stream2 = c->stream2; fresh.ev_fork = c->ev_fork; fresh.ev_join = c->ev_join;
+#endif
   fresh.live.swap(c->live); fresh.cache.swap(c->cache);
   memset(&fresh.cnt, 0, sizeof fresh.cnt); memset(&fresh.nt, 0, sizeof fresh.nt);
   *c = fresh;
@@ -365,6 +393,7 @@ void spb_destroy(spb_ctx* c) {
   free(c->pinned);
 #else
   cudaFreeHost(c->pinned);
+  if (c->stream2) { cudaStreamDestroy(c->stream2); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
 #endif
   delete c;
 }
@@ -626,19 +655,21 @@ static int dedup_staged_links(spb_ctx* c) {
   u64 cap = 1024; while (cap < 2 * nmax) cap <<= 1;
   c->cnt.table_slots = cap;
   u64* scratch[2]; ALLOC(scratch[0], u64, cap); ALLOC(scratch[1], u64, cap);
-  dev_memset(c, scratch[0], 0xFF, cap * 8);
-  if (B == 1) dev_memset(c, scratch[1], 0xFF, 8);
   u32 *seenpos, *dupbits; ALLOC(seenpos, u32, P + 8); ALLOC(dupbits, u32, P / 32 + 8);
   dev_memset(c, dupbits, 0, (P / 32 + 8) * 4);
-  u32 step = 0;
-  for (u32 b = 0; b < B; ++b) {
-    u64 lo = blo[b], n = bn[b];
-    if (n == 0) continue;
-    u64* cur = scratch[step & 1]; u64* other = scratch[(step & 1) ^ 1];
-    u64 g = std::max<u64>(nblk(n, TPB), B > 1 ? std::min<u64>(nblk(cap, TPB), 148 * 8) : 0);
-    SPB_LAUNCH(k_bkt_insert_links, g, TPB, c->stream, c->dd_keys, c->dd_pos, lo, n, c->F, c->R, T, c->k, cur, cap - 1, seenpos, dupbits, other,
-               B > 1 ? cap : 0);
-    ++step;
+  {
+    TwoStreams ts(c);
+    u32 step = 0;
+    for (u32 b = 0; b < B; ++b) {
+      u64 lo = blo[b], n = bn[b];
+      if (n == 0) continue;
+      const int i = step & 1;
+      ts.clear(c, i, scratch[i], cap * 8);
+      SPB_LAUNCH(k_bkt_insert_links, nblk(n, TPB), TPB, ts.st[i], c->dd_keys, c->dd_pos, lo, n, c->F, c->R, T, c->k, scratch[i], cap - 1, seenpos,
+                 dupbits, (u64*)nullptr, 0);
+      ++step;
+    }
+    ts.join(c);
   }
   dfree(c, scratch[0]); dfree(c, scratch[1]);
   dfree(c, c->dd_keys); dfree(c, c->dd_pos);
@@ -871,22 +902,25 @@ int spb_mg_dedup_links(spb_ctx* c, uint64_t* keys_io, uint32_t* pos_io, uint64_t
   u64 cap = 1024; while (cap < 2 * nmax) cap <<= 1;
   c->cnt.table_slots = cap;
   u64* scratch[2]; ALLOC(scratch[0], u64, cap); ALLOC(scratch[1], u64, cap);
-  dev_memset(c, scratch[0], 0xFF, cap * 8);
   u64* nlinks; ALLOC(nlinks, u64, 2); dev_memset(c, nlinks, 0, 16);
   u64 lcap = std::max<u64>(4096, n_total / 8);
   u64* links = nullptr; u64 nl = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {
     ALLOC(links, u64, lcap + 1);
     dev_memset(c, nlinks, 0, 16);
-    if (attempt) dev_memset(c, scratch[0], 0xFF, cap * 8);
-    u32 step = 0;
-    for (u32 b = 0; b < B; ++b) {
-      u64 lo = bstart[b], n = bstart[b + 1] - lo;
-      if (n == 0) continue;
-      u64* cur = scratch[step & 1]; u64* other = scratch[(step & 1) ^ 1];
-      u64 g = std::max<u64>(nblk(n, TPB), std::min<u64>(nblk(cap, TPB), 148 * 8));
-      SPB_LAUNCH(k_bkt_insert_list, g, TPB, c->stream, keys, pos, lo, n, c->F, c->R, c->T, c->k, cur, cap - 1, links, nlinks, lcap, other, cap);
-      ++step;
+    {
+      TwoStreams ts(c);
+      u32 step = 0;
+      for (u32 b = 0; b < B; ++b) {
+        u64 lo = bstart[b], n = bstart[b + 1] - lo;
+        if (n == 0) continue;
+        const int i = step & 1;
+        ts.clear(c, i, scratch[i], cap * 8);
+        SPB_LAUNCH(k_bkt_insert_list, nblk(n, TPB), TPB, ts.st[i], keys, pos, lo, n, c->F, c->R, c->T, c->k, scratch[i], cap - 1, links, nlinks, lcap,
+                   (u64*)nullptr, 0);
+        ++step;
+      }
+      ts.join(c);
     }
     nl = dread(c, nlinks);
     if (nl <= lcap) break;
