@@ -470,10 +470,10 @@ static int dd_records(spb_ctx* c, u64 pos_lo, u64 pos_hi, u32 bb, u64 min_positi
   ALLOC(keys, u64, n); ALLOC(pos, u32, n);
   u64 grid = n / TPB;
   switch ((2 * c->k + 31) / 32) {
-    case 7:  SPB_LAUNCH_PHASED(k_make_records<7>, 2, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, keys, pos, c->obits); break;
-    case 19: SPB_LAUNCH_PHASED(k_make_records<19>, 2, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, keys, pos, c->obits); break;
-    case 32: SPB_LAUNCH_PHASED(k_make_records<32>, 2, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, keys, pos, c->obits); break;
-    default: SPB_LAUNCH_PHASED(k_make_records<0>, 2, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, keys, pos, c->obits); break;
+    case 7:  SPB_LAUNCH(k_make_records<7>, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, keys, pos, c->obits); break;
+    case 19: SPB_LAUNCH(k_make_records<19>, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, keys, pos, c->obits); break;
+    case 32: SPB_LAUNCH(k_make_records<32>, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, keys, pos, c->obits); break;
+    default: SPB_LAUNCH(k_make_records<0>, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, keys, pos, c->obits); break;
   }
   if (bb > 0) {
     ALLOC(keys2, u64, n); ALLOC(pos2, u32, n);

@@ -353,58 +353,25 @@ k_extract_insert(const u32* __restrict__ F, const u32* __restrict__ R, const u32
 // that writes to one sector happen close together in time and merge in L2.  With several GPUs the
 // buckets are the unit of ownership: S1 and S3 run on the GPU that owns the positions, S2 on the GPU
 // that owns the bucket, with an all-to-all of records before and of representatives after S2.
-// Record generation.  A block covers 256 consecutive positions; the words of both strands that its windows touch
-// (256 + k bases each, ~35 words at k = 301) are staged in shared memory first: the per-limb loads then come from shared
-// memory (broadcast reads) instead of ~24 global load instructions per position, which bound the first version of this
-// kernel (ncu: issue slots 74 % busy, LSU-limited).
-#define SPB_STAGE_WORDS 288                          /* (256 + 4000) / 16 + slack: any k the reference accepts */
-template <int W> __device__ __forceinline__ u64 win_hash_s(const u32* w, u32 a, u32 k) {   // w: staged words, a: base offset in them
-  const u32* x = w + (a >> 4); const u32 sh = (a & 15) * 2;
-  const u32 n = W > 0 ? (u32)W : nlimbs(k);
-  u32 ha = 0x9E3779B9u ^ k, hb = 0x85EBCA6Bu;
-  u32 x0 = x[0];
-#pragma unroll
-  for (u32 j = 0; j < n; ++j) {
-    u32 x1 = x[j + 1];
-    u32 l = __funnelshift_l(x1, x0, sh);
-    if (j == n - 1) l &= tail_mask(k);
-    ha = ha * 0x9E3779B1u + l; hb = (hb ^ l) * 0x85EBCA77u;
-    x0 = x1;
-  }
-  return hash_finish(ha, hb);
-}
 template <int W> __global__ void SPB_LAUNCH_BOUNDS(256)
 k_make_records(const u32* __restrict__ F, const u32* __restrict__ R, const u32* __restrict__ vbits, u64 T, u32 k,
                u64 pos_lo, u64 pos_hi, u64* __restrict__ keys, u32* __restrict__ pos, u32* obits) {
-  SPB_SHARED u32 sF[SPB_STAGE_WORDS], sR[SPB_STAGE_WORDS];
-  const u64 p0 = pos_lo + (u64)blockIdx.x * 256;
-  const bool any = p0 + k <= T;                      // otherwise no window of this block fits
-  const u64 plast = any ? (p0 + 255 + k <= T ? p0 + 255 : T - k) : p0;
-  const u64 fw0 = p0 >> 4, rw0 = any ? ((T - plast - k) >> 4) : 0;
-  SPB_PHASE_BEGIN(0)
-    if (any) {
-      const u32 nF = (u32)(((plast + k) >> 4) + 2 - fw0), nR = (u32)(((T - p0) >> 4) + 2 - rw0);
-      for (u32 i = threadIdx.x; i < nF; i += 256) sF[i] = __ldg(F + fw0 + i);
-      for (u32 i = threadIdx.x; i < nR; i += 256) sR[i] = __ldg(R + rw0 + i);
-    }
-  SPB_PHASE_END
-  SPB_PHASE_BEGIN(1)
-    const u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
-    const u64 p = pos_lo + i;
-    bool valid = p < pos_hi && p + k <= T && get_bit(vbits, p);
-    bool o = false;
-    u64 key = ~0ull;
-    if (valid) {
-      const u32 fa = (u32)(p - fw0 * 16), ra = (u32)((T - p - k) - rw0 * 16);
-      u32 lx = __funnelshift_l(sF[(fa >> 4) + 1], sF[fa >> 4], (fa & 15) * 2), ly = __funnelshift_l(sR[(ra >> 4) + 1], sR[ra >> 4], (ra & 15) * 2);
-      o = (lx != ly) ? (lx > ly) : (win_cmp(F, p, R, T - p - k, k) >= 0);
-      u64 h = o ? win_hash_s<W>(sF, fa, k) : win_hash_s<W>(sR, ra, k);
-      key = (h & ~1ull) | (o ? 1ull : 0ull);
-      if (key == ~0ull) key ^= 2ull;
-    }
-    keys[i] = key; pos[i] = (u32)p;
-    store_bit(obits, p, o);
-  SPB_PHASE_END
+  u64 i = SPB_GTID();
+  u64 p = pos_lo + i;
+  bool valid = p < pos_hi && get_bit(vbits, p);
+  bool o = false;
+  u64 key = ~0ull;
+  if (valid) {
+    u64 ra = T - p - k;
+    const u32* x = F + (p >> 4); const u32* y = R + (ra >> 4);
+    u32 lx = __funnelshift_l(__ldg(x + 1), __ldg(x), (u32)(p & 15) * 2), ly = __funnelshift_l(__ldg(y + 1), __ldg(y), (u32)(ra & 15) * 2);
+    o = (lx != ly) ? (lx > ly) : (win_cmp(F, p, R, ra, k) >= 0);
+    u64 h = win_hash<W>(o ? F : R, o ? p : ra, k);
+    key = (h & ~1ull) | (o ? 1ull : 0ull);
+    if (key == ~0ull) key ^= 2ull;
+  }
+  keys[i] = key; pos[i] = (u32)p;
+  store_bit(obits, p, o);
 }
 
 // Single-pass radix partition fused with the record generation (replaces k_make_records + a library radix pass on the
