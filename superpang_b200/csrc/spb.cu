@@ -30,7 +30,7 @@ struct spb_ctx {
   std::multimap<u64, void*> cache;     // freed blocks kept for reuse (steady state: no cudaMalloc at all)
   u64* pinned = 0;                     // pinned host scratch for scalar read-backs
 #ifndef SPB_EMU
-  cudaStream_t stream2 = 0; cudaEvent_t ev_fork = 0, ev_join = 0;    // second stream for the bucket loop (two L2 tables in flight)
+  cudaStream_t stream2[3] = {0, 0, 0}; cudaEvent_t ev_fork = 0, ev_join[3] = {0, 0, 0};   // extra streams for the bucket loops
 #endif
   // ---- persistent device state
   u64* seq_off = 0;
@@ -130,22 +130,25 @@ template <class T> static T dread(spb_ctx* c, const T* p) {
 // The bucket loops keep two L2-resident tables in flight: even buckets on the context's stream, odd ones on a second
 // stream (each bucket: clear its table, then insert).  fork/join order the second stream against the first.
 struct TwoStreams {
-  spb_stream_t st[2];
+  spb_stream_t st[4];
+  int n = 2;                                         // tables / streams in flight (SPB_STREAMS=1..4, default 2: 2 x 32 MB fit in L2)
 #ifdef SPB_EMU
-  explicit TwoStreams(spb_ctx* c) { st[0] = st[1] = c->stream; }
+  explicit TwoStreams(spb_ctx* c) { for (auto& x : st) x = c->stream; if (const char* e = getenv("SPB_STREAMS")) n = std::max(1, std::min(4, atoi(e))); }
   void clear(spb_ctx*, int, void* p, u64 bytes) { memset(p, 0xFF, bytes); }
   void join(spb_ctx*) {}
 #else
   explicit TwoStreams(spb_ctx* c) {
-    if (!c->stream2) {
-      cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
-      cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+    if (const char* e = getenv("SPB_STREAMS")) n = std::max(1, std::min(4, atoi(e)));
+    if (!c->stream2[0]) {
+      for (int i = 0; i < 3; ++i) { cudaStreamCreateWithFlags(&c->stream2[i], cudaStreamNonBlocking); cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming); }
+      cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     }
-    st[0] = c->stream; st[1] = c->stream2;
-    cudaEventRecord(c->ev_fork, c->stream); cudaStreamWaitEvent(c->stream2, c->ev_fork, 0);
+    st[0] = c->stream; for (int i = 1; i < 4; ++i) st[i] = c->stream2[i - 1];
+    cudaEventRecord(c->ev_fork, c->stream);
+    for (int i = 1; i < n; ++i) cudaStreamWaitEvent(st[i], c->ev_fork, 0);
   }
   void clear(spb_ctx*, int i, void* p, u64 bytes) { cudaMemsetAsync(p, 0xFF, bytes, st[i]); }
-  void join(spb_ctx* c) { cudaEventRecord(c->ev_join, c->stream2); cudaStreamWaitEvent(c->stream, c->ev_join, 0); }
+  void join(spb_ctx* c) { for (int i = 1; i < n; ++i) { cudaEventRecord(c->ev_join[i - 1], st[i]); cudaStreamWaitEvent(c->stream, c->ev_join[i - 1], 0); } }
 #endif
 };
 
@@ -373,7 +376,8 @@ static void reset_state(spb_ctx* c) {
   spb_ctx fresh;
   fresh.device = c->device; fresh.stream = c->stream; fresh.errflag = c->errflag; fresh.pinned = c->pinned;
 #ifndef SPB_EMU
-  fresh.stream2 = c->stream2; fresh.ev_fork = c->ev_fork; fresh.ev_join = c->ev_join;
+  for (int i = 0; i < 3; ++i) { fresh.stream2[i] = c->stream2[i]; fresh.ev_join[i] = c->ev_join[i]; }
+  fresh.ev_fork = c->ev_fork;
 #endif
   fresh.live.swap(c->live); fresh.cache.swap(c->cache);
   memset(&fresh.cnt, 0, sizeof fresh.cnt); memset(&fresh.nt, 0, sizeof fresh.nt);
@@ -393,7 +397,7 @@ void spb_destroy(spb_ctx* c) {
   free(c->pinned);
 #else
   cudaFreeHost(c->pinned);
-  if (c->stream2) { cudaStreamDestroy(c->stream2); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
+  if (c->stream2[0]) { for (int i = 0; i < 3; ++i) { cudaStreamDestroy(c->stream2[i]); cudaEventDestroy(c->ev_join[i]); } cudaEventDestroy(c->ev_fork); }
 #endif
   delete c;
 }
@@ -654,16 +658,17 @@ static int dedup_staged_links(spb_ctx* c) {
   for (u32 b = 0; b < B; ++b) nmax = std::max(nmax, bn[b]);
   u64 cap = 1024; while (cap < 2 * nmax) cap <<= 1;
   c->cnt.table_slots = cap;
-  u64* scratch[2]; ALLOC(scratch[0], u64, cap); ALLOC(scratch[1], u64, cap);
+  u64* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
   u32 *seenpos, *dupbits; ALLOC(seenpos, u32, P + 8); ALLOC(dupbits, u32, P / 32 + 8);
   dev_memset(c, dupbits, 0, (P / 32 + 8) * 4);
   {
     TwoStreams ts(c);
+    for (int i = 0; i < ts.n; ++i) ALLOC(scratch[i], u64, cap);
     u32 step = 0;
     for (u32 b = 0; b < B; ++b) {
       u64 lo = blo[b], n = bn[b];
       if (n == 0) continue;
-      const int i = step & 1;
+      const int i = step % ts.n;
       ts.clear(c, i, scratch[i], cap * 8);
       SPB_LAUNCH(k_bkt_insert_links, nblk(n, TPB), TPB, ts.st[i], c->dd_keys, c->dd_pos, lo, n, c->F, c->R, T, c->k, scratch[i], cap - 1, seenpos,
                  dupbits, (u64*)nullptr, 0);
@@ -671,7 +676,7 @@ static int dedup_staged_links(spb_ctx* c) {
     }
     ts.join(c);
   }
-  dfree(c, scratch[0]); dfree(c, scratch[1]);
+  for (auto& x : scratch) dfree(c, x);
   dfree(c, c->dd_keys); dfree(c, c->dd_pos);
   snprintf(b2, sizeof b2, "\"bucket_dedup_ms\": %.4f, ", tk.stop(c)); c->stats += b2;
   u64 nb = P / 256, nw32 = P / 32;
@@ -901,7 +906,7 @@ int spb_mg_dedup_links(spb_ctx* c, uint64_t* keys_io, uint32_t* pos_io, uint64_t
   for (u32 b = 0; b < B; ++b) nmax = std::max(nmax, bstart[b + 1] - bstart[b]);
   u64 cap = 1024; while (cap < 2 * nmax) cap <<= 1;
   c->cnt.table_slots = cap;
-  u64* scratch[2]; ALLOC(scratch[0], u64, cap); ALLOC(scratch[1], u64, cap);
+  u64* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
   u64* nlinks; ALLOC(nlinks, u64, 2); dev_memset(c, nlinks, 0, 16);
   u64 lcap = std::max<u64>(4096, n_total / 8);
   u64* links = nullptr; u64 nl = 0;
@@ -910,11 +915,12 @@ int spb_mg_dedup_links(spb_ctx* c, uint64_t* keys_io, uint32_t* pos_io, uint64_t
     dev_memset(c, nlinks, 0, 16);
     {
       TwoStreams ts(c);
+      for (int i = 0; i < ts.n; ++i) if (!scratch[i]) ALLOC(scratch[i], u64, cap);
       u32 step = 0;
       for (u32 b = 0; b < B; ++b) {
         u64 lo = bstart[b], n = bstart[b + 1] - lo;
         if (n == 0) continue;
-        const int i = step & 1;
+        const int i = step % ts.n;
         ts.clear(c, i, scratch[i], cap * 8);
         SPB_LAUNCH(k_bkt_insert_list, nblk(n, TPB), TPB, ts.st[i], keys, pos, lo, n, c->F, c->R, c->T, c->k, scratch[i], cap - 1, links, nlinks, lcap,
                    (u64*)nullptr, 0);
@@ -926,7 +932,8 @@ int spb_mg_dedup_links(spb_ctx* c, uint64_t* keys_io, uint32_t* pos_io, uint64_t
     if (nl <= lcap) break;
     dfree(c, links); lcap = nl;
   }
-  dfree(c, scratch[0]); dfree(c, scratch[1]); dfree(c, nlinks); dfree(c, coff); dfree(c, sub);
+  for (auto& x : scratch) dfree(c, x);
+  dfree(c, nlinks); dfree(c, coff); dfree(c, sub);
   dfree(c, k2a); dfree(c, p2a);
   if (getenv("SPB_DEBUG")) fprintf(stderr, "[spb] dedup_links: n_total=%llu B=%u cap=%llu links=%llu\n", (unsigned long long)n_total, B, (unsigned long long)cap, (unsigned long long)nl);
   // sort by position, resolve chains, split by destination rank
