@@ -466,7 +466,7 @@ static int alloc_position_state(spb_ctx* c, u64 min_positions = 0) {
 }
 
 // S1: records of the positions [pos_lo, pos_hi) (pos_lo a multiple of 256), partitioned by the top `bb` hash bits
-static int dd_records(spb_ctx* c, u64 pos_lo, u64 pos_hi, u32 bb, u64 min_positions = 0) {
+static int dd_records(spb_ctx* c, u64 pos_lo, u64 pos_hi, u32 bb, u64 min_positions = 0, u32 spread = 0) {
   int r0 = alloc_position_state(c, min_positions); if (r0) return r0;
   if (pos_hi < pos_lo) pos_hi = pos_lo;
   u64 n = nblk(pos_hi - pos_lo, TPB) * TPB;
@@ -474,10 +474,10 @@ static int dd_records(spb_ctx* c, u64 pos_lo, u64 pos_hi, u32 bb, u64 min_positi
   ALLOC(keys, u64, n); ALLOC(pos, u32, n);
   u64 grid = n / TPB;
   switch ((2 * c->k + 31) / 32) {
-    case 7:  SPB_LAUNCH(k_make_records<7>, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, keys, pos, c->obits); break;
-    case 19: SPB_LAUNCH(k_make_records<19>, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, keys, pos, c->obits); break;
-    case 32: SPB_LAUNCH(k_make_records<32>, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, keys, pos, c->obits); break;
-    default: SPB_LAUNCH(k_make_records<0>, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, keys, pos, c->obits); break;
+    case 7:  SPB_LAUNCH(k_make_records<7>, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, keys, pos, c->obits, spread); break;
+    case 19: SPB_LAUNCH(k_make_records<19>, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, keys, pos, c->obits, spread); break;
+    case 32: SPB_LAUNCH(k_make_records<32>, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, keys, pos, c->obits, spread); break;
+    default: SPB_LAUNCH(k_make_records<0>, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, keys, pos, c->obits, spread); break;
   }
   if (bb > 0) {
     ALLOC(keys2, u64, n); ALLOC(pos2, u32, n);
@@ -688,6 +688,41 @@ static int dedup_staged_links(spb_ctx* c) {
   return r;
 }
 
+// Two-level partitioned dedup with shared-memory tables (see k_smem_dedup): records radix-sorted on the top hash bits
+// into sub-buckets of ~7.6 K records, one CTA per sub-bucket.  Returns 1 when the input does not suit it (a sub-bucket
+// beyond the table: masses of identical k-mers) -- the caller then takes the L2-table path.
+static int dedup_smem_links(spb_ctx* c) {
+  const u64 T = c->T, P = c->npos_pad;
+  u64 avg = 7680;
+  if (const char* e = getenv("SPB_SMEM_AVG")) avg = std::max(1, atoi(e));       // tests: many tiny sub-buckets
+  u32 nbits = 0; while ((P >> nbits) > avg) ++nbits;
+  if (nbits > 24) return 1;
+  StageTimer tk; char b2[160];
+  tk.start(c);
+  PRIM(dd_records(c, 0, T, nbits, 0, 1));
+  snprintf(b2, sizeof b2, "\"records_partition_ms\": %.4f, ", tk.stop(c)); c->stats += b2;
+  tk.start(c);
+  const u64 NB = 1ull << nbits;
+  u32 *seenpos, *dupbits; ALLOC(seenpos, u32, P + 8); ALLOC(dupbits, u32, P / 32 + 8);
+  dev_memset(c, dupbits, 0, (P / 32 + 8) * 4);
+  u64 nmax = 0;
+  for (u64 b = 0; b < NB; ++b) nmax = std::max(nmax, c->dd_bstart_h[b + 1] - c->dd_bstart_h[b]);
+  if (nmax <= SPB_ST_LIMIT)
+    SPB_LAUNCH_PHASED_DSMEM(k_smem_dedup, 2, NB, 512, SPB_ST_SLOTS * 4, c->stream, c->dd_keys, c->dd_pos, c->dd_bstart, c->F, c->R, T, c->k, nbits,
+                            seenpos, dupbits, c->errflag);
+  dfree(c, c->dd_keys); dfree(c, c->dd_pos); dfree(c, c->dd_bstart);
+  if (nmax > SPB_ST_LIMIT) { dfree(c, seenpos); dfree(c, dupbits); return 1; }
+  c->cnt.table_slots = SPB_ST_SLOTS;
+  snprintf(b2, sizeof b2, "\"bucket_dedup_ms\": %.4f, \"smem_tables\": %llu, ", tk.stop(c), NB); c->stats += b2;
+  u64 nb = P / 256, nw32 = P / 32;
+  SPB_LAUNCH(k_first_bits, nblk(nb, TPB), TPB, c->stream, c->vbits, dupbits, c->fbits, nb);     // first = valid and not linked
+  dev_memset(c, c->fbits + nw32, 0, 32);
+  dfree(c, dupbits);
+  int r = dd_ids(c, 0, T, nullptr, 1, seenpos, 1);
+  dfree(c, seenpos);
+  return r;
+}
+
 // the older single-table dedup (two random HBM accesses per instance); kept selectable for A/B measurements
 static int dedup_global_table(spb_ctx* c, bool allow_switch) {
   const u64 T = c->T;
@@ -752,16 +787,19 @@ int spb_build_dbg(spb_ctx* c, spb_counts* out) {
   // path (records -> buckets -> L2 scratch tables -> scatter back); measured slower on one GPU in round 1
   // (profiles/README.md), its stages are what the multi-GPU exchange is built from.
   const char* mode = getenv("SPB_DEDUP");          // global | links | staged  (default: adaptive global -> links)
-  if (mode && !strcmp(mode, "links")) {
+  if (mode && (!strcmp(mode, "links") || !strcmp(mode, "smem"))) {
     tm.start(c);
-    PRIM(dedup_staged_links(c));
+    int rc = strcmp(mode, "smem") ? 1 : dedup_smem_links(c);
+    if (rc == 1) { c->stats = "{"; rc = dedup_staged_links(c); }
+    if (rc) return rc;
     snprintf(buf, sizeof buf, "\"dedup_links_ms\": %.4f", tm.stop(c)); c->stats += buf;
   } else if (!(mode && !strcmp(mode, "staged"))) {
     tm.start(c);
     int rc = dedup_global_table(c, !mode);            // also reports k_extract_insert_ms (the kernel alone)
     if (rc == 1) {
       c->stats = "{\"switched_to_links\": 1, ";
-      rc = dedup_staged_links(c);
+      rc = getenv("SPB_NO_SMEM_TABLES") ? 1 : dedup_smem_links(c);
+      if (rc == 1) { c->stats = "{\"switched_to_links\": 1, "; rc = dedup_staged_links(c); }
     }
     if (rc) return rc;
     snprintf(buf, sizeof buf, "\"dedup_global_ms\": %.4f", tm.stop(c)); c->stats += buf;

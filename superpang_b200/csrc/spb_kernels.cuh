@@ -353,9 +353,15 @@ k_extract_insert(const u32* __restrict__ F, const u32* __restrict__ R, const u32
 // that writes to one sector happen close together in time and merge in L2.  With several GPUs the
 // buckets are the unit of ownership: S1 and S3 run on the GPU that owns the positions, S2 on the GPU
 // that owns the bucket, with an all-to-all of records before and of representatives after S2.
+__device__ __forceinline__ u64 mix64(u64 x) {
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+  return x;
+}
+// spread = 1: positions that start no k-mer get a pseudo-random key and the position SPB_INVALID (they spread evenly
+// over the sub-buckets of the two-level path instead of piling up in the last one); spread = 0: key ~0.
 template <int W> __global__ void SPB_LAUNCH_BOUNDS(256)
 k_make_records(const u32* __restrict__ F, const u32* __restrict__ R, const u32* __restrict__ vbits, u64 T, u32 k,
-               u64 pos_lo, u64 pos_hi, u64* __restrict__ keys, u32* __restrict__ pos, u32* obits) {
+               u64 pos_lo, u64 pos_hi, u64* __restrict__ keys, u32* __restrict__ pos, u32* obits, u32 spread) {
   u64 i = SPB_GTID();
   u64 p = pos_lo + i;
   bool valid = p < pos_hi && get_bit(vbits, p);
@@ -370,7 +376,8 @@ k_make_records(const u32* __restrict__ F, const u32* __restrict__ R, const u32* 
     key = (h & ~1ull) | (o ? 1ull : 0ull);
     if (key == ~0ull) key ^= 2ull;
   }
-  keys[i] = key; pos[i] = (u32)p;
+  if (spread && !valid) { keys[i] = mix64(p); pos[i] = SPB_INVALID; }
+  else { keys[i] = key; pos[i] = (u32)p; }
   store_bit(obits, p, o);
 }
 
@@ -571,6 +578,98 @@ k_bkt_insert_links(const u64* __restrict__ keys, const u32* __restrict__ pos, u6
   }
   u64 stride = (u64)gridDim.x * blockDim.x;
   for (u64 j = t; j < clear_n; j += stride) clear[j] = SPB_EMPTY;
+}
+
+// ------------------------------------------------------------------------------------ shared-memory tables
+// Two-level form of the "links" dedup: the records are radix-sorted on the top `nbits` hash bits into sub-buckets of
+// ~7.6 K records, and one CTA deduplicates a sub-bucket in a hash table in shared memory -- no global atomics at all,
+// the records stream through once.  slot = tag (18 hash bits) << 14 | index of the record inside the sub-bucket; the
+// sort is stable, so index order is position order and atomicMin on a slot keeps the first appearance.  Exceptions
+// leave links exactly as in k_bkt_insert_links.  Records are loaded four at a time per thread (independent loads in
+// flight) before their inserts.
+#define SPB_ST_SLOTS 16384u          // 64 KB of shared memory: three CTAs per SM
+#define SPB_ST_LIMIT 12288u          // records per sub-bucket the table accepts (load <= 0.75); more -> caller falls back
+#define SPB_ST_EMPTY 0xFFFFFFFFu
+#ifndef SPB_ST_BATCH
+#define SPB_ST_BATCH 4
+#endif
+#ifndef SPB_ST_MINB
+#define SPB_ST_MINB 3
+#endif
+template <class V> __device__ __forceinline__ V st_pick(const V (&a)[SPB_ST_BATCH], u32 u) {   // a[u] without local memory
+  V r = a[0];
+#pragma unroll
+  for (u32 j = 1; j < SPB_ST_BATCH; ++j) if (u == j) r = a[j];
+  return r;
+}
+__global__ void SPB_LAUNCH_BOUNDS2(512, SPB_ST_MINB)
+k_smem_dedup(const u64* __restrict__ keys, const u32* __restrict__ pos, const u64* __restrict__ sub, const u32* __restrict__ F,
+             const u32* __restrict__ R, u64 T, u32 k, u32 nbits, u32* __restrict__ seenpos, u32* dupbits, u32* err) {
+  SPB_DYN_SHARED(u32, tab, SPB_ST_SLOTS);
+  const u64 seg0 = sub[blockIdx.x];
+  const u64 n64 = sub[blockIdx.x + 1] - seg0;
+  if (n64 == 0) return;                              // uniform over the block
+  if (n64 > SPB_ST_LIMIT) { if (threadIdx.x == 0) atomicOr(err, (u32)ERR_OVERFLOW); return; }
+  const u32 n = (u32)n64;
+  SPB_PHASE_BEGIN(0)
+    for (u32 s = threadIdx.x * 4; s < SPB_ST_SLOTS; s += blockDim.x * 4) { tab[s] = SPB_ST_EMPTY; tab[s + 1] = SPB_ST_EMPTY; tab[s + 2] = SPB_ST_EMPTY; tab[s + 3] = SPB_ST_EMPTY; }
+  SPB_PHASE_END
+  SPB_PHASE_BEGIN(1)
+    for (u32 base = 0; base < n; base += blockDim.x * SPB_ST_BATCH) {
+      u64 kk[SPB_ST_BATCH]; u32 pp[SPB_ST_BATCH];
+#pragma unroll
+      for (u32 u = 0; u < SPB_ST_BATCH; ++u) {
+        const u32 i = base + u * blockDim.x + threadIdx.x;
+        pp[u] = i < n ? pos[seg0 + i] : SPB_INVALID;
+        kk[u] = i < n ? keys[seg0 + i] : 0ull;
+      }
+      // A lane takes its next record as soon as the current one is placed, so a warp iterates max-over-lanes of the
+      // SUM of the probe lengths of a batch, not the sum of the maxima (linear probing has a long tail).  The loop
+      // exit is warp-uniform, which keeps the lanes converged at the atomic.
+      u32 u = 0, s = 0, tag = 0, v = 0;
+      u64 key = 0, p = 0;
+      bool active = false;
+      for (;;) {
+        if (!active && u < SPB_ST_BATCH) {
+          key = st_pick(kk, u); p = st_pick(pp, u);
+          const u32 i = base + u * blockDim.x + threadIdx.x;
+          ++u;
+          if ((u32)p != SPB_INVALID) {                 // else: past the end, or a position that starts no k-mer
+            const u64 rem = key << nbits;              // hash bits below the sub-bucket bits: 14 -> home slot, next 18 -> tag
+            s = (u32)(rem >> 50);
+            tag = (u32)(rem >> 32) & 0x3FFFFu; v = (tag << 14) | i;
+            active = true;
+          }
+        }
+        if (active) {
+          const u32 old = atomicCAS(&tab[s], SPB_ST_EMPTY, v);
+          if (old == SPB_ST_EMPTY) active = false;
+          else {
+            bool same = false;
+            if ((old >> 14) == tag) {
+              const u64 rq = seg0 + (old & 0x3FFFu);
+              const u64 q = pos[rq];
+              const bool o = key & 1, oq = keys[rq] & 1;
+              if (win_cmp(o ? F : R, o ? p : T - p - k, oq ? F : R, oq ? q : T - q - k, k) == 0) {
+                u64 from = p, to = q;                 // default: we link to the installed record
+                if (v < old) {
+                  const u32 prev = atomicMin(&tab[s], v);
+                  const u64 pq = pos[seg0 + (prev & 0x3FFFu)];
+                  if (prev > v) { from = pq; to = p; }  // we displaced it: it links to us
+                  else to = pq;
+                }
+                seenpos[from] = (u32)to;
+                atomicOr(dupbits + (from >> 5), 1u << (from & 31));
+                same = true;
+              }
+            }
+            if (same) active = false; else s = (s + 1) & (SPB_ST_SLOTS - 1);
+          }
+        }
+        if (__all_sync(0xffffffffu, !active && u >= SPB_ST_BATCH)) break;
+      }
+    }
+  SPB_PHASE_END
 }
 
 // Owner side of the multi-GPU "links" protocol: like k_bkt_insert_links, but the links are appended to a list

@@ -25,6 +25,7 @@ typedef uint8_t u8;
 #define __forceinline__ inline
 #define __restrict__
 #define SPB_LAUNCH_BOUNDS(n)
+#define SPB_LAUNCH_BOUNDS2(n, m)
 struct spb_emu_dim3 { unsigned x = 1, y = 1, z = 1; };
 static spb_emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 typedef void* spb_stream_t;
@@ -68,6 +69,9 @@ template <class F> static inline void spb_emu_launch_phased(int nph, size_t nb, 
 }
 #define SPB_LAUNCH_PHASED(K, NPH, NB, NT, STREAM, ...) \
   do { if ((NB) > 0) { ++g_spb_launches; spb_emu_launch_phased((NPH), (size_t)(NB), (unsigned)(NT), [&]() { K(__VA_ARGS__); }); } } while (0)
+// block-cooperative kernel whose shared array exceeds the static limit (dynamic shared memory on the GPU)
+#define SPB_DYN_SHARED(type, name, n) static type name[n]
+#define SPB_LAUNCH_PHASED_DSMEM(K, NPH, NB, NT, SMEM, STREAM, ...) SPB_LAUNCH_PHASED(K, NPH, NB, NT, STREAM, __VA_ARGS__)
 static inline u64 atomicCAS(u64* a, u64 cmp, u64 val) { u64 o = *a; if (o == cmp) *a = val; return o; }
 static inline u32 atomicCAS(u32* a, u32 cmp, u32 val) { u32 o = *a; if (o == cmp) *a = val; return o; }
 static inline u64 atomicMin(u64* a, u64 v) { u64 o = *a; if (v < o) *a = v; return o; }
@@ -75,6 +79,7 @@ static inline u32 atomicMin(u32* a, u32 v) { u32 o = *a; if (v < o) *a = v; retu
 static inline u64 atomicAdd(u64* a, u64 v) { u64 o = *a; *a = o + v; return o; }
 static inline u32 atomicAdd(u32* a, u32 v) { u32 o = *a; *a = o + v; return o; }
 static inline u32 atomicOr(u32* a, u32 v) { u32 o = *a; *a = o | v; return o; }
+static inline int __all_sync(unsigned, int p) { return p; }     // one emulated thread at a time
 static inline int __popcll(u64 x) { return __builtin_popcountll(x); }
 static inline u32 __funnelshift_l(u32 lo, u32 hi, u32 sh) { sh &= 31; return sh ? (hi << sh) | (lo >> (32 - sh)) : hi; }
 static inline int __popc(u32 x) { return __builtin_popcount(x); }
@@ -87,6 +92,7 @@ template <class T> static inline T __ldcg(const T* p) { return *p; }
 // ---------------------------------------------------------------- CUDA (sm_100a)
 #include <cuda_runtime.h>
 #define SPB_LAUNCH_BOUNDS(n) __launch_bounds__(n)
+#define SPB_LAUNCH_BOUNDS2(n, m) __launch_bounds__(n, m)
 typedef cudaStream_t spb_stream_t;
 #define SPB_LAUNCH(K, NB, NT, STREAM, ...) \
   do { if ((NB) > 0) { ++g_spb_launches; K<<<(unsigned)(NB), (unsigned)(NT), 0, (STREAM)>>>(__VA_ARGS__); } } while (0)
@@ -94,6 +100,11 @@ typedef cudaStream_t spb_stream_t;
 #define SPB_PHASE_BEGIN(n) { if ((n) > 0) __syncthreads();
 #define SPB_PHASE_END }
 #define SPB_LAUNCH_PHASED(K, NPH, NB, NT, STREAM, ...) SPB_LAUNCH(K, NB, NT, STREAM, __VA_ARGS__)
+#define SPB_DYN_SHARED(type, name, n) extern __shared__ type name[]
+#define SPB_LAUNCH_PHASED_DSMEM(K, NPH, NB, NT, SMEM, STREAM, ...) \
+  do { if ((NB) > 0) { ++g_spb_launches; cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)); \
+       cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+       K<<<(unsigned)(NB), (unsigned)(NT), (SMEM), (STREAM)>>>(__VA_ARGS__); } } while (0)
 #endif
 
 // global linear thread id (64-bit)

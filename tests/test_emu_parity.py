@@ -107,6 +107,10 @@ VARIANTS = [
     {"SPB_DEDUP": "links", "SPB_BUCKET_BITS": "0", "SPB_EMU_ORDER": "reverse"},   # displacement chains
     {"SPB_DEDUP": "links", "SPB_BUCKET_BITS": "5", "SPB_EMU_ORDER": "shuffle"},
     {"SPB_DEDUP": "links", "SPB_BUCKET_BITS": "4", "SPB_PARTITION_FUSED": "1", "SPB_EMU_ORDER": "shuffle"},   # block-phased partition kernel
+    {"SPB_DEDUP": "smem"},                                           # shared-memory tables, one sub-bucket
+    {"SPB_DEDUP": "smem", "SPB_SMEM_AVG": "300", "SPB_EMU_ORDER": "reverse"},    # several sub-buckets; larger index installs first
+    {"SPB_DEDUP": "smem", "SPB_SMEM_AVG": "40", "SPB_EMU_ORDER": "shuffle"},
+    {"SPB_DEDUP": "smem", "SPB_SMEM_AVG": "1"},                      # absurd split: few hash bits left -> falls back or clusters
 ]
 
 

@@ -139,6 +139,8 @@ def test_gpu_properties_at_scale(mode):
     {"SPB_ANCHOR": "0", "SPB_CHUNK_BITS": "12"},
     {"SPB_DEDUP": "staged", "SPB_BUCKET_BITS": "4"},   # partitioned dedup, 16 buckets
     {"SPB_DEDUP": "links", "SPB_BUCKET_BITS": "4"},    # partitioned dedup, exceptions as links
+    {"SPB_DEDUP": "smem"},                             # shared-memory tables
+    {"SPB_DEDUP": "smem", "SPB_SMEM_AVG": "50"},       # ... many small sub-buckets
 ], ids=lambda e: ",".join(f"{k[4:].lower()}={v}" for k, v in e.items()))
 def test_gpu_dedup_variants(monkeypatch, env):
     """Every dedup strategy must give the reference's result (they differ only in how the table is reached)."""
@@ -180,7 +182,7 @@ def test_gpu_dedup_strategies_agree_at_scale(monkeypatch, mode):
     buf, off = concat_sequences(seqs)
 
     def run(env):
-        for k_ in ("SPB_DEDUP", "SPB_ANCHOR", "SPB_BUCKET_BITS", "SPB_CHUNK_BITS"):
+        for k_ in ("SPB_DEDUP", "SPB_ANCHOR", "SPB_BUCKET_BITS", "SPB_CHUNK_BITS", "SPB_SMEM_AVG"):
             monkeypatch.delenv(k_, raising=False)
         for k_, v in env.items():
             monkeypatch.setenv(k_, v)
@@ -197,5 +199,7 @@ def test_gpu_dedup_strategies_agree_at_scale(monkeypatch, mode):
     ref = run({"SPB_DEDUP": "global", "SPB_ANCHOR": "0"})
     assert run({"SPB_DEDUP": "global", "SPB_ANCHOR": "1"}) == ref
     assert run({"SPB_DEDUP": "links"}) == ref
+    assert run({"SPB_DEDUP": "smem"}) == ref
+    assert run({"SPB_DEDUP": "smem", "SPB_SMEM_AVG": "2000"}) == ref
     assert run({"SPB_DEDUP": "staged"}) == ref
     assert run({}) == ref
