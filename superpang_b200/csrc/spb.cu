@@ -724,9 +724,45 @@ static int dedup_smem_links(spb_ctx* c) {
 }
 
 // the older single-table dedup (two random HBM accesses per instance); kept selectable for A/B measurements
+// The choice between the dedup schemes is made on two sample chunks of positions -- the first CH positions and CH
+// positions from the middle of the input (another genome, in a genome set) -- through a table sized for them alone
+// (the full-size table of the global scheme is several GB: clearing it just to find out that the partitioned scheme
+// applies would cost more than the probe).  Returns the number of extended / duplicate positions of the second chunk.
+static int probe_sample_chunks(spb_ctx* c, u64 CH, u64* n_ext, u64* n_dup, u64* chunk_n) {
+  const u64 P = c->npos_pad;
+  u64 mid = (P / 2) / CH * CH;                       // chunk-aligned, so the bitmaps shift by whole words
+  if (mid < CH) mid = CH;
+  const u64 hi = std::min(P, mid + CH);
+  if (hi <= mid) { *n_ext = *n_dup = 0; *chunk_n = 0; return 0; }
+  const u64 shift = mid - CH;                        // position p of the second chunk is kept at index p - shift
+  u64 cap = 1024; while (cap < 4 * CH) cap <<= 1;
+  u64 *slots, *arec, *extc; u32 *wbits, *dbits, *seenpos;
+  const u64 nbw = 2 * CH / 32 + 8;
+  ALLOC(slots, u64, cap); ALLOC(arec, u64, nbw); ALLOC(extc, u64, 2);
+  ALLOC(wbits, u32, nbw); ALLOC(dbits, u32, nbw); ALLOC(seenpos, u32, 2 * CH + 8);
+  dev_memset(c, slots, 0xFF, cap * 8); dev_memset(c, extc, 0, 16);
+  dev_memset(c, dbits, 0, nbw * 4); dev_memset(c, wbits, 0, nbw * 4);
+  launch_extract_k(c, 0, CH, slots, cap, seenpos, wbits, dbits, nullptr, nullptr);
+  launch_extract_k(c, mid, hi, slots, cap, seenpos - shift, wbits - shift / 32, dbits - shift / 32, arec - shift / 32, extc);
+  *n_ext = dread(c, extc); *n_dup = dread(c, extc + 1); *chunk_n = hi - mid;
+  dfree(c, slots); dfree(c, arec); dfree(c, extc); dfree(c, wbits); dfree(c, dbits); dfree(c, seenpos);
+  return 0;
+}
+
 static int dedup_global_table(spb_ctx* c, bool allow_switch) {
   const u64 T = c->T;
   int r0 = alloc_position_state(c); if (r0) return r0;
+  int decided = 0;
+  u64 CH = 1ull << 22, switch_min = 64ull << 20;
+  if (const char* e = getenv("SPB_CHUNK_BITS")) { int b = atoi(e); if (b >= 8 && b <= 32) CH = 1ull << b; }   // tests: tiny chunks
+  if (const char* e = getenv("SPB_SWITCH_MIN")) switch_min = strtoull(e, nullptr, 10);                        // tests: small inputs switch too
+  if (allow_switch && c->n_inst >= switch_min && !getenv("SPB_ANCHOR") && c->npos_pad > CH) {
+    u64 n_ext = 0, n_dup = 0, chunk_n = 1;
+    PRIM(probe_sample_chunks(c, std::max<u64>(CH / 2, 256), &n_ext, &n_dup, &chunk_n));
+    decided = (double)n_ext >= 0.25 * (double)chunk_n ? 2 : -1;
+    // partitioned dedup only pays when almost nothing is duplicated (every duplicate costs it a scattered write)
+    if (decided < 0 && (double)n_dup < 0.02 * (double)chunk_n) return 1;
+  }
   u64 cap = 1024; while (cap < 2 * c->n_inst) cap <<= 1;
   c->cnt.table_slots = cap;
   u64* slots; ALLOC(slots, u64, cap);
@@ -738,14 +774,12 @@ static int dedup_global_table(spb_ctx* c, bool allow_switch) {
   // scheme is tried: if the second chunk extends well (genome sets that share long stretches: the realistic case), all
   // remaining chunks use it, each seeing the complete table of the chunks before it; otherwise (nearly all k-mers
   // unique) the rest is one plain launch.  The result is the same either way.
-  u64 CH = 1ull << 22;
-  if (const char* e = getenv("SPB_CHUNK_BITS")) { int b = atoi(e); if (b >= 8 && b <= 32) CH = 1ull << b; }   // tests: tiny chunks
   const u64 P = c->npos_pad;
   u64 nA = P / 32;
   u32* seenpos; u64 *arec, *extc; ALLOC(seenpos, u32, P + 8); ALLOC(arec, u64, nA + 8); ALLOC(extc, u64, 2);
   dev_memset(c, extc, 0, 16);
   StageTimer tk; tk.start(c);
-  int anchored = 0;
+  int anchored = decided;
   if (const char* e = getenv("SPB_ANCHOR")) anchored = atoi(e) ? 2 : -1;      // 1 = force on, 0 = force off (A/B measurements, tests)
   u64 done = std::min(P, CH);
   launch_extract_k(c, 0, done, slots, cap, seenpos, wbits, dbits, nullptr, nullptr);
@@ -756,7 +790,7 @@ static int dedup_global_table(spb_ctx* c, bool allow_switch) {
     if (anchored == 0) anchored = (double)n_ext >= 0.25 * (double)chunk_n ? 1 : -1;
     done = hi;
     // partitioned dedup only pays when almost nothing is duplicated (every duplicate costs it a scattered write)
-    if (anchored < 0 && allow_switch && c->n_inst >= (64ull << 20) && (double)n_dup < 0.02 * (double)chunk_n) {
+    if (anchored < 0 && allow_switch && c->n_inst >= switch_min && (double)n_dup < 0.02 * (double)chunk_n) {
       // mostly unique k-mers and a table far beyond L2: the partitioned "links" dedup is faster; start over with it
       dfree(c, arec); dfree(c, extc); dfree(c, seenpos); dfree(c, slots); dfree(c, wbits); dfree(c, dbits);
       return 1;

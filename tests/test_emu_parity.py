@@ -110,6 +110,8 @@ VARIANTS = [
     {"SPB_DEDUP": "smem"},                                           # shared-memory tables, one sub-bucket
     {"SPB_DEDUP": "smem", "SPB_SMEM_AVG": "300", "SPB_EMU_ORDER": "reverse"},    # several sub-buckets; larger index installs first
     {"SPB_DEDUP": "smem", "SPB_SMEM_AVG": "40", "SPB_EMU_ORDER": "shuffle"},
+    {"SPB_SWITCH_MIN": "1", "SPB_CHUNK_BITS": "8", "SPB_SMEM_AVG": "100"},   # adaptive default: small-table probe, then one of the three schemes
+    {"SPB_SWITCH_MIN": "1", "SPB_CHUNK_BITS": "9", "SPB_NO_SMEM_TABLES": "1", "SPB_EMU_ORDER": "reverse"},
     {"SPB_DEDUP": "smem", "SPB_SMEM_AVG": "1"},                      # absurd split: few hash bits left -> falls back or clusters
 ]
 
