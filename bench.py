@@ -246,7 +246,9 @@ def main():
         ni, nv, nbb = counts["n_inst"], counts["n_vertices"], counts["nbp_bases"]
         groups = {
             "k_extract_insert (canonical k-mer extraction + exact dedup insert)": (("k_extract_insert_ms",), 16 * W * ni + 8 * W * nv),
-            "partitioned dedup (k_make_records + radix partition + k_bkt_insert_links, 256 launches)":
+            ("partitioned-smem dedup (k_make_records + 16-bit radix sort + k_smem_dedup: one CTA and one shared-memory table per sub-bucket)"
+             if "smem_tables" in st_mean else
+             "partitioned dedup (k_make_records + radix partition + k_bkt_insert_links, 256 launches)"):
                 (("records_partition_ms", "bucket_dedup_ms"), 16 * W * ni + 8 * W * nv),
             "multi-GPU dedup (records, all-to-all, owner dedup, scatter)":
                 (("mg_records_partition_ms", "mg_exchange_records_ms", "mg_owner_dedup_ms", "mg_exchange_reps_ms", "mg_scatter_ms"),

@@ -473,6 +473,19 @@ static int dd_records(spb_ctx* c, u64 pos_lo, u64 pos_hi, u32 bb, u64 min_positi
   u64 *keys, *keys2; u32 *pos, *pos2;
   ALLOC(keys, u64, n); ALLOC(pos, u32, n);
   u64 grid = n / TPB;
+  if (!getenv("SPB_NO_ROLL")) {
+    // rolling polynomial hashes: two odd multipliers = 5 (mod 8) (multiplicative order 2^30), inverses by Newton iteration
+    RollK K;
+    K.B[0] = 0x9E3779B5u; K.B[1] = 0x85EBCA6Du;
+    for (int h = 0; h < 2; ++h) {
+      const u32 B = K.B[h];
+      u32 inv = B; for (int it = 0; it < 5; ++it) inv *= 2u - B * inv;
+      u32 pw = 1, sq = B; for (u32 e = c->k - 1; e; e >>= 1) { if (e & 1) pw *= sq; sq *= sq; }
+      K.Binv[h] = inv; K.Bk1[h] = pw; K.negBk[h] = 0u - pw * B; K.negBinv[h] = 0u - inv;
+    }
+    SPB_LAUNCH(k_make_records_roll, nblk(n / SPB_RUN, 128), 128, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, n, keys, pos, c->obits,
+               spread, K);
+  } else
   switch ((2 * c->k + 31) / 32) {
     case 7:  SPB_LAUNCH(k_make_records<7>, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, keys, pos, c->obits, spread); break;
     case 19: SPB_LAUNCH(k_make_records<19>, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, keys, pos, c->obits, spread); break;
@@ -573,15 +586,21 @@ static int dd_graph(spb_ctx* c) {
   u64* jcount; ALLOC(jcount, u64, 2);
   u64 jcap = std::max<u64>(4096, c->n_inst / 8);
   u64* Jk = nullptr; u8* Js = nullptr; u64 nj = 0;
+  u32* vobits = nullptr;
+  if (c->n_inst - nV > nV / 4) {                     // many repeated instances: per-vertex orientation bits pay off
+    ALLOC(vobits, u32, nV / 32 + 8);
+    dev_memset(c, vobits, 0, (nV / 32 + 8) * 4);
+    SPB_LAUNCH(k_vertex_obits, std::min<u64>(nblk(nV, TPB), 148 * 16), TPB, c->stream, c->v2pos, c->obits, (u32)nV, vobits);
+  }
   for (int attempt = 0; attempt < 2; ++attempt) {
     ALLOC(Jk, u64, jcap); ALLOC(Js, u8, jcap);
     dev_memset(c, jcount, 0, 16);
-    SPB_LAUNCH(k_junction_emit, std::min<u64>(nblk(T, TPB), 148 * 16), TPB, c->stream, c->sp, T, c->fbits, c->vflags, c->v2pos, c->obits, Jk, Js, jcount, jcap);
+    SPB_LAUNCH(k_junction_emit, std::min<u64>(nblk(T, TPB), 148 * 16), TPB, c->stream, c->sp, T, c->fbits, c->vflags, c->v2pos, c->obits, vobits, Jk, Js, jcount, jcap, c->errflag);
     nj = dread(c, jcount);
     if (nj <= jcap) break;
     dfree(c, Jk); dfree(c, Js); jcap = nj;
   }
-  dfree(c, jcount);
+  dfree(c, jcount); dfree(c, vobits);
   {
     u64* k2; u8* v2; ALLOC(k2, u64, nj); ALLOC(v2, u8, nj);
     PRIM(prim_sort_u64_u8(c, Jk, Js, k2, v2, nj));

@@ -381,6 +381,116 @@ k_make_records(const u32* __restrict__ F, const u32* __restrict__ R, const u32* 
   store_bit(obits, p, o);
 }
 
+// Rolling variant of k_make_records.  One thread walks SPB_RUN consecutive positions and keeps, for the k-mer at p and
+// two odd multipliers B (32-bit arithmetic: one IMAD per update),
+//   HF(p) = sum_i F[p+i] B^(k-1-i)            polynomial hash of the forward string
+//   HR(p) = sum_j (3 - F[p+j]) B^j            the same polynomial of the reverse-complement string
+// both updated in O(1) per position (HR with B^-1 mod 2^32), so a position costs a few dozen instructions instead of
+// a hash over all 2k bits (~220 at k=301); the hash of the canonical string is the pair of the chosen orientation,
+// finished by roll_finish.  Everything is read from the forward strand: the first 16 bases of the reverse-complement
+// k-mer are revcomp16 of the last 16 bases of the forward one.  Records: as k_make_records (orientation in bit 0).
+#ifndef SPB_RUN
+#define SPB_RUN 256
+#endif
+struct RollK { u32 B[2], Binv[2], Bk1[2], negBk[2], negBinv[2]; };   // B, B^-1, B^(k-1), -B^k, -B^-1  (mod 2^32)
+__device__ __forceinline__ u64 roll_finish(u32 a, u32 b) {
+  // (the rotations matter: a M + b is always even -- every coefficient M B1^e + B2^e is -- which would leave 2^31 values)
+  u32 t = a * 0x9E3779B1u + __funnelshift_l(b, b, 15); t ^= t >> 16; t *= 0x85EBCA6Bu; t ^= t >> 13; t *= 0xC2B2AE35u; t ^= t >> 16;
+  u32 u = b * 0xC2B2AE3Du + __funnelshift_l(a, a, 13); u ^= u >> 15; u *= 0x2C1B3C6Du; u ^= u >> 12; u *= 0x297A2D39u; u ^= u >> 15;
+  return ((u64)t << 32) | u;
+}
+__global__ void SPB_LAUNCH_BOUNDS(128)
+k_make_records_roll(const u32* __restrict__ F, const u32* __restrict__ R, const u32* __restrict__ vbits, u64 T, u32 k,
+                    u64 pos_lo, u64 pos_hi, u64 n, u64* __restrict__ keys, u32* __restrict__ pos, u32* obits, u32 spread, RollK K) {
+  const u64 g = SPB_GTID();
+  const bool alive = g * SPB_RUN < n;
+#ifdef SPB_EMU
+  if (!alive) return;
+#else
+  // the 32 keys a lane produces per group of steps are transposed through shared memory, so that the warp writes 32
+  // rows of 256 contiguous bytes instead of 32 scattered 8-byte pieces per store
+  __shared__ u64 tile[4][32][33];
+  const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#endif
+  const u64 p0 = pos_lo + g * SPB_RUN;               // multiple of 256
+  bool have = false, fresh = false;
+  u32 f1 = 0, f2 = 0, r1 = 0, r2 = 0;                // HF, HR for the two multipliers
+  u32 head = 0, tail = 0, wb = 0, wc = 0;            // 16 bases at p / ending at p+k-1; cached words of the two input streams
+  for (u32 w = 0; w < SPB_RUN / 32; ++w) {
+    const u64 pw = p0 + 32ull * w;
+    const u32 vb = (alive && pw < T) ? __ldg(vbits + (pw >> 5)) : 0u;
+    u32 ow = 0;
+    for (u32 j = 0; j < 32; ++j) {
+      const u64 p = pw + j;
+      const bool valid = ((vb >> j) & 1u) && p < pos_hi;
+      u64 key = ~0ull;
+      if (valid) {
+        if (!have) {                                 // direct evaluation (run start, or first k-mer of a sequence)
+          f1 = f2 = r1 = r2 = 0;
+          u32 wd = 0, q1 = 1, q2 = 1;                // q = B^i
+          for (u32 i = 0; i < k; ++i) {
+            const u64 a = p + i;
+            if (i == 0 || (a & 15) == 0) wd = __ldg(F + (a >> 4));
+            const u32 x = (wd >> (30 - 2 * (u32)(a & 15))) & 3u;
+            f1 = f1 * K.B[0] + x; f2 = f2 * K.B[1] + x;
+            r1 += (3u - x) * q1; r2 += (3u - x) * q2;
+            q1 *= K.B[0]; q2 *= K.B[1];
+          }
+          const u64 e = p + k - 16;
+          head = __funnelshift_l(__ldg(F + (p >> 4) + 1), __ldg(F + (p >> 4)), (u32)(p & 15) * 2);
+          tail = __funnelshift_l(__ldg(F + (e >> 4) + 1), __ldg(F + (e >> 4)), (u32)(e & 15) * 2);
+          have = true; fresh = true;
+        } else {                                     // roll from p-1
+          const u32 out = head >> 30;
+          const u64 ib = p + k - 1, ic = p + 15;
+          if (fresh || (ib & 15) == 0) wb = __ldg(F + (ib >> 4));
+          if (fresh || (ic & 15) == 0) wc = __ldg(F + (ic >> 4));
+          fresh = false;
+          const u32 in = (wb >> (30 - 2 * (u32)(ib & 15))) & 3u;
+          head = (head << 2) | ((wc >> (30 - 2 * (u32)(ic & 15))) & 3u);
+          tail = (tail << 2) | in;
+          const u32 co = 3u - out, ci = 3u - in;
+          f1 = f1 * K.B[0] + in + out * K.negBk[0];                              // (HF - out B^(k-1)) B + in
+          f2 = f2 * K.B[1] + in + out * K.negBk[1];
+          r1 = r1 * K.Binv[0] + (ci * K.Bk1[0] + co * K.negBinv[0]);             // (HR - co) / B + ci B^(k-1)
+          r2 = r2 * K.Binv[1] + (ci * K.Bk1[1] + co * K.negBinv[1]);
+        }
+        const u32 lx = head, ly = revcomp16(tail);
+        const bool o = (lx != ly) ? (lx > ly) : (win_cmp(F, p, R, T - p - k, k) >= 0);
+        key = (roll_finish(o ? f1 : r1, o ? f2 : r2) & ~1ull) | (o ? 1ull : 0ull);
+        if (key == ~0ull) key ^= 2ull;
+        ow |= (o ? 1u : 0u) << j;
+      } else {
+        have = false;
+        if (spread) key = mix64(p);
+      }
+#ifdef SPB_EMU
+      keys[p - pos_lo] = key; pos[p - pos_lo] = (spread && !valid) ? SPB_INVALID : (u32)p;
+#else
+      tile[wid][lane][j] = key;
+#endif
+    }
+    if (alive) obits[pw >> 5] = ow;
+#ifndef SPB_EMU
+    __syncwarp();
+    const u64 g0 = g - lane;                         // first run of the warp
+    const u64 nruns = n / SPB_RUN;
+    const u32 rows = g0 >= nruns ? 0u : (u32)min((u64)32, nruns - g0);
+    u32 vm = vb;                                     // valid steps of this lane's group (for the spread marking)
+    if (pw + 32 > pos_hi) vm = pw >= pos_hi ? 0u : (vm & ((1u << (u32)(pos_hi - pw)) - 1u));
+    u64* kq = keys + (g0 * SPB_RUN + 32u * w + lane);
+    u32* pq = pos + (g0 * SPB_RUN + 32u * w + lane);
+    u32 pv = (u32)(pos_lo + g0 * SPB_RUN + 32u * w + lane);
+    for (u32 r = 0; r < rows; ++r) {                 // row r = the 32 keys of lane r
+      const u32 vr = __shfl_sync(0xffffffffu, vm, r);
+      kq[(u64)r * SPB_RUN] = tile[wid][r][lane];
+      pq[(u64)r * SPB_RUN] = (spread && !((vr >> lane) & 1u)) ? SPB_INVALID : pv + r * SPB_RUN;
+    }
+    __syncwarp();
+#endif
+  }
+}
+
 // Single-pass radix partition fused with the record generation (replaces k_make_records + a library radix pass on the
 // single-GPU links path).  A block handles a tile of 2048 positions: hashes go to shared memory with a per-bucket
 // histogram; one atomicAdd per (block, bucket) on the global bucket cursors reserves the output run; the records
@@ -861,7 +971,8 @@ k_assign_ids(const u32* sp_in, u32* sp, const u32* __restrict__ vbits, u64 T, u6
 // K4: junction candidates.  The instance pair (p, p+1) yields edge {sp[p], sp[p+1]} (reference
 // lib/Assembler.py:199-201).  It is dropped when it coincides with an implicit edge (v, v+1).
 __global__ void k_junction_emit(const u32* __restrict__ sp, u64 T, const u32* __restrict__ fbits, const u8* __restrict__ vflags, const u32* __restrict__ v2pos,
-                                const u32* __restrict__ obits, u64* __restrict__ Jk, u8* __restrict__ Js, u64* counter, u64 cap) {
+                                const u32* __restrict__ obits, const u32* __restrict__ vobits, u64* __restrict__ Jk, u8* __restrict__ Js,
+                                u64* counter, u64 cap, u32* err) {
   // one warp per 32 positions (= one word of the first-appearance bitmap), grid-stride: a word whose 32 pairs
   // (p, p+1) are all pairs of consecutive first appearances holds only implicit edges and is skipped at once
   const u64 nwords = (T + 31) / 32;
@@ -875,8 +986,20 @@ __global__ void k_junction_emit(const u32* __restrict__ sp, u64 T, const u32* __
     if (p + 1 < T && !(get_bit(fbits, p) && get_bit(fbits, p + 1))) {
       u = sp[p]; w = sp[p + 1];
       if (u != SPB_INVALID && w != SPB_INVALID) {
-        bool implicit = (w == u + 1 && (vflags[u] & VF_R)) || (u == w + 1 && (vflags[w] & VF_R));
-        if (!implicit) n = (u == w) ? 1 : 2;
+        const bool up = w == u + 1, down = u == w + 1;
+        if (up || down) {
+          // candidate implicit edge.  A later instance of an implicit edge must attach on the same sides as the first
+          // one (both instances on the stored strand when walked upwards, both on the other strand when walked
+          // downwards); otherwise the edge is orientation-ambiguous, like a junction edge seen with two different
+          // payloads (k_unique_heads).  vobits: orientation bit per vertex, built when duplicates dominate; else
+          // through v2pos.  The loads below depend on (u, w) only and are issued together.
+          const u8 fl = vflags[up ? u : w];
+          const u32 ou = vobits ? get_bit(vobits, u) : get_bit(obits, v2pos[u]), ow = vobits ? get_bit(vobits, w) : get_bit(obits, v2pos[w]);
+          if (fl & VF_R) {
+            const u32 su = get_bit(obits, p) ^ ou, sw = get_bit(obits, p + 1) ^ ow;
+            if (su != sw || su != (down ? 1u : 0u)) atomicOr(err, (u32)ERR_DEGENERATE);
+          } else n = 2;
+        } else n = (u == w) ? 1 : 2;
       }
     }
 #ifndef SPB_EMU
@@ -890,6 +1013,24 @@ __global__ void k_junction_emit(const u32* __restrict__ sp, u64 T, const u32* __
     u32 side_w = sw ? SIDE_R : SIDE_L;                           // where u attaches on w
     Jk[slot] = ((u64)u << 32) | w; Js[slot] = (u8)(side_u | (side_w << 1));
     if (n == 2) { Jk[slot + 1] = ((u64)w << 32) | u; Js[slot + 1] = (u8)(side_w | (side_u << 1)); }
+  }
+}
+
+// orientation bit of every vertex' stored k-mer (= of its first appearance); v2pos ascends with the vertex id, so the
+// gathers are nearly sequential.  One warp per 32 vertices, grid-stride.
+__global__ void k_vertex_obits(const u32* __restrict__ v2pos, const u32* __restrict__ obits, u32 nV, u32* __restrict__ vobits) {
+  const u64 nwords = ((u64)nV + 31) / 32;
+  const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+  const u32 lane = threadIdx.x & 31;
+  for (u64 wd = SPB_GTID() >> 5; wd < nwords; wd += nwarps) {
+    const u64 v = wd * 32 + lane;
+    const bool b = v < nV && get_bit(obits, v2pos[v]);
+#ifdef SPB_EMU
+    if (b) vobits[wd] |= 1u << lane;                 // the caller zeroes the array
+#else
+    const u32 m = __ballot_sync(0xffffffffu, b);
+    if (lane == 0) vobits[wd] = m;
+#endif
   }
 }
 

@@ -50,7 +50,14 @@ def crafted_cases(k=31, seed=3):
         # self-loop reached with different attachment sides) -- found by the hypothesis test
         ("dinucleotide_selfloop", [("a", _rnd(rng, 90) + "CG" * ((k + 1) // 2) + _rnd(rng, 90)), ("b", s[:120])]),
     ]
-    return [(n, k, recs) for n, recs in cases]
+    out = [(n, k, recs) for n, recs in cases]
+    # a dinucleotide run ending a record: the pair (GAGAGAGAG, AGAGAGAGA) is walked a second time over the same
+    # consecutive-id edge but on the other strand -> orientation-ambiguous, the reference asserts (found by hypothesis)
+    out.append(("dinucleotide_tail", 9, [
+        ("s0", "CGACAATAACTCGCGGGTTGACTCGCAGCTGTAACCCAGACCCGAGCAATACACTGCAAAA"),
+        ("s3", "CGACAATAACTCGCGGGTTGACTCGCAGCTGTAACCCAGACCCGAGCAATACACTGCAAAAGTCGAGAAAGGCTGAAGTCCAATGTCTTGCTCTACACCGTCCTGCGAT"
+               "CTGCAATGATCCGTCAGCGGTTAAATCAATAAGAGTTTGAGAGAGAGAG")]))
+    return out
 
 
 def write_fasta(path, recs):
