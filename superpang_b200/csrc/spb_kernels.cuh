@@ -878,6 +878,7 @@ __global__ void k_block_counts(const u32* __restrict__ fbits, u32* __restrict__ 
   cnt[b] = c;
 }
 
+#define SPB_JU 4                                     // bitmap words per warp iteration (independent loads in flight)
 // first-appearance bitmap fbits = wbits & ~dbits, and per 256-position block counts
 __global__ void k_first_bits(const u32* __restrict__ wbits, const u32* __restrict__ dbits, u32* __restrict__ fbits, u64 nblk) {
   u64 b = SPB_GTID();
@@ -920,50 +921,72 @@ template <int W> __global__ void
 k_assign_ids(const u32* sp_in, u32* sp, const u32* __restrict__ vbits, u64 T, u64 lo, u64 hi, const u32* __restrict__ fbits,
              const u32* __restrict__ blkoff, const u8* __restrict__ wpre, const u64* __restrict__ slots, u64 capmask, const u32* __restrict__ F,
              const u32* __restrict__ R, u32 k, u32* __restrict__ v2pos, u8* __restrict__ vflags, int follow, u32* err) {
-  // one warp per 32 positions (one word of the bitmaps), grid-stride
+  // One warp per SPB_JU x 32 positions (SPB_JU words of the bitmaps), grid-stride.  The dependent loads (bitmap word ->
+  // link -> bitmap word at the link target -> rank tables) are issued for all SPB_JU words before they are consumed.
+  //   sp_in[p] = a smaller position with the same k-mer (global-table path: follow the links down to a first
+  //   appearance; a displaced winner on the way ends in an exact table lookup), a pure link (links path: follow) or
+  //   the exact representative (multi-GPU path)
   const u64 nwords = (T + 31) / 32;
   const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
   const u32 lane = threadIdx.x & 31;
-  for (u64 wd = SPB_GTID() >> 5; wd < nwords; wd += nwarps) {
-    const u64 p = wd * 32 + lane;
-    const u32 f = __ldg(fbits + wd);
-    if (f == 0xFFFFFFFFu) {                          // 32 first appearances in a row: ids are consecutive
-      u32 vid = __ldg(blkoff + (wd >> 3)) + __ldg(wpre + wd) + lane;
-      if (p >= lo && p < hi) sp[p] = vid;
-      v2pos[vid] = (u32)p;
-      vflags[vid] = (lane < 31 || (__ldg(fbits + wd + 1) & 1u)) ? VF_R : 0;
-      continue;
+  for (u64 wd0 = (SPB_GTID() >> 5) * SPB_JU; wd0 < nwords; wd0 += nwarps * SPB_JU) {
+    u32 f[SPB_JU + 1], r[SPB_JU], fr[SPB_JU];
+    bool first[SPB_JU], mine[SPB_JU], act[SPB_JU];
+#pragma unroll
+    for (u32 j = 0; j <= SPB_JU; ++j) f[j] = wd0 + j <= nwords ? __ldg(fbits + wd0 + j) : 0u;
+#pragma unroll
+    for (u32 j = 0; j < SPB_JU; ++j) {               // stage 1: the link of every repeated instance
+      const u64 wd = wd0 + j, p = wd * 32 + lane;
+      const bool inside = wd < nwords && p < T;
+      mine[j] = inside && p >= lo && p < hi;         // multi-GPU: sp is filled for the local slice only, the vertex table everywhere
+      const bool vb = inside && ((__ldg(vbits + wd) >> lane) & 1u);
+      first[j] = (f[j] >> lane) & 1u;
+      act[j] = vb && (first[j] || mine[j]);
+      if (inside && !vb && mine[j]) sp[p] = SPB_INVALID;
+      r[j] = (u32)p;
+      if (act[j] && !first[j]) r[j] = sp_in[p];
     }
-    if (p >= T) continue;
-    bool mine = p >= lo && p < hi;               // multi-GPU: sp is filled for the local slice only, the vertex table everywhere
-    if (!get_bit(vbits, p)) { if (mine) sp[p] = SPB_INVALID; continue; }
-    bool first = (f >> lane) & 1u;
-    if (!first && !mine) continue;
-    u32 r = (u32)p;
-    if (!first) {
-      // sp_in[p] = a smaller position with the same k-mer (global-table path: follow the links down to a first
-      // appearance; a displaced winner on the way ends in an exact table lookup), a pure link (links path: follow) or
-      // the exact representative (multi-GPU path)
-      r = sp_in[p];
-      if (slots) {
-        for (u32 hop = 0;; ++hop) {
-          if (r == SPB_INVALID || hop > 256) { r = lookup_rep<W>(F, R, T, k, slots, capmask, p); break; }
-          if (get_bit(fbits, r)) break;
-          r = sp_in[r];
+#pragma unroll
+    for (u32 j = 0; j < SPB_JU; ++j) {               // stage 2: bitmap word at the link target
+      fr[j] = f[j];
+      if (act[j] && !first[j] && r[j] != SPB_INVALID) fr[j] = __ldg(fbits + (r[j] >> 5));
+    }
+    u32 bo[SPB_JU], wp[SPB_JU];
+#pragma unroll
+    for (u32 j = 0; j < SPB_JU; ++j) {               // stage 3: finish the (rare) longer chains; rank tables
+      bo[j] = wp[j] = 0;
+      if (!act[j]) continue;
+      if (!first[j]) {
+        u32 x = r[j], fx = fr[j];
+        if (slots) {
+          for (u32 hop = 0;; ++hop) {
+            if (x == SPB_INVALID || hop > 256) { x = lookup_rep<W>(F, R, T, k, slots, capmask, wd0 * 32 + 32ull * j + lane); fx = __ldg(fbits + (x >> 5)); break; }
+            if ((fx >> (x & 31)) & 1u) break;
+            x = sp_in[x];
+            if (x != SPB_INVALID) fx = __ldg(fbits + (x >> 5));
+          }
+        } else if (follow) {                         // links without a table: chains strictly descend and end at a first appearance
+          while (!((fx >> (x & 31)) & 1u)) {
+            const u32 nx = sp_in[x];
+            if (nx >= x) { atomicOr(err, (u32)ERR_OVERFLOW); break; }
+            x = nx; fx = __ldg(fbits + (x >> 5));
+          }
         }
-      } else if (follow) {                           // links without a table: chains strictly descend and end at a first appearance
-        while (!get_bit(fbits, r)) {
-          u32 nx = sp_in[r];
-          if (nx >= r) { atomicOr(err, (u32)ERR_OVERFLOW); break; }
-          r = nx;
-        }
+        r[j] = x; fr[j] = fx;
       }
+      bo[j] = __ldg(blkoff + (r[j] >> 8)); wp[j] = __ldg(wpre + (r[j] >> 5));
     }
-    u32 vid = rank_first(fbits, blkoff, wpre, r);
-    if (mine) sp[p] = vid;
-    if (first) {
-      v2pos[vid] = (u32)p;
-      vflags[vid] = get_bit(fbits, p + 1) ? VF_R : 0;   // (p, p+1) both first appearances => edge (vid, vid+1)
+#pragma unroll
+    for (u32 j = 0; j < SPB_JU; ++j) {               // stage 4: ids
+      if (!act[j]) continue;
+      const u64 p = (wd0 + j) * 32 + lane;
+      const u32 vid = bo[j] + wp[j] + __popc(fr[j] & ((1u << (r[j] & 31)) - 1));
+      if (mine[j]) sp[p] = vid;
+      if (first[j]) {
+        v2pos[vid] = (u32)p;
+        const u32 nextfirst = lane < 31 ? (f[j] >> (lane + 1)) & 1u : f[j + 1] & 1u;
+        vflags[vid] = nextfirst ? VF_R : 0;          // (p, p+1) both first appearances => edge (vid, vid+1)
+      }
     }
   }
 }
@@ -973,46 +996,69 @@ k_assign_ids(const u32* sp_in, u32* sp, const u32* __restrict__ vbits, u64 T, u6
 __global__ void k_junction_emit(const u32* __restrict__ sp, u64 T, const u32* __restrict__ fbits, const u8* __restrict__ vflags, const u32* __restrict__ v2pos,
                                 const u32* __restrict__ obits, const u32* __restrict__ vobits, u64* __restrict__ Jk, u8* __restrict__ Js,
                                 u64* counter, u64 cap, u32* err) {
-  // one warp per 32 positions (= one word of the first-appearance bitmap), grid-stride: a word whose 32 pairs
-  // (p, p+1) are all pairs of consecutive first appearances holds only implicit edges and is skipped at once
+  // One warp per SPB_JU x 32 positions (SPB_JU words of the first-appearance bitmap), grid-stride.  A word whose 32
+  // pairs (p, p+1) are all pairs of consecutive first appearances holds only implicit edges and is skipped at once.
+  // The three dependent loads of a pair (bitmap -> vertex ids -> flags / orientation bits) are issued for all SPB_JU
+  // words before any of them is consumed: the kernel is bound by that latency chain, not by bandwidth.
   const u64 nwords = (T + 31) / 32;
   const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
   const u32 lane = threadIdx.x & 31;
-  for (u64 wd = SPB_GTID() >> 5; wd < nwords; wd += nwarps) {
-    u32 f = __ldg(fbits + wd), fn = __ldg(fbits + wd + 1);
-    if ((f & ((f >> 1) | (fn << 31))) == 0xFFFFFFFFu) continue;
-    u64 p = wd * 32 + lane;
-    u32 n = 0, u = 0, w = 0;
-    if (p + 1 < T && !(get_bit(fbits, p) && get_bit(fbits, p + 1))) {
-      u = sp[p]; w = sp[p + 1];
-      if (u != SPB_INVALID && w != SPB_INVALID) {
-        const bool up = w == u + 1, down = u == w + 1;
-        if (up || down) {
-          // candidate implicit edge.  A later instance of an implicit edge must attach on the same sides as the first
-          // one (both instances on the stored strand when walked upwards, both on the other strand when walked
-          // downwards); otherwise the edge is orientation-ambiguous, like a junction edge seen with two different
-          // payloads (k_unique_heads).  vobits: orientation bit per vertex, built when duplicates dominate; else
-          // through v2pos.  The loads below depend on (u, w) only and are issued together.
-          const u8 fl = vflags[up ? u : w];
-          const u32 ou = vobits ? get_bit(vobits, u) : get_bit(obits, v2pos[u]), ow = vobits ? get_bit(vobits, w) : get_bit(obits, v2pos[w]);
-          if (fl & VF_R) {
-            const u32 su = get_bit(obits, p) ^ ou, sw = get_bit(obits, p + 1) ^ ow;
-            if (su != sw || su != (down ? 1u : 0u)) atomicOr(err, (u32)ERR_DEGENERATE);
-          } else n = 2;
-        } else n = (u == w) ? 1 : 2;
+  for (u64 wd0 = (SPB_GTID() >> 5) * SPB_JU; wd0 < nwords; wd0 += nwarps * SPB_JU) {
+    u32 f[SPB_JU + 1];
+#pragma unroll
+    for (u32 j = 0; j <= SPB_JU; ++j) f[j] = wd0 + j <= nwords ? __ldg(fbits + wd0 + j) : 0u;
+    u32 u[SPB_JU], w[SPB_JU], ob[SPB_JU], on[SPB_JU];
+    bool live[SPB_JU];
+    bool any = false;
+#pragma unroll
+    for (u32 j = 0; j < SPB_JU; ++j) any = any || (wd0 + j < nwords && (f[j] & ((f[j] >> 1) | (f[j + 1] << 31))) != 0xFFFFFFFFu);
+    if (!any) continue;                              // warp-uniform: nothing but consecutive first appearances here
+#pragma unroll
+    for (u32 j = 0; j < SPB_JU; ++j) {               // stage 1: vertex ids of the pairs that are not two consecutive firsts
+      const u64 p = (wd0 + j) * 32 + lane;
+      const bool word = wd0 + j < nwords && (f[j] & ((f[j] >> 1) | (f[j + 1] << 31))) != 0xFFFFFFFFu;     // warp-uniform
+      const u32 fp = (f[j] >> lane) & 1u, fq = lane < 31 ? (f[j] >> (lane + 1)) & 1u : f[j + 1] & 1u;
+      live[j] = word && p + 1 < T && !(fp && fq);
+      u[j] = live[j] ? sp[p] : SPB_INVALID; w[j] = live[j] ? sp[p + 1] : SPB_INVALID;
+      ob[j] = word ? __ldg(obits + wd0 + j) : 0u; on[j] = word ? __ldg(obits + wd0 + j + 1) : 0u;
+    }
+    u8 fl[SPB_JU]; u32 ou[SPB_JU], ow[SPB_JU];
+#pragma unroll
+    for (u32 j = 0; j < SPB_JU; ++j) {               // stage 2: flags + stored orientations of candidate implicit edges
+      fl[j] = 0; ou[j] = ow[j] = 0;
+      live[j] = live[j] && u[j] != SPB_INVALID && w[j] != SPB_INVALID;
+      if (live[j] && (w[j] == u[j] + 1 || u[j] == w[j] + 1)) {
+        fl[j] = vflags[w[j] == u[j] + 1 ? u[j] : w[j]];
+        ou[j] = vobits ? get_bit(vobits, u[j]) : get_bit(obits, v2pos[u[j]]);
+        ow[j] = vobits ? get_bit(vobits, w[j]) : get_bit(obits, v2pos[w[j]]);
       }
     }
+#pragma unroll
+    for (u32 j = 0; j < SPB_JU; ++j) {               // stage 3: check implicit duplicates, emit junction edges
+      const u32 op = (ob[j] >> lane) & 1u, oq = lane < 31 ? (ob[j] >> (lane + 1)) & 1u : on[j] & 1u;    // orientation at p, p+1
+      u32 n = 0;
+      if (live[j]) {
+        const bool up = w[j] == u[j] + 1, down = u[j] == w[j] + 1;
+        if ((up || down) && (fl[j] & VF_R)) {
+          // a later instance of an implicit edge must attach on the same sides as the first one (both instances on
+          // the stored strand when walked upwards, both on the other strand when walked downwards); otherwise the
+          // edge is orientation-ambiguous, like a junction edge seen with two different payloads (k_unique_heads)
+          const u32 su = op ^ ou[j], sw = oq ^ ow[j];
+          if (su != sw || su != (down ? 1u : 0u)) atomicOr(err, (u32)ERR_DEGENERATE);
+        } else n = (u[j] == w[j]) ? 1 : 2;
+      }
 #ifndef SPB_EMU
-    if (__ballot_sync(0xffffffffu, n != 0) == 0) continue;
+      if (__ballot_sync(0xffffffffu, n != 0) == 0) continue;
 #endif
-    u64 slot = list_reserve(counter, n);
-    if (n == 0 || slot + n > cap) continue;
-    u32 su = get_bit(obits, p) ^ get_bit(obits, v2pos[u]);       // instance strand vs. vertex' stored k-mer
-    u32 sw = get_bit(obits, p + 1) ^ get_bit(obits, v2pos[w]);
-    u32 side_u = su ? SIDE_L : SIDE_R;                           // where w attaches on u
-    u32 side_w = sw ? SIDE_R : SIDE_L;                           // where u attaches on w
-    Jk[slot] = ((u64)u << 32) | w; Js[slot] = (u8)(side_u | (side_w << 1));
-    if (n == 2) { Jk[slot + 1] = ((u64)w << 32) | u; Js[slot + 1] = (u8)(side_w | (side_u << 1)); }
+      u64 slot = list_reserve(counter, n);
+      if (n == 0 || slot + n > cap) continue;
+      u32 su = op ^ get_bit(obits, v2pos[u[j]]);                   // instance strand vs. vertex' stored k-mer
+      u32 sw = oq ^ get_bit(obits, v2pos[w[j]]);
+      u32 side_u = su ? SIDE_L : SIDE_R;                           // where w attaches on u
+      u32 side_w = sw ? SIDE_R : SIDE_L;                           // where u attaches on w
+      Jk[slot] = ((u64)u[j] << 32) | w[j]; Js[slot] = (u8)(side_u | (side_w << 1));
+      if (n == 2) { Jk[slot + 1] = ((u64)w[j] << 32) | u[j]; Js[slot + 1] = (u8)(side_w | (side_u << 1)); }
+    }
   }
 }
 
@@ -1441,32 +1487,57 @@ k_emit_darts(const u32* __restrict__ choff, u32 nD, const u32* __restrict__ plo,
 __global__ void k_origin_pairs(const u32* __restrict__ sp, u64 T, const u32* __restrict__ fbits, const u32* __restrict__ vnbp, const u8* __restrict__ vflags,
                                const u64* __restrict__ seq_off, u32 n_seq, u64* __restrict__ opairs, u64* ocount, u64 ocap,
                                u64* __restrict__ mpairs, u64* mcount, u64 mcap, u8* __restrict__ has01, u32 sb) {
-  // one warp per 32 positions, grid-stride.  Where p-1 and p are consecutive first appearances (vertices v-1, v joined by
-  // an implicit edge) the NBP changes at p only if v starts a piece, so one flag byte decides and the two vnbp gathers
-  // are skipped.
+  // one warp per SPB_JU x 32 positions, grid-stride.  Where p-1 and p are consecutive first appearances (vertices v-1, v
+  // joined by an implicit edge) the NBP changes at p only if v starts a piece, so one flag byte decides and the two vnbp
+  // gathers are skipped.  The dependent loads (bitmap -> vertex ids -> flags / NBP ids) are issued for all SPB_JU words
+  // before they are consumed (latency-bound kernel).
   const u64 nwords = (T + 31) / 32;
   const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
   const u32 lane = threadIdx.x & 31;
-  for (u64 wd = SPB_GTID() >> 5; wd < nwords; wd += nwarps) {
-    const u64 p = wd * 32 + lane;
-    if (p >= T) continue;
-    const u32 f = __ldg(fbits + wd);
-    const u32 fprev = wd ? (__ldg(fbits + wd - 1) >> 31) : 0u;
-    const bool pair_first = ((f & ((f << 1) | fprev)) >> lane) & 1u;       // p-1 and p both first appearances
-    u32 v = sp[p];
-    if (v == SPB_INVALID) continue;
-    if (pair_first && v > 1 && !(vflags[v] & (VF_INIT | VF_PSTART))) continue;
-    u32 c = vnbp[v];
-    bool in2 = (vflags[v] & VF_IN2) != 0;
-    u32 prev = SPB_INVALID;
-    bool pfirst = true;
-    if (p > 0) { u32 pv = sp[p - 1]; if (pv != SPB_INVALID) { prev = vnbp[pv]; pfirst = false; } }
-    bool emit_o = (c != SPB_INVALID) && (pfirst || c != prev);
-    if (!emit_o && !in2 && v > 1) continue;
-    u32 s = upper_bound_u64(seq_off, n_seq + 1, p) - 1;
-    if (v <= 1) has01[2 * s + v] = 1;
-    u64 i = warp_append(ocount, emit_o); if (emit_o && i < ocap) opairs[i] = ((u64)c << sb) | s;
-    u64 j = warp_append(mcount, in2);    if (in2 && j < mcap) mpairs[j] = ((u64)v << sb) | s;
+  for (u64 wd0 = (SPB_GTID() >> 5) * SPB_JU; wd0 < nwords; wd0 += nwarps * SPB_JU) {
+    u32 v[SPB_JU], pv[SPB_JU];
+    bool pair_first[SPB_JU];
+#pragma unroll
+    for (u32 j = 0; j < SPB_JU; ++j) {               // stage 1: vertex ids at p and p-1
+      const u64 wd = wd0 + j, p = wd * 32 + lane;
+      v[j] = pv[j] = SPB_INVALID; pair_first[j] = false;
+      if (p < T) {
+        const u32 f = __ldg(fbits + wd);
+        const u32 fprev = wd ? (__ldg(fbits + wd - 1) >> 31) : 0u;
+        pair_first[j] = ((f & ((f << 1) | fprev)) >> lane) & 1u;       // p-1 and p both first appearances
+        v[j] = sp[p];
+        if (p > 0 && !pair_first[j]) pv[j] = sp[p - 1];
+      }
+    }
+    u8 fl[SPB_JU]; u32 c[SPB_JU], prev[SPB_JU];
+#pragma unroll
+    for (u32 j = 0; j < SPB_JU; ++j) {               // stage 2: flags; NBP ids where the cheap test cannot decide
+      fl[j] = 0; c[j] = prev[j] = SPB_INVALID;
+      if (v[j] != SPB_INVALID) {
+        fl[j] = vflags[v[j]];
+        if (!pair_first[j]) { c[j] = vnbp[v[j]]; if (pv[j] != SPB_INVALID) prev[j] = vnbp[pv[j]]; }
+      }
+    }
+#pragma unroll
+    for (u32 j = 0; j < SPB_JU; ++j) {               // stage 3
+      const u64 p = (wd0 + j) * 32 + lane;
+      const u32 vv = v[j];
+      if (vv == SPB_INVALID) continue;
+      bool pfirst = pv[j] == SPB_INVALID;
+      if (pair_first[j]) {
+        if (vv > 1 && !(fl[j] & (VF_INIT | VF_PSTART))) continue;
+        c[j] = vnbp[vv];                             // rare: a piece starts here
+        const u32 q = sp[p - 1];                     // p > 0 and valid, since p-1 is a first appearance
+        prev[j] = vnbp[q]; pfirst = false;
+      }
+      const bool in2 = (fl[j] & VF_IN2) != 0;
+      const bool emit_o = (c[j] != SPB_INVALID) && (pfirst || c[j] != prev[j]);
+      if (!emit_o && !in2 && vv > 1) continue;
+      u32 s = upper_bound_u64(seq_off, n_seq + 1, p) - 1;
+      if (vv <= 1) has01[2 * s + vv] = 1;
+      u64 i = warp_append(ocount, emit_o); if (emit_o && i < ocap) opairs[i] = ((u64)c[j] << sb) | s;
+      u64 jj = warp_append(mcount, in2);   if (in2 && jj < mcap) mpairs[jj] = ((u64)vv << sb) | s;
+    }
   }
 }
 // compress_vertices leading-zero quirk (reference lib/vtools.pyx:29-45): a sequence whose smallest
