@@ -111,6 +111,13 @@ int spb_mg_scatter(spb_ctx* ctx, const uint32_t* rep);
 int spb_mg_dedup_links(spb_ctx* ctx, uint64_t* keys_io, uint32_t* pos_io, uint64_t n_total, uint32_t n_owners,
                        uint64_t* send_counts, void** links_dev);
 int spb_mg_apply_links(spb_ctx* ctx, const uint64_t* links, uint64_t n, uint64_t pos_lo, uint64_t pos_hi);
+/* "Owner computes" protocol (default when the probe finds few duplicates): no record travels.  Rank `rank` of
+ * `n_owners` walks all positions itself, keeps the k-mers whose hash it owns and deduplicates them; the output has
+ * the form of spb_mg_dedup_links (links sorted by position, send_counts[r] = links for the position slice of rank r)
+ * and is consumed by spb_mg_apply_links after the all-to-all.  Replaces spb_mg_records + the record exchange +
+ * spb_mg_dedup_links; the orientation bitmap is complete on every rank afterwards (no all-gather needed for it).
+ * Same reference lines as spb_build_dbg (lib/Assembler.py:148-201). */
+int spb_mg_owned_links(spb_ctx* ctx, uint32_t rank, uint32_t n_owners, uint64_t* send_counts, void** links_dev);
 int spb_mg_buffers(spb_ctx* ctx, void** fbits_dev, void** obits_dev, void** sp_dev);
 int spb_mg_ids(spb_ctx* ctx, uint64_t pos_lo, uint64_t pos_hi);
 int spb_mg_graph(spb_ctx* ctx, spb_counts* out);

@@ -23,7 +23,7 @@ EXPORTS = (
     "spb_get_vertex2coords", "spb_get_edges", "spb_get_instance_vertices", "spb_get_seqlimits",
     "spb_get_seq_intervals", "spb_get_components", "spb_get_nbps", "spb_get_nbp_seqs",
     "spb_get_nbp_origins", "spb_get_counts", "spb_get_stage_stats", "spb_build_kind", "spb_launch_count",
-    "spb_get_nbp_graph", "spb_mg_slice", "spb_mg_probe", "spb_mg_records", "spb_mg_dedup", "spb_mg_scatter", "spb_mg_dedup_links", "spb_mg_apply_links", "spb_mg_buffers", "spb_mg_ids", "spb_mg_graph",
+    "spb_get_nbp_graph", "spb_mg_slice", "spb_mg_probe", "spb_mg_records", "spb_mg_dedup", "spb_mg_scatter", "spb_mg_dedup_links", "spb_mg_apply_links", "spb_mg_owned_links", "spb_mg_buffers", "spb_mg_ids", "spb_mg_graph",
 )
 
 
@@ -90,6 +90,7 @@ def _declare(lib):
     lib.spb_mg_scatter.argtypes = [vp, u32p]
     lib.spb_mg_dedup_links.argtypes = [vp, u64p, u32p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)]
     lib.spb_mg_apply_links.argtypes = [vp, u64p, C.c_uint64, C.c_uint64, C.c_uint64]
+    lib.spb_mg_owned_links.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)]
     lib.spb_mg_buffers.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     lib.spb_mg_ids.argtypes = [vp, C.c_uint64, C.c_uint64]
     lib.spb_mg_graph.argtypes = [vp, C.POINTER(SpbCounts)]
@@ -240,16 +241,35 @@ class Engine:
         mark("start")
         # return protocol: rank 0 samples the duplicate rate of the input (two chunks) and broadcasts the choice
         protocol = os.environ.get("SPB_MG_PROTOCOL")
-        if protocol not in ("links", "reps"):
+        if protocol not in ("links", "reps", "owned"):
             flag = torch.zeros(1, dtype=torch.int64, device=dev)
             if r == 0:
                 er, dr = C.c_double(), C.c_double()
                 self._ck(self.lib.spb_mg_probe(self.h, C.byref(er), C.byref(dr)))
                 flag[0] = 1 if dr.value < 0.02 else 0
             dist.broadcast(flag, src=0, group=group)
-            protocol = "links" if int(flag.item()) else "reps"
+            protocol = "owned" if int(flag.item()) else "reps"
         self.mg_protocol = protocol
         mark("probe")
+        if protocol == "owned":
+            # "owner computes": every rank hashes all positions itself and keeps the k-mers it owns -- no record travels;
+            # only the links (position -> first position) of repeated instances are exchanged
+            lcnt = (C.c_uint64 * G)()
+            lp = C.c_void_p()
+            self._ck(self.lib.spb_mg_owned_links(self.h, r, G, lcnt, C.byref(lp)))
+            mark("owner_dedup")
+            lsend = [int(x) for x in lcnt]
+            links = _wrap(lp.value, sum(lsend), torch.int64, cuda, self.device)
+            lsc = torch.tensor(lsend, dtype=torch.int64, device=dev)
+            lrc = torch.empty_like(lsc)
+            dist.all_to_all_single(lrc, lsc, group=group)
+            lrecv = [int(x) for x in lrc.tolist()]
+            lback = torch.empty(sum(lrecv), dtype=torch.int64, device=dev)
+            _exchange(lback, links, lrecv, lsend, r, group)
+            mark("exchange_reps")
+            sync()
+            self._ck(self.lib.spb_mg_apply_links(self.h, lback.data_ptr() if lback.numel() else None, lback.numel(), lo, max(lo, hi)))
+            return self._mg_finish(group, G, r, S, lo, hi, cuda, marks, mark, sync, gather_orientation=False)
         self._ck(self.lib.spb_mg_records(self.h, lo, max(lo, hi), G, cnt, C.byref(kp), C.byref(pp)))
         mark("records_partition")
         send = [int(x) for x in cnt]
@@ -293,10 +313,15 @@ class Engine:
             mark("exchange_reps")
             sync()
             self._ck(self.lib.spb_mg_apply_links(self.h, lback.data_ptr() if lback.numel() else None, lback.numel(), lo, max(lo, hi)))
+        return self._mg_finish(group, G, r, S, lo, hi, cuda, marks, mark, sync, gather_orientation=True)
+
+    def _mg_finish(self, group, G, r, S, lo, hi, cuda, marks, mark, sync, gather_orientation):
+        """Common tail of the distributed build: bitmap all-gather, ids, id all-gather, graph (replicated)."""
+        import torch
         fb, ob, sp = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._ck(self.lib.spb_mg_buffers(self.h, C.byref(fb), C.byref(ob), C.byref(sp)))
         mark("scatter")
-        for ptr in (fb, ob):
+        for ptr in ((fb, ob) if gather_orientation else (fb,)):
             full = _wrap(ptr.value, G * S // 32, torch.int32, cuda, self.device)
             _all_gather_inplace(full, r, G, group)
         sync()

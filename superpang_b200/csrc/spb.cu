@@ -35,6 +35,7 @@ struct spb_ctx {
   // ---- persistent device state
   u64* seq_off = 0;
   u32 *F = 0, *R = 0, *vbits = 0, *obits = 0, *fbits = 0, *sp = 0, *v2pos = 0, *seqlim = 0, *errflag = 0;
+  bool mg_owned = false;                            // spb_mg_owned_links ran (the orientation bitmap is complete on this rank)
   u8* vflags = 0;
   u32 nV = 0, nJ = 0;
   u64* Jk = 0; u8* Js = 0;
@@ -448,6 +449,10 @@ int spb_load(spb_ctx* c, const uint8_t* ascii, const uint64_t* seq_off, uint32_t
   return SPB_OK;
 }
 
+static u64 smem_limit() {                             // tests force the fallbacks with a tiny limit
+  if (const char* e = getenv("SPB_SMEM_LIMIT")) return (u64)std::max(1, atoi(e));
+  return SPB_ST_LIMIT;
+}
 static u32 default_bucket_bits(u64 n_inst, u32 n_owners) {
   u32 bb = 0;
   while (bb < 14 && (n_inst >> bb) > 1200000ull) ++bb;      // ~1 M records per bucket: 16 MB scratch table, L2 resident
@@ -465,6 +470,19 @@ static int alloc_position_state(spb_ctx* c, u64 min_positions = 0) {
   return 0;
 }
 
+// rolling polynomial hashes: two odd multipliers = 5 (mod 8) (multiplicative order 2^30), inverses by Newton iteration
+static RollK roll_constants(u32 k) {
+  RollK K;
+  K.B[0] = 0x9E3779B5u; K.B[1] = 0x85EBCA6Du;
+  for (int h = 0; h < 2; ++h) {
+    const u32 B = K.B[h];
+    u32 inv = B; for (int it = 0; it < 5; ++it) inv *= 2u - B * inv;
+    u32 pw = 1, sq = B; for (u32 e = k - 1; e; e >>= 1) { if (e & 1) pw *= sq; sq *= sq; }
+    K.Binv[h] = inv; K.Bk1[h] = pw; K.negBk[h] = 0u - pw * B; K.negBinv[h] = 0u - inv;
+  }
+  return K;
+}
+
 // S1: records of the positions [pos_lo, pos_hi) (pos_lo a multiple of 256), partitioned by the top `bb` hash bits
 static int dd_records(spb_ctx* c, u64 pos_lo, u64 pos_hi, u32 bb, u64 min_positions = 0, u32 spread = 0) {
   int r0 = alloc_position_state(c, min_positions); if (r0) return r0;
@@ -474,17 +492,9 @@ static int dd_records(spb_ctx* c, u64 pos_lo, u64 pos_hi, u32 bb, u64 min_positi
   ALLOC(keys, u64, n); ALLOC(pos, u32, n);
   u64 grid = n / TPB;
   if (!getenv("SPB_NO_ROLL")) {
-    // rolling polynomial hashes: two odd multipliers = 5 (mod 8) (multiplicative order 2^30), inverses by Newton iteration
-    RollK K;
-    K.B[0] = 0x9E3779B5u; K.B[1] = 0x85EBCA6Du;
-    for (int h = 0; h < 2; ++h) {
-      const u32 B = K.B[h];
-      u32 inv = B; for (int it = 0; it < 5; ++it) inv *= 2u - B * inv;
-      u32 pw = 1, sq = B; for (u32 e = c->k - 1; e; e >>= 1) { if (e & 1) pw *= sq; sq *= sq; }
-      K.Binv[h] = inv; K.Bk1[h] = pw; K.negBk[h] = 0u - pw * B; K.negBinv[h] = 0u - inv;
-    }
+    const RollK K = roll_constants(c->k);
     SPB_LAUNCH(k_make_records_roll, nblk(n / SPB_RUN, 128), 128, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, n, keys, pos, c->obits,
-               spread, K);
+               spread, K, 0u, 0u, (u64*)nullptr, 0ull);
   } else
   switch ((2 * c->k + 31) / 32) {
     case 7:  SPB_LAUNCH(k_make_records<7>, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, keys, pos, c->obits, spread); break;
@@ -726,11 +736,11 @@ static int dedup_smem_links(spb_ctx* c) {
   dev_memset(c, dupbits, 0, (P / 32 + 8) * 4);
   u64 nmax = 0;
   for (u64 b = 0; b < NB; ++b) nmax = std::max(nmax, c->dd_bstart_h[b + 1] - c->dd_bstart_h[b]);
-  if (nmax <= SPB_ST_LIMIT)
+  if (nmax <= smem_limit())
     SPB_LAUNCH_PHASED_DSMEM(k_smem_dedup, 2, NB, 512, SPB_ST_SLOTS * 4, c->stream, c->dd_keys, c->dd_pos, c->dd_bstart, c->F, c->R, T, c->k, nbits,
-                            seenpos, dupbits, c->errflag);
+                            seenpos, dupbits, c->errflag, (u64*)nullptr, (u64*)nullptr, 0ull);
   dfree(c, c->dd_keys); dfree(c, c->dd_pos); dfree(c, c->dd_bstart);
-  if (nmax > SPB_ST_LIMIT) { dfree(c, seenpos); dfree(c, dupbits); return 1; }
+  if (nmax > smem_limit()) { dfree(c, seenpos); dfree(c, dupbits); return 1; }
   c->cnt.table_slots = SPB_ST_SLOTS;
   snprintf(b2, sizeof b2, "\"bucket_dedup_ms\": %.4f, \"smem_tables\": %llu, ", tk.stop(c), NB); c->stats += b2;
   u64 nb = P / 256, nw32 = P / 32;
@@ -964,6 +974,24 @@ int spb_mg_probe(spb_ctx* c, double* ext_ratio, double* dup_ratio) {
 
 // Owner side, "links" protocol: dedup of the received records in L2-resident sub-bucket tables; returns only the
 // exceptions as (position -> first position) links, sorted by position, with per-destination-rank counts.
+// links (from << 32 | to): sort by position, resolve chains, split by the rank that owns the position slice
+static int finish_links(spb_ctx* c, u64* links, u64 nl, u32 n_owners, uint64_t* send_counts, void** links_dev) {
+  u64* tmp; ALLOC(tmp, u64, nl + 1);
+  PRIM(prim_sort_u64(c, links, tmp, nl));
+  SPB_LAUNCH(k_links_resolve, nblk(nl, TPB), TPB, c->stream, links, nl, tmp);
+  uint64_t slice = 0; spb_mg_slice(c, n_owners, &slice);
+  u64* bounds; ALLOC(bounds, u64, n_owners + 2);
+  SPB_LAUNCH(k_links_bounds, nblk(n_owners + 1, TPB), TPB, c->stream, tmp, nl, slice, n_owners, bounds);
+  std::vector<u64> bh(n_owners + 1);
+  dev_copy(c, bh.data(), bounds, (n_owners + 1) * 8ull); dev_sync(c);
+  for (u32 r = 0; r < n_owners; ++r) send_counts[r] = bh[r + 1] - bh[r];
+  dfree(c, bounds); dfree(c, links);
+  dfree(c, c->mg_links);
+  c->mg_links = tmp;
+  *links_dev = tmp;
+  return 0;
+}
+
 int spb_mg_dedup_links(spb_ctx* c, uint64_t* keys_io, uint32_t* pos_io, uint64_t n_total, uint32_t n_owners, uint64_t* send_counts,
                        void** links_dev) {
   if (!c) return SPB_EINVAL;
@@ -1027,27 +1055,98 @@ int spb_mg_dedup_links(spb_ctx* c, uint64_t* keys_io, uint32_t* pos_io, uint64_t
   dfree(c, nlinks); dfree(c, coff); dfree(c, sub);
   dfree(c, k2a); dfree(c, p2a);
   if (getenv("SPB_DEBUG")) fprintf(stderr, "[spb] dedup_links: n_total=%llu B=%u cap=%llu links=%llu\n", (unsigned long long)n_total, B, (unsigned long long)cap, (unsigned long long)nl);
-  // sort by position, resolve chains, split by destination rank
-  u64* tmp; ALLOC(tmp, u64, nl + 1);
-  PRIM(prim_sort_u64(c, links, tmp, nl));
-  SPB_LAUNCH(k_links_resolve, nblk(nl, TPB), TPB, c->stream, links, nl, tmp);
+  int r = finish_links(c, links, nl, n_owners, send_counts, links_dev);
+  return r ? r : check_err(c, "spb_mg_dedup_links");
+}
+
+// Multi-GPU, "owner computes" protocol: no record travels.  Every rank walks ALL positions with the rolling hashes (a few
+// ms) and keeps only the records whose hash it owns, sorts them into sub-buckets and deduplicates them in shared-memory
+// tables (k_smem_dedup, list form).  Output as spb_mg_dedup_links: links (position -> first position) sorted by
+// position, split by the rank that owns the position slice.  Also leaves the orientation bitmap complete on every rank.
+int spb_mg_owned_links(spb_ctx* c, uint32_t rank, uint32_t n_owners, uint64_t* send_counts, void** links_dev) {
+  if (!c) return SPB_EINVAL;
+  if (c->state != 1) return fail(c, SPB_ESTATE, "spb_mg_owned_links needs a loaded input");
+  if (!pow2(n_owners) || n_owners < 2 || rank >= n_owners) return fail(c, SPB_EINVAL, "n_owners must be a power of two >= 2, rank < n_owners");
+#ifndef SPB_EMU
+  CK(cudaSetDevice(c->device));
+#endif
   uint64_t slice = 0; spb_mg_slice(c, n_owners, &slice);
-  u64* bounds; ALLOC(bounds, u64, n_owners + 2);
-  SPB_LAUNCH(k_links_bounds, nblk(n_owners + 1, TPB), TPB, c->stream, tmp, nl, slice, n_owners, bounds);
-  std::vector<u64> bh(n_owners + 1);
-  dev_copy(c, bh.data(), bounds, (n_owners + 1) * 8ull); dev_sync(c);
-  for (u32 r = 0; r < n_owners; ++r) send_counts[r] = bh[r + 1] - bh[r];
-  dfree(c, bounds); dfree(c, links);
-  dfree(c, c->mg_links);
-  c->mg_links = tmp;
-  *links_dev = tmp;
-  return check_err(c, "spb_mg_dedup_links");
+  int r0 = alloc_position_state(c, slice * n_owners); if (r0) return r0;
+  const u64 T = c->T, n = nblk(T, TPB) * TPB;
+  u32 bbo = 0; while ((1u << bbo) < n_owners) ++bbo;
+  const RollK K = roll_constants(c->k);
+  u64* count; ALLOC(count, u64, 2);
+  u64 cap = n / n_owners + n / (8 * n_owners) + 65536, n_own = 0;
+  u64 *keys = nullptr, *keys2 = nullptr; u32 *pos = nullptr, *pos2 = nullptr;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    ALLOC(keys, u64, cap); ALLOC(pos, u32, cap);
+    dev_memset(c, count, 0, 16);
+    SPB_LAUNCH(k_make_records_roll, nblk(n / SPB_RUN, 128), 128, c->stream, c->F, c->R, c->vbits, T, c->k, 0ull, T, n, keys, pos, c->obits, 0u, K,
+               bbo, rank, count, cap);
+    n_own = dread(c, count);
+    if (n_own <= cap) break;
+    dfree(c, keys); dfree(c, pos); cap = n_own;      // skewed hashes (masses of identical k-mers at one owner)
+  }
+  dfree(c, count);
+  u64 avg = 7680;
+  if (const char* e = getenv("SPB_SMEM_AVG")) avg = std::max(1, atoi(e));
+  u32 nbits = 0; while ((n_own >> nbits) > avg && nbits < 24) ++nbits;
+  if (nbits > 0 && n_own) {
+    ALLOC(keys2, u64, n_own); ALLOC(pos2, u32, n_own);
+    PRIM(prim_partition_u64_u32(c, keys, pos, keys2, pos2, n_own, 64 - (int)bbo - (int)nbits, 64 - (int)bbo));
+    dfree(c, keys2); dfree(c, pos2);
+  }
+  const u64 NB = 1ull << nbits;
+  u64* sub; ALLOC(sub, u64, NB + 2);
+  std::vector<u64> bstart(NB + 1, 0);
+  if (n_own) {
+    SPB_LAUNCH(k_bucket_bounds_shift, nblk(NB + 1, TPB), TPB, c->stream, keys, n_own, bbo, nbits, (u32)NB, sub);
+    dev_copy(c, bstart.data(), sub, (NB + 1) * 8ull); dev_sync(c);
+  }
+  u64 nmax = 0;
+  for (u64 b = 0; b < NB; ++b) nmax = std::max(nmax, bstart[b + 1] - bstart[b]);
+  u64* nlinks; ALLOC(nlinks, u64, 2);
+  u64 lcap = std::max<u64>(4096, n_own / 8);
+  u64* links = nullptr; u64 nl = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    ALLOC(links, u64, lcap + 1);
+    dev_memset(c, nlinks, 0, 16);
+    if (n_own == 0) break;
+    if (nmax <= smem_limit()) {
+      c->cnt.table_slots = SPB_ST_SLOTS;
+      SPB_LAUNCH_PHASED_DSMEM(k_smem_dedup, 2, NB, 512, SPB_ST_SLOTS * 4, c->stream, keys, pos, sub, c->F, c->R, T, c->k, bbo + nbits,
+                              (u32*)nullptr, (u32*)nullptr, c->errflag, links, nlinks, lcap);
+    } else {
+      // a sub-bucket beyond the shared-memory table (masses of identical k-mers): groups of sub-buckets through tables in L2
+      u32 gb = nbits > 6 ? 6 : nbits;                // <= 64 groups
+      u64 gmax = 0;
+      for (u64 g = 0; g < (1ull << gb); ++g) gmax = std::max(gmax, bstart[(g + 1) << (nbits - gb)] - bstart[g << (nbits - gb)]);
+      u64 tcap = 1024; while (tcap < 2 * gmax) tcap <<= 1;
+      c->cnt.table_slots = tcap;
+      u64* scratch; ALLOC(scratch, u64, tcap);
+      for (u64 g = 0; g < (1ull << gb); ++g) {
+        const u64 lo = bstart[g << (nbits - gb)], ng = bstart[(g + 1) << (nbits - gb)] - lo;
+        if (ng == 0) continue;
+        dev_memset(c, scratch, 0xFF, tcap * 8);
+        SPB_LAUNCH(k_bkt_insert_list, nblk(ng, TPB), TPB, c->stream, keys, pos, lo, ng, c->F, c->R, T, c->k, scratch, tcap - 1, links, nlinks, lcap,
+                   (u64*)nullptr, 0);
+      }
+      dfree(c, scratch);
+    }
+    nl = dread(c, nlinks);
+    if (nl <= lcap) break;
+    dfree(c, links); lcap = nl;
+  }
+  dfree(c, nlinks); dfree(c, sub); dfree(c, keys); dfree(c, pos);
+  c->mg_owned = true;
+  int r = finish_links(c, links, nl, n_owners, send_counts, links_dev);
+  return r ? r : check_err(c, "spb_mg_owned_links");
 }
 
 // Position side, "links" protocol: the links received for the local slice -> first-appearance bits of the slice.
 int spb_mg_apply_links(spb_ctx* c, const uint64_t* links, uint64_t n, uint64_t pos_lo, uint64_t pos_hi) {
   if (!c) return SPB_EINVAL;
-  if (c->state != 1 || !c->dd_pos) return fail(c, SPB_ESTATE, "spb_mg_apply_links without spb_mg_records");
+  if (c->state != 1 || (!c->dd_pos && !c->mg_owned)) return fail(c, SPB_ESTATE, "spb_mg_apply_links without spb_mg_records / spb_mg_owned_links");
   const u64 P = c->npos_pad, nw32 = P / 32;
   ALLOC(c->mg_seen, u32, P + 8); ALLOC(c->mg_dup, u32, nw32 + 8);
   dev_memset(c, c->mg_dup, 0, (nw32 + 8) * 4);

@@ -401,7 +401,10 @@ __device__ __forceinline__ u64 roll_finish(u32 a, u32 b) {
 }
 __global__ void SPB_LAUNCH_BOUNDS(128)
 k_make_records_roll(const u32* __restrict__ F, const u32* __restrict__ R, const u32* __restrict__ vbits, u64 T, u32 k,
-                    u64 pos_lo, u64 pos_hi, u64 n, u64* __restrict__ keys, u32* __restrict__ pos, u32* obits, u32 spread, RollK K) {
+                    u64 pos_lo, u64 pos_hi, u64 n, u64* __restrict__ keys, u32* __restrict__ pos, u32* obits, u32 spread, RollK K,
+                    u32 own_bits, u32 own_id, u64* own_count, u64 own_cap) {
+  // own_bits > 0 ("owner computes", multi-GPU): only the records whose top own_bits hash bits equal own_id are kept,
+  // compacted behind the counter own_count (order: by warp group, not by position); nothing else is written.
   const u64 g = SPB_GTID();
   const bool alive = g * SPB_RUN < n;
 #ifdef SPB_EMU
@@ -420,6 +423,9 @@ k_make_records_roll(const u32* __restrict__ F, const u32* __restrict__ R, const 
     const u64 pw = p0 + 32ull * w;
     const u32 vb = (alive && pw < T) ? __ldg(vbits + (pw >> 5)) : 0u;
     u32 ow = 0;
+#ifndef SPB_EMU
+    u32 mine = 0;                                    // owned records of this lane's group
+#endif
     for (u32 j = 0; j < 32; ++j) {
       const u64 p = pw + j;
       const bool valid = ((vb >> j) & 1u) && p < pos_hi;
@@ -465,9 +471,12 @@ k_make_records_roll(const u32* __restrict__ F, const u32* __restrict__ R, const 
         if (spread) key = mix64(p);
       }
 #ifdef SPB_EMU
-      keys[p - pos_lo] = key; pos[p - pos_lo] = (spread && !valid) ? SPB_INVALID : (u32)p;
+      if (own_bits) {
+        if (valid && (u32)(key >> (64 - own_bits)) == own_id) { const u64 i = atomicAdd(own_count, 1ull); if (i < own_cap) { keys[i] = key; pos[i] = (u32)p; } }
+      } else { keys[p - pos_lo] = key; pos[p - pos_lo] = (spread && !valid) ? SPB_INVALID : (u32)p; }
 #else
       tile[wid][lane][j] = key;
+      if (own_bits && valid && (u32)(key >> (64 - own_bits)) == own_id) ++mine;
 #endif
     }
     if (alive) obits[pw >> 5] = ow;
@@ -478,9 +487,29 @@ k_make_records_roll(const u32* __restrict__ F, const u32* __restrict__ R, const 
     const u32 rows = g0 >= nruns ? 0u : (u32)min((u64)32, nruns - g0);
     u32 vm = vb;                                     // valid steps of this lane's group (for the spread marking)
     if (pw + 32 > pos_hi) vm = pw >= pos_hi ? 0u : (vm & ((1u << (u32)(pos_hi - pw)) - 1u));
+    u32 pv = (u32)(pos_lo + g0 * SPB_RUN + 32u * w + lane);
+    if (own_bits) {                                  // compaction: one counter update per warp and group
+      u32 incl = mine;
+#pragma unroll
+      for (u32 d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+      const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+      u64 base = 0;
+      if (lane == 0 && total) base = atomicAdd(own_count, (u64)total);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      for (u32 r = 0; r < rows; ++r) {
+        const u32 vr = __shfl_sync(0xffffffffu, vm, r);
+        const u64 off = base + __shfl_sync(0xffffffffu, incl - mine, r);
+        const u64 key = tile[wid][r][lane];
+        const bool own = ((vr >> lane) & 1u) && (u32)(key >> (64 - own_bits)) == own_id;
+        const u32 bal = __ballot_sync(0xffffffffu, own);
+        const u64 i = off + __popc(bal & ((1u << lane) - 1u));
+        if (own && i < own_cap) { keys[i] = key; pos[i] = pv + r * SPB_RUN; }
+      }
+      __syncwarp();
+      continue;
+    }
     u64* kq = keys + (g0 * SPB_RUN + 32u * w + lane);
     u32* pq = pos + (g0 * SPB_RUN + 32u * w + lane);
-    u32 pv = (u32)(pos_lo + g0 * SPB_RUN + 32u * w + lane);
     for (u32 r = 0; r < rows; ++r) {                 // row r = the 32 keys of lane r
       const u32 vr = __shfl_sync(0xffffffffu, vm, r);
       kq[(u64)r * SPB_RUN] = tile[wid][r][lane];
@@ -714,7 +743,10 @@ template <class V> __device__ __forceinline__ V st_pick(const V (&a)[SPB_ST_BATC
 }
 __global__ void SPB_LAUNCH_BOUNDS2(512, SPB_ST_MINB)
 k_smem_dedup(const u64* __restrict__ keys, const u32* __restrict__ pos, const u64* __restrict__ sub, const u32* __restrict__ F,
-             const u32* __restrict__ R, u64 T, u32 k, u32 nbits, u32* __restrict__ seenpos, u32* dupbits, u32* err) {
+             const u32* __restrict__ R, u64 T, u32 k, u32 nbits, u32* __restrict__ seenpos, u32* dupbits, u32* err,
+             u64* __restrict__ links, u64* nlinks, u64 lcap) {
+  // links != nullptr (multi-GPU owner): the exceptions are appended to a list (from << 32 | to) instead of being written
+  // in place.  The first appearance is decided by comparing positions, so the records may arrive in any order.
   SPB_DYN_SHARED(u32, tab, SPB_ST_SLOTS);
   const u64 seg0 = sub[blockIdx.x];
   const u64 n64 = sub[blockIdx.x + 1] - seg0;
@@ -762,14 +794,17 @@ k_smem_dedup(const u64* __restrict__ keys, const u32* __restrict__ pos, const u6
               const bool o = key & 1, oq = keys[rq] & 1;
               if (win_cmp(o ? F : R, o ? p : T - p - k, oq ? F : R, oq ? q : T - q - k, k) == 0) {
                 u64 from = p, to = q;                 // default: we link to the installed record
-                if (v < old) {
-                  const u32 prev = atomicMin(&tab[s], v);
-                  const u64 pq = pos[seg0 + (prev & 0x3FFFu)];
-                  if (prev > v) { from = pq; to = p; }  // we displaced it: it links to us
-                  else to = pq;
+                if (p < q) {                          // ours is the earlier position: take the slot over
+                  u32 cur = old; u64 pc = q;
+                  for (;;) {
+                    const u32 prev = atomicCAS(&tab[s], cur, v);
+                    if (prev == cur) { from = pc; to = p; break; }       // we displaced it: it links to us
+                    cur = prev; pc = pos[seg0 + (cur & 0x3FFFu)];        // another instance of the k-mer got in between
+                    if (pc < p) { to = pc; break; }
+                  }
                 }
-                seenpos[from] = (u32)to;
-                atomicOr(dupbits + (from >> 5), 1u << (from & 31));
+                if (links) { const u64 slot = warp_append(nlinks, true); if (slot < lcap) links[slot] = (from << 32) | to; }
+                else { seenpos[from] = (u32)to; atomicOr(dupbits + (from >> 5), 1u << (from & 31)); }
                 same = true;
               }
             }

@@ -29,10 +29,18 @@ def main():
         path = os.path.join(helpers.DATA, fa)
         if os.path.exists(path):
             cases.append((path, 301, helpers.load_json(name)))
-    for sd, k, want in cases:
-        A = Assembler(sd, k, engine=_capi.Engine(device=local, stream=torch.cuda.current_stream().cuda_stream), distributed=True)
-        assert A._eng.kind == "cuda sm_100a"
-        helpers.assert_summary(digests.summarize(A.to_result()), want)
+    used = set()
+    for proto in (None, "owned", "links", "reps"):           # None: chosen by the duplicate-rate probe
+        if proto:
+            os.environ["SPB_MG_PROTOCOL"] = proto
+        for sd, k, want in cases:
+            if proto and isinstance(sd, str):
+                continue                                      # the large KAT sets run once, with the probe's choice
+            A = Assembler(sd, k, engine=_capi.Engine(device=local, stream=torch.cuda.current_stream().cuda_stream), distributed=True)
+            assert A._eng.kind == "cuda sm_100a"
+            used.add(A._eng.mg_protocol)
+            helpers.assert_summary(digests.summarize(A.to_result()), want)
+    assert used == {"owned", "links", "reps"}, used
     dist.barrier()
     if dist.get_rank() == 0:
         print(f"multi-GPU parity OK on {dist.get_world_size()} ranks, {len(cases)} cases")

@@ -112,6 +112,7 @@ VARIANTS = [
     {"SPB_DEDUP": "smem", "SPB_SMEM_AVG": "40", "SPB_EMU_ORDER": "shuffle"},
     {"SPB_SWITCH_MIN": "1", "SPB_CHUNK_BITS": "8", "SPB_SMEM_AVG": "100"},   # adaptive default: small-table probe, then one of the three schemes
     {"SPB_SWITCH_MIN": "1", "SPB_CHUNK_BITS": "9", "SPB_NO_SMEM_TABLES": "1", "SPB_EMU_ORDER": "reverse"},
+    {"SPB_DEDUP": "smem", "SPB_SMEM_LIMIT": "10"},                   # a sub-bucket beyond the table -> L2-table path instead
     {"SPB_DEDUP": "smem", "SPB_SMEM_AVG": "1"},                      # absurd split: few hash bits left -> falls back or clusters
 ]
 
