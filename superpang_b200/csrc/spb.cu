@@ -737,7 +737,7 @@ static int dedup_smem_links(spb_ctx* c) {
   u64 nmax = 0;
   for (u64 b = 0; b < NB; ++b) nmax = std::max(nmax, c->dd_bstart_h[b + 1] - c->dd_bstart_h[b]);
   if (nmax <= smem_limit())
-    SPB_LAUNCH_PHASED_DSMEM(k_smem_dedup, 2, NB, 512, SPB_ST_SLOTS * 4, c->stream, c->dd_keys, c->dd_pos, c->dd_bstart, c->F, c->R, T, c->k, nbits,
+    SPB_LAUNCH_PHASED_DSMEM(k_smem_dedup<false>, 2, NB, 512, SPB_ST_SLOTS * 4, c->stream, c->dd_keys, c->dd_pos, c->dd_bstart, c->F, c->R, T, c->k, nbits,
                             seenpos, dupbits, c->errflag, (u64*)nullptr, (u64*)nullptr, 0ull);
   dfree(c, c->dd_keys); dfree(c, c->dd_pos); dfree(c, c->dd_bstart);
   if (nmax > smem_limit()) { dfree(c, seenpos); dfree(c, dupbits); return 1; }
@@ -1114,7 +1114,7 @@ int spb_mg_owned_links(spb_ctx* c, uint32_t rank, uint32_t n_owners, uint64_t* s
     if (n_own == 0) break;
     if (nmax <= smem_limit()) {
       c->cnt.table_slots = SPB_ST_SLOTS;
-      SPB_LAUNCH_PHASED_DSMEM(k_smem_dedup, 2, NB, 512, SPB_ST_SLOTS * 4, c->stream, keys, pos, sub, c->F, c->R, T, c->k, bbo + nbits,
+      SPB_LAUNCH_PHASED_DSMEM(k_smem_dedup<true>, 2, NB, 512, SPB_ST_SLOTS * 4, c->stream, keys, pos, sub, c->F, c->R, T, c->k, bbo + nbits,
                               (u32*)nullptr, (u32*)nullptr, c->errflag, links, nlinks, lcap);
     } else {
       // a sub-bucket beyond the shared-memory table (masses of identical k-mers): groups of sub-buckets through tables in L2

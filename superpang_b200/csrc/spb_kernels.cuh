@@ -722,10 +722,10 @@ k_bkt_insert_links(const u64* __restrict__ keys, const u32* __restrict__ pos, u6
 // ------------------------------------------------------------------------------------ shared-memory tables
 // Two-level form of the "links" dedup: the records are radix-sorted on the top `nbits` hash bits into sub-buckets of
 // ~7.6 K records, and one CTA deduplicates a sub-bucket in a hash table in shared memory -- no global atomics at all,
-// the records stream through once.  slot = tag (18 hash bits) << 14 | index of the record inside the sub-bucket; the
-// sort is stable, so index order is position order and atomicMin on a slot keeps the first appearance.  Exceptions
-// leave links exactly as in k_bkt_insert_links.  Records are loaded four at a time per thread (independent loads in
-// flight) before their inserts.
+// the records stream through once.  slot = tag (18 hash bits) << 14 | index of the record inside the sub-bucket; a
+// tag match is verified on the full 2k bits, and the earlier POSITION keeps the slot (CAS take-over), so the records
+// of a sub-bucket may arrive in any order.  Exceptions leave links exactly as in k_bkt_insert_links.  Records are
+// loaded four at a time per thread (independent loads in flight) before their inserts.
 #define SPB_ST_SLOTS 16384u          // 64 KB of shared memory: three CTAs per SM
 #define SPB_ST_LIMIT 12288u          // records per sub-bucket the table accepts (load <= 0.75); more -> caller falls back
 #define SPB_ST_EMPTY 0xFFFFFFFFu
@@ -741,12 +741,13 @@ template <class V> __device__ __forceinline__ V st_pick(const V (&a)[SPB_ST_BATC
   for (u32 j = 1; j < SPB_ST_BATCH; ++j) if (u == j) r = a[j];
   return r;
 }
-__global__ void SPB_LAUNCH_BOUNDS2(512, SPB_ST_MINB)
+template <bool LIST> __global__ void SPB_LAUNCH_BOUNDS2(512, SPB_ST_MINB)
 k_smem_dedup(const u64* __restrict__ keys, const u32* __restrict__ pos, const u64* __restrict__ sub, const u32* __restrict__ F,
              const u32* __restrict__ R, u64 T, u32 k, u32 nbits, u32* __restrict__ seenpos, u32* dupbits, u32* err,
              u64* __restrict__ links, u64* nlinks, u64 lcap) {
-  // links != nullptr (multi-GPU owner): the exceptions are appended to a list (from << 32 | to) instead of being written
-  // in place.  The first appearance is decided by comparing positions, so the records may arrive in any order.
+  // LIST (multi-GPU owner): the exceptions are appended to a list (from << 32 | to) instead of being written in place,
+  // and the first appearance is decided by comparing positions (CAS take-over): the records arrive in any order.
+  // !LIST (single GPU): the radix sort is stable, so index order is position order and atomicMin on the slot suffices.
   SPB_DYN_SHARED(u32, tab, SPB_ST_SLOTS);
   const u64 seg0 = sub[blockIdx.x];
   const u64 n64 = sub[blockIdx.x + 1] - seg0;
@@ -794,17 +795,28 @@ k_smem_dedup(const u64* __restrict__ keys, const u32* __restrict__ pos, const u6
               const bool o = key & 1, oq = keys[rq] & 1;
               if (win_cmp(o ? F : R, o ? p : T - p - k, oq ? F : R, oq ? q : T - q - k, k) == 0) {
                 u64 from = p, to = q;                 // default: we link to the installed record
-                if (p < q) {                          // ours is the earlier position: take the slot over
-                  u32 cur = old; u64 pc = q;
-                  for (;;) {
-                    const u32 prev = atomicCAS(&tab[s], cur, v);
-                    if (prev == cur) { from = pc; to = p; break; }       // we displaced it: it links to us
-                    cur = prev; pc = pos[seg0 + (cur & 0x3FFFu)];        // another instance of the k-mer got in between
-                    if (pc < p) { to = pc; break; }
+                if (LIST) {
+                  if (p < q) {                        // ours is the earlier position: take the slot over
+                    u32 cur = old; u64 pc = q;
+                    for (;;) {
+                      const u32 prev = atomicCAS(&tab[s], cur, v);
+                      if (prev == cur) { from = pc; to = p; break; }     // we displaced it: it links to us
+                      cur = prev; pc = pos[seg0 + (cur & 0x3FFFu)];      // another instance of the k-mer got in between
+                      if (pc < p) { to = pc; break; }
+                    }
                   }
+                  const u64 slot = warp_append(nlinks, true);
+                  if (slot < lcap) links[slot] = (from << 32) | to;
+                } else {
+                  if (v < old) {
+                    const u32 prev = atomicMin(&tab[s], v);
+                    const u64 pq = pos[seg0 + (prev & 0x3FFFu)];
+                    if (prev > v) { from = pq; to = p; }                 // we displaced it: it links to us
+                    else to = pq;
+                  }
+                  seenpos[from] = (u32)to;
+                  atomicOr(dupbits + (from >> 5), 1u << (from & 31));
                 }
-                if (links) { const u64 slot = warp_append(nlinks, true); if (slot < lcap) links[slot] = (from << 32) | to; }
-                else { seenpos[from] = (u32)to; atomicOr(dupbits + (from >> 5), 1u << (from & 31)); }
                 same = true;
               }
             }

@@ -1,6 +1,8 @@
 """CPU tier: the CUDA kernels' LOGIC, executed by the host emulator build (tests/emu, -DSPB_EMU),
 against the reference goldens and the oracle.  The emulator is test infrastructure; the product
 never loads it.  The `-m gpu` tier runs the same checks through the real sm_100a library."""
+import os
+
 import numpy as np
 import pytest
 from hypothesis import HealthCheck, given, settings, strategies as st
@@ -70,7 +72,7 @@ def genome_sets(draw):
     return seqs
 
 
-@settings(max_examples=120, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(max_examples=int(os.environ.get("SPB_HYP_EXAMPLES", "120")), deadline=None, suppress_health_check=list(HealthCheck))
 @given(genome_sets(), st.sampled_from([9, 15, 21, 31]))
 def test_emu_matches_oracle_random(emu_lib, seqs, k):
     try:
