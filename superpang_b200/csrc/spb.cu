@@ -771,10 +771,14 @@ static int probe_sample_chunks(spb_ctx* c, u64 CH, u64* n_ext, u64* n_dup, u64* 
   ALLOC(wbits, u32, nbw); ALLOC(dbits, u32, nbw); ALLOC(seenpos, u32, 2 * CH + 8);
   dev_memset(c, slots, 0xFF, cap * 8); dev_memset(c, extc, 0, 16);
   dev_memset(c, dbits, 0, nbw * 4); dev_memset(c, wbits, 0, nbw * 4);
+  u32 *obits_save = c->obits, *otmp; ALLOC(otmp, u32, nbw);           // the probe must not touch the real orientation bitmap
+  c->obits = otmp;
   launch_extract_k(c, 0, CH, slots, cap, seenpos, wbits, dbits, nullptr, nullptr);
+  c->obits = otmp - shift / 32;
   launch_extract_k(c, mid, hi, slots, cap, seenpos - shift, wbits - shift / 32, dbits - shift / 32, arec - shift / 32, extc);
+  c->obits = obits_save;
   *n_ext = dread(c, extc); *n_dup = dread(c, extc + 1); *chunk_n = hi - mid;
-  dfree(c, slots); dfree(c, arec); dfree(c, extc); dfree(c, wbits); dfree(c, dbits); dfree(c, seenpos);
+  dfree(c, slots); dfree(c, arec); dfree(c, extc); dfree(c, wbits); dfree(c, dbits); dfree(c, seenpos); dfree(c, otmp);
   return 0;
 }
 
@@ -952,28 +956,14 @@ int spb_mg_probe(spb_ctx* c, double* ext_ratio, double* dup_ratio) {
 #endif
   u64 CH = 1ull << 22;
   if (const char* e = getenv("SPB_CHUNK_BITS")) { int b = atoi(e); if (b >= 8 && b <= 32) CH = 1ull << b; }
-  const u64 P0 = nblk(c->T, TPB) * TPB + TPB;
   *ext_ratio = 0; *dup_ratio = 0;
-  if (P0 <= CH) return SPB_OK;                       // a single chunk: nothing to compare against
-  const u64 hi = std::min(P0, 2 * CH);
-  u64 cap = 1024; while (cap < 2 * hi) cap <<= 1;
-  u64 *slots, *arec, *extc; u32 *seenpos, *wbits, *dbits, *obits_save = c->obits, *otmp;
-  ALLOC(slots, u64, cap); ALLOC(arec, u64, hi / 32 + 8); ALLOC(extc, u64, 2);
-  ALLOC(seenpos, u32, hi + 8); ALLOC(wbits, u32, hi / 32 + 8); ALLOC(dbits, u32, hi / 32 + 8); ALLOC(otmp, u32, hi / 32 + 8);
-  dev_memset(c, slots, 0xFF, cap * 8); dev_memset(c, extc, 0, 16);
-  dev_memset(c, wbits, 0, (hi / 32 + 8) * 4); dev_memset(c, dbits, 0, (hi / 32 + 8) * 4); dev_memset(c, otmp, 0, (hi / 32 + 8) * 4);
-  c->obits = otmp;                                   // the probe must not touch the real orientation bitmap
-  launch_extract_k(c, 0, CH, slots, cap, seenpos, wbits, dbits, nullptr, nullptr);
-  launch_extract_k(c, CH, hi, slots, cap, seenpos, wbits, dbits, arec, extc);
-  c->obits = obits_save;
-  u64 n_ext = dread(c, extc), n_dup = dread(c, extc + 1);
-  *ext_ratio = (double)n_ext / (double)(hi - CH); *dup_ratio = (double)n_dup / (double)(hi - CH);
-  dfree(c, slots); dfree(c, arec); dfree(c, extc); dfree(c, seenpos); dfree(c, wbits); dfree(c, dbits); dfree(c, otmp);
+  if (c->npos_pad <= CH) return SPB_OK;              // a single chunk: nothing to compare against
+  u64 n_ext = 0, n_dup = 0, chunk_n = 0;
+  PRIM(probe_sample_chunks(c, std::max<u64>(CH / 2, 256), &n_ext, &n_dup, &chunk_n));
+  if (chunk_n) { *ext_ratio = (double)n_ext / (double)chunk_n; *dup_ratio = (double)n_dup / (double)chunk_n; }
   return check_err(c, "spb_mg_probe");
 }
 
-// Owner side, "links" protocol: dedup of the received records in L2-resident sub-bucket tables; returns only the
-// exceptions as (position -> first position) links, sorted by position, with per-destination-rank counts.
 // links (from << 32 | to): sort by position, resolve chains, split by the rank that owns the position slice
 static int finish_links(spb_ctx* c, u64* links, u64 nl, u32 n_owners, uint64_t* send_counts, void** links_dev) {
   u64* tmp; ALLOC(tmp, u64, nl + 1);
@@ -992,6 +982,8 @@ static int finish_links(spb_ctx* c, u64* links, u64 nl, u32 n_owners, uint64_t* 
   return 0;
 }
 
+// Owner side, "links" protocol: dedup of the received records in L2-resident sub-bucket tables; returns only the
+// exceptions as (position -> first position) links, sorted by position, with per-destination-rank counts.
 int spb_mg_dedup_links(spb_ctx* c, uint64_t* keys_io, uint32_t* pos_io, uint64_t n_total, uint32_t n_owners, uint64_t* send_counts,
                        void** links_dev) {
   if (!c) return SPB_EINVAL;
