@@ -981,6 +981,23 @@ k_assign_ids(const u32* sp_in, u32* sp, const u32* __restrict__ vbits, u64 T, u6
     bool first[SPB_JU], mine[SPB_JU], act[SPB_JU];
 #pragma unroll
     for (u32 j = 0; j <= SPB_JU; ++j) f[j] = wd0 + j <= nwords ? __ldg(fbits + wd0 + j) : 0u;
+    bool allfirst = wd0 + SPB_JU <= nwords;
+#pragma unroll
+    for (u32 j = 0; j < SPB_JU; ++j) allfirst = allfirst && f[j] == 0xFFFFFFFFu;
+    if (allfirst) {                                  // warp-uniform: 128 first appearances in a row, ids are consecutive
+      u32 b0[SPB_JU], w0[SPB_JU];
+#pragma unroll
+      for (u32 j = 0; j < SPB_JU; ++j) { b0[j] = __ldg(blkoff + ((wd0 + j) >> 3)); w0[j] = __ldg(wpre + wd0 + j); }
+#pragma unroll
+      for (u32 j = 0; j < SPB_JU; ++j) {
+        const u64 p = (wd0 + j) * 32 + lane;
+        const u32 vid = b0[j] + w0[j] + lane;
+        if (p >= lo && p < hi) sp[p] = vid;
+        v2pos[vid] = (u32)p;
+        vflags[vid] = (lane < 31 || (f[j + 1] & 1u)) ? VF_R : 0;
+      }
+      continue;
+    }
 #pragma unroll
     for (u32 j = 0; j < SPB_JU; ++j) {               // stage 1: the link of every repeated instance
       const u64 wd = wd0 + j, p = wd * 32 + lane;
