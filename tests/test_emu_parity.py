@@ -87,6 +87,16 @@ def test_emu_matches_oracle_random(emu_lib, seqs, k):
     digests.assert_same(want, run_emu(emu_lib, seqs, k).to_result())
 
 
+@pytest.mark.parametrize("k,env", [(1001, {}), (2001, {}), (1001, {"SPB_DEDUP": "smem", "SPB_SMEM_AVG": "500"}), (75, {"SPB_DEDUP": "smem"})])
+def test_emu_large_k_matches_oracle(emu_lib, monkeypatch, k, env):
+    """k beyond the specialised widths (101 / 301 / 501): the generic limb loops, the rolling hashes with a long window."""
+    for key, v in env.items():
+        monkeypatch.setenv(key, v)
+    sd = helpers.synth_seqdict(3, 12000 if k > 500 else 4000, 0.99, 7, "block")
+    want = dbg_oracle.run_oracle(sd, k)
+    digests.assert_same(want, run_emu(emu_lib, sd, k).to_result())
+
+
 def test_rejects_bad_input(emu_lib):
     with pytest.raises(_capi.SpbError):
         run_emu(emu_lib, {"a": "ACGT" * 20}, 30)           # even k
