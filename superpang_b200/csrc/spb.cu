@@ -628,7 +628,7 @@ static int dd_graph(spb_ctx* c) {
   u64 nE = 0;
   PRIM(prim_scan_u32(c, ecnt, eoff, nT, &nE));
   ALLOC(c->edges, u32, 2 * nE + 2);
-  SPB_LAUNCH(k_edge_write, nblk(nV, TPB), TPB, c->stream, g, eoff, c->edges);
+  SPB_LAUNCH(k_edge_write, std::min<u64>(nblk(nV, TPB), 148 * 32), TPB, c->stream, g, eoff, c->edges);
   dfree(c, ecnt); dfree(c, eoff);
   c->cnt.n_vertices = nV; c->cnt.n_edges = nE; c->cnt.n_junction = c->nJ;
   return 0;

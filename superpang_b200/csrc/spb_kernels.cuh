@@ -1790,26 +1790,40 @@ __device__ __forceinline__ u32 edge_rows_of(const GView& g, u32 v, u32 fl) {
   return c;
 }
 __global__ void k_edge_write(GView g, const u32* __restrict__ off8, u32* __restrict__ edges) {
-  u64 v = SPB_GTID();
-  if (v >= g.nV) return;
-  u32 i = (u32)(v & 7);
-  u64 w = *(const u64*)(g.vflags + (v & ~7ull));
-  u64 below = i ? (w & ((1ull << (8 * i)) - 1)) : 0;
-  u64 o = off8[v >> 3];
-  if (!(below & (0x0101010101010101ull * VF_HASJ))) o += __popcll(below & (0x0101010101010101ull * VF_R));
-  else for (u32 j = 0; j < i; ++j) o += edge_rows_of(g, (u32)(v - i + j), (u32)(w >> (8 * j)) & 0xFF);
-  u32 fl = (u32)(w >> (8 * i)) & 0xFF;
-  bool r = (fl & VF_R) != 0;
+  // grid-stride, four vertices per thread and iteration with their loads issued together
+  const u64 stride = (u64)gridDim.x * blockDim.x;
   uint2* rows = (uint2*)edges;
-  if (fl & VF_HASJ) {
-    u32 j = lower_bound_key(g.Jk, g.nJ, ((u64)v << 32) | v);
-    for (; j < g.nJ && (u32)(g.Jk[j] >> 32) == (u32)v; ++j) {
-      u32 d = (u32)g.Jk[j];
-      if (r && d > (u32)v + 1) { rows[o++] = make_uint2((u32)v, (u32)v + 1); r = false; }
-      rows[o++] = make_uint2((u32)v, d);
+  for (u64 vb = SPB_GTID(); vb < g.nV; vb += 4 * stride) {
+    u64 wv[4]; u32 ov[4];
+#pragma unroll
+    for (u32 q = 0; q < 4; ++q) {
+      const u64 v = vb + q * stride;
+      wv[q] = v < g.nV ? *(const u64*)(g.vflags + (v & ~7ull)) : 0ull;
+      ov[q] = v < g.nV ? off8[v >> 3] : 0u;
+    }
+#pragma unroll
+    for (u32 q = 0; q < 4; ++q) {
+      const u64 v = vb + q * stride;
+      if (v >= g.nV) break;
+      const u32 i = (u32)(v & 7);
+      const u64 w = wv[q];
+      const u64 below = i ? (w & ((1ull << (8 * i)) - 1)) : 0;
+      u64 o = ov[q];
+      if (!(below & (0x0101010101010101ull * VF_HASJ))) o += __popcll(below & (0x0101010101010101ull * VF_R));
+      else for (u32 j = 0; j < i; ++j) o += edge_rows_of(g, (u32)(v - i + j), (u32)(w >> (8 * j)) & 0xFF);
+      const u32 fl = (u32)(w >> (8 * i)) & 0xFF;
+      bool r = (fl & VF_R) != 0;
+      if (fl & VF_HASJ) {
+        u32 j = lower_bound_key(g.Jk, g.nJ, ((u64)v << 32) | v);
+        for (; j < g.nJ && (u32)(g.Jk[j] >> 32) == (u32)v; ++j) {
+          u32 d = (u32)g.Jk[j];
+          if (r && d > (u32)v + 1) { rows[o++] = make_uint2((u32)v, (u32)v + 1); r = false; }
+          rows[o++] = make_uint2((u32)v, d);
+        }
+      }
+      if (r) rows[o] = make_uint2((u32)v, (u32)v + 1);
     }
   }
-  if (r) rows[o] = make_uint2((u32)v, (u32)v + 1);
 }
 
 // seqPaths (reference lib/vtools.pyx:18-49).  Along a sequence the vertex ids form monotone runs with
