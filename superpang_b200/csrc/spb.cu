@@ -1289,8 +1289,11 @@ int spb_compact(spb_ctx* c, spb_counts* out) {
   u64 nchunks = 0;
   PRIM(prim_scan_u32(c, nch, choff, nD, &nchunks));
   if (nchunks >= (1ull << 31)) return fail(c, SPB_EINVAL, "input too large for 32-bit dart offsets");
-  SPB_LAUNCH(k_emit_darts, nchunks, 256, c->stream, choff, nD, c->plo, c->phi, c->dart_nbp, acc[cur], k, T, c->F, c->R, c->v2pos, c->voff,
-             c->soff, c->verts, c->seqs, c->vnbp);
+  ChunkParams* cpar; ALLOC(cpar, ChunkParams, nchunks + 1);
+  SPB_LAUNCH(k_chunk_table, nblk(nchunks, TPB), TPB, c->stream, (u32)nchunks, choff, nD, c->plo, c->phi, c->dart_nbp, acc[cur], k, T, c->v2pos,
+             c->voff, c->soff, cpar);
+  SPB_LAUNCH(k_emit_darts, nchunks, 256, c->stream, cpar, c->F, c->R, c->verts, c->seqs, c->vnbp);
+  dfree(c, cpar);
   SPB_LAUNCH(k_emit_short, std::min<u64>(nblk((u64)nD * 32, 256), 148 * 32), 256, c->stream, nD, c->plo, c->phi, c->dart_nbp, acc[cur], k, T,
              c->F, c->R, c->v2pos, c->voff, c->soff, c->verts, c->seqs, c->vnbp);
   dfree(c, nch); dfree(c, choff); dfree(c, head_nbp); dfree(c, nxt);

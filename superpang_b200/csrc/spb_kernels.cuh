@@ -1514,19 +1514,19 @@ __device__ __forceinline__ ChunkParams chunk_params(u32 c, const u32* choff, u32
   q.n = len - q.t0 < SPB_CHUNK ? len - q.t0 : SPB_CHUNK;
   return q;
 }
+// parameters of every chunk, one thread per chunk: the binary search and the dependent table loads of all chunks run in
+// parallel here instead of once per block at the head of k_emit_darts (where they were a serial latency chain)
+__global__ void k_chunk_table(u32 nchunks, const u32* __restrict__ choff, u32 nD, const u32* __restrict__ plo, const u32* __restrict__ phi,
+                              const u32* __restrict__ dart_nbp, const u32* __restrict__ acc, u32 k, u64 T, const u32* __restrict__ v2pos,
+                              const u64* __restrict__ voff, const u64* __restrict__ soff, ChunkParams* __restrict__ out) {
+  u64 c = SPB_GTID();
+  if (c >= nchunks) return;
+  out[c] = chunk_params((u32)c, choff, nD, plo, phi, dart_nbp, acc, k, T, v2pos, voff, soff);
+}
 __global__ void SPB_LAUNCH_BOUNDS(256)
-k_emit_darts(const u32* __restrict__ choff, u32 nD, const u32* __restrict__ plo, const u32* __restrict__ phi,
-             const u32* __restrict__ dart_nbp, const u32* __restrict__ acc, u32 k, u64 T, const u32* __restrict__ F,
-             const u32* __restrict__ R, const u32* __restrict__ v2pos, const u64* __restrict__ voff,
-             const u64* __restrict__ soff, u32* __restrict__ verts, u8* __restrict__ seq, u32* __restrict__ vnbp) {
-#ifdef SPB_EMU
-  ChunkParams q = chunk_params(blockIdx.x, choff, nD, plo, phi, dart_nbp, acc, k, T, v2pos, voff, soff);
-#else
-  __shared__ ChunkParams qs;                        // one binary search per block instead of one per thread
-  if (threadIdx.x == 0) qs = chunk_params(blockIdx.x, choff, nD, plo, phi, dart_nbp, acc, k, T, v2pos, voff, soff);
-  __syncthreads();
-  ChunkParams q = qs;
-#endif
+k_emit_darts(const ChunkParams* __restrict__ cp, const u32* __restrict__ F, const u32* __restrict__ R,
+             u32* __restrict__ verts, u8* __restrict__ seq, u32* __restrict__ vnbp) {
+  const ChunkParams q = cp[blockIdx.x];
   const u32* S = q.up ? F : R;
   for (u32 t = q.t0 + threadIdx.x; t < q.t0 + q.n; t += blockDim.x) {
     u32 v = q.up ? q.lo + t : q.hi - t;
