@@ -820,7 +820,7 @@ k_smem_dedup(const u64* __restrict__ keys, const u32* __restrict__ pos, const u6
                 same = true;
               }
             }
-            if (same) active = false; else s = (s + 1) & (SPB_ST_SLOTS - 1);
+            if (same) active = false; else s = (s + ((tag & (SPB_ST_SLOTS - 1)) | 1u)) & (SPB_ST_SLOTS - 1);   // double hashing: no clusters
           }
         }
         if (__all_sync(0xffffffffu, !active && u >= SPB_ST_BATCH)) break;
