@@ -153,6 +153,11 @@ int spb_get_nbp_origins(spb_ctx* ctx, uint64_t* off, uint32_t* seq_idx);
  * of the reverse-orientation partner of every NBP (the pairs of `lib/Assembler.py:405-455`).  Call once with NULL
  * buffers to learn *n_edges. */
 int spb_get_nbp_graph(spb_ctx* ctx, uint64_t* n_edges, uint64_t* off, uint32_t* succ, uint32_t* rev);
+/* Orientation counts: counts uint32[n_nbp], counts[i] = number of loaded sequences whose string
+ * contains the sequence of raw NBP i, i.e. that walk the NBP in its own orientation -- what the reference accumulates
+ * into nv2rightOrientation from get_seqPaths_NBPs (`lib/Assembler.py:1121-1139`, `:448-453`), including the effect of
+ * the compress_vertices leading-zero quirk on its vertex_overlap pre-filter (`lib/vtools.pyx:29-45`). */
+int spb_get_nbp_orientation_counts(spb_ctx* ctx, uint32_t* counts);
 /* Current counters (n_seq_intervals is filled by the first spb_get_seq_intervals call, which may
  * be made with NULL buffers just to size them). */
 int spb_get_counts(spb_ctx* ctx, spb_counts* out);

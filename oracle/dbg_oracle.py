@@ -414,3 +414,21 @@ def run_oracle(fasta_or_dict, k=301, with_origins=True):
         _sps=dbg["sps"],
         _comp=comp,
     )
+
+
+def nbp_orientation_counts(nbps, seqs):
+    """for every raw NBP (vertices, sequence, ...) the number of input sequences that contain its
+    string, as the reference accumulates it into nv2rightOrientation (lib/Assembler.py:448-453) from
+    get_seqPaths_NBPs (:1121-1139).  The pre-filter there, `vertex_overlap(compress_vertices(NBP), seqPath) == refLen`
+    (:1135), is implied by the substring test (:1137) except for the compress_vertices leading-zero quirk
+    (lib/vtools.pyx:29-45): a vertex list whose smallest vertex is 1 is recorded as holding vertex 0 as well, and so
+    is the path of every sequence that holds vertex 1, which makes the overlap refLen + 1 -- such an NBP is never
+    counted."""
+    out = []
+    for nbp in nbps:
+        verts, seq = nbp[0], nbp[1]
+        if min(verts) == 1:
+            out.append(0)
+            continue
+        out.append(sum(1 for s in seqs if seq in s))
+    return out

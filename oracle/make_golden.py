@@ -44,6 +44,7 @@ def full(res):
         seqPaths={n: np.asarray(v).tolist() for n, v in res["seqPaths"].items()},
         seqLimits=list(res["seqLimits"]),
         nbps=[[list(v), s, list(o), int(c), bool(cy)] for v, s, o, c, cy in res["nbps"]],
+        orient_counts=[int(x) for x in res["orient_counts"]],
     )
 
 

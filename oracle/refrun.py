@@ -121,8 +121,29 @@ def run_reference(fasta, ksize=301, threads=1, debug=True, with_origins=True, qu
                     oris = tuple(sorted({o.split('_Nsplit_')[0] for o in good}))
                 nbps_out.append((tuple(int(x) for x in NBP), seq, oris, ic, isCycle))
 
+        # ---- orientation counts: the reference's own get_seqPaths_NBPs (:1121-1139) over all NBP pairs, counted as at
+        #      :448-453 (nv2rightOrientation); -1 where the reference defines no pair (vertex set not shared by exactly two NBPs)
+        from collections import defaultdict as _dd
+        vertex2NBP = {i: n[0] for i, n in enumerate(nbps_out)}
+        NBP2seq = {n[0]: n[1] for n in nbps_out}
+        groups = _dd(list)
+        for i, n in enumerate(nbps_out):
+            groups[frozenset(n[0])].append(i)
+        psets = {fs: tuple(nvs) for fs, nvs in groups.items() if len(nvs) == 2 and len(NBP2seq) == len(nbps_out)}
+        orient = [-1] * len(nbps_out)
+        if psets:
+            names_ = list(A.seqPaths)
+            sets_ = A.multimap(A.get_seqPaths_NBPs, 1, names_, A.seqPaths, psets, NBP2seq, vertex2NBP, A.seqDict)
+            for nvs in psets.values():
+                for nv in nvs:
+                    orient[nv] = 0
+            for spGS in sets_:
+                for nv in spGS:
+                    orient[nv] += 1
+
     edges = A.DBG._edges.astype(np.uint32)
     res = dict(
+        orient_counts=orient,
         k=ksize,
         names=list(A.seqDict),
         n_inst=int(sum(len(s) - ksize + 1 for s in A.seqDict.values() if len(s) > ksize)),

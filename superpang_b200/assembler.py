@@ -170,6 +170,14 @@ class Assembler:
             out.append((v, s, o, int(comp[i]), bool(cyc[i])))
         return out
 
+    def nbp_orientation_counts(self):
+        """{vertex tuple of a raw NBP: number of input sequences that contain its string} -- what the reference
+        accumulates into nv2rightOrientation (`lib/Assembler.py:448-453`) from `get_seqPaths_NBPs` (`:1121-1139`)."""
+        self.compact()
+        voff, verts, _, _ = self._eng.nbps()
+        counts = self._eng.nbp_orientation_counts()
+        return {tuple(verts[int(voff[i]):int(voff[i + 1])].tolist()): int(counts[i]) for i in range(len(counts))}
+
     def collect_nbps(self):
         """Per component, in the reference's order (size descending, ties by label; `lib/Assembler.py:271-273`)."""
         raw = self.raw_nbps()

@@ -1495,6 +1495,58 @@ int spb_get_nbp_graph(spb_ctx* c, uint64_t* n_edges, uint64_t* off, uint32_t* su
   dev_sync(c);
   return SPB_OK;
 }
+// SURVEY 8(f) row 1, second half: per raw NBP, the number of input sequences that contain its string in their own
+// orientation (reference get_seqPaths_NBPs, lib/Assembler.py:1121-1139, counted into nv2rightOrientation at :448-453).
+int spb_get_nbp_orientation_counts(spb_ctx* c, uint32_t* counts) {
+  NEED(3);
+  if (!counts) return SPB_EINVAL;
+  int r = build_nbp_graph(c);                        // start keys are rebuilt below; the graph supplies the partner ids
+  if (r) return r;
+  const u32 nN = c->nN;
+  const u64 T = c->T;
+  if (nN == 0) return SPB_OK;
+  u64 *key, *key2; u32 *id, *id2;
+  ALLOC(key, u64, nN + 1); ALLOC(key2, u64, nN + 1); ALLOC(id, u32, nN + 1); ALLOC(id2, u32, nN + 1);
+  SPB_LAUNCH(k_nbpg_keys, nblk(nN, TPB), TPB, c->stream, c->nt, nN, key, id);
+  PRIM(prim_partition_u64_u32(c, key, id, key2, id2, nN, 0, 34));
+  dfree(c, key2); dfree(c, id2);
+  u64* cnt2; ALLOC(cnt2, u64, 2);
+  u64 ccap = std::max<u64>(4096, 4ull * nN + 4ull * c->n_seq);
+  u64* cand = nullptr; u64 nc = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    ALLOC(cand, u64, ccap);
+    dev_memset(c, cnt2, 0, 16);
+    SPB_LAUNCH(k_occ_candidates, gs_grid(T), TPB, c->stream, c->sp, T, c->vflags, c->v2pos, c->obits, c->seq_off, c->n_seq, key, id, nN, c->soff,
+               cand, cnt2, ccap);
+    nc = dread(c, cnt2);
+    if (nc <= ccap) break;
+    dfree(c, cand); ccap = nc;
+  }
+  dfree(c, key); dfree(c, id);
+  u32 sb = 1; while ((1ull << sb) < c->n_seq) ++sb;
+  u64* pairs; ALLOC(pairs, u64, nc + 1);
+  dev_memset(c, cnt2, 0, 16);
+#ifdef SPB_EMU
+  SPB_LAUNCH(k_occ_verify, nblk(nc, TPB), TPB, c->stream, cand, nc, c->F, c->seqs, c->soff, c->seq_off, c->n_seq, sb, pairs, cnt2);
+#else
+  SPB_LAUNCH(k_occ_verify, nblk(nc * 32, TPB), TPB, c->stream, cand, nc, c->F, c->seqs, c->soff, c->seq_off, c->n_seq, sb, pairs, cnt2);
+#endif
+  u64 np = dread(c, cnt2);
+  dfree(c, cand); dfree(c, cnt2);
+  u32 nu = 0;
+  if (np) {
+    u64* tmp; ALLOC(tmp, u64, np + 1);
+    PRIM(prim_sort_u64(c, pairs, tmp, np));
+    dfree(c, tmp);
+    u8* nopay = nullptr;
+    PRIM(unique_sorted(c, pairs, nopay, np, &nu));
+  }
+  u32* out; ALLOC(out, u32, nN + 1);
+  SPB_LAUNCH(k_occ_counts, nblk(nN, TPB), TPB, c->stream, pairs, nu, sb, c->nt, nN, c->g_rev, c->vnbp, c->vflags, c->nV, out);
+  dev_copy(c, counts, out, 4ull * nN); dev_sync(c);
+  dfree(c, out); dfree(c, pairs);
+  return check_err(c, "nbp_orientation_counts");
+}
 int spb_get_stage_stats(spb_ctx* c, char* buf, uint64_t cap) {
   if (!c || !buf || !cap) return SPB_EINVAL;
   snprintf(buf, cap, "%s", c->stats.c_str());

@@ -1751,6 +1751,80 @@ __global__ void k_nbpg_join(NbpTab t, u32 nN, const u64* __restrict__ skey, cons
   }
 }
 
+// ------------------------------------------------------------------------------------ NBP orientation counts
+// For every raw NBP: in how many input sequences does its string occur in the sequence's own orientation?  (reference
+// get_seqPaths_NBPs, lib/Assembler.py:1121-1139, consumed as nv2rightOrientation at :448-453.)  An occurrence starts where
+// the sequence reads the NBP's first k-mer in the NBP's orientation: candidates come from a lookup of (vertex, read
+// forward?) in the sorted start keys of the NBP graph, and every candidate is then compared base by base against the
+// emitted NBP sequence, so the count is exact whatever the walk does in between.
+__global__ void k_occ_candidates(const u32* __restrict__ sp, u64 T, const u8* __restrict__ vflags, const u32* __restrict__ v2pos,
+                                 const u32* __restrict__ obits, const u64* __restrict__ seq_off, u32 n_seq, const u64* __restrict__ skey,
+                                 const u32* __restrict__ sid, u32 nN, const u64* __restrict__ soff, u64* __restrict__ cand, u64* ncand, u64 cap) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 p = SPB_GTID(); p < T; p += stride) {
+    const u32 u = sp[p];
+    if (u == SPB_INVALID || !(vflags[u] & VF_INIT)) continue;      // NBPs start at inits (incl. the cut vertex of a cycle)
+    const u32 su = get_bit(obits, p) ^ get_bit(obits, v2pos[u]);   // instance strand vs. stored k-mer
+    const u64 key = ((u64)u << 1) | (su ? 0u : 1u);                // (vertex, read forward?)  == nbp_start_key
+    u32 lo = lower_bound_key(skey, nN, key);
+    if (lo >= nN || skey[lo] != key) continue;
+    const u32 s = upper_bound_u64(seq_off, n_seq + 1, p) - 1;
+    const u64 end = seq_off[s + 1];
+    for (; lo < nN && skey[lo] == key; ++lo) {
+      const u32 x = sid[lo];
+      if (p + (soff[x + 1] - soff[x]) > end) continue;             // does not fit into the rest of the sequence
+      const u64 i = atomicAdd(ncand, 1ull);
+      if (i < cap) cand[i] = (p << 32) | x;
+    }
+  }
+}
+// one warp per candidate: exact comparison of the NBP sequence (ASCII) with the packed forward strand at p
+__global__ void k_occ_verify(const u64* __restrict__ cand, u64 ncand, const u32* __restrict__ F, const u8* __restrict__ seqs,
+                             const u64* __restrict__ soff, const u64* __restrict__ seq_off, u32 n_seq, u32 sb, u64* __restrict__ pairs, u64* npairs) {
+#ifdef SPB_EMU
+  const u64 i = SPB_GTID();
+  if (i >= ncand) return;
+  const u64 p = cand[i] >> 32; const u32 x = (u32)cand[i];
+  const u64 len = soff[x + 1] - soff[x];
+  for (u64 j = 0; j < len; ++j) if (seqs[soff[x] + j] != code2ascii(base_at(F, p + j))) return;
+  const u32 s = upper_bound_u64(seq_off, n_seq + 1, p) - 1;
+  pairs[atomicAdd(npairs, 1ull)] = ((u64)x << sb) | s;
+#else
+  const u64 i = SPB_GTID() >> 5;
+  if (i >= ncand) return;                            // warp-uniform
+  const u32 lane = threadIdx.x & 31;
+  const u64 p = cand[i] >> 32; const u32 x = (u32)cand[i];
+  const u64 len = soff[x + 1] - soff[x], so = soff[x];
+  bool ok = true;
+  for (u64 j0 = 0; j0 < len && ok; j0 += 32) {
+    const u64 j = j0 + lane;
+    const bool bad = j < len && seqs[so + j] != code2ascii(base_at(F, p + j));
+    ok = __ballot_sync(0xffffffffu, bad) == 0;
+  }
+  if (ok && lane == 0) {
+    const u32 s = upper_bound_u64(seq_off, n_seq + 1, p) - 1;
+    pairs[atomicAdd(npairs, 1ull)] = ((u64)x << sb) | s;
+  }
+#endif
+}
+// count of distinct sequences per NBP from the sorted unique pairs; the reference's compress_vertices quirk
+// (lib/vtools.pyx:29-45: a vertex list whose smallest vertex is 1 is recorded as containing 0 too) makes its
+// pre-filter `vertex_overlap(cNBP, seqPath) == refLen` fail for every NBP that holds vertex 1 but not vertex 0.
+__device__ __forceinline__ bool nbp_holds(const NbpTab& t, const u32* rev, const u32* vnbp, const u8* vflags, u32 x, u32 v) {
+  if (t.a[x] == v || t.b[x] == v) return true;
+  if (vflags[v] & VF_INIT) return false;
+  const u32 r = rev[x];
+  return vnbp[v] == (r < x ? r : x);
+}
+__global__ void k_occ_counts(const u64* __restrict__ pairs, u32 npairs, u32 sb, NbpTab t, u32 nN, const u32* __restrict__ rev,
+                             const u32* __restrict__ vnbp, const u8* __restrict__ vflags, u32 nV, u32* __restrict__ out) {
+  const u64 x = SPB_GTID();
+  if (x >= nN) return;
+  u32 c = lower_bound_key(pairs, npairs, (x + 1) << sb) - lower_bound_key(pairs, npairs, x << sb);
+  if (nV > 1 && nbp_holds(t, rev, vnbp, vflags, (u32)x, 1u) && !nbp_holds(t, rev, vnbp, vflags, (u32)x, 0u)) c = 0;
+  out[x] = c;
+}
+
 // ------------------------------------------------------------------------------------ getters
 __global__ void k_coords(const u32* __restrict__ v2pos, u32 nV, const u64* __restrict__ seq_off, u32 n_seq, u32* __restrict__ out) {
   u64 v = SPB_GTID();

@@ -84,7 +84,11 @@ def test_emu_matches_oracle_random(emu_lib, seqs, k):
         return
     if not want["vertex2coords"].shape[0]:
         return
-    digests.assert_same(want, run_emu(emu_lib, seqs, k).to_result())
+    A = run_emu(emu_lib, seqs, k)
+    digests.assert_same(want, A.to_result())
+    raw = A.raw_nbps()                                   # orientation counts against the oracle
+    got = A.nbp_orientation_counts()
+    assert [got[r[0]] for r in raw] == dbg_oracle.nbp_orientation_counts(raw, list(seqs.values()))
 
 
 @pytest.mark.parametrize("k,env", [(1001, {}), (2001, {}), (1001, {"SPB_DEDUP": "smem", "SPB_SMEM_AVG": "500"}), (75, {"SPB_DEDUP": "smem"})])

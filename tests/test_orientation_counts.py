@@ -1,0 +1,64 @@
+"""SURVEY 8(f) row 1, second half: per raw NBP, the number of input sequences that contain it in their own orientation
+(reference get_seqPaths_NBPs / nv2rightOrientation, lib/Assembler.py:1121-1139, :448-453).  The golden counts were
+produced by the reference's own classmethod (oracle/refrun.py); -1 marks NBPs for which the reference defines no pair."""
+import pytest
+
+import dbg_oracle
+import helpers
+from superpang_b200 import _capi
+from superpang_b200.assembler import Assembler
+
+CASES = [c for c in helpers.load_crafted() if not c.get("degenerate")]
+
+
+def _golden_map(case):
+    r = case["result"]
+    return {tuple(n[0]): c for n, c in zip(r["nbps"], r["orient_counts"]) if c >= 0}
+
+
+def test_golden_defines_counts():
+    assert sum(len(_golden_map(c)) for c in CASES) > 300
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c['name']}-k{c['k']}")
+def test_oracle_counts_match_reference(case):
+    r = case["result"]
+    seqs = [s for _, s in case["records"]]
+    got = dbg_oracle.nbp_orientation_counts([(tuple(n[0]), n[1]) for n in r["nbps"]], seqs)
+    for n, want, g in zip(r["nbps"], r["orient_counts"], got):
+        if want >= 0:
+            assert g == want, (case["name"], n[0][:4], want, g)
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c['name']}-k{c['k']}")
+def test_emu_counts_match_reference(emu_lib, case):
+    A = Assembler(dict(map(tuple, case["records"])), case["k"], engine=_capi.Engine(lib=emu_lib))
+    got = A.nbp_orientation_counts()
+    want = _golden_map(case)
+    assert set(want) <= set(got)
+    assert {k: got[k] for k in want} == want
+
+
+def test_emu_counts_match_oracle_synthetic(emu_lib):
+    for c in helpers.load_json("synthetic.json")["cases"][:3]:
+        sd = helpers.synth_seqdict(c["n_genomes"], c["length"], c["ani"], c["seed"], c["mode"])
+        A = Assembler(dict(sd), c["k"], engine=_capi.Engine(lib=emu_lib))
+        raw = A.raw_nbps()
+        want = dbg_oracle.nbp_orientation_counts(raw, list(sd.values()))
+        got = A.nbp_orientation_counts()
+        assert [got[r[0]] for r in raw] == want
+
+
+@pytest.mark.gpu
+def test_gpu_counts_match_reference_and_oracle():
+    for case in CASES:
+        A = Assembler(dict(map(tuple, case["records"])), case["k"], device=0)
+        got = A.nbp_orientation_counts()
+        want = _golden_map(case)
+        assert {k: got[k] for k in want} == want, case["name"]
+    for c in helpers.load_json("synthetic.json")["cases"]:
+        sd = helpers.synth_seqdict(c["n_genomes"], c["length"], c["ani"], c["seed"], c["mode"])
+        A = Assembler(dict(sd), c["k"], device=0)
+        raw = A.raw_nbps()
+        got = A.nbp_orientation_counts()
+        assert [got[r[0]] for r in raw] == dbg_oracle.nbp_orientation_counts(raw, list(sd.values()))
