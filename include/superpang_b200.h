@@ -158,6 +158,10 @@ int spb_get_nbp_graph(spb_ctx* ctx, uint64_t* n_edges, uint64_t* off, uint32_t* 
  * into nv2rightOrientation from get_seqPaths_NBPs (`lib/Assembler.py:1121-1139`, `:448-453`), including the effect of
  * the compress_vertices leading-zero quirk on its vertex_overlap pre-filter (`lib/vtools.pyx:29-45`). */
 int spb_get_nbp_orientation_counts(spb_ctx* ctx, uint32_t* counts);
+/* Bubble candidates: group uint32[n_nbp]; NBPs that share (first vertex, last vertex) with at least
+ * one other NBP carry the smallest NBP id of their group, all others 0xFFFFFFFF -- the `path_limits` grouping of
+ * `lib/Assembler.py:728-734` (the minimap2 alignment of the members, `:749-758`, stays on the host). */
+int spb_get_bubble_groups(spb_ctx* ctx, uint32_t* group);
 /* Current counters (n_seq_intervals is filled by the first spb_get_seq_intervals call, which may
  * be made with NULL buffers just to size them). */
 int spb_get_counts(spb_ctx* ctx, spb_counts* out);

@@ -432,3 +432,14 @@ def nbp_orientation_counts(nbps, seqs):
             continue
         out.append(sum(1 for s in seqs if seq in s))
     return out
+
+
+def bubble_candidates(nbps):
+    """the reference's `path_limits` (lib/Assembler.py:728-734): NBPs grouped by (first vertex, last
+    vertex); only groups with more than one path are bubble candidates."""
+    from collections import defaultdict
+    groups = defaultdict(list)
+    for nbp in nbps:
+        verts = tuple(nbp[0])
+        groups[(verts[0], verts[-1])].append(verts)
+    return [g for g in groups.values() if len(g) > 1]

@@ -23,7 +23,7 @@ EXPORTS = (
     "spb_get_vertex2coords", "spb_get_edges", "spb_get_instance_vertices", "spb_get_seqlimits",
     "spb_get_seq_intervals", "spb_get_components", "spb_get_nbps", "spb_get_nbp_seqs",
     "spb_get_nbp_origins", "spb_get_counts", "spb_get_stage_stats", "spb_build_kind", "spb_launch_count",
-    "spb_get_nbp_graph", "spb_get_nbp_orientation_counts", "spb_mg_slice", "spb_mg_probe", "spb_mg_records", "spb_mg_dedup", "spb_mg_scatter", "spb_mg_dedup_links", "spb_mg_apply_links", "spb_mg_owned_links", "spb_mg_buffers", "spb_mg_ids", "spb_mg_graph",
+    "spb_get_nbp_graph", "spb_get_nbp_orientation_counts", "spb_get_bubble_groups", "spb_mg_slice", "spb_mg_probe", "spb_mg_records", "spb_mg_dedup", "spb_mg_scatter", "spb_mg_dedup_links", "spb_mg_apply_links", "spb_mg_owned_links", "spb_mg_buffers", "spb_mg_ids", "spb_mg_graph",
 )
 
 
@@ -84,6 +84,7 @@ def _declare(lib):
     lib.spb_launch_count.restype = C.c_uint64
     lib.spb_get_nbp_graph.argtypes = [vp, C.POINTER(C.c_uint64), u64p, u32p, u32p]
     lib.spb_get_nbp_orientation_counts.argtypes = [vp, u32p]
+    lib.spb_get_bubble_groups.argtypes = [vp, u32p]
     lib.spb_mg_slice.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint64)]
     lib.spb_mg_probe.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.spb_mg_records.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
@@ -417,6 +418,14 @@ class Engine:
         out = np.zeros(self.counts.n_nbp, dtype=np.uint32)
         if out.size:
             self._ck(self.lib.spb_get_nbp_orientation_counts(self.h, out.ctypes.data))
+        return out
+
+    def bubble_groups(self):
+        """group[i] = smallest raw NBP id among the NBPs sharing (first, last) vertex with NBP i, 0xFFFFFFFF if none
+        (the reference's bubble candidates, lib/Assembler.py:728-734)."""
+        out = np.full(self.counts.n_nbp, 0xFFFFFFFF, dtype=np.uint32)
+        if out.size:
+            self._ck(self.lib.spb_get_bubble_groups(self.h, out.ctypes.data))
         return out
 
     def nbp_origins(self):

@@ -178,6 +178,17 @@ class Assembler:
         counts = self._eng.nbp_orientation_counts()
         return {tuple(verts[int(voff[i]):int(voff[i + 1])].tolist()): int(counts[i]) for i in range(len(counts))}
 
+    def bubble_candidates(self):
+        """Groups (lists of vertex tuples) of raw NBPs that share first and last vertex -- `path_limits` entries with more
+        than one path, `lib/Assembler.py:728-734`."""
+        self.compact()
+        voff, verts, _, _ = self._eng.nbps()
+        g = self._eng.bubble_groups()
+        groups = {}
+        for i in np.nonzero(g != 0xFFFFFFFF)[0]:
+            groups.setdefault(int(g[i]), []).append(tuple(verts[int(voff[i]):int(voff[i + 1])].tolist()))
+        return list(groups.values())
+
     def collect_nbps(self):
         """Per component, in the reference's order (size descending, ties by label; `lib/Assembler.py:271-273`)."""
         raw = self.raw_nbps()

@@ -1547,6 +1547,23 @@ int spb_get_nbp_orientation_counts(spb_ctx* c, uint32_t* counts) {
   dfree(c, out); dfree(c, pairs);
   return check_err(c, "nbp_orientation_counts");
 }
+// bubble candidates = NBPs that share (first vertex, last vertex) with another NBP
+// (reference lib/Assembler.py:728-734); group[i] = smallest NBP id of i's group, 0xFFFFFFFF when i is alone.
+int spb_get_bubble_groups(spb_ctx* c, uint32_t* group) {
+  NEED(3);
+  if (!group) return SPB_EINVAL;
+  const u32 nN = c->nN;
+  if (nN == 0) return SPB_OK;
+  u64 *key, *key2; u32 *id, *id2, *out;
+  ALLOC(key, u64, nN + 1); ALLOC(key2, u64, nN + 1); ALLOC(id, u32, nN + 1); ALLOC(id2, u32, nN + 1); ALLOC(out, u32, nN + 1);
+  SPB_LAUNCH(k_bubble_keys, nblk(nN, TPB), TPB, c->stream, c->nt, nN, key, id);
+  PRIM(prim_partition_u64_u32(c, key, id, key2, id2, nN, 0, 64));
+  dfree(c, key2); dfree(c, id2);
+  SPB_LAUNCH(k_bubble_groups, nblk(nN, TPB), TPB, c->stream, key, id, nN, out);
+  dev_copy(c, group, out, 4ull * nN); dev_sync(c);
+  dfree(c, key); dfree(c, id); dfree(c, out);
+  return check_err(c, "bubble_groups");
+}
 int spb_get_stage_stats(spb_ctx* c, char* buf, uint64_t cap) {
   if (!c || !buf || !cap) return SPB_EINVAL;
   snprintf(buf, cap, "%s", c->stats.c_str());

@@ -1825,6 +1825,25 @@ __global__ void k_occ_counts(const u64* __restrict__ pairs, u32 npairs, u32 sb, 
   out[x] = c;
 }
 
+// ------------------------------------------------------------------------------------ bubble candidates
+// The reference groups the NBPs by (first vertex, last vertex) and aligns the members of every group with more than
+// one path (lib/Assembler.py:728-734).  Key = first << 32 | last; a broken cycle ends with its first vertex.
+__global__ void k_bubble_keys(NbpTab t, u32 nN, u64* __restrict__ key, u32* __restrict__ id) {
+  u64 i = SPB_GTID();
+  if (i >= nN) return;
+  key[i] = ((u64)t.a[i] << 32) | (t.cyc[i] ? t.a[i] : t.b[i]); id[i] = (u32)i;
+}
+// group[i] = smallest NBP id of the group of i when the group has more than one member, else SPB_INVALID
+__global__ void k_bubble_groups(const u64* __restrict__ skey, const u32* __restrict__ sid, u32 nN, u32* __restrict__ group) {
+  u64 j = SPB_GTID();
+  if (j >= nN) return;
+  const u64 k0 = skey[j];
+  const u32 lo = lower_bound_key(skey, nN, k0), hi = lower_bound_key(skey, nN, k0 + 1);
+  u32 m = SPB_INVALID;
+  if (hi - lo > 1) for (u32 q = lo; q < hi; ++q) m = sid[q] < m ? sid[q] : m;
+  group[sid[j]] = m;
+}
+
 // ------------------------------------------------------------------------------------ getters
 __global__ void k_coords(const u32* __restrict__ v2pos, u32 nV, const u64* __restrict__ seq_off, u32 n_seq, u32* __restrict__ out) {
   u64 v = SPB_GTID();

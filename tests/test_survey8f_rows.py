@@ -1,4 +1,5 @@
-"""SURVEY 8(f) row 1, second half: per raw NBP, the number of input sequences that contain it in their own orientation
+"""SURVEY 8(f) rows on the device.  Row 4: bubble candidates (NBPs sharing first and last vertex, lib/Assembler.py:728-734).
+Row 1, second half: per raw NBP, the number of input sequences that contain it in their own orientation
 (reference get_seqPaths_NBPs / nv2rightOrientation, lib/Assembler.py:1121-1139, :448-453).  The golden counts were
 produced by the reference's own classmethod (oracle/refrun.py); -1 marks NBPs for which the reference defines no pair."""
 import pytest
@@ -62,3 +63,34 @@ def test_gpu_counts_match_reference_and_oracle():
         raw = A.raw_nbps()
         got = A.nbp_orientation_counts()
         assert [got[r[0]] for r in raw] == dbg_oracle.nbp_orientation_counts(raw, list(sd.values()))
+
+
+def _norm(groups):
+    return sorted(sorted(g) for g in groups)
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c['name']}-k{c['k']}")
+def test_emu_bubble_candidates_match_reference_nbps(emu_lib, case):
+    """grouping of the reference's own NBP list (golden) by (first, last) vertex."""
+    want = dbg_oracle.bubble_candidates([(tuple(n[0]),) for n in case["result"]["nbps"]])
+    A = Assembler(dict(map(tuple, case["records"])), case["k"], engine=_capi.Engine(lib=emu_lib))
+    assert _norm(A.bubble_candidates()) == _norm(want)
+
+
+def test_emu_bubble_candidates_synthetic(emu_lib):
+    n_groups = 0
+    for c in helpers.load_json("synthetic.json")["cases"][:3]:
+        sd = helpers.synth_seqdict(c["n_genomes"], c["length"], c["ani"], c["seed"], c["mode"])
+        A = Assembler(dict(sd), c["k"], engine=_capi.Engine(lib=emu_lib))
+        want = dbg_oracle.bubble_candidates(A.raw_nbps())
+        assert _norm(A.bubble_candidates()) == _norm(want)
+        n_groups += len(want)
+    assert n_groups > 10                                 # SNP bubbles: the case the reference's flattening is for
+
+
+@pytest.mark.gpu
+def test_gpu_bubble_candidates():
+    for case in CASES:
+        want = dbg_oracle.bubble_candidates([(tuple(n[0]),) for n in case["result"]["nbps"]])
+        A = Assembler(dict(map(tuple, case["records"])), case["k"], device=0)
+        assert _norm(A.bubble_candidates()) == _norm(want), case["name"]
