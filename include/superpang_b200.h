@@ -158,6 +158,11 @@ int spb_get_nbp_graph(spb_ctx* ctx, uint64_t* n_edges, uint64_t* off, uint32_t* 
  * into nv2rightOrientation from get_seqPaths_NBPs (`lib/Assembler.py:1121-1139`, `:448-453`), including the effect of
  * the compress_vertices leading-zero quirk on its vertex_overlap pre-filter (`lib/vtools.pyx:29-45`). */
 int spb_get_nbp_orientation_counts(spb_ctx* ctx, uint32_t* counts);
+/* The same relation per sequence, as CSR: off uint64[n_seq + 1], nbp_ids uint32[*n_pairs] (ascending per sequence) = the
+ * raw NBPs that sequence s contains in its own orientation -- the sets `get_seqPaths_NBPs` returns
+ * (`lib/Assembler.py:1121-1139`), which the forward / reverse separation consumes (`:448`, `:480-520`).  Call once with
+ * NULL buffers to learn *n_pairs. */
+int spb_get_seq_nbps(spb_ctx* ctx, uint64_t* n_pairs, uint64_t* off, uint32_t* nbp_ids);
 /* Bubble candidates: group uint32[n_nbp]; NBPs that share (first vertex, last vertex) with at least
  * one other NBP carry the smallest NBP id of their group, all others 0xFFFFFFFF -- the `path_limits` grouping of
  * `lib/Assembler.py:728-734` (the minimap2 alignment of the members, `:749-758`, stays on the host). */

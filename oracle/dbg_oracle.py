@@ -443,3 +443,15 @@ def bubble_candidates(nbps):
         verts = tuple(nbp[0])
         groups[(verts[0], verts[-1])].append(verts)
     return [g for g in groups.values() if len(g) > 1]
+
+
+def seq_paths_nbps(nbps, seqdict):
+    """{sequence name: indices of the raw NBPs whose string the sequence contains}, i.e. the value of
+    the reference's get_seqPaths_NBPs (lib/Assembler.py:1121-1139) for every sequence, with the same leading-zero quirk
+    as in nbp_orientation_counts; sequences without any NBP are left out (:449)."""
+    out = {}
+    for name, s in seqdict.items():
+        mine = [i for i, nbp in enumerate(nbps) if min(nbp[0]) != 1 and nbp[1] in s]
+        if mine:
+            out[name] = mine
+    return out

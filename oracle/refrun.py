@@ -131,6 +131,7 @@ def run_reference(fasta, ksize=301, threads=1, debug=True, with_origins=True, qu
             groups[frozenset(n[0])].append(i)
         psets = {fs: tuple(nvs) for fs, nvs in groups.items() if len(nvs) == 2 and len(NBP2seq) == len(nbps_out)}
         orient = [-1] * len(nbps_out)
+        orient_sets = {}
         if psets:
             names_ = list(A.seqPaths)
             sets_ = A.multimap(A.get_seqPaths_NBPs, 1, names_, A.seqPaths, psets, NBP2seq, vertex2NBP, A.seqDict)
@@ -140,10 +141,12 @@ def run_reference(fasta, ksize=301, threads=1, debug=True, with_origins=True, qu
             for spGS in sets_:
                 for nv in spGS:
                     orient[nv] += 1
+            orient_sets = {name: sorted(int(nv) for nv in spGS) for name, spGS in zip(names_, sets_) if spGS}
 
     edges = A.DBG._edges.astype(np.uint32)
     res = dict(
         orient_counts=orient,
+        orient_sets=orient_sets,
         k=ksize,
         names=list(A.seqDict),
         n_inst=int(sum(len(s) - ksize + 1 for s in A.seqDict.values() if len(s) > ksize)),

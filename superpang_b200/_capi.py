@@ -23,7 +23,7 @@ EXPORTS = (
     "spb_get_vertex2coords", "spb_get_edges", "spb_get_instance_vertices", "spb_get_seqlimits",
     "spb_get_seq_intervals", "spb_get_components", "spb_get_nbps", "spb_get_nbp_seqs",
     "spb_get_nbp_origins", "spb_get_counts", "spb_get_stage_stats", "spb_build_kind", "spb_launch_count",
-    "spb_get_nbp_graph", "spb_get_nbp_orientation_counts", "spb_get_bubble_groups", "spb_mg_slice", "spb_mg_probe", "spb_mg_records", "spb_mg_dedup", "spb_mg_scatter", "spb_mg_dedup_links", "spb_mg_apply_links", "spb_mg_owned_links", "spb_mg_buffers", "spb_mg_ids", "spb_mg_graph",
+    "spb_get_nbp_graph", "spb_get_nbp_orientation_counts", "spb_get_seq_nbps", "spb_get_bubble_groups", "spb_mg_slice", "spb_mg_probe", "spb_mg_records", "spb_mg_dedup", "spb_mg_scatter", "spb_mg_dedup_links", "spb_mg_apply_links", "spb_mg_owned_links", "spb_mg_buffers", "spb_mg_ids", "spb_mg_graph",
 )
 
 
@@ -85,6 +85,7 @@ def _declare(lib):
     lib.spb_get_nbp_graph.argtypes = [vp, C.POINTER(C.c_uint64), u64p, u32p, u32p]
     lib.spb_get_nbp_orientation_counts.argtypes = [vp, u32p]
     lib.spb_get_bubble_groups.argtypes = [vp, u32p]
+    lib.spb_get_seq_nbps.argtypes = [vp, C.POINTER(C.c_uint64), u64p, u32p]
     lib.spb_mg_slice.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint64)]
     lib.spb_mg_probe.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.spb_mg_records.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
@@ -419,6 +420,16 @@ class Engine:
         if out.size:
             self._ck(self.lib.spb_get_nbp_orientation_counts(self.h, out.ctypes.data))
         return out
+
+    def seq_nbps(self):
+        """(off, ids): CSR over the loaded sequences of the raw NBPs each contains in its own orientation (the sets of the
+        reference's get_seqPaths_NBPs, lib/Assembler.py:1121-1139)."""
+        n = C.c_uint64()
+        self._ck(self.lib.spb_get_seq_nbps(self.h, C.byref(n), None, None))
+        off = np.zeros(self.counts.n_seq + 1, dtype=np.uint64)
+        ids = np.empty(n.value, dtype=np.uint32)
+        self._ck(self.lib.spb_get_seq_nbps(self.h, C.byref(n), off.ctypes.data, ids.ctypes.data))
+        return off, ids
 
     def bubble_groups(self):
         """group[i] = smallest raw NBP id among the NBPs sharing (first, last) vertex with NBP i, 0xFFFFFFFF if none

@@ -178,6 +178,24 @@ class Assembler:
         counts = self._eng.nbp_orientation_counts()
         return {tuple(verts[int(voff[i]):int(voff[i + 1])].tolist()): int(counts[i]) for i in range(len(counts))}
 
+    def seq_paths_nbps(self):
+        """{sequence name: set of raw NBPs (vertex tuples) the sequence contains in its own orientation} -- the value of
+        `get_seqPaths_NBPs` for every sequence (`lib/Assembler.py:1121-1139`); names without any NBP are left out, as
+        the reference drops them (`:449`)."""
+        self.compact()
+        voff, verts, _, _ = self._eng.nbps()
+        off, ids = self._eng.seq_nbps()
+        tup = {}
+        out = {}
+        for s, name in enumerate(self.ref2name):
+            mine = ids[int(off[s]):int(off[s + 1])]
+            if len(mine):
+                for i in mine:
+                    if int(i) not in tup:
+                        tup[int(i)] = tuple(verts[int(voff[i]):int(voff[i + 1])].tolist())
+                out[name] = {tup[int(i)] for i in mine}
+        return out
+
     def bubble_candidates(self):
         """Groups (lists of vertex tuples) of raw NBPs that share first and last vertex -- `path_limits` entries with more
         than one path, `lib/Assembler.py:728-734`."""

@@ -48,6 +48,7 @@ struct spb_ctx {
   u32 *verts = 0, *origins = 0; u8* seqs = 0;
   u32* iv = 0; u64* iv_off = 0;
   u64* g_off = 0; u32 *g_succ = 0, *g_rev = 0; u64 g_edges = 0;      // NBP graph (lazy)
+  u32 *occ_counts = 0, *occ_ids = 0; u64* occ_off = 0; u64 occ_pairs = 0;   // NBP occurrences in the sequences (lazy)
   // staged dedup state (records sent by this rank)
   u64 *dd_keys = 0, *dd_bstart = 0; u32* dd_pos = 0; u64 dd_n = 0, dd_lo = 0, dd_hi = 0; u32 dd_bb = 0; bool dd_fbits_ready = false;
   std::vector<u64> dd_bstart_h;
@@ -1495,16 +1496,15 @@ int spb_get_nbp_graph(spb_ctx* c, uint64_t* n_edges, uint64_t* off, uint32_t* su
   dev_sync(c);
   return SPB_OK;
 }
-// SURVEY 8(f) row 1, second half: per raw NBP, the number of input sequences that contain its string in their own
-// orientation (reference get_seqPaths_NBPs, lib/Assembler.py:1121-1139, counted into nv2rightOrientation at :448-453).
-int spb_get_nbp_orientation_counts(spb_ctx* c, uint32_t* counts) {
-  NEED(3);
-  if (!counts) return SPB_EINVAL;
+// SURVEY 8(f) row 1, second half: which input sequences contain which raw NBP in their own orientation (reference
+// get_seqPaths_NBPs, lib/Assembler.py:1121-1139).  Built once per compaction: sorted unique (NBP << sb | sequence) pairs
+// and the per-NBP counts (what the reference accumulates into nv2rightOrientation, :448-453).
+static int build_occurrences(spb_ctx* c) {
+  if (c->occ_counts) return 0;
   int r = build_nbp_graph(c);                        // start keys are rebuilt below; the graph supplies the partner ids
   if (r) return r;
   const u32 nN = c->nN;
   const u64 T = c->T;
-  if (nN == 0) return SPB_OK;
   u64 *key, *key2; u32 *id, *id2;
   ALLOC(key, u64, nN + 1); ALLOC(key2, u64, nN + 1); ALLOC(id, u32, nN + 1); ALLOC(id2, u32, nN + 1);
   SPB_LAUNCH(k_nbpg_keys, nblk(nN, TPB), TPB, c->stream, c->nt, nN, key, id);
@@ -1541,11 +1541,42 @@ int spb_get_nbp_orientation_counts(spb_ctx* c, uint32_t* counts) {
     u8* nopay = nullptr;
     PRIM(unique_sorted(c, pairs, nopay, np, &nu));
   }
-  u32* out; ALLOC(out, u32, nN + 1);
-  SPB_LAUNCH(k_occ_counts, nblk(nN, TPB), TPB, c->stream, pairs, nu, sb, c->nt, nN, c->g_rev, c->vnbp, c->vflags, c->nV, out);
-  dev_copy(c, counts, out, 4ull * nN); dev_sync(c);
-  dfree(c, out); dfree(c, pairs);
-  return check_err(c, "nbp_orientation_counts");
+  ALLOC(c->occ_counts, u32, nN + 1);
+  SPB_LAUNCH(k_occ_counts, nblk(nN, TPB), TPB, c->stream, pairs, nu, sb, c->nt, nN, c->g_rev, c->vnbp, c->vflags, c->nV, c->occ_counts);
+  // per-sequence view: (sequence << 32 | NBP), sorted; pairs of NBPs the reference's pre-filter rejects are dropped
+  u64 *sk, *sk2; ALLOC(sk, u64, (u64)nu + 1); ALLOC(sk2, u64, (u64)nu + 1);
+  SPB_LAUNCH(k_occ_rekey, nblk(nu, TPB), TPB, c->stream, pairs, nu, sb, c->occ_counts, sk);
+  PRIM(prim_sort_u64(c, sk, sk2, nu));
+  dfree(c, sk2); dfree(c, pairs);
+  ALLOC(c->occ_off, u64, (u64)c->n_seq + 2);
+  SPB_LAUNCH(k_occ_seq_offsets, nblk((u64)c->n_seq + 1, TPB), TPB, c->stream, sk, nu, c->n_seq, c->occ_off);
+  ALLOC(c->occ_ids, u32, (u64)nu + 1);
+  SPB_LAUNCH(k_occ_ids, nblk(nu, TPB), TPB, c->stream, sk, nu, c->occ_ids);
+  dfree(c, sk);
+  u64 last = 0;
+  dev_copy(c, &last, c->occ_off + c->n_seq, 8); dev_sync(c);
+  c->occ_pairs = last;                               // pairs that survive the filter
+  return check_err(c, "nbp_occurrences");
+}
+int spb_get_nbp_orientation_counts(spb_ctx* c, uint32_t* counts) {
+  NEED(3);
+  if (!counts) return SPB_EINVAL;
+  if (c->nN == 0) return SPB_OK;
+  int r = build_occurrences(c);
+  if (r) return r;
+  dev_copy(c, counts, c->occ_counts, 4ull * c->nN); dev_sync(c);
+  return SPB_OK;
+}
+int spb_get_seq_nbps(spb_ctx* c, uint64_t* n_pairs, uint64_t* off, uint32_t* nbp_ids) {
+  NEED(3);
+  if (c->nN == 0) { if (n_pairs) *n_pairs = 0; if (off) for (u32 s = 0; s <= c->n_seq; ++s) off[s] = 0; return SPB_OK; }
+  int r = build_occurrences(c);
+  if (r) return r;
+  if (n_pairs) *n_pairs = c->occ_pairs;
+  if (off) dev_copy(c, off, c->occ_off, 8ull * (c->n_seq + 1));
+  if (nbp_ids) dev_copy(c, nbp_ids, c->occ_ids, 4ull * c->occ_pairs);
+  dev_sync(c);
+  return SPB_OK;
 }
 // bubble candidates = NBPs that share (first vertex, last vertex) with another NBP
 // (reference lib/Assembler.py:728-734); group[i] = smallest NBP id of i's group, 0xFFFFFFFF when i is alone.

@@ -1816,6 +1816,22 @@ __device__ __forceinline__ bool nbp_holds(const NbpTab& t, const u32* rev, const
   const u32 r = rev[x];
   return vnbp[v] == (r < x ? r : x);
 }
+// (NBP << sb | sequence) -> (sequence << 32 | NBP) for the per-sequence view; pairs of NBPs the quirk excludes get ~0
+__global__ void k_occ_rekey(const u64* __restrict__ pairs, u32 npairs, u32 sb, const u32* __restrict__ counts, u64* __restrict__ out) {
+  const u64 i = SPB_GTID();
+  if (i >= npairs) return;
+  const u64 x = pairs[i] >> sb, s = pairs[i] & ((1ull << sb) - 1);
+  out[i] = counts[x] ? ((s << 32) | x) : ~0ull;
+}
+__global__ void k_occ_seq_offsets(const u64* __restrict__ keys, u32 n, u32 n_seq, u64* __restrict__ off) {
+  const u64 s = SPB_GTID();
+  if (s > n_seq) return;
+  off[s] = lower_bound_key(keys, n, s << 32);
+}
+__global__ void k_occ_ids(const u64* __restrict__ keys, u32 n, u32* __restrict__ ids) {
+  const u64 i = SPB_GTID();
+  if (i < n) ids[i] = (u32)keys[i];
+}
 __global__ void k_occ_counts(const u64* __restrict__ pairs, u32 npairs, u32 sb, NbpTab t, u32 nN, const u32* __restrict__ rev,
                              const u32* __restrict__ vnbp, const u8* __restrict__ vflags, u32 nV, u32* __restrict__ out) {
   const u64 x = SPB_GTID();

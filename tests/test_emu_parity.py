@@ -89,6 +89,9 @@ def test_emu_matches_oracle_random(emu_lib, seqs, k):
     raw = A.raw_nbps()                                   # orientation counts against the oracle
     got = A.nbp_orientation_counts()
     assert [got[r[0]] for r in raw] == dbg_oracle.nbp_orientation_counts(raw, list(seqs.values()))
+    want_sets = {n: {raw[i][0] for i in ids} for n, ids in dbg_oracle.seq_paths_nbps(raw, seqs).items()}
+    assert A.seq_paths_nbps() == want_sets
+    assert sorted(sorted(g) for g in A.bubble_candidates()) == sorted(sorted(g) for g in dbg_oracle.bubble_candidates(raw))
 
 
 @pytest.mark.parametrize("k,env", [(1001, {}), (2001, {}), (1001, {"SPB_DEDUP": "smem", "SPB_SMEM_AVG": "500"}), (75, {"SPB_DEDUP": "smem"})])

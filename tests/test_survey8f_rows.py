@@ -94,3 +94,39 @@ def test_gpu_bubble_candidates():
         want = dbg_oracle.bubble_candidates([(tuple(n[0]),) for n in case["result"]["nbps"]])
         A = Assembler(dict(map(tuple, case["records"])), case["k"], device=0)
         assert _norm(A.bubble_candidates()) == _norm(want), case["name"]
+
+
+def _golden_sets(case):
+    """{name: set of vertex tuples} from the reference's own get_seqPaths_NBPs (only NBPs with a defined pair)."""
+    r = case["result"]
+    return {name: {tuple(r["nbps"][nv][0]) for nv in nvs} for name, nvs in r.get("orient_sets", {}).items()}
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c['name']}-k{c['k']}")
+def test_oracle_seq_sets_match_reference(case):
+    r = case["result"]
+    defined = {i for i, c in enumerate(r["orient_counts"]) if c >= 0}
+    got = dbg_oracle.seq_paths_nbps([(tuple(n[0]), n[1]) for n in r["nbps"]], dict(map(tuple, case["records"])))
+    got = {name: sorted(i for i in nvs if i in defined) for name, nvs in got.items()}
+    got = {n: v for n, v in got.items() if v}
+    assert got == {n: sorted(v) for n, v in r.get("orient_sets", {}).items()}
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c['name']}-k{c['k']}")
+def test_emu_seq_sets_match_reference(emu_lib, case):
+    r = case["result"]
+    defined = {tuple(n[0]) for n, c in zip(r["nbps"], r["orient_counts"]) if c >= 0}
+    A = Assembler(dict(map(tuple, case["records"])), case["k"], engine=_capi.Engine(lib=emu_lib))
+    got = {n: {v for v in s if v in defined} for n, s in A.seq_paths_nbps().items()}
+    got = {n: s for n, s in got.items() if s}
+    assert got == _golden_sets(case)
+
+
+@pytest.mark.gpu
+def test_gpu_seq_sets_match_reference():
+    for case in CASES:
+        r = case["result"]
+        defined = {tuple(n[0]) for n, c in zip(r["nbps"], r["orient_counts"]) if c >= 0}
+        A = Assembler(dict(map(tuple, case["records"])), case["k"], device=0)
+        got = {n: {v for v in s if v in defined} for n, s in A.seq_paths_nbps().items()}
+        assert {n: s for n, s in got.items() if s} == _golden_sets(case), case["name"]
