@@ -31,6 +31,7 @@ for p in (HERE, ROOT):
 import numpy as np  # noqa: E402
 import refrun  # noqa: E402
 
+ROW1_CALLS = [0]            # how often the device-backed get_seqPaths_NBPs was called (tests check that it is used)
 RUN_ARGS = dict(minlen=0, mincov=0, bubble_identity_threshold=1, genome_assignment_threshold=1)
 
 
@@ -74,7 +75,9 @@ def run_reference_full(fasta, k, threads=1):
         return Assembler(fasta, k, threads, None, True, 1).run(max_threads=threads, debug=True, **RUN_ARGS)
 
 
-def run_dropin_full(fasta, k, engine, threads=1):
+def run_dropin_full(fasta, k, engine, threads=1, device_rows=False):
+    """device_rows=True additionally serves `get_seqPaths_NBPs` (`lib/Assembler.py:1121-1139`) from the
+    per-sequence NBP sets computed on the device (`spb_get_seq_nbps`) instead of the reference's substring tests."""
     Assembler = refrun.import_reference()
     from graph_tool.all import Graph
     from superpang_b200.assembler import Assembler as B200Assembler
@@ -92,6 +95,16 @@ def run_dropin_full(fasta, k, engine, threads=1):
     A.DBG.vp.comp = A.DBG.new_vertex_property("int16_t")
     A.DBG.ep.efilt = A.DBG.new_edge_property("bool")
     A._b200_components = B.collect_nbps()
+    if device_rows:
+        assert threads == 1                                   # the closure below is not meant to cross a fork pool
+        sets = B.seq_paths_nbps()                             # {name: {vertex tuple of every raw NBP the sequence contains}}
+
+        def get_seqPaths_NBPs(i):
+            ROW1_CALLS[0] += 1
+            names, seqPaths, psets, NBP2seq, vertex2NBP, seqDict = Assembler.get_multiprocessing_globals()
+            mine = sets.get(names[i], ())
+            return {nv for pair in psets.values() for nv in pair if vertex2NBP[nv] in mine}
+        A.get_seqPaths_NBPs = get_seqPaths_NBPs
     with contextlib.redirect_stdout(io.StringIO()):
         return A.run(max_threads=threads, debug=True, **RUN_ARGS)
 

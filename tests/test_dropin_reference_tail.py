@@ -28,6 +28,9 @@ def test_reference_tail_on_b200_head(emu_lib, case, tmp_path):
     got = dropin.run_dropin_full(fa, k, _capi.Engine(lib=emu_lib))
     assert dropin.canonical(ref) == dropin.canonical(got)
     assert dropin.contigs_digest(ref) == dropin.contigs_digest(got)
+    # SURVEY 8(f) row 1 wired in as well: get_seqPaths_NBPs answered from the device-side per-sequence NBP sets
+    got = dropin.run_dropin_full(fa, k, _capi.Engine(lib=emu_lib), device_rows=True)
+    assert dropin.canonical(ref) == dropin.canonical(got)
 
 
 def test_reference_tail_on_b200_head_synthetic(emu_lib, tmp_path):
@@ -39,3 +42,7 @@ def test_reference_tail_on_b200_head_synthetic(emu_lib, tmp_path):
     ref = dropin.run_reference_full(fa, 301)
     got = dropin.run_dropin_full(fa, 301, _capi.Engine(lib=emu_lib))
     assert dropin.canonical(ref) == dropin.canonical(got)
+    before = dropin.ROW1_CALLS[0]
+    got = dropin.run_dropin_full(fa, 301, _capi.Engine(lib=emu_lib), device_rows=True)
+    assert dropin.canonical(ref) == dropin.canonical(got)
+    assert dropin.ROW1_CALLS[0] >= before + 5           # the reference's run() did go through the device-backed function
