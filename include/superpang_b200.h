@@ -167,6 +167,11 @@ int spb_get_seq_nbps(spb_ctx* ctx, uint64_t* n_pairs, uint64_t* off, uint32_t* n
  * one other NBP carry the smallest NBP id of their group, all others 0xFFFFFFFF -- the `path_limits` grouping of
  * `lib/Assembler.py:728-734` (the minimap2 alignment of the members, `:749-758`, stays on the host). */
 int spb_get_bubble_groups(spb_ctx* ctx, uint32_t* group);
+/* Sequences of host-supplied vertex paths: `reconstruct_sequence` (`lib/Assembler.py:1038-1118`) for
+ * the joined paths of the host tail (`:911-921`).  off uint64[n_paths + 1], verts uint32[off[n_paths]] (host);
+ * ascii uint8[off[n_paths] + n_paths * (k - 1)], path i written at off[i] + i * (k - 1).  Needs spb_build_dbg only.
+ * SPB_EINVAL when a path has fewer than 2 vertices or steps between non-adjacent vertices (the reference asserts). */
+int spb_path_sequences(spb_ctx* ctx, uint32_t n_paths, const uint64_t* off, const uint32_t* verts, uint8_t* ascii);
 /* Current counters (n_seq_intervals is filled by the first spb_get_seq_intervals call, which may
  * be made with NULL buffers just to size them). */
 int spb_get_counts(spb_ctx* ctx, spb_counts* out);

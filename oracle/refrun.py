@@ -143,8 +143,21 @@ def run_reference(fasta, ksize=301, threads=1, debug=True, with_origins=True, qu
                     orient[nv] += 1
             orient_sets = {name: sorted(int(nv) for nv in spGS) for name, spGS in zip(names_, sets_) if spGS}
 
+        # ---- joined paths: NBP1 + NBP2[1:] for NBP-graph edges (:365-384), sequences by the reference's own
+        #      reconstruct_sequence (:1038-1118) -- golden vectors for spb_path_sequences
+        joined = []
+        by_start = _dd(list)
+        for n in nbps_out:
+            by_start[n[1][:ksize]].append(n)
+        for n1 in nbps_out:
+            for n2 in by_start[n1[1][-ksize:]]:
+                if len(joined) < 40 and n1[0][-1] == n2[0][0] and len(set(n1[0]) & set(n2[0])) == 1:
+                    joined.append(tuple(n1[0]) + tuple(n2[0][1:]))
+        joined_seqs = A.multimap(A.reconstruct_sequence, 1, joined, A.vertex2coords, A.ref2name, A.seqDict, A.ksize) if joined else []
+
     edges = A.DBG._edges.astype(np.uint32)
     res = dict(
+        joined=[(list(map(int, p_)), s_) for p_, s_ in zip(joined, joined_seqs)],
         orient_counts=orient,
         orient_sets=orient_sets,
         k=ksize,

@@ -196,6 +196,10 @@ class Assembler:
                 out[name] = {tup[int(i)] for i in mine}
         return out
 
+    def reconstruct_sequences(self, paths):
+        """`reconstruct_sequence` (`lib/Assembler.py:1038-1118`) for a list of vertex paths (e.g. joined NBPs)."""
+        return self._eng.path_sequences(paths, self.ksize)
+
     def bubble_candidates(self):
         """Groups (lists of vertex tuples) of raw NBPs that share first and last vertex -- `path_limits` entries with more
         than one path, `lib/Assembler.py:728-734`."""

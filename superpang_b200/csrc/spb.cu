@@ -1595,6 +1595,27 @@ int spb_get_bubble_groups(spb_ctx* c, uint32_t* group) {
   dfree(c, key); dfree(c, id); dfree(c, out);
   return check_err(c, "bubble_groups");
 }
+// SURVEY 8(f) row 2 (first half): sequences of host-supplied vertex paths -- reconstruct_sequence for the joined paths of
+// the host tail (reference lib/Assembler.py:1038-1118, called at :911-921).  off uint64[n_paths + 1] and verts
+// uint32[off[n_paths]] are host arrays; ascii receives off[n_paths] + n_paths * (k - 1) bytes, path i at
+// off[i] + i * (k - 1).  SPB_EINVAL if a path is shorter than 2 or two consecutive vertices are not adjacent.
+int spb_path_sequences(spb_ctx* c, uint32_t n_paths, const uint64_t* off, const uint32_t* verts, uint8_t* ascii) {
+  NEED(2);
+  if (!off || !verts || !ascii) return SPB_EINVAL;
+  if (n_paths == 0) return SPB_OK;
+  const u64 total = off[n_paths];
+  if (total == 0) return fail(c, SPB_EINVAL, "spb_path_sequences: empty paths");
+  u64* d_off; u32* d_verts; u8* d_out;
+  ALLOC(d_off, u64, (u64)n_paths + 1); ALLOC(d_verts, u32, total + 1); ALLOC(d_out, u8, total + (u64)n_paths * (c->k - 1) + 1);
+  dev_copy(c, d_off, off, 8ull * (n_paths + 1)); dev_copy(c, d_verts, verts, 4ull * total);
+  GView g{c->vflags, c->Jk, c->Js, c->nJ, c->nV};
+  SPB_LAUNCH(k_path_seqs, gs_grid(total), TPB, c->stream, g, c->F, c->R, c->T, c->k, c->v2pos, d_off, n_paths, d_verts, d_out, c->errflag);
+  dev_copy(c, ascii, d_out, total + (u64)n_paths * (c->k - 1)); dev_sync(c);
+  dfree(c, d_off); dfree(c, d_verts); dfree(c, d_out);
+  u32 e = dread(c, c->errflag);
+  if (e & ERR_BADPATH) { dev_memset(c, c->errflag, 0, 4); return fail(c, SPB_EINVAL, "spb_path_sequences: a path is shorter than 2 vertices or steps between vertices that are not adjacent"); }
+  return check_err(c, "spb_path_sequences");
+}
 int spb_get_stage_stats(spb_ctx* c, char* buf, uint64_t cap) {
   if (!c || !buf || !cap) return SPB_EINVAL;
   snprintf(buf, cap, "%s", c->stats.c_str());

@@ -21,7 +21,7 @@
 enum { VF_R = 1, VF_HASJ = 2, VF_SEQLIM = 4, VF_INIT = 8, VF_CYC = 16, VF_PSTART = 32, VF_PEND = 64, VF_IN2 = 128 };
 enum { JS_SRC_R = 1, JS_DST_R = 2, JS_CUT = 4 };
 enum { SIDE_L = 0, SIDE_R = 1 };
-enum { ERR_BADCHAR = 1, ERR_DEGENERATE = 2, ERR_OVERFLOW = 4 };
+enum { ERR_BADCHAR = 1, ERR_DEGENERATE = 2, ERR_OVERFLOW = 4, ERR_BADPATH = 8 };
 
 // ------------------------------------------------------------------------------------ bit helpers
 __device__ __forceinline__ u32 get_bit(const u32* bits, u64 i) { return (bits[i >> 5] >> (i & 31)) & 1u; }
@@ -1858,6 +1858,51 @@ __global__ void k_bubble_groups(const u64* __restrict__ skey, const u32* __restr
   u32 m = SPB_INVALID;
   if (hi - lo > 1) for (u32 q = lo; q < hi; ++q) m = sid[q] < m ? sid[q] : m;
   group[sid[j]] = m;
+}
+
+// ------------------------------------------------------------------------------------ sequences of arbitrary paths
+// reconstruct_sequence (reference lib/Assembler.py:1038-1118) for vertex paths the host hands in (joined NBPs): the
+// first k-mer plus the last base of every following one, each vertex read in the orientation in which it overlaps its
+// predecessor.  The orientation of a vertex in a path is local: it is read as stored (= as at its first appearance,
+// vertex2kmer :1063-1070) iff its predecessor attaches on its left side, so every path element is independent.
+// side of v on which nbr attaches (SIDE_L / SIDE_R), 2 = not adjacent.  Graph structure first; edges the cycle breaking
+// removed from it are recovered from the k-1 base overlaps of the stored k-mers.
+__device__ __forceinline__ u32 attach_side(const GView& g, const u32* __restrict__ F, const u32* __restrict__ R, u64 T, u32 k,
+                                           const u32* __restrict__ v2pos, u32 v, u32 nbr) {
+  if (nbr == v + 1 && (g.vflags[v] & VF_R)) return SIDE_R;
+  if (nbr + 1 == v && (g.vflags[nbr] & VF_R)) return SIDE_L;
+  if (g.vflags[v] & VF_HASJ) {
+    const u32 i = lower_bound_key(g.Jk, g.nJ, ((u64)v << 32) | nbr);
+    if (i < g.nJ && g.Jk[i] == (((u64)v << 32) | nbr)) return g.Js[i] & 1u;
+  }
+  const u64 pa = v2pos[v], pb = v2pos[nbr];          // stored k-mers: A = F[pa, pa+k), B = F[pb, pb+k), rc(B) = R[T-pb-k, T-pb)
+  if (win_cmp(F, pa + 1, F, pb, k - 1) == 0 || win_cmp(F, pa + 1, R, T - pb - k, k - 1) == 0) return SIDE_R;     // A[1:] == B[:-1] / rc(B)[:-1]
+  if (win_cmp(F, pb + 1, F, pa, k - 1) == 0 || win_cmp(R, T - pb - k + 1, F, pa, k - 1) == 0) return SIDE_L;     // B[1:] / rc(B)[1:] == A[:-1]
+  return 2u;
+}
+__global__ void k_path_seqs(GView g, const u32* __restrict__ F, const u32* __restrict__ R, u64 T, u32 k, const u32* __restrict__ v2pos,
+                            const u64* __restrict__ off, u32 n_paths, const u32* __restrict__ verts, u8* __restrict__ out, u32* err) {
+  const u64 total = off[n_paths];
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 e = SPB_GTID(); e < total; e += stride) {
+    const u32 path = upper_bound_u64(off, n_paths + 1, e) - 1;
+    const u64 i = e - off[path], len = off[path + 1] - off[path];
+    const u32 v = verts[e];
+    if (len < 2 || v >= g.nV) { atomicOr(err, (u32)ERR_BADPATH); continue; }
+    const u64 p = v2pos[v];
+    if (i == 0) {                                    // first k-mer: forward iff the second vertex attaches on its right side
+      const u32 w = verts[e + 1];
+      const u32 side = w < g.nV && w != v ? attach_side(g, F, R, T, k, v2pos, v, w) : 2u;
+      if (side > 1) { atomicOr(err, (u32)ERR_BADPATH); continue; }
+      const u64 o = e + (u64)path * (k - 1);
+      for (u32 j = 0; j < k; ++j) out[o + j] = code2ascii(side == SIDE_R ? base_at(F, p + j) : base_at(R, T - p - k + j));
+    } else {                                         // last base of the k-mer, read forward iff the predecessor attaches on the left
+      const u32 w = verts[e - 1];
+      const u32 side = w < g.nV && w != v ? attach_side(g, F, R, T, k, v2pos, v, w) : 2u;
+      if (side > 1) { atomicOr(err, (u32)ERR_BADPATH); continue; }
+      out[e + (u64)(path + 1) * (k - 1)] = code2ascii(side == SIDE_L ? base_at(F, p + k - 1) : 3u - base_at(F, p));
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------ getters

@@ -130,3 +130,39 @@ def test_gpu_seq_sets_match_reference():
         A = Assembler(dict(map(tuple, case["records"])), case["k"], device=0)
         got = {n: {v for v in s if v in defined} for n, s in A.seq_paths_nbps().items()}
         assert {n: s for n, s in got.items() if s} == _golden_sets(case), case["name"]
+
+
+# ---- row 2 (first half): reconstruct_sequence for arbitrary paths ---------------------------------------------------
+def _check_paths(A, case):
+    r = case["result"]
+    paths = [n[0] for n in r["nbps"]] + [j[0] for j in r.get("joined", [])]
+    want = [n[1] for n in r["nbps"]] + [j[1] for j in r.get("joined", [])]
+    assert A.reconstruct_sequences(paths) == want
+    return len(r.get("joined", []))
+
+
+def test_emu_path_sequences_match_reference(emu_lib):
+    """Every golden NBP (incl. broken cycles, which step over the cut edge) and the joined NBP pairs whose sequences
+    the reference's own reconstruct_sequence produced (oracle/refrun.py)."""
+    n_joined = 0
+    for case in CASES:
+        A = Assembler(dict(map(tuple, case["records"])), case["k"], engine=_capi.Engine(lib=emu_lib))
+        n_joined += _check_paths(A, case)
+    assert n_joined > 50
+
+
+def test_emu_path_sequences_reject_bad_paths(emu_lib):
+    case = next(c for c in CASES if c["name"] == "snp_bubble")
+    A = Assembler(dict(map(tuple, case["records"])), case["k"], engine=_capi.Engine(lib=emu_lib))
+    nv = A.vertex2coords.shape[0]
+    for bad in ([0], [0, nv // 2 + 7, 3], [0, 0], [nv + 5, 1]):
+        with pytest.raises(_capi.SpbError):
+            A.reconstruct_sequences([bad])
+    assert A.reconstruct_sequences([]) == []
+    assert len(A.reconstruct_sequences([[0, 1, 2]])[0]) == case["k"] + 2      # still usable after the errors
+
+
+@pytest.mark.gpu
+def test_gpu_path_sequences_match_reference():
+    for case in CASES:
+        _check_paths(Assembler(dict(map(tuple, case["records"])), case["k"], device=0), case)
