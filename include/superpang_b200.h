@@ -172,6 +172,13 @@ int spb_get_bubble_groups(spb_ctx* ctx, uint32_t* group);
  * ascii uint8[off[n_paths] + n_paths * (k - 1)], path i written at off[i] + i * (k - 1).  Needs spb_build_dbg only.
  * SPB_EINVAL when a path has fewer than 2 vertices or steps between non-adjacent vertices (the reference asserts). */
 int spb_path_sequences(spb_ctx* ctx, uint32_t n_paths, const uint64_t* off, const uint32_t* verts, uint8_t* ascii);
+/* Origins of host-supplied vertex paths that are concatenations of whole NBPs: the goodOris of the
+ * joined paths -- `get_ori2cov_onevertex` (`lib/Assembler.py:1212-1248`) + `:941-945`, before the `_Nsplit_` cut and
+ * without `bubble_vertex2origins` (the caller unions those in).  off / verts as for spb_path_sequences.  Result as CSR:
+ * out_off uint64[n_paths + 1], seq_idx uint32[cap] (ascending sequence indices per path); *n_pairs = number of pairs;
+ * when it exceeds cap only out_off is filled: call again with cap >= *n_pairs.  Needs spb_compact. */
+int spb_path_origins(spb_ctx* ctx, uint32_t n_paths, const uint64_t* off, const uint32_t* verts, uint64_t cap, uint64_t* n_pairs,
+                     uint64_t* out_off, uint32_t* seq_idx);
 /* Current counters (n_seq_intervals is filled by the first spb_get_seq_intervals call, which may
  * be made with NULL buffers just to size them). */
 int spb_get_counts(spb_ctx* ctx, spb_counts* out);

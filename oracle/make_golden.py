@@ -46,7 +46,7 @@ def full(res):
         nbps=[[list(v), s, list(o), int(c), bool(cy)] for v, s, o, c, cy in res["nbps"]],
         orient_counts=[int(x) for x in res["orient_counts"]],
         orient_sets=res["orient_sets"],
-        joined=[[list(p), s] for p, s in res["joined"]],
+        joined=[[list(p), s, list(o)] for p, s, o in res["joined"]],
     )
 
 

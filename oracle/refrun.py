@@ -154,10 +154,18 @@ def run_reference(fasta, ksize=301, threads=1, debug=True, with_origins=True, qu
                 if len(joined) < 40 and n1[0][-1] == n2[0][0] and len(set(n1[0]) & set(n2[0])) == 1:
                     joined.append(tuple(n1[0]) + tuple(n2[0][1:]))
         joined_seqs = A.multimap(A.reconstruct_sequence, 1, joined, A.vertex2coords, A.ref2name, A.seqDict, A.ksize) if joined else []
+        joined_oris = []
+        if joined and with_origins:                                                          # :922, :941-946
+            for o2c_ in A.multimap(A.get_ori2cov_onevertex, 1, joined, A.seqPaths, _dd(list), A.seqLimitsPerSeq, debug, chunksize=10):
+                good = {o for o, cov in o2c_.items() if cov >= 1}
+                good.add(list(sorted(o2c_, key=lambda o: o2c_[o], reverse=True))[0])
+                joined_oris.append(tuple(sorted({o.split('_Nsplit_')[0] for o in good})))
+        else:
+            joined_oris = [()] * len(joined)
 
     edges = A.DBG._edges.astype(np.uint32)
     res = dict(
-        joined=[(list(map(int, p_)), s_) for p_, s_ in zip(joined, joined_seqs)],
+        joined=[(list(map(int, p_)), s_, list(o_)) for p_, s_, o_ in zip(joined, joined_seqs, joined_oris)],
         orient_counts=orient,
         orient_sets=orient_sets,
         k=ksize,

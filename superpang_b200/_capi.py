@@ -23,7 +23,7 @@ EXPORTS = (
     "spb_get_vertex2coords", "spb_get_edges", "spb_get_instance_vertices", "spb_get_seqlimits",
     "spb_get_seq_intervals", "spb_get_components", "spb_get_nbps", "spb_get_nbp_seqs",
     "spb_get_nbp_origins", "spb_get_counts", "spb_get_stage_stats", "spb_build_kind", "spb_launch_count",
-    "spb_get_nbp_graph", "spb_get_nbp_orientation_counts", "spb_get_seq_nbps", "spb_get_bubble_groups", "spb_path_sequences", "spb_mg_slice", "spb_mg_probe", "spb_mg_records", "spb_mg_dedup", "spb_mg_scatter", "spb_mg_dedup_links", "spb_mg_apply_links", "spb_mg_owned_links", "spb_mg_buffers", "spb_mg_ids", "spb_mg_graph",
+    "spb_get_nbp_graph", "spb_get_nbp_orientation_counts", "spb_get_seq_nbps", "spb_get_bubble_groups", "spb_path_sequences", "spb_path_origins", "spb_mg_slice", "spb_mg_probe", "spb_mg_records", "spb_mg_dedup", "spb_mg_scatter", "spb_mg_dedup_links", "spb_mg_apply_links", "spb_mg_owned_links", "spb_mg_buffers", "spb_mg_ids", "spb_mg_graph",
 )
 
 
@@ -86,6 +86,7 @@ def _declare(lib):
     lib.spb_get_nbp_orientation_counts.argtypes = [vp, u32p]
     lib.spb_get_bubble_groups.argtypes = [vp, u32p]
     lib.spb_path_sequences.argtypes = [vp, C.c_uint32, u64p, u32p, u8p]
+    lib.spb_path_origins.argtypes = [vp, C.c_uint32, u64p, u32p, C.c_uint64, C.POINTER(C.c_uint64), u64p, u32p]
     lib.spb_get_seq_nbps.argtypes = [vp, C.POINTER(C.c_uint64), u64p, u32p]
     lib.spb_mg_slice.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint64)]
     lib.spb_mg_probe.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -445,6 +446,26 @@ class Engine:
         self._ck(self.lib.spb_path_sequences(self.h, len(paths), off.ctypes.data, verts.ctypes.data, out.ctypes.data))
         b = out.tobytes()
         return [b[int(off[i]) + i * (k - 1):int(off[i + 1]) + (i + 1) * (k - 1)].decode() for i in range(len(paths))]
+
+    def path_origins(self, paths):
+        """Per path (concatenation of whole NBPs, as vertex ids) the ascending indices of the sequences it originates from
+        (reference get_ori2cov_onevertex + goodOris, lib/Assembler.py:1212-1248, :941-945)."""
+        paths = [np.asarray(p, dtype=np.uint32) for p in paths]
+        if not paths:
+            return []
+        off = np.zeros(len(paths) + 1, dtype=np.uint64)
+        np.cumsum([len(p) for p in paths], out=off[1:])
+        verts = np.ascontiguousarray(np.concatenate(paths))
+        ooff = np.zeros(len(paths) + 1, dtype=np.uint64)
+        cap, n = 64 * len(paths), C.c_uint64()
+        for _ in range(2):
+            ids = np.empty(max(cap, 1), dtype=np.uint32)
+            self._ck(self.lib.spb_path_origins(self.h, len(paths), off.ctypes.data, verts.ctypes.data, cap, C.byref(n),
+                                               ooff.ctypes.data, ids.ctypes.data))
+            if n.value <= cap:
+                break
+            cap = n.value
+        return [ids[int(ooff[i]):int(ooff[i + 1])].tolist() for i in range(len(paths))]
 
     def bubble_groups(self):
         """group[i] = smallest raw NBP id among the NBPs sharing (first, last) vertex with NBP i, 0xFFFFFFFF if none

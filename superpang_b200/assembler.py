@@ -200,6 +200,13 @@ class Assembler:
         """`reconstruct_sequence` (`lib/Assembler.py:1038-1118`) for a list of vertex paths (e.g. joined NBPs)."""
         return self._eng.path_sequences(paths, self.ksize)
 
+    def path_origins(self, paths):
+        """Origin names (sorted, `_Nsplit_` suffixes cut as at `lib/Assembler.py:946`) of vertex paths that are concatenations
+        of whole NBPs -- `get_ori2cov_onevertex` + goodOris for the joined paths of the host tail."""
+        self.compact()
+        short = [n.split("_Nsplit_")[0] for n in self.ref2name]
+        return [tuple(sorted({short[j] for j in ids})) for ids in self._eng.path_origins(paths)]
+
     def bubble_candidates(self):
         """Groups (lists of vertex tuples) of raw NBPs that share first and last vertex -- `path_limits` entries with more
         than one path, `lib/Assembler.py:728-734`."""

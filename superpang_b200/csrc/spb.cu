@@ -49,6 +49,7 @@ struct spb_ctx {
   u32* iv = 0; u64* iv_off = 0;
   u64* g_off = 0; u32 *g_succ = 0, *g_rev = 0; u64 g_edges = 0;      // NBP graph (lazy)
   u32 *occ_counts = 0, *occ_ids = 0; u64* occ_off = 0; u64 occ_pairs = 0;   // NBP occurrences in the sequences (lazy)
+  u64* ivp = 0; u32 n_ivp = 0, ivp_sb = 0;                          // (init vertex, sequence) pairs (lazy)
   // staged dedup state (records sent by this rank)
   u64 *dd_keys = 0, *dd_bstart = 0; u32* dd_pos = 0; u64 dd_n = 0, dd_lo = 0, dd_hi = 0; u32 dd_bb = 0; bool dd_fbits_ready = false;
   std::vector<u64> dd_bstart_h;
@@ -1615,6 +1616,93 @@ int spb_path_sequences(spb_ctx* c, uint32_t n_paths, const uint64_t* off, const 
   u32 e = dread(c, c->errflag);
   if (e & ERR_BADPATH) { dev_memset(c, c->errflag, 0, 4); return fail(c, SPB_EINVAL, "spb_path_sequences: a path is shorter than 2 vertices or steps between vertices that are not adjacent"); }
   return check_err(c, "spb_path_sequences");
+}
+// (init vertex, sequence) pairs, sorted unique, built once per compaction (incl. the leading-zero quirk for vertex 0)
+static int build_init_seq_pairs(spb_ctx* c) {
+  if (c->ivp) return 0;
+  const u64 T = c->T;
+  u32 sb = 1; while ((1ull << sb) <= c->n_seq) ++sb;
+  u64* cnt; ALLOC(cnt, u64, 2);
+  u8* has01; ALLOC(has01, u8, 2ull * c->n_seq + 8);
+  u64 cap = std::max<u64>(4096, c->n_inst / 16);
+  u64* pairs = nullptr; u64 np = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    ALLOC(pairs, u64, cap + 1);
+    dev_memset(c, cnt, 0, 16); dev_memset(c, has01, 0, 2ull * c->n_seq + 8);
+    SPB_LAUNCH(k_init_seq_pairs, gs_grid(T), TPB, c->stream, c->sp, T, c->vflags, c->seq_off, c->n_seq, sb, pairs, cnt, cap, has01);
+    SPB_LAUNCH(k_init_seq_quirk, nblk(c->n_seq, TPB), TPB, c->stream, has01, c->n_seq, c->vflags, sb, pairs, cnt, cap);
+    np = dread(c, cnt);
+    if (np <= cap) break;
+    dfree(c, pairs); cap = np;
+  }
+  dfree(c, cnt); dfree(c, has01);
+  u32 nu = 0;
+  if (np) {
+    u64* tmp; ALLOC(tmp, u64, np + 1);
+    PRIM(prim_sort_u64(c, pairs, tmp, np));
+    dfree(c, tmp);
+    u8* nopay = nullptr;
+    PRIM(unique_sorted(c, pairs, nopay, np, &nu));
+  }
+  c->ivp = pairs; c->n_ivp = nu; c->ivp_sb = sb;
+  return check_err(c, "init_seq_pairs");
+}
+// SURVEY 8(f) row 2 (second half): origins of host-supplied vertex paths that are concatenations of whole NBPs -- the
+// goodOris of the joined paths (reference get_ori2cov_onevertex, lib/Assembler.py:1212-1248, + :941-945, without the
+// `_Nsplit_` cut and without bubble_vertex2origins, which the caller unions in).  Result as CSR over the paths:
+// out_off uint64[n_paths + 1], seq_idx uint32[<= cap] ascending per path; *n_pairs = pairs needed (call again with a
+// larger `cap` when it exceeds it).
+int spb_path_origins(spb_ctx* c, uint32_t n_paths, const uint64_t* off, const uint32_t* verts, uint64_t cap, uint64_t* n_pairs,
+                     uint64_t* out_off, uint32_t* seq_idx) {
+  NEED(3);
+  if (!off || !verts || !n_pairs || !out_off || (cap && !seq_idx)) return SPB_EINVAL;
+  *n_pairs = 0;
+  if (n_paths == 0) { out_off[0] = 0; return SPB_OK; }
+  const u64 total = off[n_paths];
+  if (total == 0) return fail(c, SPB_EINVAL, "spb_path_origins: empty paths");
+  int r = build_init_seq_pairs(c);
+  if (r) return r;
+  u64* d_off; u32* d_verts; u64 *cnt, *pairs = nullptr;
+  ALLOC(d_off, u64, (u64)n_paths + 1); ALLOC(d_verts, u32, total + 1); ALLOC(cnt, u64, 2);
+  dev_copy(c, d_off, off, 8ull * (n_paths + 1)); dev_copy(c, d_verts, verts, 4ull * total);
+  u64 pcap = std::max<u64>(4096, 8ull * n_paths + cap), np = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    ALLOC(pairs, u64, pcap + 1);
+    dev_memset(c, cnt, 0, 16);
+    SPB_LAUNCH(k_path_origin_pairs, gs_grid(total), TPB, c->stream, d_off, n_paths, d_verts, c->nV, c->vflags, c->vnbp, c->ooff, c->origins,
+               c->ivp, c->n_ivp, c->ivp_sb, pairs, cnt, pcap, c->errflag);
+    np = dread(c, cnt);
+    if (np <= pcap) break;
+    dfree(c, pairs); pcap = np;
+  }
+  dfree(c, d_off); dfree(c, d_verts); dfree(c, cnt);
+  u32 e = dread(c, c->errflag);
+  if (e & ERR_BADPATH) {
+    dev_memset(c, c->errflag, 0, 4); dfree(c, pairs);
+    return fail(c, SPB_EINVAL, "spb_path_origins: a path is shorter than 2 vertices, holds an unknown vertex, or is not a concatenation of NBPs");
+  }
+  u32 nu = 0;
+  if (np) {
+    u64* tmp; ALLOC(tmp, u64, np + 1);
+    PRIM(prim_sort_u64(c, pairs, tmp, np));
+    dfree(c, tmp);
+    u8* nopay = nullptr;
+    PRIM(unique_sorted(c, pairs, nopay, np, &nu));
+  }
+  *n_pairs = nu;
+  u64* d_out; ALLOC(d_out, u64, (u64)n_paths + 2);
+  SPB_LAUNCH(k_path_origin_offsets, nblk((u64)n_paths + 1, TPB), TPB, c->stream, pairs, nu, n_paths, d_out);
+  dev_copy(c, out_off, d_out, 8ull * (n_paths + 1));
+  if (nu && nu <= cap) {
+    u32* ids; ALLOC(ids, u32, (u64)nu + 1);
+    SPB_LAUNCH(k_occ_ids, nblk(nu, TPB), TPB, c->stream, pairs, nu, ids);
+    dev_copy(c, seq_idx, ids, 4ull * nu);
+    dev_sync(c);
+    dfree(c, ids);
+  }
+  dev_sync(c);
+  dfree(c, d_out); dfree(c, pairs);
+  return check_err(c, "spb_path_origins");
 }
 int spb_get_stage_stats(spb_ctx* c, char* buf, uint64_t cap) {
   if (!c || !buf || !cap) return SPB_EINVAL;

@@ -1905,6 +1905,79 @@ __global__ void k_path_seqs(GView g, const u32* __restrict__ F, const u32* __res
   }
 }
 
+// ------------------------------------------------------------------------------------ origins of arbitrary paths
+// get_ori2cov_onevertex + goodOris (reference lib/Assembler.py:1212-1248, :941-946) for host-supplied paths that are
+// concatenations of whole NBPs (the joined paths of the tail): a path of more than two vertices originates from every
+// sequence that holds one of its INTERIOR vertices.  An interior extender contributes the origin list of its NBP (already
+// computed: the union over the NBP's interior), an interior init contributes the sequences that hold it -- (init vertex,
+// sequence) pairs collected once from the per-position vertex ids, incl. the leading-zero quirk for vertex 0.
+__global__ void k_init_seq_pairs(const u32* __restrict__ sp, u64 T, const u8* __restrict__ vflags, const u64* __restrict__ seq_off, u32 n_seq,
+                                 u32 sb, u64* __restrict__ pairs, u64* npairs, u64 cap, u8* __restrict__ has01) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 p = SPB_GTID(); p < T; p += stride) {
+    const u32 v = sp[p];
+    if (v == SPB_INVALID) continue;
+    const bool ini = (vflags[v] & VF_INIT) != 0;
+    if (!ini && v > 1) continue;
+    const u32 s = upper_bound_u64(seq_off, n_seq + 1, p) - 1;
+    if (v <= 1) has01[2 * s + v] = 1;
+    if (ini) { const u64 i = atomicAdd(npairs, 1ull); if (i < cap) pairs[i] = ((u64)v << sb) | s; }
+  }
+}
+__global__ void k_init_seq_quirk(const u8* __restrict__ has01, u32 n_seq, const u8* __restrict__ vflags, u32 sb, u64* __restrict__ pairs,
+                                 u64* npairs, u64 cap) {
+  const u64 s = SPB_GTID();
+  if (s >= n_seq) return;
+  if (has01[2 * s + 1] && !has01[2 * s] && (vflags[0] & VF_INIT)) { const u64 i = atomicAdd(npairs, 1ull); if (i < cap) pairs[i] = s; }   // vertex 0
+}
+__global__ void k_path_origin_pairs(const u64* __restrict__ off, u32 n_paths, const u32* __restrict__ verts, u32 nV, const u8* __restrict__ vflags,
+                                    const u32* __restrict__ vnbp, const u64* __restrict__ ooff, const u32* __restrict__ origins,
+                                    const u64* __restrict__ ivp, u32 n_ivp, u32 sb, u64* __restrict__ out, u64* nout, u64 cap, u32* err) {
+  const u64 total = off[n_paths];
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 e = SPB_GTID(); e < total; e += stride) {
+    const u32 path = upper_bound_u64(off, n_paths + 1, e) - 1;
+    const u64 i = e - off[path], len = off[path + 1] - off[path];
+    const u32 v = verts[e];
+    if (len < 2 || v >= nV) { atomicOr(err, (u32)ERR_BADPATH); continue; }
+    if (len == 2) {                                  // both vertices must be held: intersection of the two init lists
+      if (i) continue;
+      const u32 w = verts[e + 1];
+      if (w >= nV || !(vflags[v] & VF_INIT) || !(vflags[w] & VF_INIT)) { atomicOr(err, (u32)ERR_BADPATH); continue; }
+      u32 a = lower_bound_key(ivp, n_ivp, (u64)v << sb), ae = lower_bound_key(ivp, n_ivp, ((u64)v + 1) << sb);
+      u32 b = lower_bound_key(ivp, n_ivp, (u64)w << sb), be = lower_bound_key(ivp, n_ivp, ((u64)w + 1) << sb);
+      const u64 m = (1ull << sb) - 1;
+      while (a < ae && b < be) {
+        const u64 x = ivp[a] & m, y = ivp[b] & m;
+        if (x < y) ++a; else if (y < x) ++b;
+        else { const u64 j = atomicAdd(nout, 1ull); if (j < cap) out[j] = ((u64)path << 32) | x; ++a; ++b; }
+      }
+      continue;
+    }
+    if (i == 0 || i == len - 1) continue;            // the end vertices overlap other paths (:1224-1227)
+    if (vflags[v] & VF_INIT) {
+      for (u32 a = lower_bound_key(ivp, n_ivp, (u64)v << sb), ae = lower_bound_key(ivp, n_ivp, ((u64)v + 1) << sb); a < ae; ++a) {
+        const u64 j = atomicAdd(nout, 1ull);
+        if (j < cap) out[j] = ((u64)path << 32) | (ivp[a] & ((1ull << sb) - 1));
+      }
+    } else {
+      const u32 x = vnbp[v];
+      if (x == SPB_INVALID) { atomicOr(err, (u32)ERR_BADPATH); continue; }
+      const u32 pv = verts[e - 1];
+      if (i > 1 && pv < nV && !(vflags[pv] & VF_INIT) && vnbp[pv] == x) continue;      // same NBP as the element before: listed once
+      for (u64 a = ooff[x]; a < ooff[x + 1]; ++a) {
+        const u64 j = atomicAdd(nout, 1ull);
+        if (j < cap) out[j] = ((u64)path << 32) | origins[a];
+      }
+    }
+  }
+}
+__global__ void k_path_origin_offsets(const u64* __restrict__ keys, u32 n, u32 n_paths, u64* __restrict__ off) {
+  const u64 p = SPB_GTID();
+  if (p > n_paths) return;
+  off[p] = lower_bound_key(keys, n, p << 32);
+}
+
 // ------------------------------------------------------------------------------------ getters
 __global__ void k_coords(const u32* __restrict__ v2pos, u32 nV, const u64* __restrict__ seq_off, u32 n_seq, u32* __restrict__ out) {
   u64 v = SPB_GTID();

@@ -138,6 +138,10 @@ def _check_paths(A, case):
     paths = [n[0] for n in r["nbps"]] + [j[0] for j in r.get("joined", [])]
     want = [n[1] for n in r["nbps"]] + [j[1] for j in r.get("joined", [])]
     assert A.reconstruct_sequences(paths) == want
+    # row 2, second half: origins of the same paths (raw NBPs: goldens of the NBP collection; joined pairs: the
+    # reference's own get_ori2cov_onevertex + goodOris, oracle/refrun.py)
+    want_o = [tuple(n[2]) for n in r["nbps"]] + [tuple(j[2]) for j in r.get("joined", [])]
+    assert A.path_origins(paths) == want_o
     return len(r.get("joined", []))
 
 
