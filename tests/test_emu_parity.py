@@ -92,6 +92,8 @@ def test_emu_matches_oracle_random(emu_lib, seqs, k):
     want_sets = {n: {raw[i][0] for i in ids} for n, ids in dbg_oracle.seq_paths_nbps(raw, seqs).items()}
     assert A.seq_paths_nbps() == want_sets
     assert sorted(sorted(g) for g in A.bubble_candidates()) == sorted(sorted(g) for g in dbg_oracle.bubble_candidates(raw))
+    assert A.reconstruct_sequences([r[0] for r in raw]) == [r[1] for r in raw]       # row 2: the path getters on the raw NBPs
+    assert A.path_origins([r[0] for r in raw]) == [r[2] for r in raw]
 
 
 @pytest.mark.parametrize("k,env", [(1001, {}), (2001, {}), (1001, {"SPB_DEDUP": "smem", "SPB_SMEM_AVG": "500"}), (75, {"SPB_DEDUP": "smem"})])
