@@ -31,6 +31,7 @@ def _free_port():
     (2, {"SPB_MG_PROTOCOL": "owned"}),                               # owner computes: nothing but links travels
     (4, {"SPB_MG_PROTOCOL": "owned", "SPB_SMEM_AVG": "60", "SPB_EMU_ORDER": "reverse"}),
     (2, {"SPB_MG_PROTOCOL": "owned", "SPB_SMEM_AVG": "1", "SPB_EMU_ORDER": "shuffle"}),
+    (8, {"SPB_MG_PROTOCOL": "owned", "SPB_SMEM_AVG": "200"}),          # the driver's largest scaling point
     (2, {"SPB_MG_PROTOCOL": "owned", "SPB_SMEM_LIMIT": "10"}),       # sub-buckets beyond the shared-memory table: tables in global memory
     (2, {"SPB_CHUNK_BITS": "8"}),                                    # protocol chosen by the duplicate-rate probe
 ], ids=lambda x: str(x) if isinstance(x, int) else (",".join(f"{k[4:].lower()}={v}" for k, v in x.items()) or "default"))
