@@ -287,6 +287,8 @@ def main():
                           # SURVEY 8(d) model, which charges every instance for a materialised 2k-bit key; the rolling-hash /
                           # verify-in-place design moves less than that, so `frac` can exceed 1 while `traffic_frac` cannot.
                           traffic_frac=(traffic / (dom_ms / 1e3) / 1e9 / peak) if traffic else None,
+                          note=("frac uses the SURVEY 8(d) byte model (a materialised 2k-bit key per instance); the design moves "
+                                "fewer bytes than that (see traffic / traffic_frac), so frac may exceed 1"),
                           peak_source=peak_src, kernel_ms=dom_ms, model_bytes=dom_bytes,
                           pipeline=dict(achieved=pipe_ach, frac=pipe_ach / peak, bytes=pipe_bytes)),
             stages_ms=st_mean,
