@@ -179,6 +179,17 @@ int spb_path_sequences(spb_ctx* ctx, uint32_t n_paths, const uint64_t* off, cons
  * when it exceeds cap only out_off is filled: call again with cap >= *n_pairs.  Needs spb_compact. */
 int spb_path_origins(spb_ctx* ctx, uint32_t n_paths, const uint64_t* off, const uint32_t* verts, uint64_t cap, uint64_t* n_pairs,
                      uint64_t* out_off, uint32_t* seq_idx);
+/* FASTA reader + N-splitter: native form of the reference's `read_fasta(fasta, ambigs='as_Ns',
+ * Ns='split', gap_size)` (`lib/utils.py:5-30`, `:52-59`): whitespace / '.' / '-' removed, upper case, U -> T, IUPAC
+ * ambiguity codes -> N, any other character is an error, records split at runs of gap_size Ns into `{name}_Nsplit_{i}`,
+ * duplicated names are an error.  Fills the buffers spb_load takes; release with spb_free_fasta.  names: n_seq names,
+ * each followed by '\n'.  err (optional) receives the message of a refused input. */
+typedef struct spb_fasta {
+  uint8_t* ascii; uint64_t* seq_off; char* names;
+  uint32_t n_seq; uint64_t n_bases; uint64_t names_bytes;
+} spb_fasta;
+int spb_read_fasta(const char* path, uint32_t gap_size, spb_fasta* out, char* err, uint64_t err_cap);
+void spb_free_fasta(spb_fasta* fa);
 /* Current counters (n_seq_intervals is filled by the first spb_get_seq_intervals call, which may
  * be made with NULL buffers just to size them). */
 int spb_get_counts(spb_ctx* ctx, spb_counts* out);

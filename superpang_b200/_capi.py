@@ -23,7 +23,7 @@ EXPORTS = (
     "spb_get_vertex2coords", "spb_get_edges", "spb_get_instance_vertices", "spb_get_seqlimits",
     "spb_get_seq_intervals", "spb_get_components", "spb_get_nbps", "spb_get_nbp_seqs",
     "spb_get_nbp_origins", "spb_get_counts", "spb_get_stage_stats", "spb_build_kind", "spb_launch_count",
-    "spb_get_nbp_graph", "spb_get_nbp_orientation_counts", "spb_get_seq_nbps", "spb_get_bubble_groups", "spb_path_sequences", "spb_path_origins", "spb_mg_slice", "spb_mg_probe", "spb_mg_records", "spb_mg_dedup", "spb_mg_scatter", "spb_mg_dedup_links", "spb_mg_apply_links", "spb_mg_owned_links", "spb_mg_buffers", "spb_mg_ids", "spb_mg_graph",
+    "spb_get_nbp_graph", "spb_get_nbp_orientation_counts", "spb_get_seq_nbps", "spb_get_bubble_groups", "spb_path_sequences", "spb_path_origins", "spb_read_fasta", "spb_free_fasta", "spb_mg_slice", "spb_mg_probe", "spb_mg_records", "spb_mg_dedup", "spb_mg_scatter", "spb_mg_dedup_links", "spb_mg_apply_links", "spb_mg_owned_links", "spb_mg_buffers", "spb_mg_ids", "spb_mg_graph",
 )
 
 
@@ -45,6 +45,28 @@ class SpbError(RuntimeError):
 
 class DegenerateInputError(SpbError):
     """Inputs on which the reference's own assertions fire (even k / orientation-ambiguous repeats)."""
+
+
+class SpbFasta(C.Structure):
+    _fields_ = [("ascii", C.POINTER(C.c_uint8)), ("seq_off", C.POINTER(C.c_uint64)), ("names", C.POINTER(C.c_char)),
+                ("n_seq", C.c_uint32), ("n_bases", C.c_uint64), ("names_bytes", C.c_uint64)]
+
+
+def read_fasta_native(path, gap_size=1, lib=None):
+    """(names, ascii uint8[T], seq_off uint64[n + 1]) through the library's FASTA reader (reference read_fasta with
+    ambigs='as_Ns', Ns='split'; lib/utils.py:5-30).  Raises ValueError for what the reference refuses."""
+    lib = lib if lib is not None else load_library()
+    fa, err = SpbFasta(), C.create_string_buffer(512)
+    rc = lib.spb_read_fasta(os.fsencode(path), int(gap_size), C.byref(fa), err, 512)
+    if rc != 0:
+        raise ValueError(err.value.decode() or f"spb_read_fasta failed ({rc})")
+    try:
+        buf = np.ctypeslib.as_array(fa.ascii, shape=(max(int(fa.n_bases), 1),))[:int(fa.n_bases)].copy()
+        off = np.ctypeslib.as_array(fa.seq_off, shape=(fa.n_seq + 1,)).copy()
+        names = C.string_at(fa.names, int(fa.names_bytes)).decode().split("\n")[:-1] if fa.names_bytes else []
+    finally:
+        lib.spb_free_fasta(C.byref(fa))
+    return names, buf, off
 
 
 def load_library(path=None):
@@ -85,6 +107,9 @@ def _declare(lib):
     lib.spb_get_nbp_graph.argtypes = [vp, C.POINTER(C.c_uint64), u64p, u32p, u32p]
     lib.spb_get_nbp_orientation_counts.argtypes = [vp, u32p]
     lib.spb_get_bubble_groups.argtypes = [vp, u32p]
+    lib.spb_read_fasta.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(SpbFasta), C.c_char_p, C.c_uint64]
+    lib.spb_free_fasta.argtypes = [C.POINTER(SpbFasta)]
+    lib.spb_free_fasta.restype = None
     lib.spb_path_sequences.argtypes = [vp, C.c_uint32, u64p, u32p, u8p]
     lib.spb_path_origins.argtypes = [vp, C.c_uint32, u64p, u32p, C.c_uint64, C.POINTER(C.c_uint64), u64p, u32p]
     lib.spb_get_seq_nbps.argtypes = [vp, C.POINTER(C.c_uint64), u64p, u32p]

@@ -1704,6 +1704,91 @@ int spb_path_origins(spb_ctx* c, uint32_t n_paths, const uint64_t* off, const ui
   dfree(c, d_out); dfree(c, pairs);
   return check_err(c, "spb_path_origins");
 }
+// ------------------------------------------------------------------------------------ FASTA reader
+// Native restatement of the reference's read_fasta(fasta, ambigs='as_Ns', Ns='split', gap_size) (lib/utils.py:5-30, :52-59):
+// the concatenated ASCII buffer + offsets that spb_load takes, without a pass through Python strings.
+static void fasta_error(char* err, uint64_t cap, const std::string& m) { if (err && cap) snprintf(err, cap, "%s", m.c_str()); }
+int spb_read_fasta(const char* path, uint32_t gap_size, spb_fasta* out, char* err, uint64_t err_cap) {
+  if (!path || !out || gap_size == 0) return SPB_EINVAL;
+  memset(out, 0, sizeof *out);
+  FILE* f = fopen(path, "rb");
+  if (!f) { fasta_error(err, err_cap, std::string("cannot open ") + path); return SPB_EINVAL; }
+  std::string txt;
+  { char buf[1 << 16]; size_t n; while ((n = fread(buf, 1, sizeof buf, f)) > 0) txt.append(buf, n); }
+  fclose(f);
+  auto is_ws = [](unsigned char ch) { return ch == ' ' || (ch >= 9 && ch <= 13) || (ch >= 28 && ch <= 31); };   // str.strip() / re \s on ASCII
+  size_t b = 0, e = txt.size();
+  while (b < e && is_ws((unsigned char)txt[b])) ++b;
+  while (e > b && is_ws((unsigned char)txt[e - 1])) --e;
+  while (b < e && txt[b] == '>') ++b;                                        // .lstrip('>')
+  std::vector<std::string> names; std::vector<std::string> seqs;
+  std::vector<std::string> keys;                                              // for the duplicate check (small inputs: linear is fine up to a few thousand; use a sorted copy)
+  std::map<std::string, int> seen;
+  const std::string gap(gap_size, 'N');
+  size_t pos = b;
+  while (pos <= e) {
+    size_t nx = txt.find("\n>", pos);
+    if (nx == std::string::npos || nx >= e) nx = e;
+    const size_t nl = txt.find('\n', pos);
+    if (nl == std::string::npos || nl >= nx) { fasta_error(err, err_cap, "record without a sequence line"); return SPB_EINVAL; }
+    std::string name = txt.substr(pos, nl - pos);
+    const size_t sp = name.find(' ');
+    if (sp != std::string::npos) name.resize(sp);
+    std::string seq; seq.reserve(nx - nl);
+    for (size_t i = nl + 1; i < nx; ++i) {
+      unsigned char ch = (unsigned char)txt[i];
+      if (is_ws(ch) || ch == '.' || ch == '-') continue;
+      if (ch >= 'a' && ch <= 'z') ch = (unsigned char)(ch - 32);
+      if (ch == 'U') ch = 'T';
+      switch (ch) { case 'R': case 'Y': case 'K': case 'M': case 'S': case 'W': case 'B': case 'D': case 'H': case 'V': ch = 'N'; default: break; }
+      if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T' && ch != 'N') {
+        fasta_error(err, err_cap, "Illegal chars in seq \"" + name + "\"");
+        return SPB_EINVAL;
+      }
+      seq.push_back((char)ch);
+    }
+    if (seen.count(name)) { fasta_error(err, err_cap, "Sequence \"" + name + "\" is duplicated in your input file"); return SPB_EINVAL; }
+    auto put = [&](const std::string& n, std::string&& q) {
+      auto it = seen.find(n);
+      if (it != seen.end()) seqs[it->second] = std::move(q);                  // dict assignment keeps the first insertion position
+      else { seen[n] = (int)names.size(); names.push_back(n); seqs.push_back(std::move(q)); }
+    };
+    if (seq.find(gap) == std::string::npos) put(name, std::move(seq));
+    else {
+      int idx = 0; size_t a = 0;
+      for (;;) {
+        size_t g = seq.find(gap, a);
+        std::string piece = seq.substr(a, g == std::string::npos ? std::string::npos : g - a);
+        size_t p0 = 0, p1 = piece.size();
+        while (p0 < p1 && piece[p0] == 'N') ++p0;
+        while (p1 > p0 && piece[p1 - 1] == 'N') --p1;
+        if (p1 > p0) { put(name + "_Nsplit_" + std::to_string(idx), piece.substr(p0, p1 - p0)); ++idx; }
+        if (g == std::string::npos) break;
+        a = g + gap.size();
+      }
+    }
+    if (nx >= e) break;
+    pos = nx + 2;
+  }
+  uint64_t total = 0, nbytes = 0;
+  for (auto& q : seqs) total += q.size();
+  for (auto& n : names) nbytes += n.size() + 1;
+  out->n_seq = (uint32_t)names.size(); out->n_bases = total; out->names_bytes = nbytes;
+  out->ascii = (uint8_t*)malloc(total ? total : 1); out->seq_off = (uint64_t*)malloc(8 * (names.size() + 1)); out->names = (char*)malloc(nbytes ? nbytes : 1);
+  if (!out->ascii || !out->seq_off || !out->names) { spb_free_fasta(out); return SPB_ENOMEM; }
+  uint64_t o = 0, no = 0;
+  for (size_t i = 0; i < names.size(); ++i) {
+    out->seq_off[i] = o; memcpy(out->ascii + o, seqs[i].data(), seqs[i].size()); o += seqs[i].size();
+    memcpy(out->names + no, names[i].data(), names[i].size()); no += names[i].size(); out->names[no++] = '\n';
+  }
+  out->seq_off[names.size()] = o;
+  return SPB_OK;
+}
+void spb_free_fasta(spb_fasta* fa) {
+  if (!fa) return;
+  free(fa->ascii); free(fa->seq_off); free(fa->names);
+  memset(fa, 0, sizeof *fa);
+}
 int spb_get_stage_stats(spb_ctx* c, char* buf, uint64_t cap) {
   if (!c || !buf || !cap) return SPB_EINVAL;
   snprintf(buf, cap, "%s", c->stats.c_str());
