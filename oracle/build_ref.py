@@ -6,8 +6,11 @@ The reference's hot path uses three Cython modules (`src/superpang/lib/Compresso
 `vtools.pyx`, `cutils.pyx`; built by the reference's `setup.py:5-7`).  This script compiles them
 *from where they lie under /root/reference* (the .pyx files are staged in a temp dir because the
 reference tree is read-only and cythonize writes the generated .c next to its input) and puts
-ONLY the built extension modules into `oracle/_ref/superpang_lib/`.  No reference source is
-copied into the repository; `oracle/_ref/` is git-ignored but travels to the GPU box.
+the built extension modules into `oracle/_ref/superpang_lib/`.  `stage()` additionally places a runnable copy of the
+reference package (its .py files, VERSION and the built extensions) under `oracle/_ref/superpang/`, so that
+`bench.py --impl reference` and the drop-in CLI test can run the UNMODIFIED reference on the GPU box, where
+/root/reference does not exist.  `oracle/_ref/` is a build output: git-ignored (no reference source enters the
+repository history) but not gpurun-ignored, so it travels to the GPU box like the built .so files.
 
 Usage:  python oracle/build_ref.py [--reference /root/reference]
 """
@@ -52,10 +55,38 @@ def build(reference="/root/reference", force=False):
     return True
 
 
+STAGED = os.path.join(HERE, "_ref", "superpang")
+
+
+def staged():
+    return os.path.exists(os.path.join(STAGED, "lib", "Assembler.py")) and all(
+        glob.glob(os.path.join(STAGED, "lib", m + ".*.so")) for m in MODULES)
+
+
+def stage(reference="/root/reference", force=False):
+    """oracle/_ref/superpang/ = runnable copy of the reference package (build container only)."""
+    src = os.path.join(reference, "src", "superpang")
+    if staged() and not force:
+        return True
+    if not build(reference, force):
+        return False
+    for sub in ("", "lib", "scripts"):
+        os.makedirs(os.path.join(STAGED, sub), exist_ok=True)
+        for f in os.listdir(os.path.join(src, sub)):
+            a = os.path.join(src, sub, f)
+            if os.path.isfile(a) and not os.path.islink(a) and (f.endswith(".py") or f == "VERSION"):
+                b = os.path.join(STAGED, sub, f)
+                shutil.copyfile(a, b)
+                os.chmod(b, 0o755 if sub == "scripts" else 0o644)
+    for so in glob.glob(os.path.join(OUT, "*.so")):
+        shutil.copyfile(so, os.path.join(STAGED, "lib", os.path.basename(so)))
+    return True
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
     ap.add_argument("--force", action="store_true")
     a = ap.parse_args()
-    ok = build(a.reference, a.force)
-    print("oracle/_ref built" if ok else "reference not present; nothing built")
+    ok = stage(a.reference, a.force)
+    print("oracle/_ref built and staged" if ok else "reference not present; nothing built")

@@ -26,21 +26,32 @@ REFERENCE = os.environ.get("SPB_REFERENCE", "/root/reference")
 
 
 def available():
-    return os.path.isdir(os.path.join(REFERENCE, "src", "superpang", "lib"))
+    """The reference can be run: either its tree is present (build container) or `build_ref.stage()` left a runnable
+    copy under oracle/_ref/superpang (which travels to the GPU box)."""
+    if HERE not in sys.path:
+        sys.path.insert(0, HERE)
+    import build_ref
+    return os.path.isdir(os.path.join(REFERENCE, "src", "superpang", "lib")) or build_ref.staged()
+
+
+def reference_root():
+    """Directory to put on sys.path so that `import superpang` finds the unmodified reference."""
+    if HERE not in sys.path:
+        sys.path.insert(0, HERE)
+    import build_ref
+    if os.path.isdir(os.path.join(REFERENCE, "src", "superpang", "lib")):
+        build_ref.stage(REFERENCE)
+    if not build_ref.staged():
+        raise RuntimeError("reference not present and not staged (run oracle/build_ref.py in the build container)")
+    return os.path.dirname(build_ref.STAGED)
 
 
 def import_reference():
-    """Import the reference Assembler class; returns (Assembler, lib modules dict)."""
-    if not available():
-        raise RuntimeError("reference tree not present")
-    sys.path.insert(0, os.path.join(HERE, "shims"))
-    sys.path.insert(0, os.path.join(REFERENCE, "src"))
-    import build_ref  # noqa  (oracle/ is on sys.path when run as a script or via tests)
-    build_ref.build(REFERENCE)
-    import superpang.lib as lib
-    p = os.path.join(HERE, "_ref", "superpang_lib")
-    if p not in lib.__path__:
-        lib.__path__.append(p)
+    """Import the reference Assembler class (from the staged copy, oracle/_ref/superpang)."""
+    root = reference_root()
+    for p in (os.path.join(HERE, "shims"), root):
+        if p not in sys.path:
+            sys.path.insert(0, p)
     from superpang.lib.Assembler import Assembler
     return Assembler
 

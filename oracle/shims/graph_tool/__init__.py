@@ -89,11 +89,18 @@ class Graph:
         self._vfilt = None                                  # live _PropertyMap (or None)
         self._vfilt_inv = False
         self._dyn_out, self._dyn_in, self._dyn_edges = [], [], []   # dynamic graphs (add_vertex / add_edge)
+        self._dyn_out_e, self._dyn_in_e = [], []                    # edge index of every adjacency entry (edge filter)
         self.vp = _PropDict()
         self.ep = _PropDict()
 
     # -- construction -------------------------------------------------------------------
     def add_edge_list(self, edges):
+        if self._directed:                                   # condense-edges.py:64: directed graph, vertices added before
+            for a, b in edges:
+                while self._nv <= max(int(a), int(b)):
+                    self.add_vertex()
+                self.add_edge(a, b)
+            return
         edges = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
         self._edges = edges
         self._nv = int(edges.max()) + 1 if edges.size else 0
@@ -117,6 +124,8 @@ class Graph:
     def add_vertex(self):
         self._dyn_out.append([])
         self._dyn_in.append([])
+        self._dyn_out_e.append([])
+        self._dyn_in_e.append([])
         self._nv += 1
         return self._nv - 1
 
@@ -124,6 +133,8 @@ class Graph:
         a, b = int(a), int(b)
         self._dyn_out[a].append(b)
         self._dyn_in[b].append(a)
+        self._dyn_out_e[a].append(len(self._dyn_edges))
+        self._dyn_in_e[b].append(len(self._dyn_edges))
         self._dyn_edges.append((a, b))
         return _Edge(a, b, len(self._dyn_edges) - 1)
 
@@ -137,6 +148,9 @@ class Graph:
             return True
         x = bool(self._vfilt.a[v])
         return (not x) if self._vfilt_inv else x
+
+    def _evis(self, e):
+        return self._efilt is None or e >= len(self._efilt) or bool(self._efilt[e])
 
     def set_vertex_filter(self, prop, inverted=False):
         self._vfilt = prop
@@ -165,7 +179,7 @@ class Graph:
             if self._efilt is not None:
                 return int(np.count_nonzero(self._efilt))
             return self._edges.shape[0]
-        return sum(1 for a, b in self._dyn_edges if self._vis(a) and self._vis(b))
+        return sum(1 for i, (a, b) in enumerate(self._dyn_edges) if self._vis(a) and self._vis(b) and self._evis(i))
 
     def vertices(self):
         for v in range(self._nv):
@@ -180,19 +194,20 @@ class Graph:
             if self._efilt is not None:
                 nbr = nbr[self._efilt[self._adj_eid[lo:hi]]]
             return nbr
-        return np.asarray([x for x in self._dyn_out[v] if self._vis(x)], dtype=np.int64)
+        return np.asarray([x for x, e in zip(self._dyn_out[v], self._dyn_out_e[v]) if self._vis(x) and self._evis(e)], dtype=np.int64)
 
     def get_in_neighbors(self, v):
         v = int(v)
         if self._adj_ptr is not None:
             return self.get_out_neighbors(v)
-        return np.asarray([x for x in self._dyn_in[v] if self._vis(x)], dtype=np.int64)
+        return np.asarray([x for x, e in zip(self._dyn_in[v], self._dyn_in_e[v]) if self._vis(x) and self._evis(e)], dtype=np.int64)
 
     def get_all_neighbors(self, v):
         v = int(v)
         if self._adj_ptr is not None:
             return self.get_out_neighbors(v)
-        return np.asarray([x for x in self._dyn_out[v] + self._dyn_in[v] if self._vis(x)], dtype=np.int64)
+        return np.asarray([x for x, e in zip(self._dyn_out[v] + self._dyn_in[v], self._dyn_out_e[v] + self._dyn_in_e[v])
+                           if self._vis(x) and self._evis(e)], dtype=np.int64)
 
     def edge(self, a, b):
         a, b = int(a), int(b)
@@ -209,7 +224,7 @@ class Graph:
                     yield _Edge(int(self._edges[e, 0]), int(self._edges[e, 1]), e)
         else:
             for i, (a, b) in enumerate(self._dyn_edges):
-                if self._vis(a) and self._vis(b):
+                if self._vis(a) and self._vis(b) and self._evis(i):
                     yield _Edge(a, b, i)
 
     def _visible_edge_array(self):
@@ -219,6 +234,8 @@ class Graph:
         if not self._dyn_edges:
             return np.zeros((0, 2), dtype=np.int64)
         e = np.asarray(self._dyn_edges, dtype=np.int64)
+        if self._efilt is not None:
+            e = e[np.asarray(self._efilt[:e.shape[0]], dtype=bool)]
         if self._vfilt is not None:
             m = self._visible_mask()
             e = e[m[e[:, 0]] & m[e[:, 1]]]

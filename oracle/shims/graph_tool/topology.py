@@ -25,3 +25,13 @@ def label_components(g, directed=False):
         out[vis] = rank[inv].astype(np.int32)
     hist = np.bincount(out[out >= 0]) if (out >= 0).any() else np.zeros(0, dtype=np.int64)
     return _PropertyMap(out, graph=g), hist
+
+
+def all_circuits(g):
+    """Elementary circuits of the visible directed graph as vertex lists (condense-edges.py:111 only sorts them by length
+    and reads their first vertex)."""
+    import networkx as nx
+    G = nx.DiGraph()
+    G.add_nodes_from(g.vertices())
+    G.add_edges_from((e.source(), e.target()) for e in g.edges())
+    return [list(c) for c in nx.simple_cycles(G)]

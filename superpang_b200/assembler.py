@@ -74,6 +74,8 @@ def concat_sequences(seqs):
 
 
 class Assembler:
+    engine_factory = None          # tests inject the kernel-logic emulator here; the product default is Engine(device) = CUDA
+
     def __init__(self, fasta, ksize, threads=1, diskdb=None, debug=False, gap_size=1, *, engine=None, device=0, dist_group=None,
                  distributed=False):
         """Build the de Bruijn graph on the GPU.
@@ -94,7 +96,9 @@ class Assembler:
             raise ValueError("sequences still contain N after splitting")
         self.ref2name = list(self.seqDict)
         self.includedSeqs = sum(1 for s in self.seqDict.values() if len(s) > self.ksize)
-        self._eng = engine if engine is not None else Engine(device=device)
+        if engine is None:
+            engine = type(self).engine_factory() if type(self).engine_factory is not None else Engine(device=device)
+        self._eng = engine
         buf, off = concat_sequences(list(self.seqDict.values()))
         self._seq_off = off
         self._eng.load(buf, off, self.ksize)
@@ -234,6 +238,13 @@ class Assembler:
             comps.append(Component(label=c, n_vertices=int(sizes[c]), NBPs=list(NBP2seq), NBP2seq=NBP2seq,
                                    isCycle=any(r[4] for r in rows), origins={r[0]: set(r[2]) for r in rows}))
         return comps
+
+    def run(self, minlen, mincov, bubble_identity_threshold, genome_assignment_threshold, max_threads, debug=False):
+        """The reference's `Assembler.run` (`lib/Assembler.py:260`): dict[(scaffold, i)] -> Contig.  DBG, NBPs, NBP sequences and
+        the per-sequence NBP sets come from the device; the host tail (`lib/Assembler.py:365-963`) is the installed
+        reference's own code (see `superpang_b200/dropin.py`)."""
+        from . import dropin
+        return dropin.run(self, minlen, mincov, bubble_identity_threshold, genome_assignment_threshold, max_threads, debug)
 
     # ---- canonical result for parity tests ----------------------------------------------------
     def to_result(self):

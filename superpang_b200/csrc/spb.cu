@@ -1716,6 +1716,15 @@ int spb_read_fasta(const char* path, uint32_t gap_size, spb_fasta* out, char* er
   std::string txt;
   { char buf[1 << 16]; size_t n; while ((n = fread(buf, 1, sizeof buf, f)) > 0) txt.append(buf, n); }
   fclose(f);
+  {                                                                           // the reference opens the file in text mode: universal newlines
+    size_t w = 0;
+    for (size_t i = 0; i < txt.size(); ++i) {
+      char ch = txt[i];
+      if (ch == '\r') { ch = '\n'; if (i + 1 < txt.size() && txt[i + 1] == '\n') ++i; }
+      txt[w++] = ch;
+    }
+    txt.resize(w);
+  }
   auto is_ws = [](unsigned char ch) { return ch == ' ' || (ch >= 9 && ch <= 13) || (ch >= 28 && ch <= 31); };   // str.strip() / re \s on ASCII
   size_t b = 0, e = txt.size();
   while (b < e && is_ws((unsigned char)txt[b])) ++b;

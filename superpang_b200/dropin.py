@@ -1,0 +1,101 @@
+"""
+Drop-in seam: `Assembler.run()` for the B200 path (`scripts/SuperPang.py:199` is the only call site of the reference).
+
+The DBG build and the NBP collection (`lib/Assembler.py:80-256`, `:269-363`) come from the CUDA library through the
+C-ABI.  Everything after that -- NBP graph, forward-strand selection, bubble popping, joining, trimming, origin
+assignment (`lib/Assembler.py:365-963`) -- is host control flow that SURVEY 8 leaves on the host: it is NOT
+re-implemented here but taken from the INSTALLED reference package at run time (`import superpang.lib.Assembler`):
+
+  * an instance of the reference class is created without running its `__init__` and given the attributes the tail
+    reads (`ksize`, `seqDict`, `ref2name`, `vertex2coords`, `seqPaths`, `seqLimits`, `seqLimitsPerSeq`, `DBG`);
+  * the reference's own `run()` is used with ONE block replaced -- the NBP collection of each component
+    (`lib/Assembler.py:297-363`, between the markers "### Reconstruct non-branching paths" and
+    "NBPs = list(NBP2seq)") takes NBPs / NBP2seq / isCycle from the device results -- which is the patch
+    INTEGRATION.md asks a maintainer to make in the source; here it is applied in memory;
+  * `get_seqPaths_NBPs` (`lib/Assembler.py:1121-1139`, SURVEY 8f row 1: the quadratic sequence x NBP substring
+    test of the forward-strand selection) is answered from the per-sequence NBP sets computed on the device
+    (`spb_get_seq_nbps`).
+
+`main()` runs the reference's CLI (`scripts/SuperPang.py`) with this class bound at its call site, so `-k`, `-t`,
+`--lowmem` and the output files (`NBPs.fasta`, `NBP2origins.tsv`, `graph.fastg`, `assembly.info.tsv`) are the CLI's own.
+"""
+import inspect
+import sys
+import textwrap
+import types
+
+# state read by `_seq_paths_nbps_from_device` (module level so that the reference's fork pool can pickle the function
+# by name; forked workers inherit the state)
+_ROW1 = {"sets": None, "ref_class": None, "calls": 0}
+
+
+def reference_class():
+    try:
+        from superpang.lib.Assembler import Assembler as Ref
+    except ModuleNotFoundError as e:
+        raise RuntimeError("Assembler.run() needs the SuperPang package importable (its host tail, lib/Assembler.py:365-963, "
+                           "is used as installed); only the DBG build + NBP compaction run on the GPU") from e
+    return Ref
+
+
+def patched_run(Ref):
+    """The reference's `run()` with the per-component NBP-collection block replaced (see the module docstring)."""
+    import superpang.lib.Assembler as mod
+    lines = textwrap.dedent(inspect.getsource(Ref.run)).split("\n")
+    start = next(i for i, l in enumerate(lines) if "### Reconstruct non-branching paths" in l)
+    end = next(i for i, l in enumerate(lines) if l.strip() == "NBPs = list(NBP2seq)")
+    indent = lines[start][:len(lines[start]) - len(lines[start].lstrip())]
+    patch = [indent + "_c = self._b200_components[ic]",
+             indent + "NBPs = list(_c.NBPs); NBP2seq = dict(_c.NBP2seq); isCycle = _c.isCycle"]
+    ns = dict(vars(mod))
+    exec(compile("\n".join(lines[:start] + patch + lines[end + 1:]), "<superpang run() with the B200 NBP collection>", "exec"), ns)
+    return ns["run"]
+
+
+def _seq_paths_nbps_from_device(i):
+    """Replacement of `Assembler.get_seqPaths_NBPs` (`lib/Assembler.py:1121-1139`): same arguments through the
+    reference's multiprocessing globals, same return value (the NBP-graph vertices whose NBP the sequence contains in
+    its own orientation)."""
+    names, seqPaths, psets, NBP2seq, vertex2NBP, seqDict = _ROW1["ref_class"].get_multiprocessing_globals()
+    _ROW1["calls"] += 1
+    mine = _ROW1["sets"].get(names[i], ())
+    return {nv for pair in psets.values() for nv in pair if vertex2NBP[nv] in mine}
+
+
+def run(b200, minlen, mincov, bubble_identity_threshold, genome_assignment_threshold, max_threads, debug=False, device_rows=True):
+    """`Assembler.run(...)` of the reference (`lib/Assembler.py:260`) on top of a `superpang_b200.assembler.Assembler`."""
+    Ref = reference_class()
+    from graph_tool.all import Graph
+    A = object.__new__(Ref)
+    A.run = types.MethodType(patched_run(Ref), A)
+    A.ksize, A.seqDict, A.ref2name, A.includedSeqs = b200.ksize, b200.seqDict, b200.ref2name, b200.includedSeqs
+    A.vertex2coords = b200.vertex2coords
+    A.seqPaths = dict(b200.seqPaths)
+    A.seqLimits = b200.seqLimits
+    A.seqLimitsPerSeq = b200.seqLimitsPerSeq
+    A.DBG = Graph(directed=False)                                  # lib/Assembler.py:251-255
+    A.DBG.add_edge_list(b200.edges)
+    A.DBG.vp.comp = A.DBG.new_vertex_property("int16_t")
+    A.DBG.ep.efilt = A.DBG.new_edge_property("bool")
+    A._b200_components = b200.collect_nbps()
+    if device_rows:
+        _ROW1.update(sets=b200.seq_paths_nbps(), ref_class=Ref)
+        A.get_seqPaths_NBPs = _seq_paths_nbps_from_device
+    try:
+        return A.run(minlen, mincov, bubble_identity_threshold, genome_assignment_threshold, max_threads, debug)
+    finally:
+        _ROW1.update(sets=None)
+
+
+def main(argv=None):
+    """The reference CLI (`scripts/SuperPang.py`) with the B200 Assembler bound at its only call site (`:199`)."""
+    from .assembler import Assembler
+    import superpang.scripts.SuperPang as cli_mod
+    cli_mod.Assembler = Assembler
+    if argv is not None:
+        sys.argv = [cli_mod.__file__] + list(argv)
+    cli_mod.cli()
+
+
+if __name__ == "__main__":
+    main()

@@ -17,6 +17,9 @@ TEXTS = {
     "tabs_cr": ">a\tb c\nAC\tGT\r\nAC\n>d\nGG\n",
     "one_record": ">only\nACGTACGT",
     "nsplit_named": ">a_Nsplit_0\nACGT\n>b\nACNNGT\n",
+    # CRLF / lone-CR files: the reference opens in text mode (universal newlines), so names must not keep a '\r' 
+    "crlf": ">s1\r\nACGTNACGT\r\nAC\r\n>s2 desc\r\nGGNNTT\r\n",
+    "lone_cr": ">s1\rACGT\rAC\r>s2\rGG\r",
 }
 BAD = {
     "illegal": ">a\nACGTX\n",
