@@ -5,17 +5,25 @@ bench.py -- canonical k-mers/s through DBG build + NBP compaction at k=301 (BASE
 A "step" = one pass of the hot path over one synthetic genome set:
     spb_load (2-bit pack, both strands) -> spb_build_dbg -> spb_compact
 `value`  : k-mer instances / s with the ASCII input already resident in HBM (CUDA events on the
-           library's stream, max over ranks).
+           library's stream, max over ranks); mean over the timed steps, median / min alongside.
 `e2e`    : same metric through the host-facing API: pinned HOST ASCII in, H2D inside the timed region,
            and the NBP sequences + origin lists + offsets copied back to pinned host memory.
-`--impl reference` : the oracle port of the reference's CPU path (oracle/dbg_oracle.py) on a bounded
-           sample of the same workload, on this box's host cores.
+`roofline`: ONE kernel -- the longest single kernel of the step (timed live with its own CUDA event pair inside the
+           library) -- with the bytes it must move by design (`achieved`) and the DRAM bytes it really moved
+           (`traffic`, ncu capture of this build committed under profiles/); `pipeline` = SURVEY 8(d) model bytes of the
+           whole step / time / (n_gpus x peak).
+`result_digest`: device-side checksums of every result buffer; at N > 1 rank 0 also runs the single-GPU path on the same
+           input and asserts that the digests are equal (multi-rank parity visible in every SCALE line).
+`--impl reference` : the reference's OWN CPU implementation of the path (unmodified lib/Assembler.py + its Cython helpers,
+           staged under oracle/_ref by build(); graph-tool replaced by the import shim) at os.cpu_count() threads on a
+           bounded sample of the same workload.
 """
 import argparse
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -33,10 +41,26 @@ WORKLOADS = {
 K = 301
 
 
-def algorithmic_bytes(n_inst, n_v, nbp_bases, k=K):
-    """SURVEY.md §8(d): N_inst*(16W+24) + N_v*(8W+32) + B_nbp, W = ceil(2k/64)."""
-    W = (2 * k + 63) // 64
+def algorithmic_bytes(n_inst, n_v, nbp_bases, k=None):
+    """SURVEY.md 8(d): N_inst*(16W+24) + N_v*(8W+32) + B_nbp, W = ceil(2k/64)."""
+    W = (2 * (k or K) + 63) // 64
     return n_inst * (16 * W + 24) + n_v * (8 * W + 32) + nbp_bases
+
+
+# Bytes each single-kernel timer's kernel must move BY DESIGN (DESIGN.md section 3), as a function of the step's counts:
+# what it has to read + write once, not the SURVEY model (which charges a materialised 2k-bit key this design never writes).
+KERNEL_BYTES = {
+    "k_roll_partition_ms": lambda c: 8 * c["n_inst"] + c["n_bases"] // 2,             # 8 B record out per instance, packed strands in
+    "k_partition2_ms": lambda c: 16 * c["n_inst"],                                    # 8 B record in + out
+    "k_smem_dedup_ms": lambda c: 8 * c["n_inst"],                                     # 8 B record in
+    "k_make_records_roll_ms": lambda c: 12 * c["n_inst"] + c["n_bases"] // 2,
+    "k_extract_insert_ms": lambda c: 16 * c["n_inst"] + c["n_bases"] // 2,            # one 8 B slot read + written per instance
+    "k_assign_ids_ms": lambda c: 4 * c["n_bases"] + 5 * c["n_vertices"],
+    "k_edge_write_ms": lambda c: 8 * c["n_edges"] + c["n_vertices"],
+    "k_emit_darts_ms": lambda c: c["nbp_bases"] + 4 * c["nbp_vertices"] + 4 * c["n_vertices"],
+    "k_origin_pairs_ms": lambda c: 4 * c["n_bases"] + 4 * c["n_vertices"],
+    "k_junction_emit_ms": lambda c: 4 * c["n_bases"],
+}
 
 
 class ClockSampler(threading.Thread):
@@ -77,43 +101,89 @@ def make_workload(name, mode):
     return w, names, buf, off, synth.n_instances(seqs, K)
 
 
-def cpu_reference_sample(workload, mode, target_inst=600_000):
-    """Oracle port of the reference CPU path on a bounded sample of the same generator output."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import dbg_oracle
-    from superpang_b200 import synth
-    w = WORKLOADS[workload]
-    n_g = min(w["n_genomes"], 3)
-    length = max(2 * K, target_inst // n_g)
-    names, seqs = synth.genome_set(n_g, length, w["ani"], seed=w["seed"], mode=mode)
-    sd = {n: s.tobytes().decode() for n, s in zip(names, seqs)}
-    t0 = time.perf_counter()
-    res = dbg_oracle.run_oracle(sd, K)
-    dt = time.perf_counter() - t0
-    return dict(value=res["n_inst"] / dt, unit="k-mers/s", cores=1, kind="port",
-                sample=f"{n_g} genomes x {length} bp of the same generator ({mode}), {res['n_inst']} k-mer instances, "
-                       f"{dt:.1f} s; oracle/dbg_oracle.py (Python port of reference lib/Assembler.py; host has {os.cpu_count()} cores)")
+def config_for(args, world):
+    """The `config` object of the JSON line: defined by the command line only, so both arms print the same one."""
+    w = WORKLOADS[args.workload]
+    return dict(workload=f"{w['desc']}, k={K}, mode={args.mode}", k=K, mode=args.mode,
+                parallelism=("1 GPU" if world == 1 else f"k-mers hash-partitioned over {world} GPUs (NCCL all-to-all of records and links), "
+                             "per-position passes, edge rows and NBP emission sharded by position slice"),
+                l2="flushed between timed iterations (256 MiB write)")
+
+
+class CpuReference:
+    """The reference's CPU path on a bounded sample of the workload (same generator, same ANI / mode / seed; fewer and
+    shorter genomes): the UNMODIFIED reference (`kind: "reference"`, oracle/_ref) when build() staged it, else the oracle
+    port (`kind: "port"`, 1 core).  The sample FASTA is generated once; every `run()` is one timed pass."""
+
+    def __init__(self, workload, mode, target_inst):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import refrun
+        from superpang_b200 import synth
+        w = WORKLOADS[workload]
+        self.n_g = min(w["n_genomes"], 4)
+        self.length = max(2 * K, min(w["length"], target_inst // self.n_g))
+        names, seqs = synth.genome_set(self.n_g, self.length, w["ani"], seed=w["seed"], mode=mode)
+        self.n_inst = synth.n_instances(seqs, K)
+        self.mode = mode
+        self.real = refrun.available()
+        self.cores = os.cpu_count() if self.real else 1
+        if self.real:
+            fd, self.fasta = tempfile.mkstemp(suffix=".fa", prefix="spb_ref_sample_")
+            os.close(fd)
+            synth.write_fasta(self.fasta, names, seqs)
+        else:
+            self.sd = {n: s.tobytes().decode() for n, s in zip(names, seqs)}
+
+    def run(self):
+        """One pass; returns (seconds, parts)."""
+        t0 = time.perf_counter()
+        if self.real:
+            import refrun
+            parts = {}
+            res = refrun.run_reference(self.fasta, K, threads=self.cores, debug=False, with_origins=True, extras=False, timing=parts)
+        else:
+            import dbg_oracle
+            parts = {}
+            res = dbg_oracle.run_oracle(self.sd, K)
+        assert res["n_inst"] == self.n_inst
+        return time.perf_counter() - t0, parts
+
+    def describe(self, dt, parts):
+        what = ("unmodified reference lib/Assembler.py (__init__ :80-256, NBP collection :269-363, origin lookup :1212-1262) from oracle/_ref, "
+                "graph-tool replaced by the import shim" if self.real else "oracle/dbg_oracle.py (Python port of the reference path)")
+        return dict(value=self.n_inst / dt, unit="k-mers/s", cores=self.cores, kind="reference" if self.real else "port",
+                    ref_dir="oracle/_ref" if self.real else None,
+                    sample=f"{self.n_g} genomes x {self.length} bp of the same generator ({self.mode}), {self.n_inst} k-mer instances, {dt:.1f} s; {what}",
+                    parts_s={k_: round(v, 3) for k_, v in parts.items()}, n_inst_sample=self.n_inst)
+
+    def close(self):
+        if self.real:
+            try:
+                os.remove(self.fasta)
+            except OSError:
+                pass
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
-    cb = None
+    ref = CpuReference(args.workload, args.mode, args.ref_inst)
+    times, parts = [], {}
     for i in range(args.warmup + args.steps):
-        cb = cpu_reference_sample(args.workload, args.mode, target_inst=args.ref_inst)
+        dt, parts = ref.run()
         if i >= args.warmup:
-            vals.append(cb["value"])
-    v = float(np.mean(vals))
-    w = WORKLOADS[args.workload]
-    cb["value"] = v
-    n_inst_sample = int(cb["sample"].split(" k-mer instances")[0].split(", ")[-1])
+            times.append(dt)
+    ref.close()
+    mean = float(np.mean(times))
+    cb = ref.describe(mean, parts)
+    v = cb["value"]
     print(json.dumps(dict(
         impl="reference", metric=f"canonical k-mers/s through DBG build+NBP compaction at k={K}", value=v, unit="k-mers/s",
-        n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * n_inst_sample / v, higher_is_better=True,
+        n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * mean, ms_per_step_median=1e3 * float(np.median(times)),
+        ms_per_step_min=1e3 * float(np.min(times)), higher_is_better=True,
         scaling="strong", vs_baseline=None, dtype="u64", data="synthetic",
-        config=dict(workload=f"{w['desc']}, k={K}, mode={args.mode}", k=K, mode=args.mode),
+        config=config_for(args, int(os.environ.get("WORLD_SIZE", "1"))),
         cpu_baseline=cb, e2e=dict(value=v, unit="k-mers/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
 
 
@@ -125,8 +195,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="snp", choices=["snp", "block"])
-    ap.add_argument("--ref-inst", type=int, default=600_000)
+    ap.add_argument("--ref-inst", type=int, default=1_000_000, help="k-mer instances of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-digest", action="store_true")
     ap.add_argument("--k", type=int, default=301, help="k-mer size (BASELINE config 5 sweeps 101 / 301 / 501)")
     args = ap.parse_args()
     global K
@@ -136,7 +207,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from superpang_b200 import _capi
+    from superpang_b200 import _capi, digest
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -217,19 +288,34 @@ def main():
     sampler.start()
     times, stages, counts = timed(step_resident, args.steps, args.warmup)
     launches = timed.launches
-    e2e_times, _, e2e_last = timed(step_e2e, args.steps, max(1, args.warmup - 1))
+    e2e_times, _, e2e_last = timed(step_e2e, args.steps, max(3, args.warmup))
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    ms = float(np.sum(times))
-    ms_e2e = float(np.sum(e2e_times))
+    # per-step times: max over ranks of every step, then mean / median / min over the steps
+    tt = torch.tensor([times, e2e_times], device=dev, dtype=torch.float64)
     if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    times, e2e_times = tt[0].tolist(), tt[1].tolist()
+    ms, ms_e2e = float(np.sum(times)), float(np.sum(e2e_times))
     total_inst = n_inst                              # strong scaling: the same genome set, k-mers hash-partitioned over the ranks
     value = total_inst * args.steps / (ms / 1e3)
     e2e_value = total_inst * args.steps / (ms_e2e / 1e3)
+
+    # ---- result digest (outside the timed region): device-side checksums of every result buffer of the last step
+    dg, dg_single = None, None
+    if not args.no_digest:
+        if rank == 0:
+            dg = digest.result_digest(eng, graph=True)
+        if world > 1:
+            dist.barrier()
+            if rank == 0:                            # the same input through the single-GPU path on this rank
+                eng.load(dbuf, off, K)
+                eng.build_dbg()
+                eng.compact()
+                dg_single = digest.result_digest(eng, graph=True)
+                assert dg_single == dg, f"multi-GPU result differs from the single-GPU result: {dg} != {dg_single}"
+            dist.barrier()
 
     if rank == 0:
         peaks = {}
@@ -239,63 +325,59 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-        # per-stage share of the SURVEY 8(d) byte model (184 B / instance + 112 B / vertex + 1 B / NBP base at k=301)
-        W = (2 * K + 63) // 64
         st_keys = sorted(stages[0])
-        st_mean = {k_: float(np.mean([s[k_] for s in stages])) for k_ in st_keys}
+        st_mean = {k_: float(np.mean([s.get(k_, 0.0) for s in stages])) for k_ in st_keys}
         ni, nv, nbb = counts["n_inst"], counts["n_vertices"], counts["nbp_bases"]
-        groups = {
-            "k_extract_insert (canonical k-mer extraction + exact dedup insert)": (("k_extract_insert_ms",), 16 * W * ni + 8 * W * nv),
-            ("partitioned-smem dedup (k_make_records + 16-bit radix sort + k_smem_dedup: one CTA and one shared-memory table per sub-bucket)"
-             if "smem_tables" in st_mean else
-             "partitioned dedup (k_make_records + radix partition + k_bkt_insert_links, 256 launches)"):
-                (("records_partition_ms", "bucket_dedup_ms"), 16 * W * ni + 8 * W * nv),
-            "multi-GPU dedup (records, all-to-all, owner dedup, scatter)":
-                (("mg_records_partition_ms", "mg_exchange_records_ms", "mg_owner_dedup_ms", "mg_exchange_reps_ms", "mg_scatter_ms"),
-                 16 * W * ni + 8 * W * nv),
-            "ids (k_assign_ids)": (("scatter_ids_ms", "mg_bitmaps_ids_ms", "mg_allgather_ids_ms"), 4 * ni + 8 * nv),
-            "edges (k_junction_emit + k_edge_*)": (("edges_ms",), 20 * ni + 8 * nv),
-            "compaction (k_classify8 .. k_rank_jump)": (("classify_rank_ms",), 16 * nv),
-            "emit (k_emit_darts + k_emit_ends)": (("emit_ms",), nbb),
-        }
-        gtime = {g: sum(st_mean.get(k_, 0.0) for k_ in ks) for g, (ks, _) in groups.items()}
-        dom = max(gtime, key=gtime.get)
-        dom_bytes, dom_ms = groups[dom][1], gtime[dom]
-        ach = dom_bytes / (dom_ms / 1e3) / 1e9
-        # measured DRAM traffic of the dominant kernel (ncu --set full, per launch), if a capture of this workload is committed
-        traffic = None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = tr.get(f"{args.workload}:{args.mode}:{world}:{K}", {}).get(dom.split(" ")[0])
-        except Exception:
-            pass
+        # the dominant SINGLE kernel: the longest of the kernels that carry their own event pair inside the library
+        kt = {k_: v for k_, v in st_mean.items() if k_ in KERNEL_BYTES and v > 0}
+        roof = None
+        if kt:
+            dom = max(kt, key=kt.get)
+            dom_ms = kt[dom]
+            dom_bytes = KERNEL_BYTES[dom](counts) / max(world, 1) if dom in ("k_roll_partition_ms", "k_partition2_ms", "k_smem_dedup_ms") else KERNEL_BYTES[dom](counts)
+            ach = dom_bytes / (dom_ms / 1e3) / 1e9
+            traffic = None
+            try:                                     # measured DRAM bytes of that kernel per launch (ncu --set full of this build)
+                tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+                traffic = tr.get(f"{args.workload}:{args.mode}:{world}:{K}", {}).get(dom[:-3])
+            except Exception:
+                pass
+            roof = dict(bound="hbm", kernel=dom[:-3], achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=traffic,
+                        traffic_frac=(traffic / (dom_ms / 1e3) / 1e9 / peak) if traffic else None,
+                        kernel_ms=dom_ms, algorithmic_bytes=dom_bytes, peak_source=peak_src,
+                        note="achieved = bytes this kernel must move by design (DESIGN.md section 3) / its live CUDA-event duration; "
+                             "traffic = dram__bytes_read+write of the same kernel from the committed ncu capture (profiles/)",
+                        kernels_ms={k_[:-3]: v for k_, v in sorted(kt.items(), key=lambda x: -x[1])})
         pipe_bytes = algorithmic_bytes(ni, nv, nbb)
         pipe_ach = pipe_bytes / (ms / args.steps / 1e3) / 1e9
+        if roof is not None:
+            # achieved = Bytes / time / (n_gpu x peak)
+            roof["pipeline"] = dict(model_bytes=pipe_bytes, achieved_per_gpu=pipe_ach / world, frac=pipe_ach / world / peak,
+                                    note="SURVEY 8(d) byte model of the whole step / step time / (n_gpus x peak); the model charges a materialised "
+                                         "2k-bit key per instance that this design never writes")
         line = dict(
             metric=f"canonical k-mers/s through DBG build+NBP compaction at k={K}", value=value, unit="k-mers/s",
-            n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True,
+            n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, ms_per_step_median=float(np.median(times)),
+            ms_per_step_min=float(np.min(times)), higher_is_better=True,
             scaling="strong", vs_baseline=None, dtype="u64", data="synthetic",
-            config=dict(workload=f"{w['desc']}, k={K}, mode={args.mode}", k=K, mode=args.mode, n_inst=n_inst,
-                        parallelism=(f"k-mers hash-partitioned over {world} GPUs (NCCL all-to-all), compaction replicated" if world > 1 else "1 GPU"),
-                        n_vertices=counts["n_vertices"], n_nbp=counts["n_nbp"], nbp_bases=counts["nbp_bases"],
-                        l2="flushed between timed iterations (256 MiB write)"),
-            e2e=dict(value=e2e_value, unit="k-mers/s", ms_per_step=ms_e2e / args.steps, h2d_bytes_per_step=int(buf.nbytes + off.nbytes),
-                     d2h_bytes_per_step=int(e2e_last[1])),
+            config=config_for(args, world),
+            counts=dict(n_inst=n_inst, n_vertices=counts["n_vertices"], n_edges=counts["n_edges"], n_nbp=counts["n_nbp"], nbp_bases=counts["nbp_bases"],
+                        n_origin_pairs=counts["n_origin_pairs"], mg_protocol=getattr(eng, "mg_protocol", None)),
+            e2e=dict(value=e2e_value, unit="k-mers/s", ms_per_step=ms_e2e / args.steps, ms_per_step_median=float(np.median(e2e_times)),
+                     h2d_bytes_per_step=int(buf.nbytes + off.nbytes), d2h_bytes_per_step=int(e2e_last[1])),
             gpu_launches=int(launches),
-            roofline=dict(bound="hbm", kernel=dom, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=traffic,
-                          # DRAM bytes actually moved (ncu) / live duration / peak: what the hardware sees.  `frac` uses the
-                          # SURVEY 8(d) model, which charges every instance for a materialised 2k-bit key; the rolling-hash /
-                          # verify-in-place design moves less than that, so `frac` can exceed 1 while `traffic_frac` cannot.
-                          traffic_frac=(traffic / (dom_ms / 1e3) / 1e9 / peak) if traffic else None,
-                          note=("frac uses the SURVEY 8(d) byte model (a materialised 2k-bit key per instance); the design moves "
-                                "fewer bytes than that (see traffic / traffic_frac), so frac may exceed 1"),
-                          peak_source=peak_src, kernel_ms=dom_ms, model_bytes=dom_bytes,
-                          pipeline=dict(achieved=pipe_ach, frac=pipe_ach / peak, bytes=pipe_bytes)),
+            roofline=roof,
             stages_ms=st_mean,
+            result_digest=digest.fold(dg) if dg else None,
+            result_checksums=dg,
+            digest_equals_single_gpu=(dg_single == dg) if dg_single is not None else None,
             clocks=sampler.summary(),
         )
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_reference_sample(args.workload, args.mode, target_inst=args.ref_inst)
+            ref = CpuReference(args.workload, args.mode, args.ref_inst)
+            dt, parts = ref.run()
+            line["cpu_baseline"] = ref.describe(dt, parts)
+            ref.close()
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -56,16 +56,25 @@ def import_reference():
     return Assembler
 
 
-def run_reference(fasta, ksize=301, threads=1, debug=True, with_origins=True, quiet=True):
-    """Run the reference DBG build + NBP collection on `fasta`; return the canonical result dict."""
+def run_reference(fasta, ksize=301, threads=1, debug=True, with_origins=True, quiet=True, extras=True, timing=None):
+    """Run the reference DBG build + NBP collection on `fasta`; return the canonical result dict.
+    timing (dict, optional) receives the wall seconds of the three parts SURVEY 8(d) names: `init_s` = Assembler.__init__
+    (`lib/Assembler.py:80-256`), `nbp_s` = the NBP-collection head of run() (`:269-363`), `origins_s` = the origin lookup
+    (`:1212-1262`).  extras=False skips the 8(f) golden material (orientation counts, joined paths)."""
     Assembler = import_reference()
     import graph_tool as gt
     import io
     import contextlib
+    import time as _time
 
+    T = timing if timing is not None else {}
+    T.update(init_s=0.0, nbp_s=0.0, origins_s=0.0)
     sink = io.StringIO() if quiet else sys.stdout
     with contextlib.redirect_stdout(sink):
+        _t0 = _time.perf_counter()
         A = Assembler(fasta, ksize, threads, None, debug, 1)
+        T["init_s"] = _time.perf_counter() - _t0
+        _t0 = _time.perf_counter()
         # ---- head of Assembler.run, reference lib/Assembler.py:269-363 (driver restatement) ----
         A.DBG.vp.comp = gt.topology.label_components(A.DBG, directed=False)[0]            # :271
         comps, sizes = np.unique(A.DBG.vp.comp.get_array(), return_counts=True)              # :272
@@ -115,12 +124,16 @@ def run_reference(fasta, ksize=301, threads=1, debug=True, with_origins=True, qu
             NBPs = [NBP for NBP in NBPs if NBP[0] != NBP[1] and NBP[-1] != NBP[-2]]          # :354
             seqs = A.multimap(A.reconstruct_sequence, threads, NBPs, A.vertex2coords, A.ref2name,
                               A.seqDict, A.ksize)                                            # :357
+            T["nbp_s"] += _time.perf_counter() - _t0
+            _t0 = _time.perf_counter()
             if with_origins:
                 from collections import defaultdict
                 o2c = A.multimap(A.get_ori2cov_onevertex, threads, NBPs, seqPathsThisComp,
                                  defaultdict(list), A.seqLimitsPerSeq, debug, chunksize=10)  # :922
             else:
                 o2c = [None] * len(NBPs)
+            T["origins_s"] += _time.perf_counter() - _t0
+            _t0 = _time.perf_counter()
             if badEdges:
                 A.DBG.clear_filters()
             for NBP, seq, ori2cov in zip(NBPs, seqs, o2c):
@@ -140,7 +153,7 @@ def run_reference(fasta, ksize=301, threads=1, debug=True, with_origins=True, qu
         groups = _dd(list)
         for i, n in enumerate(nbps_out):
             groups[frozenset(n[0])].append(i)
-        psets = {fs: tuple(nvs) for fs, nvs in groups.items() if len(nvs) == 2 and len(NBP2seq) == len(nbps_out)}
+        psets = {fs: tuple(nvs) for fs, nvs in groups.items() if extras and len(nvs) == 2 and len(NBP2seq) == len(nbps_out)}
         orient = [-1] * len(nbps_out)
         orient_sets = {}
         if psets:
@@ -160,7 +173,7 @@ def run_reference(fasta, ksize=301, threads=1, debug=True, with_origins=True, qu
         by_start = _dd(list)
         for n in nbps_out:
             by_start[n[1][:ksize]].append(n)
-        for n1 in nbps_out:
+        for n1 in (nbps_out if extras else ()):
             for n2 in by_start[n1[1][-ksize:]]:
                 if len(joined) < 40 and n1[0][-1] == n2[0][0] and len(set(n1[0]) & set(n2[0])) == 1:
                     joined.append(tuple(n1[0]) + tuple(n2[0][1:]))

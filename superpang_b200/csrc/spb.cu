@@ -54,7 +54,14 @@ struct spb_ctx {
   u64 *dd_keys = 0, *dd_bstart = 0; u32* dd_pos = 0; u64 dd_n = 0, dd_lo = 0, dd_hi = 0; u32 dd_bb = 0; bool dd_fbits_ready = false;
   std::vector<u64> dd_bstart_h;
   u64* mg_links = 0; u32 *mg_seen = 0, *mg_dup = 0;                 // multi-GPU links protocol
-  std::string stats;
+  // per-stage statistics: scalar values and (CUDA) event pairs resolved lazily by spb_get_stage_stats, so that timing a
+  // stage never synchronises the host with the stream
+  struct StatRec { std::string name; double val; int ev; };
+  std::vector<StatRec> stat;
+  size_t ev_used = 0;
+#ifndef SPB_EMU
+  std::vector<cudaEvent_t> evpool;
+#endif
 };
 
 static int fail(spb_ctx* c, int code, const char* fmt, ...) {
@@ -69,7 +76,8 @@ static void backend_free(void* p) { free(p); }
 static void dev_memset(spb_ctx*, void* p, int v, u64 bytes) { memset(p, v, bytes); }
 static void dev_copy(spb_ctx*, void* dst, const void* src, u64 bytes) { memcpy(dst, src, bytes); }
 static void dev_sync(spb_ctx*) {}
-struct StageTimer { void start(spb_ctx*) {} float stop(spb_ctx*) { return 0.f; } };
+static int t_begin(spb_ctx*) { return 0; }
+static void t_end(spb_ctx* c, int, const char* name) { c->stat.push_back({name, 0.0, -1}); }
 #else
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(c, SPB_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); } while (0)
 static void* backend_alloc(u64 bytes) {
@@ -81,13 +89,16 @@ static void backend_free(void* p) { cudaFree(p); }
 static void dev_memset(spb_ctx* c, void* p, int v, u64 bytes) { cudaMemsetAsync(p, v, bytes, c->stream); }
 static void dev_copy(spb_ctx* c, void* dst, const void* src, u64 bytes) { cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, c->stream); }
 static void dev_sync(spb_ctx* c) { cudaStreamSynchronize(c->stream); }
-struct StageTimer {
-  cudaEvent_t a = 0, b = 0;
-  void start(spb_ctx* c) { if (!a) { cudaEventCreate(&a); cudaEventCreate(&b); } cudaEventRecord(a, c->stream); }
-  float stop(spb_ctx* c) { cudaEventRecord(b, c->stream); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
-  ~StageTimer() { if (a) { cudaEventDestroy(a); cudaEventDestroy(b); } }
-};
+static int t_begin(spb_ctx* c) {                      // start of a timed stage: returns the index of its event pair
+  if (c->ev_used + 2 > c->evpool.size()) { cudaEvent_t e; for (int i = 0; i < 2; ++i) { cudaEventCreate(&e); c->evpool.push_back(e); } }
+  const int t = (int)c->ev_used; c->ev_used += 2;
+  cudaEventRecord(c->evpool[t], c->stream);
+  return t;
+}
+static void t_end(spb_ctx* c, int t, const char* name) { cudaEventRecord(c->evpool[t + 1], c->stream); c->stat.push_back({name, 0.0, t}); }
 #endif
+static void stat_set(spb_ctx* c, const char* name, double v) { c->stat.push_back({name, v, -1}); }
+static void stats_reset(spb_ctx* c) { c->stat.clear(); c->ev_used = 0; }
 
 // Caching block allocator.  Every buffer of the pipeline is used on the context's single stream, so a
 // freed block can be handed out again immediately (stream order == program order).  After the first
@@ -381,6 +392,7 @@ static void reset_state(spb_ctx* c) {
 #ifndef SPB_EMU
   for (int i = 0; i < 3; ++i) { fresh.stream2[i] = c->stream2[i]; fresh.ev_join[i] = c->ev_join[i]; }
   fresh.ev_fork = c->ev_fork;
+  fresh.evpool.swap(c->evpool);
 #endif
   fresh.live.swap(c->live); fresh.cache.swap(c->cache);
   memset(&fresh.cnt, 0, sizeof fresh.cnt); memset(&fresh.nt, 0, sizeof fresh.nt);
@@ -400,6 +412,7 @@ void spb_destroy(spb_ctx* c) {
   free(c->pinned);
 #else
   cudaFreeHost(c->pinned);
+  for (auto e : c->evpool) cudaEventDestroy(e);
   if (c->stream2[0]) { for (int i = 0; i < 3; ++i) { cudaStreamDestroy(c->stream2[i]); cudaEventDestroy(c->ev_join[i]); } cudaEventDestroy(c->ev_fork); }
 #endif
   delete c;
@@ -495,8 +508,8 @@ static int dd_records(spb_ctx* c, u64 pos_lo, u64 pos_hi, u32 bb, u64 min_positi
   u64 grid = n / TPB;
   if (!getenv("SPB_NO_ROLL")) {
     const RollK K = roll_constants(c->k);
-    SPB_LAUNCH(k_make_records_roll, nblk(n / SPB_RUN, 128), 128, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, n, keys, pos, c->obits,
-               spread, K, 0u, 0u, (u64*)nullptr, 0ull);
+    { const int tq_ = t_begin(c); SPB_LAUNCH(k_make_records_roll, nblk(n / SPB_RUN, 128), 128, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, n, keys, pos, c->obits,
+               spread, K, 0u, 0u, (u64*)nullptr, 0ull); t_end(c, tq_, "k_make_records_roll_ms"); }
   } else
   switch ((2 * c->k + 31) / 32) {
     case 7:  SPB_LAUNCH(k_make_records<7>, grid, TPB, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, keys, pos, c->obits, spread); break;
@@ -582,12 +595,14 @@ static int dd_ids(spb_ctx* c, u64 lo, u64 hi, const u64* slots, u64 cap = 1, con
   c->nV = (u32)nV;
   ALLOC(c->v2pos, u32, nV + 1); ALLOC(c->vflags, u8, nV + 64);
   dev_memset(c, c->vflags + (nV & ~7ull), 0, 64);
+  const int tq_ids = t_begin(c);
   switch ((2 * c->k + 31) / 32) {
     case 7:  SPB_LAUNCH(k_assign_ids<7>, gs_grid(T), TPB, c->stream, sp_in, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags, follow, c->errflag); break;
     case 19: SPB_LAUNCH(k_assign_ids<19>, gs_grid(T), TPB, c->stream, sp_in, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags, follow, c->errflag); break;
     case 32: SPB_LAUNCH(k_assign_ids<32>, gs_grid(T), TPB, c->stream, sp_in, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags, follow, c->errflag); break;
     default: SPB_LAUNCH(k_assign_ids<0>, gs_grid(T), TPB, c->stream, sp_in, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags, follow, c->errflag); break;
   }
+  t_end(c, tq_ids, "k_assign_ids_ms");
   dfree(c, blkcnt); dfree(c, blkoff); dfree(c, wpre);
   return 0;
 }
@@ -607,7 +622,7 @@ static int dd_graph(spb_ctx* c) {
   for (int attempt = 0; attempt < 2; ++attempt) {
     ALLOC(Jk, u64, jcap); ALLOC(Js, u8, jcap);
     dev_memset(c, jcount, 0, 16);
-    SPB_LAUNCH(k_junction_emit, std::min<u64>(nblk(T, TPB), 148 * 16), TPB, c->stream, c->sp, T, c->fbits, c->vflags, c->v2pos, c->obits, vobits, Jk, Js, jcount, jcap, c->errflag);
+    { const int tq_ = t_begin(c); SPB_LAUNCH(k_junction_emit, std::min<u64>(nblk(T, TPB), 148 * 16), TPB, c->stream, c->sp, T, c->fbits, c->vflags, c->v2pos, c->obits, vobits, Jk, Js, jcount, jcap, c->errflag); t_end(c, tq_, "k_junction_emit_ms"); }
     nj = dread(c, jcount);
     if (nj <= jcap) break;
     dfree(c, Jk); dfree(c, Js); jcap = nj;
@@ -630,7 +645,7 @@ static int dd_graph(spb_ctx* c) {
   u64 nE = 0;
   PRIM(prim_scan_u32(c, ecnt, eoff, nT, &nE));
   ALLOC(c->edges, u32, 2 * nE + 2);
-  SPB_LAUNCH(k_edge_write, std::min<u64>(nblk(nV, TPB), 148 * 32), TPB, c->stream, g, eoff, c->edges);
+  { const int tq_ = t_begin(c); SPB_LAUNCH(k_edge_write, std::min<u64>(nblk(nV, TPB), 148 * 32), TPB, c->stream, g, eoff, c->edges); t_end(c, tq_, "k_edge_write_ms"); }
   dfree(c, ecnt); dfree(c, eoff);
   c->cnt.n_vertices = nV; c->cnt.n_edges = nE; c->cnt.n_junction = c->nJ;
   return 0;
@@ -642,8 +657,7 @@ static int dedup_staged_links(spb_ctx* c) {
   const u64 T = c->T, P = c->npos_pad;
   u32 bb = 0; while (bb < 8 && (c->n_inst >> bb) > 2200000ull) ++bb;       // <= 256 buckets: one radix pass
   if (const char* e = getenv("SPB_BUCKET_BITS")) bb = (u32)atoi(e);
-  StageTimer tk; char b2[128];
-  tk.start(c);
+  int tk = t_begin(c);
   const u32 B = 1u << bb;
   std::vector<u64> blo(B), bn(B);
   // SPB_PARTITION_FUSED=1 selects the hand-written single-pass partition (k_partition_records).  Measured slower than
@@ -683,8 +697,8 @@ static int dedup_staged_links(spb_ctx* c) {
     for (u32 b = 0; b < B; ++b) { blo[b] = c->dd_bstart_h[b]; bn[b] = c->dd_bstart_h[b + 1] - blo[b]; }
     dfree(c, c->dd_bstart);
   }
-  snprintf(b2, sizeof b2, "\"records_partition_ms\": %.4f, ", tk.stop(c)); c->stats += b2;
-  tk.start(c);
+  t_end(c, tk, "records_partition_ms");
+  tk = t_begin(c);
   u64 nmax = 0;
   for (u32 b = 0; b < B; ++b) nmax = std::max(nmax, bn[b]);
   u64 cap = 1024; while (cap < 2 * nmax) cap <<= 1;
@@ -709,7 +723,7 @@ static int dedup_staged_links(spb_ctx* c) {
   }
   for (auto& x : scratch) dfree(c, x);
   dfree(c, c->dd_keys); dfree(c, c->dd_pos);
-  snprintf(b2, sizeof b2, "\"bucket_dedup_ms\": %.4f, ", tk.stop(c)); c->stats += b2;
+  t_end(c, tk, "bucket_dedup_ms");
   u64 nb = P / 256, nw32 = P / 32;
   SPB_LAUNCH(k_first_bits, nblk(nb, TPB), TPB, c->stream, c->vbits, dupbits, c->fbits, nb);     // first = valid and not linked
   dev_memset(c, c->fbits + nw32, 0, 32);
@@ -728,23 +742,22 @@ static int dedup_smem_links(spb_ctx* c) {
   if (const char* e = getenv("SPB_SMEM_AVG")) avg = std::max(1, atoi(e));       // tests: many tiny sub-buckets
   u32 nbits = 0; while ((P >> nbits) > avg) ++nbits;
   if (nbits > 24) return 1;
-  StageTimer tk; char b2[160];
-  tk.start(c);
+  int tk = t_begin(c);
   PRIM(dd_records(c, 0, T, nbits, 0, 1));
-  snprintf(b2, sizeof b2, "\"records_partition_ms\": %.4f, ", tk.stop(c)); c->stats += b2;
-  tk.start(c);
+  t_end(c, tk, "records_partition_ms");
+  tk = t_begin(c);
   const u64 NB = 1ull << nbits;
   u32 *seenpos, *dupbits; ALLOC(seenpos, u32, P + 8); ALLOC(dupbits, u32, P / 32 + 8);
   dev_memset(c, dupbits, 0, (P / 32 + 8) * 4);
   u64 nmax = 0;
   for (u64 b = 0; b < NB; ++b) nmax = std::max(nmax, c->dd_bstart_h[b + 1] - c->dd_bstart_h[b]);
   if (nmax <= smem_limit())
-    SPB_LAUNCH_PHASED_DSMEM(k_smem_dedup<false>, 2, NB, 512, SPB_ST_SLOTS * 4, c->stream, c->dd_keys, c->dd_pos, c->dd_bstart, c->F, c->R, T, c->k, nbits,
-                            seenpos, dupbits, c->errflag, (u64*)nullptr, (u64*)nullptr, 0ull);
+    { const int tq_ = t_begin(c); SPB_LAUNCH_PHASED_DSMEM(k_smem_dedup<false>, 2, NB, 512, SPB_ST_SLOTS * 4, c->stream, c->dd_keys, c->dd_pos, c->dd_bstart, c->F, c->R, T, c->k, nbits,
+                            seenpos, dupbits, c->errflag, (u64*)nullptr, (u64*)nullptr, 0ull); t_end(c, tq_, "k_smem_dedup_ms"); }
   dfree(c, c->dd_keys); dfree(c, c->dd_pos); dfree(c, c->dd_bstart);
   if (nmax > smem_limit()) { dfree(c, seenpos); dfree(c, dupbits); return 1; }
   c->cnt.table_slots = SPB_ST_SLOTS;
-  snprintf(b2, sizeof b2, "\"bucket_dedup_ms\": %.4f, \"smem_tables\": %llu, ", tk.stop(c), NB); c->stats += b2;
+  t_end(c, tk, "bucket_dedup_ms"); stat_set(c, "smem_tables", (double)NB);
   u64 nb = P / 256, nw32 = P / 32;
   SPB_LAUNCH(k_first_bits, nblk(nb, TPB), TPB, c->stream, c->vbits, dupbits, c->fbits, nb);     // first = valid and not linked
   dev_memset(c, c->fbits + nw32, 0, 32);
@@ -813,7 +826,7 @@ static int dedup_global_table(spb_ctx* c, bool allow_switch) {
   u64 nA = P / 32;
   u32* seenpos; u64 *arec, *extc; ALLOC(seenpos, u32, P + 8); ALLOC(arec, u64, nA + 8); ALLOC(extc, u64, 2);
   dev_memset(c, extc, 0, 16);
-  StageTimer tk; tk.start(c);
+  int tk = t_begin(c);
   int anchored = decided;
   if (const char* e = getenv("SPB_ANCHOR")) anchored = atoi(e) ? 2 : -1;      // 1 = force on, 0 = force off (A/B measurements, tests)
   u64 done = std::min(P, CH);
@@ -833,7 +846,7 @@ static int dedup_global_table(spb_ctx* c, bool allow_switch) {
   }
   if (anchored > 0) for (; done < P; done += CH) launch_extract_k(c, done, std::min(P, done + CH), slots, cap, seenpos, wbits, dbits, arec, nullptr);
   else launch_extract_k(c, done, P, slots, cap, seenpos, wbits, dbits, nullptr, nullptr);
-  { char b2[128]; snprintf(b2, sizeof b2, "\"k_extract_insert_ms\": %.4f, \"anchored\": %d, ", tk.stop(c), anchored > 0 ? 1 : 0); c->stats += b2; }
+  t_end(c, tk, "k_extract_insert_ms"); stat_set(c, "anchored", anchored > 0 ? 1 : 0);
   dfree(c, arec); dfree(c, extc);
   u64 nb = c->npos_pad / 256;
   SPB_LAUNCH(k_first_bits, nblk(nb, TPB), TPB, c->stream, wbits, dbits, c->fbits, nb);
@@ -851,50 +864,51 @@ int spb_build_dbg(spb_ctx* c, spb_counts* out) {
 #ifndef SPB_EMU
   CK(cudaSetDevice(c->device));
 #endif
-  StageTimer tm; char buf[256]; c->stats = "{";
+  stats_reset(c);
+  int tm;
   // Default: single global table (two random HBM accesses per instance).  SPB_DEDUP=staged selects the partitioned
   // path (records -> buckets -> L2 scratch tables -> scatter back); measured slower on one GPU in round 1
   // (profiles/README.md), its stages are what the multi-GPU exchange is built from.
   const char* mode = getenv("SPB_DEDUP");          // global | links | staged  (default: adaptive global -> links)
   if (mode && (!strcmp(mode, "links") || !strcmp(mode, "smem"))) {
-    tm.start(c);
+    tm = t_begin(c);
     int rc = strcmp(mode, "smem") ? 1 : dedup_smem_links(c);
-    if (rc == 1) { c->stats = "{"; rc = dedup_staged_links(c); }
+    if (rc == 1) { stats_reset(c); tm = t_begin(c); rc = dedup_staged_links(c); }
     if (rc) return rc;
-    snprintf(buf, sizeof buf, "\"dedup_links_ms\": %.4f", tm.stop(c)); c->stats += buf;
+    t_end(c, tm, "dedup_links_ms");
   } else if (!(mode && !strcmp(mode, "staged"))) {
-    tm.start(c);
+    tm = t_begin(c);
     int rc = dedup_global_table(c, !mode);            // also reports k_extract_insert_ms (the kernel alone)
     if (rc == 1) {
-      c->stats = "{\"switched_to_links\": 1, ";
+      stat_set(c, "switched_to_links", 1);
       rc = getenv("SPB_NO_SMEM_TABLES") ? 1 : dedup_smem_links(c);
-      if (rc == 1) { c->stats = "{\"switched_to_links\": 1, "; rc = dedup_staged_links(c); }
+      if (rc == 1) { c->stat.erase(std::remove_if(c->stat.begin(), c->stat.end(), [](const spb_ctx::StatRec& r) { return r.name == "records_partition_ms" || r.name == "bucket_dedup_ms" || r.name == "smem_tables"; }), c->stat.end()); rc = dedup_staged_links(c); }
     }
     if (rc) return rc;
-    snprintf(buf, sizeof buf, "\"dedup_global_ms\": %.4f", tm.stop(c)); c->stats += buf;
+    t_end(c, tm, "dedup_global_ms");
   } else {
     // ---- S1: records + partition
-    tm.start(c);
+    tm = t_begin(c);
     u32 bb = default_bucket_bits(c->n_inst, 1);
     if (const char* e = getenv("SPB_BUCKET_BITS")) bb = (u32)atoi(e);
     PRIM(dd_records(c, 0, c->T, bb));
-    snprintf(buf, sizeof buf, "\"records_partition_ms\": %.4f", tm.stop(c)); c->stats += buf;
+    t_end(c, tm, "records_partition_ms");
     // ---- S2: L2-staged dedup per bucket
-    tm.start(c);
+    tm = t_begin(c);
     u32* rep; ALLOC(rep, u32, c->dd_n + 1);
     u64 cc = c->dd_n;
     PRIM(dd_owner(c, c->dd_keys, c->dd_pos, &cc, 1, bb, 0, 1u << bb, rep));
-    snprintf(buf, sizeof buf, ", \"bucket_dedup_ms\": %.4f", tm.stop(c)); c->stats += buf;
+    t_end(c, tm, "bucket_dedup_ms");
     // ---- S3 + ids
-    tm.start(c);
+    tm = t_begin(c);
     PRIM(dd_scatter(c, rep));
     dfree(c, rep);
     PRIM(dd_ids(c, 0, c->T, nullptr));
-    snprintf(buf, sizeof buf, ", \"scatter_ids_ms\": %.4f", tm.stop(c)); c->stats += buf;
+    t_end(c, tm, "scatter_ids_ms");
   }
-  tm.start(c);
+  tm = t_begin(c);
   PRIM(dd_graph(c));
-  snprintf(buf, sizeof buf, ", \"edges_ms\": %.4f", tm.stop(c)); c->stats += buf;
+  t_end(c, tm, "edges_ms");
   int r = check_err(c, "spb_build_dbg");
   if (r) return r;
   c->state = 2;
@@ -1182,11 +1196,10 @@ int spb_mg_ids(spb_ctx* c, uint64_t pos_lo, uint64_t pos_hi) {
 int spb_mg_graph(spb_ctx* c, spb_counts* out) {
   if (!c) return SPB_EINVAL;
   if (c->state != 1 || !c->v2pos) return fail(c, SPB_ESTATE, "spb_mg_graph out of order");
-  c->stats = "{\"multi_gpu\": 1";
-  StageTimer tm; char buf[128];
-  tm.start(c);
+  stats_reset(c); stat_set(c, "multi_gpu", 1);
+  int tm = t_begin(c);
   PRIM(dd_graph(c));
-  snprintf(buf, sizeof buf, ", \"edges_ms\": %.4f", tm.stop(c)); c->stats += buf;
+  t_end(c, tm, "edges_ms");
   int r = check_err(c, "spb_mg_graph");
   if (r) return r;
   c->state = 2;
@@ -1201,14 +1214,14 @@ int spb_compact(spb_ctx* c, spb_counts* out) {
   CK(cudaSetDevice(c->device));
 #endif
   const u64 T = c->T; const u32 k = c->k; const u32 nV = c->nV;
-  StageTimer tm; char buf[256];
+  int tm;
   GView g{c->vflags, c->Jk, c->Js, c->nJ, nV};
   u32 *pl_nbr = 0, *pr_nbr = 0, *nxt = 0, *ptr[2] = {0, 0}, *acc[2] = {0, 0}, *root[2] = {0, 0}, *mnv[2] = {0, 0};
   u8 *pl_side = 0, *pr_side = 0;
   u32* ucount; ALLOC(ucount, u32, 4);
   int cur = 0;
   u32 ncyc = 0;
-  tm.start(c);
+  tm = t_begin(c);
   for (int pass = 0; pass < 2; ++pass) {
     // ---- K5: init detection, K6: pieces (8 vertices per thread), then one scan + compaction for the three lists
     const u32 nT = (nV + 7) / 8;
@@ -1257,9 +1270,9 @@ int spb_compact(spb_ctx* c, spb_counts* out) {
   dfree(c, ucount);
   c->cnt.n_cycle_comp = ncyc;
   const u32 nP = c->nP, nD = c->nD, nI = c->nI;
-  snprintf(buf, sizeof buf, ", \"classify_rank_ms\": %.4f", tm.stop(c)); c->stats += buf;
+  t_end(c, tm, "classify_rank_ms");
   // ---- K10: NBP table
-  tm.start(c);
+  tm = t_begin(c);
   u32* ideg; ALLOC(ideg, u32, nI + 1); ALLOC(c->ibase, u32, nI + 1);
   SPB_LAUNCH(k_init_degrees, nblk(nI, TPB), TPB, c->stream, g, c->init_list, nI, ideg);
   u64 nN64 = 0;
@@ -1294,16 +1307,16 @@ int spb_compact(spb_ctx* c, spb_counts* out) {
   ChunkParams* cpar; ALLOC(cpar, ChunkParams, nchunks + 1);
   SPB_LAUNCH(k_chunk_table, nblk(nchunks, TPB), TPB, c->stream, (u32)nchunks, choff, nD, c->plo, c->phi, c->dart_nbp, acc[cur], k, T, c->v2pos,
              c->voff, c->soff, cpar);
-  SPB_LAUNCH(k_emit_darts, nchunks, 256, c->stream, cpar, c->F, c->R, c->verts, c->seqs, c->vnbp);
+  { const int tq_ = t_begin(c); SPB_LAUNCH(k_emit_darts, nchunks, 256, c->stream, cpar, c->F, c->R, c->verts, c->seqs, c->vnbp); t_end(c, tq_, "k_emit_darts_ms"); }
   dfree(c, cpar);
   SPB_LAUNCH(k_emit_short, std::min<u64>(nblk((u64)nD * 32, 256), 148 * 32), 256, c->stream, nD, c->plo, c->phi, c->dart_nbp, acc[cur], k, T,
              c->F, c->R, c->v2pos, c->voff, c->soff, c->verts, c->seqs, c->vnbp);
   dfree(c, nch); dfree(c, choff); dfree(c, head_nbp); dfree(c, nxt);
   dfree(c, pl_nbr); dfree(c, pr_nbr); dfree(c, pl_side); dfree(c, pr_side);
   for (int i = 0; i < 2; ++i) { dfree(c, ptr[i]); dfree(c, acc[i]); dfree(c, root[i]); dfree(c, mnv[i]); }
-  snprintf(buf, sizeof buf, ", \"emit_ms\": %.4f", tm.stop(c)); c->stats += buf;
+  t_end(c, tm, "emit_ms");
   // ---- K13: origins
-  tm.start(c);
+  tm = t_begin(c);
   {
     u64* counts; ALLOC(counts, u64, 4);
     u8* has01; ALLOC(has01, u8, 2ull * c->n_seq + 8);
@@ -1315,8 +1328,8 @@ int spb_compact(spb_ctx* c, spb_counts* out) {
     for (int attempt = 0; attempt < 2; ++attempt) {
       ALLOC(op, u64, ocap + 1); ALLOC(mp, u64, mcap + 1);
       dev_memset(c, counts, 0, 32); dev_memset(c, has01, 0, 2ull * c->n_seq + 8);
-      SPB_LAUNCH(k_origin_pairs, gs_grid(T), TPB, c->stream, c->sp, T, c->fbits, c->vnbp, c->vflags, c->seq_off, c->n_seq, op, counts, ocap, mp,
-                 counts + 1, mcap, has01, sb);
+      { const int tq_ = t_begin(c); SPB_LAUNCH(k_origin_pairs, gs_grid(T), TPB, c->stream, c->sp, T, c->fbits, c->vnbp, c->vflags, c->seq_off, c->n_seq, op, counts, ocap, mp,
+                 counts + 1, mcap, has01, sb); t_end(c, tq_, "k_origin_pairs_ms"); }
       SPB_LAUNCH(k_origin_quirk, nblk(c->n_seq, TPB), TPB, c->stream, has01, c->n_seq, c->vnbp, c->vflags, op, counts, ocap, mp, counts + 1,
                  mcap, sb);
       no = dread(c, counts); nm = dread(c, counts + 1);
@@ -1343,9 +1356,9 @@ int spb_compact(spb_ctx* c, spb_counts* out) {
     dfree(c, ocnt); dfree(c, op); dfree(c, mp);
     c->cnt.n_origin_pairs = toto;
   }
-  snprintf(buf, sizeof buf, ", \"origins_ms\": %.4f", tm.stop(c)); c->stats += buf;
+  t_end(c, tm, "origins_ms");
   // ---- K14: connected components
-  tm.start(c);
+  tm = t_begin(c);
   {
     ALLOC(c->parent, u32, nI + 1); ALLOC(c->label_of_root, u32, nI + 1);
     u32* cmin; ALLOC(cmin, u32, nI + 1); dev_memset(c, cmin, 0xFF, (nI + 1) * 4ull);
@@ -1364,7 +1377,7 @@ int spb_compact(spb_ctx* c, spb_counts* out) {
     dfree(c, cmin); dfree(c, rk); dfree(c, rk2); dfree(c, nroots);
     c->cnt.n_comp = nr;
   }
-  snprintf(buf, sizeof buf, ", \"components_ms\": %.4f}", tm.stop(c)); c->stats += buf;
+  t_end(c, tm, "components_ms");
   int r = check_err(c, "spb_compact");
   if (r) return r;
   c->cnt.n_inits = nI; c->cnt.n_pieces = nP; c->cnt.n_nbp = nN; c->cnt.nbp_vertices = totv; c->cnt.nbp_bases = tots;
@@ -1800,7 +1813,21 @@ void spb_free_fasta(spb_fasta* fa) {
 }
 int spb_get_stage_stats(spb_ctx* c, char* buf, uint64_t cap) {
   if (!c || !buf || !cap) return SPB_EINVAL;
-  snprintf(buf, cap, "%s", c->stats.c_str());
+  dev_sync(c);
+  std::vector<std::pair<std::string, double>> acc;                            // insertion order, repeated names summed
+  for (auto& r : c->stat) {
+    double v = r.val;
+#ifndef SPB_EMU
+    if (r.ev >= 0) { float ms = 0; if (cudaEventElapsedTime(&ms, c->evpool[r.ev], c->evpool[r.ev + 1]) != cudaSuccess) { cudaGetLastError(); ms = 0; } v = ms; }
+#endif
+    bool found = false;
+    for (auto& a : acc) if (a.first == r.name) { a.second += v; found = true; break; }
+    if (!found) acc.push_back({r.name, v});
+  }
+  std::string js = "{";
+  for (size_t i = 0; i < acc.size(); ++i) { char b[192]; snprintf(b, sizeof b, "%s\"%s\": %.4f", i ? ", " : "", acc[i].first.c_str(), acc[i].second); js += b; }
+  js += "}";
+  snprintf(buf, cap, "%s", js.c_str());
   return SPB_OK;
 }
 
