@@ -3,6 +3,7 @@
 // Built by nvcc for sm_100a into libsuperpang_b200.so (the product), or by g++ -DSPB_EMU into
 // tests/emu/libspb_emu.so (kernel-logic emulator for the CPU-only test tier; never shipped).
 #include "spb_kernels.cuh"
+#include "spb_partition.cuh"
 #include "../../include/superpang_b200.h"
 
 #include <cstdio>
@@ -767,6 +768,79 @@ static int dedup_smem_links(spb_ctx* c) {
   return r;
 }
 
+// Launch of k_roll_partition in one of its compiled shapes (threads per CTA x positions per thread and staging group).
+static void launch_roll_partition(spb_ctx* c, u64 pos_lo, u64 pos_hi, u64 n_runs, u32 own_bits, u32 own_id, u32 l1, u64* rec1, u64 cap1, u32* cursor1) {
+  const RollK K = roll_constants(c->k);
+  int shape = 0;
+  if (const char* e = getenv("SPB_P1_SHAPE")) shape = atoi(e);
+#define SPB_P1_LAUNCH(T1, GS, MINB) SPB_LAUNCH_PHASED_DSMEM((k_roll_partition<T1, GS, MINB>), 1, nblk(n_runs, T1), T1, (T1) * (GS) * 8, c->stream, c->F, c->R, c->vbits, c->T, \
+                                         c->k, pos_lo, pos_hi, (u32)SPB_RUN, n_runs, own_bits, own_id, l1, rec1, cap1, cursor1, c->obits, K, c->errflag)
+  switch (shape) {
+    case 1: SPB_P1_LAUNCH(256, 8, 4); break;
+    case 2: SPB_P1_LAUNCH(256, 16, 2); break;
+    case 3: SPB_P1_LAUNCH(1024, 8, 1); break;
+    case 4: SPB_P1_LAUNCH(512, 16, 1); break;
+    case 5: SPB_P1_LAUNCH(512, 8, 3); break;
+    default: SPB_P1_LAUNCH(512, 8, 2); break;
+  }
+#undef SPB_P1_LAUNCH
+}
+
+// Two-level partitioned dedup, hand-written end to end (spb_partition.cuh): rolling hashes fused with the level-1 partition,
+// level-2 partition, one CTA per final bucket with a bulk-copied record block and a shared-memory table.  Returns 1 when
+// the input does not suit it (a bucket beyond its region: masses of identical k-mers) -- the caller then takes the
+// sort-based path.
+static int dedup_part_links(spb_ctx* c) {
+  const u64 T = c->T;
+  int r0 = alloc_position_state(c); if (r0) return r0;
+  const u64 P = c->npos_pad;
+  u64 avg = SPB_D_AVG;
+  if (const char* e = getenv("SPB_PART_AVG")) avg = std::max(1, atoi(e));        // tests: many tiny buckets
+  u32 nbits = 0; while ((c->n_inst >> nbits) > avg) ++nbits;
+  if (nbits > 18) return 1;
+  u32 l1 = (nbits + 1) / 2;
+  if (const char* e = getenv("SPB_PART_L1")) l1 = std::min<u32>(nbits, std::min(9, std::max(0, atoi(e))));
+  const u32 l2 = nbits - l1;
+  if (l2 > 9) return 1;
+  const u64 NB1 = 1ull << l1, NBF = 1ull << nbits;
+  const u64 n1 = nblk(c->n_inst, NB1);
+  const u64 cap1 = (n1 + n1 / 32 + 2048 + 1) & ~1ull;                              // mean + slack (hashes are uniform: sd = sqrt(mean))
+  const u64 cap2 = SPB_D_LIMIT;
+  int tk = t_begin(c);
+  u64 *rec1, *rec2; u32* cursors;
+  ALLOC(rec1, u64, NB1 * cap1 + 2); ALLOC(rec2, u64, NBF * cap2 + 2); ALLOC(cursors, u32, NB1 + NBF + 8);
+  dev_memset(c, cursors, 0, (NB1 + NBF + 8) * 4);
+  u32 *cursor1 = cursors, *cursor2 = cursors + NB1;
+  { const int tq_ = t_begin(c); launch_roll_partition(c, 0, T, P / SPB_RUN, 0, 0, l1, rec1, cap1, cursor1); t_end(c, tq_, "k_roll_partition_ms"); }
+  const u32 cpr = (u32)nblk(cap1, SPB_P2_CHUNK);
+  { const int tq_ = t_begin(c); SPB_LAUNCH_PHASED_DSMEM(k_partition2, 1, NB1 * cpr, SPB_P2_T, SPB_P2_CHUNK * 8, c->stream, rec1, cap1, cursor1, cpr, (u32)NB1, l2, rec2, cap2, cursor2, c->errflag);
+    t_end(c, tq_, "k_partition2_ms"); }
+  dfree(c, rec1);
+  t_end(c, tk, "records_partition_ms");
+  tk = t_begin(c);
+  u32 *seenpos, *dupbits; ALLOC(seenpos, u32, P + 8); ALLOC(dupbits, u32, P / 32 + 8);
+  dev_memset(c, dupbits, 0, (P / 32 + 8) * 4);
+  { const int tq_ = t_begin(c); SPB_LAUNCH_PHASED_DSMEM(k_bucket_dedup<false>, 2, NBF, SPB_D_T, (SPB_D_SLOTS / 2 + SPB_D_LIMIT + 2) * 8, c->stream, rec2, cap2, cursor2, l2, c->F, c->R, T, c->k,
+                          seenpos, dupbits, c->errflag, (u64*)nullptr, (u64*)nullptr, 0ull); t_end(c, tq_, "k_bucket_dedup_ms"); }
+  dfree(c, rec2); dfree(c, cursors);
+  const u32 e = dread(c, c->errflag);
+  if (e & ERR_OVERFLOW) {                            // skewed buckets: the caller falls back to the exact sort-based partition
+    dev_memset(c, c->errflag, 0, 4);
+    dev_memset(c, c->obits, 0, (P / 32 + 8) * 4);
+    dfree(c, seenpos); dfree(c, dupbits);
+    return 1;
+  }
+  c->cnt.table_slots = SPB_D_SLOTS;
+  t_end(c, tk, "bucket_dedup_ms"); stat_set(c, "partition2", (double)NBF);
+  u64 nb = P / 256, nw32 = P / 32;
+  SPB_LAUNCH(k_first_bits, nblk(nb, TPB), TPB, c->stream, c->vbits, dupbits, c->fbits, nb);     // first = valid and not linked
+  dev_memset(c, c->fbits + nw32, 0, 32);
+  dfree(c, dupbits);
+  int r = dd_ids(c, 0, T, nullptr, 1, seenpos, 1);
+  dfree(c, seenpos);
+  return r;
+}
+
 // the older single-table dedup (two random HBM accesses per instance); kept selectable for A/B measurements
 // The choice between the dedup schemes is made on two sample chunks of positions -- the first CH positions and CH
 // positions from the middle of the input (another genome, in a genome set) -- through a table sized for them alone
@@ -870,9 +944,10 @@ int spb_build_dbg(spb_ctx* c, spb_counts* out) {
   // path (records -> buckets -> L2 scratch tables -> scatter back); measured slower on one GPU in round 1
   // (profiles/README.md), its stages are what the multi-GPU exchange is built from.
   const char* mode = getenv("SPB_DEDUP");          // global | links | staged  (default: adaptive global -> links)
-  if (mode && (!strcmp(mode, "links") || !strcmp(mode, "smem"))) {
+  if (mode && (!strcmp(mode, "links") || !strcmp(mode, "smem") || !strcmp(mode, "part"))) {
     tm = t_begin(c);
-    int rc = strcmp(mode, "smem") ? 1 : dedup_smem_links(c);
+    int rc = !strcmp(mode, "part") ? dedup_part_links(c) : 1;
+    if (rc == 1 && strcmp(mode, "links")) { stats_reset(c); tm = t_begin(c); rc = dedup_smem_links(c); }
     if (rc == 1) { stats_reset(c); tm = t_begin(c); rc = dedup_staged_links(c); }
     if (rc) return rc;
     t_end(c, tm, "dedup_links_ms");
@@ -881,8 +956,10 @@ int spb_build_dbg(spb_ctx* c, spb_counts* out) {
     int rc = dedup_global_table(c, !mode);            // also reports k_extract_insert_ms (the kernel alone)
     if (rc == 1) {
       stat_set(c, "switched_to_links", 1);
-      rc = getenv("SPB_NO_SMEM_TABLES") ? 1 : dedup_smem_links(c);
-      if (rc == 1) { c->stat.erase(std::remove_if(c->stat.begin(), c->stat.end(), [](const spb_ctx::StatRec& r) { return r.name == "records_partition_ms" || r.name == "bucket_dedup_ms" || r.name == "smem_tables"; }), c->stat.end()); rc = dedup_staged_links(c); }
+      const auto drop_stats = [&]() { c->stat.erase(std::remove_if(c->stat.begin(), c->stat.end(), [](const spb_ctx::StatRec& r) { return r.name == "records_partition_ms" || r.name == "bucket_dedup_ms" || r.name == "smem_tables" || r.name == "k_roll_partition_ms" || r.name == "k_partition2_ms" || r.name == "k_bucket_dedup_ms" || r.name == "k_make_records_roll_ms" || r.name == "k_smem_dedup_ms"; }), c->stat.end()); };
+      rc = (getenv("SPB_NO_SMEM_TABLES") || getenv("SPB_NO_PARTITION")) ? 1 : dedup_part_links(c);
+      if (rc == 1) { drop_stats(); rc = getenv("SPB_NO_SMEM_TABLES") ? 1 : dedup_smem_links(c); }
+      if (rc == 1) { drop_stats(); rc = dedup_staged_links(c); }
     }
     if (rc) return rc;
     t_end(c, tm, "dedup_global_ms");

@@ -96,7 +96,8 @@ def test_emu_matches_oracle_random(emu_lib, seqs, k):
     assert A.path_origins([r[0] for r in raw]) == [r[2] for r in raw]
 
 
-@pytest.mark.parametrize("k,env", [(1001, {}), (2001, {}), (1001, {"SPB_DEDUP": "smem", "SPB_SMEM_AVG": "500"}), (75, {"SPB_DEDUP": "smem"})])
+@pytest.mark.parametrize("k,env", [(1001, {}), (2001, {}), (1001, {"SPB_DEDUP": "smem", "SPB_SMEM_AVG": "500"}), (75, {"SPB_DEDUP": "smem"}),
+                                   (1001, {"SPB_DEDUP": "part", "SPB_PART_AVG": "500"}), (75, {"SPB_DEDUP": "part", "SPB_PART_AVG": "100"})])
 def test_emu_large_k_matches_oracle(emu_lib, monkeypatch, k, env):
     """k beyond the specialised widths (101 / 301 / 501): the generic limb loops, the rolling hashes with a long window."""
     for key, v in env.items():
@@ -135,6 +136,12 @@ VARIANTS = [
     {"SPB_SWITCH_MIN": "1", "SPB_CHUNK_BITS": "9", "SPB_NO_SMEM_TABLES": "1", "SPB_EMU_ORDER": "reverse"},
     {"SPB_DEDUP": "smem", "SPB_SMEM_LIMIT": "10"},                   # a sub-bucket beyond the table -> L2-table path instead
     {"SPB_DEDUP": "smem", "SPB_SMEM_AVG": "1"},                      # absurd split: few hash bits left -> falls back or clusters
+    {"SPB_DEDUP": "part"},                                           # hand-written two-level partition, one bucket
+    {"SPB_DEDUP": "part", "SPB_PART_AVG": "300", "SPB_EMU_ORDER": "reverse"},     # several buckets, both levels; larger positions first
+    {"SPB_DEDUP": "part", "SPB_PART_AVG": "40", "SPB_EMU_ORDER": "shuffle"},
+    {"SPB_DEDUP": "part", "SPB_PART_AVG": "40", "SPB_PART_L1": "0"},              # level 2 only
+    {"SPB_DEDUP": "part", "SPB_PART_AVG": "2"},                      # buckets overflow their regions -> sort-based path instead
+    {"SPB_SWITCH_MIN": "1", "SPB_CHUNK_BITS": "8", "SPB_PART_AVG": "100", "SPB_EMU_ORDER": "reverse"},   # adaptive default reaching the partition
 ]
 
 
