@@ -494,7 +494,7 @@ static RollK roll_constants(u32 k) {
     const u32 B = K.B[h];
     u32 inv = B; for (int it = 0; it < 5; ++it) inv *= 2u - B * inv;
     u32 pw = 1, sq = B; for (u32 e = k - 1; e; e >>= 1) { if (e & 1) pw *= sq; sq *= sq; }
-    K.Binv[h] = inv; K.Bk1[h] = pw; K.negBk[h] = 0u - pw * B; K.negBinv[h] = 0u - inv;
+    K.Binv[h] = inv; K.Bk1[h] = pw; K.negBk[h] = 0u - pw * B; K.negBinv[h] = 0u - inv; K.B4[h] = B * B * B * B;
   }
   return K;
 }
@@ -769,20 +769,19 @@ static int dedup_smem_links(spb_ctx* c) {
 }
 
 // Launch of k_roll_partition in one of its compiled shapes (threads per CTA x positions per thread and staging group).
-static void launch_roll_partition(spb_ctx* c, u64 pos_lo, u64 pos_hi, u64 n_runs, u32 own_bits, u32 own_id, u32 l1, u64* rec1, u64 cap1, u32* cursor1) {
+static void launch_roll_partition(spb_ctx* c, u64 pos_lo, u64 pos_hi, u32 run, u64 n_runs, u32 own_bits, u32 own_id, u32 l1, u32 copies, u64* rec1, u64 cap1, u32* cursor1) {
   const RollK K = roll_constants(c->k);
   int shape = 0;
   if (const char* e = getenv("SPB_P1_SHAPE")) shape = atoi(e);
-#define SPB_P1_LAUNCH(T1, GS, MINB) SPB_LAUNCH_PHASED_DSMEM((k_roll_partition<T1, GS, MINB>), 1, nblk(n_runs, T1), T1, (T1) * (GS) * 8, c->stream, c->F, c->R, c->vbits, c->T, \
-                                         c->k, pos_lo, pos_hi, (u32)SPB_RUN, n_runs, own_bits, own_id, l1, rec1, cap1, cursor1, c->obits, K, c->errflag)
+#define SPB_P1_LAUNCH(T1, MINB) do { if (own_bits) SPB_P1_LAUNCH2(T1, MINB, true); else SPB_P1_LAUNCH2(T1, MINB, false); } while (0)
+#define SPB_P1_LAUNCH2(T1, MINB, MG) SPB_LAUNCH_PHASED_DSMEM((k_roll_partition<T1, MINB, MG>), 1, nblk(n_runs, T1), T1, (T1) * SPB_P1_GS * 8, c->stream, c->F, c->R, c->vbits, c->T, \
+                                         c->k, pos_lo, pos_hi, c->npos_pad, run, n_runs, own_bits, own_id, l1, copies, rec1, cap1, ((u64)copies << l1) * cap1, cursor1, c->obits, K, c->errflag)
   switch (shape) {
-    case 1: SPB_P1_LAUNCH(256, 8, 4); break;
-    case 2: SPB_P1_LAUNCH(256, 16, 2); break;
-    case 3: SPB_P1_LAUNCH(1024, 8, 1); break;
-    case 4: SPB_P1_LAUNCH(512, 16, 1); break;
-    case 5: SPB_P1_LAUNCH(512, 8, 3); break;
-    default: SPB_P1_LAUNCH(512, 8, 2); break;
+    case 1: SPB_P1_LAUNCH(256, 4); break;
+    case 2: SPB_P1_LAUNCH(1024, 1); break;
+    default: SPB_P1_LAUNCH(512, 2); break;
   }
+#undef SPB_P1_LAUNCH2
 #undef SPB_P1_LAUNCH
 }
 
@@ -802,26 +801,44 @@ static int dedup_part_links(spb_ctx* c) {
   if (const char* e = getenv("SPB_PART_L1")) l1 = std::min<u32>(nbits, std::min(9, std::max(0, atoi(e))));
   const u32 l2 = nbits - l1;
   if (l2 > 9) return 1;
-  const u64 NB1 = 1ull << l1, NBF = 1ull << nbits;
-  const u64 n1 = nblk(c->n_inst, NB1);
+  u32 run = 256;                                     // positions per thread of k_roll_partition (longer runs: the threads of a warp stream too far apart for L1)
+  if (const char* e = getenv("SPB_P1_RUN")) run = std::max(32, atoi(e) & ~31);
+  u32 copies = 1;                                    // regions per level-1 bucket (CTA x of k_roll_partition appends to copy x % copies); measured: no gain on one GPU
+  if (const char* e = getenv("SPB_P1_COPIES")) copies = std::max(1, std::min(64, atoi(e)));
+  if (c->n_inst < (1ull << 24) && !getenv("SPB_P1_COPIES")) copies = 1;
+  const u64 NB1 = 1ull << l1, NBF = 1ull << nbits, NR1 = NB1 * copies;
+  const u64 n1 = nblk(c->n_inst, NR1);
   const u64 cap1 = (n1 + n1 / 32 + 2048 + 1) & ~1ull;                              // mean + slack (hashes are uniform: sd = sqrt(mean))
   const u64 cap2 = SPB_D_LIMIT;
   int tk = t_begin(c);
   u64 *rec1, *rec2; u32* cursors;
-  ALLOC(rec1, u64, NB1 * cap1 + 2); ALLOC(rec2, u64, NBF * cap2 + 2); ALLOC(cursors, u32, NB1 + NBF + 8);
-  dev_memset(c, cursors, 0, (NB1 + NBF + 8) * 4);
-  u32 *cursor1 = cursors, *cursor2 = cursors + NB1;
-  { const int tq_ = t_begin(c); launch_roll_partition(c, 0, T, P / SPB_RUN, 0, 0, l1, rec1, cap1, cursor1); t_end(c, tq_, "k_roll_partition_ms"); }
+  ALLOC(rec1, u64, NR1 * cap1 + 8192 + 2); ALLOC(rec2, u64, NBF * cap2 + SPB_P2_CHUNK + 2); ALLOC(cursors, u32, NR1 + NBF + 8);
+  dev_memset(c, cursors, 0, (NR1 + NBF + 8) * 4);
+  u32 *cursor1 = cursors, *cursor2 = cursors + NR1;
+  { const int tq_ = t_begin(c); launch_roll_partition(c, 0, T, run, nblk(P, run), 0, 0, l1, copies, rec1, cap1, cursor1); t_end(c, tq_, "k_roll_partition_ms"); }
   const u32 cpr = (u32)nblk(cap1, SPB_P2_CHUNK);
-  { const int tq_ = t_begin(c); SPB_LAUNCH_PHASED_DSMEM(k_partition2, 1, NB1 * cpr, SPB_P2_T, SPB_P2_CHUNK * 8, c->stream, rec1, cap1, cursor1, cpr, (u32)NB1, l2, rec2, cap2, cursor2, c->errflag);
+#ifdef SPB_EMU
+  const u64 grid2 = NR1 * cpr, gridd = NBF;          // one chunk / bucket per block
+#else
+  const u64 grid2 = std::min<u64>(NR1 * cpr, 2 * 148), gridd = std::min<u64>(NBF, 2 * 148);   // persistent: two CTAs per SM
+#endif
+  { const int tq_ = t_begin(c); SPB_LAUNCH_PHASED_DSMEM(k_partition2, 1, grid2, SPB_P2_T, 3 * SPB_P2_CHUNK * 8, c->stream, rec1, cap1, cursor1, cpr, (u32)NR1, (u32)NB1, l2, rec2, cap2, NBF * cap2, cursor2, c->errflag);
     t_end(c, tq_, "k_partition2_ms"); }
   dfree(c, rec1);
   t_end(c, tk, "records_partition_ms");
   tk = t_begin(c);
   u32 *seenpos, *dupbits; ALLOC(seenpos, u32, P + 8); ALLOC(dupbits, u32, P / 32 + 8);
   dev_memset(c, dupbits, 0, (P / 32 + 8) * 4);
-  { const int tq_ = t_begin(c); SPB_LAUNCH_PHASED_DSMEM(k_bucket_dedup<false>, 2, NBF, SPB_D_T, (SPB_D_SLOTS / 2 + SPB_D_LIMIT + 2) * 8, c->stream, rec2, cap2, cursor2, l2, c->F, c->R, T, c->k,
-                          seenpos, dupbits, c->errflag, (u64*)nullptr, (u64*)nullptr, 0ull); t_end(c, tq_, "k_bucket_dedup_ms"); }
+  {
+    const int tq_ = t_begin(c);
+    if (!(getenv("SPB_D_NBUF") && atoi(getenv("SPB_D_NBUF")) == 2))        // measured: three resident CTAs beat two persistent ones (2.6 vs 3.1 ms, config 3)
+      SPB_LAUNCH_PHASED_DSMEM((k_bucket_dedup<false, 1>), 3, NBF, SPB_D_T, SPB_D_SMEM_U64(1) * 8, c->stream, rec2, cap2, cursor2, (u32)NBF, l2, c->F, c->R, c->obits, T, c->k,
+                              seenpos, dupbits, c->errflag, (u64*)nullptr, (u64*)nullptr, 0ull);
+    else
+      SPB_LAUNCH_PHASED_DSMEM((k_bucket_dedup<false, 2>), 3, gridd, SPB_D_T, SPB_D_SMEM_U64(2) * 8, c->stream, rec2, cap2, cursor2, (u32)NBF, l2, c->F, c->R, c->obits, T, c->k,
+                              seenpos, dupbits, c->errflag, (u64*)nullptr, (u64*)nullptr, 0ull);
+    t_end(c, tq_, "k_bucket_dedup_ms");
+  }
   dfree(c, rec2); dfree(c, cursors);
   const u32 e = dread(c, c->errflag);
   if (e & ERR_OVERFLOW) {                            // skewed buckets: the caller falls back to the exact sort-based partition

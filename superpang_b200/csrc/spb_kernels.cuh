@@ -392,7 +392,7 @@ k_make_records(const u32* __restrict__ F, const u32* __restrict__ R, const u32* 
 #ifndef SPB_RUN
 #define SPB_RUN 256
 #endif
-struct RollK { u32 B[2], Binv[2], Bk1[2], negBk[2], negBinv[2]; };   // B, B^-1, B^(k-1), -B^k, -B^-1  (mod 2^32)
+struct RollK { u32 B[2], Binv[2], Bk1[2], negBk[2], negBinv[2], B4[2]; };   // B, B^-1, B^(k-1), -B^k, -B^-1, B^4  (mod 2^32)
 __device__ __forceinline__ u64 roll_finish(u32 a, u32 b) {
   // (the rotations matter: a M + b is always even -- every coefficient M B1^e + B2^e is -- which would leave 2^31 values)
   u32 t = a * 0x9E3779B1u + __funnelshift_l(b, b, 15); t ^= t >> 16; t *= 0x85EBCA6Bu; t ^= t >> 13; t *= 0xC2B2AE35u; t ^= t >> 16;

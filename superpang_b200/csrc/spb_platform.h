@@ -23,6 +23,7 @@ typedef uint8_t u8;
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __restrict__
 #define SPB_LAUNCH_BOUNDS(n)
 #define SPB_LAUNCH_BOUNDS2(n, m)
@@ -82,6 +83,7 @@ static inline u32 atomicOr(u32* a, u32 v) { u32 o = *a; *a = o | v; return o; }
 static inline int __all_sync(unsigned, int p) { return p; }     // one emulated thread at a time
 static inline int __popcll(u64 x) { return __builtin_popcountll(x); }
 static inline u32 __funnelshift_l(u32 lo, u32 hi, u32 sh) { sh &= 31; return sh ? (hi << sh) | (lo >> (32 - sh)) : hi; }
+static inline u32 __funnelshift_r(u32 lo, u32 hi, u32 sh) { sh &= 31; return sh ? (lo >> sh) | (hi << (32 - sh)) : lo; }
 static inline int __popc(u32 x) { return __builtin_popcount(x); }
 static inline u32 __brev(u32 x) { u32 y = 0; for (int i = 0; i < 32; ++i) y |= ((x >> i) & 1u) << (31 - i); return y; }
 struct uint2 { u32 x, y; };

@@ -143,8 +143,8 @@ def test_gpu_properties_at_scale(mode):
     {"SPB_DEDUP": "smem", "SPB_SMEM_AVG": "50"},       # ... many small sub-buckets
     {"SPB_DEDUP": "part"},                             # hand-written two-level partition + bulk-copied buckets
     {"SPB_DEDUP": "part", "SPB_PART_AVG": "50"},       # ... many small buckets, both levels
-    {"SPB_DEDUP": "part", "SPB_PART_AVG": "200", "SPB_P1_SHAPE": "3"},   # ... the other CTA shapes of the fused kernel
-    {"SPB_DEDUP": "part", "SPB_PART_AVG": "200", "SPB_P1_SHAPE": "2"},
+    {"SPB_DEDUP": "part", "SPB_PART_AVG": "200", "SPB_P1_SHAPE": "1", "SPB_P1_COPIES": "4", "SPB_SWITCH_MIN": "1"},   # ... the other CTA shapes of the fused kernel, region copies
+    {"SPB_DEDUP": "part", "SPB_PART_AVG": "200", "SPB_P1_SHAPE": "2", "SPB_D_NBUF": "2"},          # ... persistent double-buffered dedup kernel
 ], ids=lambda e: ",".join(f"{k[4:].lower()}={v}" for k, v in e.items()))
 def test_gpu_dedup_variants(monkeypatch, env):
     """Every dedup strategy must give the reference's result (they differ only in how the table is reached)."""
@@ -186,7 +186,7 @@ def test_gpu_dedup_strategies_agree_at_scale(monkeypatch, mode):
     buf, off = concat_sequences(seqs)
 
     def run(env):
-        for k_ in ("SPB_DEDUP", "SPB_ANCHOR", "SPB_BUCKET_BITS", "SPB_CHUNK_BITS", "SPB_SMEM_AVG", "SPB_PART_AVG", "SPB_P1_SHAPE"):
+        for k_ in ("SPB_DEDUP", "SPB_ANCHOR", "SPB_BUCKET_BITS", "SPB_CHUNK_BITS", "SPB_SMEM_AVG", "SPB_PART_AVG", "SPB_P1_SHAPE", "SPB_P1_COPIES", "SPB_D_NBUF"):
             monkeypatch.delenv(k_, raising=False)
         for k_, v in env.items():
             monkeypatch.setenv(k_, v)
