@@ -118,6 +118,19 @@ int spb_mg_apply_links(spb_ctx* ctx, const uint64_t* links, uint64_t n, uint64_t
  * spb_mg_dedup_links; the orientation bitmap is complete on every rank afterwards (no all-gather needed for it).
  * Same reference lines as spb_build_dbg (lib/Assembler.py:148-201). */
 int spb_mg_owned_links(spb_ctx* ctx, uint32_t rank, uint32_t n_owners, uint64_t* send_counts, void** links_dev);
+/* "Part" protocol (default for mostly-unique inputs; round 2): the record exchange on the hand-written partition kernels.
+ * spb_mg_part_records turns the local slice into 8-byte records partitioned by (owner rank, level-1 bucket): recs_dev =
+ * [n_owners][*n_regions_per_owner regions] of fixed capacity (*region_records records per owner in total), counts_dev =
+ * [n_owners][*n_regions_per_owner] uint32 -- both exchanged by equal-split all-to-alls.  The host then all-gathers the
+ * orientation bitmap (spb_mg_buffers) and calls spb_mg_part_dedup on the received regions ([n_src] blocks in source-rank
+ * order), which returns links in the form of spb_mg_dedup_links.  *overflow = 1 (from either call, on any rank) means the
+ * input does not suit the fixed-capacity regions (masses of identical k-mers): every rank must then fall back to
+ * spb_mg_records / spb_mg_dedup_links.  Replaces, on this path, the reference's single-process dict loop
+ * (lib/Assembler.py:186-217) across GPUs. */
+int spb_mg_part_records(spb_ctx* ctx, uint64_t pos_lo, uint64_t pos_hi, uint32_t n_owners, uint64_t* region_records,
+                        uint32_t* n_regions_per_owner, void** recs_dev, void** counts_dev, int* overflow);
+int spb_mg_part_dedup(spb_ctx* ctx, const uint64_t* recs, const uint32_t* counts, uint32_t n_src, uint32_t n_owners,
+                      uint64_t* send_counts, void** links_dev, int* overflow);
 int spb_mg_buffers(spb_ctx* ctx, void** fbits_dev, void** obits_dev, void** sp_dev);
 int spb_mg_ids(spb_ctx* ctx, uint64_t pos_lo, uint64_t pos_hi);
 int spb_mg_graph(spb_ctx* ctx, spb_counts* out);

@@ -23,7 +23,7 @@ EXPORTS = (
     "spb_get_vertex2coords", "spb_get_edges", "spb_get_instance_vertices", "spb_get_seqlimits",
     "spb_get_seq_intervals", "spb_get_components", "spb_get_nbps", "spb_get_nbp_seqs",
     "spb_get_nbp_origins", "spb_get_counts", "spb_get_stage_stats", "spb_build_kind", "spb_launch_count",
-    "spb_get_nbp_graph", "spb_get_nbp_orientation_counts", "spb_get_seq_nbps", "spb_get_bubble_groups", "spb_path_sequences", "spb_path_origins", "spb_read_fasta", "spb_free_fasta", "spb_mg_slice", "spb_mg_probe", "spb_mg_records", "spb_mg_dedup", "spb_mg_scatter", "spb_mg_dedup_links", "spb_mg_apply_links", "spb_mg_owned_links", "spb_mg_buffers", "spb_mg_ids", "spb_mg_graph",
+    "spb_get_nbp_graph", "spb_get_nbp_orientation_counts", "spb_get_seq_nbps", "spb_get_bubble_groups", "spb_path_sequences", "spb_path_origins", "spb_read_fasta", "spb_free_fasta", "spb_mg_slice", "spb_mg_probe", "spb_mg_records", "spb_mg_dedup", "spb_mg_scatter", "spb_mg_dedup_links", "spb_mg_apply_links", "spb_mg_owned_links", "spb_mg_part_records", "spb_mg_part_dedup", "spb_mg_buffers", "spb_mg_ids", "spb_mg_graph",
 )
 
 
@@ -121,6 +121,9 @@ def _declare(lib):
     lib.spb_mg_dedup_links.argtypes = [vp, u64p, u32p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)]
     lib.spb_mg_apply_links.argtypes = [vp, u64p, C.c_uint64, C.c_uint64, C.c_uint64]
     lib.spb_mg_owned_links.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)]
+    lib.spb_mg_part_records.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_int)]
+    lib.spb_mg_part_dedup.argtypes = [vp, u64p, u32p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
     lib.spb_mg_buffers.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     lib.spb_mg_ids.argtypes = [vp, C.c_uint64, C.c_uint64]
     lib.spb_mg_graph.argtypes = [vp, C.POINTER(SpbCounts)]
@@ -271,16 +274,21 @@ class Engine:
         mark("start")
         # return protocol: rank 0 samples the duplicate rate of the input (two chunks) and broadcasts the choice
         protocol = os.environ.get("SPB_MG_PROTOCOL")
-        if protocol not in ("links", "reps", "owned"):
+        if protocol not in ("links", "reps", "owned", "part"):
             flag = torch.zeros(1, dtype=torch.int64, device=dev)
             if r == 0:
                 er, dr = C.c_double(), C.c_double()
                 self._ck(self.lib.spb_mg_probe(self.h, C.byref(er), C.byref(dr)))
                 flag[0] = 1 if dr.value < 0.02 else 0
             dist.broadcast(flag, src=0, group=group)
-            protocol = "owned" if int(flag.item()) else "reps"
+            protocol = "part" if int(flag.item()) else "reps"
         self.mg_protocol = protocol
         mark("probe")
+        if protocol == "part":
+            done = self._mg_part(group, G, r, S, lo, hi, cuda, dev, marks, mark, sync)
+            if done is not None:
+                return done
+            protocol = self.mg_protocol = "links"       # a bucket beyond its region somewhere (masses of identical k-mers): exact path instead
         if protocol == "owned":
             # "owner computes": every rank hashes all positions itself and keeps the k-mers it owns -- no record travels;
             # only the links (position -> first position) of repeated instances are exchanged
@@ -344,6 +352,80 @@ class Engine:
             sync()
             self._ck(self.lib.spb_mg_apply_links(self.h, lback.data_ptr() if lback.numel() else None, lback.numel(), lo, max(lo, hi)))
         return self._mg_finish(group, G, r, S, lo, hi, cuda, marks, mark, sync, gather_orientation=True)
+
+    def _mg_part(self, group, G, r, S, lo, hi, cuda, dev, marks, mark, sync):
+        """"Part" protocol: slice -> 8-byte records partitioned by (owner, level-1 bucket) [k_roll_partition] -> equal-split
+        all-to-all of the regions and their counts -> owner: level-2 partition + shared-memory tables [k_partition2,
+        k_bucket_dedup] -> links.  When the links are few (mostly-unique input) every rank receives ALL of them and numbers
+        all positions itself (no all-gather of the 4-byte-per-position id array); otherwise the links go to the slice
+        owners and the ids are all-gathered.  Returns None when some rank reported an overflow (caller falls back)."""
+        import torch
+        import torch.distributed as dist
+        T = int(self._keep[1][-1])
+        rr, nreg, ov = C.c_uint64(), C.c_uint32(), C.c_int()
+        rp, cp = C.c_void_p(), C.c_void_p()
+        self._ck(self.lib.spb_mg_part_records(self.h, lo, max(lo, hi), G, C.byref(rr), C.byref(nreg), C.byref(rp), C.byref(cp), C.byref(ov)))
+        mark("records_partition")
+        flag = torch.tensor([int(ov.value)], dtype=torch.int64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        if int(flag.item()):
+            return None
+        R, NR = int(rr.value), int(nreg.value)
+        recs = _wrap(rp.value, G * R, torch.int64, cuda, self.device)
+        cnts = _wrap(cp.value, G * NR, torch.int32, cuda, self.device)
+        rrecs, rcnts = torch.empty_like(recs), torch.empty_like(cnts)
+        dist.all_to_all_single(rcnts, cnts, group=group)
+        dist.all_to_all_single(rrecs, recs, group=group)
+        fb, ob, sp = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(self.lib.spb_mg_buffers(self.h, C.byref(fb), C.byref(ob), C.byref(sp)))
+        _all_gather_inplace(_wrap(ob.value, G * S // 32, torch.int32, cuda, self.device), r, G, group)   # the owners verify repeats exactly
+        mark("exchange_records")
+        sync()
+        lcnt = (C.c_uint64 * G)()
+        lp = C.c_void_p()
+        self._ck(self.lib.spb_mg_part_dedup(self.h, rrecs.data_ptr(), rcnts.data_ptr(), G, G, lcnt, C.byref(lp), C.byref(ov)))
+        del rrecs, rcnts
+        mark("owner_dedup")
+        lsend = [int(x) for x in lcnt]
+        nl = sum(lsend)
+        tot = torch.tensor([int(ov.value), nl], dtype=torch.int64, device=dev)
+        allc = [torch.empty_like(tot) for _ in range(G)]
+        dist.all_gather(allc, tot, group=group)
+        allc = [[int(v) for v in t.tolist()] for t in allc]
+        if any(a[0] for a in allc):
+            return None
+        counts = [a[1] for a in allc]
+        links = _wrap(lp.value, nl, torch.int64, cuda, self.device)
+        if 16 * sum(counts) <= T and os.environ.get("SPB_MG_ALL_LINKS", "1") != "0":
+            # few links: everybody gets all of them (padded all-gather), applies them and numbers ALL positions locally
+            m = max(max(counts), 1)
+            pad = torch.zeros(G * m, dtype=torch.int64, device=dev)
+            pad[r * m:r * m + nl].copy_(links)
+            _all_gather_inplace(pad, r, G, group)
+            alll = torch.cat([pad[i * m:i * m + counts[i]] for i in range(G)]) if sum(counts) else pad[:0]
+            mark("exchange_reps")
+            sync()
+            self._ck(self.lib.spb_mg_apply_links(self.h, alll.data_ptr() if alll.numel() else None, alll.numel(), 0, T))
+            mark("scatter")
+            self._ck(self.lib.spb_mg_ids(self.h, 0, T))
+            mark("bitmaps_ids")
+            sync()
+            self._ck(self.lib.spb_mg_graph(self.h, C.byref(self.counts)))
+            mark("graph")
+            if cuda:
+                sync()
+                self.mg_times = {f"mg_{n}_ms": marks[i - 1][1].elapsed_time(e) for i, (n, e) in enumerate(marks) if i}
+            return self.counts.as_dict()
+        lsc = torch.tensor(lsend, dtype=torch.int64, device=dev)
+        lrc = torch.empty_like(lsc)
+        dist.all_to_all_single(lrc, lsc, group=group)
+        lrecv = [int(x) for x in lrc.tolist()]
+        lback = torch.empty(sum(lrecv), dtype=torch.int64, device=dev)
+        _exchange(lback, links, lrecv, lsend, r, group)
+        mark("exchange_reps")
+        sync()
+        self._ck(self.lib.spb_mg_apply_links(self.h, lback.data_ptr() if lback.numel() else None, lback.numel(), lo, max(lo, hi)))
+        return self._mg_finish(group, G, r, S, lo, hi, cuda, marks, mark, sync, gather_orientation=False)
 
     def _mg_finish(self, group, G, r, S, lo, hi, cuda, marks, mark, sync, gather_orientation):
         """Common tail of the distributed build: bitmap all-gather, ids, id all-gather, graph (replicated)."""

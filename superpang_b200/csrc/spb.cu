@@ -60,6 +60,7 @@ struct spb_ctx {
   struct StatRec { std::string name; double val; int ev; };
   std::vector<StatRec> stat;
   size_t ev_used = 0;
+  u64 n_syncs = 0;                     // host <-> stream synchronisations since the last stats reset
 #ifndef SPB_EMU
   std::vector<cudaEvent_t> evpool;
 #endif
@@ -76,7 +77,7 @@ static void* backend_alloc(u64 bytes) { return malloc(bytes); }
 static void backend_free(void* p) { free(p); }
 static void dev_memset(spb_ctx*, void* p, int v, u64 bytes) { memset(p, v, bytes); }
 static void dev_copy(spb_ctx*, void* dst, const void* src, u64 bytes) { memcpy(dst, src, bytes); }
-static void dev_sync(spb_ctx*) {}
+static void dev_sync(spb_ctx* c) { ++c->n_syncs; }
 static int t_begin(spb_ctx*) { return 0; }
 static void t_end(spb_ctx* c, int, const char* name) { c->stat.push_back({name, 0.0, -1}); }
 #else
@@ -89,7 +90,7 @@ static void* backend_alloc(u64 bytes) {
 static void backend_free(void* p) { cudaFree(p); }
 static void dev_memset(spb_ctx* c, void* p, int v, u64 bytes) { cudaMemsetAsync(p, v, bytes, c->stream); }
 static void dev_copy(spb_ctx* c, void* dst, const void* src, u64 bytes) { cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, c->stream); }
-static void dev_sync(spb_ctx* c) { cudaStreamSynchronize(c->stream); }
+static void dev_sync(spb_ctx* c) { ++c->n_syncs; cudaStreamSynchronize(c->stream); }
 static int t_begin(spb_ctx* c) {                      // start of a timed stage: returns the index of its event pair
   if (c->ev_used + 2 > c->evpool.size()) { cudaEvent_t e; for (int i = 0; i < 2; ++i) { cudaEventCreate(&e); c->evpool.push_back(e); } }
   const int t = (int)c->ev_used; c->ev_used += 2;
@@ -219,14 +220,15 @@ struct SegMaxOp { __device__ u64 operator()(u64 a, u64 b) const { return ((a >> 
 static int prim_scan_u32(spb_ctx* c, const u32* in, u32* out, u64 n, u64* total) {
   if (n == 0) { *total = 0; return 0; }
   CUB2(cub::DeviceScan::ExclusiveSum(tmp, tb, in, out, (size_t)n, c->stream));
-  u32 a = 0, b = 0; dev_copy(c, &a, in + n - 1, 4); dev_copy(c, &b, out + n - 1, 4); dev_sync(c);
-  *total = (u64)a + b; return 0;
+  u32* pin = (u32*)c->pinned;                        // read back through pinned memory: one stream sync, no staging copy
+  dev_copy(c, pin, in + n - 1, 4); dev_copy(c, pin + 1, out + n - 1, 4); dev_sync(c);
+  *total = (u64)pin[0] + pin[1]; return 0;
 }
 static int prim_scan_u64(spb_ctx* c, const u64* in, u64* out, u64 n, u64* total) {
   if (n == 0) { *total = 0; return 0; }
   CUB2(cub::DeviceScan::ExclusiveSum(tmp, tb, in, out, (size_t)n, c->stream));
-  u64 a = 0, b = 0; dev_copy(c, &a, in + n - 1, 8); dev_copy(c, &b, out + n - 1, 8); dev_sync(c);
-  *total = a + b; return 0;
+  dev_copy(c, c->pinned, in + n - 1, 8); dev_copy(c, c->pinned + 1, out + n - 1, 8); dev_sync(c);
+  *total = c->pinned[0] + c->pinned[1]; return 0;
 }
 static int prim_sort_u64_u8(spb_ctx* c, u64*& k, u8*& v, u64*& k2, u8*& v2, u64 n) {
   if (n == 0) return 0;
@@ -435,6 +437,7 @@ int spb_load(spb_ctx* c, const uint8_t* ascii, const uint64_t* seq_off, uint32_t
   if (T == 0) return fail(c, SPB_EINVAL, "empty input");
   if (T >= (1ull << 32) - 4096) return fail(c, SPB_EINVAL, "input of %llu bases exceeds the 32-bit position range of one device", (unsigned long long)T);
   reset_state(c);
+  c->n_syncs = 0;
   dev_memset(c, c->errflag, 0, 16);
   c->k = k; c->n_seq = n_seq; c->T = T;
   c->seq_off_h.assign(seq_off, seq_off + n_seq + 1);
@@ -892,7 +895,7 @@ static int dedup_global_table(spb_ctx* c, bool allow_switch) {
   const u64 T = c->T;
   int r0 = alloc_position_state(c); if (r0) return r0;
   int decided = 0;
-  u64 CH = 1ull << 22, switch_min = 64ull << 20;
+  u64 CH = 1ull << 22, switch_min = 8ull << 20;
   if (const char* e = getenv("SPB_CHUNK_BITS")) { int b = atoi(e); if (b >= 8 && b <= 32) CH = 1ull << b; }   // tests: tiny chunks
   if (const char* e = getenv("SPB_SWITCH_MIN")) switch_min = strtoull(e, nullptr, 10);                        // tests: small inputs switch too
   if (allow_switch && c->n_inst >= switch_min && !getenv("SPB_ANCHOR") && c->npos_pad > CH) {
@@ -1243,6 +1246,105 @@ int spb_mg_owned_links(spb_ctx* c, uint32_t rank, uint32_t n_owners, uint64_t* s
   c->mg_owned = true;
   int r = finish_links(c, links, nl, n_owners, send_counts, links_dev);
   return r ? r : check_err(c, "spb_mg_owned_links");
+}
+
+// Multi-GPU, "part" protocol (default for mostly-unique inputs): record exchange with the hand-written partition kernels.
+//   spb_mg_part_records   position side: rolling hashes of the local slice fused with the partition by (owner, level-1
+//                         bucket) -- the owner is simply the top bits of the level-1 bucket index, so the regions of one
+//                         owner are contiguous: [owner][2^l1][cap1] records of 8 bytes + [owner][2^l1] counts.  The host
+//                         exchanges both with equal-split all-to-alls (the few per cent of slack travel along).
+//   spb_mg_part_dedup     owner side: level-2 partition of the n_src x 2^l1 received regions, one CTA per final bucket
+//                         with a shared-memory table (list form), links sorted by position and split by slice owner.
+// The geometry (l1, l2, cap1) is a function of (n_inst, n_owners, slice length) only, so every rank derives the same one.
+struct PartGeom { u32 own_bits, l1, l2; u64 cap1; };
+static int part_geometry(spb_ctx* c, u32 n_owners, PartGeom* g) {
+  u32 ob = 0; while ((1u << ob) < n_owners) ++ob;
+  u64 avg = SPB_D_AVG;
+  if (const char* e = getenv("SPB_PART_AVG")) avg = std::max(1, atoi(e));
+  const u64 per_owner = nblk(c->n_inst, n_owners);
+  u32 nbits = 0; while ((per_owner >> nbits) > avg) ++nbits;
+  if (ob > 9) return 1;
+  u32 l1 = std::min<u32>(9 - ob, nbits);
+  if (l1 > (nbits + 1) / 2 + 1) l1 = (nbits + 1) / 2 + 1;         // keep both levels at a useful fan-out
+  const u32 l2 = nbits - l1;
+  if (l2 > 9) return 1;
+  uint64_t slice = 0; spb_mg_slice(c, n_owners, &slice);
+  const u64 n1 = nblk(slice, (u64)n_owners << l1);                // positions of a slice per (owner, level-1 bucket)
+  g->own_bits = ob; g->l1 = l1; g->l2 = l2;
+  g->cap1 = (n1 + n1 / 16 + 2048 + 1) & ~1ull;
+  return 0;
+}
+int spb_mg_part_records(spb_ctx* c, uint64_t pos_lo, uint64_t pos_hi, uint32_t n_owners, uint64_t* region_records, uint32_t* n_regions_per_owner,
+                        void** recs_dev, void** counts_dev, int* overflow) {
+  if (!c || !region_records || !n_regions_per_owner || !recs_dev || !counts_dev || !overflow) return SPB_EINVAL;
+  if (c->state != 1) return fail(c, SPB_ESTATE, "spb_mg_part_records needs a freshly loaded input");
+  if (!pow2(n_owners)) return fail(c, SPB_EINVAL, "n_owners must be a power of two");
+  if (pos_lo % 256) return fail(c, SPB_EINVAL, "pos_lo must be a multiple of 256");
+#ifndef SPB_EMU
+  CK(cudaSetDevice(c->device));
+#endif
+  PartGeom g;
+  *overflow = 0;
+  if (part_geometry(c, n_owners, &g)) { *overflow = 1; return SPB_OK; }
+  uint64_t slice = 0; spb_mg_slice(c, n_owners, &slice);
+  int r0 = alloc_position_state(c, slice * n_owners); if (r0) return r0;
+  if (pos_hi > c->T) pos_hi = c->T;
+  if (pos_hi < pos_lo) pos_hi = pos_lo;
+  const u64 NR = (u64)n_owners << g.l1;
+  dfree(c, c->dd_keys); dfree(c, c->dd_bstart);
+  u64* rec1; u32* cursor1;
+  ALLOC(rec1, u64, NR * g.cap1 + 8192 + 2); ALLOC(cursor1, u32, NR + 8);
+  dev_memset(c, cursor1, 0, (NR + 8) * 4);
+  const u32 run = 256;
+  { const int tq_ = t_begin(c); launch_roll_partition(c, pos_lo, pos_hi, run, nblk(pos_hi - pos_lo, run), 0, 0, g.own_bits + g.l1, 1, rec1, g.cap1, cursor1); t_end(c, tq_, "k_roll_partition_ms"); }
+  const u32 e = dread(c, c->errflag);
+  if (e & ERR_OVERFLOW) { dev_memset(c, c->errflag, 0, 4); *overflow = 1; }
+  c->dd_keys = rec1; c->dd_bstart = (u64*)cursor1;               // owned by the context until spb_mg_apply_links
+  c->mg_owned = true;                                            // (the host all-gathers the orientation bitmap right after this call)
+  *region_records = g.cap1 << g.l1; *n_regions_per_owner = 1u << g.l1;
+  *recs_dev = rec1; *counts_dev = cursor1;
+  return (e & ~(u32)ERR_OVERFLOW) ? check_err(c, "spb_mg_part_records") : SPB_OK;
+}
+int spb_mg_part_dedup(spb_ctx* c, const uint64_t* recs, const uint32_t* counts, uint32_t n_src, uint32_t n_owners, uint64_t* send_counts,
+                      void** links_dev, int* overflow) {
+  if (!c || !send_counts || !links_dev || !overflow) return SPB_EINVAL;
+  if (c->state != 1) return fail(c, SPB_ESTATE, "spb_mg_part_dedup needs a loaded input");
+#ifndef SPB_EMU
+  CK(cudaSetDevice(c->device));
+#endif
+  PartGeom g;
+  *overflow = 0;
+  if (part_geometry(c, n_owners, &g)) { *overflow = 1; return SPB_OK; }
+  const u64 NB1 = 1ull << g.l1, NR1 = NB1 * n_src, NBF = 1ull << (g.l1 + g.l2), cap2 = SPB_D_LIMIT;
+  u64* rec2; u32* cursor2;
+  ALLOC(rec2, u64, NBF * cap2 + SPB_P2_CHUNK + 2); ALLOC(cursor2, u32, NBF + 8);
+  dev_memset(c, cursor2, 0, (NBF + 8) * 4);
+  const u32 cpr = (u32)nblk(g.cap1, SPB_P2_CHUNK);
+#ifdef SPB_EMU
+  const u64 grid2 = NR1 * cpr;
+#else
+  const u64 grid2 = std::min<u64>(NR1 * cpr, 2 * 148);
+#endif
+  { const int tq_ = t_begin(c); SPB_LAUNCH_PHASED_DSMEM(k_partition2, 1, grid2, SPB_P2_T, 3 * SPB_P2_CHUNK * 8, c->stream, (const u64*)recs, g.cap1, counts, cpr, (u32)NR1, (u32)NB1, g.l2, rec2, cap2,
+                            NBF * cap2, cursor2, c->errflag); t_end(c, tq_, "k_partition2_ms"); }
+  u64* nlinks; ALLOC(nlinks, u64, 2);
+  u64 lcap = std::max<u64>(4096, c->n_inst / n_owners / 8);
+  u64* links = nullptr; u64 nl = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    ALLOC(links, u64, lcap + 1);
+    dev_memset(c, nlinks, 0, 16);
+    { const int tq_ = t_begin(c); SPB_LAUNCH_PHASED_DSMEM((k_bucket_dedup<true, 1>), 3, NBF, SPB_D_T, SPB_D_SMEM_U64(1) * 8, c->stream, rec2, cap2, cursor2, (u32)NBF, g.l2, c->F, c->R, c->obits, c->T, c->k,
+                            (u32*)nullptr, (u32*)nullptr, c->errflag, links, nlinks, lcap); t_end(c, tq_, "k_bucket_dedup_ms"); }
+    nl = dread(c, nlinks);
+    if (nl <= lcap) break;
+    dfree(c, links); lcap = nl;
+  }
+  dfree(c, nlinks); dfree(c, rec2); dfree(c, cursor2);
+  c->cnt.table_slots = SPB_D_SLOTS;
+  const u32 e = dread(c, c->errflag);
+  if (e & ERR_OVERFLOW) { dev_memset(c, c->errflag, 0, 4); *overflow = 1; dfree(c, links); for (u32 r = 0; r < n_owners; ++r) send_counts[r] = 0; *links_dev = nullptr; return SPB_OK; }
+  int r = finish_links(c, links, nl, n_owners, send_counts, links_dev);
+  return r ? r : check_err(c, "spb_mg_part_dedup");
 }
 
 // Position side, "links" protocol: the links received for the local slice -> first-appearance bits of the slice.
@@ -1907,8 +2009,10 @@ void spb_free_fasta(spb_fasta* fa) {
 }
 int spb_get_stage_stats(spb_ctx* c, char* buf, uint64_t cap) {
   if (!c || !buf || !cap) return SPB_EINVAL;
+  const u64 syncs = c->n_syncs;
   dev_sync(c);
   std::vector<std::pair<std::string, double>> acc;                            // insertion order, repeated names summed
+  acc.push_back({"host_syncs", (double)syncs});
   for (auto& r : c->stat) {
     double v = r.val;
 #ifndef SPB_EMU

@@ -30,9 +30,14 @@ def main():
         if os.path.exists(path):
             cases.append((path, 301, helpers.load_json(name)))
     used = set()
-    for proto in (None, "owned", "links", "reps"):           # None: chosen by the duplicate-rate probe
+    for proto in (None, "part", "part-slice", "owned", "links", "reps"):           # None: chosen by the duplicate-rate probe
         if proto:
-            os.environ["SPB_MG_PROTOCOL"] = proto
+            os.environ["SPB_MG_PROTOCOL"] = proto.split("-")[0]
+            os.environ["SPB_MG_ALL_LINKS"] = "0" if proto.endswith("-slice") else "1"
+            if proto.startswith("part"):
+                os.environ["SPB_PART_AVG"] = "300"           # both partition levels on the small cases
+            else:
+                os.environ.pop("SPB_PART_AVG", None)
         for sd, k, want in cases:
             if proto and isinstance(sd, str):
                 continue                                      # the large KAT sets run once, with the probe's choice
@@ -40,7 +45,7 @@ def main():
             assert A._eng.kind == "cuda sm_100a"
             used.add(A._eng.mg_protocol)
             helpers.assert_summary(digests.summarize(A.to_result()), want)
-    assert used == {"owned", "links", "reps"}, used
+    assert used >= {"part", "owned", "links", "reps"}, used
     dist.barrier()
     if dist.get_rank() == 0:
         print(f"multi-GPU parity OK on {dist.get_world_size()} ranks, {len(cases)} cases")

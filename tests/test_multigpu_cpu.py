@@ -34,6 +34,11 @@ def _free_port():
     (8, {"SPB_MG_PROTOCOL": "owned", "SPB_SMEM_AVG": "200"}),          # the driver's largest scaling point
     (2, {"SPB_MG_PROTOCOL": "owned", "SPB_SMEM_LIMIT": "10"}),       # sub-buckets beyond the shared-memory table: tables in global memory
     (2, {"SPB_CHUNK_BITS": "8"}),                                    # protocol chosen by the duplicate-rate probe
+    (2, {"SPB_MG_PROTOCOL": "part", "SPB_PART_AVG": "60"}),          # record exchange on the partition kernels, all links to everybody
+    (4, {"SPB_MG_PROTOCOL": "part", "SPB_PART_AVG": "30", "SPB_EMU_ORDER": "reverse"}),
+    (2, {"SPB_MG_PROTOCOL": "part", "SPB_PART_AVG": "60", "SPB_MG_ALL_LINKS": "0", "SPB_EMU_ORDER": "shuffle"}),   # links to the slice owners, ids all-gathered
+    (8, {"SPB_MG_PROTOCOL": "part", "SPB_PART_AVG": "40", "SPB_MG_ALL_LINKS": "0"}),
+    (2, {"SPB_MG_PROTOCOL": "part", "SPB_PART_AVG": "2"}),           # regions overflow -> collective fallback to the exact path
 ], ids=lambda x: str(x) if isinstance(x, int) else (",".join(f"{k[4:].lower()}={v}" for k, v in x.items()) or "default"))
 def test_distributed_build_matches_reference(emu_lib, tmp_path, world, env):
     crafted = [c for c in helpers.load_crafted() if c["k"] == 31 and not c.get("degenerate")]
