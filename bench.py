@@ -105,8 +105,9 @@ def config_for(args, world):
     """The `config` object of the JSON line: defined by the command line only, so both arms print the same one."""
     w = WORKLOADS[args.workload]
     return dict(workload=f"{w['desc']}, k={K}, mode={args.mode}", k=K, mode=args.mode,
-                parallelism=("1 GPU" if world == 1 else f"k-mers hash-partitioned over {world} GPUs (NCCL all-to-all of records and links), "
-                             "per-position passes, edge rows and NBP emission sharded by position slice"),
+                parallelism=("1 GPU" if world == 1 else f"k-mers hash-partitioned over {world} GPUs (NCCL all-to-all of 8-byte records, all-gather of the links); "
+                             "graph build + compaction sliced: ids / junction entries / origin pairs by position slice, flags / piece lists / edge rows by "
+                             "vertex range, NBP vertex lists + sequences by NBP range; all-gathers of the short lists only; results stay sliced in HBM"),
                 l2="flushed between timed iterations (256 MiB write)")
 
 
@@ -219,7 +220,11 @@ def main():
 
     w, names, buf, off, n_inst = make_workload(args.workload, args.mode)
     host = torch.from_numpy(buf).pin_memory()
-    dbuf = host.to(dev, non_blocking=True)
+    T = host.numel()
+    Tpad = (T + world * 16 - 1) // (world * 16) * (world * 16)          # equal parts for the all-gather of the input (e2e, N > 1)
+    dpad = torch.empty(Tpad, dtype=torch.uint8, device=dev)
+    dbuf = dpad[:T]
+    dbuf.copy_(host, non_blocking=True)
     stream = torch.cuda.current_stream()
     eng = _capi.Engine(device=local, stream=stream.cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
@@ -238,14 +243,30 @@ def main():
         if world == 1:
             eng.load(host, off, K)          # H2D of the ASCII input inside the library call
         else:
-            # one H2D on rank 0, then the genome travels over NVLink (NCCL broadcast); results are read back by rank 0,
-            # the rank that hosts the reference's single-process tail
-            if rank == 0:
-                dbuf.copy_(host, non_blocking=True)
-            dist.broadcast(dbuf, src=0)
+            # every rank copies ITS 1/N of the input over ITS PCIe link, then the parts travel over NVLink (NCCL all-gather)
+            part = Tpad // world
+            a, b = rank * part, min((rank + 1) * part, T)
+            if b > a:
+                dpad[a:b].copy_(host[a:b], non_blocking=True)
+            _capi._all_gather_inplace(dpad, rank, world, None)
             eng.load(dbuf, off, K)
         build()
         c = eng.compact()
+        if world > 1 and getattr(eng, "mg_sliced", False):
+            # sliced results: every rank copies the sequences of ITS NBPs into the shared page-locked host buffer that rank 0
+            # (the process hosting the reference's single-process tail) reads; offsets and origin lists come from rank 0
+            n, nb, no = c["n_nbp"], c["nbp_bases"], c["n_origin_pairs"]
+            if out_bufs.get("key") != (n, nb, no):
+                out_bufs.update(key=(n, nb, no), shared=_capi.SharedHostBuffer(nb, tag="nbp_seqs"))
+                if rank == 0:
+                    out_bufs.update(soff=torch.empty(n + 1, dtype=torch.int64).pin_memory(), ooff=torch.empty(n + 1, dtype=torch.int64).pin_memory(),
+                                    oidx=torch.empty(max(no, 1), dtype=torch.int32).pin_memory())
+            nbytes = eng.shard_to_host("nbp_seqs", out_bufs["shared"].tensor)
+            if rank == 0:
+                eng._ck(eng.lib.spb_get_nbp_seqs(eng.h, out_bufs["soff"].data_ptr(), None))
+                eng._ck(eng.lib.spb_get_nbp_origins(eng.h, out_bufs["ooff"].data_ptr(), out_bufs["oidx"].data_ptr()))
+                nbytes += 8 * (n + 1) * 2 + 4 * no
+            return c, nbytes
         if rank != 0:
             return c, 0
         n, nb, no = c["n_nbp"], c["nbp_bases"], c["n_origin_pairs"]
@@ -294,9 +315,12 @@ def main():
 
     # per-step times: max over ranks of every step, then mean / median / min over the steps
     tt = torch.tensor([times, e2e_times], device=dev, dtype=torch.float64)
+    d2h = torch.tensor([float(e2e_last[1])], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(d2h)                         # D2H bytes of all ranks
     times, e2e_times = tt[0].tolist(), tt[1].tolist()
+    d2h_bytes = int(d2h.item())
     ms, ms_e2e = float(np.sum(times)), float(np.sum(e2e_times))
     total_inst = n_inst                              # strong scaling: the same genome set, k-mers hash-partitioned over the ranks
     value = total_inst * args.steps / (ms / 1e3)
@@ -305,7 +329,10 @@ def main():
     # ---- result digest (outside the timed region): device-side checksums of every result buffer of the last step
     dg, dg_single = None, None
     if not args.no_digest:
-        if rank == 0:
+        sliced = world > 1 and getattr(eng, "mg_sliced", False)
+        if sliced:                                   # checksums of the local parts, summed over the ranks (collective)
+            dg = digest.result_digest_sliced(eng)
+        elif rank == 0:
             dg = digest.result_digest(eng, graph=True)
         if world > 1:
             dist.barrier()
@@ -334,7 +361,8 @@ def main():
         if kt:
             dom = max(kt, key=kt.get)
             dom_ms = kt[dom]
-            dom_bytes = KERNEL_BYTES[dom](counts) / max(world, 1) if dom in ("k_roll_partition_ms", "k_partition2_ms", "k_smem_dedup_ms") else KERNEL_BYTES[dom](counts)
+            per_rank = dom in ("k_roll_partition_ms", "k_partition2_ms", "k_smem_dedup_ms") or getattr(eng, "mg_sliced", False)   # this kernel handles 1/N of the units
+            dom_bytes = KERNEL_BYTES[dom](counts) / max(world, 1) if per_rank else KERNEL_BYTES[dom](counts)
             ach = dom_bytes / (dom_ms / 1e3) / 1e9
             traffic = None
             try:                                     # measured DRAM bytes of that kernel per launch (ncu --set full of this build)
@@ -364,7 +392,7 @@ def main():
             counts=dict(n_inst=n_inst, n_vertices=counts["n_vertices"], n_edges=counts["n_edges"], n_nbp=counts["n_nbp"], nbp_bases=counts["nbp_bases"],
                         n_origin_pairs=counts["n_origin_pairs"], mg_protocol=getattr(eng, "mg_protocol", None)),
             e2e=dict(value=e2e_value, unit="k-mers/s", ms_per_step=ms_e2e / args.steps, ms_per_step_median=float(np.median(e2e_times)),
-                     h2d_bytes_per_step=int(buf.nbytes + off.nbytes), d2h_bytes_per_step=int(e2e_last[1])),
+                     h2d_bytes_per_step=int(buf.nbytes + off.nbytes), d2h_bytes_per_step=d2h_bytes),
             gpu_launches=int(launches),
             roofline=roof,
             stages_ms=st_mean,

@@ -135,6 +135,39 @@ int spb_mg_buffers(spb_ctx* ctx, void** fbits_dev, void** obits_dev, void** sp_d
 int spb_mg_ids(spb_ctx* ctx, uint64_t pos_lo, uint64_t pos_hi);
 int spb_mg_graph(spb_ctx* ctx, spb_counts* out);
 
+/* ---- sliced multi-GPU tail (round 2): graph build + NBP compaction partitioned over the ranks --------------------------
+ * Follows the "part" dedup when every rank holds all links (spb_mg_apply_links over [0, T)): fbits / obits / links are
+ * complete everywhere and nothing of size N_inst is exchanged any more.  Rank r computes
+ *   - vertex ids, junction entries and origin pairs of ITS positions (slice r of spb_mg_slice),
+ *   - implicit-edge flags of all vertices (from the replicated bitmap), init / piece flags, the sorted init / piece-bound
+ *     lists, explicit edge rows and the vertex -> NBP map of ITS vertices (first appearances of its positions, cut at
+ *     multiples of 8),
+ *   - vertex lists and sequences of ITS raw NBPs (id ranges with equal shares of the output),
+ * the host side all-gathers the short lists in between (NCCL: junction entries, inits, piece bounds, origin pairs; the
+ * exchange of the edge endpoints and of the compaction state that the reference does in one process,
+ * lib/Assembler.py:199-249, :269-363), and every rank computes the contracted graph (pieces, darts, list ranking, NBP
+ * table), the origin sets and the components -- all of size O(#NBPs) -- itself.  Call order:
+ *   spb_mg_slice_ids -> spb_mg_slice_junctions -> [all-gather J] -> spb_mg_slice_graph -> { spb_mg_slice_classify ->
+ *   [all-gather lists, sum of edge counts] -> spb_mg_slice_contract } (again while *again) -> spb_mg_slice_emit ->
+ *   [all-gather pairs, OR of has01] -> spb_mg_slice_finish.
+ * All list pointers are device pointers; the library copies what it is given.  Results stay sliced: spb_mg_shard hands
+ * out the local parts (which: 0 per-position vertex ids, 1 vertex2coords rows, 2 edge rows, 3 NBP vertex lists, 4 NBP
+ * sequences; first / count in elements (rows) of the complete array, edge rows counted from this rank's first row);
+ * counts, offsets, components, origins and the NBP table are complete on every rank.  spb_mg_complete recomputes the
+ * sliced passes over the whole input on the calling rank (no communication), after which every getter works as on one
+ * GPU; getters that need sliced arrays return SPB_ESTATE before that. */
+int spb_mg_slice_ids(spb_ctx* ctx, uint32_t rank, uint32_t n_ranks);
+int spb_mg_slice_junctions(spb_ctx* ctx, uint64_t* n, void** jk_dev, void** js_dev);
+int spb_mg_slice_graph(spb_ctx* ctx, const uint64_t* jk_all, const uint8_t* js_all, uint64_t n_all, uint64_t* n_edges_local);
+int spb_mg_slice_classify(spb_ctx* ctx, uint32_t* n_init, uint32_t* n_start, uint32_t* n_end, void** init_dev, void** plo_dev, void** phi_dev);
+int spb_mg_slice_contract(spb_ctx* ctx, const uint32_t* init_all, uint32_t n_init, const uint32_t* plo_all, const uint32_t* phi_all,
+                          uint32_t n_piece, uint64_t n_edges_total, int pass, int* again);
+int spb_mg_slice_emit(spb_ctx* ctx, uint64_t* n_op, void** op_dev, uint64_t* n_mp, void** mp_dev, void** has01_dev);
+int spb_mg_slice_finish(spb_ctx* ctx, const uint64_t* op_all, uint64_t n_op, const uint64_t* mp_all, uint64_t n_mp,
+                        const uint8_t* has01_any, spb_counts* out);
+int spb_mg_shard(spb_ctx* ctx, int which, void** dev, uint64_t* first, uint64_t* count);
+int spb_mg_complete(spb_ctx* ctx, spb_counts* out);
+
 /* ---- getters (sizes come from spb_counts; buffers are caller-owned, host or device) ---------- */
 
 /* uint32[n_vertices][2] = (ref, idx) of each vertex's first appearance (`lib/Assembler.py:194`). */

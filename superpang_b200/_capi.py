@@ -24,6 +24,8 @@ EXPORTS = (
     "spb_get_seq_intervals", "spb_get_components", "spb_get_nbps", "spb_get_nbp_seqs",
     "spb_get_nbp_origins", "spb_get_counts", "spb_get_stage_stats", "spb_build_kind", "spb_launch_count",
     "spb_get_nbp_graph", "spb_get_nbp_orientation_counts", "spb_get_seq_nbps", "spb_get_bubble_groups", "spb_path_sequences", "spb_path_origins", "spb_read_fasta", "spb_free_fasta", "spb_mg_slice", "spb_mg_probe", "spb_mg_records", "spb_mg_dedup", "spb_mg_scatter", "spb_mg_dedup_links", "spb_mg_apply_links", "spb_mg_owned_links", "spb_mg_part_records", "spb_mg_part_dedup", "spb_mg_buffers", "spb_mg_ids", "spb_mg_graph",
+    "spb_mg_slice_ids", "spb_mg_slice_junctions", "spb_mg_slice_graph", "spb_mg_slice_classify", "spb_mg_slice_contract", "spb_mg_slice_emit",
+    "spb_mg_slice_finish", "spb_mg_shard", "spb_mg_complete",
 )
 
 
@@ -127,6 +129,16 @@ def _declare(lib):
     lib.spb_mg_buffers.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     lib.spb_mg_ids.argtypes = [vp, C.c_uint64, C.c_uint64]
     lib.spb_mg_graph.argtypes = [vp, C.POINTER(SpbCounts)]
+    pv, pu64, pu32 = C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
+    lib.spb_mg_slice_ids.argtypes = [vp, C.c_uint32, C.c_uint32]
+    lib.spb_mg_slice_junctions.argtypes = [vp, pu64, pv, pv]
+    lib.spb_mg_slice_graph.argtypes = [vp, u64p, u8p, C.c_uint64, pu64]
+    lib.spb_mg_slice_classify.argtypes = [vp, pu32, pu32, pu32, pv, pv, pv]
+    lib.spb_mg_slice_contract.argtypes = [vp, u32p, C.c_uint32, u32p, u32p, C.c_uint32, C.c_uint64, C.c_int, C.POINTER(C.c_int)]
+    lib.spb_mg_slice_emit.argtypes = [vp, pu64, pv, pu64, pv, pv]
+    lib.spb_mg_slice_finish.argtypes = [vp, u64p, C.c_uint64, u64p, C.c_uint64, u8p, C.POINTER(SpbCounts)]
+    lib.spb_mg_shard.argtypes = [vp, C.c_int, pv, pu64, pu64]
+    lib.spb_mg_complete.argtypes = [vp, C.POINTER(SpbCounts)]
     return lib
 
 
@@ -147,7 +159,7 @@ def _wrap(ptr, n, dtype, cuda, device):
     dev = torch.device("cuda", device) if cuda else torch.device("cpu")
     if n == 0 or not ptr:
         return torch.empty(0, dtype=dtype, device=dev)
-    typestr, npdt, size = {torch.int64: ("<i8", np.int64, 8), torch.int32: ("<i4", np.int32, 4)}[dtype]
+    typestr, npdt, size = {torch.int64: ("<i8", np.int64, 8), torch.int32: ("<i4", np.int32, 4), torch.uint8: ("|u1", np.uint8, 1)}[dtype]
     if cuda:
         class _Ptr:
             pass
@@ -176,6 +188,54 @@ def _exchange(out, inp, out_splits, in_splits, rank, group):
         dist.all_to_all_single(out, inp, out_splits, in_splits, group=group)
 
 
+def _gather_var(parts, counts_all, rank, world, group):
+    """All-gather of variable-length device lists.  parts: tensors of this rank (one per list, any integer dtype);
+    counts_all[r][i] = length of list i on rank r (already known everywhere).  The lists of a rank travel as ONE padded
+    byte block (one collective); returns, per list, the concatenation over the ranks in rank order."""
+    import torch
+    import torch.distributed as dist
+    sizes = [p.element_size() for p in parts]
+    nbytes = [sum(int(c) * sz for c, sz in zip(cr, sizes)) for cr in counts_all]
+    m = (max(max(nbytes), 1) + 15) & ~15
+    dev = parts[0].device
+    pad = torch.empty(world * m, dtype=torch.uint8, device=dev)
+    o = rank * m
+    for p_, sz in zip(parts, sizes):
+        nb = p_.numel() * sz
+        if nb:
+            pad[o:o + nb].copy_(p_.view(torch.uint8))
+        o += nb
+    _all_gather_inplace(pad, rank, world, group)
+    out = []
+    for i, (p_, sz) in enumerate(zip(parts, sizes)):
+        chunks = []
+        for r in range(world):
+            o = r * m + sum(int(counts_all[r][j]) * sizes[j] for j in range(i))
+            nb = int(counts_all[r][i]) * sz
+            if nb:
+                chunks.append(pad[o:o + nb])
+        cat = torch.cat(chunks) if chunks else pad[:0]
+        # the byte offsets of a list inside a block are multiples of its element size only if the lists before it are:
+        # callers order the lists by decreasing element size
+        out.append(cat.view(p_.dtype) if cat.numel() else torch.empty(0, dtype=p_.dtype, device=dev))
+    return out
+
+
+def _counts_all(vals, world, dev, group):
+    """all-gather of a few host integers per rank -> list (per rank) of lists"""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([int(v) for v in vals], dtype=torch.int64, device=dev)
+    full = torch.empty(world * t.numel(), dtype=torch.int64, device=dev)
+    try:
+        dist.all_gather_into_tensor(full, t, group=group)
+    except Exception:
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t, group=group)
+        full = torch.cat(parts)
+    return full.view(world, t.numel()).tolist()
+
+
 def _all_gather_inplace(full, rank, world, group):
     """all-gather where every rank already holds its own chunk of `full` at the right offset."""
     import torch.distributed as dist
@@ -189,6 +249,38 @@ def _all_gather_inplace(full, rank, world, group):
         dist.all_gather(tmp, mine.clone(), group=group)
         for p, t in zip(parts, tmp):
             p.copy_(t)
+
+
+class SharedHostBuffer:
+    """uint8 host buffer in POSIX shared memory, mapped by every rank of the group and page-locked in each process
+    (cudaHostRegister): with results sliced over the ranks, every rank copies ITS part over ITS PCIe link straight into the
+    memory that the one process hosting the reference's single-process tail (rank 0) reads.  Collective constructor."""
+
+    def __init__(self, nbytes, group=None, tag="buf"):
+        import torch
+        import torch.distributed as dist
+        rank = dist.get_rank(group)
+        self.nbytes = max(int(nbytes), 1)
+        self.path = f"/dev/shm/spb_{os.environ.get('MASTER_PORT', '0')}_{os.getuid()}_{tag}"
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(self.nbytes)
+        dist.barrier(group)
+        self.mm = np.memmap(self.path, dtype=np.uint8, mode="r+", shape=(self.nbytes,))
+        self.tensor = torch.from_numpy(self.mm)
+        self.registered = False
+        if torch.cuda.is_available():
+            rc = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), self.nbytes, 0)
+            self.registered = int(rc) == 0
+        dist.barrier(group)
+        if rank == 0:
+            os.unlink(self.path)              # the mappings keep the memory alive
+
+    def close(self):
+        import torch
+        if self.registered:
+            torch.cuda.cudart().cudaHostUnregister(self.tensor.data_ptr())
+            self.registered = False
 
 
 class Engine:
@@ -228,6 +320,7 @@ class Engine:
         seq_off: uint64[n_seq + 1] (host)."""
         seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
         self._keep = (ascii_buf, seq_off)
+        self.mg_sliced = False
         self._ck(self.lib.spb_load(self.h, _ptr(ascii_buf), seq_off.ctypes.data, len(seq_off) - 1, int(k)))
 
     def build_dbg(self):
@@ -235,6 +328,8 @@ class Engine:
         return self.counts.as_dict()
 
     def compact(self):
+        if getattr(self, "mg_sliced", False):            # the sliced multi-GPU tail has built the graph AND compacted it
+            return self.counts.as_dict()
         self._ck(self.lib.spb_compact(self.h, C.byref(self.counts)))
         return self.counts.as_dict()
 
@@ -396,7 +491,8 @@ class Engine:
             return None
         counts = [a[1] for a in allc]
         links = _wrap(lp.value, nl, torch.int64, cuda, self.device)
-        if 16 * sum(counts) <= T and os.environ.get("SPB_MG_ALL_LINKS", "1") != "0":
+        all_links = os.environ.get("SPB_MG_ALL_LINKS", "1")       # "0": never, "2": always (tests), default: when the links are few
+        if all_links == "2" or (16 * sum(counts) <= T and all_links != "0"):
             # few links: everybody gets all of them (padded all-gather), applies them and numbers ALL positions locally
             m = max(max(counts), 1)
             pad = torch.zeros(G * m, dtype=torch.int64, device=dev)
@@ -407,6 +503,8 @@ class Engine:
             sync()
             self._ck(self.lib.spb_mg_apply_links(self.h, alll.data_ptr() if alll.numel() else None, alll.numel(), 0, T))
             mark("scatter")
+            if os.environ.get("SPB_MG_TAIL", "sliced") == "sliced":
+                return self._mg_sliced_tail(group, G, r, cuda, dev, marks, mark, sync)
             self._ck(self.lib.spb_mg_ids(self.h, 0, T))
             mark("bitmaps_ids")
             sync()
@@ -426,6 +524,94 @@ class Engine:
         sync()
         self._ck(self.lib.spb_mg_apply_links(self.h, lback.data_ptr() if lback.numel() else None, lback.numel(), lo, max(lo, hi)))
         return self._mg_finish(group, G, r, S, lo, hi, cuda, marks, mark, sync, gather_orientation=False)
+
+    def _mg_sliced_tail(self, group, G, r, cuda, dev, marks, mark, sync):
+        """Graph build + compaction sliced over the ranks (include/superpang_b200.h, "sliced multi-GPU tail"): per-position
+        passes on the own slice, per-vertex passes on the own vertices, emission of the own NBP range; only the short lists
+        (junction entries, inits, piece bounds, origin pairs) are all-gathered, the contracted graph is computed by every
+        rank.  Leaves the engine compacted, with sliced results (`shard`, `complete`)."""
+        import torch
+        import torch.distributed as dist
+        L, h = self.lib, self.h
+        self._ck(L.spb_mg_slice_ids(h, r, G))
+        mark("slice_ids")
+        n, jk, js = C.c_uint64(), C.c_void_p(), C.c_void_p()
+        self._ck(L.spb_mg_slice_junctions(h, C.byref(n), C.byref(jk), C.byref(js)))
+        ca = _counts_all([n.value], G, dev, group)
+        jk_t = _wrap(jk.value, n.value, torch.int64, cuda, self.device)
+        js_t = _wrap(js.value, n.value, torch.uint8, cuda, self.device)
+        jk_all, js_all = _gather_var([jk_t, js_t], [[c_[0], c_[0]] for c_ in ca], r, G, group)
+        sync()
+        ne = C.c_uint64()
+        self._ck(L.spb_mg_slice_graph(h, jk_all.data_ptr() if jk_all.numel() else None, js_all.data_ptr() if js_all.numel() else None,
+                                      jk_all.numel(), C.byref(ne)))
+        del jk_all, js_all
+        mark("slice_graph")
+        for p_ in range(2):
+            ni, ns, nend = C.c_uint32(), C.c_uint32(), C.c_uint32()
+            il, pl, ph = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            self._ck(L.spb_mg_slice_classify(h, C.byref(ni), C.byref(ns), C.byref(nend), C.byref(il), C.byref(pl), C.byref(ph)))
+            ca = _counts_all([ni.value, ns.value, nend.value, ne.value], G, dev, group)
+            lists = [_wrap(il.value, ni.value, torch.int32, cuda, self.device), _wrap(pl.value, ns.value, torch.int32, cuda, self.device),
+                     _wrap(ph.value, nend.value, torch.int32, cuda, self.device)]
+            init_all, plo_all, phi_all = _gather_var(lists, [c_[:3] for c_ in ca], r, G, group)
+            if plo_all.numel() != phi_all.numel():
+                raise SpbError(-4, f"internal: {plo_all.numel()} piece starts, {phi_all.numel()} piece ends over the ranks")
+            sync()
+            again = C.c_int()
+            self._ck(L.spb_mg_slice_contract(h, init_all.data_ptr() if init_all.numel() else None, init_all.numel(),
+                                             plo_all.data_ptr() if plo_all.numel() else None, phi_all.data_ptr() if phi_all.numel() else None,
+                                             plo_all.numel(), sum(c_[3] for c_ in ca), p_, C.byref(again)))
+            del init_all, plo_all, phi_all
+            if not again.value:
+                break
+        mark("slice_classify_rank")
+        no, nm = C.c_uint64(), C.c_uint64()
+        op, mp, h01 = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(L.spb_mg_slice_emit(h, C.byref(no), C.byref(op), C.byref(nm), C.byref(mp), C.byref(h01)))
+        mark("slice_emit_pairs")
+        ca = _counts_all([no.value, nm.value], G, dev, group)
+        op_all, mp_all = _gather_var([_wrap(op.value, no.value, torch.int64, cuda, self.device), _wrap(mp.value, nm.value, torch.int64, cuda, self.device)],
+                                     ca, r, G, group)
+        n_seq = len(self._keep[1]) - 1
+        has01 = _wrap(h01.value, 2 * n_seq, torch.uint8, cuda, self.device).clone()
+        dist.all_reduce(has01, op=dist.ReduceOp.MAX, group=group)
+        sync()
+        self._ck(L.spb_mg_slice_finish(h, op_all.data_ptr() if op_all.numel() else None, op_all.numel(), mp_all.data_ptr() if mp_all.numel() else None,
+                                       mp_all.numel(), has01.data_ptr(), C.byref(self.counts)))
+        mark("slice_origins_components")
+        self.mg_sliced = True
+        if cuda:
+            sync()
+            self.mg_times = {f"mg_{n_}_ms": marks[i - 1][1].elapsed_time(e) for i, (n_, e) in enumerate(marks) if i}
+        return self.counts.as_dict()
+
+    def shard(self, which):
+        """Local part of a sliced result as a zero-copy torch view (device memory on the GPU build) and the index of its
+        first element (row) in the complete array.  which: 'instance_vertices', 'vertex2coords', 'edges', 'nbp_verts',
+        'nbp_seqs' (include/superpang_b200.h, spb_mg_shard)."""
+        import torch
+        code, dt, width = {"instance_vertices": (0, torch.int32, 1), "vertex2coords": (1, torch.int32, 2), "edges": (2, torch.int32, 2),
+                           "nbp_verts": (3, torch.int32, 1), "nbp_seqs": (4, torch.uint8, 1)}[which]
+        p_, first, count = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.spb_mg_shard(self.h, code, C.byref(p_), C.byref(first), C.byref(count)))
+        return _wrap(p_.value, count.value * width, dt, self.kind.startswith("cuda"), self.device), int(first.value)
+
+    def shard_to_host(self, which, host_tensor):
+        """Copy the local part of a sliced result to its place in `host_tensor` (the complete array on the host, e.g. a
+        SharedHostBuffer tensor); asynchronous on the current stream when the host memory is page-locked.  Returns the
+        number of bytes copied."""
+        t, first = self.shard(which)
+        if t.numel():
+            host_tensor.view(t.dtype)[first:first + t.numel()].copy_(t, non_blocking=True)
+        return t.numel() * t.element_size()
+
+    def complete(self):
+        """Recompute the sliced passes over the whole input on this rank (no communication): afterwards every getter
+        works as on one GPU (spb_mg_complete)."""
+        self._ck(self.lib.spb_mg_complete(self.h, C.byref(self.counts)))
+        self.mg_sliced = False
+        return self.counts.as_dict()
 
     def _mg_finish(self, group, G, r, S, lo, hi, cuda, marks, mark, sync, gather_orientation):
         """Common tail of the distributed build: bitmap all-gather, ids, id all-gather, graph (replicated)."""

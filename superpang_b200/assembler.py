@@ -107,15 +107,26 @@ class Assembler:
         self._compacted = False
         self._cache = {}
 
+    def _full(self):
+        """Multi-GPU: graph build and compaction ran sliced over the ranks (Engine._mg_sliced_tail).  The reference's host
+        tail is one process and reads whole arrays, so the first accessor that needs them has this rank recompute the
+        sliced passes over the whole input (Engine.complete: no communication; counts, origins, components and the NBP
+        table are complete on every rank anyway)."""
+        if getattr(self._eng, "mg_sliced", False):
+            self.counts = self._eng.complete()
+            self._compacted = True
+
     # ---- DBG-build state consumed by the reference's host tail ------------------------------
     @property
     def vertex2coords(self):
+        self._full()
         if "v2c" not in self._cache:
             self._cache["v2c"] = self._eng.vertex2coords()
         return self._cache["v2c"]
 
     @property
     def edges(self):
+        self._full()
         if "edges" not in self._cache:
             self._cache["edges"] = self._eng.edges()
         return self._cache["edges"]
@@ -137,6 +148,7 @@ class Assembler:
 
     @property
     def seqPaths(self):
+        self._full()
         if "sp" not in self._cache:
             off, iv = self._eng.seq_intervals()
             self._cache["sp"] = {n: iv[int(off[i]):int(off[i + 1])] for i, n in enumerate(self.ref2name)
@@ -145,6 +157,7 @@ class Assembler:
 
     def instance_vertices(self, name):
         """The per-sequence `sp` array of `lib/Assembler.py:183-197` (vertex id of every k-mer)."""
+        self._full()
         if "inst" not in self._cache:
             self._cache["inst"] = self._eng.instance_vertices()
         i = self.ref2name.index(name)
@@ -153,6 +166,7 @@ class Assembler:
 
     # ---- NBP collection ---------------------------------------------------------------------
     def compact(self):
+        self._full()
         if not self._compacted:
             self.counts = self._eng.compact()
             self._compacted = True

@@ -55,6 +55,25 @@ struct spb_ctx {
   u64 *dd_keys = 0, *dd_bstart = 0; u32* dd_pos = 0; u64 dd_n = 0, dd_lo = 0, dd_hi = 0; u32 dd_bb = 0; bool dd_fbits_ready = false;
   std::vector<u64> dd_bstart_h;
   u64* mg_links = 0; u32 *mg_seen = 0, *mg_dup = 0;                 // multi-GPU links protocol
+  // rank tables of the first-appearance bitmap: exclusive block offsets (256 positions) and per-word prefixes
+  u32* blkoff = 0; u8* wpre = 0; u64 nb = 0;
+  // Sliced multi-GPU tail: what THIS context computes of the per-position, per-vertex and per-NBP
+  // passes.  on = false (one GPU, or the replicated tail): everything.
+  struct Slice {
+    bool on = false; u32 rank = 0, G = 1;
+    u64 pos_lo = 0, pos_hi = 0, ids_lo = 0, ids_hi = 0;    // own positions; positions whose ids are filled (one more on either side)
+    u32 v_lo = 0, v_hi = 0;                                // vertices whose first appearance lies in [pos_lo, pos_hi): v2pos is filled for them
+    u32 t_lo = 0, t_hi = 0;                                // own tiles of 8 vertices: classification, piece lists, edge rows, vertex -> NBP map
+    u32 n_lo = 0, n_hi = 0;                                // own raw NBPs: vertex lists and sequences
+    u64 vert_lo = 0, vert_n = 0, seq_lo = 0, seq_n = 0, edge_n = 0;
+  } sl;
+  u32* shard_tmp = 0;                                     // last spb_mg_shard(1) result
+  u8* seqs_base = 0;                                      // allocation behind `seqs` (the slice keeps the 4-byte phase of the global offsets)
+  // compaction state that lives across the phases (classification -> contracted graph -> NBP table -> emission -> origins)
+  u32 *pl_nbr = 0, *pr_nbr = 0, *nxt = 0, *rk_ptr[2] = {0, 0}, *rk_acc[2] = {0, 0}, *rk_root[2] = {0, 0}, *rk_mnv[2] = {0, 0};
+  u8 *pl_side = 0, *pr_side = 0;
+  int rk_cur = 0; u32 ncyc = 0;
+  u64 *op = 0, *mp = 0; u64 n_op = 0, n_mp = 0, op_cap = 0, mp_cap = 0; u8* has01 = 0;
   // per-stage statistics: scalar values and (CUDA) event pairs resolved lazily by spb_get_stage_stats, so that timing a
   // stage never synchronises the host with the stream
   struct StatRec { std::string name; double val; int ev; };
@@ -588,37 +607,58 @@ static int dd_scatter(spb_ctx* c, const u32* rep) {
 }
 
 // vertex ids for the positions [lo, hi) + the vertex table (needs the complete fbits bitmap)
-static int dd_ids(spb_ctx* c, u64 lo, u64 hi, const u64* slots, u64 cap = 1, const u32* sp_in = nullptr, int follow = 0) {
+// ---- views for the kernels that may run on a slice (single GPU: the slice is everything, the views are plain arrays)
+static VPos vpos_view(spb_ctx* c) {
+  return VPos{c->v2pos, c->sl.on ? c->sl.v_lo : 0u, c->sl.on ? c->sl.v_hi : c->nV, c->fbits, c->blkoff, c->wpre, (u32)c->nb};
+}
+static VidAt vid_view(spb_ctx* c) {
+  return VidAt{c->sp, c->sl.on ? c->sl.ids_lo : 0ull, c->sl.on ? c->sl.ids_hi : c->T, c->fbits, c->mg_seen, c->blkoff, c->wpre};
+}
+static VNbp vnbp_view(spb_ctx* c) {
+  const u32 lo = c->sl.on ? 8u * c->sl.t_lo : 0u;
+  const u32 hi = c->sl.on ? (u32)std::min<u64>(8ull * (c->sl.t_hi + 1), c->nV) : c->nV;
+  return VNbp{c->vnbp, lo, hi, c->plo, c->phi, c->nP, c->dart_nbp};
+}
+
+// vertex ids of the positions [lo, hi); vertex -> first position for the first appearances in [tlo, thi); the flag byte
+// (implicit-edge bit) of every vertex.  The rank tables of the first-appearance bitmap stay in the context.
+static int dd_ids(spb_ctx* c, u64 lo, u64 hi, const u64* slots, u64 cap = 1, const u32* sp_in = nullptr, int follow = 0, u64 tlo = 0, u64 thi = ~0ull) {
   if (!sp_in) sp_in = c->sp;
   const u64 T = c->T;
   u64 nb = c->npos_pad / 256;
-  u32 *blkcnt, *blkoff; u8* wpre; ALLOC(blkcnt, u32, nb); ALLOC(blkoff, u32, nb); ALLOC(wpre, u8, nb * 8 + 8);
-  SPB_LAUNCH(k_block_counts, nblk(nb, TPB), TPB, c->stream, c->fbits, blkcnt, wpre, nb);
+  u32* blkcnt; ALLOC(blkcnt, u32, nb);
+  dfree(c, c->blkoff); dfree(c, c->wpre);
+  ALLOC(c->blkoff, u32, nb + 1); ALLOC(c->wpre, u8, nb * 8 + 8);
+  c->nb = nb;
+  SPB_LAUNCH(k_block_counts, nblk(nb, TPB), TPB, c->stream, c->fbits, blkcnt, c->wpre, nb);
   u64 nV = 0;
-  PRIM(prim_scan_u32(c, blkcnt, blkoff, nb, &nV));
+  PRIM(prim_scan_u32(c, blkcnt, c->blkoff, nb, &nV));
+  dfree(c, blkcnt);
   c->nV = (u32)nV;
+  dfree(c, c->v2pos); dfree(c, c->vflags);
   ALLOC(c->v2pos, u32, nV + 1); ALLOC(c->vflags, u8, nV + 64);
   dev_memset(c, c->vflags + (nV & ~7ull), 0, 64);
+  const u32* blkoff = c->blkoff; const u8* wpre = c->wpre;
   const int tq_ids = t_begin(c);
   switch ((2 * c->k + 31) / 32) {
-    case 7:  SPB_LAUNCH(k_assign_ids<7>, gs_grid(T), TPB, c->stream, sp_in, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags, follow, c->errflag); break;
-    case 19: SPB_LAUNCH(k_assign_ids<19>, gs_grid(T), TPB, c->stream, sp_in, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags, follow, c->errflag); break;
-    case 32: SPB_LAUNCH(k_assign_ids<32>, gs_grid(T), TPB, c->stream, sp_in, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags, follow, c->errflag); break;
-    default: SPB_LAUNCH(k_assign_ids<0>, gs_grid(T), TPB, c->stream, sp_in, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags, follow, c->errflag); break;
+    case 7:  SPB_LAUNCH(k_assign_ids<7>, gs_grid(T), TPB, c->stream, sp_in, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags, follow, c->errflag, tlo, thi); break;
+    case 19: SPB_LAUNCH(k_assign_ids<19>, gs_grid(T), TPB, c->stream, sp_in, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags, follow, c->errflag, tlo, thi); break;
+    case 32: SPB_LAUNCH(k_assign_ids<32>, gs_grid(T), TPB, c->stream, sp_in, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags, follow, c->errflag, tlo, thi); break;
+    default: SPB_LAUNCH(k_assign_ids<0>, gs_grid(T), TPB, c->stream, sp_in, c->sp, c->vbits, T, lo, hi, c->fbits, blkoff, wpre, slots, cap - 1, c->F, c->R, c->k, c->v2pos, c->vflags, follow, c->errflag, tlo, thi); break;
   }
   t_end(c, tq_ids, "k_assign_ids_ms");
-  dfree(c, blkcnt); dfree(c, blkoff); dfree(c, wpre);
   return 0;
 }
 
-// junction edges, sequence limits, explicit edge list (needs the complete sp / obits arrays)
-static int dd_graph(spb_ctx* c) {
-  const u64 T = c->T; const u32 k = c->k; const u64 nV = c->nV;
+// raw junction entries (both directions, unsorted) of the pairs (p, p + 1) in the bitmap words [w_lo, w_hi)
+static int graph_junctions(spb_ctx* c, u64 w_lo, u64 w_hi, u64** Jk_out, u8** Js_out, u64* nj_out) {
+  const u64 T = c->T; const u64 nV = c->nV;
   u64* jcount; ALLOC(jcount, u64, 2);
-  u64 jcap = std::max<u64>(4096, c->n_inst / 8);
+  const u64 npos = 32 * (w_hi - w_lo);
+  u64 jcap = std::max<u64>(4096, npos / 8);
   u64* Jk = nullptr; u8* Js = nullptr; u64 nj = 0;
   u32* vobits = nullptr;
-  if (c->n_inst - nV > nV / 4) {                     // many repeated instances: per-vertex orientation bits pay off
+  if (!c->sl.on && c->n_inst - nV > nV / 4) {          // many repeated instances: per-vertex orientation bits pay off
     ALLOC(vobits, u32, nV / 32 + 8);
     dev_memset(c, vobits, 0, (nV / 32 + 8) * 4);
     SPB_LAUNCH(k_vertex_obits, std::min<u64>(nblk(nV, TPB), 148 * 16), TPB, c->stream, c->v2pos, c->obits, (u32)nV, vobits);
@@ -626,12 +666,20 @@ static int dd_graph(spb_ctx* c) {
   for (int attempt = 0; attempt < 2; ++attempt) {
     ALLOC(Jk, u64, jcap); ALLOC(Js, u8, jcap);
     dev_memset(c, jcount, 0, 16);
-    { const int tq_ = t_begin(c); SPB_LAUNCH(k_junction_emit, std::min<u64>(nblk(T, TPB), 148 * 16), TPB, c->stream, c->sp, T, c->fbits, c->vflags, c->v2pos, c->obits, vobits, Jk, Js, jcount, jcap, c->errflag); t_end(c, tq_, "k_junction_emit_ms"); }
+    { const int tq_ = t_begin(c); SPB_LAUNCH(k_junction_emit, std::min<u64>(nblk(npos, TPB), 148 * 16), TPB, c->stream, c->sp, T, w_lo, w_hi, c->fbits, c->vflags, vpos_view(c), c->obits, vobits, Jk, Js, jcount, jcap, c->errflag); t_end(c, tq_, "k_junction_emit_ms"); }
     nj = dread(c, jcount);
     if (nj <= jcap) break;
     dfree(c, Jk); dfree(c, Js); jcap = nj;
   }
   dfree(c, jcount); dfree(c, vobits);
+  *Jk_out = Jk; *Js_out = Js; *nj_out = nj;
+  return 0;
+}
+
+// all junction entries (takes ownership of Jk / Js) -> sorted unique J, junction / sequence-limit flags, and the explicit
+// edge rows of the vertex tiles [t_lo, t_hi) (one GPU: all of them)
+static int graph_finish(spb_ctx* c, u64* Jk, u8* Js, u64 nj) {
+  const u32 k = c->k; const u64 nV = c->nV;
   {
     u64* k2; u8* v2; ALLOC(k2, u64, nj); ALLOC(v2, u8, nj);
     PRIM(prim_sort_u64_u8(c, Jk, Js, k2, v2, nj));
@@ -641,18 +689,28 @@ static int dd_graph(spb_ctx* c) {
   c->Jk = Jk; c->Js = Js;
   SPB_LAUNCH(k_mark_hasj, nblk(c->nJ, TPB), TPB, c->stream, c->Jk, c->nJ, c->vflags);
   ALLOC(c->seqlim, u32, 2ull * c->n_seq);
-  SPB_LAUNCH(k_mark_seqlim, nblk(c->n_seq, TPB), TPB, c->stream, c->seq_off, c->n_seq, k, c->sp, c->vflags, c->seqlim);
+  SPB_LAUNCH(k_mark_seqlim, nblk(c->n_seq, TPB), TPB, c->stream, c->seq_off, c->n_seq, k, vid_view(c), c->vflags, c->seqlim);
   GView g{c->vflags, c->Jk, c->Js, c->nJ, c->nV};
-  u64 nT = (nV + 7) / 8;
+  const u32 nTall = (u32)((nV + 7) / 8);
+  const u32 t_lo = c->sl.on ? c->sl.t_lo : 0u, t_hi = c->sl.on ? c->sl.t_hi : nTall;
+  const u64 nT = t_hi - t_lo;
   u32 *ecnt, *eoff; ALLOC(ecnt, u32, nT + 1); ALLOC(eoff, u32, nT + 1);
-  SPB_LAUNCH(k_edge_counts8, nblk(nT, TPB), TPB, c->stream, g, ecnt);
+  SPB_LAUNCH(k_edge_counts8, nblk(nT, TPB), TPB, c->stream, g, ecnt, t_lo, t_hi);
   u64 nE = 0;
   PRIM(prim_scan_u32(c, ecnt, eoff, nT, &nE));
   ALLOC(c->edges, u32, 2 * nE + 2);
-  { const int tq_ = t_begin(c); SPB_LAUNCH(k_edge_write, std::min<u64>(nblk(nV, TPB), 148 * 32), TPB, c->stream, g, eoff, c->edges); t_end(c, tq_, "k_edge_write_ms"); }
+  { const int tq_ = t_begin(c); SPB_LAUNCH(k_edge_write, std::min<u64>(nblk(8 * nT, TPB), 148 * 32), TPB, c->stream, g, eoff, c->edges, t_lo, t_hi); t_end(c, tq_, "k_edge_write_ms"); }
   dfree(c, ecnt); dfree(c, eoff);
-  c->cnt.n_vertices = nV; c->cnt.n_edges = nE; c->cnt.n_junction = c->nJ;
+  c->sl.edge_n = nE;
+  c->cnt.n_vertices = nV; c->cnt.n_edges = nE; c->cnt.n_junction = c->nJ;     // (sliced: n_edges is set to the total by the caller)
   return 0;
+}
+
+// junction edges, sequence limits, explicit edge list (needs the complete sp / obits arrays)
+static int dd_graph(spb_ctx* c) {
+  u64* Jk; u8* Js; u64 nj;
+  PRIM(graph_junctions(c, 0, (c->T + 31) / 32, &Jk, &Js, &nj));
+  return graph_finish(c, Jk, Js, nj);
 }
 
 // Partitioned dedup, "links" form (single GPU, mostly-unique inputs): records -> 2^bb buckets -> one L2-resident scratch
@@ -1403,72 +1461,90 @@ int spb_mg_graph(spb_ctx* c, spb_counts* out) {
   return SPB_OK;
 }
 
-int spb_compact(spb_ctx* c, spb_counts* out) {
-  if (!c) return SPB_EINVAL;
-  if (c->state != 2) return fail(c, SPB_ESTATE, "spb_compact needs a freshly built DBG (state %d)", c->state);
-#ifndef SPB_EMU
-  CK(cudaSetDevice(c->device));
-#endif
-  const u64 T = c->T; const u32 k = c->k; const u32 nV = c->nV;
-  int tm;
+// =========================================================================================== compaction, in phases
+// One GPU runs the phases back to back over everything (spb_compact).  The sliced multi-GPU tail runs the per-vertex and
+// per-position phases on its own tiles / positions / NBPs and the contracted-graph phases (small) replicated, with the
+// host side gathering the short lists in between (spb_mg_slice_*).
+
+// K5/K6: init detection and pieces over the own tiles -> sorted lists of inits, piece starts, piece ends (local)
+static int cp_classify(spb_ctx* c, u32** init_l, u32** plo_l, u32** phi_l, u32* nI_out, u32* nP_out) {
+  const u32 nV = c->nV;
   GView g{c->vflags, c->Jk, c->Js, c->nJ, nV};
-  u32 *pl_nbr = 0, *pr_nbr = 0, *nxt = 0, *ptr[2] = {0, 0}, *acc[2] = {0, 0}, *root[2] = {0, 0}, *mnv[2] = {0, 0};
-  u8 *pl_side = 0, *pr_side = 0;
-  u32* ucount; ALLOC(ucount, u32, 4);
-  int cur = 0;
-  u32 ncyc = 0;
-  tm = t_begin(c);
-  for (int pass = 0; pass < 2; ++pass) {
-    // ---- K5: init detection, K6: pieces (8 vertices per thread), then one scan + compaction for the three lists
-    const u32 nT = (nV + 7) / 8;
-    u32 *cnt3, *off3; ALLOC(cnt3, u32, 3ull * nT + 1); ALLOC(off3, u32, 3ull * nT + 1);
-    SPB_LAUNCH(k_classify8, nblk(nT, TPB), TPB, c->stream, g, c->vflags, c->errflag);
-    SPB_LAUNCH(k_piece_flags8, nblk(nT, TPB), TPB, c->stream, c->vflags, nV, cnt3, nT);
-    u64 tot3 = 0;
-    PRIM(prim_scan_u32(c, cnt3, off3, 3ull * nT, &tot3));
-    u32 marks[2];
+  const u32 nTall = (nV + 7) / 8;
+  const u32 t_lo = c->sl.on ? c->sl.t_lo : 0u, t_hi = c->sl.on ? c->sl.t_hi : nTall;
+  const u32 f_lo = c->sl.on ? (t_lo ? t_lo - 1 : 0u) : 0u, f_hi = c->sl.on ? std::min(t_hi + 1, nTall) : nTall;   // piece flags: one tile of halo
+  const u32 c_lo = c->sl.on ? (f_lo ? f_lo - 1 : 0u) : 0u, c_hi = c->sl.on ? std::min(f_hi + 1, nTall) : nTall;   // init bits: one more
+  const u32 nT = t_hi - t_lo;
+  u32 *cnt3, *off3; ALLOC(cnt3, u32, 3ull * nT + 1); ALLOC(off3, u32, 3ull * nT + 1);
+  SPB_LAUNCH(k_classify8, nblk(c_hi - c_lo, TPB), TPB, c->stream, g, c->vflags, c->errflag, c_lo, c_hi);
+  SPB_LAUNCH(k_piece_flags8, nblk(f_hi - f_lo, TPB), TPB, c->stream, c->vflags, nV, cnt3, nT, f_lo, f_hi, t_lo, t_hi);
+  u64 tot3 = 0;
+  PRIM(prim_scan_u32(c, cnt3, off3, 3ull * nT, &tot3));
+  u32 marks[2] = {0, 0};
+  if (nT) {
     dev_copy(c, c->pinned, off3 + nT, 4); dev_copy(c, (u32*)c->pinned + 1, off3 + 2ull * nT, 4); dev_sync(c);
     memcpy(marks, c->pinned, 8);
-    c->nI = marks[0]; c->nP = marks[1] - marks[0];
-    if ((u64)c->nI + 2ull * c->nP != tot3) return fail(c, SPB_ECUDA, "internal: piece starts (%u) != piece ends (%llu)", c->nP, (unsigned long long)(tot3 - marks[1]));
-    ALLOC(c->init_list, u32, c->nI + 1); ALLOC(c->plo, u32, c->nP + 1); ALLOC(c->phi, u32, c->nP + 1);
-    SPB_LAUNCH(k_compact3, nblk(nT, TPB), TPB, c->stream, c->vflags, nV, off3, nT, c->nI, c->nP, c->init_list, c->plo, c->phi);
-    dfree(c, cnt3); dfree(c, off3);
-    const u32 nP = c->nP, nD = 2 * nP;
-    c->nD = nD;
-    ALLOC(pl_nbr, u32, nP + 1); ALLOC(pr_nbr, u32, nP + 1); ALLOC(pl_side, u8, nP + 1); ALLOC(pr_side, u8, nP + 1);
-    SPB_LAUNCH(k_piece_ends, nblk(nP, TPB), TPB, c->stream, g, c->plo, c->phi, nP, pl_nbr, pl_side, pr_nbr, pr_side, c->errflag);
-    // ---- K7/K8: darts + list ranking
-    ALLOC(nxt, u32, nD + 1);
-    SPB_LAUNCH(k_dart_next, nblk(nD, TPB), TPB, c->stream, c->vflags, c->plo, nP, pl_nbr, pl_side, pr_nbr, pr_side, nxt);
-    for (int i = 0; i < 2; ++i) { ALLOC(ptr[i], u32, nD + 1); ALLOC(acc[i], u32, nD + 1); ALLOC(root[i], u32, nD + 1); ALLOC(mnv[i], u32, nD + 1); }
-    cur = 0;
-    SPB_LAUNCH(k_rank_init, nblk(nD, TPB), TPB, c->stream, nxt, c->plo, c->phi, nD, ptr[0], acc[0], root[0], mnv[0]);
-    u32 rounds = 1; while ((1ull << rounds) < (u64)nD + 1) ++rounds;
-    ++rounds;
-    for (u32 r = 0; r < rounds && nD; ++r) {
-      SPB_LAUNCH(k_rank_jump, nblk(nD, TPB), TPB, c->stream, nD, ptr[cur], acc[cur], root[cur], mnv[cur], ptr[cur ^ 1], acc[cur ^ 1],
-                 root[cur ^ 1], mnv[cur ^ 1]);
-      cur ^= 1;
-    }
-    dev_memset(c, ucount, 0, 16);
-    SPB_LAUNCH(k_count_unresolved, nblk(nD, TPB), TPB, c->stream, ptr[cur], nD, ucount);
-    u32 unresolved = dread(c, ucount);
-    if (unresolved == 0) break;
-    if (pass == 1) return fail(c, SPB_ECUDA, "internal: %u darts unresolved after cycle cutting", unresolved);
-    // ---- K9: pure-cycle components: cut one edge per ring, then redo classification
-    SPB_LAUNCH(k_cycle_cut, nblk(nD, TPB), TPB, c->stream, g, c->vflags, c->Js, ptr[cur], mnv[cur], c->plo, nD, ucount + 1);
-    ncyc = dread(c, ucount + 1);
-    dfree(c, c->init_list); dfree(c, c->plo); dfree(c, c->phi); dfree(c, pl_nbr); dfree(c, pr_nbr); dfree(c, pl_side); dfree(c, pr_side);
-    dfree(c, nxt);
-    for (int i = 0; i < 2; ++i) { dfree(c, ptr[i]); dfree(c, acc[i]); dfree(c, root[i]); dfree(c, mnv[i]); }
   }
+  const u32 nI = marks[0], nP = marks[1] - marks[0];
+  if (!c->sl.on && (u64)nI + 2ull * nP != tot3) return fail(c, SPB_ECUDA, "internal: piece starts (%u) != piece ends (%llu)", nP, (unsigned long long)(tot3 - marks[1]));
+  const u32 nE = (u32)(tot3 - marks[1]);               // piece ends in the own tiles (a piece may cross a cut: starts != ends locally)
+  u32 *il, *pl, *ph; ALLOC(il, u32, nI + 1); ALLOC(pl, u32, nP + 1); ALLOC(ph, u32, nE + 1);
+  SPB_LAUNCH(k_compact3, nblk(nT, TPB), TPB, c->stream, c->vflags, nV, off3, nT, nI, nP, il, pl, ph, t_lo);
+  dfree(c, cnt3); dfree(c, off3);
+  *init_l = il; *plo_l = pl; *phi_l = ph; nI_out[0] = nI; nP_out[0] = nP; nP_out[1] = nE;
+  return 0;
+}
+
+static void cp_free_contracted(spb_ctx* c) {
+  dfree(c, c->pl_nbr); dfree(c, c->pr_nbr); dfree(c, c->pl_side); dfree(c, c->pr_side); dfree(c, c->nxt);
+  for (int i = 0; i < 2; ++i) { dfree(c, c->rk_ptr[i]); dfree(c, c->rk_acc[i]); dfree(c, c->rk_root[i]); dfree(c, c->rk_mnv[i]); }
+}
+
+// K7-K9 on the complete lists (c->init_list, c->plo, c->phi; c->nI, c->nP): piece ends, darts, list ranking.  *again = 1:
+// pure cycles were found and cut (pass 0 only) -- classification has to run again.
+static int cp_contract(spb_ctx* c, int pass, int* again) {
+  const u32 nV = c->nV;
+  GView g{c->vflags, c->Jk, c->Js, c->nJ, nV};
+  *again = 0;
+  const u32 nP = c->nP, nD = 2 * nP;
+  c->nD = nD;
+  ALLOC(c->pl_nbr, u32, nP + 1); ALLOC(c->pr_nbr, u32, nP + 1); ALLOC(c->pl_side, u8, nP + 1); ALLOC(c->pr_side, u8, nP + 1);
+  SPB_LAUNCH(k_piece_ends, nblk(nP, TPB), TPB, c->stream, g, c->plo, c->phi, nP, c->pl_nbr, c->pl_side, c->pr_nbr, c->pr_side, c->errflag);
+  ALLOC(c->nxt, u32, nD + 1);
+  SPB_LAUNCH(k_dart_next, nblk(nD, TPB), TPB, c->stream, c->vflags, c->plo, nP, c->pl_nbr, c->pl_side, c->pr_nbr, c->pr_side, c->nxt);
+  for (int i = 0; i < 2; ++i) { ALLOC(c->rk_ptr[i], u32, nD + 1); ALLOC(c->rk_acc[i], u32, nD + 1); ALLOC(c->rk_root[i], u32, nD + 1); ALLOC(c->rk_mnv[i], u32, nD + 1); }
+  int cur = 0;
+  SPB_LAUNCH(k_rank_init, nblk(nD, TPB), TPB, c->stream, c->nxt, c->plo, c->phi, nD, c->rk_ptr[0], c->rk_acc[0], c->rk_root[0], c->rk_mnv[0]);
+  u32 rounds = 1; while ((1ull << rounds) < (u64)nD + 1) ++rounds;
+  ++rounds;
+  for (u32 r = 0; r < rounds && nD; ++r) {
+    SPB_LAUNCH(k_rank_jump, nblk(nD, TPB), TPB, c->stream, nD, c->rk_ptr[cur], c->rk_acc[cur], c->rk_root[cur], c->rk_mnv[cur], c->rk_ptr[cur ^ 1],
+               c->rk_acc[cur ^ 1], c->rk_root[cur ^ 1], c->rk_mnv[cur ^ 1]);
+    cur ^= 1;
+  }
+  c->rk_cur = cur;
+  u32* ucount; ALLOC(ucount, u32, 4);
+  dev_memset(c, ucount, 0, 16);
+  SPB_LAUNCH(k_count_unresolved, nblk(nD, TPB), TPB, c->stream, c->rk_ptr[cur], nD, ucount);
+  const u32 unresolved = dread(c, ucount);
+  if (unresolved == 0) { dfree(c, ucount); return 0; }
+  if (pass == 1) { dfree(c, ucount); return fail(c, SPB_ECUDA, "internal: %u darts unresolved after cycle cutting", unresolved); }
+  // ---- K9: pure-cycle components: cut one edge per ring, then redo the classification
+  SPB_LAUNCH(k_cycle_cut, nblk(nD, TPB), TPB, c->stream, g, c->vflags, c->Js, c->rk_ptr[cur], c->rk_mnv[cur], c->plo, nD, ucount + 1);
+  c->ncyc = dread(c, ucount + 1);
   dfree(c, ucount);
-  c->cnt.n_cycle_comp = ncyc;
+  dfree(c, c->init_list); dfree(c, c->plo); dfree(c, c->phi);
+  cp_free_contracted(c);
+  *again = 1;
+  return 0;
+}
+
+// K10: raw NBP table, lengths and output offsets (replicated; small)
+static int cp_nbp_table(spb_ctx* c, u64* totv_out, u64* tots_out) {
+  const u32 k = c->k; const u32 nV = c->nV;
+  GView g{c->vflags, c->Jk, c->Js, c->nJ, nV};
   const u32 nP = c->nP, nD = c->nD, nI = c->nI;
-  t_end(c, tm, "classify_rank_ms");
-  // ---- K10: NBP table
-  tm = t_begin(c);
+  const int cur = c->rk_cur;
   u32* ideg; ALLOC(ideg, u32, nI + 1); ALLOC(c->ibase, u32, nI + 1);
   SPB_LAUNCH(k_init_degrees, nblk(nI, TPB), TPB, c->stream, g, c->init_list, nI, ideg);
   u64 nN64 = 0;
@@ -1481,8 +1557,9 @@ int spb_compact(spb_ctx* c, spb_counts* out) {
   u32* head_nbp; ALLOC(head_nbp, u32, nD + 1); dev_memset(c, head_nbp, 0xFF, (nD + 1) * 4ull);
   ALLOC(c->dart_nbp, u32, nD + 1);
   SPB_LAUNCH(k_nbp_heads, nblk(nI, TPB), TPB, c->stream, g, c->vflags, c->init_list, c->ibase, nI, c->plo, nP, t, head_nbp);
-  SPB_LAUNCH(k_dart_finish, nblk(nD, TPB), TPB, c->stream, nxt, root[cur], acc[cur], c->plo, c->phi, pl_nbr, pl_side, pr_nbr, pr_side,
+  SPB_LAUNCH(k_dart_finish, nblk(nD, TPB), TPB, c->stream, c->nxt, c->rk_root[cur], c->rk_acc[cur], c->plo, c->phi, c->pl_nbr, c->pl_side, c->pr_nbr, c->pr_side,
              head_nbp, nD, c->dart_nbp, t);
+  dfree(c, head_nbp);
   u64 *vlen, *slen; ALLOC(vlen, u64, nN + 1); ALLOC(slen, u64, nN + 1);
   ALLOC(c->voff, u64, nN + 1); ALLOC(c->soff, u64, nN + 1);
   SPB_LAUNCH(k_nbp_lengths, nblk(nN, TPB), TPB, c->stream, t, nN, k, vlen, slen);
@@ -1491,110 +1568,385 @@ int spb_compact(spb_ctx* c, spb_counts* out) {
   PRIM(prim_scan_u64(c, slen, c->soff, nN, &tots));
   dev_copy(c, c->voff + nN, &totv, 8); dev_copy(c, c->soff + nN, &tots, 8); dev_sync(c);
   dfree(c, vlen); dfree(c, slen);
-  // ---- K11/K12: NBP vertex lists + sequences
-  ALLOC(c->verts, u32, totv + 1); ALLOC(c->seqs, u8, tots + 1);
-  ALLOC(c->vnbp, u32, (u64)nV + 1); dev_memset(c, c->vnbp, 0xFF, ((u64)nV + 1) * 4);
-  SPB_LAUNCH(k_emit_ends, nblk((u64)nN * 32, TPB), TPB, c->stream, t, nN, k, T, c->F, c->R, c->v2pos, c->voff, c->soff, c->verts, c->seqs);
+  *totv_out = totv; *tots_out = tots;
+  return 0;
+}
+
+// K11/K12: vertex lists + sequences of the own NBPs [n_lo, n_hi), vertex -> NBP map of the own vertices
+static int cp_emit(spb_ctx* c, u64 totv, u64 tots) {
+  const u64 T = c->T; const u32 k = c->k; const u32 nV = c->nV;
+  const u32 nP = c->nP, nD = c->nD, nN = c->nN;
+  const int cur = c->rk_cur;
+  NbpTab& t = c->nt;
+  spb_ctx::Slice& sl = c->sl;
+  if (sl.on) {                                         // NBP ranges with (nearly) equal numbers of emitted vertices
+    u32* cuts; ALLOC(cuts, u32, sl.G + 2);
+    if (sl.G + 1 > 64) return fail(c, SPB_EINVAL, "more than 63 ranks");
+    SPB_LAUNCH(k_nbp_cuts, 1, 64, c->stream, c->voff, nN, sl.G, cuts);
+    dev_copy(c, c->pinned, cuts + sl.rank, 8); dev_sync(c);
+    u32 nc[2]; memcpy(nc, c->pinned, 8);
+    sl.n_lo = nc[0]; sl.n_hi = nc[1];
+    dfree(c, cuts);
+    dev_copy(c, c->pinned, c->voff + sl.n_lo, 8); dev_copy(c, c->pinned + 1, c->voff + sl.n_hi, 8);
+    dev_copy(c, c->pinned + 2, c->soff + sl.n_lo, 8); dev_copy(c, c->pinned + 3, c->soff + sl.n_hi, 8); dev_sync(c);
+    sl.vert_lo = c->pinned[0]; sl.vert_n = c->pinned[1] - c->pinned[0]; sl.seq_lo = c->pinned[2]; sl.seq_n = c->pinned[3] - c->pinned[2];
+  } else { sl.n_lo = 0; sl.n_hi = nN; sl.vert_lo = 0; sl.vert_n = totv; sl.seq_lo = 0; sl.seq_n = tots; }
+  const u32 n_lo = sl.n_lo, n_hi = sl.n_hi;
+  ALLOC(c->verts, u32, sl.vert_n + 1); ALLOC(c->seqs_base, u8, sl.seq_n + 16);
+  c->seqs = c->seqs_base + (sl.seq_lo & 3);            // word-aligned stores of the sequence kernels keep the phase of the global offsets
+  u32* verts = c->verts - sl.vert_lo; u8* seqs = c->seqs - sl.seq_lo;      // addressed with the global offsets
+  u32* vnbp_w = nullptr;
+  if (!sl.on) { ALLOC(c->vnbp, u32, (u64)nV + 1); dev_memset(c, c->vnbp, 0xFF, ((u64)nV + 1) * 4); vnbp_w = c->vnbp; }
+  const VPos vp = vpos_view(c);
+  SPB_LAUNCH(k_emit_ends, nblk((u64)(n_hi - n_lo) * 32, TPB), TPB, c->stream, t, n_lo, n_hi, k, T, c->F, c->R, vp, c->voff, c->soff, verts, seqs);
   u32 *nch, *choff; ALLOC(nch, u32, nD + 1); ALLOC(choff, u32, nD + 1);
-  SPB_LAUNCH(k_dart_chunks, nblk(nD, TPB), TPB, c->stream, c->plo, c->phi, nD, nch);
+  SPB_LAUNCH(k_dart_chunks, nblk(nD, TPB), TPB, c->stream, c->plo, c->phi, nD, c->dart_nbp, n_lo, n_hi, nch);
   u64 nchunks = 0;
   PRIM(prim_scan_u32(c, nch, choff, nD, &nchunks));
   if (nchunks >= (1ull << 31)) return fail(c, SPB_EINVAL, "input too large for 32-bit dart offsets");
   ChunkParams* cpar; ALLOC(cpar, ChunkParams, nchunks + 1);
-  SPB_LAUNCH(k_chunk_table, nblk(nchunks, TPB), TPB, c->stream, (u32)nchunks, choff, nD, c->plo, c->phi, c->dart_nbp, acc[cur], k, T, c->v2pos,
+  SPB_LAUNCH(k_chunk_table, nblk(nchunks, TPB), TPB, c->stream, (u32)nchunks, choff, nD, c->plo, c->phi, c->dart_nbp, c->rk_acc[cur], k, T, vp,
              c->voff, c->soff, cpar);
-  { const int tq_ = t_begin(c); SPB_LAUNCH(k_emit_darts, nchunks, 256, c->stream, cpar, c->F, c->R, c->verts, c->seqs, c->vnbp); t_end(c, tq_, "k_emit_darts_ms"); }
+  { const int tq_ = t_begin(c); SPB_LAUNCH(k_emit_darts, nchunks, 256, c->stream, cpar, c->F, c->R, verts, seqs, vnbp_w); t_end(c, tq_, "k_emit_darts_ms"); }
   dfree(c, cpar);
-  SPB_LAUNCH(k_emit_short, std::min<u64>(nblk((u64)nD * 32, 256), 148 * 32), 256, c->stream, nD, c->plo, c->phi, c->dart_nbp, acc[cur], k, T,
-             c->F, c->R, c->v2pos, c->voff, c->soff, c->verts, c->seqs, c->vnbp);
-  dfree(c, nch); dfree(c, choff); dfree(c, head_nbp); dfree(c, nxt);
-  dfree(c, pl_nbr); dfree(c, pr_nbr); dfree(c, pl_side); dfree(c, pr_side);
-  for (int i = 0; i < 2; ++i) { dfree(c, ptr[i]); dfree(c, acc[i]); dfree(c, root[i]); dfree(c, mnv[i]); }
-  t_end(c, tm, "emit_ms");
-  // ---- K13: origins
-  tm = t_begin(c);
+  SPB_LAUNCH(k_emit_short, std::min<u64>(nblk((u64)nD * 32, 256), 148 * 32), 256, c->stream, nD, c->plo, c->phi, c->dart_nbp, c->rk_acc[cur], k, T,
+             c->F, c->R, vp, c->voff, c->soff, verts, seqs, vnbp_w, n_lo, n_hi);
+  dfree(c, nch); dfree(c, choff);
+  if (sl.on) {                                         // vertex -> NBP map of the own tiles (+ one tile: see k_piece_flags8)
+    const VNbp vn = vnbp_view(c);
+    ALLOC(c->vnbp, u32, (u64)nV + 1);                  // addressed by the global vertex id; only [v_lo, v_hi) of it is touched
+    SPB_LAUNCH(k_fill_vnbp, nblk(nblk(vn.v_hi - vn.v_lo, 1024) * 32, TPB), TPB, c->stream, c->plo, c->phi, nP, c->dart_nbp, vn.v_lo, vn.v_hi, c->vnbp);
+  }
+  cp_free_contracted(c);
+  return 0;
+}
+
+// K13, first half: (NBP, sequence) / (init, sequence) pairs of the own positions -> c->op, c->mp (unsorted), c->has01
+static int cp_origin_pairs(spb_ctx* c) {
+  const u64 T = c->T;
+  const u32 nN = c->nN, nV = c->nV;
+  u64* counts; ALLOC(counts, u64, 4);
+  ALLOC(c->has01, u8, 2ull * c->n_seq + 8);
+  u32 sb = 1; while ((1ull << sb) <= c->n_seq) ++sb;          // keys = (NBP or vertex id) << sb | sequence index
+  (void)nN; (void)nV;
+  const u64 w_lo = c->sl.on ? c->sl.pos_lo / 32 : 0, w_hi = c->sl.on ? (c->sl.pos_hi > c->sl.pos_lo ? (c->sl.pos_hi + 31) / 32 : w_lo) : (T + 31) / 32;
+  const u64 npos = 32 * (w_hi - w_lo);
+  u64 ocap = std::max<u64>(4096, npos / 4), mcap = std::max<u64>(4096, npos / 4);
+  u64 *op = 0, *mp = 0; u64 no = 0, nm = 0;
+  const VNbp vn = vnbp_view(c);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    ALLOC(op, u64, ocap + c->n_seq + 1); ALLOC(mp, u64, mcap + c->n_seq + 1);      // room for the quirk entries (one per sequence at most)
+    dev_memset(c, counts, 0, 32); dev_memset(c, c->has01, 0, 2ull * c->n_seq + 8);
+    { const int tq_ = t_begin(c); SPB_LAUNCH(k_origin_pairs, gs_grid(npos), TPB, c->stream, c->sp, T, w_lo, w_hi, c->fbits, vn, c->vflags, c->seq_off, c->n_seq, op, counts, ocap, mp,
+               counts + 1, mcap, c->has01, sb); t_end(c, tq_, "k_origin_pairs_ms"); }
+    dev_copy(c, c->pinned, counts, 16); dev_sync(c);
+    no = c->pinned[0]; nm = c->pinned[1];
+    if (no <= ocap && nm <= mcap) break;
+    dfree(c, op); dfree(c, mp); ocap = std::max(ocap, no); mcap = std::max(mcap, nm);
+  }
+  dfree(c, counts);
+  c->op = op; c->mp = mp; c->n_op = no; c->n_mp = nm; c->op_cap = ocap + c->n_seq; c->mp_cap = mcap + c->n_seq;
+  return 0;
+}
+
+// K13, second half (replicated): all pairs -> leading-zero quirk, sort + unique, per-NBP origin lists.  op / mp have room
+// for n_seq more entries; takes ownership of op, mp, has01.
+static int cp_origins_finish(spb_ctx* c, u64* op, u64 no, u64 ocap, u64* mp, u64 nm, u64 mcap, u8* has01) {
+  const u32 nN = c->nN, nV = c->nV;
+  NbpTab& t = c->nt;
+  u32 sb = 1; while ((1ull << sb) <= c->n_seq) ++sb;
+  u32 ob = sb + 1; while (ob < 64 && (1ull << (ob - sb)) <= (u64)nN) ++ob;
+  u32 mb = sb + 1; while (mb < 64 && (1ull << (mb - sb)) <= (u64)nV) ++mb;
   {
     u64* counts; ALLOC(counts, u64, 4);
-    u8* has01; ALLOC(has01, u8, 2ull * c->n_seq + 8);
-    u32 sb = 1; while ((1ull << sb) <= c->n_seq) ++sb;          // keys = (NBP or vertex id) << sb | sequence index
-    u32 ob = sb + 1; while (ob < 64 && (1ull << (ob - sb)) <= (u64)nN) ++ob;
-    u32 mb = sb + 1; while (mb < 64 && (1ull << (mb - sb)) <= (u64)nV) ++mb;
-    u64 ocap = std::max<u64>(4096, c->n_inst / 4), mcap = std::max<u64>(4096, c->n_inst / 4);
-    u64 *op = 0, *mp = 0; u64 no = 0, nm = 0;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-      ALLOC(op, u64, ocap + 1); ALLOC(mp, u64, mcap + 1);
-      dev_memset(c, counts, 0, 32); dev_memset(c, has01, 0, 2ull * c->n_seq + 8);
-      { const int tq_ = t_begin(c); SPB_LAUNCH(k_origin_pairs, gs_grid(T), TPB, c->stream, c->sp, T, c->fbits, c->vnbp, c->vflags, c->seq_off, c->n_seq, op, counts, ocap, mp,
-                 counts + 1, mcap, has01, sb); t_end(c, tq_, "k_origin_pairs_ms"); }
-      SPB_LAUNCH(k_origin_quirk, nblk(c->n_seq, TPB), TPB, c->stream, has01, c->n_seq, c->vnbp, c->vflags, op, counts, ocap, mp, counts + 1,
-                 mcap, sb);
-      no = dread(c, counts); nm = dread(c, counts + 1);
-      if (no <= ocap && nm <= mcap) break;
-      dfree(c, op); dfree(c, mp); ocap = std::max(ocap, no); mcap = std::max(mcap, nm);
-    }
-    dfree(c, counts); dfree(c, has01);
-    u64* tmp; u8* nopay = nullptr;
-    ALLOC(tmp, u64, std::max(no, nm) + 1);
-    PRIM(prim_sort_u64(c, op, tmp, no, ob));
-    PRIM(prim_sort_u64(c, mp, tmp, nm, mb));
-    dfree(c, tmp);
-    PRIM(unique_sorted(c, op, nopay, no, &c->nO));
-    PRIM(unique_sorted(c, mp, nopay, nm, &c->nM));
-    if (!op) ALLOC(op, u64, 1);
-    if (!mp) ALLOC(mp, u64, 1);
-    u64* ocnt; ALLOC(ocnt, u64, nN + 1); ALLOC(c->ooff, u64, nN + 1);
-    SPB_LAUNCH(k_nbp_origins, nblk(nN, TPB), TPB, c->stream, t, nN, c->dart_nbp, op, c->nO, mp, c->nM, sb, (const u64*)nullptr, ocnt, (u32*)nullptr);
-    u64 toto = 0;
-    PRIM(prim_scan_u64(c, ocnt, c->ooff, nN, &toto));
-    dev_copy(c, c->ooff + nN, &toto, 8); dev_sync(c);
-    ALLOC(c->origins, u32, toto + 1);
-    SPB_LAUNCH(k_nbp_origins, nblk(nN, TPB), TPB, c->stream, t, nN, c->dart_nbp, op, c->nO, mp, c->nM, sb, c->ooff, ocnt, c->origins);
-    dfree(c, ocnt); dfree(c, op); dfree(c, mp);
-    c->cnt.n_origin_pairs = toto;
+    memcpy(c->pinned, &no, 8); memcpy(c->pinned + 1, &nm, 8);
+    dev_copy(c, counts, c->pinned, 16);
+    SPB_LAUNCH(k_origin_quirk, nblk(c->n_seq, TPB), TPB, c->stream, has01, c->n_seq, vnbp_view(c), c->vflags, op, counts, ocap, mp, counts + 1, mcap, sb);
+    dev_copy(c, c->pinned + 2, counts, 16); dev_sync(c);
+    no = c->pinned[2]; nm = c->pinned[3];
+    dfree(c, counts);
+    if (no > ocap || nm > mcap) return fail(c, SPB_ECUDA, "internal: origin pair lists too small for the quirk entries");
+  }
+  dfree(c, has01);
+  u64* tmp; u8* nopay = nullptr;
+  ALLOC(tmp, u64, std::max(no, nm) + 1);
+  PRIM(prim_sort_u64(c, op, tmp, no, ob));
+  PRIM(prim_sort_u64(c, mp, tmp, nm, mb));
+  dfree(c, tmp);
+  PRIM(unique_sorted(c, op, nopay, no, &c->nO));
+  PRIM(unique_sorted(c, mp, nopay, nm, &c->nM));
+  if (!op) ALLOC(op, u64, 1);
+  if (!mp) ALLOC(mp, u64, 1);
+  u64* ocnt; ALLOC(ocnt, u64, nN + 1); ALLOC(c->ooff, u64, nN + 1);
+  SPB_LAUNCH(k_nbp_origins, nblk(nN, TPB), TPB, c->stream, t, nN, c->dart_nbp, op, c->nO, mp, c->nM, sb, (const u64*)nullptr, ocnt, (u32*)nullptr);
+  u64 toto = 0;
+  PRIM(prim_scan_u64(c, ocnt, c->ooff, nN, &toto));
+  dev_copy(c, c->ooff + nN, &toto, 8); dev_sync(c);
+  ALLOC(c->origins, u32, toto + 1);
+  SPB_LAUNCH(k_nbp_origins, nblk(nN, TPB), TPB, c->stream, t, nN, c->dart_nbp, op, c->nO, mp, c->nM, sb, c->ooff, ocnt, c->origins);
+  dfree(c, ocnt); dfree(c, op); dfree(c, mp);
+  c->cnt.n_origin_pairs = toto;
+  return 0;
+}
+
+// K14: connected components (replicated)
+static int cp_components(spb_ctx* c) {
+  const u32 nI = c->nI, nN = c->nN, nP = c->nP;
+  NbpTab& t = c->nt;
+  ALLOC(c->parent, u32, nI + 1); ALLOC(c->label_of_root, u32, nI + 1);
+  u32* cmin; ALLOC(cmin, u32, nI + 1); dev_memset(c, cmin, 0xFF, (nI + 1) * 4ull);
+  u64 *rk, *rk2; ALLOC(rk, u64, nI + 1); ALLOC(rk2, u64, nI + 1);
+  u32* nroots; ALLOC(nroots, u32, 4); dev_memset(c, nroots, 0, 16);
+  SPB_LAUNCH(k_uf_init, nblk(nI, TPB), TPB, c->stream, c->parent, nI);
+  SPB_LAUNCH(k_uf_union, nblk(nN, TPB), TPB, c->stream, t, nN, c->init_list, nI, c->parent);
+  SPB_LAUNCH(k_comp_min_init, nblk(nI, TPB), TPB, c->stream, c->init_list, nI, c->parent, cmin);
+  SPB_LAUNCH(k_comp_min_piece, nblk(nP, TPB), TPB, c->stream, c->plo, nP, c->dart_nbp, t, c->init_list, nI, c->parent, cmin);
+  SPB_LAUNCH(k_comp_roots, nblk(nI, TPB), TPB, c->stream, c->parent, cmin, nI, rk, nroots);
+  u32 nr = dread(c, nroots);
+  PRIM(prim_sort_u64(c, rk, rk2, nr));
+  SPB_LAUNCH(k_comp_labels, nblk(nr, TPB), TPB, c->stream, rk, nr, c->label_of_root);
+  ALLOC(c->nbp_comp, int32_t, nN + 1);
+  SPB_LAUNCH(k_nbp_comp, nblk(nN, TPB), TPB, c->stream, t, nN, c->init_list, nI, c->parent, c->label_of_root, c->nbp_comp);
+  dfree(c, cmin); dfree(c, rk); dfree(c, rk2); dfree(c, nroots);
+  c->cnt.n_comp = nr;
+  return 0;
+}
+
+int spb_compact(spb_ctx* c, spb_counts* out) {
+  if (!c) return SPB_EINVAL;
+  if (c->state != 2) return fail(c, SPB_ESTATE, "spb_compact needs a freshly built DBG (state %d)", c->state);
+  if (c->sl.on) return fail(c, SPB_ESTATE, "spb_compact: the DBG of this context is sliced over several ranks (spb_mg_slice_* / spb_mg_complete)");
+#ifndef SPB_EMU
+  CK(cudaSetDevice(c->device));
+#endif
+  int tm = t_begin(c);
+  c->ncyc = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    u32 nI[1], nP[2];
+    PRIM(cp_classify(c, &c->init_list, &c->plo, &c->phi, nI, nP));
+    c->nI = nI[0]; c->nP = nP[0];
+    int again = 0;
+    PRIM(cp_contract(c, pass, &again));
+    if (!again) break;
+  }
+  c->cnt.n_cycle_comp = c->ncyc;
+  t_end(c, tm, "classify_rank_ms");
+  tm = t_begin(c);
+  u64 totv = 0, tots = 0;
+  PRIM(cp_nbp_table(c, &totv, &tots));
+  PRIM(cp_emit(c, totv, tots));
+  t_end(c, tm, "emit_ms");
+  tm = t_begin(c);
+  PRIM(cp_origin_pairs(c));
+  {
+    u64 *op = c->op, *mp = c->mp; u8* h = c->has01;
+    c->op = c->mp = nullptr; c->has01 = nullptr;
+    PRIM(cp_origins_finish(c, op, c->n_op, c->op_cap, mp, c->n_mp, c->mp_cap, h));
   }
   t_end(c, tm, "origins_ms");
-  // ---- K14: connected components
   tm = t_begin(c);
-  {
-    ALLOC(c->parent, u32, nI + 1); ALLOC(c->label_of_root, u32, nI + 1);
-    u32* cmin; ALLOC(cmin, u32, nI + 1); dev_memset(c, cmin, 0xFF, (nI + 1) * 4ull);
-    u64 *rk, *rk2; ALLOC(rk, u64, nI + 1); ALLOC(rk2, u64, nI + 1);
-    u32* nroots; ALLOC(nroots, u32, 4); dev_memset(c, nroots, 0, 16);
-    SPB_LAUNCH(k_uf_init, nblk(nI, TPB), TPB, c->stream, c->parent, nI);
-    SPB_LAUNCH(k_uf_union, nblk(nN, TPB), TPB, c->stream, t, nN, c->init_list, nI, c->parent);
-    SPB_LAUNCH(k_comp_min_init, nblk(nI, TPB), TPB, c->stream, c->init_list, nI, c->parent, cmin);
-    SPB_LAUNCH(k_comp_min_piece, nblk(nP, TPB), TPB, c->stream, c->plo, nP, c->dart_nbp, t, c->init_list, nI, c->parent, cmin);
-    SPB_LAUNCH(k_comp_roots, nblk(nI, TPB), TPB, c->stream, c->parent, cmin, nI, rk, nroots);
-    u32 nr = dread(c, nroots);
-    PRIM(prim_sort_u64(c, rk, rk2, nr));
-    SPB_LAUNCH(k_comp_labels, nblk(nr, TPB), TPB, c->stream, rk, nr, c->label_of_root);
-    ALLOC(c->nbp_comp, int32_t, nN + 1);
-    SPB_LAUNCH(k_nbp_comp, nblk(nN, TPB), TPB, c->stream, t, nN, c->init_list, nI, c->parent, c->label_of_root, c->nbp_comp);
-    dfree(c, cmin); dfree(c, rk); dfree(c, rk2); dfree(c, nroots);
-    c->cnt.n_comp = nr;
-  }
+  PRIM(cp_components(c));
   t_end(c, tm, "components_ms");
   int r = check_err(c, "spb_compact");
   if (r) return r;
-  c->cnt.n_inits = nI; c->cnt.n_pieces = nP; c->cnt.n_nbp = nN; c->cnt.nbp_vertices = totv; c->cnt.nbp_bases = tots;
+  c->cnt.n_inits = c->nI; c->cnt.n_pieces = c->nP; c->cnt.n_nbp = c->nN; c->cnt.nbp_vertices = totv; c->cnt.nbp_bases = tots;
   c->state = 3;
+  if (out) *out = c->cnt;
+  return SPB_OK;
+}
+
+// =========================================================================================== sliced multi-GPU tail
+// After the dedup ("part" protocol with all links on every rank: fbits / obits / the links in mg_seen are complete
+// everywhere) nothing of size N_inst is exchanged any more.  Rank r computes the vertex ids, junction entries and origin
+// pairs of ITS positions, the flags / piece lists / edge rows / vertex -> NBP map of ITS vertices (first appearances of
+// its positions, cut at multiples of 8) and the vertex lists and sequences of ITS NBPs (id ranges with equal shares of
+// the output); the short lists (junction entries, inits, piece bounds, origin pairs) are all-gathered by the host side
+// and the contracted graph (pieces, darts, list ranking, NBP table, origin sets, components) is computed by every rank.
+// The few entries a sliced pass needs from another rank's range are recomputed from the replicated bitmaps (VPos, VidAt,
+// VNbp in spb_kernels.cuh).  spb_mg_complete recomputes the sliced passes over the whole input on this rank (no
+// communication) so that every single-GPU getter works; spb_mg_shard hands out the local parts.
+static void free_graph_results(spb_ctx* c) {
+  dfree(c, c->Jk); dfree(c, c->Js); dfree(c, c->edges); dfree(c, c->seqlim);
+  dfree(c, c->init_list); dfree(c, c->ibase); dfree(c, c->plo); dfree(c, c->phi); dfree(c, c->dart_nbp); dfree(c, c->vnbp);
+  dfree(c, c->parent); dfree(c, c->label_of_root); dfree(c, c->nbp_comp);
+  dfree(c, c->nt.a); dfree(c, c->nt.b); dfree(c, c->nt.L); dfree(c, c->nt.head); dfree(c, c->nt.last); dfree(c, c->nt.aside); dfree(c, c->nt.bside); dfree(c, c->nt.cyc);
+  dfree(c, c->voff); dfree(c, c->soff); dfree(c, c->ooff); dfree(c, c->verts); dfree(c, c->seqs_base); c->seqs = nullptr; dfree(c, c->origins);
+  dfree(c, c->op); dfree(c, c->mp); dfree(c, c->has01);
+  cp_free_contracted(c);
+}
+
+int spb_mg_slice_ids(spb_ctx* c, uint32_t rank, uint32_t n_ranks) {
+  if (!c || !n_ranks || rank >= n_ranks) return SPB_EINVAL;
+  if (c->state != 1 || !c->sp || !c->mg_seen) return fail(c, SPB_ESTATE, "spb_mg_slice_ids needs spb_mg_apply_links over all positions first");
+  stats_reset(c); stat_set(c, "multi_gpu", 1);
+  uint64_t S = 0; spb_mg_slice(c, n_ranks, &S);
+  spb_ctx::Slice& sl = c->sl;
+  sl = spb_ctx::Slice();
+  sl.rank = rank; sl.G = n_ranks;
+  sl.pos_lo = std::min<u64>((u64)rank * S, c->T); sl.pos_hi = std::min<u64>((u64)(rank + 1) * S, c->T);
+  sl.ids_lo = sl.pos_lo ? sl.pos_lo - 1 : 0; sl.ids_hi = std::min<u64>(sl.pos_hi + 1, c->T);
+  PRIM(dd_ids(c, sl.ids_lo, sl.ids_hi, nullptr, 1, c->mg_seen, 0, sl.pos_lo, sl.pos_hi));
+  // vertices of the slice: ranks of its first and of the next slice's first position (S is a multiple of 256)
+  u32 vf[2];
+  for (int i = 0; i < 2; ++i) {
+    const u64 p = i ? sl.pos_hi : sl.pos_lo;
+    if (p >= c->T) { vf[i] = c->nV; continue; }
+    dev_copy(c, (u32*)c->pinned + i, c->blkoff + (p >> 8), 4);
+  }
+  dev_sync(c);
+  for (int i = 0; i < 2; ++i) { const u64 p = i ? sl.pos_hi : sl.pos_lo; if (p < c->T) vf[i] = ((u32*)c->pinned)[i]; }
+  sl.v_lo = vf[0]; sl.v_hi = vf[1];
+  // own tiles of 8 vertices: cut below the first vertex of every slice (an empty slice at the end of the input owns nothing)
+  const u32 nTall = (c->nV + 7) / 8;
+  sl.t_lo = sl.pos_lo >= c->T ? nTall : sl.v_lo >> 3; sl.t_hi = sl.pos_hi >= c->T ? nTall : sl.v_hi >> 3;
+  sl.on = true;
+  return check_err(c, "spb_mg_slice_ids");
+}
+
+int spb_mg_slice_junctions(spb_ctx* c, uint64_t* n, void** jk_dev, void** js_dev) {
+  if (!c || !n || !jk_dev || !js_dev) return SPB_EINVAL;
+  if (c->state != 1 || !c->sl.on) return fail(c, SPB_ESTATE, "spb_mg_slice_junctions out of order");
+  u64* Jk; u8* Js; u64 nj;
+  dfree(c, c->Jk); dfree(c, c->Js);
+  const u64 w_lo = c->sl.pos_lo / 32, w_hi = c->sl.pos_hi > c->sl.pos_lo ? (c->sl.pos_hi + 31) / 32 : w_lo;   // slices start at multiples of 1024
+  PRIM(graph_junctions(c, w_lo, w_hi, &Jk, &Js, &nj));
+  c->Jk = Jk; c->Js = Js;                              // kept until spb_mg_slice_graph replaces them by the complete list
+  *n = nj; *jk_dev = Jk; *js_dev = Js;
+  return check_err(c, "spb_mg_slice_junctions");
+}
+
+int spb_mg_slice_graph(spb_ctx* c, const uint64_t* jk_all, const uint8_t* js_all, uint64_t n_all, uint64_t* n_edges_local) {
+  if (!c) return SPB_EINVAL;
+  if (c->state != 1 || !c->sl.on) return fail(c, SPB_ESTATE, "spb_mg_slice_graph out of order");
+  u64* Jk; u8* Js;
+  ALLOC(Jk, u64, n_all + 1); ALLOC(Js, u8, n_all + 1);
+  dev_copy(c, Jk, jk_all, 8 * n_all); dev_copy(c, Js, js_all, n_all);
+  dfree(c, c->Jk); dfree(c, c->Js);
+  PRIM(graph_finish(c, Jk, Js, n_all));
+  if (n_edges_local) *n_edges_local = c->sl.edge_n;
+  int r = check_err(c, "spb_mg_slice_graph");
+  if (r) return r;
+  c->state = 2;
+  c->ncyc = 0;
+  return SPB_OK;
+}
+
+int spb_mg_slice_classify(spb_ctx* c, uint32_t* n_init, uint32_t* n_start, uint32_t* n_end, void** init_dev, void** plo_dev, void** phi_dev) {
+  if (!c || !n_init || !n_start || !n_end) return SPB_EINVAL;
+  if (c->state != 2 || !c->sl.on) return fail(c, SPB_ESTATE, "spb_mg_slice_classify out of order");
+  dfree(c, c->init_list); dfree(c, c->plo); dfree(c, c->phi);
+  u32 nI[1], nP[2];
+  PRIM(cp_classify(c, &c->init_list, &c->plo, &c->phi, nI, nP));      // local lists, replaced by the complete ones in spb_mg_slice_contract
+  *n_init = nI[0]; *n_start = nP[0]; *n_end = nP[1];
+  *init_dev = c->init_list; *plo_dev = c->plo; *phi_dev = c->phi;
+  return check_err(c, "spb_mg_slice_classify");
+}
+
+int spb_mg_slice_contract(spb_ctx* c, const uint32_t* init_all, uint32_t n_init, const uint32_t* plo_all, const uint32_t* phi_all, uint32_t n_piece,
+                          uint64_t n_edges_total, int pass, int* again) {
+  if (!c || !again) return SPB_EINVAL;
+  if (c->state != 2 || !c->sl.on) return fail(c, SPB_ESTATE, "spb_mg_slice_contract out of order");
+  u32 *il, *pl, *ph;
+  ALLOC(il, u32, n_init + 1); ALLOC(pl, u32, n_piece + 1); ALLOC(ph, u32, n_piece + 1);
+  dev_copy(c, il, init_all, 4ull * n_init); dev_copy(c, pl, plo_all, 4ull * n_piece); dev_copy(c, ph, phi_all, 4ull * n_piece);
+  dfree(c, c->init_list); dfree(c, c->plo); dfree(c, c->phi);
+  c->init_list = il; c->plo = pl; c->phi = ph; c->nI = n_init; c->nP = n_piece;
+  c->cnt.n_edges = n_edges_total;
+  SPB_LAUNCH(k_mark_inits, nblk(n_init, TPB), TPB, c->stream, c->init_list, n_init, c->vflags);       // the init bit is read at arbitrary vertices
+  PRIM(cp_contract(c, pass, again));
+  return check_err(c, "spb_mg_slice_contract");
+}
+
+int spb_mg_slice_emit(spb_ctx* c, uint64_t* n_op, void** op_dev, uint64_t* n_mp, void** mp_dev, void** has01_dev) {
+  if (!c || !n_op || !n_mp) return SPB_EINVAL;
+  if (c->state != 2 || !c->sl.on || !c->nxt) return fail(c, SPB_ESTATE, "spb_mg_slice_emit out of order");
+  c->cnt.n_cycle_comp = c->ncyc;
+  u64 totv = 0, tots = 0;
+  PRIM(cp_nbp_table(c, &totv, &tots));
+  PRIM(cp_emit(c, totv, tots));
+  c->cnt.n_inits = c->nI; c->cnt.n_pieces = c->nP; c->cnt.n_nbp = c->nN; c->cnt.nbp_vertices = totv; c->cnt.nbp_bases = tots;
+  PRIM(cp_origin_pairs(c));
+  *n_op = c->n_op; *n_mp = c->n_mp;
+  *op_dev = c->op; *mp_dev = c->mp; *has01_dev = c->has01;
+  return check_err(c, "spb_mg_slice_emit");
+}
+
+int spb_mg_slice_finish(spb_ctx* c, const uint64_t* op_all, uint64_t n_op, const uint64_t* mp_all, uint64_t n_mp, const uint8_t* has01_any, spb_counts* out) {
+  if (!c) return SPB_EINVAL;
+  if (c->state != 2 || !c->sl.on || !c->has01) return fail(c, SPB_ESTATE, "spb_mg_slice_finish out of order");
+  u64 *op, *mp; u8* h;
+  ALLOC(op, u64, n_op + c->n_seq + 1); ALLOC(mp, u64, n_mp + c->n_seq + 1); ALLOC(h, u8, 2ull * c->n_seq + 8);
+  dev_copy(c, op, op_all, 8 * n_op); dev_copy(c, mp, mp_all, 8 * n_mp); dev_copy(c, h, has01_any, 2ull * c->n_seq);
+  dfree(c, c->op); dfree(c, c->mp); dfree(c, c->has01);
+  PRIM(cp_origins_finish(c, op, n_op, n_op + c->n_seq, mp, n_mp, n_mp + c->n_seq, h));
+  PRIM(cp_components(c));
+  int r = check_err(c, "spb_mg_slice_finish");
+  if (r) return r;
+  c->state = 3;
+  if (out) *out = c->cnt;
+  return SPB_OK;
+}
+
+// local parts of the sliced results: which = 0 per-position vertex ids (u32), 1 vertex2coords rows (2 x u32 per vertex),
+// 2 edge rows (2 x u32), 3 NBP vertex lists (u32), 4 NBP sequences (u8).  first / count in elements of the complete array
+// (rows for 1 and 2; the first edge row of a rank is the sum of the counts of the ranks below it).
+int spb_mg_shard(spb_ctx* c, int which, void** dev, uint64_t* first, uint64_t* count) {
+  if (!c || !dev || !first || !count) return SPB_EINVAL;
+  if (!c->sl.on || c->state < 2) return fail(c, SPB_ESTATE, "spb_mg_shard: no sliced results in this context");
+  const spb_ctx::Slice& sl = c->sl;
+  switch (which) {
+    case 0: *dev = c->sp + sl.pos_lo; *first = sl.pos_lo; *count = sl.pos_hi - sl.pos_lo; return SPB_OK;
+    case 1: {
+      static_assert(sizeof(u32) == 4, "");
+      u32* tmp; ALLOC(tmp, u32, 2ull * (sl.v_hi - sl.v_lo) + 2);
+      SPB_LAUNCH(k_coords, nblk(sl.v_hi - sl.v_lo, TPB), TPB, c->stream, c->v2pos + sl.v_lo, sl.v_hi - sl.v_lo, c->seq_off, c->n_seq, tmp);
+      dfree(c, c->shard_tmp); c->shard_tmp = tmp;
+      *dev = tmp; *first = sl.v_lo; *count = sl.v_hi - sl.v_lo; return SPB_OK;
+    }
+    case 2: *dev = c->edges; *first = 0; *count = sl.edge_n; return SPB_OK;
+    case 3: if (c->state < 3) break; *dev = c->verts; *first = sl.vert_lo; *count = sl.vert_n; return SPB_OK;
+    case 4: if (c->state < 3) break; *dev = c->seqs; *first = sl.seq_lo; *count = sl.seq_n; return SPB_OK;
+    default: return SPB_EINVAL;
+  }
+  return fail(c, SPB_ESTATE, "spb_mg_shard: not compacted yet");
+}
+
+// every sliced pass again, over the whole input, on this rank alone: afterwards the context is in the state a single GPU
+// would have reached (all getters work).  No communication: the bitmaps and links are complete on every rank.
+int spb_mg_complete(spb_ctx* c, spb_counts* out) {
+  if (!c) return SPB_EINVAL;
+  if (!c->sl.on) { if (out) *out = c->cnt; return SPB_OK; }
+  if (!c->mg_seen) return fail(c, SPB_ESTATE, "spb_mg_complete: the links are gone");
+  const bool compacted = c->state == 3;
+  free_graph_results(c);
+  dfree(c, c->shard_tmp);
+  c->sl = spb_ctx::Slice();
+  c->state = 1;
+  PRIM(dd_ids(c, 0, c->T, nullptr, 1, c->mg_seen));
+  PRIM(dd_graph(c));
+  int r = check_err(c, "spb_mg_complete");
+  if (r) return r;
+  c->state = 2;
+  if (compacted) return spb_compact(c, out);
   if (out) *out = c->cnt;
   return SPB_OK;
 }
 
 // ------------------------------------------------------------------------------------------- getters
 #define NEED(st) do { if (!c) return SPB_EINVAL; if (c->state < (st)) return fail(c, SPB_ESTATE, "%s: results not available yet (state %d)", __func__, c->state); } while (0)
+// getters that read the per-position / per-vertex / per-NBP-vertex arrays: those are sliced over the ranks until spb_mg_complete
+#define NEED_FULL(st) do { NEED(st); if (c->sl.on) return fail(c, SPB_ESTATE, "%s: the results of this context are sliced over the ranks (spb_mg_shard for the local part, spb_mg_complete for all of it)", __func__); } while (0)
 
 int spb_get_vertex2coords(spb_ctx* c, uint32_t* out) {
-  NEED(2);
+  NEED_FULL(2);
   u32* tmp; ALLOC(tmp, u32, 2ull * c->nV + 2);
   SPB_LAUNCH(k_coords, nblk(c->nV, TPB), TPB, c->stream, c->v2pos, c->nV, c->seq_off, c->n_seq, tmp);
   dev_copy(c, out, tmp, 8ull * c->nV); dev_sync(c);
   dfree(c, tmp);
   return check_err(c, __func__);
 }
-int spb_get_edges(spb_ctx* c, uint32_t* out) { NEED(2); dev_copy(c, out, c->edges, 8ull * c->cnt.n_edges); dev_sync(c); return SPB_OK; }
-int spb_get_instance_vertices(spb_ctx* c, uint32_t* out) { NEED(2); dev_copy(c, out, c->sp, 4ull * c->T); dev_sync(c); return SPB_OK; }
+int spb_get_edges(spb_ctx* c, uint32_t* out) { NEED_FULL(2); dev_copy(c, out, c->edges, 8ull * c->cnt.n_edges); dev_sync(c); return SPB_OK; }
+int spb_get_instance_vertices(spb_ctx* c, uint32_t* out) { NEED_FULL(2); dev_copy(c, out, c->sp, 4ull * c->T); dev_sync(c); return SPB_OK; }
 int spb_get_seqlimits(spb_ctx* c, uint32_t* out) { NEED(2); dev_copy(c, out, c->seqlim, 8ull * c->n_seq); dev_sync(c); return SPB_OK; }
 
 static int build_intervals(spb_ctx* c) {
@@ -1629,7 +1981,7 @@ static int build_intervals(spb_ctx* c) {
   return check_err(c, "seq_intervals");
 }
 int spb_get_seq_intervals(spb_ctx* c, uint64_t* off, uint32_t* intervals) {
-  NEED(2);
+  NEED_FULL(2);
   int r = build_intervals(c);
   if (r) return r;
   if (off) dev_copy(c, off, c->iv_off, 8ull * (c->n_seq + 1));
@@ -1638,7 +1990,7 @@ int spb_get_seq_intervals(spb_ctx* c, uint64_t* off, uint32_t* intervals) {
   return SPB_OK;
 }
 int spb_get_components(spb_ctx* c, int32_t* out) {
-  NEED(3);
+  NEED_FULL(3);
   int32_t* tmp; ALLOC(tmp, int32_t, (u64)c->nV + 1);
   SPB_LAUNCH(k_vertex_comp, nblk(c->nV, TPB), TPB, c->stream, c->vflags, c->nV, c->vnbp, c->init_list, c->nI, c->parent, c->label_of_root,
              c->nbp_comp, tmp);
@@ -1649,6 +2001,7 @@ int spb_get_components(spb_ctx* c, int32_t* out) {
 int spb_get_nbps(spb_ctx* c, uint64_t* off, uint32_t* verts, int32_t* comp, uint8_t* is_cycle) {
   NEED(3);
   if (off) dev_copy(c, off, c->voff, 8ull * (c->nN + 1));
+  if (verts && c->sl.on) return fail(c, SPB_ESTATE, "spb_get_nbps: the vertex lists are sliced over the ranks (spb_mg_shard / spb_mg_complete)");
   if (verts) dev_copy(c, verts, c->verts, 4ull * c->cnt.nbp_vertices);
   if (comp) dev_copy(c, comp, c->nbp_comp, 4ull * c->nN);
   if (is_cycle) dev_copy(c, is_cycle, c->nt.cyc, (u64)c->nN);
@@ -1658,6 +2011,7 @@ int spb_get_nbps(spb_ctx* c, uint64_t* off, uint32_t* verts, int32_t* comp, uint
 int spb_get_nbp_seqs(spb_ctx* c, uint64_t* off, uint8_t* ascii) {
   NEED(3);
   if (off) dev_copy(c, off, c->soff, 8ull * (c->nN + 1));
+  if (ascii && c->sl.on) return fail(c, SPB_ESTATE, "spb_get_nbp_seqs: the sequences are sliced over the ranks (spb_mg_shard / spb_mg_complete)");
   if (ascii) dev_copy(c, ascii, c->seqs, c->cnt.nbp_bases);
   dev_sync(c);
   return SPB_OK;
@@ -1696,7 +2050,7 @@ static int build_nbp_graph(spb_ctx* c) {
   return check_err(c, "nbp_graph");
 }
 int spb_get_nbp_graph(spb_ctx* c, uint64_t* n_edges, uint64_t* off, uint32_t* succ, uint32_t* rev) {
-  NEED(3);
+  NEED_FULL(3);
   int r = build_nbp_graph(c);
   if (r) return r;
   if (n_edges) *n_edges = c->g_edges;
@@ -1769,7 +2123,7 @@ static int build_occurrences(spb_ctx* c) {
   return check_err(c, "nbp_occurrences");
 }
 int spb_get_nbp_orientation_counts(spb_ctx* c, uint32_t* counts) {
-  NEED(3);
+  NEED_FULL(3);
   if (!counts) return SPB_EINVAL;
   if (c->nN == 0) return SPB_OK;
   int r = build_occurrences(c);
@@ -1778,7 +2132,7 @@ int spb_get_nbp_orientation_counts(spb_ctx* c, uint32_t* counts) {
   return SPB_OK;
 }
 int spb_get_seq_nbps(spb_ctx* c, uint64_t* n_pairs, uint64_t* off, uint32_t* nbp_ids) {
-  NEED(3);
+  NEED_FULL(3);
   if (c->nN == 0) { if (n_pairs) *n_pairs = 0; if (off) for (u32 s = 0; s <= c->n_seq; ++s) off[s] = 0; return SPB_OK; }
   int r = build_occurrences(c);
   if (r) return r;
@@ -1810,7 +2164,7 @@ int spb_get_bubble_groups(spb_ctx* c, uint32_t* group) {
 // uint32[off[n_paths]] are host arrays; ascii receives off[n_paths] + n_paths * (k - 1) bytes, path i at
 // off[i] + i * (k - 1).  SPB_EINVAL if a path is shorter than 2 or two consecutive vertices are not adjacent.
 int spb_path_sequences(spb_ctx* c, uint32_t n_paths, const uint64_t* off, const uint32_t* verts, uint8_t* ascii) {
-  NEED(2);
+  NEED_FULL(2);
   if (!off || !verts || !ascii) return SPB_EINVAL;
   if (n_paths == 0) return SPB_OK;
   const u64 total = off[n_paths];
@@ -1863,7 +2217,7 @@ static int build_init_seq_pairs(spb_ctx* c) {
 // larger `cap` when it exceeds it).
 int spb_path_origins(spb_ctx* c, uint32_t n_paths, const uint64_t* off, const uint32_t* verts, uint64_t cap, uint64_t* n_pairs,
                      uint64_t* out_off, uint32_t* seq_idx) {
-  NEED(3);
+  NEED_FULL(3);
   if (!off || !verts || !n_pairs || !out_off || (cap && !seq_idx)) return SPB_EINVAL;
   *n_pairs = 0;
   if (n_paths == 0) { out_off[0] = 0; return SPB_OK; }

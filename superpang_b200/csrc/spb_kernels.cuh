@@ -939,6 +939,35 @@ __device__ __forceinline__ u32 rank_first(const u32* fbits, const u32* blkoff, c
   return __ldg(blkoff + (x >> 8)) + __ldg(wpre + (x >> 5)) + __popc(__ldg(fbits + (x >> 5)) & ((1u << (x & 31)) - 1));
 }
 
+// Multi-GPU, sliced tail: a rank fills the per-position / per-vertex arrays only for its own slice.
+// The few entries a kernel needs from outside that slice are recomputed from the replicated bitmaps and rank tables:
+//   VPos   first position of vertex v        = select(fbits, v): block by binary search in blkoff, word by wpre, bit in the word
+//   VidAt  vertex id of the instance at p    = rank_first(first position of its k-mer) (links in `seen`)
+// Single GPU: lo = 0, hi = everything -> plain array reads.
+struct VPos { const u32* v2pos; u32 vlo, vhi; const u32* fbits; const u32* blkoff; const u8* wpre; u32 nb; };
+__device__ __forceinline__ u32 vpos_at(const VPos& q, u32 v) {
+  if (v >= q.vlo && v < q.vhi) return q.v2pos[v];
+  u32 lo = 0, hi = q.nb;                             // last block b with blkoff[b] <= v (empty blocks share their offset with the next one)
+  while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (__ldg(q.blkoff + mid) <= v) lo = mid + 1; else hi = mid; }
+  const u32 b = lo - 1;
+  const u32 r = v - __ldg(q.blkoff + b);
+  u32 j = 7;
+  while (j > 0 && __ldg(q.wpre + 8ull * b + j) > r) --j;
+  u32 w = __ldg(q.fbits + 8ull * b + j);
+  for (u32 i = r - __ldg(q.wpre + 8ull * b + j); i > 0; --i) w &= w - 1;
+#ifdef SPB_EMU
+  return (u32)(256ull * b + 32 * j + (u32)__builtin_ctz(w));
+#else
+  return (u32)(256ull * b + 32 * j + (u32)(__ffs((int)w) - 1));
+#endif
+}
+struct VidAt { const u32* sp; u64 lo, hi; const u32* fbits; const u32* seen; const u32* blkoff; const u8* wpre; };
+__device__ __forceinline__ u32 vid_at(const VidAt& q, u64 p) {     // p must start a k-mer
+  if (p >= q.lo && p < q.hi) return q.sp[p];
+  const u32 r = get_bit(q.fbits, p) ? (u32)p : q.seen[p];
+  return rank_first(q.fbits, q.blkoff, q.wpre, r);
+}
+
 // exact lookup of the first position of the k-mer at p in the finished table (rarely needed, see k_assign_ids)
 template <int W> __device__ __forceinline__ u32 lookup_rep(const u32* __restrict__ F, const u32* __restrict__ R, u64 T, u32 k,
                                                            const u64* __restrict__ slots, u64 capmask, u64 p) {
@@ -967,7 +996,9 @@ template <int W> __device__ __forceinline__ u32 lookup_rep(const u32* __restrict
 template <int W> __global__ void
 k_assign_ids(const u32* sp_in, u32* sp, const u32* __restrict__ vbits, u64 T, u64 lo, u64 hi, const u32* __restrict__ fbits,
              const u32* __restrict__ blkoff, const u8* __restrict__ wpre, const u64* __restrict__ slots, u64 capmask, const u32* __restrict__ F,
-             const u32* __restrict__ R, u32 k, u32* __restrict__ v2pos, u8* __restrict__ vflags, int follow, u32* err) {
+             const u32* __restrict__ R, u32 k, u32* __restrict__ v2pos, u8* __restrict__ vflags, int follow, u32* err, u64 tlo, u64 thi) {
+  // [tlo, thi): positions whose vertex -> position entries are written (everything on one GPU; the slice plus its halo on
+  // the sliced multi-GPU tail); the flag byte of every vertex is written everywhere.
   // One warp per SPB_JU x 32 positions (SPB_JU words of the bitmaps), grid-stride.  The dependent loads (bitmap word ->
   // link -> bitmap word at the link target -> rank tables) are issued for all SPB_JU words before they are consumed.
   //   sp_in[p] = a smaller position with the same k-mer (global-table path: follow the links down to a first
@@ -993,7 +1024,7 @@ k_assign_ids(const u32* sp_in, u32* sp, const u32* __restrict__ vbits, u64 T, u6
         const u64 p = (wd0 + j) * 32 + lane;
         const u32 vid = b0[j] + w0[j] + lane;
         if (p >= lo && p < hi) sp[p] = vid;
-        v2pos[vid] = (u32)p;
+        if (p >= tlo && p < thi) v2pos[vid] = (u32)p;
         vflags[vid] = (lane < 31 || (f[j + 1] & 1u)) ? VF_R : 0;
       }
       continue;
@@ -1047,7 +1078,7 @@ k_assign_ids(const u32* sp_in, u32* sp, const u32* __restrict__ vbits, u64 T, u6
       const u32 vid = bo[j] + wp[j] + __popc(fr[j] & ((1u << (r[j] & 31)) - 1));
       if (mine[j]) sp[p] = vid;
       if (first[j]) {
-        v2pos[vid] = (u32)p;
+        if (p >= tlo && p < thi) v2pos[vid] = (u32)p;
         const u32 nextfirst = lane < 31 ? (f[j] >> (lane + 1)) & 1u : f[j + 1] & 1u;
         vflags[vid] = nextfirst ? VF_R : 0;          // (p, p+1) both first appearances => edge (vid, vid+1)
       }
@@ -1057,9 +1088,10 @@ k_assign_ids(const u32* sp_in, u32* sp, const u32* __restrict__ vbits, u64 T, u6
 
 // K4: junction candidates.  The instance pair (p, p+1) yields edge {sp[p], sp[p+1]} (reference
 // lib/Assembler.py:199-201).  It is dropped when it coincides with an implicit edge (v, v+1).
-__global__ void k_junction_emit(const u32* __restrict__ sp, u64 T, const u32* __restrict__ fbits, const u8* __restrict__ vflags, const u32* __restrict__ v2pos,
+__global__ void k_junction_emit(const u32* __restrict__ sp, u64 T, u64 w_lo, u64 w_hi, const u32* __restrict__ fbits, const u8* __restrict__ vflags, VPos vp,
                                 const u32* __restrict__ obits, const u32* __restrict__ vobits, u64* __restrict__ Jk, u8* __restrict__ Js,
                                 u64* counter, u64 cap, u32* err) {
+  // [w_lo, w_hi): bitmap words whose pairs (p, p + 1) are ours (sp must be filled up to position 32 * w_hi)
   // One warp per SPB_JU x 32 positions (SPB_JU words of the first-appearance bitmap), grid-stride.  A word whose 32
   // pairs (p, p+1) are all pairs of consecutive first appearances holds only implicit edges and is skipped at once.
   // The three dependent loads of a pair (bitmap -> vertex ids -> flags / orientation bits) are issued for all SPB_JU
@@ -1067,7 +1099,7 @@ __global__ void k_junction_emit(const u32* __restrict__ sp, u64 T, const u32* __
   const u64 nwords = (T + 31) / 32;
   const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
   const u32 lane = threadIdx.x & 31;
-  for (u64 wd0 = (SPB_GTID() >> 5) * SPB_JU; wd0 < nwords; wd0 += nwarps * SPB_JU) {
+  for (u64 wd0 = w_lo + (SPB_GTID() >> 5) * SPB_JU; wd0 < w_hi; wd0 += nwarps * SPB_JU) {
     u32 f[SPB_JU + 1];
 #pragma unroll
     for (u32 j = 0; j <= SPB_JU; ++j) f[j] = wd0 + j <= nwords ? __ldg(fbits + wd0 + j) : 0u;
@@ -1075,12 +1107,12 @@ __global__ void k_junction_emit(const u32* __restrict__ sp, u64 T, const u32* __
     bool live[SPB_JU];
     bool any = false;
 #pragma unroll
-    for (u32 j = 0; j < SPB_JU; ++j) any = any || (wd0 + j < nwords && (f[j] & ((f[j] >> 1) | (f[j + 1] << 31))) != 0xFFFFFFFFu);
+    for (u32 j = 0; j < SPB_JU; ++j) any = any || (wd0 + j < w_hi && (f[j] & ((f[j] >> 1) | (f[j + 1] << 31))) != 0xFFFFFFFFu);
     if (!any) continue;                              // warp-uniform: nothing but consecutive first appearances here
 #pragma unroll
     for (u32 j = 0; j < SPB_JU; ++j) {               // stage 1: vertex ids of the pairs that are not two consecutive firsts
       const u64 p = (wd0 + j) * 32 + lane;
-      const bool word = wd0 + j < nwords && (f[j] & ((f[j] >> 1) | (f[j + 1] << 31))) != 0xFFFFFFFFu;     // warp-uniform
+      const bool word = wd0 + j < w_hi && (f[j] & ((f[j] >> 1) | (f[j + 1] << 31))) != 0xFFFFFFFFu;     // warp-uniform
       const u32 fp = (f[j] >> lane) & 1u, fq = lane < 31 ? (f[j] >> (lane + 1)) & 1u : f[j + 1] & 1u;
       live[j] = word && p + 1 < T && !(fp && fq);
       u[j] = live[j] ? sp[p] : SPB_INVALID; w[j] = live[j] ? sp[p + 1] : SPB_INVALID;
@@ -1093,8 +1125,8 @@ __global__ void k_junction_emit(const u32* __restrict__ sp, u64 T, const u32* __
       live[j] = live[j] && u[j] != SPB_INVALID && w[j] != SPB_INVALID;
       if (live[j] && (w[j] == u[j] + 1 || u[j] == w[j] + 1)) {
         fl[j] = vflags[w[j] == u[j] + 1 ? u[j] : w[j]];
-        ou[j] = vobits ? get_bit(vobits, u[j]) : get_bit(obits, v2pos[u[j]]);
-        ow[j] = vobits ? get_bit(vobits, w[j]) : get_bit(obits, v2pos[w[j]]);
+        ou[j] = vobits ? get_bit(vobits, u[j]) : get_bit(obits, vpos_at(vp, u[j]));
+        ow[j] = vobits ? get_bit(vobits, w[j]) : get_bit(obits, vpos_at(vp, w[j]));
       }
     }
 #pragma unroll
@@ -1116,8 +1148,8 @@ __global__ void k_junction_emit(const u32* __restrict__ sp, u64 T, const u32* __
 #endif
       u64 slot = list_reserve(counter, n);
       if (n == 0 || slot + n > cap) continue;
-      u32 su = op ^ get_bit(obits, v2pos[u[j]]);                   // instance strand vs. vertex' stored k-mer
-      u32 sw = oq ^ get_bit(obits, v2pos[w[j]]);
+      u32 su = op ^ get_bit(obits, vpos_at(vp, u[j]));                   // instance strand vs. vertex' stored k-mer
+      u32 sw = oq ^ get_bit(obits, vpos_at(vp, w[j]));
       u32 side_u = su ? SIDE_L : SIDE_R;                           // where w attaches on u
       u32 side_w = sw ? SIDE_R : SIDE_L;                           // where u attaches on w
       Jk[slot] = ((u64)u[j] << 32) | w[j]; Js[slot] = (u8)(side_u | (side_w << 1));
@@ -1198,13 +1230,13 @@ __global__ void k_mark_hasj(const u64* __restrict__ Jk, u32 nJ, u8* vflags) {
   if (i > 0 && (u32)(Jk[i - 1] >> 32) == s) return;
   atomicOr((u32*)vflags + (s >> 2), (u32)VF_HASJ << ((s & 3) * 8));
 }
-__global__ void k_mark_seqlim(const u64* __restrict__ seq_off, u32 n_seq, u32 k, const u32* __restrict__ sp, u8* vflags, u32* seqlim) {
+__global__ void k_mark_seqlim(const u64* __restrict__ seq_off, u32 n_seq, u32 k, VidAt va, u8* vflags, u32* seqlim) {
   u64 s = SPB_GTID();
   if (s >= n_seq) return;
   u64 b = seq_off[s], e = seq_off[s + 1];
   u32 v0 = SPB_INVALID, v1 = SPB_INVALID;
   if (e - b > k) {
-    v0 = sp[b]; v1 = sp[e - k];
+    v0 = vid_at(va, b); v1 = vid_at(va, e - k);
     atomicOr((u32*)vflags + (v0 >> 2), (u32)VF_SEQLIM << ((v0 & 3) * 8));
     atomicOr((u32*)vflags + (v1 >> 2), (u32)VF_SEQLIM << ((v1 & 3) * 8));
   }
@@ -1227,10 +1259,10 @@ __device__ __forceinline__ bool classify_slow(const GView& g, u32 v, u8 f, u32* 
   return init;
 }
 #define SPB_M8 0x0101010101010101ull
-__global__ void k_classify8(GView g, u8* vflags, u32* err) {
-  u64 t = SPB_GTID();
+__global__ void k_classify8(GView g, u8* vflags, u32* err, u32 t_lo, u32 t_hi) {   // tiles [t_lo, t_hi) of 8 vertices
+  u64 t = SPB_GTID() + t_lo;
   u64 v0 = t * 8;
-  if (v0 >= g.nV) return;
+  if (t >= t_hi || v0 >= g.nV) return;
   u64 w = *(const u64*)(g.vflags + v0);
   u64 prev = v0 ? g.vflags[v0 - 1] : 0;
   u64 nvalid = g.nV - v0 < 8 ? g.nV - v0 : 8;
@@ -1255,10 +1287,13 @@ __global__ void k_classify8(GView g, u8* vflags, u32* err) {
 
 // K6: pieces = maximal runs of consecutive-id extender vertices linked by implicit edges; also the
 // per-thread counts of inits / piece starts / piece ends for the compaction below.
-__global__ void k_piece_flags8(u8* vflags, u32 nV, u32* __restrict__ cnt3, u32 nT) {
-  u64 t = SPB_GTID();
+// Flags are written for the tiles [f_lo, f_hi); the counts cover the tiles [t_lo, t_hi) inside them, nT = t_hi - t_lo (the
+// sliced multi-GPU tail also flags one tile on either side of its own range: the per-position passes of the slice read
+// the piece flags of vertices up to 7 ids beyond the 8-aligned cut).
+__global__ void k_piece_flags8(u8* vflags, u32 nV, u32* __restrict__ cnt3, u32 nT, u32 f_lo, u32 f_hi, u32 t_lo, u32 t_hi) {
+  u64 t = SPB_GTID() + f_lo;
   u64 v0 = t * 8;
-  if (v0 >= nV) return;
+  if (t >= f_hi || v0 >= nV) return;
   u64 w = *(const u64*)(vflags + v0);
   u64 pf = v0 ? vflags[v0 - 1] : 0;
   u64 nf = v0 + 8 < nV ? vflags[v0 + 8] : 0;
@@ -1271,15 +1306,17 @@ __global__ void k_piece_flags8(u8* vflags, u32 nV, u32* __restrict__ cnt3, u32 n
   u64 start = ext & ~(p_r & ~p_init);                 // no extender predecessor through an implicit edge
   u64 end = ext & ~(r & ~n_init);                     // no extender successor through an implicit edge
   *(u64*)(vflags + v0) = w | (start << 5) | (end << 6);
-  cnt3[t] = (u32)__popcll(init); cnt3[nT + t] = (u32)__popcll(start); cnt3[2 * (u64)nT + t] = (u32)__popcll(end);
+  if (t < t_lo || t >= t_hi) return;
+  const u64 i = t - t_lo;
+  cnt3[i] = (u32)__popcll(init); cnt3[nT + i] = (u32)__popcll(start); cnt3[2 * (u64)nT + i] = (u32)__popcll(end);
 }
 __global__ void k_compact3(const u8* __restrict__ vflags, u32 nV, const u32* __restrict__ off3, u32 nT, u32 totI, u32 totS,
-                           u32* __restrict__ init_list, u32* __restrict__ plo, u32* __restrict__ phi) {
-  u64 t = SPB_GTID();
-  u64 v0 = t * 8;
-  if (v0 >= nV) return;
+                           u32* __restrict__ init_list, u32* __restrict__ plo, u32* __restrict__ phi, u32 t_lo) {
+  u64 i3 = SPB_GTID();
+  u64 v0 = (i3 + t_lo) * 8;
+  if (i3 >= nT || v0 >= nV) return;
   u64 w = *(const u64*)(vflags + v0);
-  u32 oI = off3[t], oS = off3[nT + t] - totI, oE = off3[2 * (u64)nT + t] - totI - totS;
+  u32 oI = off3[i3], oS = off3[nT + i3] - totI, oE = off3[2 * (u64)nT + i3] - totI - totS;
   for (u32 i = 0; i < 8 && v0 + i < nV; ++i) {
     u32 f = (u32)(w >> (8 * i)) & 0xFF;
     if (f & VF_INIT) init_list[oI++] = (u32)(v0 + i);
@@ -1288,6 +1325,13 @@ __global__ void k_compact3(const u8* __restrict__ vflags, u32 nV, const u32* __r
   }
 }
 
+// sliced multi-GPU tail: the init vertices found by the other ranks (the init bit is read at arbitrary vertices below)
+__global__ void k_mark_inits(const u32* __restrict__ init_list, u32 nI, u8* vflags) {
+  u64 i = SPB_GTID();
+  if (i >= nI) return;
+  const u32 v = init_list[i];
+  atomicOr((u32*)vflags + (v >> 2), (u32)VF_INIT << ((v & 3) * 8));
+}
 __global__ void k_init_degrees(GView g, const u32* __restrict__ init_list, u32 nI, u32* __restrict__ ideg) {
   u64 i = SPB_GTID();
   if (i >= nI) return;
@@ -1435,18 +1479,19 @@ __global__ void k_nbp_lengths(NbpTab t, u32 nN, u32 k, u64* __restrict__ vlen, u
 __device__ __forceinline__ u8 code2ascii(u32 c) { return (u8)("ACGT"[c]); }
 
 // K11: NBP head / tail: first vertex with its k oriented bases, last vertex with its last base.
-__global__ void k_emit_ends(NbpTab t, u32 nN, u32 k, u64 T, const u32* __restrict__ F, const u32* __restrict__ R,
-                            const u32* __restrict__ v2pos, const u64* __restrict__ voff, const u64* __restrict__ soff,
+// (verts / seq: buffers of the NBPs [n_lo, n_hi) only, addressed with the global offsets minus those of NBP n_lo)
+__global__ void k_emit_ends(NbpTab t, u32 n_lo, u32 n_hi, u32 k, u64 T, const u32* __restrict__ F, const u32* __restrict__ R,
+                            VPos vp, const u64* __restrict__ voff, const u64* __restrict__ soff,
                             u32* __restrict__ verts, u8* __restrict__ seq) {
-  u64 id = SPB_GTID() >> 5;                    // one warp per NBP
+  u64 id = (SPB_GTID() >> 5) + n_lo;           // one warp per NBP
   u32 lane = threadIdx.x & 31;
-  if (id >= nN) return;
+  if (id >= n_hi) return;
   u32 a = t.a[id], b = t.b[id];
   u64 vo = voff[id], so = soff[id];
   u32 L = t.L[id];
   bool afwd = t.aside[id] == SIDE_R;          // second vertex on a's right => a read forward
   bool bfwd = t.bside[id] == SIDE_L;          // predecessor on b's left  => b read forward
-  u64 pa = v2pos[a], pb = v2pos[b];
+  u64 pa = vpos_at(vp, a), pb = vpos_at(vp, b);
   const u32* S = afwd ? F : R;
   u64 s0 = afwd ? pa : T - pa - k;
   for (u32 j = lane; j < k; j += 32) seq[so + j] = code2ascii(base_at(S, s0 + j));
@@ -1464,11 +1509,13 @@ __global__ void k_emit_ends(NbpTab t, u32 nN, u32 k, u64 T, const u32* __restric
 #define SPB_CHUNK 4096
 #define SPB_SHORT_DART 512
 // long darts are cut into chunks (k_emit_darts), short ones are emitted element-parallel (k_emit_short)
-__global__ void k_dart_chunks(const u32* __restrict__ plo, const u32* __restrict__ phi, u32 nD, u32* __restrict__ nch) {
+__global__ void k_dart_chunks(const u32* __restrict__ plo, const u32* __restrict__ phi, u32 nD, const u32* __restrict__ dart_nbp, u32 n_lo, u32 n_hi,
+                              u32* __restrict__ nch) {
   u64 d = SPB_GTID();
   if (d >= nD) return;
   u32 len = phi[d >> 1] - plo[d >> 1] + 1;
-  bool is_short = len < SPB_SHORT_DART;
+  const u32 id = dart_nbp[d];
+  bool is_short = len < SPB_SHORT_DART || id < n_lo || id >= n_hi;      // darts of other ranks' NBPs: no chunks here
   nch[d] = is_short ? 0 : (len + SPB_CHUNK - 1) / SPB_CHUNK;
 }
 // short darts: one warp per dart (grid-stride over all darts, long ones are skipped); the per-dart parameters are
@@ -1476,8 +1523,8 @@ __global__ void k_dart_chunks(const u32* __restrict__ plo, const u32* __restrict
 __global__ void SPB_LAUNCH_BOUNDS(256)
 k_emit_short(u32 nD, const u32* __restrict__ plo, const u32* __restrict__ phi,
              const u32* __restrict__ dart_nbp, const u32* __restrict__ acc, u32 k, u64 T, const u32* __restrict__ F,
-             const u32* __restrict__ R, const u32* __restrict__ v2pos, const u64* __restrict__ voff,
-             const u64* __restrict__ soff, u32* __restrict__ verts, u8* __restrict__ seq, u32* __restrict__ vnbp) {
+             const u32* __restrict__ R, VPos vp, const u64* __restrict__ voff,
+             const u64* __restrict__ soff, u32* __restrict__ verts, u8* __restrict__ seq, u32* __restrict__ vnbp, u32 n_lo, u32 n_hi) {
   const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
   const u32 lane = threadIdx.x & 31;
   for (u64 d = SPB_GTID() >> 5; d < nD; d += nwarps) {
@@ -1485,22 +1532,23 @@ k_emit_short(u32 nD, const u32* __restrict__ plo, const u32* __restrict__ phi,
     u32 lo = plo[P], hi = phi[P], len = hi - lo + 1;
     if (len >= SPB_SHORT_DART) continue;
     u32 id = dart_nbp[d], un = dart_nbp[d ^ 1];
+    if (id < n_lo || id >= n_hi) continue;
     if (id < un) un = id;
     u64 r0 = acc[d];
     u64 vo = voff[id] + r0, so = soff[id] + (k - 1) + r0;
-    u64 src = up ? (u64)v2pos[lo] + k - 1 : T - 1 - (u64)v2pos[hi];
+    u64 src = up ? (u64)vpos_at(vp, lo) + k - 1 : T - 1 - (u64)vpos_at(vp, hi);
     const u32* S = up ? F : R;
     for (u32 t = lane; t < len; t += 32) {
       u32 v = up ? lo + t : hi - t;
       verts[vo + t] = v;
       seq[so + t] = code2ascii(base_at(S, src + t));
-      if (up) vnbp[v] = un;
+      if (up && vnbp) vnbp[v] = un;
     }
   }
 }
 struct ChunkParams { u64 vo, so, src; u32 lo, hi, un, t0, n; u32 up; };
 __device__ __forceinline__ ChunkParams chunk_params(u32 c, const u32* choff, u32 nD, const u32* plo, const u32* phi, const u32* dart_nbp,
-                                                    const u32* acc, u32 k, u64 T, const u32* v2pos, const u64* voff, const u64* soff) {
+                                                    const u32* acc, u32 k, u64 T, const VPos& vp, const u64* voff, const u64* soff) {
   ChunkParams q;
   u32 d = upper_bound_u32(choff, nD, c) - 1;
   u32 P = d >> 1; q.up = !(d & 1);
@@ -1509,7 +1557,7 @@ __device__ __forceinline__ ChunkParams chunk_params(u32 c, const u32* choff, u32
   u32 id = dart_nbp[d];
   u32 un = dart_nbp[d ^ 1]; q.un = id < un ? id : un;
   q.vo = voff[id] + acc[d]; q.so = soff[id] + (k - 1) + acc[d];
-  q.src = q.up ? (u64)v2pos[q.lo] + k - 1 : T - 1 - (u64)v2pos[q.hi];
+  q.src = q.up ? (u64)vpos_at(vp, q.lo) + k - 1 : T - 1 - (u64)vpos_at(vp, q.hi);
   q.t0 = (c - choff[d]) * SPB_CHUNK;
   q.n = len - q.t0 < SPB_CHUNK ? len - q.t0 : SPB_CHUNK;
   return q;
@@ -1517,11 +1565,11 @@ __device__ __forceinline__ ChunkParams chunk_params(u32 c, const u32* choff, u32
 // parameters of every chunk, one thread per chunk: the binary search and the dependent table loads of all chunks run in
 // parallel here instead of once per block at the head of k_emit_darts (where they were a serial latency chain)
 __global__ void k_chunk_table(u32 nchunks, const u32* __restrict__ choff, u32 nD, const u32* __restrict__ plo, const u32* __restrict__ phi,
-                              const u32* __restrict__ dart_nbp, const u32* __restrict__ acc, u32 k, u64 T, const u32* __restrict__ v2pos,
+                              const u32* __restrict__ dart_nbp, const u32* __restrict__ acc, u32 k, u64 T, VPos vp,
                               const u64* __restrict__ voff, const u64* __restrict__ soff, ChunkParams* __restrict__ out) {
   u64 c = SPB_GTID();
   if (c >= nchunks) return;
-  out[c] = chunk_params((u32)c, choff, nD, plo, phi, dart_nbp, acc, k, T, v2pos, voff, soff);
+  out[c] = chunk_params((u32)c, choff, nD, plo, phi, dart_nbp, acc, k, T, vp, voff, soff);
 }
 __global__ void SPB_LAUNCH_BOUNDS(256)
 k_emit_darts(const ChunkParams* __restrict__ cp, const u32* __restrict__ F, const u32* __restrict__ R,
@@ -1531,7 +1579,7 @@ k_emit_darts(const ChunkParams* __restrict__ cp, const u32* __restrict__ F, cons
   for (u32 t = q.t0 + threadIdx.x; t < q.t0 + q.n; t += blockDim.x) {
     u32 v = q.up ? q.lo + t : q.hi - t;
     verts[q.vo + t] = v;
-    if (q.up) vnbp[v] = q.un;
+    if (q.up && vnbp) vnbp[v] = q.un;
   }
   // sequence bytes: one aligned 4-byte word of the output per thread (4 bases = 8 bits of the strand)
   u64 D0 = q.so + q.t0, D1 = D0 + q.n;
@@ -1546,9 +1594,54 @@ k_emit_darts(const ChunkParams* __restrict__ cp, const u32* __restrict__ F, cons
   }
 }
 
+// Sliced multi-GPU tail: NBPs are emitted by the rank that owns their id range, so the vertex -> (undirected) NBP map is
+// not a by-product of the emission there; every rank fills it for its own vertex range from the sorted piece list.  One
+// warp per 1024 vertices: first piece by binary search, then the pieces that intersect the tile in order.
+__global__ void k_fill_vnbp(const u32* __restrict__ plo, const u32* __restrict__ phi, u32 nP, const u32* __restrict__ dart_nbp, u32 v_lo, u32 v_hi,
+                            u32* __restrict__ vnbp) {
+  const u64 wid = SPB_GTID() >> 5;
+  const u32 lane = threadIdx.x & 31;
+  const u64 a = (u64)v_lo + 1024ull * wid;
+  if (a >= v_hi) return;
+  const u32 b = (u32)(a + 1024 < v_hi ? a + 1024 : v_hi);
+  for (u32 v = (u32)a + lane; v < b; v += 32) vnbp[v] = SPB_INVALID;
+  u32 P = upper_bound_u32(plo, nP, (u32)a);          // pieces that start at or before a: the last one may reach into the tile
+  P = P ? P - 1 : 0;
+  for (; P < nP && plo[P] < b; ++P) {
+    const u32 lo = plo[P] > (u32)a ? plo[P] : (u32)a, hi = phi[P] < b - 1 ? phi[P] : b - 1;
+    if (hi < lo) continue;
+    u32 un = dart_nbp[2 * P], dn = dart_nbp[2 * P + 1];
+    if (dn < un) un = dn;
+    const u32 first = lo + ((lane + 32u - ((lo - (u32)a) & 31u)) & 31u);   // every lane keeps to the vertices it cleared above
+    for (u32 v = first; v <= hi; v += 32) vnbp[v] = un;
+  }
+}
+// vertex -> (undirected) NBP id: array inside [v_lo, v_hi), piece lookup outside (repeated instances whose vertex
+// belongs to another rank's range)
+struct VNbp { const u32* vnbp; u32 v_lo, v_hi; const u32* plo; const u32* phi; u32 nP; const u32* dart_nbp; };
+__device__ __forceinline__ u32 vnbp_at(const VNbp& q, u32 v) {
+  if (v >= q.v_lo && v < q.v_hi) return q.vnbp[v];
+  u32 P = upper_bound_u32(q.plo, q.nP, v);
+  if (!P) return SPB_INVALID;
+  --P;
+  if (v > q.phi[P]) return SPB_INVALID;               // not inside a piece: an init
+  const u32 un = q.dart_nbp[2 * P], dn = q.dart_nbp[2 * P + 1];
+  return dn < un ? dn : un;
+}
+// first NBP of every rank: NBP ranges with (nearly) equal numbers of emitted vertices; cuts[r] = first id with voff >= r * total / G
+__global__ void k_nbp_cuts(const u64* __restrict__ voff, u32 nN, u32 G, u32* __restrict__ cuts) {
+  u64 r = SPB_GTID();
+  if (r > G) return;
+  if (r == G) { cuts[r] = nN; return; }
+  const u64 want = (voff[nN] / G) * r;
+  u32 lo = 0, hi = nN;
+  while (lo < hi) { u32 mid = (lo + hi) >> 1; if (voff[mid] < want) lo = mid + 1; else hi = mid; }
+  cuts[r] = lo;
+}
+
 // K13: origins.  (undirected NBP, sequence) pairs where the NBP changes along a sequence; (init vertex,
 // sequence) membership pairs for the inits of 2-vertex NBPs (reference lib/Assembler.py:1212-1262).
-__global__ void k_origin_pairs(const u32* __restrict__ sp, u64 T, const u32* __restrict__ fbits, const u32* __restrict__ vnbp, const u8* __restrict__ vflags,
+__global__ void k_origin_pairs(const u32* __restrict__ sp, u64 T, u64 w_lo, u64 w_hi, const u32* __restrict__ fbits, VNbp vn, const u8* __restrict__ vflags,
                                const u64* __restrict__ seq_off, u32 n_seq, u64* __restrict__ opairs, u64* ocount, u64 ocap,
                                u64* __restrict__ mpairs, u64* mcount, u64 mcap, u8* __restrict__ has01, u32 sb) {
   // one warp per SPB_JU x 32 positions, grid-stride.  Where p-1 and p are consecutive first appearances (vertices v-1, v
@@ -1558,14 +1651,14 @@ __global__ void k_origin_pairs(const u32* __restrict__ sp, u64 T, const u32* __r
   const u64 nwords = (T + 31) / 32;
   const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
   const u32 lane = threadIdx.x & 31;
-  for (u64 wd0 = (SPB_GTID() >> 5) * SPB_JU; wd0 < nwords; wd0 += nwarps * SPB_JU) {
+  for (u64 wd0 = w_lo + (SPB_GTID() >> 5) * SPB_JU; wd0 < w_hi; wd0 += nwarps * SPB_JU) {   // [w_lo, w_hi): our bitmap words (sp filled from position 32 * w_lo - 1)
     u32 v[SPB_JU], pv[SPB_JU];
     bool pair_first[SPB_JU];
 #pragma unroll
     for (u32 j = 0; j < SPB_JU; ++j) {               // stage 1: vertex ids at p and p-1
       const u64 wd = wd0 + j, p = wd * 32 + lane;
       v[j] = pv[j] = SPB_INVALID; pair_first[j] = false;
-      if (p < T) {
+      if (p < T && wd < w_hi) {
         const u32 f = __ldg(fbits + wd);
         const u32 fprev = wd ? (__ldg(fbits + wd - 1) >> 31) : 0u;
         pair_first[j] = ((f & ((f << 1) | fprev)) >> lane) & 1u;       // p-1 and p both first appearances
@@ -1579,7 +1672,7 @@ __global__ void k_origin_pairs(const u32* __restrict__ sp, u64 T, const u32* __r
       fl[j] = 0; c[j] = prev[j] = SPB_INVALID;
       if (v[j] != SPB_INVALID) {
         fl[j] = vflags[v[j]];
-        if (!pair_first[j]) { c[j] = vnbp[v[j]]; if (pv[j] != SPB_INVALID) prev[j] = vnbp[pv[j]]; }
+        if (!pair_first[j]) { c[j] = vnbp_at(vn, v[j]); if (pv[j] != SPB_INVALID) prev[j] = vnbp_at(vn, pv[j]); }
       }
     }
 #pragma unroll
@@ -1590,9 +1683,9 @@ __global__ void k_origin_pairs(const u32* __restrict__ sp, u64 T, const u32* __r
       bool pfirst = pv[j] == SPB_INVALID;
       if (pair_first[j]) {
         if (vv > 1 && !(fl[j] & (VF_INIT | VF_PSTART))) continue;
-        c[j] = vnbp[vv];                             // rare: a piece starts here
+        c[j] = vnbp_at(vn, vv);                             // rare: a piece starts here
         const u32 q = sp[p - 1];                     // p > 0 and valid, since p-1 is a first appearance
-        prev[j] = vnbp[q]; pfirst = false;
+        prev[j] = vnbp_at(vn, q); pfirst = false;
       }
       const bool in2 = (fl[j] & VF_IN2) != 0;
       const bool emit_o = (c[j] != SPB_INVALID) && (pfirst || c[j] != prev[j]);
@@ -1606,12 +1699,12 @@ __global__ void k_origin_pairs(const u32* __restrict__ sp, u64 T, const u32* __r
 }
 // compress_vertices leading-zero quirk (reference lib/vtools.pyx:29-45): a sequence whose smallest
 // vertex id is 1 is recorded as containing vertex 0 as well.
-__global__ void k_origin_quirk(const u8* __restrict__ has01, u32 n_seq, const u32* __restrict__ vnbp, const u8* __restrict__ vflags,
+__global__ void k_origin_quirk(const u8* __restrict__ has01, u32 n_seq, VNbp vn, const u8* __restrict__ vflags,
                                u64* __restrict__ opairs, u64* ocount, u64 ocap, u64* __restrict__ mpairs, u64* mcount, u64 mcap, u32 sb) {
   u64 s = SPB_GTID();
   if (s >= n_seq) return;
   if (!(has01[2 * s + 1] && !has01[2 * s])) return;
-  u32 c = vnbp[0];
+  u32 c = vnbp_at(vn, 0);
   if (c != SPB_INVALID) { u64 i = atomicAdd(ocount, 1ull); if (i < ocap) opairs[i] = ((u64)c << sb) | s; }
   if (vflags[0] & VF_IN2) { u64 i = atomicAdd(mcount, 1ull); if (i < mcap) mpairs[i] = (u64)s; }
 }
@@ -1989,10 +2082,10 @@ __global__ void k_coords(const u32* __restrict__ v2pos, u32 nV, const u64* __res
 
 // explicit edge list (reference lib/Assembler.py:247-249): per vertex v the rows (v, x), x >= v:
 // self-loop first, then the implicit (v, v+1), then junction neighbours above v.  8 vertices per thread.
-__global__ void k_edge_counts8(GView g, u32* __restrict__ cnt) {
-  u64 t = SPB_GTID();
+__global__ void k_edge_counts8(GView g, u32* __restrict__ cnt, u32 t_lo, u32 t_hi) {   // tiles [t_lo, t_hi) of 8 vertices; cnt[t - t_lo]
+  u64 t = SPB_GTID() + t_lo;
   u64 v0 = t * 8;
-  if (v0 >= g.nV) return;
+  if (t >= t_hi || v0 >= g.nV) return;
   u64 w = *(const u64*)(g.vflags + v0);
   u32 c = 0;
   for (u32 i = 0; i < 8 && v0 + i < g.nV; ++i) {
@@ -2004,9 +2097,9 @@ __global__ void k_edge_counts8(GView g, u32* __restrict__ cnt) {
       for (; j < g.nJ && (u32)(g.Jk[j] >> 32) == v; ++j) ++c;
     }
   }
-  cnt[t] = c;
+  cnt[t - t_lo] = c;
 }
-// rows of vertex v start at off8[v / 8] + (rows of the lower vertices of its group); one thread per vertex so that
+// rows of vertex v start at off8[v / 8 - t_lo] + (rows of the lower vertices of its group); one thread per vertex so that
 // the common case -- only the implicit (v, v+1) row -- is written as consecutive 8-byte stores
 __device__ __forceinline__ u32 edge_rows_of(const GView& g, u32 v, u32 fl) {
   u32 c = (fl & VF_R) ? 1 : 0;
@@ -2016,22 +2109,23 @@ __device__ __forceinline__ u32 edge_rows_of(const GView& g, u32 v, u32 fl) {
   }
   return c;
 }
-__global__ void k_edge_write(GView g, const u32* __restrict__ off8, u32* __restrict__ edges) {
-  // grid-stride, four vertices per thread and iteration with their loads issued together
+__global__ void k_edge_write(GView g, const u32* __restrict__ off8, u32* __restrict__ edges, u32 t_lo, u32 t_hi) {
+  // grid-stride over the vertices of the tiles [t_lo, t_hi), four vertices per thread and iteration with their loads issued together
   const u64 stride = (u64)gridDim.x * blockDim.x;
   uint2* rows = (uint2*)edges;
-  for (u64 vb = SPB_GTID(); vb < g.nV; vb += 4 * stride) {
+  const u64 v_end = 8ull * t_hi < g.nV ? 8ull * t_hi : g.nV;
+  for (u64 vb = 8ull * t_lo + SPB_GTID(); vb < v_end; vb += 4 * stride) {
     u64 wv[4]; u32 ov[4];
 #pragma unroll
     for (u32 q = 0; q < 4; ++q) {
       const u64 v = vb + q * stride;
-      wv[q] = v < g.nV ? *(const u64*)(g.vflags + (v & ~7ull)) : 0ull;
-      ov[q] = v < g.nV ? off8[v >> 3] : 0u;
+      wv[q] = v < v_end ? *(const u64*)(g.vflags + (v & ~7ull)) : 0ull;
+      ov[q] = v < v_end ? off8[(v >> 3) - t_lo] : 0u;
     }
 #pragma unroll
     for (u32 q = 0; q < 4; ++q) {
       const u64 v = vb + q * stride;
-      if (v >= g.nV) break;
+      if (v >= v_end) break;
       const u32 i = (u32)(v & 7);
       const u64 w = wv[q];
       const u64 below = i ? (w & ((1ull << (8 * i)) - 1)) : 0;

@@ -13,14 +13,15 @@ _M2 = -4658895280553007687          # 0xBF58476D1CE4E5B9 as int64
 _CH = 1 << 26
 
 
-def checksum(t):
-    """64-bit order-sensitive checksum of a 1-D integer torch tensor (device or host); returns a Python int."""
+def checksum(t, base=0):
+    """64-bit order-sensitive checksum of a 1-D integer torch tensor (device or host); returns a Python int.  `base` = index
+    of t[0] in the complete array: the checksum of an array is the sum (mod 2^64) of the checksums of its parts."""
     import torch
     t = t.reshape(-1)
     acc = torch.zeros((), dtype=torch.int64, device=t.device)
     for a in range(0, t.numel(), _CH):
         x = t[a:a + _CH].to(torch.int64)
-        i = torch.arange(a, a + x.numel(), dtype=torch.int64, device=t.device)
+        i = torch.arange(base + a, base + a + x.numel(), dtype=torch.int64, device=t.device)
         w = (i * _M1) ^ ((i >> 9) * _M2)
         w = (w ^ (w >> 29)) | 1
         acc += ((x + 1) * w).sum()
@@ -58,6 +59,53 @@ def result_digest(eng, graph=True):
         out["vertex2coords"] = checksum(_filled(eng, 2 * c.n_vertices, torch.int32, lambda p: L.spb_get_vertex2coords(h, p)))
         out["edges"] = checksum(_filled(eng, 2 * c.n_edges, torch.int32, lambda p: L.spb_get_edges(h, p)))
         out["instance_vertices"] = checksum(_filled(eng, c.n_bases, torch.int32, lambda p: L.spb_get_instance_vertices(h, p)))
+    out["counts"] = {k_: int(getattr(c, k_)) for k_ in ("n_inst", "n_vertices", "n_edges", "n_nbp", "nbp_vertices", "nbp_bases",
+                                                         "n_origin_pairs", "n_comp", "n_cycle_comp")}
+    return out
+
+
+def result_digest_sliced(eng, group=None):
+    """result_digest(graph=True) of a result that is sliced over the ranks (Engine._mg_sliced_tail): every rank checksums
+    its local parts with their global indices, the sums are all-reduced; offsets, origins, components, cycle flags and
+    counts are complete on every rank.  Equal to the digest of the same input on one GPU iff the concatenation of the
+    local parts is the single-GPU result.  Collective: every rank must call it; all ranks get the digest."""
+    import torch
+    import torch.distributed as dist
+    L, h, c = eng.lib, eng.h, eng.counts
+    n = int(c.n_nbp)
+    out = {}
+    out["nbp_seq_off"] = checksum(_filled(eng, n + 1, torch.int64, lambda p: L.spb_get_nbp_seqs(h, p, None)))
+    ooff = _filled(eng, n + 1, torch.int64, lambda p: L.spb_get_nbp_origins(h, p, None))
+    out["nbp_origin_off"] = checksum(ooff)
+    out["nbp_origins"] = checksum(_filled(eng, c.n_origin_pairs, torch.int32, lambda p: L.spb_get_nbp_origins(h, None, p)))
+    out["nbp_vert_off"] = checksum(_filled(eng, n + 1, torch.int64, lambda p: L.spb_get_nbps(h, p, None, None, None)))
+    out["nbp_comp"] = checksum(_filled(eng, n, torch.int32, lambda p: L.spb_get_nbps(h, None, None, p, None)))
+    out["nbp_cycle"] = checksum(_filled(eng, n, torch.uint8, lambda p: L.spb_get_nbps(h, None, None, None, p)))
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    parts, rows = {}, {}
+    for name, which, width in (("nbp_seqs", "nbp_seqs", 1), ("nbp_verts", "nbp_verts", 1), ("vertex2coords", "vertex2coords", 2),
+                               ("edges", "edges", 2), ("instance_vertices", "instance_vertices", 1)):
+        t, first = eng.shard(which)
+        parts[name] = (t, first, width)
+        rows[name] = t.numel() // width
+    dev = parts["edges"][0].device
+    er = torch.zeros(world, dtype=torch.int64, device=dev)
+    er[rank] = rows["edges"]
+    dist.all_reduce(er, group=group)
+    edge_first = int(er[:rank].sum().item())
+    sums = []
+    for name in ("nbp_seqs", "nbp_verts", "vertex2coords", "edges", "instance_vertices"):
+        t, first, width = parts[name]
+        if name == "edges":
+            first = edge_first
+        if name == "instance_vertices":                        # the single-GPU digest covers the n_bases positions of the input
+            t = t[:max(0, min(t.numel(), int(c.n_bases) - first))]
+        v = checksum(t, base=first * width)
+        sums.append(v - (1 << 64) if v >> 63 else v)
+    tot = torch.tensor(sums, dtype=torch.int64, device=dev)
+    dist.all_reduce(tot, group=group)                          # int64 sums wrap: mod 2^64
+    for name, v in zip(("nbp_seqs", "nbp_verts", "vertex2coords", "edges", "instance_vertices"), tot.tolist()):
+        out[name] = int(v) & 0xFFFFFFFFFFFFFFFF
     out["counts"] = {k_: int(getattr(c, k_)) for k_ in ("n_inst", "n_vertices", "n_edges", "n_nbp", "nbp_vertices", "nbp_bases",
                                                          "n_origin_pairs", "n_comp", "n_cycle_comp")}
     return out

@@ -39,6 +39,10 @@ def _free_port():
     (2, {"SPB_MG_PROTOCOL": "part", "SPB_PART_AVG": "60", "SPB_MG_ALL_LINKS": "0", "SPB_EMU_ORDER": "shuffle"}),   # links to the slice owners, ids all-gathered
     (8, {"SPB_MG_PROTOCOL": "part", "SPB_PART_AVG": "40", "SPB_MG_ALL_LINKS": "0"}),
     (2, {"SPB_MG_PROTOCOL": "part", "SPB_PART_AVG": "2"}),           # regions overflow -> collective fallback to the exact path
+    (2, {"SPB_MG_PROTOCOL": "part", "SPB_PART_AVG": "60", "SPB_MG_ALL_LINKS": "2", "SPB_EXPECT_SLICED": "1"}),   # sliced tail forced on repeat-rich inputs too (remote vertices everywhere)
+    (4, {"SPB_MG_PROTOCOL": "part", "SPB_PART_AVG": "30", "SPB_MG_ALL_LINKS": "2", "SPB_EMU_ORDER": "shuffle", "SPB_EXPECT_SLICED": "1"}),
+    (8, {"SPB_MG_PROTOCOL": "part", "SPB_PART_AVG": "40", "SPB_MG_ALL_LINKS": "2", "SPB_EXPECT_SLICED": "1"}),
+    (2, {"SPB_MG_PROTOCOL": "part", "SPB_PART_AVG": "60", "SPB_MG_TAIL": "replicated"}),   # all links, graph + compaction on every rank
 ], ids=lambda x: str(x) if isinstance(x, int) else (",".join(f"{k[4:].lower()}={v}" for k, v in x.items()) or "default"))
 def test_distributed_build_matches_reference(emu_lib, tmp_path, world, env):
     crafted = [c for c in helpers.load_crafted() if c["k"] == 31 and not c.get("degenerate")]
@@ -62,3 +66,35 @@ def test_distributed_build_matches_reference(emu_lib, tmp_path, world, env):
         assert len(got) == len(want)
         for g, w in zip(got, want):
             helpers.assert_summary(g, w)
+
+
+def test_sliced_tail_random_pangenomes(emu_lib, tmp_path):
+    """Sliced graph build + compaction (4 ranks) on random pangenomes large enough that every rank owns positions, vertices
+    and NBPs: every rank's complete() result must equal the single-engine result, and the concatenation of the local
+    parts of all ranks must equal it too (checked inside the worker, tests/mg_worker.py: check_shards)."""
+    from superpang_b200 import _capi
+    from superpang_b200.assembler import Assembler
+    import digests
+    specs = [(6, 2500, 0.95, 101, "snp", 31), (5, 3000, 0.9, 102, "block", 31), (8, 1500, 0.97, 103, "snp", 21), (4, 4000, 0.85, 104, "block", 41),
+             (3, 6000, 0.99, 105, "snp", 31)]
+    cases, want = [], []
+    for n, length, ani, seed, mode, k in specs:
+        sd = helpers.synth_seqdict(n, length, ani, seed, mode)
+        # a short circular-ish repeat and a sequence shorter than k, to cross the code paths of the crafted cases at this size
+        sd["tiny"] = "ACGT" * 3
+        cases.append(dict(records=list(sd.items()), k=k))
+        A = Assembler(sd, k, engine=_capi.Engine(lib=emu_lib))
+        want.append(digests.summarize(A.to_result()))
+    case_path = os.path.join(tmp_path, "cases.json")
+    json.dump(cases, open(case_path, "w"))
+    out = os.path.join(tmp_path, "out.json")
+    port = _free_port()
+    env = {"SPB_MG_PROTOCOL": "part", "SPB_PART_AVG": "40", "SPB_MG_ALL_LINKS": "2", "SPB_EXPECT_SLICED": "1"}
+    world = 4
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "mg_worker.py"), str(r), str(world), port, case_path, out],
+                              env=dict(os.environ, **env)) for r in range(world)]
+    for p in procs:
+        assert p.wait(timeout=900) == 0
+    for r in range(world):
+        got = json.load(open(f"{out}.{r}"))
+        assert got == want
