@@ -30,10 +30,13 @@ def main():
         if os.path.exists(path):
             cases.append((path, 301, helpers.load_json(name)))
     used = set()
-    for proto in (None, "part", "part-slice", "owned", "links", "reps"):           # None: chosen by the duplicate-rate probe
+    from mg_worker import gather_shards, check_shards
+    n_sliced = 0
+    for proto in (None, "part", "part-all", "part-slice", "owned", "links", "reps"):           # None: chosen by the duplicate-rate probe
         if proto:
             os.environ["SPB_MG_PROTOCOL"] = proto.split("-")[0]
-            os.environ["SPB_MG_ALL_LINKS"] = "0" if proto.endswith("-slice") else "1"
+            # part-all: the sliced tail (graph build + compaction partitioned over the ranks) on every case, repeat-rich or not
+            os.environ["SPB_MG_ALL_LINKS"] = "0" if proto.endswith("-slice") else "2" if proto.endswith("-all") else "1"
             if proto.startswith("part"):
                 os.environ["SPB_PART_AVG"] = "300"           # both partition levels on the small cases
             else:
@@ -44,8 +47,15 @@ def main():
             A = Assembler(sd, k, engine=_capi.Engine(device=local, stream=torch.cuda.current_stream().cuda_stream), distributed=True)
             assert A._eng.kind == "cuda sm_100a"
             used.add(A._eng.mg_protocol)
-            helpers.assert_summary(digests.summarize(A.to_result()), want)
+            sliced = gather_shards(A._eng, dist) if getattr(A._eng, "mg_sliced", False) else None
+            assert sliced is not None or proto != "part-all"
+            res = A.to_result()                   # (sliced tail: the first accessor recomputes everything on this rank)
+            if sliced is not None:
+                check_shards(A, sliced)           # concatenation of the local parts of all ranks == the complete result
+                n_sliced += 1
+            helpers.assert_summary(digests.summarize(res), want)
     assert used >= {"part", "owned", "links", "reps"}, used
+    assert n_sliced >= len(cases) - 2, n_sliced
     dist.barrier()
     if dist.get_rank() == 0:
         print(f"multi-GPU parity OK on {dist.get_world_size()} ranks, {len(cases)} cases")

@@ -18,7 +18,7 @@ def gather_shards(eng, dist):
     for which in ("instance_vertices", "vertex2coords", "edges", "nbp_verts", "nbp_seqs"):
         t, first = eng.shard(which)
         parts = [None] * dist.get_world_size()
-        dist.all_gather_object(parts, (first, t.numpy().copy()))
+        dist.all_gather_object(parts, (first, t.cpu().numpy().copy()))
         if which != "edges":                     # contiguous, in rank order, no gaps
             pos = parts[0][0]
             width = 2 if which == "vertex2coords" else 1
