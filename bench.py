@@ -274,6 +274,7 @@ def main():
         if out_bufs.get("key") != key:
             out_bufs.update(key=key, soff=torch.empty(n + 1, dtype=torch.int64).pin_memory(), seq=torch.empty(max(nb, 1), dtype=torch.uint8).pin_memory(),
                             ooff=torch.empty(n + 1, dtype=torch.int64).pin_memory(), oidx=torch.empty(max(no, 1), dtype=torch.int32).pin_memory())
+            eng.set_host_output(out_bufs["seq"])     # from the next step on compact() copies the sequences while it computes the rest
         eng._ck(eng.lib.spb_get_nbp_seqs(eng.h, out_bufs["soff"].data_ptr(), out_bufs["seq"].data_ptr()))
         eng._ck(eng.lib.spb_get_nbp_origins(eng.h, out_bufs["ooff"].data_ptr(), out_bufs["oidx"].data_ptr()))
         return c, 8 * (n + 1) * 2 + nb + 4 * no

@@ -166,7 +166,16 @@ int spb_mg_slice_emit(spb_ctx* ctx, uint64_t* n_op, void** op_dev, uint64_t* n_m
 int spb_mg_slice_finish(spb_ctx* ctx, const uint64_t* op_all, uint64_t n_op, const uint64_t* mp_all, uint64_t n_mp,
                         const uint8_t* has01_any, spb_counts* out);
 int spb_mg_shard(spb_ctx* ctx, int which, void** dev, uint64_t* first, uint64_t* count);
+/* spb_mg_shard + copy of the local part to its place in the complete array at host_base (asynchronous on the context's
+ * stream when the host memory is page-locked, e.g. shared memory registered by every rank); *bytes = size of the part. */
+int spb_mg_shard_to_host(spb_ctx* ctx, int which, void* host_base, uint64_t* bytes);
 int spb_mg_complete(spb_ctx* ctx, spb_counts* out);
+
+/* Page-locked host buffer that is to receive the NBP sequences (the bytes spb_get_nbp_seqs returns; what the CLI writes
+ * to NBPs.fasta, scripts/SuperPang.py:257-268).  When set, spb_compact starts the device-to-host copy on a second stream as
+ * soon as the sequences are emitted, overlapping it with the origin sets, components and edge rows; a later
+ * spb_get_nbp_seqs(ctx, off, the same pointer) only waits for that copy.  capacity in bytes; nullptr clears. */
+int spb_set_host_output(spb_ctx* ctx, uint8_t* nbp_seqs_host, uint64_t capacity);
 
 /* ---- getters (sizes come from spb_counts; buffers are caller-owned, host or device) ---------- */
 

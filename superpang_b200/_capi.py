@@ -25,7 +25,7 @@ EXPORTS = (
     "spb_get_nbp_origins", "spb_get_counts", "spb_get_stage_stats", "spb_build_kind", "spb_launch_count",
     "spb_get_nbp_graph", "spb_get_nbp_orientation_counts", "spb_get_seq_nbps", "spb_get_bubble_groups", "spb_path_sequences", "spb_path_origins", "spb_read_fasta", "spb_free_fasta", "spb_mg_slice", "spb_mg_probe", "spb_mg_records", "spb_mg_dedup", "spb_mg_scatter", "spb_mg_dedup_links", "spb_mg_apply_links", "spb_mg_owned_links", "spb_mg_part_records", "spb_mg_part_dedup", "spb_mg_buffers", "spb_mg_ids", "spb_mg_graph",
     "spb_mg_slice_ids", "spb_mg_slice_junctions", "spb_mg_slice_graph", "spb_mg_slice_classify", "spb_mg_slice_contract", "spb_mg_slice_emit",
-    "spb_mg_slice_finish", "spb_mg_shard", "spb_mg_complete",
+    "spb_mg_slice_finish", "spb_mg_shard", "spb_mg_complete", "spb_set_host_output", "spb_mg_shard_to_host",
 )
 
 
@@ -139,6 +139,8 @@ def _declare(lib):
     lib.spb_mg_slice_finish.argtypes = [vp, u64p, C.c_uint64, u64p, C.c_uint64, u8p, C.POINTER(SpbCounts)]
     lib.spb_mg_shard.argtypes = [vp, C.c_int, pv, pu64, pu64]
     lib.spb_mg_complete.argtypes = [vp, C.POINTER(SpbCounts)]
+    lib.spb_set_host_output.argtypes = [vp, u8p, C.c_uint64]
+    lib.spb_mg_shard_to_host.argtypes = [vp, C.c_int, vp, pu64]
     return lib
 
 
@@ -322,6 +324,13 @@ class Engine:
         self._keep = (ascii_buf, seq_off)
         self.mg_sliced = False
         self._ck(self.lib.spb_load(self.h, _ptr(ascii_buf), seq_off.ctypes.data, len(seq_off) - 1, int(k)))
+
+    def set_host_output(self, nbp_seqs_host):
+        """Page-locked uint8 host tensor / array that is to receive the NBP sequences: compact() then copies them on a second
+        stream while origins, components and edge rows are computed (spb_set_host_output); None clears."""
+        self._out_keep = nbp_seqs_host
+        n = 0 if nbp_seqs_host is None else (nbp_seqs_host.numel() if hasattr(nbp_seqs_host, "numel") else nbp_seqs_host.size)
+        self._ck(self.lib.spb_set_host_output(self.h, _ptr(nbp_seqs_host), int(n)))
 
     def build_dbg(self):
         self._ck(self.lib.spb_build_dbg(self.h, C.byref(self.counts)))
@@ -599,12 +608,12 @@ class Engine:
 
     def shard_to_host(self, which, host_tensor):
         """Copy the local part of a sliced result to its place in `host_tensor` (the complete array on the host, e.g. a
-        SharedHostBuffer tensor); asynchronous on the current stream when the host memory is page-locked.  Returns the
-        number of bytes copied."""
-        t, first = self.shard(which)
-        if t.numel():
-            host_tensor.view(t.dtype)[first:first + t.numel()].copy_(t, non_blocking=True)
-        return t.numel() * t.element_size()
+        SharedHostBuffer tensor); asynchronous on the engine's stream when the host memory is page-locked
+        (spb_mg_shard_to_host).  Returns the number of bytes copied."""
+        code = {"instance_vertices": 0, "vertex2coords": 1, "edges": 2, "nbp_verts": 3, "nbp_seqs": 4}[which]
+        n = C.c_uint64()
+        self._ck(self.lib.spb_mg_shard_to_host(self.h, code, _ptr(host_tensor), C.byref(n)))
+        return int(n.value)
 
     def complete(self):
         """Recompute the sliced passes over the whole input on this rank (no communication): afterwards every getter

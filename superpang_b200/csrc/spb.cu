@@ -67,6 +67,14 @@ struct spb_ctx {
     u32 n_lo = 0, n_hi = 0;                                // own raw NBPs: vertex lists and sequences
     u64 vert_lo = 0, vert_n = 0, seq_lo = 0, seq_n = 0, edge_n = 0;
   } sl;
+  // NBP sequences straight to the caller's page-locked host buffer (spb_set_host_output): copied on a second stream as
+  // soon as they are emitted, while origins / components / edge rows are still being computed
+  u8* out_seq_host = 0; u64 out_seq_cap = 0; bool d2h_pending = false;
+#ifndef SPB_EMU
+  cudaStream_t copy_stream = 0; cudaEvent_t ev_emit = 0, ev_d2h = 0;
+#endif
+  // explicit edge rows: counted at DBG build (n_edges), written after the NBP emission (or at the first getter that needs them)
+  u32* edge_off = 0; bool edges_pending = false;
   u32* shard_tmp = 0;                                     // last spb_mg_shard(1) result
   u8* seqs_base = 0;                                      // allocation behind `seqs` (the slice keeps the 4-byte phase of the global offsets)
   // compaction state that lives across the phases (classification -> contracted graph -> NBP table -> emission -> origins)
@@ -411,9 +419,12 @@ static void reset_state(spb_ctx* c) {
   for (void* p : blocks) dev_free_raw(c, p);
   spb_ctx fresh;
   fresh.device = c->device; fresh.stream = c->stream; fresh.errflag = c->errflag; fresh.pinned = c->pinned;
+  fresh.out_seq_host = c->out_seq_host; fresh.out_seq_cap = c->out_seq_cap;
 #ifndef SPB_EMU
   for (int i = 0; i < 3; ++i) { fresh.stream2[i] = c->stream2[i]; fresh.ev_join[i] = c->ev_join[i]; }
   fresh.ev_fork = c->ev_fork;
+  fresh.copy_stream = c->copy_stream; fresh.ev_emit = c->ev_emit; fresh.ev_d2h = c->ev_d2h;
+  if (c->d2h_pending) cudaEventSynchronize(c->ev_d2h);          // a copy into the caller's buffer is still in flight
   fresh.evpool.swap(c->evpool);
 #endif
   fresh.live.swap(c->live); fresh.cache.swap(c->cache);
@@ -436,6 +447,7 @@ void spb_destroy(spb_ctx* c) {
   cudaFreeHost(c->pinned);
   for (auto e : c->evpool) cudaEventDestroy(e);
   if (c->stream2[0]) { for (int i = 0; i < 3; ++i) { cudaStreamDestroy(c->stream2[i]); cudaEventDestroy(c->ev_join[i]); } cudaEventDestroy(c->ev_fork); }
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); cudaEventDestroy(c->ev_emit); cudaEventDestroy(c->ev_d2h); }
 #endif
   delete c;
 }
@@ -698,11 +710,24 @@ static int graph_finish(spb_ctx* c, u64* Jk, u8* Js, u64 nj) {
   SPB_LAUNCH(k_edge_counts8, nblk(nT, TPB), TPB, c->stream, g, ecnt, t_lo, t_hi);
   u64 nE = 0;
   PRIM(prim_scan_u32(c, ecnt, eoff, nT, &nE));
-  ALLOC(c->edges, u32, 2 * nE + 2);
-  { const int tq_ = t_begin(c); SPB_LAUNCH(k_edge_write, std::min<u64>(nblk(8 * nT, TPB), 148 * 32), TPB, c->stream, g, eoff, c->edges, t_lo, t_hi); t_end(c, tq_, "k_edge_write_ms"); }
-  dfree(c, ecnt); dfree(c, eoff);
-  c->sl.edge_n = nE;
+  dfree(c, ecnt);
+  c->edge_off = eoff; c->edges_pending = true;          // rows are written by ensure_edges (after the NBP emission, so that the
+  c->sl.edge_n = nE;                                    // copy of the sequences to the host overlaps with it)
   c->cnt.n_vertices = nV; c->cnt.n_edges = nE; c->cnt.n_junction = c->nJ;     // (sliced: n_edges is set to the total by the caller)
+  return 0;
+}
+
+// explicit edge rows of the own vertex tiles (reference lib/Assembler.py:247-249): deferred part of graph_finish
+static int ensure_edges(spb_ctx* c) {
+  if (!c->edges_pending) return 0;
+  GView g{c->vflags, c->Jk, c->Js, c->nJ, c->nV};
+  const u32 nTall = (u32)(((u64)c->nV + 7) / 8);
+  const u32 t_lo = c->sl.on ? c->sl.t_lo : 0u, t_hi = c->sl.on ? c->sl.t_hi : nTall;
+  const u64 nT = t_hi - t_lo;
+  ALLOC(c->edges, u32, 2 * c->sl.edge_n + 2);
+  { const int tq_ = t_begin(c); SPB_LAUNCH(k_edge_write, std::min<u64>(nblk(8 * nT, TPB), 148 * 32), TPB, c->stream, g, c->edge_off, c->edges, t_lo, t_hi); t_end(c, tq_, "k_edge_write_ms"); }
+  dfree(c, c->edge_off);
+  c->edges_pending = false;
   return 0;
 }
 
@@ -1530,6 +1555,7 @@ static int cp_contract(spb_ctx* c, int pass, int* again) {
   if (unresolved == 0) { dfree(c, ucount); return 0; }
   if (pass == 1) { dfree(c, ucount); return fail(c, SPB_ECUDA, "internal: %u darts unresolved after cycle cutting", unresolved); }
   // ---- K9: pure-cycle components: cut one edge per ring, then redo the classification
+  PRIM(ensure_edges(c));                               // the edge rows still hold the edges that are cut for the walks
   SPB_LAUNCH(k_cycle_cut, nblk(nD, TPB), TPB, c->stream, g, c->vflags, c->Js, c->rk_ptr[cur], c->rk_mnv[cur], c->plo, nD, ucount + 1);
   c->ncyc = dread(c, ucount + 1);
   dfree(c, ucount);
@@ -1736,6 +1762,22 @@ int spb_compact(spb_ctx* c, spb_counts* out) {
   PRIM(cp_nbp_table(c, &totv, &tots));
   PRIM(cp_emit(c, totv, tots));
   t_end(c, tm, "emit_ms");
+#ifndef SPB_EMU
+  if (c->out_seq_host && tots <= c->out_seq_cap) {     // sequences to the caller's host buffer while the rest is computed
+    if (!c->copy_stream) {
+      CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&c->ev_emit, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->ev_d2h, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(c->ev_emit, c->stream));
+    CK(cudaStreamWaitEvent(c->copy_stream, c->ev_emit, 0));
+    CK(cudaMemcpyAsync(c->out_seq_host, c->seqs, tots, cudaMemcpyDeviceToHost, c->copy_stream));
+    CK(cudaEventRecord(c->ev_d2h, c->copy_stream));
+    c->d2h_pending = true;
+  }
+#endif
+  tm = t_begin(c);
+  PRIM(ensure_edges(c));
+  t_end(c, tm, "edge_rows_ms");
   tm = t_begin(c);
   PRIM(cp_origin_pairs(c));
   {
@@ -1766,7 +1808,7 @@ int spb_compact(spb_ctx* c, spb_counts* out) {
 // VNbp in spb_kernels.cuh).  spb_mg_complete recomputes the sliced passes over the whole input on this rank (no
 // communication) so that every single-GPU getter works; spb_mg_shard hands out the local parts.
 static void free_graph_results(spb_ctx* c) {
-  dfree(c, c->Jk); dfree(c, c->Js); dfree(c, c->edges); dfree(c, c->seqlim);
+  dfree(c, c->Jk); dfree(c, c->Js); dfree(c, c->edges); dfree(c, c->edge_off); c->edges_pending = false; dfree(c, c->seqlim);
   dfree(c, c->init_list); dfree(c, c->ibase); dfree(c, c->plo); dfree(c, c->phi); dfree(c, c->dart_nbp); dfree(c, c->vnbp);
   dfree(c, c->parent); dfree(c, c->label_of_root); dfree(c, c->nbp_comp);
   dfree(c, c->nt.a); dfree(c, c->nt.b); dfree(c, c->nt.L); dfree(c, c->nt.head); dfree(c, c->nt.last); dfree(c, c->nt.aside); dfree(c, c->nt.bside); dfree(c, c->nt.cyc);
@@ -1866,6 +1908,7 @@ int spb_mg_slice_emit(spb_ctx* c, uint64_t* n_op, void** op_dev, uint64_t* n_mp,
   PRIM(cp_emit(c, totv, tots));
   c->cnt.n_inits = c->nI; c->cnt.n_pieces = c->nP; c->cnt.n_nbp = c->nN; c->cnt.nbp_vertices = totv; c->cnt.nbp_bases = tots;
   PRIM(cp_origin_pairs(c));
+  PRIM(ensure_edges(c));
   *n_op = c->n_op; *n_mp = c->n_mp;
   *op_dev = c->op; *mp_dev = c->mp; *has01_dev = c->has01;
   return check_err(c, "spb_mg_slice_emit");
@@ -1903,12 +1946,25 @@ int spb_mg_shard(spb_ctx* c, int which, void** dev, uint64_t* first, uint64_t* c
       dfree(c, c->shard_tmp); c->shard_tmp = tmp;
       *dev = tmp; *first = sl.v_lo; *count = sl.v_hi - sl.v_lo; return SPB_OK;
     }
-    case 2: *dev = c->edges; *first = 0; *count = sl.edge_n; return SPB_OK;
+    case 2: PRIM(ensure_edges(c)); *dev = c->edges; *first = 0; *count = sl.edge_n; return SPB_OK;
     case 3: if (c->state < 3) break; *dev = c->verts; *first = sl.vert_lo; *count = sl.vert_n; return SPB_OK;
     case 4: if (c->state < 3) break; *dev = c->seqs; *first = sl.seq_lo; *count = sl.seq_n; return SPB_OK;
     default: return SPB_EINVAL;
   }
   return fail(c, SPB_ESTATE, "spb_mg_shard: not compacted yet");
+}
+
+// local part of a sliced result to its place in the complete array at host_base (asynchronous on the context's stream when
+// the host memory is page-locked, e.g. a shared buffer registered by every rank); *bytes = size of the part
+int spb_mg_shard_to_host(spb_ctx* c, int which, void* host_base, uint64_t* bytes) {
+  if (!c || !host_base) return SPB_EINVAL;
+  void* dev = nullptr; uint64_t first = 0, count = 0;
+  int r = spb_mg_shard(c, which, &dev, &first, &count);
+  if (r) return r;
+  const u64 w = which == 4 ? 1 : (which == 1 || which == 2) ? 8 : 4;
+  if (count) dev_copy(c, (u8*)host_base + first * w, dev, count * w);
+  if (bytes) *bytes = count * w;
+  return SPB_OK;
 }
 
 // every sliced pass again, over the whole input, on this rank alone: afterwards the context is in the state a single GPU
@@ -1945,7 +2001,7 @@ int spb_get_vertex2coords(spb_ctx* c, uint32_t* out) {
   dfree(c, tmp);
   return check_err(c, __func__);
 }
-int spb_get_edges(spb_ctx* c, uint32_t* out) { NEED_FULL(2); dev_copy(c, out, c->edges, 8ull * c->cnt.n_edges); dev_sync(c); return SPB_OK; }
+int spb_get_edges(spb_ctx* c, uint32_t* out) { NEED_FULL(2); PRIM(ensure_edges(c)); dev_copy(c, out, c->edges, 8ull * c->cnt.n_edges); dev_sync(c); return SPB_OK; }
 int spb_get_instance_vertices(spb_ctx* c, uint32_t* out) { NEED_FULL(2); dev_copy(c, out, c->sp, 4ull * c->T); dev_sync(c); return SPB_OK; }
 int spb_get_seqlimits(spb_ctx* c, uint32_t* out) { NEED(2); dev_copy(c, out, c->seqlim, 8ull * c->n_seq); dev_sync(c); return SPB_OK; }
 
@@ -2012,8 +2068,28 @@ int spb_get_nbp_seqs(spb_ctx* c, uint64_t* off, uint8_t* ascii) {
   NEED(3);
   if (off) dev_copy(c, off, c->soff, 8ull * (c->nN + 1));
   if (ascii && c->sl.on) return fail(c, SPB_ESTATE, "spb_get_nbp_seqs: the sequences are sliced over the ranks (spb_mg_shard / spb_mg_complete)");
+#ifndef SPB_EMU
+  if (ascii && ascii == c->out_seq_host && c->d2h_pending) {           // copied by spb_compact on the second stream: wait for it
+    dev_sync(c);
+    CK(cudaEventSynchronize(c->ev_d2h));
+    c->d2h_pending = false;
+    return SPB_OK;
+  }
+#endif
   if (ascii) dev_copy(c, ascii, c->seqs, c->cnt.nbp_bases);
   dev_sync(c);
+  return SPB_OK;
+}
+
+// Page-locked host buffer that is to receive the NBP sequences (the bytes spb_get_nbp_seqs returns): when set, spb_compact
+// starts the copy on a second stream as soon as the sequences are emitted, so that it overlaps with the origin sets,
+// components and edge rows; spb_get_nbp_seqs(ctx, off, the same pointer) then only waits for it.  nullptr clears.
+int spb_set_host_output(spb_ctx* c, uint8_t* nbp_seqs_host, uint64_t capacity) {
+  if (!c) return SPB_EINVAL;
+#ifndef SPB_EMU
+  if (c->d2h_pending) { cudaEventSynchronize(c->ev_d2h); c->d2h_pending = false; }
+#endif
+  c->out_seq_host = nbp_seqs_host; c->out_seq_cap = nbp_seqs_host ? capacity : 0;
   return SPB_OK;
 }
 int spb_get_nbp_origins(spb_ctx* c, uint64_t* off, uint32_t* seq_idx) {

@@ -1025,7 +1025,17 @@ k_assign_ids(const u32* sp_in, u32* sp, const u32* __restrict__ vbits, u64 T, u6
         const u32 vid = b0[j] + w0[j] + lane;
         if (p >= lo && p < hi) sp[p] = vid;
         if (p >= tlo && p < thi) v2pos[vid] = (u32)p;
-        vflags[vid] = (lane < 31 || (f[j + 1] & 1u)) ? VF_R : 0;
+      }
+      // flag bytes of the 32 * SPB_JU consecutive vertices [vb, vb + 128): all VF_R except possibly the last one.  One
+      // aligned 4-byte store per lane for the aligned middle part (full sectors), byte stores for the ragged ends.
+      {
+        const u32 vb = b0[0] + w0[0], ve = vb + 32 * SPB_JU;
+        const u8 lastf = (f[SPB_JU] & 1u) ? VF_R : 0;
+        const u32 a0 = (vb + 3) & ~3u, a1 = ve & ~3u;             // aligned words [a0, a1)
+        const u32 wv = a0 + 4 * lane;
+        if (wv + 4 <= a1) *(u32*)(vflags + wv) = (wv + 4 == ve) ? (0x00010101u | ((u32)lastf << 24)) : 0x01010101u;
+        if (lane < a0 - vb) vflags[vb + lane] = VF_R;             // head (a0 - vb < 4 <= 128: never the last vertex)
+        if (lane < ve - a1) vflags[a1 + lane] = (a1 + lane == ve - 1) ? lastf : (u8)VF_R;
       }
       continue;
     }
