@@ -157,6 +157,22 @@ static void dev_free_raw(spb_ctx* c, void* p) {
   c->live.erase(it);
 }
 
+// Small read-backs (counters, scan totals) into the context's pinned scratch.  On the GPU they are written by a tiny kernel
+// through the mapped host pointer instead of a copy-engine transfer: a cudaMemcpy would queue behind the bulk device-to-host
+// copy of the NBP sequences that spb_compact keeps in flight on its second stream, and every host sync behind it would
+// wait for the whole gigabyte.
+#ifdef SPB_EMU
+static void pin_read(spb_ctx*, void* pinned_dst, const void* src, u64 bytes) { memcpy(pinned_dst, src, bytes); }
+#else
+__global__ void k_pin_copy(const u32* __restrict__ src, u32* dst, u32 nwords) {
+  for (u32 i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+}
+static void pin_read(spb_ctx* c, void* pinned_dst, const void* src, u64 bytes) {      // bytes: a multiple of 4, src 4-byte aligned
+  ++g_spb_launches;
+  k_pin_copy<<<1, 128, 0, c->stream>>>((const u32*)src, (u32*)pinned_dst, (u32)(bytes / 4));
+}
+#endif
 template <class T> static T* dalloc(spb_ctx* c, u64 n) { return (T*)dev_alloc_raw(c, n * sizeof(T) + 64); }
 template <class T> static void dfree(spb_ctx* c, T*& p) {
   if (!p) return;
@@ -166,7 +182,8 @@ template <class T> static void dfree(spb_ctx* c, T*& p) {
 #define ALLOC(ptr, T, n) do { (ptr) = dalloc<T>(c, (n)); if (!(ptr)) return fail(c, SPB_ENOMEM, "device allocation of %llu bytes failed (%s)", (unsigned long long)((n) * sizeof(T)), #ptr); } while (0)
 // scalar read-back through pinned host memory (one stream sync)
 template <class T> static T dread(spb_ctx* c, const T* p) {
-  dev_copy(c, c->pinned, p, sizeof(T)); dev_sync(c);
+  static_assert(sizeof(T) % 4 == 0, "");
+  pin_read(c, c->pinned, p, sizeof(T)); dev_sync(c);
   T v; memcpy(&v, c->pinned, sizeof(T)); return v;
 }
 
@@ -248,13 +265,13 @@ static int prim_scan_u32(spb_ctx* c, const u32* in, u32* out, u64 n, u64* total)
   if (n == 0) { *total = 0; return 0; }
   CUB2(cub::DeviceScan::ExclusiveSum(tmp, tb, in, out, (size_t)n, c->stream));
   u32* pin = (u32*)c->pinned;                        // read back through pinned memory: one stream sync, no staging copy
-  dev_copy(c, pin, in + n - 1, 4); dev_copy(c, pin + 1, out + n - 1, 4); dev_sync(c);
+  pin_read(c, pin, in + n - 1, 4); pin_read(c, pin + 1, out + n - 1, 4); dev_sync(c);
   *total = (u64)pin[0] + pin[1]; return 0;
 }
 static int prim_scan_u64(spb_ctx* c, const u64* in, u64* out, u64 n, u64* total) {
   if (n == 0) { *total = 0; return 0; }
   CUB2(cub::DeviceScan::ExclusiveSum(tmp, tb, in, out, (size_t)n, c->stream));
-  dev_copy(c, c->pinned, in + n - 1, 8); dev_copy(c, c->pinned + 1, out + n - 1, 8); dev_sync(c);
+  pin_read(c, c->pinned, in + n - 1, 8); pin_read(c, c->pinned + 1, out + n - 1, 8); dev_sync(c);
   *total = c->pinned[0] + c->pinned[1]; return 0;
 }
 static int prim_sort_u64_u8(spb_ctx* c, u64*& k, u8*& v, u64*& k2, u8*& v2, u64 n) {
@@ -403,7 +420,7 @@ int spb_create(spb_ctx** out, int device, void* cuda_stream) {
 #ifdef SPB_EMU
   c->pinned = (u64*)malloc(4096);
 #else
-  if (cudaHostAlloc((void**)&c->pinned, 4096, cudaHostAllocDefault) != cudaSuccess) { delete c; return SPB_ENOMEM; }
+  if (cudaHostAlloc((void**)&c->pinned, 4096, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { delete c; return SPB_ENOMEM; }
 #endif
   c->errflag = dalloc<u32>(c, 4);
   if (!c->errflag) { delete c; return SPB_ENOMEM; }
@@ -766,7 +783,7 @@ static int dedup_staged_links(spb_ctx* c) {
       default: SPB_LAUNCH_PHASED(k_partition_records<0>, 4, tiles, TPB, c->stream, c->F, c->R, c->vbits, T, c->k, bb, keys, pos, bcap, cursor, c->obits, c->errflag); break;
     }
     std::vector<u32> cnt_h(B);
-    dev_copy(c, c->pinned, cursor, B * 4ull); dev_sync(c);
+    pin_read(c, c->pinned, cursor, B * 4ull); dev_sync(c);
     memcpy(cnt_h.data(), c->pinned, B * 4ull);
     u32 e = dread(c, c->errflag);
     dfree(c, cursor);
@@ -1507,7 +1524,7 @@ static int cp_classify(spb_ctx* c, u32** init_l, u32** plo_l, u32** phi_l, u32* 
   PRIM(prim_scan_u32(c, cnt3, off3, 3ull * nT, &tot3));
   u32 marks[2] = {0, 0};
   if (nT) {
-    dev_copy(c, c->pinned, off3 + nT, 4); dev_copy(c, (u32*)c->pinned + 1, off3 + 2ull * nT, 4); dev_sync(c);
+    pin_read(c, c->pinned, off3 + nT, 4); pin_read(c, (u32*)c->pinned + 1, off3 + 2ull * nT, 4); dev_sync(c);
     memcpy(marks, c->pinned, 8);
   }
   const u32 nI = marks[0], nP = marks[1] - marks[0];
@@ -1609,12 +1626,12 @@ static int cp_emit(spb_ctx* c, u64 totv, u64 tots) {
     u32* cuts; ALLOC(cuts, u32, sl.G + 2);
     if (sl.G + 1 > 64) return fail(c, SPB_EINVAL, "more than 63 ranks");
     SPB_LAUNCH(k_nbp_cuts, 1, 64, c->stream, c->voff, nN, sl.G, cuts);
-    dev_copy(c, c->pinned, cuts + sl.rank, 8); dev_sync(c);
+    pin_read(c, c->pinned, cuts + sl.rank, 8); dev_sync(c);
     u32 nc[2]; memcpy(nc, c->pinned, 8);
     sl.n_lo = nc[0]; sl.n_hi = nc[1];
     dfree(c, cuts);
-    dev_copy(c, c->pinned, c->voff + sl.n_lo, 8); dev_copy(c, c->pinned + 1, c->voff + sl.n_hi, 8);
-    dev_copy(c, c->pinned + 2, c->soff + sl.n_lo, 8); dev_copy(c, c->pinned + 3, c->soff + sl.n_hi, 8); dev_sync(c);
+    pin_read(c, c->pinned, c->voff + sl.n_lo, 8); pin_read(c, c->pinned + 1, c->voff + sl.n_hi, 8);
+    pin_read(c, c->pinned + 2, c->soff + sl.n_lo, 8); pin_read(c, c->pinned + 3, c->soff + sl.n_hi, 8); dev_sync(c);
     sl.vert_lo = c->pinned[0]; sl.vert_n = c->pinned[1] - c->pinned[0]; sl.seq_lo = c->pinned[2]; sl.seq_n = c->pinned[3] - c->pinned[2];
   } else { sl.n_lo = 0; sl.n_hi = nN; sl.vert_lo = 0; sl.vert_n = totv; sl.seq_lo = 0; sl.seq_n = tots; }
   const u32 n_lo = sl.n_lo, n_hi = sl.n_hi;
@@ -1665,7 +1682,7 @@ static int cp_origin_pairs(spb_ctx* c) {
     dev_memset(c, counts, 0, 32); dev_memset(c, c->has01, 0, 2ull * c->n_seq + 8);
     { const int tq_ = t_begin(c); SPB_LAUNCH(k_origin_pairs, gs_grid(npos), TPB, c->stream, c->sp, T, w_lo, w_hi, c->fbits, vn, c->vflags, c->seq_off, c->n_seq, op, counts, ocap, mp,
                counts + 1, mcap, c->has01, sb); t_end(c, tq_, "k_origin_pairs_ms"); }
-    dev_copy(c, c->pinned, counts, 16); dev_sync(c);
+    pin_read(c, c->pinned, counts, 16); dev_sync(c);
     no = c->pinned[0]; nm = c->pinned[1];
     if (no <= ocap && nm <= mcap) break;
     dfree(c, op); dfree(c, mp); ocap = std::max(ocap, no); mcap = std::max(mcap, nm);
@@ -1688,7 +1705,7 @@ static int cp_origins_finish(spb_ctx* c, u64* op, u64 no, u64 ocap, u64* mp, u64
     memcpy(c->pinned, &no, 8); memcpy(c->pinned + 1, &nm, 8);
     dev_copy(c, counts, c->pinned, 16);
     SPB_LAUNCH(k_origin_quirk, nblk(c->n_seq, TPB), TPB, c->stream, has01, c->n_seq, vnbp_view(c), c->vflags, op, counts, ocap, mp, counts + 1, mcap, sb);
-    dev_copy(c, c->pinned + 2, counts, 16); dev_sync(c);
+    pin_read(c, c->pinned + 2, counts, 16); dev_sync(c);
     no = c->pinned[2]; nm = c->pinned[3];
     dfree(c, counts);
     if (no > ocap || nm > mcap) return fail(c, SPB_ECUDA, "internal: origin pair lists too small for the quirk entries");
@@ -1833,7 +1850,7 @@ int spb_mg_slice_ids(spb_ctx* c, uint32_t rank, uint32_t n_ranks) {
   for (int i = 0; i < 2; ++i) {
     const u64 p = i ? sl.pos_hi : sl.pos_lo;
     if (p >= c->T) { vf[i] = c->nV; continue; }
-    dev_copy(c, (u32*)c->pinned + i, c->blkoff + (p >> 8), 4);
+    pin_read(c, (u32*)c->pinned + i, c->blkoff + (p >> 8), 4);
   }
   dev_sync(c);
   for (int i = 0; i < 2; ++i) { const u64 p = i ? sl.pos_hi : sl.pos_lo; if (p < c->T) vf[i] = ((u32*)c->pinned)[i]; }

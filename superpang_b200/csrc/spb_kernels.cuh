@@ -1016,20 +1016,28 @@ k_assign_ids(const u32* sp_in, u32* sp, const u32* __restrict__ vbits, u64 T, u6
 #pragma unroll
     for (u32 j = 0; j < SPB_JU; ++j) allfirst = allfirst && f[j] == 0xFFFFFFFFu;
     if (allfirst) {                                  // warp-uniform: 128 first appearances in a row, ids are consecutive
-      u32 b0[SPB_JU], w0[SPB_JU];
+      const u64 g0 = wd0 * 32, g1 = g0 + 32 * SPB_JU;
+      const u32 vb = __ldg(blkoff + (wd0 >> 3)) + __ldg(wpre + wd0);     // vertex of position g0; position g0 + i is vertex vb + i
+      // (all tests on the group's range are warp-uniform: nothing but the flag bytes is written for a group outside the
+      // caller's position ranges, and a group inside them needs no per-lane test)
+      if (g0 >= lo && g1 <= hi) {
 #pragma unroll
-      for (u32 j = 0; j < SPB_JU; ++j) { b0[j] = __ldg(blkoff + ((wd0 + j) >> 3)); w0[j] = __ldg(wpre + wd0 + j); }
+        for (u32 j = 0; j < SPB_JU; ++j) sp[g0 + 32 * j + lane] = vb + 32 * j + lane;
+      } else if (g0 < hi && g1 > lo) {
 #pragma unroll
-      for (u32 j = 0; j < SPB_JU; ++j) {
-        const u64 p = (wd0 + j) * 32 + lane;
-        const u32 vid = b0[j] + w0[j] + lane;
-        if (p >= lo && p < hi) sp[p] = vid;
-        if (p >= tlo && p < thi) v2pos[vid] = (u32)p;
+        for (u32 j = 0; j < SPB_JU; ++j) { const u64 p = g0 + 32 * j + lane; if (p >= lo && p < hi) sp[p] = vb + 32 * j + lane; }
+      }
+      if (g0 >= tlo && g1 <= thi) {
+#pragma unroll
+        for (u32 j = 0; j < SPB_JU; ++j) v2pos[vb + 32 * j + lane] = (u32)(g0 + 32 * j + lane);
+      } else if (g0 < thi && g1 > tlo) {
+#pragma unroll
+        for (u32 j = 0; j < SPB_JU; ++j) { const u64 p = g0 + 32 * j + lane; if (p >= tlo && p < thi) v2pos[vb + 32 * j + lane] = (u32)p; }
       }
       // flag bytes of the 32 * SPB_JU consecutive vertices [vb, vb + 128): all VF_R except possibly the last one.  One
       // aligned 4-byte store per lane for the aligned middle part (full sectors), byte stores for the ragged ends.
       {
-        const u32 vb = b0[0] + w0[0], ve = vb + 32 * SPB_JU;
+        const u32 ve = vb + 32 * SPB_JU;
         const u8 lastf = (f[SPB_JU] & 1u) ? VF_R : 0;
         const u32 a0 = (vb + 3) & ~3u, a1 = ve & ~3u;             // aligned words [a0, a1)
         const u32 wv = a0 + 4 * lane;
