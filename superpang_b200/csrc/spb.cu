@@ -1680,7 +1680,7 @@ static int cp_origin_pairs(spb_ctx* c) {
   for (int attempt = 0; attempt < 2; ++attempt) {
     ALLOC(op, u64, ocap + c->n_seq + 1); ALLOC(mp, u64, mcap + c->n_seq + 1);      // room for the quirk entries (one per sequence at most)
     dev_memset(c, counts, 0, 32); dev_memset(c, c->has01, 0, 2ull * c->n_seq + 8);
-    { const int tq_ = t_begin(c); SPB_LAUNCH(k_origin_pairs, gs_grid(npos), TPB, c->stream, c->sp, T, w_lo, w_hi, c->fbits, vn, c->vflags, c->seq_off, c->n_seq, op, counts, ocap, mp,
+    { const int tq_ = t_begin(c); SPB_LAUNCH(k_origin_pairs, gs_grid(npos), TPB, c->stream, c->sp, T, w_lo, w_hi, c->fbits, c->blkoff, c->wpre, vn, c->vflags, c->seq_off, c->n_seq, op, counts, ocap, mp,
                counts + 1, mcap, c->has01, sb); t_end(c, tq_, "k_origin_pairs_ms"); }
     pin_read(c, c->pinned, counts, 16); dev_sync(c);
     no = c->pinned[0]; nm = c->pinned[1];

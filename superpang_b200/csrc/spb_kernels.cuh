@@ -926,6 +926,22 @@ __global__ void k_block_counts(const u32* __restrict__ fbits, u32* __restrict__ 
 }
 
 #define SPB_JU 4                                     // bitmap words per warp iteration (independent loads in flight)
+// The per-position passes (ids, junction entries, origin pairs) walk the first-appearance bitmap in windows of 32 words
+// (1024 positions, one word per lane).  A window in which every position is a first appearance -- the normal case on
+// mostly-unique inputs -- is handled with ONE memory round trip per window (the passes are latency-bound, not
+// bandwidth-bound); any other window goes through the general code, SPB_JU words at a time.
+#define SPB_WIN 32
+__device__ __forceinline__ bool window_all_first(const u32* __restrict__ fbits, u64 wb, u64 nwords, u32 lane) {
+#ifdef SPB_EMU
+  (void)lane;
+  if (wb + SPB_WIN > nwords) return false;
+  for (u32 i = 0; i < SPB_WIN; ++i) if (fbits[wb + i] != 0xFFFFFFFFu) return false;
+  return true;
+#else
+  const u32 fw = wb + lane < nwords ? __ldg(fbits + wb + lane) : 0u;
+  return __all_sync(0xffffffffu, fw == 0xFFFFFFFFu);
+#endif
+}
 // first-appearance bitmap fbits = wbits & ~dbits, and per 256-position block counts
 __global__ void k_first_bits(const u32* __restrict__ wbits, const u32* __restrict__ dbits, u32* __restrict__ fbits, u64 nblk) {
   u64 b = SPB_GTID();
@@ -1007,7 +1023,41 @@ k_assign_ids(const u32* sp_in, u32* sp, const u32* __restrict__ vbits, u64 T, u6
   const u64 nwords = (T + 31) / 32;
   const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
   const u32 lane = threadIdx.x & 31;
-  for (u64 wd0 = (SPB_GTID() >> 5) * SPB_JU; wd0 < nwords; wd0 += nwarps * SPB_JU) {
+  for (u64 wb = (SPB_GTID() >> 5) * SPB_WIN; wb < nwords; wb += nwarps * SPB_WIN) {
+   {
+    // ---- window of 1024 consecutive first appearances: vertex vb + i at position g0 + i.  The rank of the window and the
+    // bit that follows it are loaded together with the bitmap words (independent addresses: one round trip).
+    const u32 vb_w = __ldg(blkoff + (wb >> 3)) + __ldg(wpre + wb);
+    const u32 nextbit = wb + SPB_WIN <= nwords ? (__ldg(fbits + wb + SPB_WIN) & 1u) : 0u;
+    if (window_all_first(fbits, wb, nwords, lane)) {
+      const u64 g0 = wb * 32, g1 = g0 + 32 * SPB_WIN;
+      if (g0 >= lo && g1 <= hi) {
+#pragma unroll 8
+        for (u32 j = 0; j < SPB_WIN; ++j) sp[g0 + 32 * j + lane] = vb_w + 32 * j + lane;
+      } else if (g0 < hi && g1 > lo) {
+        for (u32 j = 0; j < SPB_WIN; ++j) { const u64 p = g0 + 32 * j + lane; if (p >= lo && p < hi) sp[p] = vb_w + 32 * j + lane; }
+      }
+      if (g0 >= tlo && g1 <= thi) {
+#pragma unroll 8
+        for (u32 j = 0; j < SPB_WIN; ++j) v2pos[vb_w + 32 * j + lane] = (u32)(g0 + 32 * j + lane);
+      } else if (g0 < thi && g1 > tlo) {
+        for (u32 j = 0; j < SPB_WIN; ++j) { const u64 p = g0 + 32 * j + lane; if (p >= tlo && p < thi) v2pos[vb_w + 32 * j + lane] = (u32)p; }
+      }
+      // flag bytes [vb, vb + 1024): VF_R everywhere except possibly the last one; aligned 4-byte stores for the middle
+      const u32 ve = vb_w + 32 * SPB_WIN;
+      const u8 lastf = nextbit ? VF_R : 0;
+      const u32 a0 = (vb_w + 3) & ~3u, a1 = ve & ~3u;
+#pragma unroll 8
+      for (u32 j = 0; j < SPB_WIN / 4; ++j) {
+        const u32 wv = a0 + 4 * (32 * j + lane);
+        if (wv + 4 <= a1) *(u32*)(vflags + wv) = (wv + 4 == ve) ? (0x00010101u | ((u32)lastf << 24)) : 0x01010101u;
+      }
+      if (lane < a0 - vb_w) vflags[vb_w + lane] = VF_R;
+      if (lane < ve - a1) vflags[a1 + lane] = (a1 + lane == ve - 1) ? lastf : (u8)VF_R;
+      continue;
+    }
+   }
+   for (u64 wd0 = wb; wd0 < wb + SPB_WIN && wd0 < nwords; wd0 += SPB_JU) {
     u32 f[SPB_JU + 1], r[SPB_JU], fr[SPB_JU];
     bool first[SPB_JU], mine[SPB_JU], act[SPB_JU];
 #pragma unroll
@@ -1101,6 +1151,7 @@ k_assign_ids(const u32* sp_in, u32* sp, const u32* __restrict__ vbits, u64 T, u6
         vflags[vid] = nextfirst ? VF_R : 0;          // (p, p+1) both first appearances => edge (vid, vid+1)
       }
     }
+   }
   }
 }
 
@@ -1117,7 +1168,13 @@ __global__ void k_junction_emit(const u32* __restrict__ sp, u64 T, u64 w_lo, u64
   const u64 nwords = (T + 31) / 32;
   const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
   const u32 lane = threadIdx.x & 31;
-  for (u64 wd0 = w_lo + (SPB_GTID() >> 5) * SPB_JU; wd0 < w_hi; wd0 += nwarps * SPB_JU) {
+  for (u64 wb = w_lo + (SPB_GTID() >> 5) * SPB_WIN; wb < w_hi; wb += nwarps * SPB_WIN) {
+   {
+    // window of 1024 first appearances followed by one more: nothing but implicit edges
+    const u32 nextbit = wb + SPB_WIN <= nwords ? (__ldg(fbits + wb + SPB_WIN) & 1u) : 0u;
+    if (wb + SPB_WIN <= w_hi && window_all_first(fbits, wb, nwords, lane) && nextbit) continue;
+   }
+   for (u64 wd0 = wb; wd0 < wb + SPB_WIN && wd0 < w_hi; wd0 += SPB_JU) {
     u32 f[SPB_JU + 1];
 #pragma unroll
     for (u32 j = 0; j <= SPB_JU; ++j) f[j] = wd0 + j <= nwords ? __ldg(fbits + wd0 + j) : 0u;
@@ -1173,6 +1230,7 @@ __global__ void k_junction_emit(const u32* __restrict__ sp, u64 T, u64 w_lo, u64
       Jk[slot] = ((u64)u[j] << 32) | w[j]; Js[slot] = (u8)(side_u | (side_w << 1));
       if (n == 2) { Jk[slot + 1] = ((u64)w[j] << 32) | u[j]; Js[slot + 1] = (u8)(side_w | (side_u << 1)); }
     }
+   }
   }
 }
 
@@ -1657,9 +1715,26 @@ __global__ void k_nbp_cuts(const u64* __restrict__ voff, u32 nN, u32 G, u32* __r
   cuts[r] = lo;
 }
 
+// do any of the n flag bytes from vflags[v0] on carry one of the bits of `mask8`?  (warp-cooperative: aligned 4-byte loads;
+// the up to three bytes before v0 that share its word are looked at too -- a false positive only costs the general path)
+__device__ __forceinline__ bool window_flags_any(const u8* __restrict__ vflags, u32 v0, u32 n, u32 mask8, u32 lane) {
+#ifdef SPB_EMU
+  (void)lane;
+  for (u32 i = 0; i < n; ++i) if (vflags[v0 + i] & mask8) return true;
+  return false;
+#else
+  const u32 m = mask8 * 0x01010101u;
+  const u32 b = v0 & ~3u, e = v0 + n;
+  bool hit = false;
+  for (u32 w = b + 4 * lane; w < e; w += 128) hit |= (__ldg((const u32*)(vflags + w)) & m) != 0;
+  return __any_sync(0xffffffffu, hit);
+#endif
+}
+
 // K13: origins.  (undirected NBP, sequence) pairs where the NBP changes along a sequence; (init vertex,
 // sequence) membership pairs for the inits of 2-vertex NBPs (reference lib/Assembler.py:1212-1262).
-__global__ void k_origin_pairs(const u32* __restrict__ sp, u64 T, u64 w_lo, u64 w_hi, const u32* __restrict__ fbits, VNbp vn, const u8* __restrict__ vflags,
+__global__ void k_origin_pairs(const u32* __restrict__ sp, u64 T, u64 w_lo, u64 w_hi, const u32* __restrict__ fbits, const u32* __restrict__ blkoff,
+                               const u8* __restrict__ wpre, VNbp vn, const u8* __restrict__ vflags,
                                const u64* __restrict__ seq_off, u32 n_seq, u64* __restrict__ opairs, u64* ocount, u64 ocap,
                                u64* __restrict__ mpairs, u64* mcount, u64 mcap, u8* __restrict__ has01, u32 sb) {
   // one warp per SPB_JU x 32 positions, grid-stride.  Where p-1 and p are consecutive first appearances (vertices v-1, v
@@ -1669,7 +1744,17 @@ __global__ void k_origin_pairs(const u32* __restrict__ sp, u64 T, u64 w_lo, u64 
   const u64 nwords = (T + 31) / 32;
   const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
   const u32 lane = threadIdx.x & 31;
-  for (u64 wd0 = w_lo + (SPB_GTID() >> 5) * SPB_JU; wd0 < w_hi; wd0 += nwarps * SPB_JU) {   // [w_lo, w_hi): our bitmap words (sp filled from position 32 * w_lo - 1)
+  for (u64 wb = w_lo + (SPB_GTID() >> 5) * SPB_WIN; wb < w_hi; wb += nwarps * SPB_WIN) {   // [w_lo, w_hi): our bitmap words (sp filled from position 32 * w_lo - 1)
+   {
+    // window of 1024 first appearances preceded by one more: vertices vb .. vb + 1023 in a row, every position follows its
+    // predecessor over an implicit edge, so the NBP changes only where a vertex is an init or starts a piece -- if no flag
+    // byte of the window says so (pieces are long), there is nothing to emit here
+    const u32 vb_w = __ldg(blkoff + (wb >> 3)) + __ldg(wpre + wb);
+    const u32 prevbit = wb ? (__ldg(fbits + wb - 1) >> 31) : 0u;
+    if (wb + SPB_WIN <= w_hi && prevbit && vb_w > 1 && window_all_first(fbits, wb, nwords, lane) &&
+        !window_flags_any(vflags, vb_w, 32 * SPB_WIN, VF_INIT | VF_PSTART | VF_IN2, lane)) continue;
+   }
+   for (u64 wd0 = wb; wd0 < wb + SPB_WIN && wd0 < w_hi; wd0 += SPB_JU) {
     u32 v[SPB_JU], pv[SPB_JU];
     bool pair_first[SPB_JU];
 #pragma unroll
@@ -1713,6 +1798,7 @@ __global__ void k_origin_pairs(const u32* __restrict__ sp, u64 T, u64 w_lo, u64 
       u64 i = warp_append(ocount, emit_o); if (emit_o && i < ocap) opairs[i] = ((u64)c[j] << sb) | s;
       u64 jj = warp_append(mcount, in2);   if (in2 && jj < mcap) mpairs[jj] = ((u64)vv << sb) | s;
     }
+   }
   }
 }
 // compress_vertices leading-zero quirk (reference lib/vtools.pyx:29-45): a sequence whose smallest
