@@ -245,6 +245,22 @@ typedef struct spb_fasta {
 } spb_fasta;
 int spb_read_fasta(const char* path, uint32_t gap_size, spb_fasta* out, char* err, uint64_t err_cap);
 void spb_free_fasta(spb_fasta* fa);
+
+/* ---- output writers (writer half) -------------------------------------------------------------------
+ * spb_write_fasta: ">{name}\n{seq}\n" per record in the order given -- byte for byte what the reference's write_fasta
+ * (lib/utils.py:62-65) writes for a dict, i.e. the format of NBPs.fasta, graph.fastg, *.core.fasta and *.aux.fasta
+ * (scripts/SuperPang.py:279-282).  names: the n names back to back with name_off[n + 1] (host); seqs / seq_off[n + 1] may be
+ * HOST or DEVICE memory (the CSR of spb_get_nbp_seqs or spb_path_sequences left on the device): the sequences are streamed
+ * to the file in 64 MB chunks.
+ * spb_write_origins_tsv: NBP2origins.tsv and the edge table (scripts/SuperPang.py:284-294): `header`, then per node
+ * "{node}\t{origins ','-joined}\t{their bins ','-joined}\t{distinct bins}/{n_genomes}\n"; origins as a CSR of indices
+ * into the source-sequence name table (origin_off / origin_idx: host or device, the form of spb_get_nbp_origins). */
+int spb_write_fasta(const char* path, uint64_t n, const char* names, const uint64_t* name_off, const uint8_t* seqs, const uint64_t* seq_off,
+                    char* err, uint64_t err_cap);
+int spb_write_origins_tsv(const char* path, const char* header, uint64_t n, const char* node_names, const uint64_t* node_off,
+                          const uint64_t* origin_off, const uint32_t* origin_idx, uint32_t n_orig, const char* orig_names,
+                          const uint64_t* orig_name_off, const uint32_t* orig_bin, const char* bin_names, const uint64_t* bin_name_off,
+                          uint32_t n_bins, uint32_t n_genomes, char* err, uint64_t err_cap);
 /* Current counters (n_seq_intervals is filled by the first spb_get_seq_intervals call, which may
  * be made with NULL buffers just to size them). */
 int spb_get_counts(spb_ctx* ctx, spb_counts* out);

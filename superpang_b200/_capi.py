@@ -25,7 +25,7 @@ EXPORTS = (
     "spb_get_nbp_origins", "spb_get_counts", "spb_get_stage_stats", "spb_build_kind", "spb_launch_count",
     "spb_get_nbp_graph", "spb_get_nbp_orientation_counts", "spb_get_seq_nbps", "spb_get_bubble_groups", "spb_path_sequences", "spb_path_origins", "spb_read_fasta", "spb_free_fasta", "spb_mg_slice", "spb_mg_probe", "spb_mg_records", "spb_mg_dedup", "spb_mg_scatter", "spb_mg_dedup_links", "spb_mg_apply_links", "spb_mg_owned_links", "spb_mg_part_records", "spb_mg_part_dedup", "spb_mg_buffers", "spb_mg_ids", "spb_mg_graph",
     "spb_mg_slice_ids", "spb_mg_slice_junctions", "spb_mg_slice_graph", "spb_mg_slice_classify", "spb_mg_slice_contract", "spb_mg_slice_emit",
-    "spb_mg_slice_finish", "spb_mg_shard", "spb_mg_complete", "spb_set_host_output", "spb_mg_shard_to_host",
+    "spb_mg_slice_finish", "spb_mg_shard", "spb_mg_complete", "spb_set_host_output", "spb_mg_shard_to_host", "spb_write_fasta", "spb_write_origins_tsv",
 )
 
 
@@ -69,6 +69,41 @@ def read_fasta_native(path, gap_size=1, lib=None):
     finally:
         lib.spb_free_fasta(C.byref(fa))
     return names, buf, off
+
+
+def _name_table(names):
+    """(bytes blob, uint64 offsets[n + 1]) of a list of str."""
+    enc = [n.encode() for n in names]
+    off = np.zeros(len(enc) + 1, dtype=np.uint64)
+    np.cumsum([len(e) for e in enc], out=off[1:])
+    return b"".join(enc), off
+
+
+def write_fasta_native(path, names, seqs, seq_off, lib=None):
+    """FASTA file of `names` with the sequences of a CSR (seqs uint8, seq_off uint64[n + 1]) that may live in HOST or DEVICE
+    memory (numpy arrays, torch tensors or raw device pointers) -- spb_write_fasta; byte-identical to the reference's
+    write_fasta (lib/utils.py:62-65) on the same records."""
+    lib = lib if lib is not None else load_library()
+    blob, noff = _name_table(names)
+    err = C.create_string_buffer(512)
+    rc = lib.spb_write_fasta(os.fsencode(path), len(names), blob, noff.ctypes.data, _ptr(seqs), _ptr(seq_off), err, 512)
+    if rc != 0:
+        raise OSError(err.value.decode() or f"spb_write_fasta failed ({rc})")
+
+
+def write_origins_tsv_native(path, header, node_names, origin_off, origin_idx, orig_names, orig_bin, bin_names, n_genomes, lib=None):
+    """NBP2origins.tsv-style table (scripts/SuperPang.py:284-294) -- spb_write_origins_tsv.  origin_off / origin_idx: CSR of
+    indices into orig_names (host or device memory); orig_bin[i] = index into bin_names of source sequence i."""
+    lib = lib if lib is not None else load_library()
+    nb, noff = _name_table(node_names)
+    ob, ooff = _name_table(orig_names)
+    bb, boff = _name_table(bin_names)
+    orig_bin = np.ascontiguousarray(orig_bin, dtype=np.uint32)
+    err = C.create_string_buffer(512)
+    rc = lib.spb_write_origins_tsv(os.fsencode(path), header.encode(), len(node_names), nb, noff.ctypes.data, _ptr(origin_off), _ptr(origin_idx),
+                                   len(orig_names), ob, ooff.ctypes.data, orig_bin.ctypes.data, bb, boff.ctypes.data, len(bin_names), int(n_genomes), err, 512)
+    if rc != 0:
+        raise OSError(err.value.decode() or f"spb_write_origins_tsv failed ({rc})")
 
 
 def load_library(path=None):
@@ -141,6 +176,9 @@ def _declare(lib):
     lib.spb_mg_complete.argtypes = [vp, C.POINTER(SpbCounts)]
     lib.spb_set_host_output.argtypes = [vp, u8p, C.c_uint64]
     lib.spb_mg_shard_to_host.argtypes = [vp, C.c_int, vp, pu64]
+    lib.spb_write_fasta.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, u64p, u8p, u64p, C.c_char_p, C.c_uint64]
+    lib.spb_write_origins_tsv.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_char_p, u64p, u64p, u32p, C.c_uint32, C.c_char_p, u64p, u32p,
+                                          C.c_char_p, u64p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint64]
     return lib
 
 
@@ -705,6 +743,21 @@ class Engine:
         seq = np.empty(self.counts.nbp_bases, dtype=np.uint8)
         self._ck(self.lib.spb_get_nbp_seqs(self.h, off.ctypes.data, seq.ctypes.data))
         return off, seq
+
+    def write_nbp_fasta(self, path, names=None):
+        """The raw NBP sequences as a FASTA file straight from the device buffers (no host copy of the sequence array in
+        Python): record i is named names[i] (default "NBP_{i}").  Returns the number of records."""
+        import torch
+        n = int(self.counts.n_nbp)
+        names = [f"NBP_{i}" for i in range(n)] if names is None else list(names)
+        assert len(names) == n
+        cuda = self.kind.startswith("cuda")
+        dev = torch.device("cuda", self.device) if cuda else torch.device("cpu")
+        soff = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        seq = torch.empty(max(int(self.counts.nbp_bases), 1), dtype=torch.uint8, device=dev)
+        self._ck(self.lib.spb_get_nbp_seqs(self.h, soff.data_ptr(), seq.data_ptr()))      # device-to-device
+        write_fasta_native(path, names, seq, soff, lib=self.lib)
+        return n
 
     def nbp_graph(self):
         """(off, succ, rev): successors CSR of the NBP graph and the reverse-orientation partner of every raw NBP."""

@@ -2449,6 +2449,100 @@ int spb_read_fasta(const char* path, uint32_t gap_size, spb_fasta* out, char* er
   out->seq_off[names.size()] = o;
   return SPB_OK;
 }
+// ------------------------------------------------------------------------------------------- writers
+// copy `n` bytes that may live in device memory to the host, through a small pinned staging buffer
+static bool fetch_bytes(const uint8_t* src, u64 n, std::vector<uint8_t>& host) {
+  host.resize(n);
+  if (!n) return true;
+#ifdef SPB_EMU
+  memcpy(host.data(), src, n);
+  return true;
+#else
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, src) != cudaSuccess || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)) {
+    cudaGetLastError();                                // plain host memory (also: no device present at all)
+    memcpy(host.data(), src, n);
+    return true;
+  }
+  return cudaMemcpy(host.data(), src, n, cudaMemcpyDeviceToHost) == cudaSuccess;
+#endif
+}
+// FASTA records ">{name}\n{seq}\n" in the order given -- what the reference's write_fasta (lib/utils.py:62-65) produces for
+// a dict in insertion order, as used for NBPs.fasta / graph.fastg / *.core.fasta / *.aux.fasta (scripts/SuperPang.py:279-282).
+// names: the n names back to back (no terminators) with name_off[n + 1]; seqs + seq_off[n + 1]: sequence bytes, in host
+// OR device memory (e.g. the buffers of spb_get_nbp_seqs / spb_path_sequences left on the device); written in chunks of
+// 64 MB so that a multi-gigabyte result never needs a second full copy on the host.
+int spb_write_fasta(const char* path, uint64_t n, const char* names, const uint64_t* name_off, const uint8_t* seqs, const uint64_t* seq_off,
+                    char* err, uint64_t err_cap) {
+  if (!path || (n && (!names || !name_off || !seqs || !seq_off))) return SPB_EINVAL;
+  FILE* f = fopen(path, "wb");
+  if (!f) { fasta_error(err, err_cap, std::string("cannot open ") + path + " for writing"); return SPB_EINVAL; }
+  std::vector<uint64_t> so;
+  { std::vector<uint8_t> tmp; if (n && !fetch_bytes((const uint8_t*)seq_off, 8 * (n + 1), tmp)) { fclose(f); fasta_error(err, err_cap, "cannot read the sequence offsets"); return SPB_ECUDA; }
+    so.resize(n + 1); if (n) memcpy(so.data(), tmp.data(), 8 * (n + 1)); }
+  const u64 CH = 64ull << 20;
+  std::vector<uint8_t> buf; std::string out;
+  u64 i = 0;
+  while (i < n) {                                       // records [i, j): as many as fit into one chunk (at least one)
+    u64 j = i + 1;
+    while (j < n && so[j + 1] - so[i] <= CH) ++j;
+    if (!fetch_bytes(seqs + so[i], so[j] - so[i], buf)) { fclose(f); fasta_error(err, err_cap, "cannot read the sequences"); return SPB_ECUDA; }
+    out.clear(); out.reserve((so[j] - so[i]) + (name_off[j] - name_off[i]) + 3 * (j - i));
+    for (u64 r = i; r < j; ++r) {
+      out.push_back('>'); out.append(names + name_off[r], name_off[r + 1] - name_off[r]); out.push_back('\n');
+      out.append((const char*)buf.data() + (so[r] - so[i]), so[r + 1] - so[r]); out.push_back('\n');
+    }
+    if (fwrite(out.data(), 1, out.size(), f) != out.size()) { fclose(f); fasta_error(err, err_cap, std::string("short write to ") + path); return SPB_EINVAL; }
+    i = j;
+  }
+  if (fclose(f) != 0) { fasta_error(err, err_cap, std::string("cannot close ") + path); return SPB_EINVAL; }
+  return SPB_OK;
+}
+// NBP2origins.tsv / the edge table (scripts/SuperPang.py:284-294): header, then per node
+//   "{node}\t{origins joined by ','}\t{bin of every origin joined by ','}\t{number of distinct bins}/{n_genomes}\n".
+// Origins are indices into the table of source-sequence names (orig_names / orig_name_off[n_orig + 1]), in the order the
+// caller wants them printed, as a CSR (origin_off[n + 1], origin_idx -- host or device memory, the form of
+// spb_get_nbp_origins); orig_bin[n_orig] = index of the bin (genome) of every source sequence, bin names likewise.
+int spb_write_origins_tsv(const char* path, const char* header, uint64_t n, const char* node_names, const uint64_t* node_off,
+                          const uint64_t* origin_off, const uint32_t* origin_idx, uint32_t n_orig, const char* orig_names,
+                          const uint64_t* orig_name_off, const uint32_t* orig_bin, const char* bin_names, const uint64_t* bin_name_off,
+                          uint32_t n_bins, uint32_t n_genomes, char* err, uint64_t err_cap) {
+  if (!path || !header || (n && (!node_names || !node_off || !origin_off))) return SPB_EINVAL;
+  std::vector<uint8_t> t0, t1;
+  if (n && !fetch_bytes((const uint8_t*)origin_off, 8 * (n + 1), t0)) { fasta_error(err, err_cap, "cannot read the origin offsets"); return SPB_ECUDA; }
+  const uint64_t* oo = (const uint64_t*)t0.data();
+  const u64 tot = n ? oo[n] : 0;
+  if (tot && !fetch_bytes((const uint8_t*)origin_idx, 4 * tot, t1)) { fasta_error(err, err_cap, "cannot read the origin lists"); return SPB_ECUDA; }
+  const uint32_t* oi = (const uint32_t*)t1.data();
+  FILE* f = fopen(path, "wb");
+  if (!f) { fasta_error(err, err_cap, std::string("cannot open ") + path + " for writing"); return SPB_EINVAL; }
+  std::string out(header);
+  std::vector<uint32_t> seen_mark(n_bins, 0xFFFFFFFFu);
+  for (u64 r = 0; r < n; ++r) {
+    out.append(node_names + node_off[r], node_off[r + 1] - node_off[r]); out.push_back('\t');
+    for (u64 x = oo[r]; x < oo[r + 1]; ++x) {
+      const u32 o = oi[x];
+      if (o >= n_orig) { fclose(f); fasta_error(err, err_cap, "origin index out of range"); return SPB_EINVAL; }
+      if (x > oo[r]) out.push_back(',');
+      out.append(orig_names + orig_name_off[o], orig_name_off[o + 1] - orig_name_off[o]);
+    }
+    out.push_back('\t');
+    u32 distinct = 0;
+    for (u64 x = oo[r]; x < oo[r + 1]; ++x) {
+      const u32 b = orig_bin[oi[x]];
+      if (b >= n_bins) { fclose(f); fasta_error(err, err_cap, "bin index out of range"); return SPB_EINVAL; }
+      if (x > oo[r]) out.push_back(',');
+      out.append(bin_names + bin_name_off[b], bin_name_off[b + 1] - bin_name_off[b]);
+      if (seen_mark[b] != (u32)r) { seen_mark[b] = (u32)r; ++distinct; }
+    }
+    out.push_back('\t'); out.append(std::to_string(distinct)); out.push_back('/'); out.append(std::to_string(n_genomes)); out.push_back('\n');
+    if (out.size() > (32u << 20)) { if (fwrite(out.data(), 1, out.size(), f) != out.size()) { fclose(f); fasta_error(err, err_cap, "short write"); return SPB_EINVAL; } out.clear(); }
+  }
+  if (fwrite(out.data(), 1, out.size(), f) != out.size()) { fclose(f); fasta_error(err, err_cap, "short write"); return SPB_EINVAL; }
+  if (fclose(f) != 0) { fasta_error(err, err_cap, std::string("cannot close ") + path); return SPB_EINVAL; }
+  return SPB_OK;
+}
+
 void spb_free_fasta(spb_fasta* fa) {
   if (!fa) return;
   free(fa->ascii); free(fa->seq_off); free(fa->names);

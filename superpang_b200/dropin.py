@@ -16,7 +16,8 @@ re-implemented here but taken from the INSTALLED reference package at run time (
     test of the forward-strand selection) is answered from the per-sequence NBP sets computed on the device
     (`spb_get_seq_nbps`).
 
-`main()` runs the reference's CLI (`scripts/SuperPang.py`) with this class bound at its call site, so `-k`, `-t`,
+`main()` runs the reference's CLI (`scripts/SuperPang.py`) with this class bound at its call site and the native FASTA
+writer (`spb_write_fasta`) bound in place of `lib/utils.py:write_fasta`, so `-k`, `-t`,
 `--lowmem` and the output files (`NBPs.fasta`, `NBP2origins.tsv`, `graph.fastg`, `assembly.info.tsv`) are the CLI's own.
 """
 import inspect
@@ -90,8 +91,10 @@ def run(b200, minlen, mincov, bubble_identity_threshold, genome_assignment_thres
 def main(argv=None):
     """The reference CLI (`scripts/SuperPang.py`) with the B200 Assembler bound at its only call site (`:199`)."""
     from .assembler import Assembler
+    from . import writers
     import superpang.scripts.SuperPang as cli_mod
     cli_mod.Assembler = Assembler
+    cli_mod.write_fasta = writers.write_fasta          # NBPs.fasta / graph.fastg / *.core / *.aux through the native writer (:279-282)
     if argv is not None:
         sys.argv = [cli_mod.__file__] + list(argv)
     cli_mod.cli()
