@@ -234,6 +234,18 @@ int spb_path_sequences(spb_ctx* ctx, uint32_t n_paths, const uint64_t* off, cons
  * when it exceeds cap only out_off is filled: call again with cap >= *n_pairs.  Needs spb_compact. */
 int spb_path_origins(spb_ctx* ctx, uint32_t n_paths, const uint64_t* off, const uint32_t* verts, uint64_t cap, uint64_t* n_pairs,
                      uint64_t* out_off, uint32_t* seq_idx);
+/* Extended forms (completed in round 2).  kind 0: paths are vertex lists (as above); kind 1: paths are lists
+ * of RAW NBP IDS (indices into spb_get_nbps; consecutive NBPs share their junction vertex, the way the reference joins them,
+ * `lib/Assembler.py:810`) and are expanded to vertex lists on the device -- no vertex ever crosses PCIe.
+ * spb_path_sequences_ex: vert_off (optional, host uint64[n_paths + 1]) receives the vertex offsets of the paths; ascii ==
+ * NULL asks for the sizes only; path i is written at vert_off[i] + i * (k - 1).
+ * spb_path_origins_ex: additionally takes `bubble_vertex2origins` (`lib/Assembler.py:922`, `:1236`) as a CSR over ascending
+ * vertex ids -- bub_vert uint32[n_bub], bub_off uint64[n_bub + 1], bub_seq uint32 (sequence indices), host arrays -- whose
+ * lists are united with the origins of every vertex the rule looks at, as the reference does. */
+int spb_path_sequences_ex(spb_ctx* ctx, int kind, uint32_t n_paths, const uint64_t* off, const uint32_t* items, uint64_t* vert_off, uint8_t* ascii);
+int spb_path_origins_ex(spb_ctx* ctx, int kind, uint32_t n_paths, const uint64_t* off, const uint32_t* items, uint32_t n_bub,
+                        const uint32_t* bub_vert, const uint64_t* bub_off, const uint32_t* bub_seq, uint64_t cap, uint64_t* n_pairs,
+                        uint64_t* out_off, uint32_t* seq_idx);
 /* FASTA reader + N-splitter: native form of the reference's `read_fasta(fasta, ambigs='as_Ns',
  * Ns='split', gap_size)` (`lib/utils.py:5-30`, `:52-59`): whitespace / '.' / '-' removed, upper case, U -> T, IUPAC
  * ambiguity codes -> N, any other character is an error, records split at runs of gap_size Ns into `{name}_Nsplit_{i}`,

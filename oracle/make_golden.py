@@ -47,6 +47,7 @@ def full(res):
         orient_counts=[int(x) for x in res["orient_counts"]],
         orient_sets=res["orient_sets"],
         joined=[[list(p), s, list(o)] for p, s, o in res["joined"]],
+        bubble_map=res["bubble_map"], bubble_oris=res["bubble_oris"],
     )
 
 

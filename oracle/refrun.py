@@ -186,10 +186,28 @@ def run_reference(fasta, ksize=301, threads=1, debug=True, with_origins=True, qu
                 joined_oris.append(tuple(sorted({o.split('_Nsplit_')[0] for o in good})))
         else:
             joined_oris = [()] * len(joined)
+        # ---- the same origin rule with a NON-EMPTY bubble_vertex2origins (:922, :1236): golden vectors for
+        #      spb_path_origins_ex.  The map is made up deterministically from the paths themselves (a popped bubble leaves
+        #      exactly such vertex -> origin-name lists behind); every raw NBP and joined path is then asked about.
+        bubble_map, bubble_oris = {}, []
+        if extras and with_origins:
+            all_paths = [tuple(n[0]) for n in nbps_out] + list(joined)
+            names_all = list(A.seqDict)
+            for i, p_ in enumerate(all_paths):
+                if i % 3 == 0 and names_all:
+                    v_ = int(p_[len(p_) // 2] if len(p_) > 2 else p_[i % 2])
+                    nm = names_all[(7 * i + 3) % len(names_all)]
+                    if nm not in bubble_map.setdefault(v_, []):
+                        bubble_map[v_].append(nm)
+            bmap = _dd(list, {v_: list(l_) for v_, l_ in bubble_map.items()})
+            for o2c_ in (A.multimap(A.get_ori2cov_onevertex, 1, all_paths, A.seqPaths, bmap, A.seqLimitsPerSeq, debug, chunksize=10) if all_paths else []):
+                bubble_oris.append(sorted(o for o, cov in o2c_.items() if cov >= 1))      # before the "best origin" fallback and the _Nsplit_ cut
 
     edges = A.DBG._edges.astype(np.uint32)
     res = dict(
         joined=[(list(map(int, p_)), s_, list(o_)) for p_, s_, o_ in zip(joined, joined_seqs, joined_oris)],
+        bubble_map=[[int(v_), list(l_)] for v_, l_ in sorted(bubble_map.items())],
+        bubble_oris=bubble_oris,
         orient_counts=orient,
         orient_sets=orient_sets,
         k=ksize,

@@ -25,7 +25,7 @@ EXPORTS = (
     "spb_get_nbp_origins", "spb_get_counts", "spb_get_stage_stats", "spb_build_kind", "spb_launch_count",
     "spb_get_nbp_graph", "spb_get_nbp_orientation_counts", "spb_get_seq_nbps", "spb_get_bubble_groups", "spb_path_sequences", "spb_path_origins", "spb_read_fasta", "spb_free_fasta", "spb_mg_slice", "spb_mg_probe", "spb_mg_records", "spb_mg_dedup", "spb_mg_scatter", "spb_mg_dedup_links", "spb_mg_apply_links", "spb_mg_owned_links", "spb_mg_part_records", "spb_mg_part_dedup", "spb_mg_buffers", "spb_mg_ids", "spb_mg_graph",
     "spb_mg_slice_ids", "spb_mg_slice_junctions", "spb_mg_slice_graph", "spb_mg_slice_classify", "spb_mg_slice_contract", "spb_mg_slice_emit",
-    "spb_mg_slice_finish", "spb_mg_shard", "spb_mg_complete", "spb_set_host_output", "spb_mg_shard_to_host", "spb_write_fasta", "spb_write_origins_tsv",
+    "spb_mg_slice_finish", "spb_mg_shard", "spb_mg_complete", "spb_set_host_output", "spb_mg_shard_to_host", "spb_write_fasta", "spb_write_origins_tsv", "spb_path_sequences_ex", "spb_path_origins_ex",
 )
 
 
@@ -176,6 +176,8 @@ def _declare(lib):
     lib.spb_mg_complete.argtypes = [vp, C.POINTER(SpbCounts)]
     lib.spb_set_host_output.argtypes = [vp, u8p, C.c_uint64]
     lib.spb_mg_shard_to_host.argtypes = [vp, C.c_int, vp, pu64]
+    lib.spb_path_sequences_ex.argtypes = [vp, C.c_int, C.c_uint32, u64p, u32p, u64p, u8p]
+    lib.spb_path_origins_ex.argtypes = [vp, C.c_int, C.c_uint32, u64p, u32p, C.c_uint32, u32p, u64p, u32p, C.c_uint64, C.POINTER(C.c_uint64), u64p, u32p]
     lib.spb_write_fasta.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, u64p, u8p, u64p, C.c_char_p, C.c_uint64]
     lib.spb_write_origins_tsv.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_char_p, u64p, u64p, u32p, C.c_uint32, C.c_char_p, u64p, u32p,
                                           C.c_char_p, u64p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint64]
@@ -788,35 +790,50 @@ class Engine:
         self._ck(self.lib.spb_get_seq_nbps(self.h, C.byref(n), off.ctypes.data, ids.ctypes.data))
         return off, ids
 
-    def path_sequences(self, paths, k):
-        """Sequences (str) of vertex paths (iterables of vertex ids, each >= 2 long, consecutive vertices adjacent): the
-        reference's reconstruct_sequence (lib/Assembler.py:1038-1118) for arbitrary, e.g. joined, paths."""
+    def path_sequences(self, paths, k, nbp_ids=False):
+        """Sequences (str) of paths: the reference's reconstruct_sequence (lib/Assembler.py:1038-1118) for arbitrary, e.g.
+        joined, paths.  paths: iterables of vertex ids (each >= 2 long, consecutive vertices adjacent), or -- nbp_ids=True --
+        of RAW NBP IDS whose NBPs are joined the reference's way (path + succ[1:], :810); those are expanded to vertex
+        lists on the device (spb_path_sequences_ex)."""
         paths = [np.asarray(p, dtype=np.uint32) for p in paths]
         if not paths:
             return []
         off = np.zeros(len(paths) + 1, dtype=np.uint64)
         np.cumsum([len(p) for p in paths], out=off[1:])
-        verts = np.ascontiguousarray(np.concatenate(paths))
-        out = np.empty(int(off[-1]) + len(paths) * (k - 1), dtype=np.uint8)
-        self._ck(self.lib.spb_path_sequences(self.h, len(paths), off.ctypes.data, verts.ctypes.data, out.ctypes.data))
+        items = np.ascontiguousarray(np.concatenate(paths))
+        voff = np.zeros(len(paths) + 1, dtype=np.uint64)
+        if nbp_ids:
+            self._ck(self.lib.spb_path_sequences_ex(self.h, 1, len(paths), off.ctypes.data, items.ctypes.data, voff.ctypes.data, None))
+        else:
+            voff = off
+        out = np.empty(int(voff[-1]) + len(paths) * (k - 1), dtype=np.uint8)
+        self._ck(self.lib.spb_path_sequences_ex(self.h, 1 if nbp_ids else 0, len(paths), off.ctypes.data, items.ctypes.data, None, out.ctypes.data))
         b = out.tobytes()
-        return [b[int(off[i]) + i * (k - 1):int(off[i + 1]) + (i + 1) * (k - 1)].decode() for i in range(len(paths))]
+        return [b[int(voff[i]) + i * (k - 1):int(voff[i + 1]) + (i + 1) * (k - 1)].decode() for i in range(len(paths))]
 
-    def path_origins(self, paths):
-        """Per path (concatenation of whole NBPs, as vertex ids) the ascending indices of the sequences it originates from
-        (reference get_ori2cov_onevertex + goodOris, lib/Assembler.py:1212-1248, :941-945)."""
+    def path_origins(self, paths, nbp_ids=False, bubble_vertex2origins=None):
+        """Per path (concatenation of whole NBPs, as vertex ids or -- nbp_ids=True -- raw NBP ids) the ascending indices of
+        the sequences it originates from (reference get_ori2cov_onevertex, lib/Assembler.py:1212-1248, cov >= 1).
+        bubble_vertex2origins: {vertex: iterable of sequence indices} left behind by popped bubbles (:922, :1236), united
+        with the origins of every vertex the rule looks at."""
         paths = [np.asarray(p, dtype=np.uint32) for p in paths]
         if not paths:
             return []
         off = np.zeros(len(paths) + 1, dtype=np.uint64)
         np.cumsum([len(p) for p in paths], out=off[1:])
-        verts = np.ascontiguousarray(np.concatenate(paths))
+        items = np.ascontiguousarray(np.concatenate(paths))
+        bub = sorted((int(v), sorted(set(int(x) for x in l))) for v, l in (bubble_vertex2origins or {}).items() if len(l))
+        bv = np.asarray([v for v, _ in bub], dtype=np.uint32)
+        bo = np.zeros(len(bub) + 1, dtype=np.uint64)
+        np.cumsum([len(l) for _, l in bub], out=bo[1:])
+        bs = np.asarray([x for _, l in bub for x in l], dtype=np.uint32)
         ooff = np.zeros(len(paths) + 1, dtype=np.uint64)
         cap, n = 64 * len(paths), C.c_uint64()
         for _ in range(2):
             ids = np.empty(max(cap, 1), dtype=np.uint32)
-            self._ck(self.lib.spb_path_origins(self.h, len(paths), off.ctypes.data, verts.ctypes.data, cap, C.byref(n),
-                                               ooff.ctypes.data, ids.ctypes.data))
+            self._ck(self.lib.spb_path_origins_ex(self.h, 1 if nbp_ids else 0, len(paths), off.ctypes.data, items.ctypes.data, len(bub),
+                                                  bv.ctypes.data if len(bub) else None, bo.ctypes.data if len(bub) else None,
+                                                  bs.ctypes.data if len(bub) else None, cap, C.byref(n), ooff.ctypes.data, ids.ctypes.data))
             if n.value <= cap:
                 break
             cap = n.value

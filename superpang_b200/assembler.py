@@ -218,12 +218,18 @@ class Assembler:
         """`reconstruct_sequence` (`lib/Assembler.py:1038-1118`) for a list of vertex paths (e.g. joined NBPs)."""
         return self._eng.path_sequences(paths, self.ksize)
 
-    def path_origins(self, paths):
-        """Origin names (sorted, `_Nsplit_` suffixes cut as at `lib/Assembler.py:946`) of vertex paths that are concatenations
-        of whole NBPs -- `get_ori2cov_onevertex` + goodOris for the joined paths of the host tail."""
+    def path_origins(self, paths, bubble_vertex2origins=None, nbp_ids=False):
+        """Origin names (sorted, `_Nsplit_` suffixes cut as at `lib/Assembler.py:946`) of paths that are concatenations of
+        whole NBPs -- `get_ori2cov_onevertex` + goodOris for the joined paths of the host tail.  paths: vertex tuples, or raw
+        NBP ids (nbp_ids=True); bubble_vertex2origins: {vertex: origin names} as the host tail keeps it (`:922`)."""
         self.compact()
         short = [n.split("_Nsplit_")[0] for n in self.ref2name]
-        return [tuple(sorted({short[j] for j in ids})) for ids in self._eng.path_origins(paths)]
+        bmap = None
+        if bubble_vertex2origins:
+            index = {n: i for i, n in enumerate(self.ref2name)}
+            bmap = {int(v): [index[n] for n in names] for v, names in bubble_vertex2origins.items() if names}
+        got = self._eng.path_origins(paths, nbp_ids=nbp_ids, bubble_vertex2origins=bmap)
+        return [tuple(sorted({short[j] for j in ids})) for ids in got]
 
     def bubble_candidates(self):
         """Groups (lists of vertex tuples) of raw NBPs that share first and last vertex -- `path_limits` entries with more

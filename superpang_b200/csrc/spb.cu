@@ -2256,15 +2256,45 @@ int spb_get_bubble_groups(spb_ctx* c, uint32_t* group) {
 // the host tail (reference lib/Assembler.py:1038-1118, called at :911-921).  off uint64[n_paths + 1] and verts
 // uint32[off[n_paths]] are host arrays; ascii receives off[n_paths] + n_paths * (k - 1) bytes, path i at
 // off[i] + i * (k - 1).  SPB_EINVAL if a path is shorter than 2 or two consecutive vertices are not adjacent.
-int spb_path_sequences(spb_ctx* c, uint32_t n_paths, const uint64_t* off, const uint32_t* verts, uint8_t* ascii) {
+// host-supplied paths -> device vertex lists.  kind 0: vertex ids; kind 1: raw NBP ids (expanded on the device).  On
+// return d_off[n_paths + 1] / d_verts hold the vertex paths on the device, *total their length.
+static int paths_to_device(spb_ctx* c, int kind, uint32_t n_paths, const uint64_t* off, const uint32_t* items, u64** d_off_out, u32** d_verts_out, u64* total_out) {
+  const u64 n_items = off[n_paths];
+  u64* d_off; u32* d_items;
+  ALLOC(d_off, u64, (u64)n_paths + 2); ALLOC(d_items, u32, n_items + 1);
+  dev_copy(c, d_off, off, 8ull * (n_paths + 1)); dev_copy(c, d_items, items, 4ull * n_items);
+  if (kind == 0) { *d_off_out = d_off; *d_verts_out = d_items; *total_out = n_items; return 0; }
+  if (c->state < 3 || c->sl.on) return fail(c, SPB_ESTATE, "paths as NBP ids need the complete NBP vertex lists (spb_compact)");
+  u64 *el_len, *el_off; ALLOC(el_len, u64, n_items + 1); ALLOC(el_off, u64, n_items + 1);
+  SPB_LAUNCH(k_nbp_path_lengths, nblk(n_items, TPB), TPB, c->stream, d_off, n_paths, d_items, c->nN, c->voff, c->verts, el_len, c->errflag);
+  u64 total = 0;
+  PRIM(prim_scan_u64(c, el_len, el_off, n_items, &total));
+  u32 e = dread(c, c->errflag);
+  if (e & ERR_BADPATH) {
+    dev_memset(c, c->errflag, 0, 4); dfree(c, d_off); dfree(c, d_items); dfree(c, el_len); dfree(c, el_off);
+    return fail(c, SPB_EINVAL, "a path holds an unknown NBP id, or two consecutive NBPs that do not share their junction vertex");
+  }
+  u64* v_off; u32* v_verts; ALLOC(v_off, u64, (u64)n_paths + 2); ALLOC(v_verts, u32, total + 1);
+  SPB_LAUNCH(k_nbp_path_write, std::min<u64>(nblk(n_items * 32, TPB), 148 * 16), TPB, c->stream, d_off, n_paths, d_items, c->voff, c->verts, el_off, v_off, v_verts);
+  dev_copy(c, v_off + n_paths, &total, 8); dev_sync(c);
+  dfree(c, d_off); dfree(c, d_items); dfree(c, el_len); dfree(c, el_off);
+  *d_off_out = v_off; *d_verts_out = v_verts; *total_out = total;
+  return 0;
+}
+
+// kind 0: paths are vertex lists; kind 1: lists of raw NBP ids.  vert_off (optional, host uint64[n_paths + 1]) receives the
+// vertex offsets of the paths; ascii == nullptr: sizes only (path i needs vert_off[i + 1] - vert_off[i] + k - 1 bytes at
+// vert_off[i] + i * (k - 1)).
+int spb_path_sequences_ex(spb_ctx* c, int kind, uint32_t n_paths, const uint64_t* off, const uint32_t* items, uint64_t* vert_off, uint8_t* ascii) {
   NEED_FULL(2);
-  if (!off || !verts || !ascii) return SPB_EINVAL;
-  if (n_paths == 0) return SPB_OK;
-  const u64 total = off[n_paths];
-  if (total == 0) return fail(c, SPB_EINVAL, "spb_path_sequences: empty paths");
-  u64* d_off; u32* d_verts; u8* d_out;
-  ALLOC(d_off, u64, (u64)n_paths + 1); ALLOC(d_verts, u32, total + 1); ALLOC(d_out, u8, total + (u64)n_paths * (c->k - 1) + 1);
-  dev_copy(c, d_off, off, 8ull * (n_paths + 1)); dev_copy(c, d_verts, verts, 4ull * total);
+  if (!off || !items || (kind != 0 && kind != 1) || (!ascii && !vert_off)) return SPB_EINVAL;
+  if (n_paths == 0) { if (vert_off) vert_off[0] = 0; return SPB_OK; }
+  if (off[n_paths] == 0) return fail(c, SPB_EINVAL, "spb_path_sequences: empty paths");
+  u64* d_off; u32* d_verts; u64 total = 0;
+  PRIM(paths_to_device(c, kind, n_paths, off, items, &d_off, &d_verts, &total));
+  if (vert_off) { dev_copy(c, vert_off, d_off, 8ull * (n_paths + 1)); dev_sync(c); }
+  if (!ascii) { dfree(c, d_off); dfree(c, d_verts); return SPB_OK; }
+  u8* d_out; ALLOC(d_out, u8, total + (u64)n_paths * (c->k - 1) + 1);
   GView g{c->vflags, c->Jk, c->Js, c->nJ, c->nV};
   SPB_LAUNCH(k_path_seqs, gs_grid(total), TPB, c->stream, g, c->F, c->R, c->T, c->k, c->v2pos, d_off, n_paths, d_verts, d_out, c->errflag);
   dev_copy(c, ascii, d_out, total + (u64)n_paths * (c->k - 1)); dev_sync(c);
@@ -2273,7 +2303,11 @@ int spb_path_sequences(spb_ctx* c, uint32_t n_paths, const uint64_t* off, const 
   if (e & ERR_BADPATH) { dev_memset(c, c->errflag, 0, 4); return fail(c, SPB_EINVAL, "spb_path_sequences: a path is shorter than 2 vertices or steps between vertices that are not adjacent"); }
   return check_err(c, "spb_path_sequences");
 }
-// (init vertex, sequence) pairs, sorted unique, built once per compaction (incl. the leading-zero quirk for vertex 0)
+int spb_path_sequences(spb_ctx* c, uint32_t n_paths, const uint64_t* off, const uint32_t* verts, uint8_t* ascii) {
+  if (!ascii) return SPB_EINVAL;
+  return spb_path_sequences_ex(c, 0, n_paths, off, verts, nullptr, ascii);
+}
+
 static int build_init_seq_pairs(spb_ctx* c) {
   if (c->ivp) return 0;
   const u64 T = c->T;
@@ -2310,28 +2344,43 @@ static int build_init_seq_pairs(spb_ctx* c) {
 // larger `cap` when it exceeds it).
 int spb_path_origins(spb_ctx* c, uint32_t n_paths, const uint64_t* off, const uint32_t* verts, uint64_t cap, uint64_t* n_pairs,
                      uint64_t* out_off, uint32_t* seq_idx) {
+  return spb_path_origins_ex(c, 0, n_paths, off, verts, 0, nullptr, nullptr, nullptr, cap, n_pairs, out_off, seq_idx);
+}
+// kind as for spb_path_sequences_ex; bubble_vertex2origins as a CSR over ascending vertex ids (n_bub vertices, host arrays):
+// bub_vert uint32[n_bub], bub_off uint64[n_bub + 1], bub_seq uint32[bub_off[n_bub]] (sequence indices)
+int spb_path_origins_ex(spb_ctx* c, int kind, uint32_t n_paths, const uint64_t* off, const uint32_t* items, uint32_t n_bub, const uint32_t* bub_vert,
+                        const uint64_t* bub_off, const uint32_t* bub_seq, uint64_t cap, uint64_t* n_pairs, uint64_t* out_off, uint32_t* seq_idx) {
   NEED_FULL(3);
-  if (!off || !verts || !n_pairs || !out_off || (cap && !seq_idx)) return SPB_EINVAL;
+  if (!off || !items || !n_pairs || !out_off || (cap && !seq_idx) || (kind != 0 && kind != 1) || (n_bub && (!bub_vert || !bub_off || !bub_seq))) return SPB_EINVAL;
   *n_pairs = 0;
   if (n_paths == 0) { out_off[0] = 0; return SPB_OK; }
-  const u64 total = off[n_paths];
-  if (total == 0) return fail(c, SPB_EINVAL, "spb_path_origins: empty paths");
+  if (off[n_paths] == 0) return fail(c, SPB_EINVAL, "spb_path_origins: empty paths");
+  for (u32 i = 1; i < n_bub; ++i) if (bub_vert[i] <= bub_vert[i - 1]) return fail(c, SPB_EINVAL, "spb_path_origins: bubble vertices must ascend");
   int r = build_init_seq_pairs(c);
   if (r) return r;
-  u64* d_off; u32* d_verts; u64 *cnt, *pairs = nullptr;
-  ALLOC(d_off, u64, (u64)n_paths + 1); ALLOC(d_verts, u32, total + 1); ALLOC(cnt, u64, 2);
-  dev_copy(c, d_off, off, 8ull * (n_paths + 1)); dev_copy(c, d_verts, verts, 4ull * total);
-  u64 pcap = std::max<u64>(4096, 8ull * n_paths + cap), np = 0;
+  u64* d_off; u32* d_verts; u64 *cnt, *pairs = nullptr; u64 total = 0;
+  PRIM(paths_to_device(c, kind, n_paths, off, items, &d_off, &d_verts, &total));
+  ALLOC(cnt, u64, 2);
+  BubbleOri bub{nullptr, nullptr, nullptr, 0};
+  u32 *d_bv = nullptr, *d_bs = nullptr; u64* d_bo = nullptr;
+  if (n_bub) {
+    const u64 nbs = bub_off[n_bub];
+    for (u64 x = 0; x < nbs; ++x) if (bub_seq[x] >= c->n_seq) return fail(c, SPB_EINVAL, "spb_path_origins: bubble origin index out of range");
+    ALLOC(d_bv, u32, n_bub + 1); ALLOC(d_bo, u64, (u64)n_bub + 2); ALLOC(d_bs, u32, nbs + 1);
+    dev_copy(c, d_bv, bub_vert, 4ull * n_bub); dev_copy(c, d_bo, bub_off, 8ull * (n_bub + 1)); dev_copy(c, d_bs, bub_seq, 4ull * nbs);
+    bub = BubbleOri{d_bv, d_bo, d_bs, n_bub};
+  }
+  u64 pcap = std::max<u64>(4096, 8ull * n_paths + cap + (n_bub ? bub_off[n_bub] : 0)), np = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {
     ALLOC(pairs, u64, pcap + 1);
     dev_memset(c, cnt, 0, 16);
     SPB_LAUNCH(k_path_origin_pairs, gs_grid(total), TPB, c->stream, d_off, n_paths, d_verts, c->nV, c->vflags, c->vnbp, c->ooff, c->origins,
-               c->ivp, c->n_ivp, c->ivp_sb, pairs, cnt, pcap, c->errflag);
+               c->ivp, c->n_ivp, c->ivp_sb, bub, pairs, cnt, pcap, c->errflag);
     np = dread(c, cnt);
     if (np <= pcap) break;
     dfree(c, pairs); pcap = np;
   }
-  dfree(c, d_off); dfree(c, d_verts); dfree(c, cnt);
+  dfree(c, d_off); dfree(c, d_verts); dfree(c, cnt); dfree(c, d_bv); dfree(c, d_bo); dfree(c, d_bs);
   u32 e = dread(c, c->errflag);
   if (e & ERR_BADPATH) {
     dev_memset(c, c->errflag, 0, 4); dfree(c, pairs);

@@ -2127,9 +2127,64 @@ __global__ void k_init_seq_quirk(const u8* __restrict__ has01, u32 n_seq, const 
   if (s >= n_seq) return;
   if (has01[2 * s + 1] && !has01[2 * s] && (vflags[0] & VF_INIT)) { const u64 i = atomicAdd(npairs, 1ull); if (i < cap) pairs[i] = s; }   // vertex 0
 }
+// Paths given as lists of raw NBP ids (consecutive NBPs share one vertex: the reference joins them as path + succ[1:],
+// lib/Assembler.py:810) -> vertex lists.  el_len[e] = vertices element e contributes; after the scan one warp per element
+// copies them.  A pair of consecutive NBPs that does not share its junction vertex flags ERR_BADPATH.
+__global__ void k_nbp_path_lengths(const u64* __restrict__ poff, u32 n_paths, const u32* __restrict__ ids, u32 nN, const u64* __restrict__ voff,
+                                   const u32* __restrict__ verts, u64* __restrict__ el_len, u32* err) {
+  const u64 total = poff[n_paths];
+  const u64 e = SPB_GTID();
+  if (e >= total) return;
+  const u32 id = ids[e];
+  if (id >= nN) { atomicOr(err, (u32)ERR_BADPATH); el_len[e] = 0; return; }
+  const u32 path = upper_bound_u64(poff, n_paths + 1, e) - 1;
+  const bool first = e == poff[path];
+  const u64 len = voff[id + 1] - voff[id];
+  if (!first) {
+    const u32 prev = ids[e - 1];
+    if (prev >= nN || verts[voff[prev + 1] - 1] != verts[voff[id]]) atomicOr(err, (u32)ERR_BADPATH);
+  }
+  el_len[e] = first ? len : len - 1;
+}
+__global__ void k_nbp_path_write(const u64* __restrict__ poff, u32 n_paths, const u32* __restrict__ ids, const u64* __restrict__ voff,
+                                 const u32* __restrict__ verts, const u64* __restrict__ el_off, u64* __restrict__ out_off, u32* __restrict__ out_verts) {
+  const u64 total = poff[n_paths];
+  const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+  const u32 lane = threadIdx.x & 31;
+  for (u64 e = SPB_GTID() >> 5; e < total; e += nwarps) {
+    const u32 id = ids[e];
+    const u32 path = upper_bound_u64(poff, n_paths + 1, e) - 1;
+    const bool first = e == poff[path];
+    if (first && lane == 0) out_off[path] = el_off[e];
+    const u64 src = voff[id] + (first ? 0 : 1), n = voff[id + 1] - src;
+    for (u64 t = lane; t < n; t += 32) out_verts[el_off[e] + t] = verts[src + t];
+  }
+}
+
+// bubble_vertex2origins (reference lib/Assembler.py:922, :1236): extra (vertex -> sequences) lists left behind by popped
+// bubbles, as a CSR over ascending vertex ids; every vertex a path is asked about contributes them as well
+struct BubbleOri { const u32* vert; const u64* off; const u32* seq; u32 n; };
+__device__ __forceinline__ bool bubble_range(const BubbleOri& b, u32 v, u64* lo, u64* hi) {
+  if (!b.n) return false;
+  u32 l = 0, h = b.n;
+  while (l < h) { const u32 m = (l + h) >> 1; if (b.vert[m] < v) l = m + 1; else h = m; }
+  if (l >= b.n || b.vert[l] != v) return false;
+  *lo = b.off[l]; *hi = b.off[l + 1];
+  return true;
+}
+__device__ __forceinline__ bool bubble_has(const BubbleOri& b, u32 v, u32 s) {
+  u64 lo, hi;
+  if (!bubble_range(b, v, &lo, &hi)) return false;
+  for (u64 x = lo; x < hi; ++x) if (b.seq[x] == s) return true;
+  return false;
+}
+__device__ __forceinline__ bool ivp_has(const u64* ivp, u32 n_ivp, u32 sb, u32 v, u32 s) {
+  const u32 i = lower_bound_key(ivp, n_ivp, ((u64)v << sb) | s);
+  return i < n_ivp && ivp[i] == (((u64)v << sb) | s);
+}
 __global__ void k_path_origin_pairs(const u64* __restrict__ off, u32 n_paths, const u32* __restrict__ verts, u32 nV, const u8* __restrict__ vflags,
                                     const u32* __restrict__ vnbp, const u64* __restrict__ ooff, const u32* __restrict__ origins,
-                                    const u64* __restrict__ ivp, u32 n_ivp, u32 sb, u64* __restrict__ out, u64* nout, u64 cap, u32* err) {
+                                    const u64* __restrict__ ivp, u32 n_ivp, u32 sb, BubbleOri bub, u64* __restrict__ out, u64* nout, u64 cap, u32* err) {
   const u64 total = off[n_paths];
   const u64 stride = (u64)gridDim.x * blockDim.x;
   for (u64 e = SPB_GTID(); e < total; e += stride) {
@@ -2144,14 +2199,26 @@ __global__ void k_path_origin_pairs(const u64* __restrict__ off, u32 n_paths, co
       u32 a = lower_bound_key(ivp, n_ivp, (u64)v << sb), ae = lower_bound_key(ivp, n_ivp, ((u64)v + 1) << sb);
       u32 b = lower_bound_key(ivp, n_ivp, (u64)w << sb), be = lower_bound_key(ivp, n_ivp, ((u64)w + 1) << sb);
       const u64 m = (1ull << sb) - 1;
-      while (a < ae && b < be) {
-        const u64 x = ivp[a] & m, y = ivp[b] & m;
-        if (x < y) ++a; else if (y < x) ++b;
-        else { const u64 j = atomicAdd(nout, 1ull); if (j < cap) out[j] = ((u64)path << 32) | x; ++a; ++b; }
+      if (!bub.n) {
+        while (a < ae && b < be) {
+          const u64 x = ivp[a] & m, y = ivp[b] & m;
+          if (x < y) ++a; else if (y < x) ++b;
+          else { const u64 j = atomicAdd(nout, 1ull); if (j < cap) out[j] = ((u64)path << 32) | x; ++a; ++b; }
+        }
+      } else {
+        // with bubble lists: a sequence counts for a vertex when the vertex is in it OR a popped bubble says so; it is kept
+        // when that holds for both vertices (the sort + unique of the caller removes what is found twice)
+        u64 lo = 0, hi = 0;
+        for (u32 x = a; x < ae; ++x) { const u32 q = (u32)(ivp[x] & m); if (ivp_has(ivp, n_ivp, sb, w, q) || bubble_has(bub, w, q)) { const u64 j = atomicAdd(nout, 1ull); if (j < cap) out[j] = ((u64)path << 32) | q; } }
+        if (bubble_range(bub, v, &lo, &hi)) for (u64 x = lo; x < hi; ++x) { const u32 q = bub.seq[x]; if (ivp_has(ivp, n_ivp, sb, w, q) || bubble_has(bub, w, q)) { const u64 j = atomicAdd(nout, 1ull); if (j < cap) out[j] = ((u64)path << 32) | q; } }
       }
       continue;
     }
     if (i == 0 || i == len - 1) continue;            // the end vertices overlap other paths (:1224-1227)
+    {
+      u64 lo = 0, hi = 0;
+      if (bubble_range(bub, v, &lo, &hi)) for (u64 x = lo; x < hi; ++x) { const u64 j = atomicAdd(nout, 1ull); if (j < cap) out[j] = ((u64)path << 32) | bub.seq[x]; }
+    }
     if (vflags[v] & VF_INIT) {
       for (u32 a = lower_bound_key(ivp, n_ivp, (u64)v << sb), ae = lower_bound_key(ivp, n_ivp, ((u64)v + 1) << sb); a < ae; ++a) {
         const u64 j = atomicAdd(nout, 1ull);

@@ -142,6 +142,26 @@ def _check_paths(A, case):
     # reference's own get_ori2cov_onevertex + goodOris, oracle/refrun.py)
     want_o = [tuple(n[2]) for n in r["nbps"]] + [tuple(j[2]) for j in r.get("joined", [])]
     assert A.path_origins(paths) == want_o
+    # the same joined paths handed over as lists of RAW NBP IDS (expanded on the device, spb_path_*_ex kind 1)
+    voff, verts, _, _ = A._eng.nbps()
+    ids = {tuple(verts[int(voff[i]):int(voff[i + 1])].tolist()): i for i in range(len(voff) - 1)}
+    id_paths, vert_paths = [[ids[tuple(n[0])]] for n in r["nbps"][:5]], [n[0] for n in r["nbps"][:5]]
+    for j in r.get("joined", []):
+        p = tuple(j[0])
+        for cut in range(2, len(p)):
+            if p[:cut] in ids and p[cut - 1:] in ids:
+                id_paths.append([ids[p[:cut]], ids[p[cut - 1:]]]); vert_paths.append(list(p))
+                break
+    if id_paths:
+        assert A._eng.path_sequences(id_paths, case["k"], nbp_ids=True) == A._eng.path_sequences(vert_paths, case["k"])
+        assert A._eng.path_origins(id_paths, nbp_ids=True) == A._eng.path_origins(vert_paths)
+    # origins with a non-empty bubble_vertex2origins: the reference's own get_ori2cov_onevertex (cov >= 1) on every raw NBP
+    # and joined path, with the made-up bubble map of oracle/refrun.py
+    if r.get("bubble_oris"):
+        index = {n: i for i, n in enumerate(A.ref2name)}
+        bmap = {int(v): [index[n] for n in l] for v, l in r["bubble_map"]}
+        got = A._eng.path_origins(paths, bubble_vertex2origins=bmap)
+        assert [sorted(A.ref2name[i] for i in g) for g in got] == [sorted(w) for w in r["bubble_oris"]], case["name"]
     return len(r.get("joined", []))
 
 
@@ -162,6 +182,11 @@ def test_emu_path_sequences_reject_bad_paths(emu_lib):
     for bad in ([0], [0, nv // 2 + 7, 3], [0, 0], [nv + 5, 1]):
         with pytest.raises(_capi.SpbError):
             A.reconstruct_sequences([bad])
+    A.compact()
+    n = A.counts["n_nbp"]
+    for bad in ([n + 3], [0, 0]):                                             # unknown NBP id; NBPs that do not share their junction vertex
+        with pytest.raises(_capi.SpbError):
+            A._eng.path_sequences([bad], case["k"], nbp_ids=True)
     assert A.reconstruct_sequences([]) == []
     assert len(A.reconstruct_sequences([[0, 1, 2]])[0]) == case["k"] + 2      # still usable after the errors
 
