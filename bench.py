@@ -199,6 +199,7 @@ def main():
     ap.add_argument("--ref-inst", type=int, default=1_000_000, help="k-mer instances of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-digest", action="store_true")
+    ap.add_argument("--no-k-sweep", action="store_true", help="skip the k = 101 / 501 steps (BASELINE config 5) after the headline run")
     ap.add_argument("--k", type=int, default=301, help="k-mer size (BASELINE config 5 sweeps 101 / 301 / 501)")
     args = ap.parse_args()
     global K
@@ -327,6 +328,29 @@ def main():
     value = total_inst * args.steps / (ms / 1e3)
     e2e_value = total_inst * args.steps / (ms_e2e / 1e3)
 
+    # ---- BASELINE config 5 (k-size sweep on the same genome set), N = 1 only: a few untimed-for-the-headline steps at the other
+    # k values, reported next to the headline so that the sweep is measured by the same command
+    k_sweep = None
+    if world == 1 and args.workload == "c3" and K == 301 and not args.no_k_sweep:
+        k_sweep = {}
+        for kk in (101, 501):
+            ts = []
+            for i in range(4):
+                flush.fill_(1)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                eng.load(dbuf, off, kk)
+                eng.build_dbg()
+                cc = eng.compact()
+                e1.record(stream)
+                torch.cuda.synchronize()
+                if i:
+                    ts.append(e0.elapsed_time(e1))
+            k_sweep[str(kk)] = dict(ms_per_step=float(np.mean(ts)), ms_per_step_min=float(np.min(ts)), n_inst=int(cc["n_inst"]),
+                                    value=float(cc["n_inst"] / (np.mean(ts) / 1e3)), n_vertices=int(cc["n_vertices"]), n_nbp=int(cc["n_nbp"]))
+        step_resident()                              # back to the headline configuration for the digest below
+
     # ---- result digest (outside the timed region): device-side checksums of every result buffer of the last step
     dg, dg_single = None, None
     if not args.no_digest:
@@ -401,6 +425,7 @@ def main():
             result_checksums=dg,
             digest_equals_single_gpu=(dg_single == dg) if dg_single is not None else None,
             clocks=sampler.summary(),
+            k_sweep=k_sweep,
         )
         if not args.no_cpu_baseline:
             ref = CpuReference(args.workload, args.mode, args.ref_inst)

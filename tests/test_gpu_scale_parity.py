@@ -22,13 +22,13 @@ K = 301
 ENV_KEYS = ("SPB_DEDUP", "SPB_ANCHOR", "SPB_BUCKET_BITS", "SPB_CHUNK_BITS", "SPB_SMEM_AVG", "SPB_PARTITION")
 
 
-def _run(monkeypatch, env, dbuf, off, graph=True):
+def _run(monkeypatch, env, dbuf, off, graph=True, k=None):
     for k_ in ENV_KEYS:
         monkeypatch.delenv(k_, raising=False)
     for k_, v in env.items():
         monkeypatch.setenv(k_, v)
     eng = _capi.Engine(device=0)
-    eng.load(dbuf, off, K)
+    eng.load(dbuf, off, k or K)
     eng.build_dbg()
     eng.compact()
     stats = eng.stage_stats()
@@ -106,3 +106,25 @@ def test_config3_two_algorithms_and_invariants(monkeypatch, mode):
             checked += 1
     assert checked >= 5
     eng.close()
+
+
+def test_config5_k_sweep_two_algorithms(monkeypatch):
+    """BASELINE config 5 (k = 101 / 501 on 100 x 5 Mbp): the default path and the single global table -- two different
+    algorithms -- must give byte-identical device digests at full scale for the other k values of the sweep too, and N_v
+    must equal the independent sort-count."""
+    import torch
+    names, seqs = synth.genome_set(100, 5_000_000, 0.96, seed=2, mode="snp")
+    buf, off = concat_sequences(seqs)
+    del seqs
+    dev = torch.device("cuda", 0)
+    dbuf = torch.from_numpy(buf).to(dev)
+    for k in (101, 501):
+        eng, d_default, st = _run(monkeypatch, {}, dbuf, off, k=k)
+        eng.close()
+        torch.cuda.empty_cache()
+        eng_g, d_global, st_g = _run(monkeypatch, {"SPB_DEDUP": "global"}, dbuf, off, k=k)
+        eng_g.close()
+        torch.cuda.empty_cache()
+        assert "k_extract_insert_ms" in st_g, st_g
+        assert d_default == d_global, (k, {k_: (d_default[k_], d_global[k_]) for k_ in d_default if d_default[k_] != d_global[k_]})
+        assert digest.independent_vertex_count(dbuf, off, k) == d_default["counts"]["n_vertices"], k
