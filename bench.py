@@ -37,6 +37,11 @@ WORKLOADS = {
     "c2": dict(n_genomes=10, length=2_000_000, ani=0.97, seed=1, desc="synthetic 10 genomes x 2 Mbp ANI 0.97"),
     "c3": dict(n_genomes=100, length=5_000_000, ani=0.96, seed=2, desc="synthetic 100 genomes x 5 Mbp ANI 0.96"),
     "tiny": dict(n_genomes=4, length=200_000, ani=0.97, seed=5, desc="synthetic 4 genomes x 200 kbp ANI 0.97"),
+    # BASELINE configs[3] at the 32-bit position limit of this build: 800 (not 1000) x 5 Mbp = 4.0e9 bases, multi-GPU only
+    # (every per-position / per-vertex array is sliced over the ranks); generated on the device, no e2e / CPU legs
+    "c4s": dict(n_genomes=800, length=5_000_000, ani=0.96, seed=4, device_gen=True,
+                desc="synthetic 800 genomes x 5 Mbp ANI 0.96 (BASELINE config 4 at the 32-bit position limit, 4.0e9 bases; generated on the device)"),
+    "c4t": dict(n_genomes=16, length=500_000, ani=0.96, seed=4, device_gen=True, desc="synthetic 16 genomes x 500 kbp ANI 0.96 (generated on the device; test of the c4s plumbing)"),
 }
 K = 301
 
@@ -219,13 +224,24 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    w, names, buf, off, n_inst = make_workload(args.workload, args.mode)
-    host = torch.from_numpy(buf).pin_memory()
-    T = host.numel()
-    Tpad = (T + world * 16 - 1) // (world * 16) * (world * 16)          # equal parts for the all-gather of the input (e2e, N > 1)
-    dpad = torch.empty(Tpad, dtype=torch.uint8, device=dev)
-    dbuf = dpad[:T]
-    dbuf.copy_(host, non_blocking=True)
+    device_gen = bool(WORKLOADS[args.workload].get("device_gen"))
+    if device_gen:
+        from superpang_b200 import synth
+        w = WORKLOADS[args.workload]
+        assert args.mode == "snp", "device-generated workloads are snp mode"
+        dbuf, off = synth.genome_set_device(w["n_genomes"], w["length"], w["ani"], w["seed"], dev)
+        n_inst = w["n_genomes"] * (w["length"] - K + 1)
+        T = dbuf.numel()
+        host, buf, dpad, Tpad = None, None, None, T
+        args.no_cpu_baseline = True
+    else:
+        w, names, buf, off, n_inst = make_workload(args.workload, args.mode)
+        host = torch.from_numpy(buf).pin_memory()
+        T = host.numel()
+        Tpad = (T + world * 16 - 1) // (world * 16) * (world * 16)          # equal parts for the all-gather of the input (e2e, N > 1)
+        dpad = torch.empty(Tpad, dtype=torch.uint8, device=dev)
+        dbuf = dpad[:T]
+        dbuf.copy_(host, non_blocking=True)
     stream = torch.cuda.current_stream()
     eng = _capi.Engine(device=local, stream=stream.cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
@@ -311,7 +327,10 @@ def main():
     sampler.start()
     times, stages, counts = timed(step_resident, args.steps, args.warmup)
     launches = timed.launches
-    e2e_times, _, e2e_last = timed(step_e2e, args.steps, max(3, args.warmup))
+    if device_gen:                                   # no host copy of this input exists: resident number only
+        e2e_times, e2e_last = [float("nan")] * args.steps, (None, 0)
+    else:
+        e2e_times, _, e2e_last = timed(step_e2e, args.steps, max(3, args.warmup))
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -361,7 +380,7 @@ def main():
             dg = digest.result_digest(eng, graph=True)
         if world > 1:
             dist.barrier()
-            if rank == 0:                            # the same input through the single-GPU path on this rank
+            if rank == 0 and not device_gen:         # the same input through the single-GPU path on this rank
                 eng.load(dbuf, off, K)
                 eng.build_dbg()
                 eng.compact()
@@ -412,12 +431,12 @@ def main():
             metric=f"canonical k-mers/s through DBG build+NBP compaction at k={K}", value=value, unit="k-mers/s",
             n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, ms_per_step_median=float(np.median(times)),
             ms_per_step_min=float(np.min(times)), higher_is_better=True,
-            scaling="strong", vs_baseline=None, dtype="u64", data="synthetic",
+            scaling="weak" if device_gen else "strong", vs_baseline=None, dtype="u64", data="synthetic",
             config=config_for(args, world),
             counts=dict(n_inst=n_inst, n_vertices=counts["n_vertices"], n_edges=counts["n_edges"], n_nbp=counts["n_nbp"], nbp_bases=counts["nbp_bases"],
                         n_origin_pairs=counts["n_origin_pairs"], mg_protocol=getattr(eng, "mg_protocol", None)),
-            e2e=dict(value=e2e_value, unit="k-mers/s", ms_per_step=ms_e2e / args.steps, ms_per_step_median=float(np.median(e2e_times)),
-                     h2d_bytes_per_step=int(buf.nbytes + off.nbytes), d2h_bytes_per_step=d2h_bytes),
+            e2e=None if device_gen else dict(value=e2e_value, unit="k-mers/s", ms_per_step=ms_e2e / args.steps, ms_per_step_median=float(np.median(e2e_times)),
+                                             h2d_bytes_per_step=int(buf.nbytes + off.nbytes), d2h_bytes_per_step=d2h_bytes),
             gpu_launches=int(launches),
             roofline=roof,
             stages_ms=st_mean,

@@ -925,7 +925,7 @@ static int dedup_part_links(spb_ctx* c) {
 #else
   const u64 grid2 = std::min<u64>(NR1 * cpr, 2 * 148), gridd = std::min<u64>(NBF, 2 * 148);   // persistent: two CTAs per SM
 #endif
-  { const int tq_ = t_begin(c); SPB_LAUNCH_PHASED_DSMEM(k_partition2, 1, grid2, SPB_P2_T, 3 * SPB_P2_CHUNK * 8, c->stream, rec1, cap1, cursor1, cpr, (u32)NR1, (u32)NB1, l2, rec2, cap2, NBF * cap2, cursor2, c->errflag);
+  { const int tq_ = t_begin(c); SPB_LAUNCH_PHASED_DSMEM(k_partition2, 1, grid2, SPB_P2_T, 3 * SPB_P2_CHUNK * 8, c->stream, rec1, cap1, cursor1, cpr, (u32)NR1, (u32)NB1, l2, rec2, cap2, NBF * cap2, cursor2, c->errflag, 0u);
     t_end(c, tq_, "k_partition2_ms"); }
   dfree(c, rec1);
   t_end(c, tk, "records_partition_ms");
@@ -1356,7 +1356,7 @@ int spb_mg_owned_links(spb_ctx* c, uint32_t rank, uint32_t n_owners, uint64_t* s
 //   spb_mg_part_dedup     owner side: level-2 partition of the n_src x 2^l1 received regions, one CTA per final bucket
 //                         with a shared-memory table (list form), links sorted by position and split by slice owner.
 // The geometry (l1, l2, cap1) is a function of (n_inst, n_owners, slice length) only, so every rank derives the same one.
-struct PartGeom { u32 own_bits, l1, l2; u64 cap1; };
+struct PartGeom { u32 own_bits, l1, l2, l2a; u64 cap1, capA; };      // l2a > 0: two level-2 passes (l2a bits, then l2 - l2a)
 static int part_geometry(spb_ctx* c, u32 n_owners, PartGeom* g) {
   u32 ob = 0; while ((1u << ob) < n_owners) ++ob;
   u64 avg = SPB_D_AVG;
@@ -1367,7 +1367,12 @@ static int part_geometry(spb_ctx* c, u32 n_owners, PartGeom* g) {
   u32 l1 = std::min<u32>(9 - ob, nbits);
   if (l1 > (nbits + 1) / 2 + 1) l1 = (nbits + 1) / 2 + 1;         // keep both levels at a useful fan-out
   const u32 l2 = nbits - l1;
-  if (l2 > 9) return 1;
+  u32 l2max = 9;                                                   // one level-2 pass handles 2^9 buckets (tests lower it to reach the two-pass form)
+  if (const char* e = getenv("SPB_PART_L2MAX")) l2max = (u32)std::max(1, std::min(9, atoi(e)));
+  if (l2 > 2 * l2max) return 1;
+  g->l2a = l2 > l2max ? (l2 + 1) / 2 : 0;                          // more than that: the level-2 kernel runs twice
+  const u64 perA = per_owner >> (l1 + g->l2a);
+  g->capA = (perA + perA / 8 + 4096 + 1) & ~1ull;
   uint64_t slice = 0; spb_mg_slice(c, n_owners, &slice);
   const u64 n1 = nblk(slice, (u64)n_owners << l1);                // positions of a slice per (owner, level-1 bucket)
   g->own_bits = ob; g->l1 = l1; g->l2 = l2;
@@ -1425,8 +1430,32 @@ int spb_mg_part_dedup(spb_ctx* c, const uint64_t* recs, const uint32_t* counts, 
 #else
   const u64 grid2 = std::min<u64>(NR1 * cpr, 2 * 148);
 #endif
-  { const int tq_ = t_begin(c); SPB_LAUNCH_PHASED_DSMEM(k_partition2, 1, grid2, SPB_P2_T, 3 * SPB_P2_CHUNK * 8, c->stream, (const u64*)recs, g.cap1, counts, cpr, (u32)NR1, (u32)NB1, g.l2, rec2, cap2,
-                            NBF * cap2, cursor2, c->errflag); t_end(c, tq_, "k_partition2_ms"); }
+  if (!g.l2a) {
+    const int tq_ = t_begin(c); SPB_LAUNCH_PHASED_DSMEM(k_partition2, 1, grid2, SPB_P2_T, 3 * SPB_P2_CHUNK * 8, c->stream, (const u64*)recs, g.cap1, counts, cpr, (u32)NR1, (u32)NB1, g.l2, rec2, cap2,
+                            NBF * cap2, cursor2, c->errflag, 0u); t_end(c, tq_, "k_partition2_ms");
+  } else {
+    // very large inputs (more than 2^18 final buckets per owner's level-1 fan-out): level 2 in two passes through an
+    // intermediate set of 2^(l1 + l2a) regions
+    const u64 NBA = 1ull << (g.l1 + g.l2a);
+    if (getenv("SPB_DEBUG")) fprintf(stderr, "[spb] part dedup: level 2 in two passes (l1=%u l2=%u+%u, %llu intermediate regions of %llu)\n", g.l1, g.l2a, g.l2 - g.l2a, (unsigned long long)NBA, (unsigned long long)g.capA);
+    stat_set(c, "partition2_passes", 2);
+    u64* recA; u32* cursorA;
+    ALLOC(recA, u64, NBA * g.capA + SPB_P2_CHUNK + 2); ALLOC(cursorA, u32, NBA + 8);
+    dev_memset(c, cursorA, 0, (NBA + 8) * 4);
+    const int tq_ = t_begin(c);
+    SPB_LAUNCH_PHASED_DSMEM(k_partition2, 1, grid2, SPB_P2_T, 3 * SPB_P2_CHUNK * 8, c->stream, (const u64*)recs, g.cap1, counts, cpr, (u32)NR1, (u32)NB1, g.l2a, recA, g.capA,
+                            NBA * g.capA, cursorA, c->errflag, 0u);
+    const u32 cprA = (u32)nblk(g.capA, SPB_P2_CHUNK);
+#ifdef SPB_EMU
+    const u64 gridB = NBA * cprA;
+#else
+    const u64 gridB = std::min<u64>(NBA * cprA, 2 * 148);
+#endif
+    SPB_LAUNCH_PHASED_DSMEM(k_partition2, 1, gridB, SPB_P2_T, 3 * SPB_P2_CHUNK * 8, c->stream, (const u64*)recA, g.capA, cursorA, cprA, (u32)NBA, (u32)NBA, g.l2 - g.l2a, rec2, cap2,
+                            NBF * cap2, cursor2, c->errflag, g.l2a);
+    t_end(c, tq_, "k_partition2_ms");
+    dfree(c, recA); dfree(c, cursorA);
+  }
   u64* nlinks; ALLOC(nlinks, u64, 2);
   u64 lcap = std::max<u64>(4096, c->n_inst / n_owners / 8);
   u64* links = nullptr; u64 nl = 0;

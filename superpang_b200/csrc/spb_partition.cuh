@@ -359,7 +359,8 @@ k_roll_partition(const u32* __restrict__ F, const u32* __restrict__ R, const u32
 // overlaps with the scatter into `sorted2`.
 __global__ void SPB_LAUNCH_BOUNDS2(SPB_P2_T, 2)
 k_partition2(const u64* __restrict__ rec_in, u64 cap_in, const u32* __restrict__ cnt_in, u32 chunks_per_region, u32 n_regions, u32 parent_mod, u32 l2bits,
-             u64* __restrict__ rec2, u64 cap2, u64 trash, u32* cursor2, u32* err) {
+             u64* __restrict__ rec2, u64 cap2, u64 trash, u32* cursor2, u32* err, u32 skip2) {
+  // skip2: stored hash bits already consumed by an earlier level-2 pass (very large inputs run this kernel twice)
   // trash: index of SPB_P2_CHUNK spare records behind the regions (runs of an overflowing bucket; the overflow is flagged)
 #ifdef SPB_EMU
   const u32 region = blockIdx.x / chunks_per_region, chunk = blockIdx.x % chunks_per_region;
@@ -373,7 +374,7 @@ k_partition2(const u64* __restrict__ rec_in, u64 cap_in, const u32* __restrict__
     const u32 i = j * SPB_P2_T + threadIdx.x;
     if (i >= m) continue;
     const u64 r = src[i];
-    const u64 ob = out0 + top_bits(r, l2bits);
+    const u64 ob = out0 + top_bits(r << skip2, l2bits);
     const u32 s = atomicAdd(cursor2 + ob, 1u);
     if (s < cap2) rec2[ob * cap2 + s] = r; else atomicOr(err, (u32)ERR_OVERFLOW);
   }
@@ -433,7 +434,7 @@ k_partition2(const u64* __restrict__ rec_in, u64 cap_in, const u32* __restrict__
 #pragma unroll
       for (u32 j = 0; j < SPB_P2_PT; ++j) { const u32 i = j * SPB_P2_T + tid; rec[j] = i < m ? *reinterpret_cast<const uint2*>(st + i) : make_uint2(0u, 0u); }
 #pragma unroll
-      for (u32 j = 0; j < SPB_P2_PT; ++j) { const u32 i = j * SPB_P2_T + tid; rk[j] = i < m ? atomicAdd(&hist[top_bits32(rec[j].y, l2bits)], 1u) : 0u; }
+      for (u32 j = 0; j < SPB_P2_PT; ++j) { const u32 i = j * SPB_P2_T + tid; rk[j] = i < m ? atomicAdd(&hist[top_bits32(rec[j].y << skip2, l2bits)], 1u) : 0u; }
       __syncthreads();
       const u32 b = tid;                             // SPB_P2_T == SPB_PART_MAXB: one bucket per thread
       const u32 cnt = b < NB ? hist[b] : 0u;
@@ -450,7 +451,7 @@ k_partition2(const u64* __restrict__ rec_in, u64 cap_in, const u32* __restrict__
       hist[b] = 0;
       __syncthreads();
 #pragma unroll
-      for (u32 j = 0; j < SPB_P2_PT; ++j) { const u32 i = j * SPB_P2_T + tid; if (i < m) *reinterpret_cast<uint2*>(sorted2 + base[top_bits32(rec[j].y, l2bits)] + rk[j]) = rec[j]; }
+      for (u32 j = 0; j < SPB_P2_PT; ++j) { const u32 i = j * SPB_P2_T + tid; if (i < m) *reinterpret_cast<uint2*>(sorted2 + base[top_bits32(rec[j].y << skip2, l2bits)] + rk[j]) = rec[j]; }
       u64 gd = (out0 + b) * cap2 + gb - off;
       if (cnt && (u64)gb + cnt > cap2) { gd = trash; atomicOr(err, (u32)ERR_OVERFLOW); }
       gdst[b] = gd;
@@ -460,7 +461,7 @@ k_partition2(const u64* __restrict__ rec_in, u64 cap_in, const u32* __restrict__
         const u32 i = j * SPB_P2_T + tid;
         if (i < m) {
           const uint2 r = *reinterpret_cast<const uint2*>(sorted2 + i);
-          *reinterpret_cast<uint2*>(rec2 + gdst[top_bits32(r.y, l2bits)] + i) = r;
+          *reinterpret_cast<uint2*>(rec2 + gdst[top_bits32(r.y << skip2, l2bits)] + i) = r;
         }
       }
     }

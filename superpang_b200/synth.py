@@ -124,3 +124,25 @@ def write_fasta(path, names, seqs, width=0):
 
 def n_instances(seqs, k):
     return int(sum(max(0, len(s) - k + 1) for s in seqs if len(s) > k))
+
+
+def genome_set_device(n_genomes, length, ani, seed, device):
+    """SNP-mode genome set generated ON THE DEVICE (torch RNG; for workloads too large to generate and ship from the host
+    within a benchmark run, e.g. BASELINE config 4 at 4e9 bases): ancestor iid uniform, every base of genome g substituted
+    independently with p = (1 - ani) / 2.  Deterministic for a given (seed, GPU model): every rank of a multi-GPU run
+    generates the same bytes.  Returns (uint8 ASCII device tensor of n_genomes * length bases, uint64 offsets)."""
+    import torch
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(seed))
+    anc = torch.randint(0, 4, (length,), dtype=torch.uint8, device=device, generator=gen)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    out = torch.empty(n_genomes * length, dtype=torch.uint8, device=device)
+    p = (1.0 - ani) / 2.0
+    for g in range(n_genomes):
+        gen.manual_seed(int(seed) + 1 + g)
+        mask = torch.rand(length, device=device, generator=gen) < p
+        shift = torch.randint(1, 4, (length,), dtype=torch.uint8, device=device, generator=gen)
+        c = torch.where(mask, (anc + shift) & 3, anc)
+        out[g * length:(g + 1) * length] = lut[c.long()]
+    off = np.arange(n_genomes + 1, dtype=np.uint64) * np.uint64(length)
+    return out, off

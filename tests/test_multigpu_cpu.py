@@ -43,6 +43,7 @@ def _free_port():
     (4, {"SPB_MG_PROTOCOL": "part", "SPB_PART_AVG": "30", "SPB_MG_ALL_LINKS": "2", "SPB_EMU_ORDER": "shuffle", "SPB_EXPECT_SLICED": "1"}),
     (8, {"SPB_MG_PROTOCOL": "part", "SPB_PART_AVG": "40", "SPB_MG_ALL_LINKS": "2", "SPB_EXPECT_SLICED": "1"}),
     (2, {"SPB_MG_PROTOCOL": "part", "SPB_PART_AVG": "60", "SPB_MG_TAIL": "replicated"}),   # all links, graph + compaction on every rank
+    (2, {"SPB_MG_PROTOCOL": "part", "SPB_PART_AVG": "4", "SPB_PART_L2MAX": "4", "SPB_MG_ALL_LINKS": "2"}),   # level-2 partition in two passes (very large inputs)
 ], ids=lambda x: str(x) if isinstance(x, int) else (",".join(f"{k[4:].lower()}={v}" for k, v in x.items()) or "default"))
 def test_distributed_build_matches_reference(emu_lib, tmp_path, world, env):
     crafted = [c for c in helpers.load_crafted() if c["k"] == 31 and not c.get("degenerate")]
