@@ -388,12 +388,18 @@ class Engine:
         K-mers are hash-partitioned over the ranks: positions are cut into equal slices, each rank turns its
         slice into (hash, position) records, an all-to-all routes every record to the rank owning its hash
         range, the owner deduplicates exactly and an all-to-all returns the first position of every record.
-        First-appearance / orientation bitmaps and the per-position vertex ids are all-gathered, after which
-        every rank holds the complete DBG and `compact()` proceeds unchanged (replicated).  NCCL on GPUs;
-        the CPU test tier drives the same code with the host emulator over gloo."""
+        Mostly-unique inputs then build the graph and compact it SLICED over the ranks (`_mg_sliced_tail`); otherwise the
+        first-appearance / orientation bitmaps and the per-position vertex ids are all-gathered, after which every rank
+        holds the complete DBG and `compact()` proceeds unchanged (replicated).  The number of ranks must be a power of two
+        (one rank: plain `build_dbg()`).  NCCL on GPUs; the CPU test tier drives the same code with the host emulator over gloo."""
         import torch
         import torch.distributed as dist
         G, r = dist.get_world_size(group), dist.get_rank(group)
+        if G == 1:
+            return self.build_dbg()
+        if G & (G - 1):
+            # the owner of a k-mer is the top log2(G) bits of its hash: checked here, before any collective is issued
+            raise ValueError(f"build_dbg_distributed needs a power-of-two number of ranks (got {G})")
         cuda = self.kind.startswith("cuda")
         dev = torch.device("cuda", self.device) if cuda else torch.device("cpu")
         marks = []

@@ -390,6 +390,18 @@ static void launch_extract_k(spb_ctx* c, u64 lo, u64 hi, u64* slots, u64 cap, u3
   }
 }
 
+// Entry points make the context's device current and give the caller's device back when they return (a host process
+// that drives another GPU with its own runtime calls must not find its current device switched underneath it).
+#ifndef SPB_EMU
+struct DevGuard {
+  int prev = -1;
+  explicit DevGuard(int dev) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define SPB_ON_DEVICE(c) DevGuard spb_dev_guard_((c)->device)
+#else
+#define SPB_ON_DEVICE(c) do {} while (0)
+#endif
 // =========================================================================================== C-ABI
 extern "C" {
 
@@ -451,9 +463,7 @@ static void reset_state(spb_ctx* c) {
 
 void spb_destroy(spb_ctx* c) {
   if (!c) return;
-#ifndef SPB_EMU
-  cudaSetDevice(c->device);
-#endif
+  SPB_ON_DEVICE(c);
   dev_sync(c);
   for (auto& kv : c->live) backend_free(kv.first);
   c->live.clear();
@@ -473,9 +483,7 @@ const char* spb_last_error(const spb_ctx* c) { return c ? c->err : "null context
 
 int spb_load(spb_ctx* c, const uint8_t* ascii, const uint64_t* seq_off, uint32_t n_seq, uint32_t k) {
   if (!c) return SPB_EINVAL;
-#ifndef SPB_EMU
-  CK(cudaSetDevice(c->device));
-#endif
+  SPB_ON_DEVICE(c);
   if (!ascii || !seq_off || n_seq == 0) return fail(c, SPB_EINVAL, "empty input");
   if (k < 3 || (k & 1) == 0) return fail(c, SPB_EINVAL, "k must be odd and >= 3 (got %u); the reference assumes odd k (SURVEY Q8)", k);
   if (k > 4000) return fail(c, SPB_EINVAL, "k = %u exceeds the reference's limit (Compressor.pyx:35)", k);
@@ -1055,9 +1063,7 @@ int spb_build_dbg(spb_ctx* c, spb_counts* out) {
   if (!c) return SPB_EINVAL;
   if (c->state < 1) return fail(c, SPB_ESTATE, "spb_build_dbg before spb_load");
   if (c->state > 1) return fail(c, SPB_ESTATE, "spb_build_dbg called twice; call spb_load again");
-#ifndef SPB_EMU
-  CK(cudaSetDevice(c->device));
-#endif
+  SPB_ON_DEVICE(c);
   stats_reset(c);
   int tm;
   // Default: single global table (two random HBM accesses per instance).  SPB_DEDUP=staged selects the partitioned
@@ -1133,9 +1139,7 @@ int spb_mg_records(spb_ctx* c, uint64_t pos_lo, uint64_t pos_hi, uint32_t n_owne
   if (c->state != 1) return fail(c, SPB_ESTATE, "spb_mg_records needs a freshly loaded input");
   if (!pow2(n_owners)) return fail(c, SPB_EINVAL, "n_owners must be a power of two");
   if (pos_lo % 256) return fail(c, SPB_EINVAL, "pos_lo must be a multiple of 256");
-#ifndef SPB_EMU
-  CK(cudaSetDevice(c->device));
-#endif
+  SPB_ON_DEVICE(c);
   u32 bb = 0; while ((1u << bb) < n_owners) ++bb;
   uint64_t slice = 0; spb_mg_slice(c, n_owners, &slice);
   if (pos_hi > c->T) pos_hi = c->T;
@@ -1150,9 +1154,7 @@ int spb_mg_dedup(spb_ctx* c, const uint64_t* keys, const uint32_t* pos, const ui
   if (!c) return SPB_EINVAL;
   if (c->state != 1) return fail(c, SPB_ESTATE, "spb_mg_dedup needs a loaded input");
   if (!pow2(n_owners) || owner >= n_owners) return fail(c, SPB_EINVAL, "bad owner / n_owners");
-#ifndef SPB_EMU
-  CK(cudaSetDevice(c->device));
-#endif
+  SPB_ON_DEVICE(c);
   u32 bb = 0; while ((1u << bb) < n_owners) ++bb;
   PRIM(dd_owner(c, (const u64*)keys, pos, (const u64*)chunk_counts, n_chunks, bb, owner, owner + 1, rep_out));
   return check_err(c, "spb_mg_dedup");
@@ -1164,9 +1166,7 @@ int spb_mg_dedup(spb_ctx* c, const uint64_t* keys, const uint32_t* pos, const ui
 int spb_mg_probe(spb_ctx* c, double* ext_ratio, double* dup_ratio) {
   if (!c || !ext_ratio || !dup_ratio) return SPB_EINVAL;
   if (c->state != 1) return fail(c, SPB_ESTATE, "spb_mg_probe needs a freshly loaded input");
-#ifndef SPB_EMU
-  CK(cudaSetDevice(c->device));
-#endif
+  SPB_ON_DEVICE(c);
   u64 CH = 1ull << 22;
   if (const char* e = getenv("SPB_CHUNK_BITS")) { int b = atoi(e); if (b >= 8 && b <= 32) CH = 1ull << b; }
   *ext_ratio = 0; *dup_ratio = 0;
@@ -1202,9 +1202,7 @@ int spb_mg_dedup_links(spb_ctx* c, uint64_t* keys_io, uint32_t* pos_io, uint64_t
   if (!c) return SPB_EINVAL;
   if (c->state != 1) return fail(c, SPB_ESTATE, "spb_mg_dedup_links needs a loaded input");
   if (!pow2(n_owners)) return fail(c, SPB_EINVAL, "n_owners must be a power of two");
-#ifndef SPB_EMU
-  CK(cudaSetDevice(c->device));
-#endif
+  SPB_ON_DEVICE(c);
   u32 bbo = 0; while ((1u << bbo) < n_owners) ++bbo;
   u32 sb = 0; while (sb < 8 && (n_total >> sb) > 2200000ull) ++sb;          // sub-buckets of ~2 M records
   if (const char* e = getenv("SPB_BUCKET_BITS")) sb = (u32)atoi(e);
@@ -1272,9 +1270,7 @@ int spb_mg_owned_links(spb_ctx* c, uint32_t rank, uint32_t n_owners, uint64_t* s
   if (!c) return SPB_EINVAL;
   if (c->state != 1) return fail(c, SPB_ESTATE, "spb_mg_owned_links needs a loaded input");
   if (!pow2(n_owners) || n_owners < 2 || rank >= n_owners) return fail(c, SPB_EINVAL, "n_owners must be a power of two >= 2, rank < n_owners");
-#ifndef SPB_EMU
-  CK(cudaSetDevice(c->device));
-#endif
+  SPB_ON_DEVICE(c);
   uint64_t slice = 0; spb_mg_slice(c, n_owners, &slice);
   int r0 = alloc_position_state(c, slice * n_owners); if (r0) return r0;
   const u64 T = c->T, n = nblk(T, TPB) * TPB;
@@ -1385,9 +1381,7 @@ int spb_mg_part_records(spb_ctx* c, uint64_t pos_lo, uint64_t pos_hi, uint32_t n
   if (c->state != 1) return fail(c, SPB_ESTATE, "spb_mg_part_records needs a freshly loaded input");
   if (!pow2(n_owners)) return fail(c, SPB_EINVAL, "n_owners must be a power of two");
   if (pos_lo % 256) return fail(c, SPB_EINVAL, "pos_lo must be a multiple of 256");
-#ifndef SPB_EMU
-  CK(cudaSetDevice(c->device));
-#endif
+  SPB_ON_DEVICE(c);
   PartGeom g;
   *overflow = 0;
   if (part_geometry(c, n_owners, &g)) { *overflow = 1; return SPB_OK; }
@@ -1414,9 +1408,7 @@ int spb_mg_part_dedup(spb_ctx* c, const uint64_t* recs, const uint32_t* counts, 
                       void** links_dev, int* overflow) {
   if (!c || !send_counts || !links_dev || !overflow) return SPB_EINVAL;
   if (c->state != 1) return fail(c, SPB_ESTATE, "spb_mg_part_dedup needs a loaded input");
-#ifndef SPB_EMU
-  CK(cudaSetDevice(c->device));
-#endif
+  SPB_ON_DEVICE(c);
   PartGeom g;
   *overflow = 0;
   if (part_geometry(c, n_owners, &g)) { *overflow = 1; return SPB_OK; }
@@ -1479,6 +1471,7 @@ int spb_mg_part_dedup(spb_ctx* c, const uint64_t* recs, const uint32_t* counts, 
 // Position side, "links" protocol: the links received for the local slice -> first-appearance bits of the slice.
 int spb_mg_apply_links(spb_ctx* c, const uint64_t* links, uint64_t n, uint64_t pos_lo, uint64_t pos_hi) {
   if (!c) return SPB_EINVAL;
+  SPB_ON_DEVICE(c);
   if (c->state != 1 || (!c->dd_pos && !c->mg_owned)) return fail(c, SPB_ESTATE, "spb_mg_apply_links without spb_mg_records / spb_mg_owned_links");
   const u64 P = c->npos_pad, nw32 = P / 32;
   ALLOC(c->mg_seen, u32, P + 8); ALLOC(c->mg_dup, u32, nw32 + 8);
@@ -1496,6 +1489,7 @@ int spb_mg_apply_links(spb_ctx* c, const uint64_t* links, uint64_t n, uint64_t p
 
 int spb_mg_scatter(spb_ctx* c, const uint32_t* rep) {
   if (!c) return SPB_EINVAL;
+  SPB_ON_DEVICE(c);
   if (c->state != 1 || !c->dd_pos) return fail(c, SPB_ESTATE, "spb_mg_scatter without spb_mg_records");
   PRIM(dd_scatter(c, rep));
   return check_err(c, "spb_mg_scatter");
@@ -1511,6 +1505,7 @@ int spb_mg_buffers(spb_ctx* c, void** fbits_dev, void** obits_dev, void** sp_dev
 
 int spb_mg_ids(spb_ctx* c, uint64_t pos_lo, uint64_t pos_hi) {
   if (!c) return SPB_EINVAL;
+  SPB_ON_DEVICE(c);
   if (c->state != 1 || !c->sp) return fail(c, SPB_ESTATE, "spb_mg_ids out of order");
   if (pos_hi > c->T) pos_hi = c->T;
   PRIM(dd_ids(c, pos_lo, pos_hi, nullptr, 1, c->mg_seen));       // links protocol: the representatives live in mg_seen
@@ -1520,6 +1515,7 @@ int spb_mg_ids(spb_ctx* c, uint64_t pos_lo, uint64_t pos_hi) {
 
 int spb_mg_graph(spb_ctx* c, spb_counts* out) {
   if (!c) return SPB_EINVAL;
+  SPB_ON_DEVICE(c);
   if (c->state != 1 || !c->v2pos) return fail(c, SPB_ESTATE, "spb_mg_graph out of order");
   stats_reset(c); stat_set(c, "multi_gpu", 1);
   int tm = t_begin(c);
@@ -1788,9 +1784,7 @@ int spb_compact(spb_ctx* c, spb_counts* out) {
   if (!c) return SPB_EINVAL;
   if (c->state != 2) return fail(c, SPB_ESTATE, "spb_compact needs a freshly built DBG (state %d)", c->state);
   if (c->sl.on) return fail(c, SPB_ESTATE, "spb_compact: the DBG of this context is sliced over several ranks (spb_mg_slice_* / spb_mg_complete)");
-#ifndef SPB_EMU
-  CK(cudaSetDevice(c->device));
-#endif
+  SPB_ON_DEVICE(c);
   int tm = t_begin(c);
   c->ncyc = 0;
   for (int pass = 0; pass < 2; ++pass) {
@@ -1865,6 +1859,7 @@ static void free_graph_results(spb_ctx* c) {
 
 int spb_mg_slice_ids(spb_ctx* c, uint32_t rank, uint32_t n_ranks) {
   if (!c || !n_ranks || rank >= n_ranks) return SPB_EINVAL;
+  SPB_ON_DEVICE(c);
   if (c->state != 1 || !c->sp || !c->mg_seen) return fail(c, SPB_ESTATE, "spb_mg_slice_ids needs spb_mg_apply_links over all positions first");
   stats_reset(c); stat_set(c, "multi_gpu", 1);
   uint64_t S = 0; spb_mg_slice(c, n_ranks, &S);
@@ -1893,6 +1888,7 @@ int spb_mg_slice_ids(spb_ctx* c, uint32_t rank, uint32_t n_ranks) {
 
 int spb_mg_slice_junctions(spb_ctx* c, uint64_t* n, void** jk_dev, void** js_dev) {
   if (!c || !n || !jk_dev || !js_dev) return SPB_EINVAL;
+  SPB_ON_DEVICE(c);
   if (c->state != 1 || !c->sl.on) return fail(c, SPB_ESTATE, "spb_mg_slice_junctions out of order");
   u64* Jk; u8* Js; u64 nj;
   dfree(c, c->Jk); dfree(c, c->Js);
@@ -1905,6 +1901,7 @@ int spb_mg_slice_junctions(spb_ctx* c, uint64_t* n, void** jk_dev, void** js_dev
 
 int spb_mg_slice_graph(spb_ctx* c, const uint64_t* jk_all, const uint8_t* js_all, uint64_t n_all, uint64_t* n_edges_local) {
   if (!c) return SPB_EINVAL;
+  SPB_ON_DEVICE(c);
   if (c->state != 1 || !c->sl.on) return fail(c, SPB_ESTATE, "spb_mg_slice_graph out of order");
   u64* Jk; u8* Js;
   ALLOC(Jk, u64, n_all + 1); ALLOC(Js, u8, n_all + 1);
@@ -1921,6 +1918,7 @@ int spb_mg_slice_graph(spb_ctx* c, const uint64_t* jk_all, const uint8_t* js_all
 
 int spb_mg_slice_classify(spb_ctx* c, uint32_t* n_init, uint32_t* n_start, uint32_t* n_end, void** init_dev, void** plo_dev, void** phi_dev) {
   if (!c || !n_init || !n_start || !n_end) return SPB_EINVAL;
+  SPB_ON_DEVICE(c);
   if (c->state != 2 || !c->sl.on) return fail(c, SPB_ESTATE, "spb_mg_slice_classify out of order");
   dfree(c, c->init_list); dfree(c, c->plo); dfree(c, c->phi);
   u32 nI[1], nP[2];
@@ -1933,6 +1931,7 @@ int spb_mg_slice_classify(spb_ctx* c, uint32_t* n_init, uint32_t* n_start, uint3
 int spb_mg_slice_contract(spb_ctx* c, const uint32_t* init_all, uint32_t n_init, const uint32_t* plo_all, const uint32_t* phi_all, uint32_t n_piece,
                           uint64_t n_edges_total, int pass, int* again) {
   if (!c || !again) return SPB_EINVAL;
+  SPB_ON_DEVICE(c);
   if (c->state != 2 || !c->sl.on) return fail(c, SPB_ESTATE, "spb_mg_slice_contract out of order");
   u32 *il, *pl, *ph;
   ALLOC(il, u32, n_init + 1); ALLOC(pl, u32, n_piece + 1); ALLOC(ph, u32, n_piece + 1);
@@ -1947,6 +1946,7 @@ int spb_mg_slice_contract(spb_ctx* c, const uint32_t* init_all, uint32_t n_init,
 
 int spb_mg_slice_emit(spb_ctx* c, uint64_t* n_op, void** op_dev, uint64_t* n_mp, void** mp_dev, void** has01_dev) {
   if (!c || !n_op || !n_mp) return SPB_EINVAL;
+  SPB_ON_DEVICE(c);
   if (c->state != 2 || !c->sl.on || !c->nxt) return fail(c, SPB_ESTATE, "spb_mg_slice_emit out of order");
   c->cnt.n_cycle_comp = c->ncyc;
   u64 totv = 0, tots = 0;
@@ -1962,6 +1962,7 @@ int spb_mg_slice_emit(spb_ctx* c, uint64_t* n_op, void** op_dev, uint64_t* n_mp,
 
 int spb_mg_slice_finish(spb_ctx* c, const uint64_t* op_all, uint64_t n_op, const uint64_t* mp_all, uint64_t n_mp, const uint8_t* has01_any, spb_counts* out) {
   if (!c) return SPB_EINVAL;
+  SPB_ON_DEVICE(c);
   if (c->state != 2 || !c->sl.on || !c->has01) return fail(c, SPB_ESTATE, "spb_mg_slice_finish out of order");
   u64 *op, *mp; u8* h;
   ALLOC(op, u64, n_op + c->n_seq + 1); ALLOC(mp, u64, n_mp + c->n_seq + 1); ALLOC(h, u8, 2ull * c->n_seq + 8);
@@ -1981,6 +1982,7 @@ int spb_mg_slice_finish(spb_ctx* c, const uint64_t* op_all, uint64_t n_op, const
 // (rows for 1 and 2; the first edge row of a rank is the sum of the counts of the ranks below it).
 int spb_mg_shard(spb_ctx* c, int which, void** dev, uint64_t* first, uint64_t* count) {
   if (!c || !dev || !first || !count) return SPB_EINVAL;
+  SPB_ON_DEVICE(c);
   if (!c->sl.on || c->state < 2) return fail(c, SPB_ESTATE, "spb_mg_shard: no sliced results in this context");
   const spb_ctx::Slice& sl = c->sl;
   switch (which) {
@@ -2017,6 +2019,7 @@ int spb_mg_shard_to_host(spb_ctx* c, int which, void* host_base, uint64_t* bytes
 // would have reached (all getters work).  No communication: the bitmaps and links are complete on every rank.
 int spb_mg_complete(spb_ctx* c, spb_counts* out) {
   if (!c) return SPB_EINVAL;
+  SPB_ON_DEVICE(c);
   if (!c->sl.on) { if (out) *out = c->cnt; return SPB_OK; }
   if (!c->mg_seen) return fail(c, SPB_ESTATE, "spb_mg_complete: the links are gone");
   const bool compacted = c->state == 3;
@@ -2035,9 +2038,9 @@ int spb_mg_complete(spb_ctx* c, spb_counts* out) {
 }
 
 // ------------------------------------------------------------------------------------------- getters
-#define NEED(st) do { if (!c) return SPB_EINVAL; if (c->state < (st)) return fail(c, SPB_ESTATE, "%s: results not available yet (state %d)", __func__, c->state); } while (0)
+#define NEED(st) if (!c) return SPB_EINVAL; SPB_ON_DEVICE(c); if (c->state < (st)) return fail(c, SPB_ESTATE, "%s: results not available yet (state %d)", __func__, c->state)
 // getters that read the per-position / per-vertex / per-NBP-vertex arrays: those are sliced over the ranks until spb_mg_complete
-#define NEED_FULL(st) do { NEED(st); if (c->sl.on) return fail(c, SPB_ESTATE, "%s: the results of this context are sliced over the ranks (spb_mg_shard for the local part, spb_mg_complete for all of it)", __func__); } while (0)
+#define NEED_FULL(st) NEED(st); if (c->sl.on) return fail(c, SPB_ESTATE, "%s: the results of this context are sliced over the ranks (spb_mg_shard for the local part, spb_mg_complete for all of it)", __func__)
 
 int spb_get_vertex2coords(spb_ctx* c, uint32_t* out) {
   NEED_FULL(2);
@@ -2132,6 +2135,7 @@ int spb_get_nbp_seqs(spb_ctx* c, uint64_t* off, uint8_t* ascii) {
 // components and edge rows; spb_get_nbp_seqs(ctx, off, the same pointer) then only waits for it.  nullptr clears.
 int spb_set_host_output(spb_ctx* c, uint8_t* nbp_seqs_host, uint64_t capacity) {
   if (!c) return SPB_EINVAL;
+  SPB_ON_DEVICE(c);
 #ifndef SPB_EMU
   if (c->d2h_pending) { cudaEventSynchronize(c->ev_d2h); c->d2h_pending = false; }
 #endif

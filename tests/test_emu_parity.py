@@ -159,3 +159,38 @@ def test_emu_variants_match_reference_golden(emu_lib, monkeypatch, env):
     for case in helpers.load_json("synthetic.json")["cases"][:3]:
         sd = helpers.synth_seqdict(case["n_genomes"], case["length"], case["ani"], case["seed"], case["mode"])
         helpers.assert_summary(digests.summarize(run_emu(emu_lib, sd, case["k"]).to_result()), case["summary"])
+
+
+def test_all_sequences_shorter_than_k(emu_lib):
+    """Every sequence has len <= k: the reference builds an empty graph and yields no contigs (`lib/Assembler.py:150-153`);
+    the new path must do the same instead of failing in the compaction."""
+    from superpang_b200 import _capi
+    from superpang_b200.assembler import Assembler
+    A = Assembler({"a": "ACGTACGTAC", "b": "ACG"}, 31, engine=_capi.Engine(lib=emu_lib))
+    assert A.counts["n_inst"] == 0 and A.counts["n_vertices"] == 0
+    c = A.compact()
+    assert c["n_nbp"] == 0 and c["n_comp"] == 0
+    assert A.collect_nbps() == [] and A.vertex2coords.shape == (0, 2) and A.edges.shape == (0, 2) and A.seqPaths == {}
+
+
+def test_distributed_build_validates_world_size(emu_lib):
+    """world size 1 falls back to the single-GPU build; a non-power-of-two size is refused before any collective."""
+    import torch.distributed as dist
+    from superpang_b200 import _capi
+
+    class _FakeDist:
+        def __init__(self, n):
+            self.n = n
+    eng = _capi.Engine(lib=emu_lib)
+    import numpy as np
+    seq = np.frombuffer(b"ACGTTGCATGGACCATTGACGGTACCATGACAGTTGACCATGAAACCCGTGTTAGC", dtype=np.uint8)
+    eng.load(seq, np.array([0, len(seq)], dtype=np.uint64), 31)
+    real = (dist.get_world_size, dist.get_rank)
+    try:
+        dist.get_world_size, dist.get_rank = (lambda group=None: 3), (lambda group=None: 0)
+        with pytest.raises(ValueError):
+            eng.build_dbg_distributed()
+        dist.get_world_size = lambda group=None: 1
+        assert eng.build_dbg_distributed()["n_inst"] == len(seq) - 30
+    finally:
+        dist.get_world_size, dist.get_rank = real
