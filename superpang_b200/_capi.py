@@ -407,12 +407,12 @@ class Engine:
         def mark(name):                      # stage boundaries (CUDA events on the current stream)
             if cuda:
                 e = torch.cuda.Event(enable_timing=True)
-                e.record(torch.cuda.current_stream())
+                e.record(torch.cuda.current_stream(self.device))
                 marks.append((name, e))
 
         def sync():
             if cuda:
-                torch.cuda.current_stream().synchronize()
+                torch.cuda.current_stream(self.device).synchronize()
 
         T = int(self._keep[1][-1])
         S = C.c_uint64()

@@ -1392,6 +1392,7 @@ __global__ void k_compact3(const u8* __restrict__ vflags, u32 nV, const u32* __r
   u64 v0 = (i3 + t_lo) * 8;
   if (i3 >= nT || v0 >= nV) return;
   u64 w = *(const u64*)(vflags + v0);
+  if (!(w & (SPB_M8 * (u64)(VF_INIT | VF_PSTART | VF_PEND)))) return;     // nothing to list in this tile (the usual case): no offsets needed
   u32 oI = off3[i3], oS = off3[nT + i3] - totI, oE = off3[2 * (u64)nT + i3] - totI - totS;
   for (u32 i = 0; i < 8 && v0 + i < nV; ++i) {
     u32 f = (u32)(w >> (8 * i)) & 0xFF;
@@ -2281,34 +2282,58 @@ __device__ __forceinline__ u32 edge_rows_of(const GView& g, u32 v, u32 fl) {
   return c;
 }
 __global__ void k_edge_write(GView g, const u32* __restrict__ off8, u32* __restrict__ edges, u32 t_lo, u32 t_hi) {
-  // grid-stride over the vertices of the tiles [t_lo, t_hi), four vertices per thread and iteration with their loads issued together
-  const u64 stride = (u64)gridDim.x * blockDim.x;
+  // One warp per window of 1024 vertices of the tiles [t_lo, t_hi), grid-stride.  A window in which every vertex carries the
+  // implicit edge and no junction entries (the usual case) is written without per-vertex offsets: row i is
+  // (v0 + i, v0 + i + 1) at off8[first tile] + i, two rows per 16-byte store.  Any other window: one vertex per lane and step,
+  // rows of vertex v start at off8[v / 8 - t_lo] + (rows of the lower vertices of its tile).
   uint2* rows = (uint2*)edges;
+  const u64 v_first = 8ull * t_lo;
   const u64 v_end = 8ull * t_hi < g.nV ? 8ull * t_hi : g.nV;
-  for (u64 vb = 8ull * t_lo + SPB_GTID(); vb < v_end; vb += 4 * stride) {
-    u64 wv[4]; u32 ov[4];
-#pragma unroll
-    for (u32 q = 0; q < 4; ++q) {
-      const u64 v = vb + q * stride;
-      wv[q] = v < v_end ? *(const u64*)(g.vflags + (v & ~7ull)) : 0ull;
-      ov[q] = v < v_end ? off8[(v >> 3) - t_lo] : 0u;
+  if (v_end <= v_first) return;
+  const u64 n_win = (v_end - v_first + 1023) / 1024;
+  const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+  const u32 lane = threadIdx.x & 31;
+  for (u64 wi = SPB_GTID() >> 5; wi < n_win; wi += nwarps) {
+    const u64 v0 = v_first + 1024 * wi;
+#ifndef SPB_EMU
+    if (v0 + 1024 <= v_end) {
+      const u64 need = SPB_M8 * (u64)(VF_R | VF_HASJ), want = SPB_M8 * (u64)VF_R;
+      const u64* fp = reinterpret_cast<const u64*>(g.vflags + v0 + 32 * lane);                     // 32 flag bytes per lane (v0 is a multiple of 8)
+      const u64 f0 = fp[0], f1 = fp[1], f2 = fp[2], f3 = fp[3];
+      const bool plain = ((f0 & need) == want) && ((f1 & need) == want) && ((f2 & need) == want) && ((f3 & need) == want);
+      if (__all_sync(0xffffffffu, plain)) {
+        const u64 o = off8[(v0 >> 3) - t_lo];
+        uint2* dst = rows + o;
+        if ((o & 1) == 0) {                                                                       // 16-byte aligned: two rows per store
+#pragma unroll 4
+          for (u32 j = 0; j < 16; ++j) {
+            const u32 i = 2 * (32 * j + lane);
+            const u32 v = (u32)v0 + i;
+            *reinterpret_cast<uint4*>(dst + i) = make_uint4(v, v + 1, v + 1, v + 2);
+          }
+        } else {
+#pragma unroll 4
+          for (u32 j = 0; j < 32; ++j) { const u32 i = 32 * j + lane; dst[i] = make_uint2((u32)v0 + i, (u32)v0 + i + 1); }
+        }
+        continue;
+      }
     }
-#pragma unroll
-    for (u32 q = 0; q < 4; ++q) {
-      const u64 v = vb + q * stride;
+#endif
+    for (u32 j = 0; j < 32; ++j) {
+      const u64 v = v0 + 32 * j + lane;
       if (v >= v_end) break;
+      const u64 w = *(const u64*)(g.vflags + (v & ~7ull));
+      u64 o = off8[(v >> 3) - t_lo];
       const u32 i = (u32)(v & 7);
-      const u64 w = wv[q];
       const u64 below = i ? (w & ((1ull << (8 * i)) - 1)) : 0;
-      u64 o = ov[q];
       if (!(below & (0x0101010101010101ull * VF_HASJ))) o += __popcll(below & (0x0101010101010101ull * VF_R));
-      else for (u32 j = 0; j < i; ++j) o += edge_rows_of(g, (u32)(v - i + j), (u32)(w >> (8 * j)) & 0xFF);
+      else for (u32 x = 0; x < i; ++x) o += edge_rows_of(g, (u32)(v - i + x), (u32)(w >> (8 * x)) & 0xFF);
       const u32 fl = (u32)(w >> (8 * i)) & 0xFF;
       bool r = (fl & VF_R) != 0;
       if (fl & VF_HASJ) {
-        u32 j = lower_bound_key(g.Jk, g.nJ, ((u64)v << 32) | v);
-        for (; j < g.nJ && (u32)(g.Jk[j] >> 32) == (u32)v; ++j) {
-          u32 d = (u32)g.Jk[j];
+        u32 x = lower_bound_key(g.Jk, g.nJ, ((u64)v << 32) | v);
+        for (; x < g.nJ && (u32)(g.Jk[x] >> 32) == (u32)v; ++x) {
+          u32 d = (u32)g.Jk[x];
           if (r && d > (u32)v + 1) { rows[o++] = make_uint2((u32)v, (u32)v + 1); r = false; }
           rows[o++] = make_uint2((u32)v, d);
         }
