@@ -653,8 +653,19 @@ static VidAt vid_view(spb_ctx* c) {
 }
 static VNbp vnbp_view(spb_ctx* c) {
   const u32 lo = c->sl.on ? 8u * c->sl.t_lo : 0u;
-  const u32 hi = c->sl.on ? (u32)std::min<u64>(8ull * (c->sl.t_hi + 1), c->nV) : c->nV;
+  const u32 hi = c->sl.on ? (u32)std::min<u64>(8ull * (c->sl.t_hi + 4), c->nV) : c->nV;     // first appearances of the slice reach up to 31 ids beyond the cut
+  if (!c->vnbp) return VNbp{nullptr, 0u, 0u, c->plo, c->phi, c->nP, c->dart_nbp};     // not materialised: every lookup goes through the piece list
   return VNbp{c->vnbp, lo, hi, c->plo, c->phi, c->nP, c->dart_nbp};
+}
+// vertex -> NBP map of ALL vertices (one GPU / completed state), built from the sorted piece list when a getter needs the
+// array and the compaction did not write it (mostly-unique inputs, see cp_emit)
+static int ensure_vnbp(spb_ctx* c) {
+  if (c->vnbp || c->state < 3) return 0;
+  const u32 nV = c->nV;
+  ALLOC(c->vnbp, u32, (u64)nV + 1);
+  dev_memset(c, c->vnbp + nV, 0xFF, 4);
+  SPB_LAUNCH(k_fill_vnbp, nblk(nblk(nV, 1024) * 32, TPB), TPB, c->stream, c->plo, c->phi, c->nP, c->dart_nbp, 0u, nV, c->vnbp);
+  return 0;
 }
 
 // vertex ids of the positions [lo, hi); vertex -> first position for the first appearances in [tlo, thi); the flag byte
@@ -1537,14 +1548,15 @@ int spb_mg_graph(spb_ctx* c, spb_counts* out) {
 static int cp_classify(spb_ctx* c, u32** init_l, u32** plo_l, u32** phi_l, u32* nI_out, u32* nP_out) {
   const u32 nV = c->nV;
   GView g{c->vflags, c->Jk, c->Js, c->nJ, nV};
-  const u32 nTall = (nV + 7) / 8;
-  const u32 t_lo = c->sl.on ? c->sl.t_lo : 0u, t_hi = c->sl.on ? c->sl.t_hi : nTall;
-  const u32 f_lo = c->sl.on ? (t_lo ? t_lo - 1 : 0u) : 0u, f_hi = c->sl.on ? std::min(t_hi + 1, nTall) : nTall;   // piece flags: one tile of halo
-  const u32 c_lo = c->sl.on ? (f_lo ? f_lo - 1 : 0u) : 0u, c_hi = c->sl.on ? std::min(f_hi + 1, nTall) : nTall;   // init bits: one more
+  // groups of 8 * SPB_CW = 32 vertices; the slice's tile range is aligned to them (spb_mg_slice_ids)
+  const u32 nGall = (u32)(((u64)nV + 8 * SPB_CW - 1) / (8 * SPB_CW));
+  const u32 nTall = (u32)(((u64)nV + 7) / 8);
+  const auto grp = [&](u32 t) { return t >= nTall ? nGall : t / SPB_CW; };      // tile cuts are multiples of SPB_CW, or the end
+  const u32 t_lo = c->sl.on ? grp(c->sl.t_lo) : 0u, t_hi = c->sl.on ? grp(c->sl.t_hi) : nGall;
+  const u32 f_lo = c->sl.on ? (t_lo ? t_lo - 1 : 0u) : 0u, f_hi = c->sl.on ? std::min(t_hi + 1, nGall) : nGall;   // piece flags: one group of halo
   const u32 nT = t_hi - t_lo;
   u32 *cnt3, *off3; ALLOC(cnt3, u32, 3ull * nT + 1); ALLOC(off3, u32, 3ull * nT + 1);
-  SPB_LAUNCH(k_classify8, nblk(c_hi - c_lo, TPB), TPB, c->stream, g, c->vflags, c->errflag, c_lo, c_hi);
-  SPB_LAUNCH(k_piece_flags8, nblk(f_hi - f_lo, TPB), TPB, c->stream, c->vflags, nV, cnt3, nT, f_lo, f_hi, t_lo, t_hi);
+  SPB_LAUNCH(k_classify_pieces, nblk(f_hi - f_lo, TPB), TPB, c->stream, g, c->vflags, cnt3, nT, f_lo, f_hi, t_lo, t_hi, c->errflag);
   u64 tot3 = 0;
   PRIM(prim_scan_u32(c, cnt3, off3, 3ull * nT, &tot3));
   u32 marks[2] = {0, 0};
@@ -1554,7 +1566,7 @@ static int cp_classify(spb_ctx* c, u32** init_l, u32** plo_l, u32** phi_l, u32* 
   }
   const u32 nI = marks[0], nP = marks[1] - marks[0];
   if (!c->sl.on && (u64)nI + 2ull * nP != tot3) return fail(c, SPB_ECUDA, "internal: piece starts (%u) != piece ends (%llu)", nP, (unsigned long long)(tot3 - marks[1]));
-  const u32 nE = (u32)(tot3 - marks[1]);               // piece ends in the own tiles (a piece may cross a cut: starts != ends locally)
+  const u32 nE = (u32)(tot3 - marks[1]);               // piece ends in the own groups (a piece may cross a cut: starts != ends locally)
   u32 *il, *pl, *ph; ALLOC(il, u32, nI + 1); ALLOC(pl, u32, nP + 1); ALLOC(ph, u32, nE + 1);
   SPB_LAUNCH(k_compact3, nblk(nT, TPB), TPB, c->stream, c->vflags, nV, off3, nT, nI, nP, il, pl, ph, t_lo);
   dfree(c, cnt3); dfree(c, off3);
@@ -1664,7 +1676,11 @@ static int cp_emit(spb_ctx* c, u64 totv, u64 tots) {
   c->seqs = c->seqs_base + (sl.seq_lo & 3);            // word-aligned stores of the sequence kernels keep the phase of the global offsets
   u32* verts = c->verts - sl.vert_lo; u8* seqs = c->seqs - sl.seq_lo;      // addressed with the global offsets
   u32* vnbp_w = nullptr;
-  if (!sl.on) { ALLOC(c->vnbp, u32, (u64)nV + 1); dev_memset(c, c->vnbp, 0xFF, ((u64)nV + 1) * 4); vnbp_w = c->vnbp; }
+  // The vertex -> NBP map costs 4 bytes per vertex to write.  On mostly-unique inputs the origin pass asks for a handful of
+  // vertices only (windows of consecutive first appearances are decided by their flag bytes), which the piece list answers
+  // by binary search; the array is then built lazily for the getters that want it (ensure_vnbp).
+  const bool lazy_vnbp = !sl.on && (c->n_inst - nV) * 16 < (u64)nV && !getenv("SPB_EAGER_VNBP");
+  if (!sl.on && !lazy_vnbp) { ALLOC(c->vnbp, u32, (u64)nV + 1); dev_memset(c, c->vnbp, 0xFF, ((u64)nV + 1) * 4); vnbp_w = c->vnbp; }
   const VPos vp = vpos_view(c);
   SPB_LAUNCH(k_emit_ends, nblk((u64)(n_hi - n_lo) * 32, TPB), TPB, c->stream, t, n_lo, n_hi, k, T, c->F, c->R, vp, c->voff, c->soff, verts, seqs);
   u32 *nch, *choff; ALLOC(nch, u32, nD + 1); ALLOC(choff, u32, nD + 1);
@@ -1681,8 +1697,8 @@ static int cp_emit(spb_ctx* c, u64 totv, u64 tots) {
              c->F, c->R, vp, c->voff, c->soff, verts, seqs, vnbp_w, n_lo, n_hi);
   dfree(c, nch); dfree(c, choff);
   if (sl.on) {                                         // vertex -> NBP map of the own tiles (+ one tile: see k_piece_flags8)
-    const VNbp vn = vnbp_view(c);
     ALLOC(c->vnbp, u32, (u64)nV + 1);                  // addressed by the global vertex id; only [v_lo, v_hi) of it is touched
+    const VNbp vn = vnbp_view(c);
     SPB_LAUNCH(k_fill_vnbp, nblk(nblk(vn.v_hi - vn.v_lo, 1024) * 32, TPB), TPB, c->stream, c->plo, c->phi, nP, c->dart_nbp, vn.v_lo, vn.v_hi, c->vnbp);
   }
   cp_free_contracted(c);
@@ -1881,7 +1897,7 @@ int spb_mg_slice_ids(spb_ctx* c, uint32_t rank, uint32_t n_ranks) {
   sl.v_lo = vf[0]; sl.v_hi = vf[1];
   // own tiles of 8 vertices: cut below the first vertex of every slice (an empty slice at the end of the input owns nothing)
   const u32 nTall = (c->nV + 7) / 8;
-  sl.t_lo = sl.pos_lo >= c->T ? nTall : sl.v_lo >> 3; sl.t_hi = sl.pos_hi >= c->T ? nTall : sl.v_hi >> 3;
+  sl.t_lo = sl.pos_lo >= c->T ? nTall : (sl.v_lo >> 5) << 2; sl.t_hi = sl.pos_hi >= c->T ? nTall : (sl.v_hi >> 5) << 2;     // cut below multiples of 32 ids
   sl.on = true;
   return check_err(c, "spb_mg_slice_ids");
 }
@@ -2097,6 +2113,7 @@ int spb_get_seq_intervals(spb_ctx* c, uint64_t* off, uint32_t* intervals) {
 int spb_get_components(spb_ctx* c, int32_t* out) {
   NEED_FULL(3);
   int32_t* tmp; ALLOC(tmp, int32_t, (u64)c->nV + 1);
+  PRIM(ensure_vnbp(c));
   SPB_LAUNCH(k_vertex_comp, nblk(c->nV, TPB), TPB, c->stream, c->vflags, c->nV, c->vnbp, c->init_list, c->nI, c->parent, c->label_of_root,
              c->nbp_comp, tmp);
   dev_copy(c, out, tmp, 4ull * c->nV); dev_sync(c);
@@ -2232,6 +2249,7 @@ static int build_occurrences(spb_ctx* c) {
     PRIM(unique_sorted(c, pairs, nopay, np, &nu));
   }
   ALLOC(c->occ_counts, u32, nN + 1);
+  PRIM(ensure_vnbp(c));
   SPB_LAUNCH(k_occ_counts, nblk(nN, TPB), TPB, c->stream, pairs, nu, sb, c->nt, nN, c->g_rev, c->vnbp, c->vflags, c->nV, c->occ_counts);
   // per-sequence view: (sequence << 32 | NBP), sorted; pairs of NBPs the reference's pre-filter rejects are dropped
   u64 *sk, *sk2; ALLOC(sk, u64, (u64)nu + 1); ALLOC(sk2, u64, (u64)nu + 1);
@@ -2391,6 +2409,7 @@ int spb_path_origins_ex(spb_ctx* c, int kind, uint32_t n_paths, const uint64_t* 
   for (u32 i = 1; i < n_bub; ++i) if (bub_vert[i] <= bub_vert[i - 1]) return fail(c, SPB_EINVAL, "spb_path_origins: bubble vertices must ascend");
   int r = build_init_seq_pairs(c);
   if (r) return r;
+  PRIM(ensure_vnbp(c));
   u64* d_off; u32* d_verts; u64 *cnt, *pairs = nullptr; u64 total = 0;
   PRIM(paths_to_device(c, kind, n_paths, off, items, &d_off, &d_verts, &total));
   ALLOC(cnt, u64, 2);

@@ -1335,70 +1335,92 @@ __device__ __forceinline__ bool classify_slow(const GView& g, u32 v, u8 f, u32* 
   return init;
 }
 #define SPB_M8 0x0101010101010101ull
-__global__ void k_classify8(GView g, u8* vflags, u32* err, u32 t_lo, u32 t_hi) {   // tiles [t_lo, t_hi) of 8 vertices
-  u64 t = SPB_GTID() + t_lo;
-  u64 v0 = t * 8;
-  if (t >= t_hi || v0 >= g.nV) return;
-  u64 w = *(const u64*)(g.vflags + v0);
-  u64 prev = v0 ? g.vflags[v0 - 1] : 0;
-  u64 nvalid = g.nV - v0 < 8 ? g.nV - v0 : 8;
-  u64 vm = nvalid == 8 ? ~0ull : ((1ull << (8 * nvalid)) - 1);
-  // all eight bytes at once (VF_R = bit 0, VF_HASJ = bit 1, VF_INIT = bit 3)
-  u64 r = w & SPB_M8, rprev = (r << 8) | (prev & VF_R);
-  u64 hasj = (w >> 1) & SPB_M8;
-  u64 init = ~(r & rprev) & SPB_M8 & ~hasj;          // no junction entries: init <=> not both implicit neighbours
+
+// K5 + K6 fused, 32 vertices (4 flag words = one 32-byte sector) per thread: init bits, then pieces = maximal runs of
+// consecutive-id extender vertices linked by implicit edges, and the per-thread counts of inits / piece starts / piece
+// ends for the compaction below.  The init bits of the two vertices next to the thread's range are recomputed from the
+// neighbouring words (they depend on the stable bits R / HASJ / SEQLIM / CYC and on J only), so ONE pass over the flag bytes
+// replaces the classification pass + the piece pass, and the count arrays are 4 times shorter than with one word per thread.
+#define SPB_CW 4                                     // flag words per thread
+__device__ __forceinline__ u64 classify_word(const GView& g, u64 v0, u64 w, u64 prev_byte, u32* err, bool report) {
+  const u64 nvalid = g.nV - v0 < 8 ? g.nV - v0 : 8;
+  const u64 vm = nvalid == 8 ? ~0ull : ((1ull << (8 * nvalid)) - 1);
+  const u64 r = w & SPB_M8, rprev = (r << 8) | (prev_byte & VF_R);
+  const u64 hasj = (w >> 1) & SPB_M8;
+  const u64 init = ~(r & rprev) & SPB_M8 & ~hasj;    // no junction entries: init <=> not both implicit neighbours
   u64 out = (w & ~(SPB_M8 * (u64)(VF_INIT | VF_PSTART | VF_PEND | VF_IN2))) | ((init & vm) << 3);
   u64 slow = hasj & vm;
+  u32 dummy = 0;
   while (slow) {                                      // the few vertices with junction entries: general rule
 #ifdef SPB_EMU
-    u32 i = (u32)(__builtin_ctzll(slow) >> 3);
+    const u32 i = (u32)(__builtin_ctzll(slow) >> 3);
 #else
-    u32 i = (u32)((__ffsll((long long)slow) - 1) >> 3);
+    const u32 i = (u32)((__ffsll((long long)slow) - 1) >> 3);
 #endif
     slow &= slow - 1;
-    if (classify_slow(g, (u32)(v0 + i), (u8)(w >> (8 * i)), err)) out |= (u64)VF_INIT << (8 * i);
+    if (classify_slow(g, (u32)(v0 + i), (u8)(w >> (8 * i)), report ? err : &dummy)) out |= (u64)VF_INIT << (8 * i);
   }
-  *(u64*)(vflags + v0) = out;
+  return out;
 }
-
-// K6: pieces = maximal runs of consecutive-id extender vertices linked by implicit edges; also the
-// per-thread counts of inits / piece starts / piece ends for the compaction below.
-// Flags are written for the tiles [f_lo, f_hi); the counts cover the tiles [t_lo, t_hi) inside them, nT = t_hi - t_lo (the
-// sliced multi-GPU tail also flags one tile on either side of its own range: the per-position passes of the slice read
-// the piece flags of vertices up to 7 ids beyond the 8-aligned cut).
-__global__ void k_piece_flags8(u8* vflags, u32 nV, u32* __restrict__ cnt3, u32 nT, u32 f_lo, u32 f_hi, u32 t_lo, u32 t_hi) {
-  u64 t = SPB_GTID() + f_lo;
-  u64 v0 = t * 8;
-  if (t >= f_hi || v0 >= nV) return;
-  u64 w = *(const u64*)(vflags + v0);
-  u64 pf = v0 ? vflags[v0 - 1] : 0;
-  u64 nf = v0 + 8 < nV ? vflags[v0 + 8] : 0;
-  u64 nvalid = nV - v0 < 8 ? nV - v0 : 8;
-  u64 vm = nvalid == 8 ? ~0ull : ((1ull << (8 * nvalid)) - 1);
-  u64 init = (w >> 3) & SPB_M8 & vm, r = w & SPB_M8 & vm;
-  u64 ext = ~init & SPB_M8 & vm;
-  u64 p_r = (r << 8) | (pf & 1), p_init = (init << 8) | ((pf >> 3) & 1);
-  u64 n_init = (init >> 8) | (((nf >> 3) & 1) << 56);
-  u64 start = ext & ~(p_r & ~p_init);                 // no extender predecessor through an implicit edge
-  u64 end = ext & ~(r & ~n_init);                     // no extender successor through an implicit edge
-  *(u64*)(vflags + v0) = w | (start << 5) | (end << 6);
+// Flags are written for the groups [f_lo, f_hi) of 32 vertices; the counts cover the groups [t_lo, t_hi) inside them,
+// nT = t_hi - t_lo (the sliced multi-GPU tail also flags one group on either side of its own range: the per-position passes
+// of the slice read the piece flags of vertices up to 31 ids beyond the 32-aligned cut).
+__global__ void k_classify_pieces(GView g, u8* vflags, u32* __restrict__ cnt3, u32 nT, u32 f_lo, u32 f_hi, u32 t_lo, u32 t_hi, u32* err) {
+  const u64 t = SPB_GTID() + f_lo;
+  const u64 v0 = t * 8 * SPB_CW;
+  if (t >= f_hi || v0 >= g.nV) return;
+  const u64 nVw = ((u64)g.nV + 7) / 8;               // flag words that hold vertices (the array is padded with zero bytes)
+  const u64 w0 = v0 >> 3;
+  // words w0 - 1 .. w0 + SPB_CW (neighbours included), classified from their stable bits
+  u64 c[SPB_CW + 2];
+#pragma unroll
+  for (int i = -1; i <= SPB_CW; ++i) {
+    const long long wi = (long long)w0 + i;
+    u64 out = 0;
+    if (wi >= 0 && (u64)wi < nVw) {
+      const u64 w = *(const u64*)(g.vflags + 8 * wi);
+      const u64 pb = wi ? g.vflags[8 * wi - 1] : 0;
+      out = classify_word(g, 8ull * wi, w, pb, err, i >= 0 && i < SPB_CW);
+    }
+    c[i + 1] = out;
+  }
+  u32 nI = 0, nS = 0, nE = 0;
+#pragma unroll
+  for (int i = 0; i < SPB_CW; ++i) {
+    const u64 wi = w0 + i;
+    if (wi >= nVw) break;
+    const u64 w = c[i + 1], pf = c[i] >> 56, nf = c[i + 2] & 0xFF;
+    const u64 vb = 8 * wi;
+    const u64 nvalid = g.nV - vb < 8 ? g.nV - vb : 8;
+    const u64 vm = nvalid == 8 ? ~0ull : ((1ull << (8 * nvalid)) - 1);
+    const u64 init = (w >> 3) & SPB_M8 & vm, r = w & SPB_M8 & vm;
+    const u64 ext = ~init & SPB_M8 & vm;
+    const u64 p_r = (r << 8) | (pf & 1), p_init = (init << 8) | ((pf >> 3) & 1);
+    const u64 n_init = (init >> 8) | (((nf >> 3) & 1) << 56);
+    const u64 start = ext & ~(p_r & ~p_init);           // no extender predecessor through an implicit edge
+    const u64 end = ext & ~(r & ~n_init);               // no extender successor through an implicit edge
+    *(u64*)(vflags + vb) = w | (start << 5) | (end << 6);
+    nI += (u32)__popcll(init); nS += (u32)__popcll(start); nE += (u32)__popcll(end);
+  }
   if (t < t_lo || t >= t_hi) return;
-  const u64 i = t - t_lo;
-  cnt3[i] = (u32)__popcll(init); cnt3[nT + i] = (u32)__popcll(start); cnt3[2 * (u64)nT + i] = (u32)__popcll(end);
+  const u64 i3 = t - t_lo;
+  cnt3[i3] = nI; cnt3[nT + i3] = nS; cnt3[2 * (u64)nT + i3] = nE;
 }
 __global__ void k_compact3(const u8* __restrict__ vflags, u32 nV, const u32* __restrict__ off3, u32 nT, u32 totI, u32 totS,
                            u32* __restrict__ init_list, u32* __restrict__ plo, u32* __restrict__ phi, u32 t_lo) {
-  u64 i3 = SPB_GTID();
-  u64 v0 = (i3 + t_lo) * 8;
+  const u64 i3 = SPB_GTID();
+  const u64 v0 = (i3 + t_lo) * 8 * SPB_CW;
   if (i3 >= nT || v0 >= nV) return;
-  u64 w = *(const u64*)(vflags + v0);
-  if (!(w & (SPB_M8 * (u64)(VF_INIT | VF_PSTART | VF_PEND)))) return;     // nothing to list in this tile (the usual case): no offsets needed
+  u64 w[SPB_CW]; u64 any = 0;
+#pragma unroll
+  for (u32 i = 0; i < SPB_CW; ++i) { w[i] = v0 + 8 * i < nV ? *(const u64*)(vflags + v0 + 8 * i) : 0ull; any |= w[i]; }
+  if (!(any & (SPB_M8 * (u64)(VF_INIT | VF_PSTART | VF_PEND)))) return;     // nothing to list in this group (the usual case): no offsets needed
   u32 oI = off3[i3], oS = off3[nT + i3] - totI, oE = off3[2 * (u64)nT + i3] - totI - totS;
-  for (u32 i = 0; i < 8 && v0 + i < nV; ++i) {
-    u32 f = (u32)(w >> (8 * i)) & 0xFF;
-    if (f & VF_INIT) init_list[oI++] = (u32)(v0 + i);
-    if (f & VF_PSTART) plo[oS++] = (u32)(v0 + i);
-    if (f & VF_PEND) phi[oE++] = (u32)(v0 + i);
+  for (u32 x = 0; x < 8 * SPB_CW && v0 + x < nV; ++x) {
+    const u32 f = (u32)(w[x >> 3] >> (8 * (x & 7))) & 0xFF;
+    if (f & VF_INIT) init_list[oI++] = (u32)(v0 + x);
+    if (f & VF_PSTART) plo[oS++] = (u32)(v0 + x);
+    if (f & VF_PEND) phi[oE++] = (u32)(v0 + x);
   }
 }
 
