@@ -1330,7 +1330,7 @@ __device__ __forceinline__ bool classify_slow(const GView& g, u32 v, u8 f, u32* 
   bool init = cnt != 2;
   if (!init && s0 == s1) {
     init = true;
-    if (!(f & VF_SEQLIM)) atomicOr(err, (u32)ERR_DEGENERATE);  // the reference would assert (lib/Assembler.py:1104)
+    if (!(f & VF_SEQLIM) && err) atomicOr(err, (u32)ERR_DEGENERATE);  // the reference would assert (lib/Assembler.py:1104)
   }
   return init;
 }
@@ -1350,7 +1350,6 @@ __device__ __forceinline__ u64 classify_word(const GView& g, u64 v0, u64 w, u64 
   const u64 init = ~(r & rprev) & SPB_M8 & ~hasj;    // no junction entries: init <=> not both implicit neighbours
   u64 out = (w & ~(SPB_M8 * (u64)(VF_INIT | VF_PSTART | VF_PEND | VF_IN2))) | ((init & vm) << 3);
   u64 slow = hasj & vm;
-  u32 dummy = 0;
   while (slow) {                                      // the few vertices with junction entries: general rule
 #ifdef SPB_EMU
     const u32 i = (u32)(__builtin_ctzll(slow) >> 3);
@@ -1358,7 +1357,7 @@ __device__ __forceinline__ u64 classify_word(const GView& g, u64 v0, u64 w, u64 
     const u32 i = (u32)((__ffsll((long long)slow) - 1) >> 3);
 #endif
     slow &= slow - 1;
-    if (classify_slow(g, (u32)(v0 + i), (u8)(w >> (8 * i)), report ? err : &dummy)) out |= (u64)VF_INIT << (8 * i);
+    if (classify_slow(g, (u32)(v0 + i), (u8)(w >> (8 * i)), report ? err : nullptr)) out |= (u64)VF_INIT << (8 * i);
   }
   return out;
 }

@@ -163,7 +163,6 @@ __device__ __forceinline__ void blk32_load(Blk32& b, const u32* __restrict__ F, 
 }
 __device__ __forceinline__ void roll_fast8(RollSt& s, const Blk32& b, const RollK& K, const u32* __restrict__ F, const u32* __restrict__ R, u64 T, u32 k,
                                            u64 pblk, const u32 q0, u64 (&h)[8], u32& ow) {
-  u32 ties = 0;                                      // positions whose first 16 bases equal those of the reverse complement: decided after the loop
 #pragma unroll
   for (u32 j = 0; j < 8; ++j) {
     const u32 q = q0 + j, w = q >> 4, q16 = q & 15;
@@ -176,24 +175,11 @@ __device__ __forceinline__ void roll_fast8(RollSt& s, const Blk32& b, const Roll
     s.f2 = s.f2 * K.B[1] + in + out * K.negBk[1];
     s.r1 = s.r1 * K.Binv[0] + (ci * K.Bk1[0] + co * K.negBinv[0]);
     s.r2 = s.r2 * K.Binv[1] + (ci * K.Bk1[1] + co * K.negBinv[1]);
-    const bool o = s.head > s.rct;                   // (a tie -- one position in ~65 000 -- is redone below: no branch in the loop)
-    ties |= (s.head == s.rct ? 1u : 0u) << j;
+    const bool o = (s.head != s.rct) ? (s.head > s.rct) : (win_cmp(F, pblk + q, R, T - (pblk + q) - k, k) >= 0);
     h[j] = roll_finish(o ? s.f1 : s.r1, o ? s.f2 : s.r2);
     ow |= (o ? 1u : 0u) << q;
   }
   s.fresh = true;                                    // the cached words of the generic path are stale now
-  while (ties) {                                     // full comparison of the two orientations, hash evaluated directly
-#ifdef SPB_EMU
-    const u32 j = (u32)__builtin_ctz(ties);
-#else
-    const u32 j = (u32)__ffs((int)ties) - 1;
-#endif
-    ties &= ties - 1;
-    RollSt t; t.have = false; t.fresh = false; t.f1 = t.f2 = t.r1 = t.r2 = t.head = t.rct = t.wb = t.wc = 0;
-    const RollRes r = roll_key_slow(t, F, R, T, k, K, pblk + q0 + j);
-    h[j] = r.h;
-    ow = (ow & ~(1u << (q0 + j))) | (r.o << (q0 + j));
-  }
 }
 
 // The hash bits are consumed from the top: own_bits (owner GPU) | l1bits (level-1 bucket) | 32 bits kept in the record
