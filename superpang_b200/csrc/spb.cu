@@ -951,14 +951,22 @@ static int dedup_part_links(spb_ctx* c) {
   tk = t_begin(c);
   u32 *seenpos, *dupbits; ALLOC(seenpos, u32, P + 8); ALLOC(dupbits, u32, P / 32 + 8);
   dev_memset(c, dupbits, 0, (P / 32 + 8) * 4);
+  // Optimistic links (default): records whose 49 known hash bits agree are linked without touching the genome and every link
+  // is verified afterwards in one streaming pass (SPB_D_EXACT=1: the inline, warp-cooperative verification instead).
+  const bool opt = !getenv("SPB_D_EXACT");
+  u32 hmask = 0xFFFFFFFFu;                             // tests clear stored hash bits to provoke collisions (both forms stay exact)
+  if (const char* e = getenv("SPB_D_HMASK")) hmask = (u32)strtoul(e, nullptr, 16);
   {
     const int tq_ = t_begin(c);
-    if (!(getenv("SPB_D_NBUF") && atoi(getenv("SPB_D_NBUF")) == 2))        // measured: three resident CTAs beat two persistent ones (2.6 vs 3.1 ms, config 3)
-      SPB_LAUNCH_PHASED_DSMEM((k_bucket_dedup<false, 1>), 3, NBF, SPB_D_T, SPB_D_SMEM_U64(1) * 8, c->stream, rec2, cap2, cursor2, (u32)NBF, l2, c->F, c->R, c->obits, T, c->k,
-                              seenpos, dupbits, c->errflag, (u64*)nullptr, (u64*)nullptr, 0ull);
+    if (opt)                                                                // optimistic links, verified below
+      SPB_LAUNCH_PHASED_DSMEM((k_bucket_dedup<false, 1, true>), 3, NBF, SPB_D_T, SPB_D_SMEM_U64(1) * 8, c->stream, rec2, cap2, cursor2, (u32)NBF, l2, c->F, c->R, c->obits, T, c->k,
+                              seenpos, dupbits, c->errflag, (u64*)nullptr, (u64*)nullptr, 0ull, hmask);
+    else if (!(getenv("SPB_D_NBUF") && atoi(getenv("SPB_D_NBUF")) == 2))   // measured: three resident CTAs beat two persistent ones (2.6 vs 3.1 ms, config 3)
+      SPB_LAUNCH_PHASED_DSMEM((k_bucket_dedup<false, 1, false>), 3, NBF, SPB_D_T, SPB_D_SMEM_U64(1) * 8, c->stream, rec2, cap2, cursor2, (u32)NBF, l2, c->F, c->R, c->obits, T, c->k,
+                              seenpos, dupbits, c->errflag, (u64*)nullptr, (u64*)nullptr, 0ull, hmask);
     else
-      SPB_LAUNCH_PHASED_DSMEM((k_bucket_dedup<false, 2>), 3, gridd, SPB_D_T, SPB_D_SMEM_U64(2) * 8, c->stream, rec2, cap2, cursor2, (u32)NBF, l2, c->F, c->R, c->obits, T, c->k,
-                              seenpos, dupbits, c->errflag, (u64*)nullptr, (u64*)nullptr, 0ull);
+      SPB_LAUNCH_PHASED_DSMEM((k_bucket_dedup<false, 2, false>), 3, gridd, SPB_D_T, SPB_D_SMEM_U64(2) * 8, c->stream, rec2, cap2, cursor2, (u32)NBF, l2, c->F, c->R, c->obits, T, c->k,
+                              seenpos, dupbits, c->errflag, (u64*)nullptr, (u64*)nullptr, 0ull, hmask);
     t_end(c, tq_, "k_bucket_dedup_ms");
   }
   dfree(c, rec2); dfree(c, cursors);
@@ -970,6 +978,39 @@ static int dedup_part_links(spb_ctx* c) {
     return 1;
   }
   c->cnt.table_slots = SPB_D_SLOTS;
+  if (opt) {
+    const u64 FCAP = 1u << 16;
+    const int tq_ = t_begin(c);
+    u32 *failbits, *flist; u64* nfail;
+    ALLOC(failbits, u32, P / 32 + 8); ALLOC(flist, u32, FCAP + 1); ALLOC(nfail, u64, 2);
+    dev_memset(c, failbits, 0, (P / 32 + 8) * 4); dev_memset(c, nfail, 0, 16);
+    const u64 nwd = P / 32;
+    SPB_LAUNCH(k_verify_links, gs_grid(P), TPB, c->stream, seenpos, dupbits, nwd, c->F, c->R, c->obits, T, c->k, 0, failbits, flist, nfail, FCAP);
+    u64 nf = dread(c, nfail);
+    for (int it = 0; nf && nf <= FCAP && it < 64; ++it) {          // links checked against a predecessor that failed: compare in full
+      SPB_LAUNCH(k_verify_links, gs_grid(P), TPB, c->stream, seenpos, dupbits, nwd, c->F, c->R, c->obits, T, c->k, 1, failbits, flist, nfail, FCAP);
+      const u64 n2 = dread(c, nfail);
+      if (n2 == nf) break;
+      nf = n2;
+      if (it == 63) nf = FCAP + 1;
+    }
+    t_end(c, tq_, "k_verify_links_ms");
+    stat_set(c, "failed_links", (double)nf);
+    if (nf > FCAP) {                                 // far more hash collisions than any real input produces: exact path instead
+      dfree(c, failbits); dfree(c, flist); dfree(c, nfail);
+      dev_memset(c, c->obits, 0, (P / 32 + 8) * 4);
+      dfree(c, seenpos); dfree(c, dupbits);
+      return 1;
+    }
+    if (nf) {
+      u32 *roots, *newt; ALLOC(roots, u32, nf + 1); ALLOC(newt, u32, nf + 1);
+      SPB_LAUNCH(k_repair_roots, nblk(nf, TPB), TPB, c->stream, flist, (u32)nf, seenpos, dupbits, roots);
+      SPB_LAUNCH(k_repair_find, nblk(nf, TPB), TPB, c->stream, flist, (u32)nf, roots, seenpos, dupbits, c->F, c->R, c->obits, T, c->k, newt);
+      SPB_LAUNCH(k_repair_apply, nblk(nf, TPB), TPB, c->stream, flist, (u32)nf, newt, seenpos, dupbits);
+      dfree(c, roots); dfree(c, newt);
+    }
+    dfree(c, failbits); dfree(c, flist); dfree(c, nfail);
+  }
   t_end(c, tk, "bucket_dedup_ms"); stat_set(c, "partition2", (double)NBF);
   u64 nb = P / 256, nw32 = P / 32;
   SPB_LAUNCH(k_first_bits, nblk(nb, TPB), TPB, c->stream, c->vbits, dupbits, c->fbits, nb);     // first = valid and not linked
@@ -1465,8 +1506,8 @@ int spb_mg_part_dedup(spb_ctx* c, const uint64_t* recs, const uint32_t* counts, 
   for (int attempt = 0; attempt < 2; ++attempt) {
     ALLOC(links, u64, lcap + 1);
     dev_memset(c, nlinks, 0, 16);
-    { const int tq_ = t_begin(c); SPB_LAUNCH_PHASED_DSMEM((k_bucket_dedup<true, 1>), 3, NBF, SPB_D_T, SPB_D_SMEM_U64(1) * 8, c->stream, rec2, cap2, cursor2, (u32)NBF, g.l2, c->F, c->R, c->obits, c->T, c->k,
-                            (u32*)nullptr, (u32*)nullptr, c->errflag, links, nlinks, lcap); t_end(c, tq_, "k_bucket_dedup_ms"); }
+    { const int tq_ = t_begin(c); SPB_LAUNCH_PHASED_DSMEM((k_bucket_dedup<true, 1, false>), 3, NBF, SPB_D_T, SPB_D_SMEM_U64(1) * 8, c->stream, rec2, cap2, cursor2, (u32)NBF, g.l2, c->F, c->R, c->obits, c->T, c->k,
+                            (u32*)nullptr, (u32*)nullptr, c->errflag, links, nlinks, lcap, 0xFFFFFFFFu); t_end(c, tq_, "k_bucket_dedup_ms"); }
     nl = dread(c, nlinks);
     if (nl <= lcap) break;
     dfree(c, links); lcap = nl;

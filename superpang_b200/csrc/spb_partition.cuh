@@ -497,15 +497,19 @@ dd_link(u32* tab, const u64* recs, u32 s, u32 v, u32 old, u64 p, u64 q, u32* __r
     atomicOr(dupbits + (from >> 5), 1u << (from & 31));
   }
 }
-template <bool LIST> __device__ __forceinline__ bool
+template <bool LIST, bool OPT> __device__ __forceinline__ bool
 dd_probe(u32* tab, const u64* recs, u32 s, u32 tag, u32 v, u64 rec, const u32* __restrict__ F, const u32* __restrict__ R, const u32* __restrict__ obits, u64 T, u32 k,
-         u32* __restrict__ seenpos, u32* dupbits, u64* __restrict__ links, u64* nlinks, u64 lcap) {
+         u32* __restrict__ seenpos, u32* dupbits, u64* __restrict__ links, u64* nlinks, u64 lcap, u32 hmask) {
   const u32 old = atomicCAS(&tab[s], SPB_D_EMPTY, v);
   if (old == SPB_D_EMPTY) return true;
   if ((old >> 13) != tag) return false;
   const u64 rq = recs[old & 0x1FFFu];
-  if ((rq >> 32) != (rec >> 32)) return false;         // all 32 stored hash bits agree: verify the 2k bits
+  if ((((u32)(rq >> 32) ^ (u32)(rec >> 32)) & hmask) != 0) return false;         // all stored hash bits agree: verify the 2k bits
   const u64 p = (u32)rec, q = (u32)rq;
+  if (OPT) {                                           // optimistic form: linked now, verified by k_verify_links afterwards
+    dd_link<LIST>(tab, recs, s, v, old, p, q, seenpos, dupbits, links, nlinks, lcap);
+    return true;
+  }
   const bool o = get_bit(obits, p), oq = get_bit(obits, q);   // canonical orientations, left by k_roll_partition
   if (win_cmp(o ? F : R, o ? p : T - p - k, oq ? F : R, oq ? q : T - q - k, k) != 0) return false;
   dd_link<LIST>(tab, recs, s, v, old, p, q, seenpos, dupbits, links, nlinks, lcap);
@@ -530,8 +534,8 @@ __device__ __forceinline__ bool warp_same_kmer(const u32* __restrict__ F, const 
 #endif
 // slot / tag / step of a record: of the 32 stored hash bits the level-2 partition consumed the first skip_bits (equal for
 // the whole bucket); the next 13 are the home slot, the rest the tag
-__device__ __forceinline__ void dd_hash(u64 rec, u32 skip_bits, u32 i, u32& s, u32& tag, u32& v, u32& step) {
-  const u32 h = (u32)(rec >> 32) << skip_bits;
+__device__ __forceinline__ void dd_hash(u64 rec, u32 skip_bits, u32 i, u32& s, u32& tag, u32& v, u32& step, u32 hmask) {
+  const u32 h = ((u32)(rec >> 32) & hmask) << skip_bits;
   s = h >> 19; tag = h & 0x7FFFFu; v = (tag << 13) | i;
   step = ((h >> 5) & (SPB_D_SLOTS - 1)) | 1u;          // double hashing: no clusters
 }
@@ -545,9 +549,14 @@ __device__ __forceinline__ void dd_hash(u64 rec, u32 skip_bits, u32 i, u32& s, u
 // NBUF = 2: persistent, two CTAs per SM (double-buffered records); NBUF = 1: one bucket per CTA, three CTAs per SM (the
 // copy of a bucket overlaps with the work of the two other resident CTAs only).
 #define SPB_D_SMEM_U64(NBUF) (SPB_D_SLOTS / 2 + (NBUF) * SPB_D_LIMIT + SPB_D_DEFER / 4 + 8)
-template <bool LIST, int NBUF> __global__ void SPB_LAUNCH_BOUNDS2(SPB_D_T, (NBUF == 1 ? 3 : 2))
+// OPT (in-place form, one GPU): a record whose stored hash bits (and bucket: 49 bits in all) equal those of the installed one
+// is linked WITHOUT looking at the genome; k_verify_links checks every link afterwards in one streaming pass (a link whose
+// predecessor position is linked to the neighbouring target costs one base compare) and k_repair_* re-homes the few
+// positions whose 49 bits collided with another k-mer.  hmask: stored hash bits in use (all; tests clear some to provoke
+// collisions).
+template <bool LIST, int NBUF, bool OPT> __global__ void SPB_LAUNCH_BOUNDS2(SPB_D_T, (NBUF == 1 ? 3 : 2))
 k_bucket_dedup(const u64* __restrict__ recs_g, u64 cap, const u32* __restrict__ cnt, u32 n_buckets, u32 skip_bits, const u32* __restrict__ F, const u32* __restrict__ R,
-               const u32* __restrict__ obits, u64 T, u32 k, u32* __restrict__ seenpos, u32* dupbits, u32* err, u64* __restrict__ links, u64* nlinks, u64 lcap) {
+               const u32* __restrict__ obits, u64 T, u32 k, u32* __restrict__ seenpos, u32* dupbits, u32* err, u64* __restrict__ links, u64* nlinks, u64 lcap, u32 hmask) {
   SPB_DYN_SHARED(u64, dsm, SPB_D_SMEM_U64(2));
   u32* tab = (u32*)dsm;
   u64* recs0 = dsm + SPB_D_SLOTS / 2;
@@ -569,12 +578,12 @@ k_bucket_dedup(const u64* __restrict__ recs_g, u64 cap, const u32* __restrict__ 
     for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
       const u64 rec = recs[i];
       u32 s, tag, v, step;
-      dd_hash(rec, skip_bits, i, s, tag, v, step);
+      dd_hash(rec, skip_bits, i, s, tag, v, step, hmask);
       if (atomicCAS(&tab[s], SPB_D_EMPTY, v) != SPB_D_EMPTY) {
         const u32 d = atomicAdd(ndefer, 1u);
         if (d < SPB_D_DEFER) defer[d] = (unsigned short)i;
         else for (;;) {                                // list full (a bucket of repeats): finish this record here
-          if (dd_probe<LIST>(tab, recs, s, tag, v, rec, F, R, obits, T, k, seenpos, dupbits, links, nlinks, lcap)) break;
+          if (dd_probe<LIST, OPT>(tab, recs, s, tag, v, rec, F, R, obits, T, k, seenpos, dupbits, links, nlinks, lcap, hmask)) break;
           s = (s + step) & (SPB_D_SLOTS - 1);
         }
       }
@@ -586,8 +595,8 @@ k_bucket_dedup(const u64* __restrict__ recs_g, u64 cap, const u32* __restrict__ 
       const u32 i = defer[d];
       const u64 rec = recs[i];
       u32 s, tag, v, step;
-      dd_hash(rec, skip_bits, i, s, tag, v, step);
-      while (!dd_probe<LIST>(tab, recs, s, tag, v, rec, F, R, obits, T, k, seenpos, dupbits, links, nlinks, lcap)) s = (s + step) & (SPB_D_SLOTS - 1);
+      dd_hash(rec, skip_bits, i, s, tag, v, step, hmask);
+      while (!dd_probe<LIST, OPT>(tab, recs, s, tag, v, rec, F, R, obits, T, k, seenpos, dupbits, links, nlinks, lcap, hmask)) s = (s + step) & (SPB_D_SLOTS - 1);
     }
   SPB_PHASE_END
   (void)n_buckets;
@@ -643,7 +652,7 @@ k_bucket_dedup(const u64* __restrict__ recs_g, u64 cap, const u32* __restrict__ 
         bool fail = false;
         if (i < n) {
           rec = recs[i];
-          dd_hash(rec, skip_bits, i, s, tag, v, step);
+          dd_hash(rec, skip_bits, i, s, tag, v, step, hmask);
           fail = atomicCAS(&tab[s], SPB_D_EMPTY, v) != SPB_D_EMPTY;
         }
         const u32 bal = __ballot_sync(0xffffffffu, fail);          // one list reservation per warp
@@ -655,7 +664,7 @@ k_bucket_dedup(const u64* __restrict__ recs_g, u64 cap, const u32* __restrict__ 
             const u32 d = d0 + __popc(bal & ((1u << lane) - 1u));
             if (d < SPB_D_DEFER) defer[d] = (unsigned short)i;
             else for (;;) {                            // list full (a bucket of repeats): finish this record here
-              if (dd_probe<LIST>(tab, recs, s, tag, v, rec, F, R, obits, T, k, seenpos, dupbits, links, nlinks, lcap)) break;
+              if (dd_probe<LIST, OPT>(tab, recs, s, tag, v, rec, F, R, obits, T, k, seenpos, dupbits, links, nlinks, lcap, hmask)) break;
               s = (s + step) & (SPB_D_SLOTS - 1);
             }
           }
@@ -672,7 +681,7 @@ k_bucket_dedup(const u64* __restrict__ recs_g, u64 cap, const u32* __restrict__ 
         if (!active && d < nd) {
           const u32 i = defer[d];
           rec = recs[i];
-          dd_hash(rec, skip_bits, i, s, tag, v, step);
+          dd_hash(rec, skip_bits, i, s, tag, v, step, hmask);
           d += SPB_D_T;
           active = true;
         }
@@ -681,11 +690,14 @@ k_bucket_dedup(const u64* __restrict__ recs_g, u64 cap, const u32* __restrict__ 
           old = atomicCAS(&tab[s], SPB_D_EMPTY, v);
           if (old == SPB_D_EMPTY) active = false;
           else {
-            if ((old >> 13) == tag) { rq = recs[old & 0x1FFFu]; cand = (rq >> 32) == (rec >> 32); }
+            if ((old >> 13) == tag) { rq = recs[old & 0x1FFFu]; cand = (((u32)(rq >> 32) ^ (u32)(rec >> 32)) & hmask) == 0; }
             if (!cand) s = (s + step) & (SPB_D_SLOTS - 1);
           }
         }
-        u32 cm = __ballot_sync(0xffffffffu, cand);
+        if (OPT) {                                   // optimistic: every candidate is linked at once, no genome access
+          if (cand) { dd_link<LIST>(tab, recs, s, v, old, (u32)rec, (u32)rq, seenpos, dupbits, links, nlinks, lcap); active = false; }
+        }
+        u32 cm = OPT ? 0u : __ballot_sync(0xffffffffu, cand);
         while (cm) {
           const u32 l = __ffs(cm) - 1; cm &= cm - 1;
           const u64 pp = __shfl_sync(0xffffffffu, (u32)rec, l), qq = __shfl_sync(0xffffffffu, (u32)rq, l);
@@ -701,4 +713,84 @@ k_bucket_dedup(const u64* __restrict__ recs_g, u64 cap, const u32* __restrict__ 
     __syncthreads();                                 // end of the iteration: table, list and this buffer may be reused
   }
 #endif
+}
+
+
+// ------------------------------------------------------------------------------------ optimistic links: verification + repair
+// canonical k-mers at p and q equal?  (exact: 2k bits of the packed genome, orientation bits from k_roll_partition)
+__device__ __forceinline__ bool kmer_equal(const u32* __restrict__ F, const u32* __restrict__ R, const u32* __restrict__ obits, u64 T, u32 k, u64 p, u64 q) {
+  const bool o = get_bit(obits, p), oq = get_bit(obits, q);
+  return win_cmp(o ? F : R, o ? p : T - p - k, oq ? F : R, oq ? q : T - q - k, k) == 0;
+}
+// Can the link p -> q be checked against the link of p - 1?  Yes if p - 1 is linked to the position next to q on the matching
+// side with the same strand relation: the two k-mers then overlap their (verified) predecessors in k - 1 bases and only the
+// new base has to agree -- exact by induction along the run, whose first link is always compared in full.
+__device__ __forceinline__ bool link_extends(const u32* __restrict__ seenpos, const u32* __restrict__ dupbits, const u32* __restrict__ obits, u64 p, u64 q, bool* same_out) {
+  const bool same = get_bit(obits, p) == get_bit(obits, q);
+  *same_out = same;
+  if (p == 0 || !get_bit(dupbits, p - 1)) return false;
+  const u64 q1 = seenpos[p - 1];
+  if ((get_bit(obits, p - 1) == get_bit(obits, q1)) != same) return false;
+  return same ? (q1 + 1 == q) : (q1 == q + 1);
+}
+// mode 0: every linked position; a failed link is flagged (failbits) and listed.  mode 1: links that were checked against a
+// predecessor which turned out to be wrong are compared in full (run until the list stops growing).
+__global__ void k_verify_links(const u32* __restrict__ seenpos, const u32* __restrict__ dupbits, u64 nwords, const u32* __restrict__ F, const u32* __restrict__ R,
+                               const u32* __restrict__ obits, u64 T, u32 k, int mode, u32* failbits, u32* __restrict__ flist, u64* nfail, u64 fcap) {
+  const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+  const u32 lane = threadIdx.x & 31;
+  for (u64 wd = SPB_GTID() >> 5; wd < nwords; wd += nwarps) {
+    const u32 d = __ldg(dupbits + wd);
+    if (!((d >> lane) & 1u)) continue;
+    const u64 p = wd * 32 + lane, q = seenpos[p];
+    bool same;
+    const bool ext = link_extends(seenpos, dupbits, obits, p, q, &same);
+    bool ok;
+    if (mode == 0) {
+      if (ext) ok = same ? base_at(F, p + k - 1) == base_at(F, q + k - 1) : base_at(F, p + k - 1) == (3u - base_at(F, q));
+      else ok = kmer_equal(F, R, obits, T, k, p, q);
+    } else {
+      if (!ext || !get_bit(failbits, p - 1) || get_bit(failbits, p)) continue;
+      ok = kmer_equal(F, R, obits, T, k, p, q);
+    }
+    if (!ok) {
+      atomicOr(failbits + wd, 1u << lane);
+      const u64 i = atomicAdd(nfail, 1ull);
+      if (i < fcap) flist[i] = (u32)p;
+    }
+  }
+}
+// Repair of the failed links (a handful per 10^9 records: distinct k-mers whose 49 hash bits agree).  The records of one
+// hash class were all linked towards the class' slot holders (always the smallest position seen so far), so the true first
+// position of a failed one is either a holder further down its target's chain or another failed position of the class.
+__global__ void k_repair_roots(const u32* __restrict__ flist, u32 nf, const u32* __restrict__ seenpos, const u32* __restrict__ dupbits, u32* __restrict__ roots) {
+  const u64 i = SPB_GTID();
+  if (i >= nf) return;
+  u32 x = seenpos[flist[i]];
+  while (get_bit(dupbits, x)) x = seenpos[x];
+  roots[i] = x;
+}
+__global__ void k_repair_find(const u32* __restrict__ flist, u32 nf, const u32* __restrict__ roots, const u32* __restrict__ seenpos, const u32* __restrict__ dupbits,
+                              const u32* __restrict__ F, const u32* __restrict__ R, const u32* __restrict__ obits, u64 T, u32 k, u32* __restrict__ newt) {
+  const u64 i = SPB_GTID();
+  if (i >= nf) return;
+  const u32 p = flist[i];
+  u32 best = p;
+  for (u32 x = seenpos[p];; x = seenpos[x]) {          // holders from the target down to the root: positions descend
+    if (x < best && kmer_equal(F, R, obits, T, k, p, x)) best = x;
+    if (!get_bit(dupbits, x)) break;
+  }
+  for (u32 j = 0; j < nf; ++j)
+    if (roots[j] == roots[i] && flist[j] < best && kmer_equal(F, R, obits, T, k, p, flist[j])) best = flist[j];
+  newt[i] = best;
+}
+__global__ void k_repair_apply(const u32* __restrict__ flist, u32 nf, const u32* __restrict__ newt, u32* __restrict__ seenpos, u32* dupbits) {
+  const u64 i = SPB_GTID();
+  if (i >= nf) return;
+  const u32 p = flist[i];
+  if (newt[i] != p) { seenpos[p] = newt[i]; return; }
+  u32* wp = dupbits + (p >> 5);                        // its own k-mer's first position: no link
+  const u32 bit = 1u << (p & 31);
+  u32 old = *wp;
+  while (true) { const u32 prev = atomicCAS(wp, old, old & ~bit); if (prev == old) break; old = prev; }
 }

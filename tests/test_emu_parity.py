@@ -141,6 +141,15 @@ VARIANTS = [
     {"SPB_DEDUP": "part", "SPB_PART_AVG": "40", "SPB_EMU_ORDER": "shuffle"},
     {"SPB_DEDUP": "part", "SPB_PART_AVG": "40", "SPB_PART_L1": "0"},              # level 2 only
     {"SPB_DEDUP": "part", "SPB_PART_AVG": "2"},                      # buckets overflow their regions -> sort-based path instead
+    {"SPB_DEDUP": "part", "SPB_D_EXACT": "1", "SPB_PART_AVG": "300"},                 # inline exact verification instead of optimistic links
+    # optimistic links with stored hash bits masked away: distinct k-mers collide, their links fail the verification pass and
+    # are re-homed by the repair kernels (normally a handful per 10^9 records)
+    {"SPB_DEDUP": "part", "SPB_D_HMASK": "FFF00000", "SPB_PART_AVG": "300"},
+    {"SPB_DEDUP": "part", "SPB_D_HMASK": "FFF00000", "SPB_PART_AVG": "300", "SPB_EMU_ORDER": "reverse"},   # take-over chains through wrong links
+    {"SPB_DEDUP": "part", "SPB_D_HMASK": "FFC00000", "SPB_PART_AVG": "100", "SPB_EMU_ORDER": "shuffle"},
+    {"SPB_DEDUP": "part", "SPB_D_HMASK": "F0000000", "SPB_PART_AVG": "300"},          # more failures than the repair list holds -> exact path
+    {"SPB_DEDUP": "part", "SPB_D_HMASK": "0", "SPB_PART_AVG": "40"},                  # every record of a bucket collides
+    {"SPB_DEDUP": "part", "SPB_D_HMASK": "80000000", "SPB_D_EXACT": "1", "SPB_PART_AVG": "100"},
     {"SPB_SWITCH_MIN": "1", "SPB_CHUNK_BITS": "8", "SPB_PART_AVG": "100", "SPB_EMU_ORDER": "reverse"},   # adaptive default reaching the partition
 ]
 

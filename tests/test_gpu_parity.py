@@ -144,7 +144,9 @@ def test_gpu_properties_at_scale(mode):
     {"SPB_DEDUP": "part"},                             # hand-written two-level partition + bulk-copied buckets
     {"SPB_DEDUP": "part", "SPB_PART_AVG": "50"},       # ... many small buckets, both levels
     {"SPB_DEDUP": "part", "SPB_PART_AVG": "200", "SPB_P1_SHAPE": "1", "SPB_P1_COPIES": "4", "SPB_SWITCH_MIN": "1"},   # ... the other CTA shapes of the fused kernel, region copies
-    {"SPB_DEDUP": "part", "SPB_PART_AVG": "200", "SPB_P1_SHAPE": "2", "SPB_D_NBUF": "2"},          # ... persistent double-buffered dedup kernel
+    {"SPB_DEDUP": "part", "SPB_PART_AVG": "200", "SPB_P1_SHAPE": "2", "SPB_D_NBUF": "2", "SPB_D_EXACT": "1"},          # ... persistent double-buffered dedup kernel (inline verification)
+    {"SPB_DEDUP": "part", "SPB_PART_AVG": "200", "SPB_D_EXACT": "1"},                            # ... inline warp-cooperative verification instead of optimistic links
+    {"SPB_DEDUP": "part", "SPB_PART_AVG": "200", "SPB_D_HMASK": "FFF00000"},                     # ... optimistic links with provoked hash collisions: verification pass + repair kernels
 ], ids=lambda e: ",".join(f"{k[4:].lower()}={v}" for k, v in e.items()))
 def test_gpu_dedup_variants(monkeypatch, env):
     """Every dedup strategy must give the reference's result (they differ only in how the table is reached)."""
