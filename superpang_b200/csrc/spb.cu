@@ -979,20 +979,17 @@ static int dedup_part_links(spb_ctx* c) {
   }
   c->cnt.table_slots = SPB_D_SLOTS;
   if (opt) {
-    const u64 FCAP = 1u << 16;
+    const u64 FCAP = 1u << 20;
     const int tq_ = t_begin(c);
     u32 *failbits, *flist; u64* nfail;
     ALLOC(failbits, u32, P / 32 + 8); ALLOC(flist, u32, FCAP + 1); ALLOC(nfail, u64, 2);
     dev_memset(c, failbits, 0, (P / 32 + 8) * 4); dev_memset(c, nfail, 0, 16);
     const u64 nwd = P / 32;
-    SPB_LAUNCH(k_verify_links, gs_grid(P), TPB, c->stream, seenpos, dupbits, nwd, c->F, c->R, c->obits, T, c->k, 0, failbits, flist, nfail, FCAP);
+    SPB_LAUNCH(k_verify_links, std::min<u64>(nblk(nwd, TPB), 148 * 16), TPB, c->stream, seenpos, dupbits, nwd, c->F, c->R, c->obits, T, c->k, failbits, flist, nfail, FCAP);
     u64 nf = dread(c, nfail);
-    for (int it = 0; nf && nf <= FCAP && it < 64; ++it) {          // links checked against a predecessor that failed: compare in full
-      SPB_LAUNCH(k_verify_links, gs_grid(P), TPB, c->stream, seenpos, dupbits, nwd, c->F, c->R, c->obits, T, c->k, 1, failbits, flist, nfail, FCAP);
-      const u64 n2 = dread(c, nfail);
-      if (n2 == nf) break;
-      nf = n2;
-      if (it == 63) nf = FCAP + 1;
+    if (nf && nf <= FCAP) {                            // links that leaned on a failed predecessor: compared in full
+      SPB_LAUNCH(k_verify_followups, nblk(nf, TPB), TPB, c->stream, (u32)nf, seenpos, dupbits, c->F, c->R, c->obits, T, c->k, failbits, flist, nfail, FCAP);
+      nf = dread(c, nfail);
     }
     t_end(c, tq_, "k_verify_links_ms");
     stat_set(c, "failed_links", (double)nf);
@@ -1003,11 +1000,12 @@ static int dedup_part_links(spb_ctx* c) {
       return 1;
     }
     if (nf) {
-      u32 *roots, *newt; ALLOC(roots, u32, nf + 1); ALLOC(newt, u32, nf + 1);
-      SPB_LAUNCH(k_repair_roots, nblk(nf, TPB), TPB, c->stream, flist, (u32)nf, seenpos, dupbits, roots);
-      SPB_LAUNCH(k_repair_find, nblk(nf, TPB), TPB, c->stream, flist, (u32)nf, roots, seenpos, dupbits, c->F, c->R, c->obits, T, c->k, newt);
-      SPB_LAUNCH(k_repair_apply, nblk(nf, TPB), TPB, c->stream, flist, (u32)nf, newt, seenpos, dupbits);
-      dfree(c, roots); dfree(c, newt);
+      u64 *keys, *keys2; u32* newt; ALLOC(keys, u64, nf + 1); ALLOC(keys2, u64, nf + 1); ALLOC(newt, u32, nf + 1);
+      SPB_LAUNCH(k_repair_roots, nblk(nf, TPB), TPB, c->stream, flist, (u32)nf, seenpos, dupbits, keys);
+      PRIM(prim_sort_u64(c, keys, keys2, nf));
+      SPB_LAUNCH(k_repair_find, nblk(nf, TPB), TPB, c->stream, keys, (u32)nf, seenpos, dupbits, c->F, c->R, c->obits, T, c->k, newt);
+      SPB_LAUNCH(k_repair_apply, nblk(nf, TPB), TPB, c->stream, keys, (u32)nf, newt, seenpos, dupbits);
+      dfree(c, keys); dfree(c, keys2); dfree(c, newt);
     }
     dfree(c, failbits); dfree(c, flist); dfree(c, nfail);
   }

@@ -733,61 +733,94 @@ __device__ __forceinline__ bool link_extends(const u32* __restrict__ seenpos, co
   if ((get_bit(obits, p - 1) == get_bit(obits, q1)) != same) return false;
   return same ? (q1 + 1 == q) : (q1 == q + 1);
 }
-// mode 0: every linked position; a failed link is flagged (failbits) and listed.  mode 1: links that were checked against a
-// predecessor which turned out to be wrong are compared in full (run until the list stops growing).
+// one linked position: check against the predecessor's link where possible, in full otherwise; a failed link is flagged
+// (failbits) and listed
+__device__ __forceinline__ void verify_one(u64 p, const u32* __restrict__ seenpos, const u32* __restrict__ dupbits, const u32* __restrict__ F, const u32* __restrict__ R,
+                                           const u32* __restrict__ obits, u64 T, u32 k, u32* failbits, u32* __restrict__ flist, u64* nfail, u64 fcap) {
+  const u64 q = seenpos[p];
+  bool same;
+  const bool ext = link_extends(seenpos, dupbits, obits, p, q, &same);
+  bool ok;
+  if (ext) ok = same ? base_at(F, p + k - 1) == base_at(F, q + k - 1) : base_at(F, p + k - 1) == (3u - base_at(F, q));
+  else ok = kmer_equal(F, R, obits, T, k, p, q);
+  if (!ok) {
+    atomicOr(failbits + (p >> 5), 1u << (p & 31));
+    const u64 i = atomicAdd(nfail, 1ull);
+    if (i < fcap) flist[i] = (u32)p;
+  }
+}
+// every linked position (the bitmap of linked positions is sparse on mostly-unique inputs: 32 words per warp iteration, only
+// the non-zero ones are looked at)
 __global__ void k_verify_links(const u32* __restrict__ seenpos, const u32* __restrict__ dupbits, u64 nwords, const u32* __restrict__ F, const u32* __restrict__ R,
-                               const u32* __restrict__ obits, u64 T, u32 k, int mode, u32* failbits, u32* __restrict__ flist, u64* nfail, u64 fcap) {
+                               const u32* __restrict__ obits, u64 T, u32 k, u32* failbits, u32* __restrict__ flist, u64* nfail, u64 fcap) {
   const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
   const u32 lane = threadIdx.x & 31;
-  for (u64 wd = SPB_GTID() >> 5; wd < nwords; wd += nwarps) {
-    const u32 d = __ldg(dupbits + wd);
-    if (!((d >> lane) & 1u)) continue;
-    const u64 p = wd * 32 + lane, q = seenpos[p];
+#ifdef SPB_EMU
+  for (u64 wd = SPB_GTID() >> 5; wd < nwords; wd += nwarps)
+    if ((dupbits[wd] >> lane) & 1u) verify_one(wd * 32 + lane, seenpos, dupbits, F, R, obits, T, k, failbits, flist, nfail, fcap);
+#else
+  for (u64 wb = (SPB_GTID() >> 5) * 32; wb < nwords; wb += nwarps * 32) {
+    const u32 d = wb + lane < nwords ? __ldg(dupbits + wb + lane) : 0u;
+    u32 nz = __ballot_sync(0xffffffffu, d != 0);
+    while (nz) {
+      const u32 j = (u32)__ffs((int)nz) - 1;
+      nz &= nz - 1;
+      const u32 dj = __shfl_sync(0xffffffffu, d, j);
+      if ((dj >> lane) & 1u) verify_one((wb + j) * 32 + lane, seenpos, dupbits, F, R, obits, T, k, failbits, flist, nfail, fcap);
+    }
+  }
+#endif
+}
+// A link that was checked against its predecessor's link is only as good as that one: from every failed position walk on
+// while the next position leaned on the one before it, comparing in full; the first that holds on its own ends the walk.
+// One thread per failure of the first pass (new failures are appended and handled by the thread that finds them).
+__global__ void k_verify_followups(u32 nf0, const u32* __restrict__ seenpos, const u32* __restrict__ dupbits, const u32* __restrict__ F, const u32* __restrict__ R,
+                                   const u32* __restrict__ obits, u64 T, u32 k, u32* failbits, u32* flist, u64* nfail, u64 fcap) {
+  const u64 i = SPB_GTID();
+  if (i >= nf0) return;
+  for (u64 t = (u64)flist[i] + 1;; ++t) {
+    if (!get_bit(dupbits, t)) break;
+    const u64 q = seenpos[t];
     bool same;
-    const bool ext = link_extends(seenpos, dupbits, obits, p, q, &same);
-    bool ok;
-    if (mode == 0) {
-      if (ext) ok = same ? base_at(F, p + k - 1) == base_at(F, q + k - 1) : base_at(F, p + k - 1) == (3u - base_at(F, q));
-      else ok = kmer_equal(F, R, obits, T, k, p, q);
-    } else {
-      if (!ext || !get_bit(failbits, p - 1) || get_bit(failbits, p)) continue;
-      ok = kmer_equal(F, R, obits, T, k, p, q);
-    }
-    if (!ok) {
-      atomicOr(failbits + wd, 1u << lane);
-      const u64 i = atomicAdd(nfail, 1ull);
-      if (i < fcap) flist[i] = (u32)p;
-    }
+    if (!link_extends(seenpos, dupbits, obits, t, q, &same)) break;        // compared in full already
+    if (get_bit(failbits, t)) break;                                        // somebody else's walk starts here
+    if (kmer_equal(F, R, obits, T, k, t, q)) break;
+    atomicOr(failbits + (t >> 5), 1u << (t & 31));
+    const u64 j = atomicAdd(nfail, 1ull);
+    if (j < fcap) flist[j] = (u32)t;
   }
 }
 // Repair of the failed links (a handful per 10^9 records: distinct k-mers whose 49 hash bits agree).  The records of one
 // hash class were all linked towards the class' slot holders (always the smallest position seen so far), so the true first
 // position of a failed one is either a holder further down its target's chain or another failed position of the class.
-__global__ void k_repair_roots(const u32* __restrict__ flist, u32 nf, const u32* __restrict__ seenpos, const u32* __restrict__ dupbits, u32* __restrict__ roots) {
-  const u64 i = SPB_GTID();
-  if (i >= nf) return;
-  u32 x = seenpos[flist[i]];
-  while (get_bit(dupbits, x)) x = seenpos[x];
-  roots[i] = x;
-}
-__global__ void k_repair_find(const u32* __restrict__ flist, u32 nf, const u32* __restrict__ roots, const u32* __restrict__ seenpos, const u32* __restrict__ dupbits,
-                              const u32* __restrict__ F, const u32* __restrict__ R, const u32* __restrict__ obits, u64 T, u32 k, u32* __restrict__ newt) {
+__global__ void k_repair_roots(const u32* __restrict__ flist, u32 nf, const u32* __restrict__ seenpos, const u32* __restrict__ dupbits, u64* __restrict__ keys) {
   const u64 i = SPB_GTID();
   if (i >= nf) return;
   const u32 p = flist[i];
+  u32 x = seenpos[p];
+  while (get_bit(dupbits, x)) x = seenpos[x];
+  keys[i] = ((u64)x << 32) | p;                        // (root of the hash class, position): sorted by the caller
+}
+__global__ void k_repair_find(const u64* __restrict__ keys, u32 nf, const u32* __restrict__ seenpos, const u32* __restrict__ dupbits,
+                              const u32* __restrict__ F, const u32* __restrict__ R, const u32* __restrict__ obits, u64 T, u32 k, u32* __restrict__ newt) {
+  const u64 i = SPB_GTID();
+  if (i >= nf) return;
+  const u32 p = (u32)keys[i], root = (u32)(keys[i] >> 32);
   u32 best = p;
   for (u32 x = seenpos[p];; x = seenpos[x]) {          // holders from the target down to the root: positions descend
     if (x < best && kmer_equal(F, R, obits, T, k, p, x)) best = x;
     if (!get_bit(dupbits, x)) break;
   }
-  for (u32 j = 0; j < nf; ++j)
-    if (roots[j] == roots[i] && flist[j] < best && kmer_equal(F, R, obits, T, k, p, flist[j])) best = flist[j];
+  for (u64 j = i; j-- > 0 && (u32)(keys[j] >> 32) == root;) {             // the failed positions of the same class below p (sorted)
+    const u32 f = (u32)keys[j];
+    if (f < best && kmer_equal(F, R, obits, T, k, p, f)) best = f;
+  }
   newt[i] = best;
 }
-__global__ void k_repair_apply(const u32* __restrict__ flist, u32 nf, const u32* __restrict__ newt, u32* __restrict__ seenpos, u32* dupbits) {
+__global__ void k_repair_apply(const u64* __restrict__ keys, u32 nf, const u32* __restrict__ newt, u32* __restrict__ seenpos, u32* dupbits) {
   const u64 i = SPB_GTID();
   if (i >= nf) return;
-  const u32 p = flist[i];
+  const u32 p = (u32)keys[i];
   if (newt[i] != p) { seenpos[p] = newt[i]; return; }
   u32* wp = dupbits + (p >> 5);                        // its own k-mer's first position: no link
   const u32 bit = 1u << (p & 31);
