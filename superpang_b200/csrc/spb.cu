@@ -951,7 +951,7 @@ static int dedup_part_links(spb_ctx* c) {
   tk = t_begin(c);
   u32 *seenpos, *dupbits; ALLOC(seenpos, u32, P + 8); ALLOC(dupbits, u32, P / 32 + 8);
   dev_memset(c, dupbits, 0, (P / 32 + 8) * 4);
-  // Optimistic links (default): records whose 49 known hash bits agree are linked without touching the genome and every link
+  // Optimistic links (default): records whose known hash bits (bucket + 32 stored) agree are linked without touching the genome and every link
   // is verified afterwards in one streaming pass (SPB_D_EXACT=1: the inline, warp-cooperative verification instead).
   const bool opt = !getenv("SPB_D_EXACT");
   u32 hmask = 0xFFFFFFFFu;                             // tests clear stored hash bits to provoke collisions (both forms stay exact)

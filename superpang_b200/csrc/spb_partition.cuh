@@ -549,10 +549,10 @@ __device__ __forceinline__ void dd_hash(u64 rec, u32 skip_bits, u32 i, u32& s, u
 // NBUF = 2: persistent, two CTAs per SM (double-buffered records); NBUF = 1: one bucket per CTA, three CTAs per SM (the
 // copy of a bucket overlaps with the work of the two other resident CTAs only).
 #define SPB_D_SMEM_U64(NBUF) (SPB_D_SLOTS / 2 + (NBUF) * SPB_D_LIMIT + SPB_D_DEFER / 4 + 8)
-// OPT (in-place form, one GPU): a record whose stored hash bits (and bucket: 49 bits in all) equal those of the installed one
+// OPT (in-place form, one GPU): a record whose stored hash bits (and bucket: 9 + 32 = 41 bits at config 3) equal those of the installed one
 // is linked WITHOUT looking at the genome; k_verify_links checks every link afterwards in one streaming pass (a link whose
 // predecessor position is linked to the neighbouring target costs one base compare) and k_repair_* re-homes the few
-// positions whose 49 bits collided with another k-mer.  hmask: stored hash bits in use (all; tests clear some to provoke
+// positions whose known bits collided with another k-mer (5.7e4 of 5e8 records at config 3).  hmask: stored hash bits in use (all; tests clear some to provoke
 // collisions).
 template <bool LIST, int NBUF, bool OPT> __global__ void SPB_LAUNCH_BOUNDS2(SPB_D_T, (NBUF == 1 ? 3 : 2))
 k_bucket_dedup(const u64* __restrict__ recs_g, u64 cap, const u32* __restrict__ cnt, u32 n_buckets, u32 skip_bits, const u32* __restrict__ F, const u32* __restrict__ R,
@@ -790,7 +790,7 @@ __global__ void k_verify_followups(u32 nf0, const u32* __restrict__ seenpos, con
     if (j < fcap) flist[j] = (u32)t;
   }
 }
-// Repair of the failed links (a handful per 10^9 records: distinct k-mers whose 49 hash bits agree).  The records of one
+// Repair of the failed links (distinct k-mers whose known hash bits agree: 5.7e4 of 5e8 records at config 3).  The records of one
 // hash class were all linked towards the class' slot holders (always the smallest position seen so far), so the true first
 // position of a failed one is either a holder further down its target's chain or another failed position of the class.
 __global__ void k_repair_roots(const u32* __restrict__ flist, u32 nf, const u32* __restrict__ seenpos, const u32* __restrict__ dupbits, u64* __restrict__ keys) {
