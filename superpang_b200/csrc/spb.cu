@@ -1735,7 +1735,7 @@ static int cp_emit(spb_ctx* c, u64 totv, u64 tots) {
   SPB_LAUNCH(k_emit_short, std::min<u64>(nblk((u64)nD * 32, 256), 148 * 32), 256, c->stream, nD, c->plo, c->phi, c->dart_nbp, c->rk_acc[cur], k, T,
              c->F, c->R, vp, c->voff, c->soff, verts, seqs, vnbp_w, n_lo, n_hi);
   dfree(c, nch); dfree(c, choff);
-  if (sl.on) {                                         // vertex -> NBP map of the own tiles (+ one tile: see k_piece_flags8)
+  if (sl.on) {                                         // vertex -> NBP map of the own tiles (+ one group of 32: see k_classify_pieces)
     ALLOC(c->vnbp, u32, (u64)nV + 1);                  // addressed by the global vertex id; only [v_lo, v_hi) of it is touched
     const VNbp vn = vnbp_view(c);
     SPB_LAUNCH(k_fill_vnbp, nblk(nblk(vn.v_hi - vn.v_lo, 1024) * 32, TPB), TPB, c->stream, c->plo, c->phi, nP, c->dart_nbp, vn.v_lo, vn.v_hi, c->vnbp);
