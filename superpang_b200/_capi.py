@@ -596,7 +596,6 @@ class Engine:
         jk_t = _wrap(jk.value, n.value, torch.int64, cuda, self.device)
         js_t = _wrap(js.value, n.value, torch.uint8, cuda, self.device)
         jk_all, js_all = _gather_var([jk_t, js_t], [[c_[0], c_[0]] for c_ in ca], r, G, group)
-        sync()
         ne = C.c_uint64()
         self._ck(L.spb_mg_slice_graph(h, jk_all.data_ptr() if jk_all.numel() else None, js_all.data_ptr() if js_all.numel() else None,
                                       jk_all.numel(), C.byref(ne)))
@@ -612,7 +611,6 @@ class Engine:
             init_all, plo_all, phi_all = _gather_var(lists, [c_[:3] for c_ in ca], r, G, group)
             if plo_all.numel() != phi_all.numel():
                 raise SpbError(-4, f"internal: {plo_all.numel()} piece starts, {phi_all.numel()} piece ends over the ranks")
-            sync()
             again = C.c_int()
             self._ck(L.spb_mg_slice_contract(h, init_all.data_ptr() if init_all.numel() else None, init_all.numel(),
                                              plo_all.data_ptr() if plo_all.numel() else None, phi_all.data_ptr() if phi_all.numel() else None,
@@ -631,7 +629,6 @@ class Engine:
         n_seq = len(self._keep[1]) - 1
         has01 = _wrap(h01.value, 2 * n_seq, torch.uint8, cuda, self.device).clone()
         dist.all_reduce(has01, op=dist.ReduceOp.MAX, group=group)
-        sync()
         self._ck(L.spb_mg_slice_finish(h, op_all.data_ptr() if op_all.numel() else None, op_all.numel(), mp_all.data_ptr() if mp_all.numel() else None,
                                        mp_all.numel(), has01.data_ptr(), C.byref(self.counts)))
         mark("slice_origins_components")

@@ -1938,7 +1938,7 @@ int spb_mg_slice_ids(spb_ctx* c, uint32_t rank, uint32_t n_ranks) {
   const u32 nTall = (c->nV + 7) / 8;
   sl.t_lo = sl.pos_lo >= c->T ? nTall : (sl.v_lo >> 5) << 2; sl.t_hi = sl.pos_hi >= c->T ? nTall : (sl.v_hi >> 5) << 2;     // cut below multiples of 32 ids
   sl.on = true;
-  return check_err(c, "spb_mg_slice_ids");
+  return SPB_OK;                                       // (error flags are read once per step, by spb_mg_slice_graph / spb_mg_slice_finish: no host sync here)
 }
 
 int spb_mg_slice_junctions(spb_ctx* c, uint64_t* n, void** jk_dev, void** js_dev) {
@@ -1951,7 +1951,7 @@ int spb_mg_slice_junctions(spb_ctx* c, uint64_t* n, void** jk_dev, void** js_dev
   PRIM(graph_junctions(c, w_lo, w_hi, &Jk, &Js, &nj));
   c->Jk = Jk; c->Js = Js;                              // kept until spb_mg_slice_graph replaces them by the complete list
   *n = nj; *jk_dev = Jk; *js_dev = Js;
-  return check_err(c, "spb_mg_slice_junctions");
+  return SPB_OK;                                       // (error flags are read once per step, by spb_mg_slice_graph / spb_mg_slice_finish: no host sync here)
 }
 
 int spb_mg_slice_graph(spb_ctx* c, const uint64_t* jk_all, const uint8_t* js_all, uint64_t n_all, uint64_t* n_edges_local) {
@@ -1980,7 +1980,7 @@ int spb_mg_slice_classify(spb_ctx* c, uint32_t* n_init, uint32_t* n_start, uint3
   PRIM(cp_classify(c, &c->init_list, &c->plo, &c->phi, nI, nP));      // local lists, replaced by the complete ones in spb_mg_slice_contract
   *n_init = nI[0]; *n_start = nP[0]; *n_end = nP[1];
   *init_dev = c->init_list; *plo_dev = c->plo; *phi_dev = c->phi;
-  return check_err(c, "spb_mg_slice_classify");
+  return SPB_OK;                                       // (error flags are read once per step, by spb_mg_slice_graph / spb_mg_slice_finish: no host sync here)
 }
 
 int spb_mg_slice_contract(spb_ctx* c, const uint32_t* init_all, uint32_t n_init, const uint32_t* plo_all, const uint32_t* phi_all, uint32_t n_piece,
@@ -1996,7 +1996,7 @@ int spb_mg_slice_contract(spb_ctx* c, const uint32_t* init_all, uint32_t n_init,
   c->cnt.n_edges = n_edges_total;
   SPB_LAUNCH(k_mark_inits, nblk(n_init, TPB), TPB, c->stream, c->init_list, n_init, c->vflags);       // the init bit is read at arbitrary vertices
   PRIM(cp_contract(c, pass, again));
-  return check_err(c, "spb_mg_slice_contract");
+  return SPB_OK;                                       // (error flags are read once per step, by spb_mg_slice_graph / spb_mg_slice_finish: no host sync here)
 }
 
 int spb_mg_slice_emit(spb_ctx* c, uint64_t* n_op, void** op_dev, uint64_t* n_mp, void** mp_dev, void** has01_dev) {
@@ -2012,7 +2012,7 @@ int spb_mg_slice_emit(spb_ctx* c, uint64_t* n_op, void** op_dev, uint64_t* n_mp,
   PRIM(ensure_edges(c));
   *n_op = c->n_op; *n_mp = c->n_mp;
   *op_dev = c->op; *mp_dev = c->mp; *has01_dev = c->has01;
-  return check_err(c, "spb_mg_slice_emit");
+  return SPB_OK;                                       // (error flags are read once per step, by spb_mg_slice_graph / spb_mg_slice_finish: no host sync here)
 }
 
 int spb_mg_slice_finish(spb_ctx* c, const uint64_t* op_all, uint64_t n_op, const uint64_t* mp_all, uint64_t n_mp, const uint8_t* has01_any, spb_counts* out) {
