@@ -420,6 +420,11 @@ def main():
                         note="achieved = bytes this kernel must move by design (DESIGN.md section 3) / its live CUDA-event duration; "
                              "traffic = dram__bytes_read+write of the same kernel from the committed ncu capture (profiles/)",
                         kernels_ms={k_[:-3]: v for k_, v in sorted(kt.items(), key=lambda x: -x[1])})
+        if roof is not None and world > 1 and getattr(eng, "mg_exchange_bytes", None) and st_mean.get("mg_exchange_records_ms"):
+            # the one bulk collective of the step: all-to-all of the 8-byte records (+ orientation bitmap all-gather), per rank and direction
+            xb, xms = float(eng.mg_exchange_bytes), st_mean["mg_exchange_records_ms"]
+            roof["nvlink"] = dict(bytes_per_rank=int(xb), ms=xms, achieved=xb / (xms / 1e3) / 1e9, peak=900.0, unit="GB/s per GPU and direction",
+                                  frac=xb / (xms / 1e3) / 1e9 / 900.0, peak_source="NVLink 5 nominal (18 links x 50 GB/s per direction)")
         pipe_bytes = algorithmic_bytes(ni, nv, nbb)
         pipe_ach = pipe_bytes / (ms / args.steps / 1e3) / 1e9
         if roof is not None:

@@ -526,6 +526,9 @@ class Engine:
         rrecs, rcnts = torch.empty_like(recs), torch.empty_like(cnts)
         dist.all_to_all_single(rcnts, cnts, group=group)
         dist.all_to_all_single(rrecs, recs, group=group)
+        # bytes this rank sends over NVLink in the record exchange (fixed-capacity regions: padding included) + the orientation
+        # bitmap parts it receives: what `mg_exchange_records_ms` moves
+        self.mg_exchange_bytes = (recs.numel() * 8 + cnts.numel() * 4) * (G - 1) // G + (G - 1) * (S // 8)
         fb, ob, sp = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._ck(self.lib.spb_mg_buffers(self.h, C.byref(fb), C.byref(ob), C.byref(sp)))
         _all_gather_inplace(_wrap(ob.value, G * S // 32, torch.int32, cuda, self.device), r, G, group)   # the owners verify repeats exactly

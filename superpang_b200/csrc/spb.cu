@@ -1058,7 +1058,9 @@ static int dedup_global_table(spb_ctx* c, bool allow_switch) {
   if (const char* e = getenv("SPB_SWITCH_MIN")) switch_min = strtoull(e, nullptr, 10);                        // tests: small inputs switch too
   if (allow_switch && c->n_inst >= switch_min && !getenv("SPB_ANCHOR") && c->npos_pad > CH) {
     u64 n_ext = 0, n_dup = 0, chunk_n = 1;
-    PRIM(probe_sample_chunks(c, std::max<u64>(CH / 2, 256), &n_ext, &n_dup, &chunk_n));
+    u64 CHp = 256;                                     // sample chunks: a power of two, at most CH / 2 positions and 1/64 of the input
+    while (2 * CHp <= CH / 2 && 2 * CHp <= c->n_inst / 64) CHp *= 2;
+    PRIM(probe_sample_chunks(c, CHp, &n_ext, &n_dup, &chunk_n));
     decided = (double)n_ext >= 0.25 * (double)chunk_n ? 2 : -1;
     // partitioned dedup only pays when almost nothing is duplicated (every duplicate costs it a scattered write)
     if (decided < 0 && (double)n_dup < 0.02 * (double)chunk_n) return 1;
