@@ -335,6 +335,14 @@ def main():
     sampler.join(timeout=2)
 
     # per-step times: max over ranks of every step, then mean / median / min over the steps
+    # hash partition balance: k-mer instances owned per rank (max / mean over the ranks)
+    balance = None
+    if world > 1 and getattr(eng, "mg_owned_records", None) is not None:
+        ow = torch.zeros(world, dtype=torch.float64, device=dev)
+        ow[rank] = float(eng.mg_owned_records.item())
+        dist.all_reduce(ow)
+        balance = dict(owned_instances_max=int(ow.max().item()), owned_instances_mean=float(ow.mean().item()),
+                       max_over_mean=float((ow.max() / ow.mean()).item()))
     tt = torch.tensor([times, e2e_times], device=dev, dtype=torch.float64)
     d2h = torch.tensor([float(e2e_last[1])], device=dev, dtype=torch.float64)
     if world > 1:
@@ -450,6 +458,7 @@ def main():
             digest_equals_single_gpu=(dg_single == dg) if dg_single is not None else None,
             clocks=sampler.summary(),
             k_sweep=k_sweep,
+            balance=balance,
         )
         if not args.no_cpu_baseline:
             ref = CpuReference(args.workload, args.mode, args.ref_inst)

@@ -529,6 +529,7 @@ class Engine:
         # bytes this rank sends over NVLink in the record exchange (fixed-capacity regions: padding included) + the orientation
         # bitmap parts it receives: what `mg_exchange_records_ms` moves
         self.mg_exchange_bytes = (recs.numel() * 8 + cnts.numel() * 4) * (G - 1) // G + (G - 1) * (S // 8)
+        self.mg_owned_records = rcnts.sum()             # k-mer instances this rank owns (device scalar: read after the timed region)
         fb, ob, sp = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._ck(self.lib.spb_mg_buffers(self.h, C.byref(fb), C.byref(ob), C.byref(sp)))
         _all_gather_inplace(_wrap(ob.value, G * S // 32, torch.int32, cuda, self.device), r, G, group)   # the owners verify repeats exactly
