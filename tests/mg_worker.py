@@ -65,10 +65,21 @@ def main():
         A = Assembler(dict(map(tuple, c["records"])), c["k"], engine=_capi.Engine(lib=lib), distributed=True)
         if os.environ.get("SPB_EXPECT_SLICED") == "1":
             assert getattr(A._eng, "mg_sliced", False), f"case went through {A._eng.mg_protocol}, not the sliced tail"
+        shared = None
+        if getattr(A._eng, "mg_sliced", False):
+            # every rank copies the sequences of ITS NBPs to their place in one host buffer in POSIX shared memory (the e2e
+            # path of bench.py at N > 1); compared with the complete result below
+            shared = _capi.SharedHostBuffer(int(A._eng.counts.nbp_bases), tag=f"t{len(out)}")
+            A._eng.shard_to_host("nbp_seqs", shared.tensor)
+            dist.barrier()
         sliced = gather_shards(A._eng, dist) if getattr(A._eng, "mg_sliced", False) else None
         res = A.to_result()                      # (sliced tail: the first accessor recomputes everything on this rank)
         if sliced is not None:
             check_shards(A, sliced)
+            import numpy as np
+            n = int(A._eng.counts.nbp_bases)
+            assert np.array_equal(shared.tensor.numpy()[:n], A._eng.nbp_seqs()[1]), "shared host buffer differs from the complete NBP sequences"
+            shared.close()
         out.append(digests.summarize(res))
     if rank == 0 or True:
         json.dump(out, open(f"{out_path}.{rank}", "w"))
