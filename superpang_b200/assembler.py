@@ -214,6 +214,16 @@ class Assembler:
                 out[name] = {tup[int(i)] for i in mine}
         return out
 
+    def nbp_successors(self):
+        """{vertex tuple of a raw NBP: tuple of the vertex tuples of its successors} -- NBP2 follows NBP1 when the last k bases
+        of NBP1 are the first k bases of NBP2, the edge rule of the reference's NBP graph (`lib/Assembler.py:365-384`);
+        NBPs without successors are left out.  From `spb_get_nbp_graph` (a k-base string is a (vertex, orientation) pair there)."""
+        self.compact()
+        voff, verts, _, _ = self._eng.nbps()
+        off, succ, _rev = self._eng.nbp_graph()
+        tup = [tuple(verts[int(voff[i]):int(voff[i + 1])].tolist()) for i in range(len(voff) - 1)]
+        return {tup[i]: tuple(tup[int(j)] for j in succ[int(off[i]):int(off[i + 1])]) for i in range(len(tup)) if off[i + 1] > off[i]}
+
     def reconstruct_sequences(self, paths):
         """`reconstruct_sequence` (`lib/Assembler.py:1038-1118`) for a list of vertex paths (e.g. joined NBPs)."""
         return self._eng.path_sequences(paths, self.ksize)

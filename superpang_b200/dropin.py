@@ -14,7 +14,8 @@ re-implemented here but taken from the INSTALLED reference package at run time (
     INTEGRATION.md asks a maintainer to make in the source; here it is applied in memory;
   * `get_seqPaths_NBPs` (`lib/Assembler.py:1121-1139`, SURVEY 8f row 1: the quadratic sequence x NBP substring
     test of the forward-strand selection) is answered from the per-sequence NBP sets computed on the device
-    (`spb_get_seq_nbps`).
+    (`spb_get_seq_nbps`), and the NBP graph of every component (`:365-384`: successors by equality of the last / first k
+    bases) is built from the successor lists of `spb_get_nbp_graph` instead of 2 x #NBPs k-base string keys.
 
 `main()` runs the reference's CLI (`scripts/SuperPang.py`) with this class bound at its call site and the native FASTA
 writer (`spb_write_fasta`) bound in place of `lib/utils.py:write_fasta`, so `-k`, `-t`,
@@ -39,8 +40,12 @@ def reference_class():
     return Ref
 
 
-def patched_run(Ref):
-    """The reference's `run()` with the per-component NBP-collection block replaced (see the module docstring)."""
+def patched_run(Ref, nbp_graph=False):
+    """The reference's `run()` with the per-component NBP-collection block replaced (see the module docstring).
+    nbp_graph=True also replaces the construction of the NBP graph (`lib/Assembler.py:365-384`: every NBP's first / last k
+    bases as dict keys, successors by string equality) by the successor lists computed on the device (`spb_get_nbp_graph`,
+    SURVEY 8f row 1).  The groups are rebuilt as Python sets with the SAME members inserted in the SAME order as the
+    reference's `start2NBPs`, so that the edge order of the graph -- and with it everything downstream -- is unchanged."""
     import superpang.lib.Assembler as mod
     lines = textwrap.dedent(inspect.getsource(Ref.run)).split("\n")
     start = next(i for i, l in enumerate(lines) if "### Reconstruct non-branching paths" in l)
@@ -48,8 +53,25 @@ def patched_run(Ref):
     indent = lines[start][:len(lines[start]) - len(lines[start].lstrip())]
     patch = [indent + "_c = self._b200_components[ic]",
              indent + "NBPs = list(_c.NBPs); NBP2seq = dict(_c.NBP2seq); isCycle = _c.isCycle"]
+    tail = lines[end + 1:]
+    if nbp_graph:
+        g0 = next(i for i, l in enumerate(tail) if "# Collect prefixes-suffixes for locating potential overlaps" in l)
+        g1 = next(i for i, l in enumerate(tail) if l.strip() == "# Build graph of non-branching paths")
+        gi = tail[g0][:len(tail[g0]) - len(tail[g0].lstrip())]
+        gpatch = [gi + l for l in (
+            "# successors from the device: sEnd / sStart hold the key of a start group (its smallest member) instead of a string",
+            "start2NBPs = defaultdict(set); sStart = {}; sEnd = {}; _gid = {}",
+            "for NBP in NBPs:",
+            "    _S = self._b200_nbp_succ.get(NBP, ())",
+            "    sEnd[NBP] = min(_S) if _S else None",
+            "    for _N2 in _S: _gid[_N2] = sEnd[NBP]",
+            "for NBP in NBPs:",
+            "    sStart[NBP] = _gid.get(NBP)",
+            "    if sStart[NBP] is not None: start2NBPs[sStart[NBP]].add(NBP)",
+            "")]
+        tail = tail[:g0] + gpatch + tail[g1:]
     ns = dict(vars(mod))
-    exec(compile("\n".join(lines[:start] + patch + lines[end + 1:]), "<superpang run() with the B200 NBP collection>", "exec"), ns)
+    exec(compile("\n".join(lines[:start] + patch + tail), "<superpang run() with the B200 NBP collection>", "exec"), ns)
     return ns["run"]
 
 
@@ -68,7 +90,7 @@ def run(b200, minlen, mincov, bubble_identity_threshold, genome_assignment_thres
     Ref = reference_class()
     from graph_tool.all import Graph
     A = object.__new__(Ref)
-    A.run = types.MethodType(patched_run(Ref), A)
+    A.run = types.MethodType(patched_run(Ref, nbp_graph=device_rows), A)
     A.ksize, A.seqDict, A.ref2name, A.includedSeqs = b200.ksize, b200.seqDict, b200.ref2name, b200.includedSeqs
     A.vertex2coords = b200.vertex2coords
     A.seqPaths = dict(b200.seqPaths)
@@ -82,6 +104,7 @@ def run(b200, minlen, mincov, bubble_identity_threshold, genome_assignment_thres
     if device_rows:
         _ROW1.update(sets=b200.seq_paths_nbps(), ref_class=Ref)
         A.get_seqPaths_NBPs = _seq_paths_nbps_from_device
+        A._b200_nbp_succ = b200.nbp_successors()            # NBP graph (lib/Assembler.py:365-384) from spb_get_nbp_graph
     try:
         return A.run(minlen, mincov, bubble_identity_threshold, genome_assignment_threshold, max_threads, debug)
     finally:
