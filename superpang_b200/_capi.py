@@ -304,13 +304,31 @@ class SharedHostBuffer:
         rank = dist.get_rank(group)
         self.nbytes = max(int(nbytes), 1)
         self.path = f"/dev/shm/spb_{os.environ.get('MASTER_PORT', '0')}_{os.getuid()}_{tag}"
+        # rank 0 checks that the shared-memory file system has room (a tmpfs lets the file grow past its limit and faults on
+        # the first write instead); without it every rank falls back to a private page-locked buffer (`shared` = False:
+        # the parts are then on the host, but not in one process)
+        ok = [True]
+        if rank == 0:
+            try:
+                st = os.statvfs("/dev/shm")
+                ok[0] = st.f_bavail * st.f_frsize > self.nbytes + (64 << 20)
+            except OSError:
+                ok[0] = False
+        dist.broadcast_object_list(ok, src=0, group=group)
+        self.shared = bool(ok[0])
+        self.registered = False
+        if not self.shared:
+            self.mm = None
+            self.tensor = torch.empty(self.nbytes, dtype=torch.uint8)
+            if torch.cuda.is_available():
+                self.tensor = self.tensor.pin_memory()
+            return
         if rank == 0:
             with open(self.path, "wb") as f:
                 f.truncate(self.nbytes)
         dist.barrier(group)
         self.mm = np.memmap(self.path, dtype=np.uint8, mode="r+", shape=(self.nbytes,))
         self.tensor = torch.from_numpy(self.mm)
-        self.registered = False
         if torch.cuda.is_available():
             rc = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), self.nbytes, 0)
             self.registered = int(rc) == 0

@@ -78,7 +78,8 @@ def main():
             check_shards(A, sliced)
             import numpy as np
             n = int(A._eng.counts.nbp_bases)
-            assert np.array_equal(shared.tensor.numpy()[:n], A._eng.nbp_seqs()[1]), "shared host buffer differs from the complete NBP sequences"
+            if shared.shared:
+                assert np.array_equal(shared.tensor.numpy()[:n], A._eng.nbp_seqs()[1]), "shared host buffer differs from the complete NBP sequences"
             shared.close()
         out.append(digests.summarize(res))
     if rank == 0 or True:
