@@ -179,13 +179,19 @@ class Assembler:
         soff, seqs = self._eng.nbp_seqs()
         ooff, oidx = self._eng.nbp_origins()
         short = [n.split("_Nsplit_")[0] for n in self.ref2name]           # lib/Assembler.py:946
-        sbytes = seqs.tobytes()
+        # one bulk conversion each instead of one numpy call per NBP (the containers themselves -- a tuple of vertex ids and
+        # a str per NBP -- are what the reference's host tail works on and cannot be avoided here)
+        vl, sbytes = verts.tolist(), seqs.tobytes()
+        vo, so, oo, ol = voff.tolist(), soff.tolist(), ooff.tolist(), oidx.tolist()
+        cl, cy = comp.tolist(), cyc.tolist()
+        names_of = {}                                                     # origin-index lists repeat a lot: name tuples are cached
         out = []
-        for i in range(len(comp)):
-            v = tuple(verts[int(voff[i]):int(voff[i + 1])].tolist())
-            s = sbytes[int(soff[i]):int(soff[i + 1])].decode()
-            o = tuple(sorted({short[j] for j in oidx[int(ooff[i]):int(ooff[i + 1])]}))
-            out.append((v, s, o, int(comp[i]), bool(cyc[i])))
+        for i in range(len(cl)):
+            key = tuple(ol[oo[i]:oo[i + 1]])
+            o = names_of.get(key)
+            if o is None:
+                o = names_of[key] = tuple(sorted({short[j] for j in key}))
+            out.append((tuple(vl[vo[i]:vo[i + 1]]), sbytes[so[i]:so[i + 1]].decode(), o, cl[i], bool(cy[i])))
         return out
 
     def nbp_orientation_counts(self):
