@@ -15,7 +15,8 @@ re-implemented here but taken from the INSTALLED reference package at run time (
   * `get_seqPaths_NBPs` (`lib/Assembler.py:1121-1139`, SURVEY 8f row 1: the quadratic sequence x NBP substring
     test of the forward-strand selection) is answered from the per-sequence NBP sets computed on the device
     (`spb_get_seq_nbps`), and the NBP graph of every component (`:365-384`: successors by equality of the last / first k
-    bases) is built from the successor lists of `spb_get_nbp_graph` instead of 2 x #NBPs k-base string keys.
+    bases) is built from the successor lists of `spb_get_nbp_graph` instead of 2 x #NBPs k-base string keys, and the
+    sequences of the joined paths (`:826`, row 2) come from `spb_path_sequences`.
 
 `main()` runs the reference's CLI (`scripts/SuperPang.py`) with this class bound at its call site and the native FASTA
 writer (`spb_write_fasta`) bound in place of `lib/utils.py:write_fasta`, so `-k`, `-t`,
@@ -70,6 +71,12 @@ def patched_run(Ref, nbp_graph=False):
             "    if sStart[NBP] is not None: start2NBPs[sStart[NBP]].add(NBP)",
             "")]
         tail = tail[:g0] + gpatch + tail[g1:]
+        # joined paths (`lib/Assembler.py:826`): their sequences come from `spb_path_sequences` on the device
+        # instead of `reconstruct_sequence` in a fork pool
+        old_call = "self.multimap(self.reconstruct_sequence, threads, newPaths, self.vertex2coords, self.ref2name, self.seqDict, self.ksize)"
+        hits = [i for i, l in enumerate(tail) if old_call in l]
+        assert len(hits) == 1, "the reference's run() changed: joined-path reconstruction not found"
+        tail[hits[0]] = tail[hits[0]].replace(old_call, "self._b200_reconstruct(newPaths)")
     ns = dict(vars(mod))
     exec(compile("\n".join(lines[:start] + patch + tail), "<superpang run() with the B200 NBP collection>", "exec"), ns)
     return ns["run"]
@@ -105,6 +112,11 @@ def run(b200, minlen, mincov, bubble_identity_threshold, genome_assignment_thres
         _ROW1.update(sets=b200.seq_paths_nbps(), ref_class=Ref)
         A.get_seqPaths_NBPs = _seq_paths_nbps_from_device
         A._b200_nbp_succ = b200.nbp_successors()            # NBP graph (lib/Assembler.py:365-384) from spb_get_nbp_graph
+
+        def _reconstruct(paths):
+            _ROW1["joined"] = _ROW1.get("joined", 0) + len(paths)
+            return b200.reconstruct_sequences([list(p) for p in paths]) if paths else []
+        A._b200_reconstruct = _reconstruct
     try:
         return A.run(minlen, mincov, bubble_identity_threshold, genome_assignment_threshold, max_threads, debug)
     finally:

@@ -29,8 +29,12 @@ def test_reference_tail_on_b200_head(emu_lib, case, tmp_path):
     assert dropin.canonical(ref) == dropin.canonical(got)
     assert dropin.contigs_digest(ref) == dropin.contigs_digest(got)
     # SURVEY 8(f) row 1 wired in as well: get_seqPaths_NBPs answered from the device-side per-sequence NBP sets
+    from superpang_b200 import dropin as product
+    product._ROW1["joined"] = 0
     got = dropin.run_dropin_full(fa, k, _capi.Engine(lib=emu_lib), device_rows=True)
     assert dropin.canonical(ref) == dropin.canonical(got)
+    if name == "inverted_repeat":                   # the one crafted case whose tail joins NBPs (bubble popping is off here):
+        assert product._ROW1["joined"] >= 1         # their sequences came from spb_path_sequences
 
 
 def test_reference_tail_on_b200_head_synthetic(emu_lib, tmp_path):
