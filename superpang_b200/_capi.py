@@ -380,6 +380,7 @@ class Engine:
         seq_off: uint64[n_seq + 1] (host)."""
         seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
         self._keep = (ascii_buf, seq_off)
+        self._k = int(k)
         self.mg_sliced = False
         self._ck(self.lib.spb_load(self.h, _ptr(ascii_buf), seq_off.ctypes.data, len(seq_off) - 1, int(k)))
 
@@ -450,6 +451,8 @@ class Engine:
                 flag[0] = 1 if dr.value < 0.02 else 0
             dist.broadcast(flag, src=0, group=group)
             protocol = "part" if int(flag.item()) else "reps"
+        if protocol == "owned" and int(self._k) < 17:
+            protocol = "links"                          # the rolling-hash kernels of that protocol need k >= 17
         self.mg_protocol = protocol
         mark("probe")
         if protocol == "part":
@@ -602,6 +605,13 @@ class Engine:
         self._ck(self.lib.spb_mg_apply_links(self.h, lback.data_ptr() if lback.numel() else None, lback.numel(), lo, max(lo, hi)))
         return self._mg_finish(group, G, r, S, lo, hi, cuda, marks, mark, sync, gather_orientation=False)
 
+    def _raise_code(self, code, local_rc):
+        """Raise what status `code` (the worst over all ranks) stands for; the local message if this rank saw it itself."""
+        if code == 0:
+            return
+        msg = self.lib.spb_last_error(self.h).decode(errors="replace") if local_rc == code else "reported by another rank of the group"
+        raise (DegenerateInputError if code == -3 else SpbError)(code, msg)
+
     def _mg_sliced_tail(self, group, G, r, cuda, dev, marks, mark, sync):
         """Graph build + compaction sliced over the ranks (include/superpang_b200.h, "sliced multi-GPU tail"): per-position
         passes on the own slice, per-vertex passes on the own vertices, emission of the own NBP range; only the short lists
@@ -618,16 +628,21 @@ class Engine:
         jk_t = _wrap(jk.value, n.value, torch.int64, cuda, self.device)
         js_t = _wrap(js.value, n.value, torch.uint8, cuda, self.device)
         jk_all, js_all = _gather_var([jk_t, js_t], [[c_[0], c_[0]] for c_ in ca], r, G, group)
+        # The error flags are rank-local here (a rank only sees the degenerate repeats of ITS positions and vertices), so a status
+        # is never raised before every rank knows it: it travels with the next gather of counts / one final reduction, and all
+        # ranks raise together instead of leaving the others waiting in a collective.
         ne = C.c_uint64()
-        self._ck(L.spb_mg_slice_graph(h, jk_all.data_ptr() if jk_all.numel() else None, js_all.data_ptr() if js_all.numel() else None,
-                                      jk_all.numel(), C.byref(ne)))
+        rc_graph = L.spb_mg_slice_graph(h, jk_all.data_ptr() if jk_all.numel() else None, js_all.data_ptr() if js_all.numel() else None,
+                                        jk_all.numel(), C.byref(ne))
         del jk_all, js_all
         mark("slice_graph")
         for p_ in range(2):
             ni, ns, nend = C.c_uint32(), C.c_uint32(), C.c_uint32()
             il, pl, ph = C.c_void_p(), C.c_void_p(), C.c_void_p()
-            self._ck(L.spb_mg_slice_classify(h, C.byref(ni), C.byref(ns), C.byref(nend), C.byref(il), C.byref(pl), C.byref(ph)))
-            ca = _counts_all([ni.value, ns.value, nend.value, ne.value], G, dev, group)
+            rc_cls = 0 if rc_graph else L.spb_mg_slice_classify(h, C.byref(ni), C.byref(ns), C.byref(nend), C.byref(il), C.byref(pl), C.byref(ph))
+            local_rc = rc_graph or rc_cls
+            ca = _counts_all([ni.value, ns.value, nend.value, ne.value, -local_rc], G, dev, group)
+            self._raise_code(-max(c_[4] for c_ in ca), local_rc)
             lists = [_wrap(il.value, ni.value, torch.int32, cuda, self.device), _wrap(pl.value, ns.value, torch.int32, cuda, self.device),
                      _wrap(ph.value, nend.value, torch.int32, cuda, self.device)]
             init_all, plo_all, phi_all = _gather_var(lists, [c_[:3] for c_ in ca], r, G, group)
@@ -651,8 +666,11 @@ class Engine:
         n_seq = len(self._keep[1]) - 1
         has01 = _wrap(h01.value, 2 * n_seq, torch.uint8, cuda, self.device).clone()
         dist.all_reduce(has01, op=dist.ReduceOp.MAX, group=group)
-        self._ck(L.spb_mg_slice_finish(h, op_all.data_ptr() if op_all.numel() else None, op_all.numel(), mp_all.data_ptr() if mp_all.numel() else None,
-                                       mp_all.numel(), has01.data_ptr(), C.byref(self.counts)))
+        rc_fin = L.spb_mg_slice_finish(h, op_all.data_ptr() if op_all.numel() else None, op_all.numel(), mp_all.data_ptr() if mp_all.numel() else None,
+                                       mp_all.numel(), has01.data_ptr(), C.byref(self.counts))
+        worst = torch.tensor([-rc_fin], dtype=torch.int64, device=dev)
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=group)
+        self._raise_code(-int(worst.item()), rc_fin)
         mark("slice_origins_components")
         self.mg_sliced = True
         if cuda:

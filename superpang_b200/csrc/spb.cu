@@ -566,7 +566,7 @@ static int dd_records(spb_ctx* c, u64 pos_lo, u64 pos_hi, u32 bb, u64 min_positi
   u64 *keys, *keys2; u32 *pos, *pos2;
   ALLOC(keys, u64, n); ALLOC(pos, u32, n);
   u64 grid = n / TPB;
-  if (!getenv("SPB_NO_ROLL")) {
+  if (!getenv("SPB_NO_ROLL") && c->k >= 17) {        // (the rolling kernels keep 16-base windows of both strand ends: k >= 16)
     const RollK K = roll_constants(c->k);
     { const int tq_ = t_begin(c); SPB_LAUNCH(k_make_records_roll, nblk(n / SPB_RUN, 128), 128, c->stream, c->F, c->R, c->vbits, c->T, c->k, pos_lo, pos_hi, n, keys, pos, c->obits,
                spread, K, 0u, 0u, (u64*)nullptr, 0ull); t_end(c, tq_, "k_make_records_roll_ms"); }
@@ -913,6 +913,7 @@ static void launch_roll_partition(spb_ctx* c, u64 pos_lo, u64 pos_hi, u32 run, u
 // sort-based path.
 static int dedup_part_links(spb_ctx* c) {
   const u64 T = c->T;
+  if (c->k < 17) return 1;                           // the rolling kernels keep 16-base windows of both strand ends: other paths for tiny k
   int r0 = alloc_position_state(c); if (r0) return r0;
   const u64 P = c->npos_pad;
   u64 avg = SPB_D_AVG;
@@ -1322,6 +1323,7 @@ int spb_mg_owned_links(spb_ctx* c, uint32_t rank, uint32_t n_owners, uint64_t* s
   if (!c) return SPB_EINVAL;
   if (c->state != 1) return fail(c, SPB_ESTATE, "spb_mg_owned_links needs a loaded input");
   if (!pow2(n_owners) || n_owners < 2 || rank >= n_owners) return fail(c, SPB_EINVAL, "n_owners must be a power of two >= 2, rank < n_owners");
+  if (c->k < 17) return fail(c, SPB_EINVAL, "the owner-computes protocol needs k >= 17 (rolling hashes over 16-base windows): use the record protocols");
   SPB_ON_DEVICE(c);
   uint64_t slice = 0; spb_mg_slice(c, n_owners, &slice);
   int r0 = alloc_position_state(c, slice * n_owners); if (r0) return r0;
@@ -1436,7 +1438,7 @@ int spb_mg_part_records(spb_ctx* c, uint64_t pos_lo, uint64_t pos_hi, uint32_t n
   SPB_ON_DEVICE(c);
   PartGeom g;
   *overflow = 0;
-  if (part_geometry(c, n_owners, &g)) { *overflow = 1; return SPB_OK; }
+  if (c->k < 17 || part_geometry(c, n_owners, &g)) { *overflow = 1; return SPB_OK; }      // tiny k: the caller falls back to the record protocols
   uint64_t slice = 0; spb_mg_slice(c, n_owners, &slice);
   int r0 = alloc_position_state(c, slice * n_owners); if (r0) return r0;
   if (pos_hi > c->T) pos_hi = c->T;

@@ -62,6 +62,14 @@ def main():
     case = json.load(open(case_path))
     out = []
     for c in case:
+        if c.get("degenerate"):
+            # orientation-ambiguous input: EVERY rank must refuse it (no rank may be left waiting in a collective)
+            try:
+                Assembler(dict(map(tuple, c["records"])), c["k"], engine=_capi.Engine(lib=lib), distributed=True).compact()
+                out.append("accepted")
+            except _capi.DegenerateInputError:
+                out.append("degenerate")
+            continue
         A = Assembler(dict(map(tuple, c["records"])), c["k"], engine=_capi.Engine(lib=lib), distributed=True)
         if os.environ.get("SPB_EXPECT_SLICED") == "1":
             assert getattr(A._eng, "mg_sliced", False), f"case went through {A._eng.mg_protocol}, not the sliced tail"

@@ -107,6 +107,32 @@ def test_emu_large_k_matches_oracle(emu_lib, monkeypatch, k, env):
     digests.assert_same(want, run_emu(emu_lib, sd, k).to_result())
 
 
+@pytest.mark.parametrize("k", [3, 9, 15, 17, 19])
+@pytest.mark.parametrize("env", [{}, {"SPB_DEDUP": "part", "SPB_PART_AVG": "100"}, {"SPB_DEDUP": "smem", "SPB_SMEM_AVG": "100"},
+                                 {"SPB_DEDUP": "links", "SPB_BUCKET_BITS": "3"}, {"SPB_DEDUP": "staged", "SPB_BUCKET_BITS": "3"}],
+                         ids=lambda e: ",".join(f"{k_[4:].lower()}={v}" for k_, v in e.items()) or "default")
+def test_emu_tiny_k_matches_oracle(emu_lib, monkeypatch, k, env):
+    """k below and just above the 16-base windows of the rolling-hash kernels: those paths must hand tiny k over to the
+    kernels that hash all limbs (k < 17) instead of reading in front of the k-mer, and agree with the oracle either way."""
+    for key, v in env.items():
+        monkeypatch.setenv(key, v)
+    rng = np.random.default_rng(100 + k)
+    anc = rng.integers(0, 4, 3000)
+    sd = {}
+    for g in range(3):
+        x = anc.copy()
+        m = rng.random(x.size) < 0.03
+        x[m] = (x[m] + rng.integers(1, 4, int(m.sum()))) & 3
+        sd[f"g{g}|c"] = "".join("ACGT"[v] for v in x)
+    try:
+        want = dbg_oracle.run_oracle(sd, k)
+    except AssertionError:                              # orientation-ambiguous at this k: the new path must refuse as well
+        with pytest.raises(_capi.DegenerateInputError):
+            run_emu(emu_lib, sd, k).to_result()
+        return
+    digests.assert_same(want, run_emu(emu_lib, sd, k).to_result())
+
+
 def test_rejects_bad_input(emu_lib):
     with pytest.raises(_capi.SpbError):
         run_emu(emu_lib, {"a": "ACGT" * 20}, 30)           # even k

@@ -99,3 +99,35 @@ def test_sliced_tail_random_pangenomes(emu_lib, tmp_path):
     for r in range(world):
         got = json.load(open(f"{out}.{r}"))
         assert got == want
+
+
+@pytest.mark.parametrize("world,env", [
+    (2, {"SPB_MG_PROTOCOL": "part", "SPB_PART_AVG": "60", "SPB_MG_ALL_LINKS": "2"}),          # sliced tail: the error flags are rank-local
+    (4, {"SPB_MG_PROTOCOL": "part", "SPB_PART_AVG": "30", "SPB_MG_ALL_LINKS": "2"}),
+    (2, {"SPB_MG_PROTOCOL": "owned"}),                                                       # replicated tail
+], ids=lambda x: str(x) if isinstance(x, int) else ",".join(f"{k[4:].lower()}={v}" for k, v in x.items()))
+def test_degenerate_input_is_refused_by_every_rank(emu_lib, tmp_path, world, env):
+    """Orientation-ambiguous inputs (the reference asserts on them, `lib/Assembler.py:1088`, `:1104`) in between good ones:
+    every rank raises DegenerateInputError for them -- also when only one rank's slice holds the offending positions -- and the
+    ranks stay in step for the cases that follow."""
+    crafted = helpers.load_crafted()
+    deg = [c for c in crafted if c.get("degenerate")]
+    good = [c for c in crafted if not c.get("degenerate") and c["k"] == 31][:2]
+    assert deg
+    cases = [dict(records=good[0]["records"], k=good[0]["k"])]
+    for c in deg:
+        cases.append(dict(records=c["records"], k=c["k"], degenerate=True))
+    cases.append(dict(records=good[1]["records"], k=good[1]["k"]))
+    case_path = os.path.join(tmp_path, "cases.json")
+    json.dump(cases, open(case_path, "w"))
+    out = os.path.join(tmp_path, "out.json")
+    port = _free_port()
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "mg_worker.py"), str(r), str(world), port, case_path, out],
+                              env=dict(os.environ, **env)) for r in range(world)]
+    for p in procs:
+        assert p.wait(timeout=600) == 0
+    for r in range(world):
+        got = json.load(open(f"{out}.{r}"))
+        assert got[1:1 + len(deg)] == ["degenerate"] * len(deg), got[1:1 + len(deg)]
+        helpers.assert_summary(got[0], good[0]["summary"])
+        helpers.assert_summary(got[-1], good[1]["summary"])
