@@ -133,6 +133,45 @@ def test_emu_tiny_k_matches_oracle(emu_lib, monkeypatch, k, env):
     digests.assert_same(want, run_emu(emu_lib, sd, k).to_result())
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_emu_optimistic_links_fuzz(emu_lib, monkeypatch, seed):
+    """Optimistic links + verification + repair against the oracle on random genome sets (SNPs, reverse-complemented and
+    rotated copies), with random subsets of the stored hash bits masked away (so that distinct k-mers collide and links
+    fail), random bucket sizes and thread orders."""
+    import random
+    rnd = random.Random(seed)
+    checked = 0
+    for _ in range(14):
+        k = rnd.choice([17, 21, 31, 33, 45])
+        n, L, p = rnd.randint(2, 5), rnd.randint(200, 2000), rnd.choice([0.0, 0.01, 0.03, 0.1])
+        rng = np.random.default_rng(rnd.randint(0, 1 << 30))
+        anc = rng.integers(0, 4, L)
+        sd = {}
+        for g in range(n):
+            x = anc.copy()
+            m = rng.random(L) < p
+            x[m] = (x[m] + rng.integers(1, 4, int(m.sum()))) & 3
+            if rnd.random() < 0.3:
+                x = (3 - x)[::-1]
+            if rnd.random() < 0.3:
+                a = rnd.randint(0, L - 50)
+                x = np.concatenate([x[a:], x[:a]])
+            sd[f"g{g}"] = "".join("ACGT"[v] for v in x)
+        for key, v in dict(SPB_DEDUP="part", SPB_PART_AVG=str(rnd.choice([20, 60, 300])),
+                           SPB_D_HMASK=rnd.choice(["FFFFFFFF", "FFF00000", "FF000000", "FFFF0000", "F8000000"]),
+                           SPB_EMU_ORDER=rnd.choice(["", "reverse", "shuffle"])).items():
+            monkeypatch.setenv(key, v)
+        try:
+            want = dbg_oracle.run_oracle(sd, k)
+        except AssertionError:
+            with pytest.raises(_capi.DegenerateInputError):
+                run_emu(emu_lib, sd, k).to_result()
+            continue
+        digests.assert_same(want, run_emu(emu_lib, sd, k).to_result())
+        checked += 1
+    assert checked >= 10
+
+
 def test_rejects_bad_input(emu_lib):
     with pytest.raises(_capi.SpbError):
         run_emu(emu_lib, {"a": "ACGT" * 20}, 30)           # even k
